@@ -1,0 +1,172 @@
+/*
+ * infgen_b200.h - C ABI of the B200-native (sm_100a) closed-loop decode engine.
+ *
+ * This library replaces ONE path of OrangeSodahub/InfGen: `InfGenAgentDecoder.inference`
+ * (reference infgen/modules/agent_decoder.py:1605-2389) and the operators under it
+ * (reference infgen/modules/layers.py:16-215).  The reference is pure Python/PyTorch and has no FFI of its
+ * own; the binding a maintainer adds is the ctypes stub shown in INTEGRATION.md (the shipped one is
+ * infgen_b200/_capi.py).  Every entry point below cites the reference interface it stands in for.
+ *
+ * Conventions
+ *   - plain C, no torch types.  All pointers are caller-owned; `loc` says where they live
+ *     (INFGEN_HOST: pageable or pinned host memory, INFGEN_DEVICE: device memory of the engine's GPU).
+ *   - every function returns 0 on success and a negative `infgen_status` otherwise; the text of the last
+ *     failure (per thread) is available from infgen_last_error().
+ *   - an engine is not thread-safe; all device work is enqueued on the engine's stream
+ *     (infgen_set_stream to share the caller's stream, e.g. torch.cuda.current_stream().cuda_stream).
+ *   - rows: agents of all scenes of a batch live in one row space, scene b owning rows
+ *     [b*row_capacity, b*row_capacity + n_rows[b]).  Columns are the reference's 2 Hz token columns.
+ */
+#ifndef INFGEN_B200_H
+#define INFGEN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define INFGEN_ABI_VERSION 3
+
+typedef enum {
+    INFGEN_OK = 0,
+    INFGEN_ERR_INVALID_ARG = -1,
+    INFGEN_ERR_CAPACITY = -2,
+    INFGEN_ERR_CUDA = -3,
+    INFGEN_ERR_STATE = -4,
+    INFGEN_ERR_NO_DEVICE = -5
+} infgen_status;
+
+typedef enum { INFGEN_HOST = 0, INFGEN_DEVICE = 1 } infgen_loc;
+
+typedef struct infgen_engine infgen_engine;
+
+/* Run-time knobs of `InfGenAgentDecoder.__init__` (agent_decoder.py:100-314) that reach the decode loop. */
+typedef struct {
+    int32_t abi_version;          /* must be INFGEN_ABI_VERSION */
+    int32_t device;               /* CUDA device ordinal */
+    int32_t num_layers;           /* 6   num_agent_layers */
+    int32_t hist_cols;            /* 2   (num_historical_steps-1)//shift, agent_decoder.py:1636 */
+    int32_t window;               /* 12  time_span/shift, agent_decoder.py:586-587 */
+    int32_t shift;                /* 5 */
+    int32_t num_historical_steps; /* 11 */
+    int32_t token_size;           /* 2048 */
+    int32_t grid_size;            /* 1961 cells of Attr_Tokenizer, attr_tokenizer.py:24-43 */
+    int32_t num_seed_feature;     /* 10: rows at the tail of a scene that get no temporal edges, :553-556 */
+    int32_t max_pl2a_neighbors;   /* 5   agent_decoder.py:711 */
+    int32_t max_a2a_neighbors;    /* 300 agent_decoder.py:633 */
+    float pl2a_radius;            /* 30 */
+    float a2a_radius;             /* 60 */
+    int32_t use_state_token;      /* agent_decoder.py:2170-2171 */
+    int32_t disable_insertion;    /* agent_decoder.py:2172-2173: every predicted state forced to 'valid' */
+    int32_t motion_beam_size;     /* top-k of the motion-token sampler, 1 = greedy (agent_decoder.py:300, 2163) */
+    uint32_t seed;                /* sampler seed (counter-based; see DESIGN.md "sampler") */
+    int32_t use_cuda_graph;       /* replay one captured decode iteration per step */
+    int32_t trace;                /* keep per-iteration head inputs / logits / layer outputs for parity tests */
+} infgen_config;
+
+/* One batch of scenes, already filtered/padded as agent_decoder.py:1609-1657 does (host side: infgen_b200/host.py). */
+typedef struct {
+    int32_t n_scenes;
+    int32_t row_capacity;         /* rows reserved per scene (>= max n_rows; multiple of 4) */
+    int32_t n_cols;               /* T = num_infer_step, agent_decoder.py:1637 */
+    int32_t n_iters;              /* S = num_recurrent_steps_val // shift, agent_decoder.py:1741 */
+    const int32_t *n_rows;        /* [n_scenes] agents valid at the current column */
+    const int32_t *ego_row;       /* [n_scenes] row (within the scene) of the ego agent, agent_decoder.py:1648-1650 */
+    const int32_t *scene_id;      /* [n_scenes] sampler stream id of each scene */
+    /* per row, [n_scenes*row_capacity, ...]; only rows < n_rows[scene] are read */
+    const float *pos_hist;        /* [R][hist_cols][2]  token_pos   */
+    const float *head_hist;       /* [R][hist_cols]     token_heading */
+    const int32_t *state_hist;    /* [R][hist_cols]     state_idx   */
+    const int32_t *token_hist;    /* [R][hist_cols]     token_idx (-1 none, -2 BOS) */
+    const int32_t *grid_hist;     /* [R][hist_cols]     grid_token_idx (-1 invalid) */
+    const uint8_t *tsrc_hist;     /* [R][hist_cols]     column usable as temporal source (temporal_mask & col>=bos) */
+    const uint8_t *interact_hist; /* [R][hist_cols]     interact_mask, agent_decoder.py:1707-1719 */
+    const int32_t *type;          /* [R] 0 veh 1 ped 2 cyc */
+    const float *shape;           /* [R][3] shape at the current step */
+    /* map tokens of all scenes, concatenated; scene b owns [pt_ptr[b], pt_ptr[b+1]) */
+    const int32_t *pt_ptr;        /* [n_scenes+1] */
+    const float *pt_pos;          /* [P][2] */
+    const float *pt_ori;          /* [P]    */
+    const float *x_pt;            /* [P][128] map encoder output, agent_decoder.py:2143 */
+} infgen_scene_batch;
+
+/* Result buffers of one batch (any pointer may be NULL = not wanted). Layout [R = n_scenes*row_capacity][...]. */
+typedef struct {
+    float *pos;                   /* [R][T][2]   pos_a   */
+    float *head;                  /* [R][T]      head_a  */
+    float *pred_traj;             /* [R][5*S][2] generated part of pred_traj (agent_decoder.py:2201-2204) */
+    float *pred_head;             /* [R][5*S]    */
+    float *pred_state;            /* [R][5*S]    */
+    int32_t *next_token;          /* [R][T]      history columns then one sampled token per iteration */
+    int32_t *next_state;          /* [R][T]      */
+    float *hist_traj;             /* [R][hist_cols*5][2] raw steps 1..10 rebuilt from history tokens (:2311-2335) */
+    float *hist_head;             /* [R][hist_cols*5] */
+} infgen_outputs;
+
+/* ---- library ------------------------------------------------------------------------------------------- */
+int32_t infgen_abi_version(void);
+const char *infgen_last_error(void);
+
+/* ---- weights: replaces nn.Module.load_state_dict for the decoder (names: infgen_b200/weights.py) ---------- */
+/* The library owns the packed layout; the host packs `state_dict()` tensors into one float blob by asking for
+ * the offset/shape of each packed tensor by name. */
+int32_t infgen_weight_count(void);
+const char *infgen_weight_name(int32_t i);
+int64_t infgen_weight_offset(const char *name);   /* in floats, -1 if unknown */
+int64_t infgen_weight_numel(const char *name);
+int64_t infgen_weight_blob_floats(void);
+
+/* ---- engine life cycle ---------------------------------------------------------------------------------- */
+/* InfGenAgentDecoder.__init__ + load_state_dict (agent_decoder.py:100-314).
+ * weights: packed blob (host).  grid_cells: [grid_size][2] Attr_Tokenizer.grid (attr_tokenizer.py:24-43, host).
+ * vocab: [3][token_size][6][4][2] motion-token box tracks veh/ped/cyc (preprocess.py:302-311, host). */
+int32_t infgen_create(const infgen_config *cfg, const float *weights, int64_t n_floats, const float *grid_cells,
+                      const float *vocab, infgen_engine **out);
+int32_t infgen_destroy(infgen_engine *e);
+int32_t infgen_set_stream(infgen_engine *e, void *cuda_stream);   /* NULL = engine-owned stream */
+int32_t infgen_set_sampler(infgen_engine *e, int32_t motion_beam_size, uint32_t seed);
+int32_t infgen_synchronize(infgen_engine *e);
+
+/* ---- the decode path: InfGenAgentDecoder.inference (agent_decoder.py:1605-2389) ------------------------------ */
+/* setup (:1609-1719): upload one batch, build per-scene caches (map K/V of the six pt2a layers, embeddings). */
+int32_t infgen_load_scenes(infgen_engine *e, const infgen_scene_batch *batch, int32_t loc);
+/* teacher forcing for parity tests: [R][S] tokens / states applied instead of the sampled ones (NULL = off). */
+int32_t infgen_set_forcing(infgen_engine *e, const int32_t *tokens, const int32_t *states, int32_t loc);
+/* history columns through the layer stack (what iteration 0 of the reference computes for column 0, :2149-2150) */
+int32_t infgen_prefill(infgen_engine *e);
+/* n decode iterations of the loop at :1740-2301 (edges, 6x{temporal, map, agent} attention, heads, sampling,
+ * token->pose advance, next-column embedding).  Asynchronous on the engine stream. */
+int32_t infgen_step(infgen_engine *e, int32_t n_iters);
+/* prefill + all remaining iterations */
+int32_t infgen_rollout(infgen_engine *e);
+/* outputs (:2303-2389). Synchronises the stream when loc == INFGEN_HOST. */
+int32_t infgen_read(infgen_engine *e, const infgen_outputs *out, int32_t loc);
+int32_t infgen_iterations_done(infgen_engine *e);
+/* number of kernels this library launched (or replayed through graphs) since the engine was created */
+int64_t infgen_kernel_launches(infgen_engine *e);
+
+/* ---- parity/debug taps (tests only): copy a named internal buffer to host; returns bytes written or <0 ------- */
+int64_t infgen_debug_read(infgen_engine *e, const char *name, void *dst, int64_t max_bytes);
+
+/* ---- operator level: the reference's layers.py modules, for unit parity ------------------------------------- */
+/* AttentionLayer.forward((x_src, x_dst), r, edge_index) (layers.py:61-113).  `layer` is the state_dict prefix,
+ * e.g. "a2a_attn_layers.3".  Edges are grouped by destination: edges of node i are
+ * [edge_ptr[i], edge_ptr[i+1]) with source ids edge_src[] (PyG edge_index[0]); r is [E][128] (pre-LayerNorm).
+ * x_src == NULL means the non-bipartite form (x_src = x_dst). All pointers host. */
+int32_t infgen_op_attention_layer(infgen_engine *e, const char *layer, const float *x_src, int32_t n_src,
+                                  const float *x_dst, int32_t n_dst, const float *r, const int32_t *edge_ptr,
+                                  const int32_t *edge_src, float *out);
+/* FourierEmbedding.forward(continuous_inputs, [categorical sum]) (layers.py:142-160); name e.g. "r_t_emb". */
+int32_t infgen_op_fourier_embedding(infgen_engine *e, const char *name, const float *x, int32_t n, int32_t dim,
+                                    const float *cat, float *out);
+/* MLPEmbedding.forward (layers.py:189); name e.g. "fusion_emb". */
+int32_t infgen_op_mlp_embedding(infgen_engine *e, const char *name, const float *x, int32_t n, int32_t dim,
+                                float *out);
+/* MLPLayer.forward (layers.py:213-215); name "token_predict_head" | "state_predict_head". */
+int32_t infgen_op_mlp_layer(infgen_engine *e, const char *name, const float *x, int32_t n, float *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INFGEN_B200_H */

@@ -1,0 +1,193 @@
+"""`B200AgentDecoder`: drop-in for the reference `InfGenAgentDecoder.inference` (infgen/modules/agent_decoder.py:1605).
+
+    dec = B200AgentDecoder.from_state_dict(agent_encoder.state_dict(), cfg)
+    out = dec.inference(data, map_enc)            # same arguments, same output dict as the reference method
+
+or, to leave `run.py` / `val.py` untouched, `install(model.encoder.agent_encoder)` swaps the bound method.
+The decode loop runs in libinfgen_b200.so (hand-written sm_100a CUDA); this module only does the per-scene host
+setup the reference also does outside its loop and has no CPU fallback.
+"""
+import ctypes as C
+import types
+from typing import Dict, List, Optional, Sequence
+import numpy as np
+import torch
+
+from . import _capi
+from .config import DecoderConfig, HIDDEN, NUM_LAYERS, TOKEN_SIZE
+from .grid import PositionGrid
+from .host import HostBatch, SceneHost, assemble_outputs, prepare_scene
+from .weights import pack_state_dict
+
+
+class B200AgentDecoder:
+    def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: Optional[DecoderConfig] = None, device: int = 0,
+                 use_cuda_graph: bool = True, trace: bool = False, seed: int = 2024,
+                 vocab: Optional[Dict[str, torch.Tensor]] = None):
+        self.cfg = cfg or DecoderConfig()
+        self.lib = _capi.load()
+        self.device = device
+        self.trace = trace
+        sd = {k[len('encoder.agent_encoder.'):] if k.startswith('encoder.agent_encoder.') else k: v
+              for k, v in state_dict.items()}
+        blob = pack_state_dict(sd, self.lib)
+        grid = PositionGrid(self.cfg.grid_range, self.cfg.grid_interval, self.cfg.pl2seed_radius,
+                            self.cfg.angle_interval)
+        self.grid = grid
+        if vocab is None:
+            from .synth import load_vocab
+            vocab = load_vocab()
+        self._vocab_key = tuple(int(vocab[k].data_ptr()) for k in ('veh', 'ped', 'cyc'))
+        vocab_arr = np.ascontiguousarray(
+            torch.stack([vocab['veh'], vocab['ped'], vocab['cyc']]).float().cpu().numpy())
+        assert vocab_arr.shape == (3, TOKEN_SIZE, 6, 4, 2)
+        cells = np.ascontiguousarray(grid.cells.numpy().astype(np.float32))
+        c = _capi.Config(
+            abi_version=_capi.ABI_VERSION, device=device, num_layers=NUM_LAYERS, hist_cols=self.cfg.hist_cols,
+            window=self.cfg.window, shift=self.cfg.shift, num_historical_steps=self.cfg.num_historical_steps,
+            token_size=TOKEN_SIZE, grid_size=grid.grid_size, num_seed_feature=self.cfg.num_seed_feature,
+            max_pl2a_neighbors=self.cfg.max_pl2a_neighbors, max_a2a_neighbors=self.cfg.max_a2a_neighbors,
+            pl2a_radius=self.cfg.pl2a_radius, a2a_radius=self.cfg.a2a_radius,
+            use_state_token=int(self.cfg.use_state_token), disable_insertion=int(self.cfg.disable_insertion),
+            motion_beam_size=self.cfg.motion_beam_size, seed=seed, use_cuda_graph=int(use_cuda_graph),
+            trace=int(trace))
+        h = C.c_void_p()
+        _capi.check(self.lib.infgen_create(C.byref(c), _capi.f32p(blob), blob.size, _capi.f32p(cells),
+                                           _capi.f32p(vocab_arr), C.byref(h)))
+        self._h = h
+        self._batch: Optional[HostBatch] = None
+        self._scenes: Optional[Sequence[SceneHost]] = None
+
+    # ---- construction helpers ---------------------------------------------------------------------------------
+    @classmethod
+    def from_state_dict(cls, state_dict, cfg=None, **kw):
+        return cls(state_dict, cfg, **kw)
+
+    @classmethod
+    def from_reference(cls, agent_encoder, cfg=None, **kw):
+        """Build from a live reference `InfGenAgentDecoder` module (weights stay owned by the module)."""
+        return cls(agent_encoder.state_dict(), cfg, **kw)
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self.lib.infgen_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- low level ------------------------------------------------------------------------------------------------
+    def set_sampler(self, motion_beam_size: int, seed: int):
+        _capi.check(self.lib.infgen_set_sampler(self._h, motion_beam_size, seed))
+
+    def load(self, batch: HostBatch, scenes: Optional[Sequence[SceneHost]] = None):
+        b = batch
+        sb = _capi.SceneBatch(
+            n_scenes=b.n_scenes, row_capacity=b.cap, n_cols=b.T, n_iters=b.S,
+            n_rows=_capi.i32p(b.n_rows), ego_row=_capi.i32p(b.ego_row), scene_id=_capi.i32p(b.scene_id),
+            pos_hist=_capi.f32p(b.pos_hist), head_hist=_capi.f32p(b.head_hist), state_hist=_capi.i32p(b.state_hist),
+            token_hist=_capi.i32p(b.token_hist), grid_hist=_capi.i32p(b.grid_hist), tsrc_hist=_capi.u8p(b.tsrc_hist),
+            interact_hist=_capi.u8p(b.interact_hist), type=_capi.i32p(b.type), shape=_capi.f32p(b.shape),
+            pt_ptr=_capi.i32p(b.pt_ptr), pt_pos=_capi.f32p(b.pt_pos), pt_ori=_capi.f32p(b.pt_ori),
+            x_pt=_capi.f32p(b.x_pt))
+        _capi.check(self.lib.infgen_load_scenes(self._h, C.byref(sb), _capi.HOST))
+        self._batch, self._scenes = batch, scenes
+
+    def set_forcing(self, tokens: Optional[torch.Tensor], states: Optional[torch.Tensor]):
+        """[R, S] int32 teacher-forcing overrides in the batch row space (None = off)."""
+        tk = tokens.to(torch.int32).contiguous() if tokens is not None else None
+        st = states.to(torch.int32).contiguous() if states is not None else None
+        _capi.check(self.lib.infgen_set_forcing(self._h, _capi.i32p(tk), _capi.i32p(st), _capi.HOST))
+        _capi.check(self.lib.infgen_synchronize(self._h))
+
+    def prefill(self):
+        _capi.check(self.lib.infgen_prefill(self._h))
+
+    def step(self, n: int = 1):
+        _capi.check(self.lib.infgen_step(self._h, n))
+
+    def rollout(self):
+        _capi.check(self.lib.infgen_rollout(self._h))
+
+    def synchronize(self):
+        _capi.check(self.lib.infgen_synchronize(self._h))
+
+    def read(self):
+        b = self._batch
+        o = _capi.Outputs(
+            pos=_capi.f32p(b.out_pos), head=_capi.f32p(b.out_head), pred_traj=_capi.f32p(b.out_pred_traj),
+            pred_head=_capi.f32p(b.out_pred_head), pred_state=_capi.f32p(b.out_pred_state),
+            next_token=_capi.i32p(b.out_next_token), next_state=_capi.i32p(b.out_next_state),
+            hist_traj=_capi.f32p(b.out_hist_traj), hist_head=_capi.f32p(b.out_hist_head))
+        _capi.check(self.lib.infgen_read(self._h, C.byref(o), _capi.HOST))
+
+    def kernel_launches(self) -> int:
+        return int(self.lib.infgen_kernel_launches(self._h))
+
+    def debug_read(self, name: str, shape, dtype=np.float32) -> np.ndarray:
+        arr = np.zeros(shape, dtype=dtype)
+        n = self.lib.infgen_debug_read(self._h, name.encode(), arr.ctypes.data, arr.nbytes)
+        if n < 0:
+            _capi.check(int(n))
+        if n < arr.nbytes:
+            raise RuntimeError(f'debug buffer {name!r} holds {n} bytes, {arr.nbytes} requested')
+        return arr
+
+    def trace_arrays(self) -> Dict[str, np.ndarray]:
+        """Per-iteration taps (trace=True): head_in [S,R,128], token_logits [S,R,2048], state_logits [S,R,3],
+        layer_out [S,6,R,128] in the batch row space."""
+        b = self._batch
+        return {
+            'head_in': self.debug_read('trace_head_in', (b.S, b.R, HIDDEN)),
+            'token_logits': self.debug_read('trace_token_logits', (b.S, b.R, TOKEN_SIZE)),
+            'state_logits': self.debug_read('trace_state_logits', (b.S, b.R, 3)),
+            'layer_out': self.debug_read('trace_layer_out', (b.S, 6, b.R, HIDDEN)),
+        }
+
+    # ---- the reference call boundary ----------------------------------------------------------------------------
+    def inference_batch(self, datas: Sequence[Dict], map_encs: Sequence[Dict],
+                        scene_ids: Optional[Sequence[int]] = None, motion_only: bool = False) -> List[Dict]:
+        """Closed-loop rollout of several independent scenes in one launch sequence (a capability the reference
+        lacks: its inference is batch-size-1, agent_decoder.py:1631; the oracle is one reference call per scene)."""
+        if not self.cfg.disable_insertion and not motion_only:
+            raise NotImplementedError('the agent-insertion stage (agent_decoder.py:1773-2114) is not built yet: '
+                                      'construct with disable_insertion=True or pass motion_only=True')
+        self._check_vocab(datas[0])
+        scenes = [prepare_scene(d, m, self.cfg) for d, m in zip(datas, map_encs)]
+        batch = HostBatch(scenes, self.cfg, scene_ids)
+        self.load(batch, scenes)
+        self.rollout()
+        self.read()
+        return assemble_outputs(batch, scenes, self.cfg)
+
+    def inference(self, data: Dict, map_enc: Dict, motion_only: bool = False) -> Dict:
+        """`InfGenAgentDecoder.inference(data, map_enc)` (agent_decoder.py:1605-2389)."""
+        return self.inference_batch([data], [map_enc], motion_only=motion_only)[0]
+
+    def _check_vocab(self, data):
+        ag = data['agent']
+        if 'trajectory_token_veh' in ag:
+            key = tuple(int(ag[f'trajectory_token_{k}'].data_ptr()) for k in ('veh', 'ped', 'cyc'))
+            if key != self._vocab_key:
+                from .synth import load_vocab
+                v = load_vocab()
+                same = all(torch.equal(ag[f'trajectory_token_{k}'].cpu().float(), v[k]) for k in ('veh', 'ped', 'cyc'))
+                if not same:
+                    raise ValueError('scene uses a different motion-token vocabulary than the engine was built with')
+                self._vocab_key = key
+
+
+def install(agent_encoder, cfg: Optional[DecoderConfig] = None, **kw) -> B200AgentDecoder:
+    """Replace `agent_encoder.inference` (reference InfGenAgentDecoder) by the B200 path, in place."""
+    dec = B200AgentDecoder.from_reference(agent_encoder, cfg, **kw)
+
+    def _inference(self, data, map_enc):
+        out = dec.inference(data, map_enc)
+        dev = map_enc['x_pt'].device
+        return {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in out.items()}
+    agent_encoder.inference = types.MethodType(_inference, agent_encoder)
+    agent_encoder._b200 = dec
+    return dec

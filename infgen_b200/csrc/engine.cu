@@ -1,0 +1,988 @@
+// Host side of libinfgen_b200.so: weight layout registry, engine state, launch sequences, CUDA-graph replay, C ABI.
+// See include/infgen_b200.h for the contract of every exported function.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <unordered_map>
+#include <algorithm>
+
+#include "../../include/infgen_b200.h"
+#include "common.cuh"
+#include "ops.cuh"
+#include "decode.cuh"
+
+using namespace infgen;
+
+// ---------------------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CK(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t _e = (call);                                                                              \
+        if (_e != cudaSuccess)                                                                                \
+            return fail(INFGEN_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,                 \
+                        cudaGetErrorString(_e));                                                              \
+    } while (0)
+#define CKL()                                                                                                 \
+    do {                                                                                                      \
+        cudaError_t _e = cudaGetLastError();                                                                  \
+        if (_e != cudaSuccess)                                                                                \
+            return fail(INFGEN_ERR_CUDA, "kernel launch failed at %s:%d: %s", __FILE__, __LINE__,             \
+                        cudaGetErrorString(_e));                                                              \
+    } while (0)
+#define RET(call)                                                                                             \
+    do {                                                                                                      \
+        int _r = (call);                                                                                      \
+        if (_r != 0) return _r;                                                                               \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------
+// packed weight layout (single source of truth; the host packs by name, see infgen_b200/weights.py)
+// ---------------------------------------------------------------------------------------------------------------
+struct WEntry { std::string name; int64_t numel, offset; };
+static std::vector<WEntry> g_layout;
+static std::unordered_map<std::string, int> g_index;
+static int64_t g_total = 0;
+
+static void w_add(const std::string &name, int64_t numel) {
+    WEntry e{name, numel, g_total};
+    g_index[name] = (int)g_layout.size();
+    g_layout.push_back(e);
+    g_total += (numel + 31) / 32 * 32;
+}
+static int64_t gemm_numel(int k, int n) { return (int64_t)((k + 3) / 4) * n * 4; }
+static void w_ln(const std::string &p) { w_add(p + ".g", 128); w_add(p + ".b", 128); }
+static void w_attn(const std::string &p, bool has_pos) {
+    w_ln(p + ".ln_src"); w_ln(p + ".ln_dst");
+    w_add(p + ".w_qs", gemm_numel(128, 256)); w_add(p + ".b_qs", 256);
+    w_add(p + ".w_kv", gemm_numel(128, 256)); w_add(p + ".b_kv", 256);
+    if (has_pos) {
+        w_add(p + ".w_kr", 128 * 128); w_ln(p + ".ln_r");
+        w_add(p + ".w_vr", gemm_numel(128, 128)); w_add(p + ".b_vr", 128);
+    }
+    w_add(p + ".w_g", gemm_numel(256, 128)); w_add(p + ".b_g", 128);
+    w_add(p + ".w_out", gemm_numel(128, 128)); w_add(p + ".b_out", 128);
+    w_ln(p + ".ln_post"); w_ln(p + ".ln_ffpre");
+    w_add(p + ".w_ff1", gemm_numel(128, 512)); w_add(p + ".b_ff1", 512);
+    w_add(p + ".w_ff2", gemm_numel(512, 128)); w_add(p + ".b_ff2", 128);
+    w_ln(p + ".ln_ffpost");
+}
+static void w_fourier(const std::string &p, int d) {
+    w_add(p + ".freqs", d * 64);
+    for (int i = 0; i < d; ++i) {
+        std::string q = p + ".mlps." + std::to_string(i);
+        w_add(q + ".w0", gemm_numel(129, 128)); w_add(q + ".b0", 128); w_ln(q + ".ln");
+        w_add(q + ".w3", gemm_numel(128, 128)); w_add(q + ".b3", 128);
+    }
+    w_ln(p + ".out_ln"); w_add(p + ".w_out", gemm_numel(128, 128)); w_add(p + ".b_out", 128);
+}
+static void w_mlp_emb(const std::string &p, int kin) {
+    w_add(p + ".w0", gemm_numel(kin, 128)); w_add(p + ".b0", 128); w_ln(p + ".ln1");
+    w_add(p + ".w3", gemm_numel(128, 128)); w_add(p + ".b3", 128); w_ln(p + ".ln4");
+    w_add(p + ".w6", gemm_numel(128, 128)); w_add(p + ".b6", 128);
+}
+static int pad128(int n) { return (n + 127) / 128 * 128; }
+static void w_head(const std::string &p, int kin, int nout) {
+    w_add(p + ".w0", gemm_numel(kin, 128)); w_add(p + ".b0", 128); w_ln(p + ".ln");
+    w_add(p + ".w3", gemm_numel(128, pad128(nout))); w_add(p + ".b3", pad128(nout));
+}
+static const int GRID_SIZE = 1961, ANGLE_SIZE = 120, TOKEN_SIZE = 2048;
+static void build_layout() {
+    if (!g_layout.empty()) return;
+    w_add("type_a_emb", 4 * 128); w_add("state_a_emb", 4 * 128);
+    w_add("no_token_emb", 128); w_add("bos_token_emb", 128); w_add("invalid_offset_token_emb", 128);
+    w_mlp_emb("shape_emb", 3);
+    w_fourier("x_a_emb", 2); w_fourier("r_t_emb", 4); w_fourier("r_pt2a_emb", 3); w_fourier("r_a2a_emb", 3);
+    w_fourier("r_pt2sa_emb", 3); w_fourier("r_a2sa_emb", 3);
+    w_mlp_emb("token_emb_veh", 8); w_mlp_emb("token_emb_ped", 8); w_mlp_emb("token_emb_cyc", 8);
+    w_mlp_emb("token_emb_grid", 2); w_mlp_emb("fusion_emb", 512);
+    const char *stacks6[] = {"t_attn_layers", "pt2a_attn_layers", "a2a_attn_layers"};
+    for (auto s : stacks6)
+        for (int i = 0; i < 6; ++i) w_attn(std::string(s) + "." + std::to_string(i), true);
+    for (int i = 0; i < 3; ++i) w_attn("pt2sa_attn_layers." + std::to_string(i), true);
+    for (int i = 0; i < 3; ++i) w_attn("a2sa_attn_layers." + std::to_string(i), true);
+    for (int i = 0; i < 3; ++i) w_attn("occ2sa_attn_layers." + std::to_string(i), false);
+    w_head("token_predict_head", 128, TOKEN_SIZE); w_head("state_predict_head", 128, 3);
+    w_head("seed_state_predict_head", 128, 2); w_head("seed_type_predict_head", 128, 3);
+    w_head("seed_shape_predict_head", 128, 3); w_head("seed_pos_rel_token_predict_head", 128, GRID_SIZE);
+    w_head("seed_offset_xy_predict_head", 128, 2); w_head("seed_agent_occ_embed", GRID_SIZE, 128);
+    w_head("seed_heading_rel_token_predict_head", 128, ANGLE_SIZE);
+    w_head("grid_agent_occ_head", 128, GRID_SIZE); w_head("grid_pt_occ_head", 128, GRID_SIZE);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// engine
+// ---------------------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+struct infgen_engine {
+    infgen_config cfg;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    float *blob = nullptr;
+    float *grid_cells = nullptr, *vocab = nullptr;
+    float *tok_tab = nullptr, *grid_tab = nullptr;      // [3][V+2][128], [G+1][128]
+    AttnW t[6], m[6], a[6];
+    FourierW f_t, f_m, f_a, f_x;
+    MlpEmbW e_shape, e_fusion, e_tok[3], e_grid;
+    MlpHeadW h_tok, h_state;
+    const float *type_emb = nullptr, *state_emb = nullptr;
+    // scene batch
+    bool loaded = false;
+    int n_scenes = 0, cap = 0, T = 0, S = 0, R = 0, P = 0, n_rows_sum = 0, max_rows = 0;
+    int iters_done = 0, prefilled = 0;
+    std::unordered_map<std::string, DevBuf> bufs;       // named device buffers (debug-readable)
+    DecState st;
+    int row_tile = 4;
+    int *d_err = nullptr;
+    // forcing
+    bool forcing = false;
+    // graph
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    size_t graph_nodes = 0;
+    int64_t launches = 0;
+    bool capturing = false;
+};
+
+static const float *W(infgen_engine *e, const std::string &name) {
+    auto it = g_index.find(name);
+    if (it == g_index.end()) {
+        fprintf(stderr, "infgen_b200: unknown packed weight '%s'\n", name.c_str());
+        abort();
+    }
+    return e->blob + g_layout[it->second].offset;
+}
+static AttnW make_attn(infgen_engine *e, const std::string &p, bool has_pos) {
+    AttnW w;
+    memset(&w, 0, sizeof(w));
+    w.ln_src_g = W(e, p + ".ln_src.g"); w.ln_src_b = W(e, p + ".ln_src.b");
+    w.ln_dst_g = W(e, p + ".ln_dst.g"); w.ln_dst_b = W(e, p + ".ln_dst.b");
+    w.w_qs = W(e, p + ".w_qs"); w.b_qs = W(e, p + ".b_qs"); w.w_kv = W(e, p + ".w_kv"); w.b_kv = W(e, p + ".b_kv");
+    if (has_pos) {
+        w.w_kr = W(e, p + ".w_kr"); w.ln_r_g = W(e, p + ".ln_r.g"); w.ln_r_b = W(e, p + ".ln_r.b");
+        w.w_vr = W(e, p + ".w_vr"); w.b_vr = W(e, p + ".b_vr");
+    }
+    w.w_g = W(e, p + ".w_g"); w.b_g = W(e, p + ".b_g"); w.w_out = W(e, p + ".w_out"); w.b_out = W(e, p + ".b_out");
+    w.ln_post_g = W(e, p + ".ln_post.g"); w.ln_post_b = W(e, p + ".ln_post.b");
+    w.ln_ffpre_g = W(e, p + ".ln_ffpre.g"); w.ln_ffpre_b = W(e, p + ".ln_ffpre.b");
+    w.w_ff1 = W(e, p + ".w_ff1"); w.b_ff1 = W(e, p + ".b_ff1"); w.w_ff2 = W(e, p + ".w_ff2"); w.b_ff2 = W(e, p + ".b_ff2");
+    w.ln_ffpost_g = W(e, p + ".ln_ffpost.g"); w.ln_ffpost_b = W(e, p + ".ln_ffpost.b");
+    w.has_pos = has_pos ? 1 : 0;
+    return w;
+}
+static FourierW make_fourier(infgen_engine *e, const std::string &p, int d) {
+    FourierW w;
+    memset(&w, 0, sizeof(w));
+    w.freqs = W(e, p + ".freqs");
+    for (int i = 0; i < d; ++i) {
+        std::string q = p + ".mlps." + std::to_string(i);
+        w.w0[i] = W(e, q + ".w0"); w.b0[i] = W(e, q + ".b0"); w.ln_g[i] = W(e, q + ".ln.g"); w.ln_b[i] = W(e, q + ".ln.b");
+        w.w3[i] = W(e, q + ".w3"); w.b3[i] = W(e, q + ".b3");
+    }
+    w.out_ln_g = W(e, p + ".out_ln.g"); w.out_ln_b = W(e, p + ".out_ln.b");
+    w.w_out = W(e, p + ".w_out"); w.b_out = W(e, p + ".b_out");
+    return w;
+}
+static MlpEmbW make_mlp_emb(infgen_engine *e, const std::string &p) {
+    MlpEmbW w;
+    w.w0 = W(e, p + ".w0"); w.b0 = W(e, p + ".b0"); w.ln1_g = W(e, p + ".ln1.g"); w.ln1_b = W(e, p + ".ln1.b");
+    w.w3 = W(e, p + ".w3"); w.b3 = W(e, p + ".b3"); w.ln4_g = W(e, p + ".ln4.g"); w.ln4_b = W(e, p + ".ln4.b");
+    w.w6 = W(e, p + ".w6"); w.b6 = W(e, p + ".b6");
+    return w;
+}
+static MlpHeadW make_head(infgen_engine *e, const std::string &p, int kin, int nout) {
+    MlpHeadW w;
+    w.w0 = W(e, p + ".w0"); w.b0 = W(e, p + ".b0"); w.ln_g = W(e, p + ".ln.g"); w.ln_b = W(e, p + ".ln.b");
+    w.w3 = W(e, p + ".w3"); w.b3 = W(e, p + ".b3");
+    w.k4_in = (kin + 3) / 4; w.n_out = nout; w.n_pad = pad128(nout);
+    return w;
+}
+
+static int ensure(infgen_engine *e, const char *name, size_t bytes, void **out) {
+    DevBuf &b = e->bufs[name];
+    if (b.bytes < bytes) {
+        if (b.p) CK(cudaFree(b.p));
+        b.p = nullptr; b.bytes = 0;
+        size_t alloc = (bytes + 255) / 256 * 256;
+        CK(cudaMalloc(&b.p, alloc));
+        CK(cudaMemsetAsync(b.p, 0, alloc, e->stream));
+        b.bytes = alloc;
+        if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+        if (e->graph) { cudaGraphDestroy(e->graph); e->graph = nullptr; }
+    }
+    *out = b.p;
+    return 0;
+}
+template <typename Tp>
+static int ensure_t(infgen_engine *e, const char *name, size_t count, Tp **out) {
+    void *p = nullptr;
+    RET(ensure(e, name, count * sizeof(Tp), &p));
+    *out = (Tp *)p;
+    return 0;
+}
+static float *fbuf(infgen_engine *e, const char *name) { return (float *)e->bufs[name].p; }
+
+static inline void count_launch(infgen_engine *e) { if (!e->capturing) e->launches++; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------------------------------------------
+static int launch_node(infgen_engine *e, const NodeArgs &a, int n_rows_space) {
+    if (e->row_tile == 16) {
+        k_node_update<16><<<(n_rows_space + 15) / 16, NT, NodeSmem<16>::BYTES, e->stream>>>(a);
+    } else {
+        k_node_update<4><<<(n_rows_space + 3) / 4, NT, NodeSmem<4>::BYTES, e->stream>>>(a);
+    }
+    CKL();
+    count_launch(e);
+    return 0;
+}
+static int launch_attn(infgen_engine *e, const AttnArgs &a) {
+    size_t smem = (size_t)NWARP * a.max_deg * 8 * sizeof(float);
+    k_edge_attn<<<(a.rows.n_total + NWARP - 1) / NWARP, NT, smem, e->stream>>>(a);
+    CKL();
+    count_launch(e);
+    return 0;
+}
+static int launch_fourier(infgen_engine *e, const FourierArgs &a, int d) {
+    int grid = (a.n_slots + FM - 1) / FM;
+    if (grid == 0) return 0;
+    switch (d) {
+        case 2: k_fourier<2><<<grid, NT, FOURIER_SMEM, e->stream>>>(a); break;
+        case 3: k_fourier<3><<<grid, NT, FOURIER_SMEM, e->stream>>>(a); break;
+        case 4: k_fourier<4><<<grid, NT, FOURIER_SMEM, e->stream>>>(a); break;
+        default: return fail(INFGEN_ERR_INVALID_ARG, "FourierEmbedding input_dim %d unsupported", d);
+    }
+    CKL();
+    count_launch(e);
+    return 0;
+}
+static int launch_mlp_embed(infgen_engine *e, const MlpEmbArgs &a) {
+    int grid = (a.rows.n_total + EM - 1) / EM;
+    if (grid == 0) return 0;
+    k_mlp_embed<<<grid, NT, mlp_embed_smem(a.k4), e->stream>>>(a);
+    CKL();
+    count_launch(e);
+    return 0;
+}
+
+static RowSpace scene_rows(infgen_engine *e) {
+    RowSpace r;
+    r.n_total = e->R; r.cap = e->cap; r.n_rows = e->st.n_rows;
+    return r;
+}
+static RowSpace flat_rows(int n) {
+    RowSpace r;
+    r.n_total = n; r.cap = 0; r.n_rows = nullptr;
+    return r;
+}
+
+// column embedding (agent_decoder.py:2265-2287) of column col+col_add, then the pre half of temporal layer 0
+static int enqueue_embed_column(infgen_engine *e, int col_add) {
+    DecState &s = e->st;
+    const int R = e->R;
+    k_embed_inputs<<<(R + 127) / 128, 128, 0, e->stream>>>(s, col_add);
+    CKL(); count_launch(e);
+    FourierArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.n_slots = R; fa.cnt = s.n_rows; fa.stride = e->cap; fa.raw = s.xa_raw; fa.w = e->f_x;
+    fa.cat_tab = fbuf(e, "cat_tab"); fa.cat_idx = s.cat_idx; fa.out = fbuf(e, "xa"); fa.normalize = 0;
+    RET(launch_fourier(e, fa, 2));
+    MlpEmbArgs ma;
+    memset(&ma, 0, sizeof(ma));
+    ma.rows = scene_rows(e); ma.w = e->e_fusion; ma.kin = 512; ma.k4 = 128; ma.fusion = 1;
+    ma.tok_tab = e->tok_tab; ma.tok_row = s.tok_row; ma.xa = fbuf(e, "xa"); ma.state_tab = e->state_emb;
+    ma.state_idx = s.state_idx; ma.grid_tab = e->grid_tab; ma.grid_row = s.grid_row;
+    ma.out = fbuf(e, "x"); ma.out_ld = 128;
+    RET(launch_mlp_embed(e, ma));
+    NodeArgs na;
+    memset(&na, 0, sizeof(na));
+    na.rows = scene_rows(e); na.has_post = 0; na.x_in = fbuf(e, "x");
+    na.has_pre = 1; na.pre = e->t[0]; na.pre_kv = 1;
+    na.q_out = fbuf(e, "q"); na.s_out = fbuf(e, "s"); na.qr_out = fbuf(e, "qr");
+    na.kv_out = fbuf(e, "kv_t"); na.kv_ring = 1; na.col_ptr = s.col; na.col_add = col_add;
+    RET(launch_node(e, na, R));
+    return 0;
+}
+
+// the 18-layer stack for the current column. with_edges=false: history columns that receive no edges (prefill).
+static int enqueue_layers(infgen_engine *e, bool with_edges, int trace_iter) {
+    DecState &s = e->st;
+    const int R = e->R;
+    float *x = fbuf(e, "x"), *q = fbuf(e, "q"), *sb = fbuf(e, "s"), *qr = fbuf(e, "qr");
+    float *agg = fbuf(e, "agg"), *ragg = fbuf(e, "ragg"), *sal = fbuf(e, "sal"), *zero = fbuf(e, "zero");
+    float *kv_t = fbuf(e, "kv_t"), *kv_m = fbuf(e, "kv_m"), *kv_a = fbuf(e, "kv_a");
+    const size_t kv_t_layer = (size_t)R * RING * 256, kv_m_layer = (size_t)e->P * 256;
+    for (int i = 0; i < 6; ++i) {
+        for (int kind = 0; kind < 3; ++kind) {          // 0 temporal, 1 map->agent, 2 agent<->agent
+            if (with_edges) {
+                AttnArgs aa;
+                memset(&aa, 0, sizeof(aa));
+                aa.rows = scene_rows(e); aa.q = q; aa.qr = qr; aa.has_pos = 1;
+                aa.agg = agg; aa.ragg = ragg; aa.sal = sal; aa.err = e->d_err;
+                if (kind == 0) {
+                    aa.kv = kv_t + i * kv_t_layer; aa.cnt = s.t_cnt; aa.start = nullptr; aa.stride = s.W;
+                    aa.src = s.t_src; aa.rhat = fbuf(e, "rhat_t"); aa.max_deg = s.W;
+                } else if (kind == 1) {
+                    aa.kv = kv_m + i * kv_m_layer; aa.cnt = s.m_cnt; aa.start = nullptr; aa.stride = s.max_m;
+                    aa.src = s.m_src; aa.rhat = fbuf(e, "rhat_m"); aa.max_deg = s.max_m;
+                } else {
+                    aa.kv = kv_a; aa.cnt = s.a_cnt; aa.start = s.a_start; aa.stride = 0;
+                    aa.src = s.a_src; aa.rhat = fbuf(e, "rhat_a"); aa.max_deg = e->cap;
+                }
+                RET(launch_attn(e, aa));
+            }
+            NodeArgs na;
+            memset(&na, 0, sizeof(na));
+            na.rows = scene_rows(e);
+            na.has_post = 1;
+            na.post = kind == 0 ? e->t[i] : kind == 1 ? e->m[i] : e->a[i];
+            na.x_in = x; na.s_in = sb;
+            na.agg = with_edges ? agg : zero; na.ragg = with_edges ? ragg : zero; na.sal = with_edges ? sal : zero;
+            na.x_out = x;
+            na.q_out = q; na.s_out = sb; na.qr_out = qr; na.col_ptr = s.col; na.col_add = 0;
+            if (kind == 0) {            // next: map->agent layer i (bipartite: only q, s of the agent rows)
+                na.has_pre = 1; na.pre = e->m[i]; na.pre_kv = 0;
+            } else if (kind == 1) {     // next: agent<->agent layer i
+                na.has_pre = 1; na.pre = e->a[i]; na.pre_kv = 1; na.kv_out = kv_a; na.kv_ring = 0;
+            } else if (i < 5) {         // next: temporal layer i+1
+                na.has_pre = 1; na.pre = e->t[i + 1]; na.pre_kv = 1;
+                na.kv_out = kv_t + (i + 1) * kv_t_layer; na.kv_ring = 1;
+            } else {
+                na.has_pre = 0;
+            }
+            if (kind == 2 && trace_iter >= 0 && e->cfg.trace)
+                na.trace_out = fbuf(e, "trace_layer_out") + ((size_t)trace_iter * 6 + i) * R * 128;
+            RET(launch_node(e, na, R));
+        }
+    }
+    return 0;
+}
+
+static int enqueue_iteration(infgen_engine *e, int trace_iter) {
+    DecState &s = e->st;
+    const int R = e->R;
+    k_edge_build<<<e->n_scenes, NT, 0, e->stream>>>(s);
+    CKL(); count_launch(e);
+    FourierArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.normalize = 1;
+    fa.n_slots = R * s.W; fa.cnt = s.t_cnt; fa.stride = s.W; fa.raw = s.t_raw; fa.w = e->f_t; fa.out = fbuf(e, "rhat_t");
+    RET(launch_fourier(e, fa, 4));
+    fa.n_slots = R * s.max_m; fa.cnt = s.m_cnt; fa.stride = s.max_m; fa.raw = s.m_raw; fa.w = e->f_m; fa.out = fbuf(e, "rhat_m");
+    RET(launch_fourier(e, fa, 3));
+    fa.n_slots = e->n_scenes * e->cap * e->cap; fa.cnt = s.a_total; fa.stride = e->cap * e->cap; fa.raw = s.a_raw;
+    fa.w = e->f_a; fa.out = fbuf(e, "rhat_a");
+    RET(launch_fourier(e, fa, 3));
+    RET(enqueue_layers(e, true, trace_iter));
+    HeadArgs ha;
+    memset(&ha, 0, sizeof(ha));
+    ha.rows = scene_rows(e); ha.x = fbuf(e, "x"); ha.tok = e->h_tok; ha.st = e->h_state;
+    ha.part_v = fbuf(e, "part_v"); ha.part_i = (int *)e->bufs["part_i"].p;
+    ha.part_m = fbuf(e, "part_m"); ha.part_s = fbuf(e, "part_s"); ha.state_logits = fbuf(e, "state_logits");
+    if (e->cfg.trace && trace_iter >= 0) {
+        ha.trace_head_in = fbuf(e, "trace_head_in") + (size_t)trace_iter * R * 128;
+        ha.trace_logits = fbuf(e, "trace_token_logits") + (size_t)trace_iter * R * e->cfg.token_size;
+        ha.trace_state = fbuf(e, "trace_state_logits") + (size_t)trace_iter * R * 3;
+    }
+    k_heads<<<dim3((R + HM - 1) / HM, NSLICE), NT, 0, e->stream>>>(ha);
+    CKL(); count_launch(e);
+    k_advance<<<e->n_scenes, NT, 0, e->stream>>>(s);
+    CKL(); count_launch(e);
+    RET(enqueue_embed_column(e, 1));
+    k_next_iter<<<1, 1, 0, e->stream>>>(s.col, s.iter);
+    CKL(); count_launch(e);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int32_t infgen_abi_version(void) { return INFGEN_ABI_VERSION; }
+const char *infgen_last_error(void) { return g_err; }
+
+int32_t infgen_weight_count(void) { build_layout(); return (int32_t)g_layout.size(); }
+const char *infgen_weight_name(int32_t i) {
+    build_layout();
+    return (i >= 0 && i < (int)g_layout.size()) ? g_layout[i].name.c_str() : nullptr;
+}
+int64_t infgen_weight_offset(const char *name) {
+    build_layout();
+    auto it = g_index.find(name);
+    return it == g_index.end() ? -1 : g_layout[it->second].offset;
+}
+int64_t infgen_weight_numel(const char *name) {
+    build_layout();
+    auto it = g_index.find(name);
+    return it == g_index.end() ? -1 : g_layout[it->second].numel;
+}
+int64_t infgen_weight_blob_floats(void) { build_layout(); return g_total; }
+
+static int build_tables(infgen_engine *e) {
+    const int V = e->cfg.token_size, G = e->cfg.grid_size;
+    CK(cudaMalloc(&e->tok_tab, (size_t)3 * (V + 2) * 128 * sizeof(float)));
+    CK(cudaMalloc(&e->grid_tab, (size_t)(G + 1) * 128 * sizeof(float)));
+    for (int ty = 0; ty < 3; ++ty) {          // agent_decoder.py:347-362: MLPEmbedding of the last sub-step box, + BOS, + none
+        MlpEmbArgs ma;
+        memset(&ma, 0, sizeof(ma));
+        ma.rows = flat_rows(V); ma.w = e->e_tok[ty]; ma.kin = 8; ma.k4 = 2;
+        ma.x = e->vocab + (size_t)ty * V * 48 + 40; ma.x_ld = 48;
+        ma.out = e->tok_tab + (size_t)ty * (V + 2) * 128; ma.out_ld = 128;
+        RET(launch_mlp_embed(e, ma));
+        CK(cudaMemcpyAsync(e->tok_tab + ((size_t)ty * (V + 2) + V) * 128, W(e, "bos_token_emb"), 128 * sizeof(float),
+                           cudaMemcpyDeviceToDevice, e->stream));
+        CK(cudaMemcpyAsync(e->tok_tab + ((size_t)ty * (V + 2) + V + 1) * 128, W(e, "no_token_emb"), 128 * sizeof(float),
+                           cudaMemcpyDeviceToDevice, e->stream));
+    }
+    MlpEmbArgs ga;                            // agent_decoder.py:371-373
+    memset(&ga, 0, sizeof(ga));
+    ga.rows = flat_rows(G); ga.w = e->e_grid; ga.kin = 2; ga.k4 = 1; ga.x = e->grid_cells; ga.x_ld = 2;
+    ga.out = e->grid_tab; ga.out_ld = 128;
+    RET(launch_mlp_embed(e, ga));
+    CK(cudaMemcpyAsync(e->grid_tab + (size_t)G * 128, W(e, "invalid_offset_token_emb"), 128 * sizeof(float),
+                       cudaMemcpyDeviceToDevice, e->stream));
+    return 0;
+}
+
+int32_t infgen_create(const infgen_config *cfg, const float *weights, int64_t n_floats, const float *grid_cells,
+                      const float *vocab, infgen_engine **out) {
+    build_layout();
+    if (!cfg || !weights || !grid_cells || !vocab || !out) return fail(INFGEN_ERR_INVALID_ARG, "null argument");
+    if (cfg->abi_version != INFGEN_ABI_VERSION)
+        return fail(INFGEN_ERR_INVALID_ARG, "ABI version %d != library %d", cfg->abi_version, INFGEN_ABI_VERSION);
+    if (n_floats != g_total) return fail(INFGEN_ERR_INVALID_ARG, "weight blob has %lld floats, expected %lld",
+                                          (long long)n_floats, (long long)g_total);
+    if (cfg->num_layers != 6 || cfg->token_size != TOKEN_SIZE || cfg->window + 1 > RING || cfg->window > 32 ||
+        cfg->hist_cols < 1 || cfg->motion_beam_size < 1 || cfg->motion_beam_size > KTOP || cfg->max_pl2a_neighbors > 32)
+        return fail(INFGEN_ERR_INVALID_ARG, "unsupported configuration (layers=%d tokens=%d window=%d beam=%d)",
+                    cfg->num_layers, cfg->token_size, cfg->window, cfg->motion_beam_size);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(INFGEN_ERR_NO_DEVICE, "no CUDA device: the decode path has no CPU fallback");
+    }
+    CK(cudaSetDevice(cfg->device));
+    infgen_engine *e = new infgen_engine();
+    e->cfg = *cfg;
+    CK(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+    e->stream = e->own_stream;
+    CK(cudaMalloc(&e->blob, (size_t)g_total * sizeof(float)));
+    CK(cudaMemcpyAsync(e->blob, weights, (size_t)g_total * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMalloc(&e->grid_cells, (size_t)cfg->grid_size * 2 * sizeof(float)));
+    CK(cudaMemcpyAsync(e->grid_cells, grid_cells, (size_t)cfg->grid_size * 2 * sizeof(float), cudaMemcpyHostToDevice,
+                       e->stream));
+    CK(cudaMalloc(&e->vocab, (size_t)3 * cfg->token_size * 48 * sizeof(float)));
+    CK(cudaMemcpyAsync(e->vocab, vocab, (size_t)3 * cfg->token_size * 48 * sizeof(float), cudaMemcpyHostToDevice,
+                       e->stream));
+    CK(cudaMalloc(&e->d_err, sizeof(int)));
+    CK(cudaMemsetAsync(e->d_err, 0, sizeof(int), e->stream));
+    for (int i = 0; i < 6; ++i) {
+        e->t[i] = make_attn(e, "t_attn_layers." + std::to_string(i), true);
+        e->m[i] = make_attn(e, "pt2a_attn_layers." + std::to_string(i), true);
+        e->a[i] = make_attn(e, "a2a_attn_layers." + std::to_string(i), true);
+    }
+    e->f_t = make_fourier(e, "r_t_emb", 4); e->f_m = make_fourier(e, "r_pt2a_emb", 3);
+    e->f_a = make_fourier(e, "r_a2a_emb", 3); e->f_x = make_fourier(e, "x_a_emb", 2);
+    e->e_shape = make_mlp_emb(e, "shape_emb"); e->e_fusion = make_mlp_emb(e, "fusion_emb");
+    e->e_tok[0] = make_mlp_emb(e, "token_emb_veh"); e->e_tok[1] = make_mlp_emb(e, "token_emb_ped");
+    e->e_tok[2] = make_mlp_emb(e, "token_emb_cyc"); e->e_grid = make_mlp_emb(e, "token_emb_grid");
+    e->h_tok = make_head(e, "token_predict_head", 128, cfg->token_size);
+    e->h_state = make_head(e, "state_predict_head", 128, 3);
+    e->type_emb = W(e, "type_a_emb"); e->state_emb = W(e, "state_a_emb");
+    // kernels that need more than 48 KB of dynamic shared memory
+    CK(cudaFuncSetAttribute(k_node_update<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NodeSmem<16>::BYTES));
+    CK(cudaFuncSetAttribute(k_node_update<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NodeSmem<4>::BYTES));
+    CK(cudaFuncSetAttribute(k_fourier<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FOURIER_SMEM));
+    CK(cudaFuncSetAttribute(k_fourier<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FOURIER_SMEM));
+    CK(cudaFuncSetAttribute(k_fourier<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FOURIER_SMEM));
+    CK(cudaFuncSetAttribute(k_edge_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, NWARP * MAX_CAP * 8 * 4));
+    CK(cudaFuncSetAttribute(k_mlp_embed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mlp_embed_smem(128)));
+    RET(build_tables(e));
+    CK(cudaStreamSynchronize(e->stream));
+    *out = e;
+    return 0;
+}
+
+int32_t infgen_destroy(infgen_engine *e) {
+    if (!e) return 0;
+    cudaStreamSynchronize(e->stream);
+    if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+    if (e->graph) cudaGraphDestroy(e->graph);
+    for (auto &kv : e->bufs)
+        if (kv.second.p) cudaFree(kv.second.p);
+    cudaFree(e->blob); cudaFree(e->grid_cells); cudaFree(e->vocab); cudaFree(e->tok_tab); cudaFree(e->grid_tab);
+    cudaFree(e->d_err);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    delete e;
+    return 0;
+}
+
+static void drop_graph(infgen_engine *e) {
+    if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+    if (e->graph) { cudaGraphDestroy(e->graph); e->graph = nullptr; }
+}
+
+int32_t infgen_set_stream(infgen_engine *e, void *cuda_stream) {
+    if (!e) return fail(INFGEN_ERR_INVALID_ARG, "null engine");
+    CK(cudaStreamSynchronize(e->stream));
+    e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+    drop_graph(e);
+    return 0;
+}
+int32_t infgen_set_sampler(infgen_engine *e, int32_t beam, uint32_t seed) {
+    if (!e) return fail(INFGEN_ERR_INVALID_ARG, "null engine");
+    if (beam < 1 || beam > KTOP) return fail(INFGEN_ERR_INVALID_ARG, "motion_beam_size %d not in [1,%d]", beam, KTOP);
+    if (e->cfg.motion_beam_size != beam || e->cfg.seed != seed) drop_graph(e);
+    e->cfg.motion_beam_size = beam; e->cfg.seed = seed;
+    e->st.beam = beam; e->st.seed = seed;
+    return 0;
+}
+int32_t infgen_synchronize(infgen_engine *e) {
+    if (!e) return fail(INFGEN_ERR_INVALID_ARG, "null engine");
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+static cudaMemcpyKind in_kind(int loc) { return loc == INFGEN_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice; }
+static cudaMemcpyKind out_kind(int loc) { return loc == INFGEN_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost; }
+
+int32_t infgen_load_scenes(infgen_engine *e, const infgen_scene_batch *b, int32_t loc) {
+    if (!e || !b) return fail(INFGEN_ERR_INVALID_ARG, "null argument");
+    if (b->n_scenes < 1 || b->row_capacity < 1 || b->row_capacity % 4 != 0 || b->row_capacity > MAX_CAP)
+        return fail(INFGEN_ERR_CAPACITY, "row_capacity %d must be a multiple of 4 in [4,%d]", b->row_capacity, MAX_CAP);
+    if (b->row_capacity > e->cfg.max_a2a_neighbors)
+        return fail(INFGEN_ERR_CAPACITY, "row_capacity %d exceeds max_a2a_neighbors %d (neighbour truncation is not implemented)",
+                    b->row_capacity, e->cfg.max_a2a_neighbors);
+    const int HC = e->cfg.hist_cols;
+    if (b->n_cols < HC + b->n_iters || b->n_iters < 0)
+        return fail(INFGEN_ERR_INVALID_ARG, "n_cols %d < hist_cols %d + n_iters %d", b->n_cols, HC, b->n_iters);
+    if (loc != INFGEN_HOST) return fail(INFGEN_ERR_INVALID_ARG, "scene descriptors must be host memory (loc=0)");
+    const int ns = b->n_scenes, cap = b->row_capacity, R = ns * cap, T = b->n_cols, S = b->n_iters;
+    int sum = 0, mx = 0;
+    for (int i = 0; i < ns; ++i) {
+        if (b->n_rows[i] < 1 || b->n_rows[i] > cap) return fail(INFGEN_ERR_CAPACITY, "scene %d has %d rows, capacity %d", i, b->n_rows[i], cap);
+        if (b->ego_row[i] < 0 || b->ego_row[i] >= b->n_rows[i]) return fail(INFGEN_ERR_INVALID_ARG, "scene %d: ego row %d out of range", i, b->ego_row[i]);
+        sum += b->n_rows[i]; mx = std::max(mx, b->n_rows[i]);
+    }
+    const int P = b->pt_ptr[ns];
+    if (b->pt_ptr[0] != 0 || P < 0) return fail(INFGEN_ERR_INVALID_ARG, "pt_ptr must start at 0");
+    if (e->n_scenes != ns || e->cap != cap || e->T != T || e->S != S || e->P != P) drop_graph(e);
+    e->n_scenes = ns; e->cap = cap; e->R = R; e->T = T; e->S = S; e->P = P; e->n_rows_sum = sum; e->max_rows = mx;
+    e->row_tile = sum > 512 ? 16 : 4;
+    e->iters_done = 0; e->prefilled = 0; e->forcing = false;
+    const int W = e->cfg.window, MM = e->cfg.max_pl2a_neighbors, V = e->cfg.token_size;
+    DecState &s = e->st;
+    DecState old = s;
+    memset(&s, 0, sizeof(s));
+    s.n_scenes = ns; s.cap = cap; s.T = T; s.S = S; s.HC = HC; s.W = W; s.q_rows = e->cfg.num_seed_feature;
+    s.G = e->cfg.grid_size; s.V = V; s.max_m = MM;
+    s.r_m2 = e->cfg.pl2a_radius * e->cfg.pl2a_radius; s.r_a2 = e->cfg.a2a_radius * e->cfg.a2a_radius;
+    s.use_state_token = e->cfg.use_state_token; s.disable_insertion = e->cfg.disable_insertion;
+    s.beam = e->cfg.motion_beam_size; s.seed = e->cfg.seed;
+    s.grid_cells = e->grid_cells; s.vocab = e->vocab;
+    // ---- inputs ----
+    int *d_n_rows, *d_ego, *d_sid, *d_type, *d_pt_ptr, *d_state_h, *d_token_h, *d_grid_h;
+    float *d_pos_h, *d_head_h, *d_shape, *d_pt_pos, *d_pt_ori, *d_x_pt;
+    uint8_t *d_tsrc_h, *d_int_h;
+    RET(ensure_t(e, "n_rows", ns, &d_n_rows)); RET(ensure_t(e, "ego_row", ns, &d_ego)); RET(ensure_t(e, "scene_id", ns, &d_sid));
+    RET(ensure_t(e, "type", R, &d_type)); RET(ensure_t(e, "pt_ptr", ns + 1, &d_pt_ptr));
+    RET(ensure_t(e, "state_hist", (size_t)R * HC, &d_state_h)); RET(ensure_t(e, "token_hist", (size_t)R * HC, &d_token_h));
+    RET(ensure_t(e, "grid_hist", (size_t)R * HC, &d_grid_h));
+    RET(ensure_t(e, "pos_hist", (size_t)R * HC * 2, &d_pos_h)); RET(ensure_t(e, "head_hist", (size_t)R * HC, &d_head_h));
+    RET(ensure_t(e, "shape", (size_t)R * 3, &d_shape));
+    RET(ensure_t(e, "pt_pos", (size_t)std::max(P, 1) * 2, &d_pt_pos)); RET(ensure_t(e, "pt_ori", (size_t)std::max(P, 1), &d_pt_ori));
+    RET(ensure_t(e, "x_pt", (size_t)std::max(P, 1) * 128, &d_x_pt));
+    RET(ensure_t(e, "tsrc_hist", (size_t)R * HC, &d_tsrc_h)); RET(ensure_t(e, "interact_hist", (size_t)R * HC, &d_int_h));
+    const cudaMemcpyKind k = in_kind(loc);
+    cudaStream_t st = e->stream;
+    CK(cudaMemcpyAsync(d_n_rows, b->n_rows, ns * sizeof(int), k, st));
+    CK(cudaMemcpyAsync(d_ego, b->ego_row, ns * sizeof(int), k, st));
+    CK(cudaMemcpyAsync(d_sid, b->scene_id, ns * sizeof(int), k, st));
+    CK(cudaMemcpyAsync(d_type, b->type, (size_t)R * sizeof(int), k, st));
+    CK(cudaMemcpyAsync(d_pt_ptr, b->pt_ptr, (ns + 1) * sizeof(int), k, st));
+    CK(cudaMemcpyAsync(d_state_h, b->state_hist, (size_t)R * HC * sizeof(int), k, st));
+    CK(cudaMemcpyAsync(d_token_h, b->token_hist, (size_t)R * HC * sizeof(int), k, st));
+    CK(cudaMemcpyAsync(d_grid_h, b->grid_hist, (size_t)R * HC * sizeof(int), k, st));
+    CK(cudaMemcpyAsync(d_pos_h, b->pos_hist, (size_t)R * HC * 2 * sizeof(float), k, st));
+    CK(cudaMemcpyAsync(d_head_h, b->head_hist, (size_t)R * HC * sizeof(float), k, st));
+    CK(cudaMemcpyAsync(d_shape, b->shape, (size_t)R * 3 * sizeof(float), k, st));
+    CK(cudaMemcpyAsync(d_tsrc_h, b->tsrc_hist, (size_t)R * HC, k, st));
+    CK(cudaMemcpyAsync(d_int_h, b->interact_hist, (size_t)R * HC, k, st));
+    if (P > 0) {
+        CK(cudaMemcpyAsync(d_pt_pos, b->pt_pos, (size_t)P * 2 * sizeof(float), k, st));
+        CK(cudaMemcpyAsync(d_pt_ori, b->pt_ori, (size_t)P * sizeof(float), k, st));
+        CK(cudaMemcpyAsync(d_x_pt, b->x_pt, (size_t)P * 128 * sizeof(float), k, st));
+    }
+    s.n_rows = d_n_rows; s.ego_row = d_ego; s.scene_id = d_sid; s.type = d_type; s.pt_ptr = d_pt_ptr;
+    s.pt_pos = d_pt_pos; s.pt_ori = d_pt_ori;
+    // ---- state ----
+    RET(ensure_t(e, "col", 2, &s.col)); s.iter = s.col + 1;
+    RET(ensure_t(e, "pos", (size_t)R * T * 2, &s.pos)); RET(ensure_t(e, "head", (size_t)R * T, &s.head));
+    RET(ensure_t(e, "state", (size_t)R * T, &s.state)); RET(ensure_t(e, "token", (size_t)R * T, &s.token));
+    RET(ensure_t(e, "grid", (size_t)R * T, &s.grid));
+    RET(ensure_t(e, "interact", (size_t)R * T, &s.interact)); RET(ensure_t(e, "tsrc", (size_t)R * T, &s.tsrc));
+    RET(ensure_t(e, "t_cnt", R, &s.t_cnt)); RET(ensure_t(e, "t_src", (size_t)R * W, &s.t_src));
+    RET(ensure_t(e, "t_raw", (size_t)R * W * 4, &s.t_raw));
+    RET(ensure_t(e, "m_cnt", R, &s.m_cnt)); RET(ensure_t(e, "m_src", (size_t)R * MM, &s.m_src));
+    RET(ensure_t(e, "m_raw", (size_t)R * MM * 3, &s.m_raw));
+    RET(ensure_t(e, "a_cnt", R, &s.a_cnt)); RET(ensure_t(e, "a_start", R, &s.a_start)); RET(ensure_t(e, "a_total", ns, &s.a_total));
+    RET(ensure_t(e, "a_src", (size_t)R * cap, &s.a_src)); RET(ensure_t(e, "a_raw", (size_t)R * cap * 3, &s.a_raw));
+    RET(ensure_t(e, "xa_raw", (size_t)R * 2, &s.xa_raw));
+    RET(ensure_t(e, "tok_row", R, &s.tok_row)); RET(ensure_t(e, "state_idx", R, &s.state_idx));
+    RET(ensure_t(e, "grid_row", R, &s.grid_row)); RET(ensure_t(e, "cat_idx", R, &s.cat_idx));
+    float *part_v, *part_m, *part_s, *slog; int *part_i;
+    RET(ensure_t(e, "part_v", (size_t)R * NSLICE * KTOP, &part_v)); RET(ensure_t(e, "part_i", (size_t)R * NSLICE * KTOP, &part_i));
+    RET(ensure_t(e, "part_m", (size_t)R * NSLICE, &part_m)); RET(ensure_t(e, "part_s", (size_t)R * NSLICE, &part_s));
+    RET(ensure_t(e, "state_logits", (size_t)R * 4, &slog));
+    s.part_v = part_v; s.part_i = part_i; s.part_m = part_m; s.part_s = part_s; s.state_logits = slog;
+    const int NR = std::max(5 * S, 1);
+    RET(ensure_t(e, "pred_traj", (size_t)R * NR * 2, &s.pred_traj)); RET(ensure_t(e, "pred_head", (size_t)R * NR, &s.pred_head));
+    RET(ensure_t(e, "pred_state", (size_t)R * NR, &s.pred_state));
+    RET(ensure_t(e, "next_token", (size_t)R * T, &s.next_token)); RET(ensure_t(e, "next_state", (size_t)R * T, &s.next_state));
+    // ---- scratch ----
+    float *tmp;
+    RET(ensure_t(e, "x", (size_t)R * 128, &tmp)); RET(ensure_t(e, "q", (size_t)R * 128, &tmp)); RET(ensure_t(e, "s", (size_t)R * 128, &tmp));
+    RET(ensure_t(e, "qr", (size_t)R * 1024, &tmp)); RET(ensure_t(e, "agg", (size_t)R * 128, &tmp));
+    RET(ensure_t(e, "ragg", (size_t)R * 1024, &tmp)); RET(ensure_t(e, "sal", (size_t)R * 8, &tmp));
+    RET(ensure_t(e, "zero", (size_t)R * 1024, &tmp)); RET(ensure_t(e, "xa", (size_t)R * 128, &tmp));
+    RET(ensure_t(e, "kv_t", (size_t)6 * R * RING * 256, &tmp)); RET(ensure_t(e, "kv_a", (size_t)R * 256, &tmp));
+    RET(ensure_t(e, "kv_m", (size_t)6 * std::max(P, 1) * 256, &tmp));
+    RET(ensure_t(e, "rhat_t", (size_t)R * W * 128, &tmp)); RET(ensure_t(e, "rhat_m", (size_t)R * MM * 128, &tmp));
+    RET(ensure_t(e, "rhat_a", (size_t)R * cap * 128, &tmp));
+    RET(ensure_t(e, "cat_tab", (size_t)(R + 1) * 128, &tmp)); RET(ensure_t(e, "shape_rows", (size_t)(R + 1) * 4, &tmp));
+    RET(ensure_t(e, "hist_traj", (size_t)R * HC * 5 * 2, &tmp)); RET(ensure_t(e, "hist_head", (size_t)R * HC * 5, &tmp));
+    if (e->cfg.trace && S > 0) {
+        RET(ensure_t(e, "trace_head_in", (size_t)S * R * 128, &tmp));
+        RET(ensure_t(e, "trace_token_logits", (size_t)S * R * V, &tmp));
+        RET(ensure_t(e, "trace_state_logits", (size_t)S * R * 3, &tmp));
+        RET(ensure_t(e, "trace_layer_out", (size_t)S * 6 * R * 128, &tmp));
+    }
+    if (memcmp(&old, &s, sizeof(s)) != 0) drop_graph(e);
+    // ---- expand history into the state arrays, zero counters ----
+    SetupArgs sa;
+    sa.s = s; sa.pos_hist = d_pos_h; sa.head_hist = d_head_h; sa.state_hist = d_state_h; sa.token_hist = d_token_h;
+    sa.grid_hist = d_grid_h; sa.tsrc_hist = d_tsrc_h; sa.interact_hist = d_int_h;
+    k_setup_state<<<(R * T + 255) / 256, 256, 0, st>>>(sa);
+    CKL(); count_launch(e);
+    CK(cudaMemsetAsync(s.a_total, 0, ns * sizeof(int), st));
+    CK(cudaMemsetAsync(s.col, 0, 2 * sizeof(int), st));
+    // ---- categorical embedding rows (type + shape, agent_decoder.py:449-478) ----
+    float *shape_rows = fbuf(e, "shape_rows"), *cat_tab = fbuf(e, "cat_tab");
+    k_fill_shape_rows<<<((R + 1) * 3 + 255) / 256, 256, 0, st>>>(shape_rows, d_shape, R);
+    CKL(); count_launch(e);
+    MlpEmbArgs ma;
+    memset(&ma, 0, sizeof(ma));
+    ma.rows = flat_rows(R + 1); ma.w = e->e_shape; ma.kin = 3; ma.k4 = 1; ma.x = shape_rows; ma.x_ld = 3;
+    ma.out = cat_tab; ma.out_ld = 128;
+    RET(launch_mlp_embed(e, ma));
+    k_add_type_emb<<<((R + 1) * 128 + 255) / 256, 256, 0, st>>>(cat_tab, e->type_emb, d_type, R, 3);
+    CKL(); count_launch(e);
+    // ---- map K/V cache of the six pt2a layers (x_pt is constant during the rollout) ----
+    if (P > 0) {
+        KvArgs ka;
+        memset(&ka, 0, sizeof(ka));
+        ka.n = P; ka.x = d_x_pt;
+        for (int i = 0; i < 6; ++i) { ka.w[i] = e->m[i]; ka.out[i] = fbuf(e, "kv_m") + (size_t)i * P * 256; }
+        k_kv_project<16><<<dim3((P + 15) / 16, 6), NT, 0, st>>>(ka);
+        CKL(); count_launch(e);
+    }
+    e->loaded = true;
+    return 0;
+}
+
+int32_t infgen_set_forcing(infgen_engine *e, const int32_t *tokens, const int32_t *states, int32_t loc) {
+    if (!e || !e->loaded) return fail(INFGEN_ERR_STATE, "no scenes loaded");
+    const size_t n = (size_t)e->R * std::max(e->S, 1);
+    const int *old_t = e->st.forced_tok, *old_s = e->st.forced_state;
+    e->st.forced_tok = nullptr; e->st.forced_state = nullptr;
+    if (tokens) {
+        int *d; RET(ensure_t(e, "forced_tok", n, &d));
+        CK(cudaMemcpyAsync(d, tokens, n * sizeof(int), in_kind(loc), e->stream));
+        e->st.forced_tok = d;
+    }
+    if (states) {
+        int *d; RET(ensure_t(e, "forced_state", n, &d));
+        CK(cudaMemcpyAsync(d, states, n * sizeof(int), in_kind(loc), e->stream));
+        e->st.forced_state = d;
+    }
+    if (old_t != e->st.forced_tok || old_s != e->st.forced_state) drop_graph(e);
+    return 0;
+}
+
+int32_t infgen_prefill(infgen_engine *e) {
+    if (!e || !e->loaded) return fail(INFGEN_ERR_STATE, "no scenes loaded");
+    if (e->prefilled) return fail(INFGEN_ERR_STATE, "prefill already done for this batch");
+    DecState &s = e->st;
+    CK(cudaMemsetAsync(s.col, 0, 2 * sizeof(int), e->stream));
+    for (int c = 0; c + 1 < s.HC; ++c) {
+        RET(enqueue_embed_column(e, 0));
+        RET(enqueue_layers(e, false, -1));
+        k_set_scalar<<<1, 1, 0, e->stream>>>(s.col, c + 1);
+        CKL(); count_launch(e);
+    }
+    RET(enqueue_embed_column(e, 0));
+    e->prefilled = 1;
+    return 0;
+}
+
+int32_t infgen_step(infgen_engine *e, int32_t n_iters) {
+    if (!e || !e->loaded) return fail(INFGEN_ERR_STATE, "no scenes loaded");
+    if (!e->prefilled) return fail(INFGEN_ERR_STATE, "infgen_prefill has not run");
+    if (n_iters < 0 || e->iters_done + n_iters > e->S)
+        return fail(INFGEN_ERR_INVALID_ARG, "%d iterations requested, %d of %d already done", n_iters, e->iters_done, e->S);
+    const bool use_graph = e->cfg.use_cuda_graph && !e->cfg.trace;
+    for (int i = 0; i < n_iters; ++i) {
+        if (use_graph) {
+            if (!e->graph_exec) {
+                CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+                e->capturing = true;
+                int rc = enqueue_iteration(e, -1);
+                e->capturing = false;
+                cudaGraph_t g = nullptr;
+                cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
+                if (rc != 0) { if (g) cudaGraphDestroy(g); return rc; }
+                if (ce != cudaSuccess) return fail(INFGEN_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+                e->graph = g;
+                CK(cudaGraphGetNodes(g, nullptr, &e->graph_nodes));
+                CK(cudaGraphInstantiate(&e->graph_exec, g, 0));
+            }
+            CK(cudaGraphLaunch(e->graph_exec, e->stream));
+            e->launches += (int64_t)e->graph_nodes;
+        } else {
+            RET(enqueue_iteration(e, e->iters_done));
+        }
+        e->iters_done++;
+    }
+    return 0;
+}
+
+int32_t infgen_rollout(infgen_engine *e) {
+    if (!e || !e->loaded) return fail(INFGEN_ERR_STATE, "no scenes loaded");
+    if (!e->prefilled) RET(infgen_prefill(e));
+    return infgen_step(e, e->S - e->iters_done);
+}
+
+int32_t infgen_iterations_done(infgen_engine *e) { return e ? e->iters_done : -1; }
+int64_t infgen_kernel_launches(infgen_engine *e) { return e ? e->launches : -1; }
+
+int32_t infgen_read(infgen_engine *e, const infgen_outputs *o, int32_t loc) {
+    if (!e || !e->loaded || !o) return fail(INFGEN_ERR_STATE, "no scenes loaded");
+    DecState &s = e->st;
+    const size_t R = e->R, T = e->T, NR = (size_t)5 * e->S, HC = s.HC;
+    const cudaMemcpyKind k = out_kind(loc);
+    cudaStream_t st = e->stream;
+    if (o->hist_traj || o->hist_head) {
+        k_history_traj<<<((int)R + 127) / 128, 128, 0, st>>>(s, fbuf(e, "hist_traj"), fbuf(e, "hist_head"));
+        CKL(); count_launch(e);
+    }
+    if (o->pos) CK(cudaMemcpyAsync(o->pos, s.pos, R * T * 2 * sizeof(float), k, st));
+    if (o->head) CK(cudaMemcpyAsync(o->head, s.head, R * T * sizeof(float), k, st));
+    if (o->pred_traj && NR) CK(cudaMemcpyAsync(o->pred_traj, s.pred_traj, R * NR * 2 * sizeof(float), k, st));
+    if (o->pred_head && NR) CK(cudaMemcpyAsync(o->pred_head, s.pred_head, R * NR * sizeof(float), k, st));
+    if (o->pred_state && NR) CK(cudaMemcpyAsync(o->pred_state, s.pred_state, R * NR * sizeof(float), k, st));
+    if (o->next_token) CK(cudaMemcpyAsync(o->next_token, s.next_token, R * T * sizeof(int), k, st));
+    if (o->next_state) CK(cudaMemcpyAsync(o->next_state, s.next_state, R * T * sizeof(int), k, st));
+    if (o->hist_traj) CK(cudaMemcpyAsync(o->hist_traj, fbuf(e, "hist_traj"), R * HC * 5 * 2 * sizeof(float), k, st));
+    if (o->hist_head) CK(cudaMemcpyAsync(o->hist_head, fbuf(e, "hist_head"), R * HC * 5 * sizeof(float), k, st));
+    if (loc == INFGEN_HOST) {
+        CK(cudaStreamSynchronize(st));
+        int err = 0;
+        CK(cudaMemcpy(&err, e->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+        if (err) return fail(INFGEN_ERR_CAPACITY, "an attention row exceeded its edge capacity");
+    }
+    return 0;
+}
+
+int64_t infgen_debug_read(infgen_engine *e, const char *name, void *dst, int64_t max_bytes) {
+    if (!e || !name || !dst) return fail(INFGEN_ERR_INVALID_ARG, "null argument");
+    auto it = e->bufs.find(name);
+    if (it == e->bufs.end() || !it->second.p) return fail(INFGEN_ERR_INVALID_ARG, "no buffer named '%s'", name);
+    const int64_t n = std::min<int64_t>(max_bytes, (int64_t)it->second.bytes);
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(dst, it->second.p, (size_t)n, cudaMemcpyDeviceToHost));
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// operator level
+// ---------------------------------------------------------------------------------------------------------------
+}  // extern "C"
+struct TmpDev {
+    std::vector<void *> ptrs;
+    ~TmpDev() { for (void *p : ptrs) cudaFree(p); }
+    template <typename Tp> Tp *alloc(size_t n) {
+        void *p = nullptr;
+        if (cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(Tp)) != cudaSuccess) return nullptr;
+        cudaMemset(p, 0, std::max<size_t>(n, 1) * sizeof(Tp));
+        ptrs.push_back(p);
+        return (Tp *)p;
+    }
+    template <typename Tp> Tp *upload(const Tp *h, size_t n) {
+        Tp *d = alloc<Tp>(n);
+        if (d && n) cudaMemcpy(d, h, n * sizeof(Tp), cudaMemcpyHostToDevice);
+        return d;
+    }
+};
+extern "C" {
+
+int32_t infgen_op_attention_layer(infgen_engine *e, const char *layer, const float *x_src, int32_t n_src,
+                                  const float *x_dst, int32_t n_dst, const float *r, const int32_t *edge_ptr,
+                                  const int32_t *edge_src, float *out) {
+    if (!e || !layer || !x_dst || !edge_ptr || !out) return fail(INFGEN_ERR_INVALID_ARG, "null argument");
+    std::string p(layer);
+    if (g_index.find(p + ".w_qs") == g_index.end()) return fail(INFGEN_ERR_INVALID_ARG, "unknown layer '%s'", layer);
+    const bool has_pos = g_index.find(p + ".w_kr") != g_index.end() && r != nullptr;
+    AttnW w = make_attn(e, p, g_index.find(p + ".w_kr") != g_index.end());
+    w.has_pos = has_pos ? 1 : 0;
+    const bool bip = x_src != nullptr;
+    const int E = edge_ptr[n_dst];
+    int max_deg = 1;
+    std::vector<int> cnt(n_dst), start(n_dst);
+    for (int i = 0; i < n_dst; ++i) {
+        cnt[i] = edge_ptr[i + 1] - edge_ptr[i]; start[i] = edge_ptr[i];
+        max_deg = std::max(max_deg, cnt[i]);
+    }
+    if (max_deg > MAX_CAP) return fail(INFGEN_ERR_CAPACITY, "degree %d exceeds %d", max_deg, MAX_CAP);
+    CK(cudaStreamSynchronize(e->stream));
+    TmpDev tmp;
+    float *d_x = tmp.upload(x_dst, (size_t)n_dst * 128);
+    float *d_q = tmp.alloc<float>((size_t)n_dst * 128), *d_s = tmp.alloc<float>((size_t)n_dst * 128);
+    float *d_qr = tmp.alloc<float>((size_t)n_dst * 1024), *d_agg = tmp.alloc<float>((size_t)n_dst * 128);
+    float *d_ragg = tmp.alloc<float>((size_t)n_dst * 1024), *d_sal = tmp.alloc<float>((size_t)n_dst * 8);
+    float *d_out = tmp.alloc<float>((size_t)n_dst * 128);
+    const int n_kv = bip ? n_src : n_dst;
+    float *d_kv = tmp.alloc<float>((size_t)n_kv * 256);
+    int *d_cnt = tmp.upload(cnt.data(), n_dst), *d_start = tmp.upload(start.data(), n_dst);
+    int *d_src = tmp.upload(edge_src, (size_t)E);
+    float *d_rhat = nullptr;
+    if (has_pos) {
+        float *d_r = tmp.upload(r, (size_t)E * 128);
+        d_rhat = tmp.alloc<float>((size_t)E * 128);
+        if (E > 0) {
+            k_standardize<<<(E + NWARP - 1) / NWARP, NT, 0, e->stream>>>(d_r, d_rhat, E);
+            count_launch(e);
+        }
+    }
+    if (!d_x || !d_out || !d_kv || !d_src) return fail(INFGEN_ERR_CUDA, "temporary allocation failed");
+    const int saved_tile = e->row_tile;
+    e->row_tile = n_dst > 512 ? 16 : 4;
+    NodeArgs na;
+    memset(&na, 0, sizeof(na));
+    na.rows = flat_rows(n_dst); na.x_in = d_x; na.has_pre = 1; na.pre = w; na.pre_kv = bip ? 0 : 1;
+    na.q_out = d_q; na.s_out = d_s; na.qr_out = d_qr; na.kv_out = d_kv; na.kv_ring = 0;
+    int rc = launch_node(e, na, n_dst);
+    if (rc == 0 && bip) {
+        float *d_xs = tmp.upload(x_src, (size_t)n_src * 128);
+        KvArgs ka;
+        memset(&ka, 0, sizeof(ka));
+        ka.n = n_src; ka.x = d_xs; ka.w[0] = w; ka.out[0] = d_kv;
+        k_kv_project<16><<<dim3((n_src + 15) / 16, 1), NT, 0, e->stream>>>(ka);
+        count_launch(e);
+    }
+    if (rc == 0) {
+        AttnArgs aa;
+        memset(&aa, 0, sizeof(aa));
+        aa.rows = flat_rows(n_dst); aa.q = d_q; aa.qr = d_qr; aa.kv = d_kv; aa.cnt = d_cnt; aa.start = d_start;
+        aa.src = d_src; aa.rhat = d_rhat; aa.has_pos = has_pos; aa.max_deg = max_deg;
+        aa.agg = d_agg; aa.ragg = d_ragg; aa.sal = d_sal; aa.err = e->d_err;
+        rc = launch_attn(e, aa);
+    }
+    if (rc == 0) {
+        memset(&na, 0, sizeof(na));
+        na.rows = flat_rows(n_dst); na.has_post = 1; na.post = w; na.x_in = d_x; na.s_in = d_s;
+        na.agg = d_agg; na.ragg = d_ragg; na.sal = d_sal; na.x_out = d_out; na.has_pre = 0;
+        rc = launch_node(e, na, n_dst);
+    }
+    e->row_tile = saved_tile;
+    RET(rc);
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(out, d_out, (size_t)n_dst * 128 * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int32_t infgen_op_fourier_embedding(infgen_engine *e, const char *name, const float *x, int32_t n, int32_t dim,
+                                    const float *cat, float *out) {
+    if (!e || !name || !x || !out) return fail(INFGEN_ERR_INVALID_ARG, "null argument");
+    std::string p(name);
+    if (g_index.find(p + ".freqs") == g_index.end()) return fail(INFGEN_ERR_INVALID_ARG, "unknown embedding '%s'", name);
+    if (g_layout[g_index[p + ".freqs"]].numel != dim * 64) return fail(INFGEN_ERR_INVALID_ARG, "'%s' has a different input_dim", name);
+    CK(cudaStreamSynchronize(e->stream));
+    TmpDev tmp;
+    FourierArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.n_slots = n; fa.raw = tmp.upload(x, (size_t)n * dim); fa.w = make_fourier(e, p, dim);
+    fa.cat_tab = cat ? tmp.upload(cat, (size_t)n * 128) : nullptr;
+    float *d_out = tmp.alloc<float>((size_t)n * 128);
+    fa.out = d_out; fa.normalize = 0;
+    RET(launch_fourier(e, fa, dim));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(out, d_out, (size_t)n * 128 * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int32_t infgen_op_mlp_embedding(infgen_engine *e, const char *name, const float *x, int32_t n, int32_t dim,
+                                float *out) {
+    if (!e || !name || !x || !out) return fail(INFGEN_ERR_INVALID_ARG, "null argument");
+    std::string p(name);
+    if (g_index.find(p + ".w6") == g_index.end()) return fail(INFGEN_ERR_INVALID_ARG, "unknown embedding '%s'", name);
+    if (g_layout[g_index[p + ".w0"]].numel != gemm_numel(dim, 128)) return fail(INFGEN_ERR_INVALID_ARG, "'%s' has a different input_dim", name);
+    CK(cudaStreamSynchronize(e->stream));
+    TmpDev tmp;
+    MlpEmbArgs ma;
+    memset(&ma, 0, sizeof(ma));
+    ma.rows = flat_rows(n); ma.w = make_mlp_emb(e, p); ma.kin = dim; ma.k4 = (dim + 3) / 4;
+    ma.x = tmp.upload(x, (size_t)n * dim); ma.x_ld = dim;
+    float *d_out = tmp.alloc<float>((size_t)n * 128);
+    ma.out = d_out; ma.out_ld = 128;
+    if (ma.k4 > 128) return fail(INFGEN_ERR_INVALID_ARG, "input_dim %d too large", dim);
+    RET(launch_mlp_embed(e, ma));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(out, d_out, (size_t)n * 128 * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int32_t infgen_op_mlp_layer(infgen_engine *e, const char *name, const float *x, int32_t n, float *out) {
+    if (!e || !name || !x || !out) return fail(INFGEN_ERR_INVALID_ARG, "null argument");
+    std::string p(name);
+    if (g_index.find(p + ".w3") == g_index.end() || g_index.find(p + ".ln.g") == g_index.end())
+        return fail(INFGEN_ERR_INVALID_ARG, "unknown head '%s'", name);
+    if (g_layout[g_index[p + ".w0"]].numel != gemm_numel(128, 128)) return fail(INFGEN_ERR_INVALID_ARG, "'%s' does not take 128 inputs", name);
+    const int n_pad = (int)g_layout[g_index[p + ".b3"]].numel;
+    int n_out = n_pad;
+    if (p == "state_predict_head" || p == "seed_type_predict_head" || p == "seed_shape_predict_head") n_out = 3;
+    else if (p == "seed_state_predict_head" || p == "seed_offset_xy_predict_head") n_out = 2;
+    else if (p == "seed_heading_rel_token_predict_head") n_out = ANGLE_SIZE;
+    else if (p == "token_predict_head") n_out = TOKEN_SIZE;
+    else n_out = GRID_SIZE;
+    CK(cudaStreamSynchronize(e->stream));
+    TmpDev tmp;
+    MlpLayerArgs la;
+    memset(&la, 0, sizeof(la));
+    la.n = n; la.x = tmp.upload(x, (size_t)n * 128); la.w = make_head(e, p, 128, n_out);
+    float *d_out = tmp.alloc<float>((size_t)n * n_out);
+    la.out = d_out;
+    k_mlp_layer<<<dim3((n + HM - 1) / HM, std::min(la.w.n_pad / 128, 16)), NT, 0, e->stream>>>(la);
+    CKL(); count_launch(e);
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(out, d_out, (size_t)n * n_out * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,227 @@
+"""Host-side setup and read-back of `InfGenAgentDecoder.inference` (reference infgen/modules/agent_decoder.py).
+
+What stays on the host is what the reference also does once per scene outside the decode loop:
+  * row filtering, padding to the rollout horizon and the history masks      agent_decoder.py:1609-1657, 1695-1719
+  * assembling the output dict from the device results                         agent_decoder.py:2303-2389
+Everything inside the `for t in range(...)` loop (:1740-2301) runs in libinfgen_b200.so.
+"""
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+import numpy as np
+import torch
+
+from .config import DecoderConfig, AGENT_SHAPE, STATE_TOKEN
+
+INVALID, VALID, ENTER, EXIT = (STATE_TOKEN[k] for k in ('invalid', 'valid', 'enter', 'exit'))
+
+
+@dataclass
+class SceneHost:
+    """One scene after the reference's setup stage, history columns only (numpy, CPU)."""
+    n_rows: int
+    ego_row: int
+    n_cols: int                 # T
+    n_iters: int                # S
+    n_rec: int                  # num_recurrent_steps_val
+    pos_hist: np.ndarray        # [A, HC, 2] f32
+    head_hist: np.ndarray       # [A, HC]
+    state_hist: np.ndarray      # [A, HC] i32
+    token_hist: np.ndarray      # [A, HC] i32
+    grid_hist: np.ndarray       # [A, HC] i32
+    tsrc_hist: np.ndarray       # [A, HC] u8
+    interact_hist: np.ndarray   # [A, HC] u8
+    type: np.ndarray            # [A] i32
+    shape: np.ndarray           # [A, 3] f32
+    pt_pos: np.ndarray          # [P, 2]
+    pt_ori: np.ndarray          # [P]
+    x_pt: np.ndarray            # [P, 128]
+    # kept for the output dict
+    agent_id: torch.Tensor
+    valid_mask: torch.Tensor
+    gt_traj: torch.Tensor
+    pred_shape: torch.Tensor
+    pos0: torch.Tensor          # position[:, 0, :2]
+    head0: torch.Tensor         # heading[:, 0]
+    hist_state_full: torch.Tensor
+
+
+def _t(x):
+    return x if isinstance(x, torch.Tensor) else torch.as_tensor(x)
+
+
+def prepare_scene(data: Dict, map_enc: Dict, cfg: DecoderConfig) -> SceneHost:
+    """agent_decoder.py:1609-1657 (filter, pad, zero the future) and :1695-1719 (history masks)."""
+    ag = data['agent']
+    HC, nh = cfg.hist_cols, cfg.num_historical_steps
+    state_all = _t(ag['state_idx']).cpu()
+    filt = state_all[:, HC - 1] != INVALID
+    eval_mask = _t(ag['valid_mask']).cpu()[filt, nh - 1]
+    valid = _t(ag['raw_agent_valid_mask']).cpu()[filt].clone()
+    pos = _t(ag['token_pos']).cpu()[filt].float()
+    token = _t(ag['token_idx']).cpu()[filt].long()
+    state = state_all[filt].long()
+    head = _t(ag['token_heading']).cpu()[filt].float()
+    shape = _t(ag['shape']).cpu()[filt].float()
+    type_a = _t(ag['type']).cpu()[filt].long()
+    grid = _t(ag['grid_token_idx']).cpu()[filt].long()
+    position = _t(ag['position']).cpu()
+    n_rec = cfg.num_recurrent_steps_val
+    if n_rec == -1:
+        n_rec = position.shape[1] - nh
+    A, T0 = state.shape
+    T = (n_rec + nh) // cfg.shift
+    if T < T0:
+        raise ValueError('horizon shorter than the scene is unsupported by the reference (agent_decoder.py:1638)')
+    if A < 1:
+        raise ValueError('scene has no agent valid at the current step')
+    if T > T0:
+        valid = torch.cat([valid, torch.ones(A, T - T0, dtype=torch.bool)], 1)
+    av0 = int(_t(ag['av_index']).reshape(-1)[0])
+    av = av0 - int((~filt[:av0]).sum())
+    valid[:, HC:] = True
+    valid[~eval_mask] = False
+
+    # history masks: only the first HC columns can differ from "all true" (agent_decoder.py:1695-1719)
+    hstate = state[:, :HC].clone()
+    hvalid = valid[:, :HC].clone()
+    is_bos, is_eos = hstate == ENTER, hstate == EXIT
+    bos = torch.where(is_bos.any(1), is_bos.long().argmax(1), torch.tensor(0))
+    eos = torch.where(is_eos.any(1), is_eos.long().argmax(1), torch.tensor(T - 1))
+    col = torch.arange(HC)[None].expand(A, HC)
+    motion_mask = (col > bos[:, None]) & (col <= eos[:, None])
+    motion_mask[:, nh // cfg.shift:] = False
+    temporal_mask = torch.ones(A, HC, dtype=torch.bool)
+    temporal_mask[motion_mask] = hvalid[motion_mask]
+    interact_mask = torch.ones(A, HC, dtype=torch.bool)
+    non_motion = ~motion_mask
+    non_motion[:, nh // cfg.shift:] = False
+    interact_mask[non_motion] = False
+    interact_mask[hstate == ENTER] = True
+    interact_mask[av] = True
+    tsrc = temporal_mask & (col >= bos[:, None])          # _build_temporal_edge :547-552
+
+    f32 = lambda t: np.ascontiguousarray(t.numpy().astype(np.float32))
+    i32 = lambda t: np.ascontiguousarray(t.numpy().astype(np.int32))
+    u8 = lambda t: np.ascontiguousarray(t.numpy().astype(np.uint8))
+    pt_pos = _t(data['pt_token']['position']).cpu().float()[:, :2]
+    return SceneHost(
+        n_rows=A, ego_row=av, n_cols=T, n_iters=n_rec // cfg.shift, n_rec=n_rec,
+        pos_hist=f32(pos[:, :HC]), head_hist=f32(head[:, :HC]), state_hist=i32(hstate), token_hist=i32(token[:, :HC]),
+        grid_hist=i32(grid[:, :HC]), tsrc_hist=u8(tsrc), interact_hist=u8(interact_mask), type=i32(type_a),
+        shape=f32(shape[:, nh - 1]), pt_pos=f32(pt_pos), pt_ori=f32(_t(data['pt_token']['orientation']).cpu().float()),
+        x_pt=f32(_t(map_enc['x_pt']).cpu().float()),
+        agent_id=_t(ag['id']).cpu()[filt].clone(), valid_mask=valid, gt_traj=position[filt, nh:, :2].contiguous(),
+        pred_shape=shape[:, HC - 1].clone(), pos0=position[filt, 0, :2].clone(),
+        head0=_t(ag['heading']).cpu()[filt, 0].clone(), hist_state_full=state[:, :HC].clone())
+
+
+class HostBatch:
+    """Scenes packed into the capacity row space of `infgen_scene_batch` (pinned when CUDA is available)."""
+
+    def __init__(self, scenes: Sequence[SceneHost], cfg: DecoderConfig, scene_ids: Optional[Sequence[int]] = None,
+                 row_capacity: Optional[int] = None, pin: bool = True):
+        assert len(scenes) > 0
+        T, S = scenes[0].n_cols, scenes[0].n_iters
+        assert all(s.n_cols == T and s.n_iters == S for s in scenes), 'all scenes of a batch share the horizon'
+        HC = cfg.hist_cols
+        cap = row_capacity or max(s.n_rows for s in scenes)
+        cap = (cap + 3) // 4 * 4
+        ns = len(scenes)
+        R = ns * cap
+        P = sum(s.pt_pos.shape[0] for s in scenes)
+        pin = pin and torch.cuda.is_available()
+
+        def buf(shape, dtype):
+            t = torch.zeros(shape, dtype=dtype)
+            return t.pin_memory() if pin else t
+        self.n_scenes, self.cap, self.T, self.S, self.R, self.P = ns, cap, T, S, R, P
+        self.n_rows = buf((ns,), torch.int32)
+        self.ego_row = buf((ns,), torch.int32)
+        self.scene_id = buf((ns,), torch.int32)
+        self.pos_hist = buf((R, HC, 2), torch.float32)
+        self.head_hist = buf((R, HC), torch.float32)
+        self.state_hist = buf((R, HC), torch.int32)
+        self.token_hist = buf((R, HC), torch.int32)
+        self.grid_hist = buf((R, HC), torch.int32)
+        self.tsrc_hist = buf((R, HC), torch.uint8)
+        self.interact_hist = buf((R, HC), torch.uint8)
+        self.type = buf((R,), torch.int32)
+        self.shape = buf((R, 3), torch.float32)
+        self.pt_ptr = buf((ns + 1,), torch.int32)
+        self.pt_pos = buf((max(P, 1), 2), torch.float32)
+        self.pt_ori = buf((max(P, 1),), torch.float32)
+        self.x_pt = buf((max(P, 1), 128), torch.float32)
+        p0 = 0
+        for b, s in enumerate(scenes):
+            r0, n = b * cap, s.n_rows
+            self.n_rows[b], self.ego_row[b] = n, s.ego_row
+            self.scene_id[b] = scene_ids[b] if scene_ids is not None else b
+            for name in ('pos_hist', 'head_hist', 'state_hist', 'token_hist', 'grid_hist', 'tsrc_hist',
+                         'interact_hist', 'type', 'shape'):
+                getattr(self, name)[r0:r0 + n] = torch.from_numpy(getattr(s, name))
+            np_ = s.pt_pos.shape[0]
+            self.pt_ptr[b + 1] = p0 + np_
+            self.pt_pos[p0:p0 + np_] = torch.from_numpy(s.pt_pos)
+            self.pt_ori[p0:p0 + np_] = torch.from_numpy(s.pt_ori)
+            self.x_pt[p0:p0 + np_] = torch.from_numpy(s.x_pt)
+            p0 += np_
+        # result buffers
+        NR = max(5 * S, 1)
+        self.out_pos = buf((R, T, 2), torch.float32)
+        self.out_head = buf((R, T), torch.float32)
+        self.out_pred_traj = buf((R, NR, 2), torch.float32)
+        self.out_pred_head = buf((R, NR), torch.float32)
+        self.out_pred_state = buf((R, NR), torch.float32)
+        self.out_next_token = buf((R, T), torch.int32)
+        self.out_next_state = buf((R, T), torch.int32)
+        self.out_hist_traj = buf((R, HC * 5, 2), torch.float32)
+        self.out_hist_head = buf((R, HC * 5), torch.float32)
+
+    def h2d_bytes(self) -> int:
+        names = ('n_rows', 'ego_row', 'scene_id', 'pos_hist', 'head_hist', 'state_hist', 'token_hist', 'grid_hist',
+                 'tsrc_hist', 'interact_hist', 'type', 'shape', 'pt_ptr', 'pt_pos', 'pt_ori', 'x_pt')
+        return sum(getattr(self, n).numel() * getattr(self, n).element_size() for n in names)
+
+    def d2h_bytes(self) -> int:
+        names = ('out_pos', 'out_head', 'out_pred_traj', 'out_pred_head', 'out_pred_state', 'out_next_token',
+                 'out_next_state', 'out_hist_traj', 'out_hist_head')
+        return sum(getattr(self, n).numel() * getattr(self, n).element_size() for n in names)
+
+
+def assemble_outputs(batch: HostBatch, scenes: Sequence[SceneHost], cfg: DecoderConfig) -> List[Dict]:
+    """agent_decoder.py:2303-2389: the per-scene output dict (keys/dtypes/shapes of the reference; motion stage)."""
+    outs = []
+    nh, HC = cfg.num_historical_steps, cfg.hist_cols
+    for b, s in enumerate(scenes):
+        r0, n = b * batch.cap, s.n_rows
+        sl = slice(r0, r0 + n)
+        n_rec = s.n_rec
+        pred_traj = torch.zeros(n, nh + n_rec, 2)
+        pred_head = torch.zeros(n, nh + n_rec)
+        pred_state = torch.zeros(n, nh + n_rec)
+        pred_traj[:, 0] = s.pos0
+        pred_head[:, 0] = s.head0
+        pred_traj[:, 1:nh] = batch.out_hist_traj[sl]
+        pred_head[:, 1:nh] = batch.out_hist_head[sl]
+        pred_state[:, 1:nh] = s.hist_state_full.repeat_interleave(cfg.shift, dim=1).float()
+        if n_rec:
+            pred_traj[:, nh:] = batch.out_pred_traj[sl, :n_rec]
+            pred_head[:, nh:] = batch.out_pred_head[sl, :n_rec]
+            pred_state[:, nh:] = batch.out_pred_state[sl, :n_rec]
+        pred_valid = (pred_state != INVALID) & (pred_state != ENTER)
+        type_a = torch.from_numpy(s.type).long()
+        eval_shape = torch.zeros_like(s.pred_shape)
+        for ti, key in enumerate(('vehicle', 'pedstrain', 'cyclist')):
+            eval_shape[type_a == ti] = torch.tensor(AGENT_SHAPE[key])
+        ncol = HC + s.n_iters
+        outs.append({
+            'ego_index': s.ego_row, 'agent_id': s.agent_id, 'valid_mask': s.valid_mask,
+            'pos_a': batch.out_pos[sl].clone(), 'head_a': batch.out_head[sl].clone(), 'gt_traj': s.gt_traj,
+            'pred_traj': pred_traj, 'pred_head': pred_head, 'pred_type': type_a.clone(), 'pred_state': pred_state,
+            'pred_z': torch.zeros_like(pred_traj[..., 0]), 'pred_shape': s.pred_shape, 'eval_shape': eval_shape,
+            'pred_valid': pred_valid,
+            'next_token_idx': batch.out_next_token[sl, :ncol].long(),
+            'next_state_idx': batch.out_next_state[sl, :ncol].long(),
+            'agent_labels': [], 'log_message': 'No agents inserted!',
+        })
+    return outs

@@ -154,3 +154,124 @@ def make_state_dict(seed: int = 0, perturb: bool = True) -> Dict[str, torch.Tens
             for leaf in ('weight', 'bias'):
                 sd[f'{stack}.{i}.attn_prenorm_x_dst.{leaf}'] = sd[f'{stack}.{i}.attn_prenorm_x_src.{leaf}'].clone()
     return sd
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# packing `state_dict()` into the library's blob (layout owned by csrc/engine.cu: build_layout)
+# ----------------------------------------------------------------------------------------------------------------
+def _np(t) -> np.ndarray:
+    return t.detach().cpu().numpy().astype(np.float32) if hasattr(t, 'detach') else np.asarray(t, dtype=np.float32)
+
+
+def gemm_pack(weight: np.ndarray, n_pad: int = None) -> np.ndarray:
+    """nn.Linear weight [N, K] -> K-major blocks [ceil(K/4)][N_pad][4] (zero padded), see csrc/common.cuh block_gemm."""
+    n, k = weight.shape
+    n_pad = n_pad or n
+    k4 = (k + 3) // 4
+    wt = np.zeros((k4 * 4, n_pad), dtype=np.float32)
+    wt[:k, :n] = weight.T
+    return np.ascontiguousarray(wt.reshape(k4, 4, n_pad).transpose(0, 2, 1)).reshape(-1)
+
+
+def _pad_vec(v: np.ndarray, n_pad: int) -> np.ndarray:
+    out = np.zeros(n_pad, dtype=np.float32)
+    out[:v.shape[0]] = v
+    return out
+
+
+def _pack_attention(out, sd, p, has_pos):
+    g = lambda k: _np(sd[f'{p}.{k}'])
+    for dst, src in (('ln_src', 'attn_prenorm_x_src'), ('ln_dst', 'attn_prenorm_x_dst'), ('ln_post', 'attn_postnorm'),
+                     ('ln_ffpre', 'ff_prenorm'), ('ln_ffpost', 'ff_postnorm')):
+        out[f'{p}.{dst}.g'], out[f'{p}.{dst}.b'] = g(f'{src}.weight'), g(f'{src}.bias')
+    out[f'{p}.w_qs'] = gemm_pack(np.concatenate([g('to_q.weight'), g('to_s.weight')]))
+    out[f'{p}.b_qs'] = np.concatenate([g('to_q.bias'), g('to_s.bias')])
+    out[f'{p}.w_kv'] = gemm_pack(np.concatenate([g('to_k.weight'), g('to_v.weight')]))
+    out[f'{p}.b_kv'] = np.concatenate([np.zeros(HIDDEN, np.float32), g('to_v.bias')])      # to_k has no bias
+    if has_pos:
+        out[f'{p}.w_kr'] = g('to_k_r.weight').reshape(-1)                                  # [out][in] row-major
+        out[f'{p}.ln_r.g'], out[f'{p}.ln_r.b'] = g('attn_prenorm_r.weight'), g('attn_prenorm_r.bias')
+        out[f'{p}.w_vr'] = gemm_pack(g('to_v_r.weight'))
+        out[f'{p}.b_vr'] = g('to_v_r.bias')
+    out[f'{p}.w_g'], out[f'{p}.b_g'] = gemm_pack(g('to_g.weight')), g('to_g.bias')
+    out[f'{p}.w_out'], out[f'{p}.b_out'] = gemm_pack(g('to_out.weight')), g('to_out.bias')
+    out[f'{p}.w_ff1'], out[f'{p}.b_ff1'] = gemm_pack(g('ff_mlp.0.weight')), g('ff_mlp.0.bias')
+    out[f'{p}.w_ff2'], out[f'{p}.b_ff2'] = gemm_pack(g('ff_mlp.3.weight')), g('ff_mlp.3.bias')
+
+
+def _pack_fourier(out, sd, p, dim):
+    g = lambda k: _np(sd[f'{p}.{k}'])
+    out[f'{p}.freqs'] = g('freqs.weight').reshape(-1)
+    for d in range(dim):
+        q = f'{p}.mlps.{d}'
+        out[f'{q}.w0'], out[f'{q}.b0'] = gemm_pack(g(f'mlps.{d}.0.weight')), g(f'mlps.{d}.0.bias')
+        out[f'{q}.ln.g'], out[f'{q}.ln.b'] = g(f'mlps.{d}.1.weight'), g(f'mlps.{d}.1.bias')
+        out[f'{q}.w3'], out[f'{q}.b3'] = gemm_pack(g(f'mlps.{d}.3.weight')), g(f'mlps.{d}.3.bias')
+    out[f'{p}.out_ln.g'], out[f'{p}.out_ln.b'] = g('to_out.0.weight'), g('to_out.0.bias')
+    out[f'{p}.w_out'], out[f'{p}.b_out'] = gemm_pack(g('to_out.2.weight')), g('to_out.2.bias')
+
+
+def _pack_mlp_embedding(out, sd, p):
+    g = lambda k: _np(sd[f'{p}.mlp.{k}'])
+    out[f'{p}.w0'], out[f'{p}.b0'] = gemm_pack(g('0.weight')), g('0.bias')
+    out[f'{p}.ln1.g'], out[f'{p}.ln1.b'] = g('1.weight'), g('1.bias')
+    out[f'{p}.w3'], out[f'{p}.b3'] = gemm_pack(g('3.weight')), g('3.bias')
+    out[f'{p}.ln4.g'], out[f'{p}.ln4.b'] = g('4.weight'), g('4.bias')
+    out[f'{p}.w6'], out[f'{p}.b6'] = gemm_pack(g('6.weight')), g('6.bias')
+
+
+def _pack_mlp_layer(out, sd, p):
+    g = lambda k: _np(sd[f'{p}.mlp.{k}'])
+    n_out = g('3.weight').shape[0]
+    n_pad = (n_out + 127) // 128 * 128
+    out[f'{p}.w0'], out[f'{p}.b0'] = gemm_pack(g('0.weight')), g('0.bias')
+    out[f'{p}.ln.g'], out[f'{p}.ln.b'] = g('1.weight'), g('1.bias')
+    out[f'{p}.w3'], out[f'{p}.b3'] = gemm_pack(g('3.weight'), n_pad), _pad_vec(g('3.bias'), n_pad)
+
+
+def packed_tensors(sd: Dict[str, torch.Tensor]) -> Dict[str, np.ndarray]:
+    """Every packed tensor of the library layout, keyed by the library's names."""
+    out: Dict[str, np.ndarray] = {}
+    for k in ('type_a_emb', 'state_a_emb', 'no_token_emb', 'bos_token_emb', 'invalid_offset_token_emb'):
+        out[k] = _np(sd[f'{k}.weight']).reshape(-1)
+    _pack_mlp_embedding(out, sd, 'shape_emb')
+    for name, dim in (('x_a_emb', 2), ('r_t_emb', 4), ('r_pt2a_emb', 3), ('r_a2a_emb', 3), ('r_pt2sa_emb', 3),
+                      ('r_a2sa_emb', 3)):
+        _pack_fourier(out, sd, name, dim)
+    for name in ('token_emb_veh', 'token_emb_ped', 'token_emb_cyc', 'token_emb_grid', 'fusion_emb'):
+        _pack_mlp_embedding(out, sd, name)
+    for stack, n, pos in (('t_attn_layers', NUM_LAYERS, True), ('pt2a_attn_layers', NUM_LAYERS, True),
+                          ('a2a_attn_layers', NUM_LAYERS, True), ('pt2sa_attn_layers', SEED_LAYERS, True),
+                          ('a2sa_attn_layers', SEED_LAYERS, True), ('occ2sa_attn_layers', SEED_LAYERS, False)):
+        for i in range(n):
+            _pack_attention(out, sd, f'{stack}.{i}', pos)
+    for name in ('token_predict_head', 'state_predict_head', 'seed_state_predict_head', 'seed_type_predict_head',
+                 'seed_shape_predict_head', 'seed_pos_rel_token_predict_head', 'seed_offset_xy_predict_head',
+                 'seed_agent_occ_embed', 'seed_heading_rel_token_predict_head', 'grid_agent_occ_head',
+                 'grid_pt_occ_head'):
+        _pack_mlp_layer(out, sd, name)
+    return out
+
+
+def pack_state_dict(sd: Dict[str, torch.Tensor], lib) -> np.ndarray:
+    """One float32 blob in the layout `lib` (libinfgen_b200.so) reports; raises if a tensor is missing or mis-sized.
+
+    `sd` uses the reference's `InfGenAgentDecoder.state_dict()` names (a full-model checkpoint's
+    `encoder.agent_encoder.` prefix is stripped by the caller).
+    """
+    tensors = packed_tensors(sd)
+    blob = np.zeros(int(lib.infgen_weight_blob_floats()), dtype=np.float32)
+    n = lib.infgen_weight_count()
+    for i in range(n):
+        name = lib.infgen_weight_name(i).decode()
+        if name not in tensors:
+            raise KeyError(f'library expects packed tensor {name!r} that the packer did not produce')
+        arr = np.ascontiguousarray(tensors[name], dtype=np.float32).reshape(-1)
+        numel, off = int(lib.infgen_weight_numel(name.encode())), int(lib.infgen_weight_offset(name.encode()))
+        if arr.size != numel:
+            raise ValueError(f'{name}: packed {arr.size} floats, library expects {numel}')
+        blob[off:off + numel] = arr
+    extra = set(tensors) - {lib.infgen_weight_name(i).decode() for i in range(n)}
+    if extra:
+        raise KeyError(f'packer produced tensors the library does not know: {sorted(extra)[:5]}')
+    return blob

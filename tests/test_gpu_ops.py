@@ -1,0 +1,97 @@
+"""Operator-level parity on the GPU: each CUDA operator (through the C ABI) against the oracle's restatement of the
+reference module it replaces (reference infgen/modules/layers.py).  Tolerance: 1e-3 relative / 1e-4 absolute fp32
+(BASELINE.json north_star: "within 1e-3 rel fp32")."""
+import numpy as np
+import pytest
+import torch
+
+from infgen_b200.weights import make_state_dict
+from infgen_b200.config import DecoderConfig
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-3, 1e-4
+
+
+@pytest.fixture(scope='module')
+def dec_and_sd():
+    from infgen_b200.agent_decoder import B200AgentDecoder
+    sd = make_state_dict(3)
+    dec = B200AgentDecoder(sd, DecoderConfig(disable_insertion=True), use_cuda_graph=False)
+    yield dec, sd
+    dec.close()
+
+
+def _close(a, b, what):
+    a, b = np.asarray(a), np.asarray(b)
+    err = np.abs(a - b)
+    tol = ATOL + RTOL * np.abs(b)
+    bad = err > tol
+    assert not bad.any(), (f'{what}: {bad.sum()}/{bad.size} elements out of tolerance, max abs err {err.max():.3e}, '
+                           f'first bad at {np.argwhere(bad)[0].tolist()} got {a[bad][0]} want {b[bad][0]}')
+
+
+@pytest.mark.parametrize('name,dim', [('shape_emb', 3), ('token_emb_veh', 8), ('token_emb_grid', 2), ('fusion_emb', 512)])
+def test_mlp_embedding(dec_and_sd, name, dim):
+    from infgen_b200 import ops
+    from oracle.agent_decoder_oracle import mlp_embedding
+    dec, sd = dec_and_sd
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(37, dim, generator=g) * 2.0
+    _close(ops.mlp_embedding(dec, name, x), mlp_embedding(sd, name, x), name)
+
+
+@pytest.mark.parametrize('name,dim,with_cat', [('x_a_emb', 2, True), ('r_t_emb', 4, False), ('r_pt2a_emb', 3, False),
+                                              ('r_a2a_emb', 3, False)])
+def test_fourier_embedding(dec_and_sd, name, dim, with_cat):
+    from infgen_b200 import ops
+    from oracle.agent_decoder_oracle import fourier_embedding
+    dec, sd = dec_and_sd
+    g = torch.Generator().manual_seed(2)
+    n = 75
+    x = torch.randn(n, dim, generator=g)
+    x[:, 0] = x[:, 0].abs() * 30.0          # distances up to tens of metres
+    x[::7] = -2.0                            # the invalid sentinels of agent_decoder.py:595-601
+    cat = torch.randn(n, 128, generator=g) * 0.1 if with_cat else None
+    _close(ops.fourier_embedding(dec, name, x, cat), fourier_embedding(sd, name, x, cat), name)
+
+
+@pytest.mark.parametrize('name,n_out', [('token_predict_head', 2048), ('state_predict_head', 3)])
+def test_mlp_layer(dec_and_sd, name, n_out):
+    from infgen_b200 import ops
+    from oracle.agent_decoder_oracle import mlp_layer
+    dec, sd = dec_and_sd
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(21, 128, generator=g)
+    _close(ops.mlp_layer(dec, name, x, n_out), mlp_layer(sd, name, x), name)
+
+
+def _random_graph(n_src, n_dst, max_deg, g, bipartite):
+    src, dst = [], []
+    for i in range(n_dst):
+        deg = int(torch.randint(0, max_deg + 1, (1,), generator=g))
+        if i % 5 == 0:
+            deg = 0                          # destinations without any edge (PyG: zero aggregation)
+        cand = torch.randperm(n_src, generator=g)[:deg].sort().values
+        for j in cand.tolist():
+            if not bipartite and j == i:
+                continue
+            src.append(j)
+            dst.append(i)
+    return torch.tensor([src, dst], dtype=torch.long)
+
+
+@pytest.mark.parametrize('layer,bipartite,n_dst,n_src,max_deg', [
+    ('t_attn_layers.0', False, 50, 50, 12), ('a2a_attn_layers.3', False, 64, 64, 63),
+    ('pt2a_attn_layers.5', True, 41, 300, 5), ('a2a_attn_layers.1', False, 600, 600, 20)])
+def test_attention_layer(dec_and_sd, layer, bipartite, n_dst, n_src, max_deg):
+    from infgen_b200 import ops
+    from oracle.agent_decoder_oracle import attention_layer
+    dec, sd = dec_and_sd
+    g = torch.Generator().manual_seed(4)
+    x_dst = torch.randn(n_dst, 128, generator=g)
+    x_src = torch.randn(n_src, 128, generator=g) if bipartite else x_dst
+    ei = _random_graph(n_src, n_dst, max_deg, g, bipartite)
+    r = torch.randn(ei.shape[1], 128, generator=g)
+    want = attention_layer(sd, layer, x_src, x_dst, r, ei[0], ei[1], bipartite)
+    got = ops.attention_layer(dec, layer, (x_src, x_dst) if bipartite else x_dst, r, ei)
+    _close(got, want, layer)
