@@ -129,7 +129,8 @@ int32_t infgen_set_sampler(infgen_engine *e, int32_t motion_beam_size, uint32_t 
 int32_t infgen_synchronize(infgen_engine *e);
 
 /* ---- the decode path: InfGenAgentDecoder.inference (agent_decoder.py:1605-2389) ------------------------------ */
-/* setup (:1609-1719): upload one batch, build per-scene caches (map K/V of the six pt2a layers, embeddings). */
+/* setup (:1609-1719): upload one batch, build per-scene caches (map K/V of the six pt2a layers, embeddings).
+ * `loc` applies to the per-row / per-map-token arrays; n_rows, ego_row, scene_id and pt_ptr are always host. */
 int32_t infgen_load_scenes(infgen_engine *e, const infgen_scene_batch *batch, int32_t loc);
 /* teacher forcing for parity tests: [R][S] tokens / states applied instead of the sampled ones (NULL = off). */
 int32_t infgen_set_forcing(infgen_engine *e, const int32_t *tokens, const int32_t *states, int32_t loc);
@@ -145,6 +146,13 @@ int32_t infgen_read(infgen_engine *e, const infgen_outputs *out, int32_t loc);
 int32_t infgen_iterations_done(infgen_engine *e);
 /* number of kernels this library launched (or replayed through graphs) since the engine was created */
 int64_t infgen_kernel_launches(infgen_engine *e);
+
+/* ---- per-kernel-class device timing for the roofline report (bench.py): CUDA events around every launch; turns
+ * graph replay off while enabled ------------------------------------------------------------------------------ */
+int32_t infgen_set_profile(infgen_engine *e, int32_t on);
+int32_t infgen_profile_class_count(void);
+const char *infgen_profile_class_name(int32_t cls);
+int32_t infgen_profile_read(infgen_engine *e, int32_t cls, double *total_ms, int64_t *count);
 
 /* ---- parity/debug taps (tests only): copy a named internal buffer to host; returns bytes written or <0 ------- */
 int64_t infgen_debug_read(infgen_engine *e, const char *name, void *dst, int64_t max_bytes);

@@ -67,6 +67,10 @@ SYMBOLS = {
     'infgen_read': (C.c_int32, [C.c_void_p, C.POINTER(Outputs), C.c_int32]),
     'infgen_iterations_done': (C.c_int32, [C.c_void_p]),
     'infgen_kernel_launches': (C.c_int64, [C.c_void_p]),
+    'infgen_set_profile': (C.c_int32, [C.c_void_p, C.c_int32]),
+    'infgen_profile_class_count': (C.c_int32, []),
+    'infgen_profile_class_name': (C.c_char_p, [C.c_int32]),
+    'infgen_profile_read': (C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     'infgen_debug_read': (C.c_int64, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
     'infgen_op_attention_layer': (C.c_int32, [C.c_void_p, C.c_char_p, c_f32p, C.c_int32, c_f32p, C.c_int32, c_f32p,
                                               c_i32p, c_i32p, c_f32p]),

@@ -223,7 +223,10 @@ __global__ void k_embed_inputs(const DecState s, int col_add) {
     s.state_idx[r] = st;
     const int g = s.grid[(size_t)r * T + col];
     s.grid_row[r] = g < 0 ? s.G : g;                                            // [-1] = invalid-offset row
-    s.cat_idx[r] = inv ? R : r;                                                 // row R = seed type + 0.1 shape
+    // row R = seed type + 0.1 shape.  The reference builds the categorical embeddings once, while every future
+    // column is still 'invalid' (agent_decoder.py:1653-1657, 458-470), and later only rewrites them for steps that
+    // turn invalid (:2235-2239): every generated column therefore carries the seed/0.1 row, valid or not.
+    s.cat_idx[r] = (inv || col >= s.HC) ? R : r;
 }
 
 // counter-based uniform in [0,1): mirrors oracle.agent_decoder_oracle.uniform01

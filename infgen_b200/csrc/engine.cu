@@ -130,8 +130,12 @@ struct DevBuf {
     size_t bytes = 0;
 };
 
+struct ProfRec { int cls; cudaEvent_t a, b; };
+
 struct infgen_engine {
     infgen_config cfg;
+    bool profile = false;
+    std::vector<ProfRec> prof;
     cudaStream_t stream = nullptr, own_stream = nullptr;
     float *blob = nullptr;
     float *grid_cells = nullptr, *vocab = nullptr;
@@ -239,10 +243,31 @@ static float *fbuf(infgen_engine *e, const char *name) { return (float *)e->bufs
 
 static inline void count_launch(infgen_engine *e) { if (!e->capturing) e->launches++; }
 
+// per-kernel-class device timing (bench.py roofline leg): event pairs around every launch, plain launches only
+enum KClass { KC_EDGE_BUILD, KC_FOURIER_T, KC_FOURIER_M, KC_FOURIER_A, KC_FOURIER_X, KC_FUSION, KC_NODE, KC_ATTN_T,
+              KC_ATTN_M, KC_ATTN_A, KC_HEADS, KC_ADVANCE, KC_MISC, KC_COUNT };
+static const char *KCLASS_NAME[KC_COUNT] = {"k_edge_build", "k_fourier<4>:temporal", "k_fourier<3>:map", "k_fourier<3>:agent",
+                                            "k_fourier<2>:x_a", "k_mlp_embed:fusion", "k_node_update", "k_edge_attn:temporal",
+                                            "k_edge_attn:map", "k_edge_attn:agent", "k_heads", "k_advance", "misc"};
+struct ProfScope {
+    infgen_engine *e;
+    bool on;
+    ProfScope(infgen_engine *e_, int cls) : e(e_), on(e_->profile && !e_->capturing) {
+        if (!on) return;
+        ProfRec r;
+        r.cls = cls;
+        cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+        cudaEventRecord(r.a, e->stream);
+        e->prof.push_back(r);
+    }
+    ~ProfScope() { if (on) cudaEventRecord(e->prof.back().b, e->stream); }
+};
+
 // ---------------------------------------------------------------------------------------------------------------
 // launch helpers
 // ---------------------------------------------------------------------------------------------------------------
 static int launch_node(infgen_engine *e, const NodeArgs &a, int n_rows_space) {
+    ProfScope ps(e, KC_NODE);
     if (e->row_tile == 16) {
         k_node_update<16><<<(n_rows_space + 15) / 16, NT, NodeSmem<16>::BYTES, e->stream>>>(a);
     } else {
@@ -252,16 +277,18 @@ static int launch_node(infgen_engine *e, const NodeArgs &a, int n_rows_space) {
     count_launch(e);
     return 0;
 }
-static int launch_attn(infgen_engine *e, const AttnArgs &a) {
+static int launch_attn(infgen_engine *e, const AttnArgs &a, int cls = KC_MISC) {
+    ProfScope ps(e, cls);
     size_t smem = (size_t)NWARP * a.max_deg * 8 * sizeof(float);
     k_edge_attn<<<(a.rows.n_total + NWARP - 1) / NWARP, NT, smem, e->stream>>>(a);
     CKL();
     count_launch(e);
     return 0;
 }
-static int launch_fourier(infgen_engine *e, const FourierArgs &a, int d) {
+static int launch_fourier(infgen_engine *e, const FourierArgs &a, int d, int cls = KC_MISC) {
     int grid = (a.n_slots + FM - 1) / FM;
     if (grid == 0) return 0;
+    ProfScope ps(e, cls);
     switch (d) {
         case 2: k_fourier<2><<<grid, NT, FOURIER_SMEM, e->stream>>>(a); break;
         case 3: k_fourier<3><<<grid, NT, FOURIER_SMEM, e->stream>>>(a); break;
@@ -272,9 +299,10 @@ static int launch_fourier(infgen_engine *e, const FourierArgs &a, int d) {
     count_launch(e);
     return 0;
 }
-static int launch_mlp_embed(infgen_engine *e, const MlpEmbArgs &a) {
+static int launch_mlp_embed(infgen_engine *e, const MlpEmbArgs &a, int cls = KC_MISC) {
     int grid = (a.rows.n_total + EM - 1) / EM;
     if (grid == 0) return 0;
+    ProfScope ps(e, cls);
     k_mlp_embed<<<grid, NT, mlp_embed_smem(a.k4), e->stream>>>(a);
     CKL();
     count_launch(e);
@@ -296,20 +324,23 @@ static RowSpace flat_rows(int n) {
 static int enqueue_embed_column(infgen_engine *e, int col_add) {
     DecState &s = e->st;
     const int R = e->R;
-    k_embed_inputs<<<(R + 127) / 128, 128, 0, e->stream>>>(s, col_add);
+    {
+        ProfScope ps(e, KC_MISC);
+        k_embed_inputs<<<(R + 127) / 128, 128, 0, e->stream>>>(s, col_add);
+    }
     CKL(); count_launch(e);
     FourierArgs fa;
     memset(&fa, 0, sizeof(fa));
     fa.n_slots = R; fa.cnt = s.n_rows; fa.stride = e->cap; fa.raw = s.xa_raw; fa.w = e->f_x;
     fa.cat_tab = fbuf(e, "cat_tab"); fa.cat_idx = s.cat_idx; fa.out = fbuf(e, "xa"); fa.normalize = 0;
-    RET(launch_fourier(e, fa, 2));
+    RET(launch_fourier(e, fa, 2, KC_FOURIER_X));
     MlpEmbArgs ma;
     memset(&ma, 0, sizeof(ma));
     ma.rows = scene_rows(e); ma.w = e->e_fusion; ma.kin = 512; ma.k4 = 128; ma.fusion = 1;
     ma.tok_tab = e->tok_tab; ma.tok_row = s.tok_row; ma.xa = fbuf(e, "xa"); ma.state_tab = e->state_emb;
     ma.state_idx = s.state_idx; ma.grid_tab = e->grid_tab; ma.grid_row = s.grid_row;
     ma.out = fbuf(e, "x"); ma.out_ld = 128;
-    RET(launch_mlp_embed(e, ma));
+    RET(launch_mlp_embed(e, ma, KC_FUSION));
     NodeArgs na;
     memset(&na, 0, sizeof(na));
     na.rows = scene_rows(e); na.has_post = 0; na.x_in = fbuf(e, "x");
@@ -345,7 +376,7 @@ static int enqueue_layers(infgen_engine *e, bool with_edges, int trace_iter) {
                     aa.kv = kv_a; aa.cnt = s.a_cnt; aa.start = s.a_start; aa.stride = 0;
                     aa.src = s.a_src; aa.rhat = fbuf(e, "rhat_a"); aa.max_deg = e->cap;
                 }
-                RET(launch_attn(e, aa));
+                RET(launch_attn(e, aa, kind == 0 ? KC_ATTN_T : kind == 1 ? KC_ATTN_M : KC_ATTN_A));
             }
             NodeArgs na;
             memset(&na, 0, sizeof(na));
@@ -377,18 +408,21 @@ static int enqueue_layers(infgen_engine *e, bool with_edges, int trace_iter) {
 static int enqueue_iteration(infgen_engine *e, int trace_iter) {
     DecState &s = e->st;
     const int R = e->R;
-    k_edge_build<<<e->n_scenes, NT, 0, e->stream>>>(s);
+    {
+        ProfScope ps(e, KC_EDGE_BUILD);
+        k_edge_build<<<e->n_scenes, NT, 0, e->stream>>>(s);
+    }
     CKL(); count_launch(e);
     FourierArgs fa;
     memset(&fa, 0, sizeof(fa));
     fa.normalize = 1;
     fa.n_slots = R * s.W; fa.cnt = s.t_cnt; fa.stride = s.W; fa.raw = s.t_raw; fa.w = e->f_t; fa.out = fbuf(e, "rhat_t");
-    RET(launch_fourier(e, fa, 4));
+    RET(launch_fourier(e, fa, 4, KC_FOURIER_T));
     fa.n_slots = R * s.max_m; fa.cnt = s.m_cnt; fa.stride = s.max_m; fa.raw = s.m_raw; fa.w = e->f_m; fa.out = fbuf(e, "rhat_m");
-    RET(launch_fourier(e, fa, 3));
+    RET(launch_fourier(e, fa, 3, KC_FOURIER_M));
     fa.n_slots = e->n_scenes * e->cap * e->cap; fa.cnt = s.a_total; fa.stride = e->cap * e->cap; fa.raw = s.a_raw;
     fa.w = e->f_a; fa.out = fbuf(e, "rhat_a");
-    RET(launch_fourier(e, fa, 3));
+    RET(launch_fourier(e, fa, 3, KC_FOURIER_A));
     RET(enqueue_layers(e, true, trace_iter));
     HeadArgs ha;
     memset(&ha, 0, sizeof(ha));
@@ -400,12 +434,21 @@ static int enqueue_iteration(infgen_engine *e, int trace_iter) {
         ha.trace_logits = fbuf(e, "trace_token_logits") + (size_t)trace_iter * R * e->cfg.token_size;
         ha.trace_state = fbuf(e, "trace_state_logits") + (size_t)trace_iter * R * 3;
     }
-    k_heads<<<dim3((R + HM - 1) / HM, NSLICE), NT, 0, e->stream>>>(ha);
+    {
+        ProfScope ps(e, KC_HEADS);
+        k_heads<<<dim3((R + HM - 1) / HM, NSLICE), NT, 0, e->stream>>>(ha);
+    }
     CKL(); count_launch(e);
-    k_advance<<<e->n_scenes, NT, 0, e->stream>>>(s);
+    {
+        ProfScope ps(e, KC_ADVANCE);
+        k_advance<<<e->n_scenes, NT, 0, e->stream>>>(s);
+    }
     CKL(); count_launch(e);
     RET(enqueue_embed_column(e, 1));
-    k_next_iter<<<1, 1, 0, e->stream>>>(s.col, s.iter);
+    {
+        ProfScope ps(e, KC_MISC);
+        k_next_iter<<<1, 1, 0, e->stream>>>(s.col, s.iter);
+    }
     CKL(); count_launch(e);
     return 0;
 }
@@ -525,6 +568,7 @@ int32_t infgen_destroy(infgen_engine *e) {
     cudaStreamSynchronize(e->stream);
     if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
     if (e->graph) cudaGraphDestroy(e->graph);
+    for (auto &r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto &kv : e->bufs)
         if (kv.second.p) cudaFree(kv.second.p);
     cudaFree(e->blob); cudaFree(e->grid_cells); cudaFree(e->vocab); cudaFree(e->tok_tab); cudaFree(e->grid_tab);
@@ -573,7 +617,6 @@ int32_t infgen_load_scenes(infgen_engine *e, const infgen_scene_batch *b, int32_
     const int HC = e->cfg.hist_cols;
     if (b->n_cols < HC + b->n_iters || b->n_iters < 0)
         return fail(INFGEN_ERR_INVALID_ARG, "n_cols %d < hist_cols %d + n_iters %d", b->n_cols, HC, b->n_iters);
-    if (loc != INFGEN_HOST) return fail(INFGEN_ERR_INVALID_ARG, "scene descriptors must be host memory (loc=0)");
     const int ns = b->n_scenes, cap = b->row_capacity, R = ns * cap, T = b->n_cols, S = b->n_iters;
     int sum = 0, mx = 0;
     for (int i = 0; i < ns; ++i) {
@@ -612,11 +655,12 @@ int32_t infgen_load_scenes(infgen_engine *e, const infgen_scene_batch *b, int32_
     RET(ensure_t(e, "tsrc_hist", (size_t)R * HC, &d_tsrc_h)); RET(ensure_t(e, "interact_hist", (size_t)R * HC, &d_int_h));
     const cudaMemcpyKind k = in_kind(loc);
     cudaStream_t st = e->stream;
-    CK(cudaMemcpyAsync(d_n_rows, b->n_rows, ns * sizeof(int), k, st));
-    CK(cudaMemcpyAsync(d_ego, b->ego_row, ns * sizeof(int), k, st));
-    CK(cudaMemcpyAsync(d_sid, b->scene_id, ns * sizeof(int), k, st));
+    // the small per-scene descriptors are always host memory (they are validated above)
+    CK(cudaMemcpyAsync(d_n_rows, b->n_rows, ns * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_ego, b->ego_row, ns * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_sid, b->scene_id, ns * sizeof(int), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_type, b->type, (size_t)R * sizeof(int), k, st));
-    CK(cudaMemcpyAsync(d_pt_ptr, b->pt_ptr, (ns + 1) * sizeof(int), k, st));
+    CK(cudaMemcpyAsync(d_pt_ptr, b->pt_ptr, (ns + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_state_h, b->state_hist, (size_t)R * HC * sizeof(int), k, st));
     CK(cudaMemcpyAsync(d_token_h, b->token_hist, (size_t)R * HC * sizeof(int), k, st));
     CK(cudaMemcpyAsync(d_grid_h, b->grid_hist, (size_t)R * HC * sizeof(int), k, st));
@@ -747,7 +791,7 @@ int32_t infgen_step(infgen_engine *e, int32_t n_iters) {
     if (!e->prefilled) return fail(INFGEN_ERR_STATE, "infgen_prefill has not run");
     if (n_iters < 0 || e->iters_done + n_iters > e->S)
         return fail(INFGEN_ERR_INVALID_ARG, "%d iterations requested, %d of %d already done", n_iters, e->iters_done, e->S);
-    const bool use_graph = e->cfg.use_cuda_graph && !e->cfg.trace;
+    const bool use_graph = e->cfg.use_cuda_graph && !e->cfg.trace && !e->profile;
     for (int i = 0; i < n_iters; ++i) {
         if (use_graph) {
             if (!e->graph_exec) {
@@ -807,6 +851,33 @@ int32_t infgen_read(infgen_engine *e, const infgen_outputs *o, int32_t loc) {
         CK(cudaMemcpy(&err, e->d_err, sizeof(int), cudaMemcpyDeviceToHost));
         if (err) return fail(INFGEN_ERR_CAPACITY, "an attention row exceeded its edge capacity");
     }
+    return 0;
+}
+
+static void prof_clear(infgen_engine *e) {
+    for (auto &r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    e->prof.clear();
+}
+int32_t infgen_set_profile(infgen_engine *e, int32_t on) {
+    if (!e) return fail(INFGEN_ERR_INVALID_ARG, "null engine");
+    CK(cudaStreamSynchronize(e->stream));
+    prof_clear(e);
+    e->profile = on != 0;
+    return 0;
+}
+int32_t infgen_profile_class_count(void) { return KC_COUNT; }
+const char *infgen_profile_class_name(int32_t cls) { return (cls >= 0 && cls < KC_COUNT) ? KCLASS_NAME[cls] : nullptr; }
+int32_t infgen_profile_read(infgen_engine *e, int32_t cls, double *total_ms, int64_t *count) {
+    if (!e || !total_ms || !count) return fail(INFGEN_ERR_INVALID_ARG, "null argument");
+    CK(cudaStreamSynchronize(e->stream));
+    double tot = 0; int64_t n = 0;
+    for (auto &r : e->prof) {
+        if (r.cls != cls) continue;
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, r.a, r.b));
+        tot += ms; n++;
+    }
+    *total_ms = tot; *count = n;
     return 0;
 }
 
