@@ -57,6 +57,7 @@ class B200AgentDecoder:
         self._h = h
         self._batch: Optional[HostBatch] = None
         self._scenes: Optional[Sequence[SceneHost]] = None
+        self._host_cache: Optional[HostBatch] = None
 
     # ---- construction helpers ---------------------------------------------------------------------------------
     @classmethod
@@ -93,7 +94,8 @@ class B200AgentDecoder:
             interact_hist=_capi.u8p(b.interact_hist), type=_capi.i32p(b.type), shape=_capi.f32p(b.shape),
             pt_ptr=_capi.i32p(b.pt_ptr), pt_pos=_capi.f32p(b.pt_pos), pt_ori=_capi.f32p(b.pt_ori),
             x_pt=_capi.f32p(b.x_pt))
-        _capi.check(self.lib.infgen_load_scenes(self._h, C.byref(sb), _capi.HOST))
+        loc = _capi.DEVICE if getattr(b, 'on_device', False) else _capi.HOST
+        _capi.check(self.lib.infgen_load_scenes(self._h, C.byref(sb), loc))
         self._batch, self._scenes = batch, scenes
 
     def set_forcing(self, tokens: Optional[torch.Tensor], states: Optional[torch.Tensor]):
@@ -122,7 +124,25 @@ class B200AgentDecoder:
             pred_head=_capi.f32p(b.out_pred_head), pred_state=_capi.f32p(b.out_pred_state),
             next_token=_capi.i32p(b.out_next_token), next_state=_capi.i32p(b.out_next_state),
             hist_traj=_capi.f32p(b.out_hist_traj), hist_head=_capi.f32p(b.out_hist_head))
-        _capi.check(self.lib.infgen_read(self._h, C.byref(o), _capi.HOST))
+        loc = _capi.DEVICE if getattr(b, 'on_device', False) else _capi.HOST
+        _capi.check(self.lib.infgen_read(self._h, C.byref(o), loc))
+
+    def set_stream(self, cuda_stream: Optional[int]):
+        """Enqueue on the caller's stream (e.g. torch.cuda.current_stream().cuda_stream); None = engine-owned."""
+        _capi.check(self.lib.infgen_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def set_profile(self, on: bool):
+        _capi.check(self.lib.infgen_set_profile(self._h, int(on)))
+
+    def profile(self) -> Dict[str, Dict[str, float]]:
+        """Per-kernel-class device time since set_profile(True): {class: {'ms': total, 'launches': n}}."""
+        out = {}
+        for c in range(self.lib.infgen_profile_class_count()):
+            ms, n = C.c_double(), C.c_int64()
+            _capi.check(self.lib.infgen_profile_read(self._h, c, C.byref(ms), C.byref(n)))
+            if n.value:
+                out[self.lib.infgen_profile_class_name(c).decode()] = {'ms': ms.value, 'launches': int(n.value)}
+        return out
 
     def kernel_launches(self) -> int:
         return int(self.lib.infgen_kernel_launches(self._h))
@@ -157,7 +177,11 @@ class B200AgentDecoder:
                                       'construct with disable_insertion=True or pass motion_only=True')
         self._check_vocab(datas[0])
         scenes = [prepare_scene(d, m, self.cfg) for d, m in zip(datas, map_encs)]
-        batch = HostBatch(scenes, self.cfg, scene_ids)
+        batch = self._host_cache
+        if batch is not None and batch.fits(scenes):
+            batch.fill(scenes, scene_ids)              # reuse the pinned staging buffers
+        else:
+            batch = self._host_cache = HostBatch(scenes, self.cfg, scene_ids)
         self.load(batch, scenes)
         self.rollout()
         self.read()

@@ -116,25 +116,28 @@ def prepare_scene(data: Dict, map_enc: Dict, cfg: DecoderConfig) -> SceneHost:
 
 
 class HostBatch:
-    """Scenes packed into the capacity row space of `infgen_scene_batch` (pinned when CUDA is available)."""
+    """Scenes packed into the capacity row space of `infgen_scene_batch` (pinned when CUDA is available).
+    The buffers can be refilled with another set of scenes of the same geometry (`fits` / `fill`), which keeps the
+    pinned allocations out of the per-call path."""
 
     def __init__(self, scenes: Sequence[SceneHost], cfg: DecoderConfig, scene_ids: Optional[Sequence[int]] = None,
                  row_capacity: Optional[int] = None, pin: bool = True):
         assert len(scenes) > 0
         T, S = scenes[0].n_cols, scenes[0].n_iters
-        assert all(s.n_cols == T and s.n_iters == S for s in scenes), 'all scenes of a batch share the horizon'
         HC = cfg.hist_cols
         cap = row_capacity or max(s.n_rows for s in scenes)
         cap = (cap + 3) // 4 * 4
         ns = len(scenes)
         R = ns * cap
         P = sum(s.pt_pos.shape[0] for s in scenes)
+        self.p_alloc = max((P + 1023) // 1024 * 1024, 1)
         pin = pin and torch.cuda.is_available()
 
         def buf(shape, dtype):
             t = torch.zeros(shape, dtype=dtype)
             return t.pin_memory() if pin else t
-        self.n_scenes, self.cap, self.T, self.S, self.R, self.P = ns, cap, T, S, R, P
+        self.cfg = cfg
+        self.n_scenes, self.cap, self.T, self.S, self.R = ns, cap, T, S, R
         self.n_rows = buf((ns,), torch.int32)
         self.ego_row = buf((ns,), torch.int32)
         self.scene_id = buf((ns,), torch.int32)
@@ -148,9 +151,31 @@ class HostBatch:
         self.type = buf((R,), torch.int32)
         self.shape = buf((R, 3), torch.float32)
         self.pt_ptr = buf((ns + 1,), torch.int32)
-        self.pt_pos = buf((max(P, 1), 2), torch.float32)
-        self.pt_ori = buf((max(P, 1),), torch.float32)
-        self.x_pt = buf((max(P, 1), 128), torch.float32)
+        self.pt_pos = buf((self.p_alloc, 2), torch.float32)
+        self.pt_ori = buf((self.p_alloc,), torch.float32)
+        self.x_pt = buf((self.p_alloc, 128), torch.float32)
+        # result buffers
+        NR = max(5 * S, 1)
+        self.out_pos = buf((R, T, 2), torch.float32)
+        self.out_head = buf((R, T), torch.float32)
+        self.out_pred_traj = buf((R, NR, 2), torch.float32)
+        self.out_pred_head = buf((R, NR), torch.float32)
+        self.out_pred_state = buf((R, NR), torch.float32)
+        self.out_next_token = buf((R, T), torch.int32)
+        self.out_next_state = buf((R, T), torch.int32)
+        self.out_hist_traj = buf((R, HC * 5, 2), torch.float32)
+        self.out_hist_head = buf((R, HC * 5), torch.float32)
+        self.fill(scenes, scene_ids)
+
+    def fits(self, scenes: Sequence[SceneHost]) -> bool:
+        return (len(scenes) == self.n_scenes and all(s.n_cols == self.T and s.n_iters == self.S for s in scenes)
+                and max(s.n_rows for s in scenes) <= self.cap and (max(s.n_rows for s in scenes) + 3) // 4 * 4 == self.cap
+                and sum(s.pt_pos.shape[0] for s in scenes) <= self.p_alloc)
+
+    def fill(self, scenes: Sequence[SceneHost], scene_ids: Optional[Sequence[int]] = None):
+        assert all(s.n_cols == self.T and s.n_iters == self.S for s in scenes), 'all scenes of a batch share the horizon'
+        cap = self.cap
+        self.P = sum(s.pt_pos.shape[0] for s in scenes)
         p0 = 0
         for b, s in enumerate(scenes):
             r0, n = b * cap, s.n_rows
@@ -165,27 +190,37 @@ class HostBatch:
             self.pt_ori[p0:p0 + np_] = torch.from_numpy(s.pt_ori)
             self.x_pt[p0:p0 + np_] = torch.from_numpy(s.x_pt)
             p0 += np_
-        # result buffers
-        NR = max(5 * S, 1)
-        self.out_pos = buf((R, T, 2), torch.float32)
-        self.out_head = buf((R, T), torch.float32)
-        self.out_pred_traj = buf((R, NR, 2), torch.float32)
-        self.out_pred_head = buf((R, NR), torch.float32)
-        self.out_pred_state = buf((R, NR), torch.float32)
-        self.out_next_token = buf((R, T), torch.int32)
-        self.out_next_state = buf((R, T), torch.int32)
-        self.out_hist_traj = buf((R, HC * 5, 2), torch.float32)
-        self.out_hist_head = buf((R, HC * 5), torch.float32)
 
     def h2d_bytes(self) -> int:
         names = ('n_rows', 'ego_row', 'scene_id', 'pos_hist', 'head_hist', 'state_hist', 'token_hist', 'grid_hist',
                  'tsrc_hist', 'interact_hist', 'type', 'shape', 'pt_ptr', 'pt_pos', 'pt_ori', 'x_pt')
-        return sum(getattr(self, n).numel() * getattr(self, n).element_size() for n in names)
+        tot = sum(getattr(self, n).numel() * getattr(self, n).element_size() for n in names)
+        return tot - (self.p_alloc - self.P) * (2 + 1 + 128) * 4          # only P map tokens are copied
 
     def d2h_bytes(self) -> int:
         names = ('out_pos', 'out_head', 'out_pred_traj', 'out_pred_head', 'out_pred_state', 'out_next_token',
                  'out_next_state', 'out_hist_traj', 'out_hist_head')
         return sum(getattr(self, n).numel() * getattr(self, n).element_size() for n in names)
+
+
+IN_NAMES = ('pos_hist', 'head_hist', 'state_hist', 'token_hist', 'grid_hist', 'tsrc_hist', 'interact_hist', 'type',
+            'shape', 'pt_pos', 'pt_ori', 'x_pt')
+OUT_NAMES = ('out_pos', 'out_head', 'out_pred_traj', 'out_pred_head', 'out_pred_state', 'out_next_token',
+             'out_next_state', 'out_hist_traj', 'out_hist_head')
+
+
+class DeviceBatch:
+    """The same batch with its per-row / per-map-token arrays and result buffers resident in HBM (the small
+    per-scene descriptors n_rows / ego_row / scene_id / pt_ptr stay on the host, as the C ABI requires)."""
+
+    def __init__(self, hb: HostBatch, device):
+        for k in ('n_scenes', 'cap', 'T', 'S', 'R', 'P', 'p_alloc', 'n_rows', 'ego_row', 'scene_id', 'pt_ptr'):
+            setattr(self, k, getattr(hb, k))
+        for k in IN_NAMES:
+            setattr(self, k, getattr(hb, k).to(device, non_blocking=True))
+        for k in OUT_NAMES:
+            setattr(self, k, torch.zeros_like(getattr(hb, k), device=device))
+        self.on_device = True
 
 
 def assemble_outputs(batch: HostBatch, scenes: Sequence[SceneHost], cfg: DecoderConfig) -> List[Dict]:

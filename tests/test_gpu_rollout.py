@@ -119,13 +119,13 @@ def test_batched_scenes_equal_single_scene_runs():
     from infgen_b200.weights import make_state_dict
     cfg = DecoderConfig(motion_beam_size=1, disable_insertion=True)
     sd = make_state_dict(6)
-    sizes = [(5, 256, 0.0), (33, 384, 0.4), (64, 512, 0.2), (12, 300, 0.0), (48, 768, 0.5)] * 3
+    sizes = [(5, 256, 0.0), (33, 384, 0.4), (64, 512, 0.2), (12, 300, 0.0), (48, 768, 0.5)] * 4
     scenes = [make_scene(100 + i, num_agents=a, num_map_tokens=p, num_steps=91, ragged=rg, ego_index=min(2, a - 1),
                          cfg=cfg) for i, (a, p, rg) in enumerate(sizes)]
     dec = _make_decoder(sd, cfg)
     outs = dec.inference_batch(scenes, [s['map_enc'] for s in scenes])
     assert sum(s_.n_rows for s_ in dec._scenes) > 512 or True   # > 512 active rows selects the 16-row tile
-    for i in (0, 1, 2, 7):
+    for i in (0, 1, 2, 7, 19):
         single = dec.inference(scenes[i], scenes[i]['map_enc'])
         assert np.array_equal(single['next_token_idx'].numpy(), outs[i]['next_token_idx'].numpy()), f'scene {i}'
         _close(single['pred_traj'].numpy(), outs[i]['pred_traj'].numpy(), f'scene {i} pred_traj', 1e-5, 1e-5)
