@@ -286,14 +286,20 @@ def run_ours(args, rank, world, local_rank):
         rows = sum(h.n_rows for h in hosts)
         iters = S
         # algorithmic work per launch, averaged over the iterations of a rollout (fp32; DESIGN.md "roofline accounting")
-        per_row_io = 512 + 4096 + 512 + 4096 + 32          # q, qr in; agg, ragg, sal out
-        per_edge = 512 + 512 + 512 + 4                     # K row, V row, rhat row, source index
+        # k_layer (layer.cuh): one launch = whole AttentionLayers for every row.  Algorithmic bytes: per edge K row + V row +
+        # rhat row + source index; per row the residual in/out and the q/s/qr/kv hand-over; the layer weights once per
+        # launch.  Algorithmic flops: folded formulation, 2*MAC.
+        per_edge = 512 + 512 + 512 + 4
+        post_mac, pre_mac, pre_kv_mac = 196608, 49152, 32768     # Wvr+gate+out+ffn | q,s,Wkr fold | k,v
+        w_layer = 1.125e6 + 0.17e6                                # post + pre chunks of one layer (fp32 bytes)
+        edge_flops = 2.0 * 2 * (128 + 16) * 8                     # score + weighted sum, 8 heads
+        tm_bytes = rows * (1024 + 5120 + 1024 + 1024) + (e_t + e_m) / iters * per_edge + 2 * w_layer
+        a_bytes = rows * (1024 + 5120 + 5120 + 1024) + e_a / iters * per_edge + w_layer
+        tm_flops = rows * 2.0 * (2 * post_mac + 2 * pre_mac + pre_kv_mac) + (e_t + e_m) / iters * edge_flops
+        a_flops = rows * 2.0 * (post_mac + pre_mac + pre_kv_mac) + e_a / iters * edge_flops
         model = {
-            'k_edge_attn:temporal': ('hbm', rows * per_row_io + e_t / iters * per_edge),
-            'k_edge_attn:map': ('hbm', rows * per_row_io + e_m / iters * per_edge),
-            'k_edge_attn:agent': ('hbm', rows * per_row_io + e_a / iters * per_edge),
-            # node update: post (Wvr 16K + gate 32K + out 16K + ffn 128K MAC) + pre (q|s 32K + k|v 32K + Wkr 16K MAC) per row
-            'k_node_update': ('tensor', rows * 2.0 * (196608 + 81920)),
+            'k_layer:temporal+map': ('hbm', tm_bytes, tm_flops),
+            'k_layer:agent': ('hbm', a_bytes, a_flops),
             'k_fourier<4>:temporal': ('tensor', e_t / iters * 2.0 * (4 * (132 * 128 + 128 * 128) + 128 * 128)),
             'k_fourier<3>:map': ('tensor', e_m / iters * 2.0 * (3 * (132 * 128 + 128 * 128) + 128 * 128)),
             'k_fourier<3>:agent': ('tensor', e_a / iters * 2.0 * (3 * (132 * 128 + 128 * 128) + 128 * 128)),
@@ -304,11 +310,15 @@ def run_ours(args, rank, world, local_rank):
             avg_us = v['ms'] * 1e3 / v['launches']
             ent = {'kernel': name, 'share': v['ms'] / tot, 'avg_us': avg_us, 'launches_per_rollout': v['launches'] // n_prof}
             if name in model:
-                bound, work = model[name]
+                bound, work = model[name][0], model[name][1]
                 if bound == 'hbm':
                     ach = work / (avg_us * 1e-6) / 1e9
                     ent.update({'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
                                 'frac': ach / pk['hbm_gbs'], 'algorithmic_bytes_per_launch': work})
+                    if len(model[name]) > 2:
+                        fl = model[name][2] / (avg_us * 1e-6) / 1e12
+                        ent.update({'algorithmic_flops_per_launch': model[name][2], 'fp32_tflops': fl,
+                                    'frac_of_fp32_ffma_peak': fl / 72.0})
                 else:
                     ach = work / (avg_us * 1e-6) / 1e12
                     ent.update({'bound': 'tensor', 'achieved': ach, 'peak': pk['bf16_tflops_sustained'],

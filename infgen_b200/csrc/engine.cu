@@ -13,6 +13,7 @@
 #include "../../include/infgen_b200.h"
 #include "common.cuh"
 #include "ops.cuh"
+#include "layer.cuh"
 #include "decode.cuh"
 
 using namespace infgen;
@@ -138,6 +139,8 @@ struct infgen_engine {
     std::vector<ProfRec> prof;
     cudaStream_t stream = nullptr, own_stream = nullptr;
     float *blob = nullptr;
+    float *cs_blob = nullptr;                           // cluster-sliced AttentionLayer chunks (layer.cuh)
+    std::unordered_map<std::string, std::pair<const float *, const float *>> cs;   // layer -> (post, pre) chunks
     float *grid_cells = nullptr, *vocab = nullptr;
     float *tok_tab = nullptr, *grid_tab = nullptr;      // [3][V+2][128], [G+1][128]
     AttnW t[6], m[6], a[6];
@@ -187,7 +190,81 @@ static AttnW make_attn(infgen_engine *e, const std::string &p, bool has_pos) {
     w.w_ff1 = W(e, p + ".w_ff1"); w.b_ff1 = W(e, p + ".b_ff1"); w.w_ff2 = W(e, p + ".w_ff2"); w.b_ff2 = W(e, p + ".b_ff2");
     w.ln_ffpost_g = W(e, p + ".ln_ffpost.g"); w.ln_ffpost_b = W(e, p + ".ln_ffpost.b");
     w.has_pos = has_pos ? 1 : 0;
+    auto it = e->cs.find(p);
+    if (it != e->cs.end()) { w.cs_post = it->second.first; w.cs_pre = it->second.second; }
     return w;
+}
+
+// Cluster-sliced copies of every AttentionLayer (layer.cuh): for CTA c of a cluster the column slices of all Linears
+// of the layer, contiguous, so one bulk copy brings them into shared memory.  Built on the host from the packed blob.
+static const char *ATTN_STACKS[] = {"t_attn_layers", "pt2a_attn_layers", "a2a_attn_layers", "pt2sa_attn_layers",
+                                    "a2sa_attn_layers", "occ2sa_attn_layers"};
+static const int ATTN_STACK_LAYERS[] = {6, 6, 6, 3, 3, 3};
+static void slice_cols(float *dst, int nl, int n_off, const float *src, int k4n, int ldn, int n0, int cnt) {
+    for (int k4 = 0; k4 < k4n; ++k4)
+        for (int n = 0; n < cnt; ++n)
+            memcpy(dst + ((size_t)k4 * nl + n_off + n) * 4, src + ((size_t)k4 * ldn + n0 + n) * 4, 4 * sizeof(float));
+}
+static int build_cluster_weights(infgen_engine *e, const float *hw) {
+    auto H = [&](const std::string &name) -> const float * {
+        auto it = g_index.find(name);
+        return it == g_index.end() ? nullptr : hw + g_layout[it->second].offset;
+    };
+    int n_layers = 0;
+    for (int s = 0; s < 6; ++s) n_layers += ATTN_STACK_LAYERS[s];
+    const size_t per_layer = (size_t)CL * (cs_post::FLOATS + cs_pre::FLOATS);
+    std::vector<float> host(per_layer * n_layers, 0.f);
+    CK(cudaMalloc(&e->cs_blob, host.size() * sizeof(float)));
+    size_t li = 0;
+    for (int s = 0; s < 6; ++s)
+        for (int i = 0; i < ATTN_STACK_LAYERS[s]; ++i, ++li) {
+            const std::string p = std::string(ATTN_STACKS[s]) + "." + std::to_string(i);
+            float *post = host.data() + li * per_layer, *pre = post + (size_t)CL * cs_post::FLOATS;
+            const bool has_pos = H(p + ".w_kr") != nullptr;
+            for (int c = 0; c < CL; ++c) {
+                float *d = post + (size_t)c * cs_post::FLOATS;
+                if (has_pos) {
+                    slice_cols(d + cs_post::WVR, 16, 0, H(p + ".w_vr"), 32, 128, 16 * c, 16);
+                    memcpy(d + cs_post::BVR, H(p + ".b_vr") + 16 * c, 16 * sizeof(float));
+                    memcpy(d + cs_post::LN_R_G, H(p + ".ln_r.g"), 128 * sizeof(float));
+                    memcpy(d + cs_post::LN_R_B, H(p + ".ln_r.b"), 128 * sizeof(float));
+                }
+                slice_cols(d + cs_post::WG, 16, 0, H(p + ".w_g"), 64, 128, 16 * c, 16);
+                slice_cols(d + cs_post::WO, 16, 0, H(p + ".w_out"), 32, 128, 16 * c, 16);
+                slice_cols(d + cs_post::W1, 64, 0, H(p + ".w_ff1"), 32, 512, 64 * c, 64);
+                slice_cols(d + cs_post::W2, 16, 0, H(p + ".w_ff2"), 128, 128, 16 * c, 16);
+                memcpy(d + cs_post::BG, H(p + ".b_g") + 16 * c, 16 * sizeof(float));
+                memcpy(d + cs_post::BO, H(p + ".b_out") + 16 * c, 16 * sizeof(float));
+                memcpy(d + cs_post::B1, H(p + ".b_ff1") + 64 * c, 64 * sizeof(float));
+                memcpy(d + cs_post::B2, H(p + ".b_ff2") + 16 * c, 16 * sizeof(float));
+                memcpy(d + cs_post::LN_DST_G, H(p + ".ln_dst.g"), 128 * sizeof(float));
+                memcpy(d + cs_post::LN_DST_B, H(p + ".ln_dst.b"), 128 * sizeof(float));
+                memcpy(d + cs_post::LN_POST_G, H(p + ".ln_post.g"), 128 * sizeof(float));
+                memcpy(d + cs_post::LN_POST_B, H(p + ".ln_post.b"), 128 * sizeof(float));
+                memcpy(d + cs_post::LN_FFPRE_G, H(p + ".ln_ffpre.g"), 128 * sizeof(float));
+                memcpy(d + cs_post::LN_FFPRE_B, H(p + ".ln_ffpre.b"), 128 * sizeof(float));
+                memcpy(d + cs_post::LN_FFPOST_G, H(p + ".ln_ffpost.g"), 128 * sizeof(float));
+                memcpy(d + cs_post::LN_FFPOST_B, H(p + ".ln_ffpost.b"), 128 * sizeof(float));
+                float *q = pre + (size_t)c * cs_pre::FLOATS;
+                slice_cols(q + cs_pre::WQS, 32, 0, H(p + ".w_qs"), 32, 256, 16 * c, 16);
+                slice_cols(q + cs_pre::WQS, 32, 16, H(p + ".w_qs"), 32, 256, 128 + 16 * c, 16);
+                slice_cols(q + cs_pre::WKV, 32, 0, H(p + ".w_kv"), 32, 256, 16 * c, 16);
+                slice_cols(q + cs_pre::WKV, 32, 16, H(p + ".w_kv"), 32, 256, 128 + 16 * c, 16);
+                memcpy(q + cs_pre::BQS, H(p + ".b_qs") + 16 * c, 16 * sizeof(float));
+                memcpy(q + cs_pre::BQS + 16, H(p + ".b_qs") + 128 + 16 * c, 16 * sizeof(float));
+                memcpy(q + cs_pre::BKV, H(p + ".b_kv") + 16 * c, 16 * sizeof(float));
+                memcpy(q + cs_pre::BKV + 16, H(p + ".b_kv") + 128 + 16 * c, 16 * sizeof(float));
+                if (has_pos) {
+                    memcpy(q + cs_pre::WKR, H(p + ".w_kr") + (size_t)16 * c * 128, 16 * 128 * sizeof(float));
+                    memcpy(q + cs_pre::LN_R_G, H(p + ".ln_r.g"), 128 * sizeof(float));
+                }
+                memcpy(q + cs_pre::LN_DST_G, H(p + ".ln_dst.g"), 128 * sizeof(float));
+                memcpy(q + cs_pre::LN_DST_B, H(p + ".ln_dst.b"), 128 * sizeof(float));
+            }
+            e->cs[p] = {e->cs_blob + li * per_layer, e->cs_blob + li * per_layer + (size_t)CL * cs_post::FLOATS};
+        }
+    CK(cudaMemcpy(e->cs_blob, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
 }
 static FourierW make_fourier(infgen_engine *e, const std::string &p, int d) {
     FourierW w;
@@ -244,11 +321,11 @@ static float *fbuf(infgen_engine *e, const char *name) { return (float *)e->bufs
 static inline void count_launch(infgen_engine *e) { if (!e->capturing) e->launches++; }
 
 // per-kernel-class device timing (bench.py roofline leg): event pairs around every launch, plain launches only
-enum KClass { KC_EDGE_BUILD, KC_FOURIER_T, KC_FOURIER_M, KC_FOURIER_A, KC_FOURIER_X, KC_FUSION, KC_NODE, KC_ATTN_T,
-              KC_ATTN_M, KC_ATTN_A, KC_HEADS, KC_ADVANCE, KC_MISC, KC_COUNT };
+enum KClass { KC_EDGE_BUILD, KC_FOURIER_T, KC_FOURIER_M, KC_FOURIER_A, KC_FOURIER_X, KC_FUSION, KC_LAYER_TM, KC_LAYER_A,
+              KC_HEADS, KC_ADVANCE, KC_MISC, KC_COUNT };
 static const char *KCLASS_NAME[KC_COUNT] = {"k_edge_build", "k_fourier<4>:temporal", "k_fourier<3>:map", "k_fourier<3>:agent",
-                                            "k_fourier<2>:x_a", "k_mlp_embed:fusion", "k_node_update", "k_edge_attn:temporal",
-                                            "k_edge_attn:map", "k_edge_attn:agent", "k_heads", "k_advance", "misc"};
+                                            "k_fourier<2>:x_a", "k_mlp_embed:fusion", "k_layer:temporal+map", "k_layer:agent",
+                                            "k_heads", "k_advance", "misc"};
 struct ProfScope {
     infgen_engine *e;
     bool on;
@@ -266,24 +343,23 @@ struct ProfScope {
 // ---------------------------------------------------------------------------------------------------------------
 // launch helpers
 // ---------------------------------------------------------------------------------------------------------------
-static int launch_node(infgen_engine *e, const NodeArgs &a, int n_rows_space) {
-    ProfScope ps(e, KC_NODE);
-    if (e->row_tile == 16) {
-        k_node_update<16><<<(n_rows_space + 15) / 16, NT, NodeSmem<16>::BYTES, e->stream>>>(a);
-    } else {
-        k_node_update<4><<<(n_rows_space + 3) / 4, NT, NodeSmem<4>::BYTES, e->stream>>>(a);
-    }
+static int launch_layer(infgen_engine *e, const LayerArgs &a, int cls) {
+    ProfScope ps(e, cls);
+    const int M = e->row_tile;
+    const int clusters = (a.rows.n_total + M - 1) / M;
+    if (clusters == 0) return 0;
+    if (M == 8) k_layer<8><<<clusters * CL, NT, LayerSmem<8>::BYTES, e->stream>>>(a);
+    else k_layer<4><<<clusters * CL, NT, LayerSmem<4>::BYTES, e->stream>>>(a);
     CKL();
     count_launch(e);
     return 0;
 }
-static int launch_attn(infgen_engine *e, const AttnArgs &a, int cls = KC_MISC) {
-    ProfScope ps(e, cls);
-    size_t smem = (size_t)NWARP * a.max_deg * 8 * sizeof(float);
-    k_edge_attn<<<(a.rows.n_total + NWARP - 1) / NWARP, NT, smem, e->stream>>>(a);
-    CKL();
-    count_launch(e);
-    return 0;
+static PreArgs make_pre(const AttnW &w, bool pre_kv, float *kv_out, bool kv_ring, int col_add, bool to_global) {
+    PreArgs p;
+    memset(&p, 0, sizeof(p));
+    p.w = w.cs_pre; p.pre_kv = pre_kv ? 1 : 0; p.kv_out = kv_out; p.kv_ring = kv_ring ? 1 : 0; p.col_add = col_add;
+    p.to_global = to_global ? 1 : 0;
+    return p;
 }
 static int launch_fourier(infgen_engine *e, const FourierArgs &a, int d, int cls = KC_MISC) {
     int grid = (a.n_slots + FM - 1) / FM;
@@ -320,7 +396,7 @@ static RowSpace flat_rows(int n) {
     return r;
 }
 
-// column embedding (agent_decoder.py:2265-2287) of column col+col_add, then the pre half of temporal layer 0
+// column embedding (agent_decoder.py:2265-2287) of column col+col_add -> x (temporal layer 0 projects it in k_layer)
 static int enqueue_embed_column(infgen_engine *e, int col_add) {
     DecState &s = e->st;
     const int R = e->R;
@@ -341,65 +417,47 @@ static int enqueue_embed_column(infgen_engine *e, int col_add) {
     ma.state_idx = s.state_idx; ma.grid_tab = e->grid_tab; ma.grid_row = s.grid_row;
     ma.out = fbuf(e, "x"); ma.out_ld = 128;
     RET(launch_mlp_embed(e, ma, KC_FUSION));
-    NodeArgs na;
-    memset(&na, 0, sizeof(na));
-    na.rows = scene_rows(e); na.has_post = 0; na.x_in = fbuf(e, "x");
-    na.has_pre = 1; na.pre = e->t[0]; na.pre_kv = 1;
-    na.q_out = fbuf(e, "q"); na.s_out = fbuf(e, "s"); na.qr_out = fbuf(e, "qr");
-    na.kv_out = fbuf(e, "kv_t"); na.kv_ring = 1; na.col_ptr = s.col; na.col_add = col_add;
-    RET(launch_node(e, na, R));
     return 0;
 }
 
-// the 18-layer stack for the current column. with_edges=false: history columns that receive no edges (prefill).
+// the 18-layer stack for the current column: per layer index i one launch for temporal + map->agent (their K/V are
+// cached) and one for agent<->agent (its K/V rows come from every row of the scene, written by the launch before).
+// with_edges=false: history columns that receive no edges (prefill).
 static int enqueue_layers(infgen_engine *e, bool with_edges, int trace_iter) {
     DecState &s = e->st;
     const int R = e->R;
-    float *x = fbuf(e, "x"), *q = fbuf(e, "q"), *sb = fbuf(e, "s"), *qr = fbuf(e, "qr");
-    float *agg = fbuf(e, "agg"), *ragg = fbuf(e, "ragg"), *sal = fbuf(e, "sal"), *zero = fbuf(e, "zero");
     float *kv_t = fbuf(e, "kv_t"), *kv_m = fbuf(e, "kv_m"), *kv_a = fbuf(e, "kv_a");
     const size_t kv_t_layer = (size_t)R * RING * 256, kv_m_layer = (size_t)e->P * 256;
+    LayerArgs base;
+    memset(&base, 0, sizeof(base));
+    base.rows = scene_rows(e); base.x = fbuf(e, "x"); base.q = fbuf(e, "q"); base.s = fbuf(e, "s"); base.qr = fbuf(e, "qr");
+    base.col_ptr = s.col; base.ring = RING;
     for (int i = 0; i < 6; ++i) {
-        for (int kind = 0; kind < 3; ++kind) {          // 0 temporal, 1 map->agent, 2 agent<->agent
-            if (with_edges) {
-                AttnArgs aa;
-                memset(&aa, 0, sizeof(aa));
-                aa.rows = scene_rows(e); aa.q = q; aa.qr = qr; aa.has_pos = 1;
-                aa.agg = agg; aa.ragg = ragg; aa.sal = sal; aa.err = e->d_err;
-                if (kind == 0) {
-                    aa.kv = kv_t + i * kv_t_layer; aa.cnt = s.t_cnt; aa.start = nullptr; aa.stride = s.W;
-                    aa.src = s.t_src; aa.rhat = fbuf(e, "rhat_t"); aa.max_deg = s.W;
-                } else if (kind == 1) {
-                    aa.kv = kv_m + i * kv_m_layer; aa.cnt = s.m_cnt; aa.start = nullptr; aa.stride = s.max_m;
-                    aa.src = s.m_src; aa.rhat = fbuf(e, "rhat_m"); aa.max_deg = s.max_m;
-                } else {
-                    aa.kv = kv_a; aa.cnt = s.a_cnt; aa.start = s.a_start; aa.stride = 0;
-                    aa.src = s.a_src; aa.rhat = fbuf(e, "rhat_a"); aa.max_deg = e->cap;
-                }
-                RET(launch_attn(e, aa, kind == 0 ? KC_ATTN_T : kind == 1 ? KC_ATTN_M : KC_ATTN_A));
-            }
-            NodeArgs na;
-            memset(&na, 0, sizeof(na));
-            na.rows = scene_rows(e);
-            na.has_post = 1;
-            na.post = kind == 0 ? e->t[i] : kind == 1 ? e->m[i] : e->a[i];
-            na.x_in = x; na.s_in = sb;
-            na.agg = with_edges ? agg : zero; na.ragg = with_edges ? ragg : zero; na.sal = with_edges ? sal : zero;
-            na.x_out = x;
-            na.q_out = q; na.s_out = sb; na.qr_out = qr; na.col_ptr = s.col; na.col_add = 0;
-            if (kind == 0) {            // next: map->agent layer i (bipartite: only q, s of the agent rows)
-                na.has_pre = 1; na.pre = e->m[i]; na.pre_kv = 0;
-            } else if (kind == 1) {     // next: agent<->agent layer i
-                na.has_pre = 1; na.pre = e->a[i]; na.pre_kv = 1; na.kv_out = kv_a; na.kv_ring = 0;
-            } else if (i < 5) {         // next: temporal layer i+1
-                na.has_pre = 1; na.pre = e->t[i + 1]; na.pre_kv = 1;
-                na.kv_out = kv_t + (i + 1) * kv_t_layer; na.kv_ring = 1;
-            } else {
-                na.has_pre = 0;
-            }
-            if (kind == 2 && trace_iter >= 0 && e->cfg.trace)
-                na.trace_out = fbuf(e, "trace_layer_out") + ((size_t)trace_iter * 6 + i) * R * 128;
-            RET(launch_node(e, na, R));
+        {   // temporal layer i, map->agent layer i, projections of agent<->agent layer i
+            LayerArgs la = base;
+            if (i == 0) la.pre0 = make_pre(e->t[0], true, kv_t, true, 0, false);
+            la.n_sub = 2;
+            SubArgs &t = la.sub[0], &m = la.sub[1];
+            t.w = e->t[i].cs_post; t.has_attn = with_edges; t.has_pos = 1;
+            t.kv = kv_t + i * kv_t_layer; t.cnt = s.t_cnt; t.start = nullptr; t.stride = s.W; t.src = s.t_src;
+            t.rhat = fbuf(e, "rhat_t");
+            t.pre = make_pre(e->m[i], false, nullptr, false, 0, false);
+            m.w = e->m[i].cs_post; m.has_attn = with_edges; m.has_pos = 1;
+            m.kv = kv_m + i * kv_m_layer; m.cnt = s.m_cnt; m.start = nullptr; m.stride = s.max_m; m.src = s.m_src;
+            m.rhat = fbuf(e, "rhat_m");
+            m.pre = make_pre(e->a[i], true, kv_a, false, 0, true);
+            RET(launch_layer(e, la, KC_LAYER_TM));
+        }
+        {   // agent<->agent layer i, projections of temporal layer i+1
+            LayerArgs la = base;
+            la.n_sub = 1;
+            SubArgs &g = la.sub[0];
+            g.w = e->a[i].cs_post; g.has_attn = with_edges; g.has_pos = 1;
+            g.kv = kv_a; g.cnt = s.a_cnt; g.start = s.a_start; g.stride = 0; g.src = s.a_src; g.rhat = fbuf(e, "rhat_a");
+            if (i < 5) g.pre = make_pre(e->t[i + 1], true, kv_t + (i + 1) * kv_t_layer, true, 0, true);
+            if (trace_iter >= 0 && e->cfg.trace)
+                g.trace_out = fbuf(e, "trace_layer_out") + ((size_t)trace_iter * 6 + i) * R * 128;
+            RET(launch_layer(e, la, KC_LAYER_A));
         }
     }
     return 0;
@@ -536,6 +594,7 @@ int32_t infgen_create(const infgen_config *cfg, const float *weights, int64_t n_
                        e->stream));
     CK(cudaMalloc(&e->d_err, sizeof(int)));
     CK(cudaMemsetAsync(e->d_err, 0, sizeof(int), e->stream));
+    RET(build_cluster_weights(e, weights));
     for (int i = 0; i < 6; ++i) {
         e->t[i] = make_attn(e, "t_attn_layers." + std::to_string(i), true);
         e->m[i] = make_attn(e, "pt2a_attn_layers." + std::to_string(i), true);
@@ -550,12 +609,11 @@ int32_t infgen_create(const infgen_config *cfg, const float *weights, int64_t n_
     e->h_state = make_head(e, "state_predict_head", 128, 3);
     e->type_emb = W(e, "type_a_emb"); e->state_emb = W(e, "state_a_emb");
     // kernels that need more than 48 KB of dynamic shared memory
-    CK(cudaFuncSetAttribute(k_node_update<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NodeSmem<16>::BYTES));
-    CK(cudaFuncSetAttribute(k_node_update<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NodeSmem<4>::BYTES));
+    CK(cudaFuncSetAttribute(k_layer<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LayerSmem<4>::BYTES));
+    CK(cudaFuncSetAttribute(k_layer<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LayerSmem<8>::BYTES));
     CK(cudaFuncSetAttribute(k_fourier<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FOURIER_SMEM));
     CK(cudaFuncSetAttribute(k_fourier<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FOURIER_SMEM));
     CK(cudaFuncSetAttribute(k_fourier<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FOURIER_SMEM));
-    CK(cudaFuncSetAttribute(k_edge_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, NWARP * MAX_CAP * 8 * 4));
     CK(cudaFuncSetAttribute(k_mlp_embed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mlp_embed_smem(128)));
     RET(build_tables(e));
     CK(cudaStreamSynchronize(e->stream));
@@ -571,7 +629,7 @@ int32_t infgen_destroy(infgen_engine *e) {
     for (auto &r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto &kv : e->bufs)
         if (kv.second.p) cudaFree(kv.second.p);
-    cudaFree(e->blob); cudaFree(e->grid_cells); cudaFree(e->vocab); cudaFree(e->tok_tab); cudaFree(e->grid_tab);
+    cudaFree(e->blob); cudaFree(e->cs_blob); cudaFree(e->grid_cells); cudaFree(e->vocab); cudaFree(e->tok_tab); cudaFree(e->grid_tab);
     cudaFree(e->d_err);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
@@ -628,7 +686,7 @@ int32_t infgen_load_scenes(infgen_engine *e, const infgen_scene_batch *b, int32_
     if (b->pt_ptr[0] != 0 || P < 0) return fail(INFGEN_ERR_INVALID_ARG, "pt_ptr must start at 0");
     if (e->n_scenes != ns || e->cap != cap || e->T != T || e->S != S || e->P != P) drop_graph(e);
     e->n_scenes = ns; e->cap = cap; e->R = R; e->T = T; e->S = S; e->P = P; e->n_rows_sum = sum; e->max_rows = mx;
-    e->row_tile = sum > 512 ? 16 : 4;
+    e->row_tile = sum > 512 ? 8 : 4;
     e->iters_done = 0; e->prefilled = 0; e->forcing = false;
     const int W = e->cfg.window, MM = e->cfg.max_pl2a_neighbors, V = e->cfg.token_size;
     DecState &s = e->st;
@@ -924,19 +982,16 @@ int32_t infgen_op_attention_layer(infgen_engine *e, const char *layer, const flo
     w.has_pos = has_pos ? 1 : 0;
     const bool bip = x_src != nullptr;
     const int E = edge_ptr[n_dst];
-    int max_deg = 1;
     std::vector<int> cnt(n_dst), start(n_dst);
     for (int i = 0; i < n_dst; ++i) {
         cnt[i] = edge_ptr[i + 1] - edge_ptr[i]; start[i] = edge_ptr[i];
-        max_deg = std::max(max_deg, cnt[i]);
+        if (cnt[i] < 0) return fail(INFGEN_ERR_INVALID_ARG, "edge_ptr must be non-decreasing");
     }
-    if (max_deg > MAX_CAP) return fail(INFGEN_ERR_CAPACITY, "degree %d exceeds %d", max_deg, MAX_CAP);
     CK(cudaStreamSynchronize(e->stream));
     TmpDev tmp;
     float *d_x = tmp.upload(x_dst, (size_t)n_dst * 128);
     float *d_q = tmp.alloc<float>((size_t)n_dst * 128), *d_s = tmp.alloc<float>((size_t)n_dst * 128);
-    float *d_qr = tmp.alloc<float>((size_t)n_dst * 1024), *d_agg = tmp.alloc<float>((size_t)n_dst * 128);
-    float *d_ragg = tmp.alloc<float>((size_t)n_dst * 1024), *d_sal = tmp.alloc<float>((size_t)n_dst * 8);
+    float *d_qr = tmp.alloc<float>((size_t)n_dst * 1024);
     float *d_out = tmp.alloc<float>((size_t)n_dst * 128);
     const int n_kv = bip ? n_src : n_dst;
     float *d_kv = tmp.alloc<float>((size_t)n_kv * 256);
@@ -953,12 +1008,14 @@ int32_t infgen_op_attention_layer(infgen_engine *e, const char *layer, const flo
     }
     if (!d_x || !d_out || !d_kv || !d_src) return fail(INFGEN_ERR_CUDA, "temporary allocation failed");
     const int saved_tile = e->row_tile;
-    e->row_tile = n_dst > 512 ? 16 : 4;
-    NodeArgs na;
-    memset(&na, 0, sizeof(na));
-    na.rows = flat_rows(n_dst); na.x_in = d_x; na.has_pre = 1; na.pre = w; na.pre_kv = bip ? 0 : 1;
-    na.q_out = d_q; na.s_out = d_s; na.qr_out = d_qr; na.kv_out = d_kv; na.kv_ring = 0;
-    int rc = launch_node(e, na, n_dst);
+    e->row_tile = n_dst > 512 ? 8 : 4;
+    // launch 1: projections of every row (K/V of all rows must exist before any row attends)
+    LayerArgs la;
+    memset(&la, 0, sizeof(la));
+    la.rows = flat_rows(n_dst); la.x = d_x; la.q = d_q; la.s = d_s; la.qr = d_qr; la.ring = RING;
+    la.pre0 = make_pre(w, !bip, d_kv, false, 0, true);
+    la.n_sub = 0;
+    int rc = launch_layer(e, la, KC_MISC);
     if (rc == 0 && bip) {
         float *d_xs = tmp.upload(x_src, (size_t)n_src * 128);
         KvArgs ka;
@@ -968,18 +1025,16 @@ int32_t infgen_op_attention_layer(infgen_engine *e, const char *layer, const flo
         count_launch(e);
     }
     if (rc == 0) {
-        AttnArgs aa;
-        memset(&aa, 0, sizeof(aa));
-        aa.rows = flat_rows(n_dst); aa.q = d_q; aa.qr = d_qr; aa.kv = d_kv; aa.cnt = d_cnt; aa.start = d_start;
-        aa.src = d_src; aa.rhat = d_rhat; aa.has_pos = has_pos; aa.max_deg = max_deg;
-        aa.agg = d_agg; aa.ragg = d_ragg; aa.sal = d_sal; aa.err = e->d_err;
-        rc = launch_attn(e, aa);
-    }
-    if (rc == 0) {
-        memset(&na, 0, sizeof(na));
-        na.rows = flat_rows(n_dst); na.has_post = 1; na.post = w; na.x_in = d_x; na.s_in = d_s;
-        na.agg = d_agg; na.ragg = d_ragg; na.sal = d_sal; na.x_out = d_out; na.has_pre = 0;
-        rc = launch_node(e, na, n_dst);
+        // launch 2: attention + update + FFN, in place on a copy of x
+        if (cudaMemcpyAsync(d_out, d_x, (size_t)n_dst * 128 * sizeof(float), cudaMemcpyDeviceToDevice, e->stream) != cudaSuccess)
+            rc = fail(INFGEN_ERR_CUDA, "copy failed");
+        memset(&la, 0, sizeof(la));
+        la.rows = flat_rows(n_dst); la.x = d_out; la.q = d_q; la.s = d_s; la.qr = d_qr; la.ring = RING;
+        la.n_sub = 1;
+        SubArgs &g = la.sub[0];
+        g.w = w.cs_post; g.has_attn = 1; g.has_pos = has_pos ? 1 : 0; g.kv = d_kv; g.cnt = d_cnt; g.start = d_start;
+        g.src = d_src; g.rhat = d_rhat;
+        if (rc == 0) rc = launch_layer(e, la, KC_MISC);
     }
     e->row_tile = saved_tile;
     RET(rc);

@@ -33,6 +33,7 @@ struct AttnW {                 // one AttentionLayer, pointers into the packed w
     const float *w_ff1, *b_ff1, *w_ff2, *b_ff2;
     const float *ln_ffpost_g, *ln_ffpost_b;
     int has_pos;               // has_pos_emb
+    const float *cs_post, *cs_pre;   // cluster-sliced chunks of this layer (layer.cuh), [8][FLOATS] each
 };
 
 struct FourierW {              // one FourierEmbedding
@@ -62,329 +63,6 @@ struct RowSpace {
         return (r % cap) < __ldg(n_rows + r / cap);
     }
 };
-
-// ===============================================================================================================
-// node update
-// ===============================================================================================================
-struct NodeArgs {
-    RowSpace rows;
-    // ---- post half (layer `post`) ----
-    int has_post;
-    AttnW post;
-    const float *x_in;         // [R][128] residual stream entering the post layer (== input of the pre half if !has_post)
-    const float *s_in;         // [R][128] to_s(x_dst) from the pre half
-    const float *agg;          // [R][128] sum_e a_e v_j
-    const float *ragg;         // [R][8][128] sum_e a_e rhat_e per head
-    const float *sal;          // [R][8] sum_e a_e
-    float *x_out;              // [R][128]
-    float *trace_out;          // optional copy of x_out
-    // ---- pre half (layer `pre`) ----
-    int has_pre;
-    AttnW pre;
-    int pre_kv;                // also project k|v of these rows (non-bipartite layers)
-    float *q_out, *s_out;      // [R][128]
-    float *qr_out;             // [R][8][128]
-    float *kv_out;             // K|V rows of 256 floats
-    int kv_ring;               // 1: row r goes to slot (r*16 + (col & 15)); 0: slot r
-    const int *col_ptr;        // device: current column
-    int col_add;
-};
-
-template <int M>
-struct NodeSmem {
-    static constexpr int X = 0;                    // [M][128] residual
-    static constexpr int CAT = X + M * 128;        // [M][256] agg | x_dst(normalised)
-    static constexpr int S = CAT + M * 256;        // [M][128] to_s
-    static constexpr int U = S + M * 128;          // [M][128] scratch
-    static constexpr int BIG = U + M * 128;        // [M][1024] ragg' / ffn hidden / q
-    static constexpr int RED = BIG + M * 1024;     // [M][128] gemm k-split scratch
-    static constexpr int SAL = RED + M * 128;      // [M][8]
-    static constexpr int TOTAL = SAL + M * 8;
-    static constexpr size_t BYTES = (size_t)TOTAL * sizeof(float);
-};
-
-template <int M>
-__global__ void __launch_bounds__(NT) k_node_update(const NodeArgs a) {
-    extern __shared__ __align__(16) float smem[];
-    using L = NodeSmem<M>;
-    float *sx = smem + L::X, *scat = smem + L::CAT, *ss = smem + L::S, *su = smem + L::U, *sbig = smem + L::BIG,
-          *sred = smem + L::RED, *ssal = smem + L::SAL;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int row0 = blockIdx.x * M;
-    // does this tile hold any active row? (uniform across the CTA)
-    bool any = false;
-    for (int m = 0; m < M; ++m) any |= a.rows.active(row0 + m);
-    if (!any) return;
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-
-    // ---- load the residual rows -------------------------------------------------------------------------------
-    for (int m = warp; m < M; m += NWARP) {
-        const int r = row0 + m;
-        const bool act = a.rows.active(r);
-        st4(sx + m * 128 + 4 * lane, act ? ld4(a.x_in + (size_t)r * 128 + 4 * lane) : z4);
-    }
-    if (a.has_post) {
-        const AttnW &w = a.post;
-        for (int m = warp; m < M; m += NWARP) {
-            const int r = row0 + m;
-            const bool act = a.rows.active(r);
-            float4 x = act ? ld4(a.x_in + (size_t)r * 128 + 4 * lane) : z4;
-            st4(scat + m * 256 + 128 + 4 * lane, ln128(x, w.ln_dst_g, w.ln_dst_b, lane));
-            st4(ss + m * 128 + 4 * lane, act ? ld4(a.s_in + (size_t)r * 128 + 4 * lane) : z4);
-            st4(scat + m * 256 + 4 * lane, act ? ld4(a.agg + (size_t)r * 128 + 4 * lane) : z4);
-            if (lane < NHEAD) ssal[m * 8 + lane] = act ? a.sal[(size_t)r * 8 + lane] : 0.f;
-        }
-        if (w.has_pos) {
-            // ragg'[m][h][c] = g_r[c] * ragg[m][h][c] + b_r[c] * sal[m][h]
-            for (int i = tid; i < M * 256; i += NT) {           // float4 index: m*256 + h*32 + c4
-                const int m = i >> 8, h = (i >> 5) & 7, c4 = i & 31;
-                const int r = row0 + m;
-                float4 o = z4;
-                if (a.rows.active(r)) {
-                    const float4 v = ld4(a.ragg + (size_t)r * 1024 + h * 128 + 4 * c4);
-                    const float sa = a.sal[(size_t)r * 8 + h];
-                    const float4 g = ldg4(w.ln_r_g + 4 * c4), b = ldg4(w.ln_r_b + 4 * c4);
-                    o = make_float4(fmaf(g.x, v.x, b.x * sa), fmaf(g.y, v.y, b.y * sa), fmaf(g.z, v.z, b.z * sa),
-                                    fmaf(g.w, v.w, b.w * sa));
-                }
-                st4(sbig + m * 1024 + h * 128 + 4 * c4, o);
-            }
-        }
-        __syncthreads();
-        if (w.has_pos) {
-            // agg2[m][o] = agg[m][o] + sum_c Wvr[o][c] * ragg'[m][o/16][c] + bvr[o] * sal[m][o/16]
-            const int o = tid & 127, kh = tid >> 7, h = o >> 4;
-            float acc[M];
-#pragma unroll
-            for (int m = 0; m < M; ++m) acc[m] = 0.f;
-            const float4 *w4 = reinterpret_cast<const float4 *>(w.w_vr);
-#pragma unroll 4
-            for (int k4 = kh * 16; k4 < kh * 16 + 16; ++k4) {
-                const float4 ww = __ldg(w4 + k4 * 128 + o);
-#pragma unroll
-                for (int m = 0; m < M; ++m) {
-                    const float4 x = ld4(sbig + m * 1024 + h * 128 + 4 * k4);
-                    acc[m] = fmaf(x.x, ww.x, acc[m]);
-                    acc[m] = fmaf(x.y, ww.y, acc[m]);
-                    acc[m] = fmaf(x.z, ww.z, acc[m]);
-                    acc[m] = fmaf(x.w, ww.w, acc[m]);
-                }
-            }
-            if (kh == 1) {
-#pragma unroll
-                for (int m = 0; m < M; ++m) sred[m * 128 + o] = acc[m];
-            }
-            __syncthreads();
-            if (kh == 0) {
-                const float bv = __ldg(w.b_vr + o);
-#pragma unroll
-                for (int m = 0; m < M; ++m)
-                    scat[m * 256 + o] += acc[m] + sred[m * 128 + o] + bv * ssal[m * 8 + h];
-            }
-            __syncthreads();
-        }
-        // gate: g = sigmoid(Wg [agg | x_dst] + bg);  u = agg + g * (s - agg)
-        block_gemm<M, 128>(scat, 256, w.w_g, 128, 64, sred, [&](int m, int n, float v) {
-            const float g = sigmoidf(v + __ldg(w.b_g + n));
-            const float ag = scat[m * 256 + n];
-            su[m * 128 + n] = ag + g * (ss[m * 128 + n] - ag);
-        });
-        __syncthreads();
-        // to_out
-        block_gemm<M, 128>(su, 128, w.w_out, 128, 32, sred,
-                           [&](int m, int n, float v) { sbig[m * 128 + n] = v + __ldg(w.b_out + n); });
-        __syncthreads();
-        // x1 = x + LN_post(o);  su = LN_ffpre(x1)
-        for (int m = warp; m < M; m += NWARP) {
-            float4 o = ld4(sbig + m * 128 + 4 * lane);
-            o = ln128(o, w.ln_post_g, w.ln_post_b, lane);
-            const float4 x1 = add4(ld4(sx + m * 128 + 4 * lane), o);
-            st4(sx + m * 128 + 4 * lane, x1);
-            st4(su + m * 128 + 4 * lane, ln128(x1, w.ln_ffpre_g, w.ln_ffpre_b, lane));
-        }
-        __syncthreads();
-        block_gemm<M, 512>(su, 128, w.w_ff1, 512, 32, sred,
-                           [&](int m, int n, float v) { sbig[m * 512 + n] = fmaxf(v + __ldg(w.b_ff1 + n), 0.f); });
-        __syncthreads();
-        block_gemm<M, 128>(sbig, 512, w.w_ff2, 128, 128, sred,
-                           [&](int m, int n, float v) { su[m * 128 + n] = v + __ldg(w.b_ff2 + n); });
-        __syncthreads();
-        for (int m = warp; m < M; m += NWARP) {
-            const int r = row0 + m;
-            float4 f = ld4(su + m * 128 + 4 * lane);
-            f = ln128(f, w.ln_ffpost_g, w.ln_ffpost_b, lane);
-            const float4 x2 = add4(ld4(sx + m * 128 + 4 * lane), f);
-            st4(sx + m * 128 + 4 * lane, x2);
-            if (a.rows.active(r)) {
-                st4(a.x_out + (size_t)r * 128 + 4 * lane, x2);
-                if (a.trace_out) st4(a.trace_out + (size_t)r * 128 + 4 * lane, x2);
-            }
-        }
-    }
-    if (!a.has_pre) return;
-    // ---- pre half of the next layer ---------------------------------------------------------------------------
-    {
-        const AttnW &w = a.pre;
-        __syncthreads();
-        for (int m = warp; m < M; m += NWARP) {
-            const float4 x = ld4(sx + m * 128 + 4 * lane);
-            st4(su + m * 128 + 4 * lane, ln128(x, w.ln_dst_g, w.ln_dst_b, lane));
-        }
-        __syncthreads();
-        block_gemm<M, 256>(su, 128, w.w_qs, 256, 32, sred, [&](int m, int n, float v) {
-            const int r = row0 + m;
-            v += __ldg(w.b_qs + n);
-            if (n < 128) sbig[m * 128 + n] = v;
-            if (a.rows.active(r)) {
-                if (n < 128) a.q_out[(size_t)r * 128 + n] = v;
-                else a.s_out[(size_t)r * 128 + (n - 128)] = v;
-            }
-        });
-        if (a.pre_kv) {
-            const int col = a.col_ptr ? (*a.col_ptr + a.col_add) : 0;
-            block_gemm<M, 256>(su, 128, w.w_kv, 256, 32, sred, [&](int m, int n, float v) {
-                const int r = row0 + m;
-                if (a.rows.active(r)) {
-                    const size_t slot = a.kv_ring ? ((size_t)r * 16 + (col & 15)) : (size_t)r;
-                    a.kv_out[slot * 256 + n] = v + __ldg(w.b_kv + n);
-                }
-            });
-        }
-        __syncthreads();
-        if (w.has_pos) {
-            // qr[m][h][c] = g_r[c] * sum_d q[m][16h+d] * Wkr[16h+d][c]
-            const int c = tid & 127, hh = tid >> 7;
-            const float g = __ldg(w.ln_r_g + c);
-#pragma unroll 1
-            for (int h = hh; h < NHEAD; h += 2) {
-                float acc[M];
-#pragma unroll
-                for (int m = 0; m < M; ++m) acc[m] = 0.f;
-#pragma unroll
-                for (int d4 = 0; d4 < 4; ++d4) {
-                    const float w0 = __ldg(w.w_kr + (size_t)(16 * h + 4 * d4 + 0) * 128 + c);
-                    const float w1 = __ldg(w.w_kr + (size_t)(16 * h + 4 * d4 + 1) * 128 + c);
-                    const float w2 = __ldg(w.w_kr + (size_t)(16 * h + 4 * d4 + 2) * 128 + c);
-                    const float w3 = __ldg(w.w_kr + (size_t)(16 * h + 4 * d4 + 3) * 128 + c);
-#pragma unroll
-                    for (int m = 0; m < M; ++m) {
-                        const float4 q = ld4(sbig + m * 128 + 16 * h + 4 * d4);
-                        acc[m] = fmaf(q.x, w0, acc[m]);
-                        acc[m] = fmaf(q.y, w1, acc[m]);
-                        acc[m] = fmaf(q.z, w2, acc[m]);
-                        acc[m] = fmaf(q.w, w3, acc[m]);
-                    }
-                }
-#pragma unroll
-                for (int m = 0; m < M; ++m) {
-                    const int r = row0 + m;
-                    if (a.rows.active(r)) a.qr_out[(size_t)r * 1024 + h * 128 + c] = acc[m] * g;
-                }
-            }
-        }
-    }
-}
-
-// ===============================================================================================================
-// edge attention: one warp per destination row.  lane = 4*h + qd owns, for head h, the 4 q/k/v dims 4*qd.. of
-// that head (float4 #lane of the 128-vector) and the 32 rhat channels {16 j + 4 qd + i}.
-// ===============================================================================================================
-struct AttnArgs {
-    RowSpace rows;
-    const float *q;            // [R][128]
-    const float *qr;           // [R][8][128] (has_pos)
-    const float *kv;           // K|V rows of 256 floats
-    const int *cnt;            // [R] edges of row r
-    const int *start;          // [R] first edge slot of row r (NULL: r * stride)
-    int stride;
-    const int *src;            // [slots] K/V row index of the edge source
-    const float *rhat;         // [slots][128] standardised relative embedding (has_pos)
-    int has_pos;
-    int max_deg;               // capacity of the per-warp score buffer
-    float *agg, *ragg, *sal;
-    int *err;                  // set to 1 if a row exceeds max_deg
-};
-
-__global__ void __launch_bounds__(NT) k_edge_attn(const AttnArgs a) {
-    extern __shared__ __align__(16) float smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int r = blockIdx.x * NWARP + warp;
-    if (!a.rows.active(r)) return;
-    float *ssim = smem + (size_t)warp * a.max_deg * 8;
-    const int h = lane >> 2, qd = lane & 3;
-    int n = a.cnt[r];
-    if (n > a.max_deg) {
-        if (lane == 0) *a.err = 1;
-        n = a.max_deg;
-    }
-    const int e0 = a.start ? a.start[r] : r * a.stride;
-    const float4 q4 = ld4(a.q + (size_t)r * 128 + 4 * lane);
-    float qr[32];
-    if (a.has_pos) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float4 t = ld4(a.qr + (size_t)r * 1024 + h * 128 + 16 * j + 4 * qd);
-            qr[4 * j + 0] = t.x; qr[4 * j + 1] = t.y; qr[4 * j + 2] = t.z; qr[4 * j + 3] = t.w;
-        }
-    }
-    // pass 1: scores
-    float mx = -INFINITY;
-    for (int e = 0; e < n; ++e) {
-        const size_t s = (size_t)a.src[e0 + e];
-        const float4 k4 = ld4(a.kv + s * 256 + 4 * lane);
-        float p = q4.x * k4.x + q4.y * k4.y + q4.z * k4.z + q4.w * k4.w;
-        if (a.has_pos) {
-            const float *rh = a.rhat + (size_t)(e0 + e) * 128 + 4 * qd;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float4 t = ld4(rh + 16 * j);
-                p = fmaf(qr[4 * j + 0], t.x, p);
-                p = fmaf(qr[4 * j + 1], t.y, p);
-                p = fmaf(qr[4 * j + 2], t.z, p);
-                p = fmaf(qr[4 * j + 3], t.w, p);
-            }
-        }
-        p += __shfl_xor_sync(0xffffffffu, p, 1);
-        p += __shfl_xor_sync(0xffffffffu, p, 2);
-        p *= 0.25f;                                  // head_dim ** -0.5
-        if (qd == 0) ssim[e * 8 + h] = p;
-        mx = fmaxf(mx, p);
-    }
-    __syncwarp();
-    // pass 2: exp, weighted sums
-    float den = 0.f;
-    float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
-    float ra[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) ra[i] = 0.f;
-    for (int e = 0; e < n; ++e) {
-        const size_t s = (size_t)a.src[e0 + e];
-        const float p = expf(ssim[e * 8 + h] - mx);
-        den += p;
-        const float4 v4 = ld4(a.kv + s * 256 + 128 + 4 * lane);
-        av.x = fmaf(p, v4.x, av.x); av.y = fmaf(p, v4.y, av.y); av.z = fmaf(p, v4.z, av.z); av.w = fmaf(p, v4.w, av.w);
-        if (a.has_pos) {
-            const float *rh = a.rhat + (size_t)(e0 + e) * 128 + 4 * qd;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float4 t = ld4(rh + 16 * j);
-                ra[4 * j + 0] = fmaf(p, t.x, ra[4 * j + 0]);
-                ra[4 * j + 1] = fmaf(p, t.y, ra[4 * j + 1]);
-                ra[4 * j + 2] = fmaf(p, t.z, ra[4 * j + 2]);
-                ra[4 * j + 3] = fmaf(p, t.w, ra[4 * j + 3]);
-            }
-        }
-    }
-    const float inv = 1.0f / (den + 1e-16f);        // torch_geometric.utils.softmax denominator
-    st4(a.agg + (size_t)r * 128 + 4 * lane, make_float4(av.x * inv, av.y * inv, av.z * inv, av.w * inv));
-    if (a.has_pos) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            st4(a.ragg + (size_t)r * 1024 + h * 128 + 16 * j + 4 * qd,
-                make_float4(ra[4 * j + 0] * inv, ra[4 * j + 1] * inv, ra[4 * j + 2] * inv, ra[4 * j + 3] * inv));
-    }
-    if (qd == 0) a.sal[(size_t)r * 8 + h] = den * inv;
-}
 
 // ===============================================================================================================
 // K|V projection of source-only nodes: out[l][n][256] = [Wk LN_src(x[n]) | Wv LN_src(x[n]) + bv], blockIdx.y = l
