@@ -46,158 +46,125 @@ __device__ __forceinline__ unsigned lanemask_lt() { return (1u << (threadIdx.x &
 
 // ---------------------------------------------------------------------------------------------------------------
 // edges whose destination is column `cur` (agent_decoder.py:540-610, 612-681, 683-758 with the inference masks of
-// :2119-2121).  One CTA per scene.  Semantics of the third-party calls (oracle/shims): radius = strict `<`, the
-// first max_num_neighbors sources by ascending index; edges ordered by destination then source.
+// :2119-2121).  One warp per (row, edge type).  Semantics of the third-party calls (oracle/shims): radius = strict `<`,
+// the first max_num_neighbors sources by ascending index; edges ordered by destination then source.
+// Slots: temporal r*W + k, map r*max_m + k, agent r*cap + k (k-th neighbour by ascending source row).
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT) k_edge_build(const DecState s) {
-    __shared__ int s_acnt[MAX_CAP];
-    __shared__ int s_astart[MAX_CAP];
-    __shared__ unsigned s_amask[MAX_CAP][MAX_CAP / 32];
-    const int b = blockIdx.x, n = s.n_rows[b], col = *s.col, T = s.T;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * NWARP + warp;
+    const int r = gw / 3, kind = gw - 3 * r;
+    const int R = s.n_scenes * s.cap;
+    if (r >= R) return;
+    const int b = r / s.cap, i = r - b * s.cap, n = s.n_rows[b];
+    if (i >= n) return;
+    const int col = *s.col, T = s.T;
     const int r0 = b * s.cap;
-    const int pt0 = s.pt_ptr[b], pt1 = s.pt_ptr[b + 1];
-    const int nwords = (n + 31) / 32;
-    for (int i = warp; i < n; i += NWARP) {
-        const int r = r0 + i;
-        const float px = s.pos[((size_t)r * T + col) * 2], py = s.pos[((size_t)r * T + col) * 2 + 1];
-        const float hd = s.head[(size_t)r * T + col];
-        const float hx = cosf(hd), hy = sinf(hd);
-        const bool inv_d = s.state[(size_t)r * T + col] == ST_INVALID;
-        const bool inter = s.interact[(size_t)r * T + col] != 0;
-        // ---- temporal: (r, c) -> (r, col), 0 < col - c <= W --------------------------------------------------
-        {
-            int cnt = 0;
-            if (i < n - s.q_rows) {
-                const int c = col - s.W + lane;
-                const bool ok = lane < s.W && c >= 0 && s.tsrc[(size_t)r * T + c] != 0;
-                const unsigned mask = __ballot_sync(0xffffffffu, ok);
-                if (ok) {
-                    const int slot = r * s.W + __popc(mask & lanemask_lt());
-                    const bool inv_s = s.state[(size_t)r * T + c] == ST_INVALID;
-                    float rx = __fsub_rn(s.pos[((size_t)r * T + c) * 2], px);
-                    float ry = __fsub_rn(s.pos[((size_t)r * T + c) * 2 + 1], py);
-                    float rh = wrap_angle(__fsub_rn(s.head[(size_t)r * T + c], hd));
-                    if (inv_s && !inv_d) { rx = -1.f; ry = -1.f; rh = -1.f; }       // :595-601 sentinels
-                    if (!inv_s && inv_d) { rx = 1.f; ry = 1.f; }
-                    if (inv_s && inv_d) { rx = -2.f; ry = -2.f; rh = -2.f; }
-                    s.t_src[slot] = r * RING + (c & (RING - 1));
-                    float4 raw = make_float4(norm2(rx, ry), angle_between(hx, hy, rx, ry), rh, (float)(c - col));
-                    st4(s.t_raw + (size_t)slot * 4, raw);
-                }
-                cnt = __popc(mask);
-            }
-            if (lane == 0) s.t_cnt[r] = cnt;
-        }
-        // ---- map -> agent: first max_m tokens within the radius ---------------------------------------------
-        {
-            int cnt = 0;
-            if (inter) {
-                for (int p0 = pt0; p0 < pt1 && cnt < s.max_m; p0 += 32) {
-                    const int p = p0 + lane;
-                    float dx = 0.f, dy = 0.f;
-                    bool ok = false;
-                    if (p < pt1) {
-                        dx = __fsub_rn(px, s.pt_pos[(size_t)p * 2]);
-                        dy = __fsub_rn(py, s.pt_pos[(size_t)p * 2 + 1]);
-                        ok = dist2(dx, dy) < s.r_m2;
-                    }
-                    const unsigned mask = __ballot_sync(0xffffffffu, ok);
-                    const int rank = cnt + __popc(mask & lanemask_lt());
-                    if (ok && rank < s.max_m) {
-                        const int slot = r * s.max_m + rank;
-                        float rx = -dx, ry = -dy;
-                        float ro = wrap_angle(__fsub_rn(s.pt_ori[p], hd));
-                        if (inv_d) { rx = 1.f; ry = 1.f; ro = 1.f; }                    // :722-723
-                        s.m_src[slot] = p;
-                        s.m_raw[(size_t)slot * 3 + 0] = norm2(rx, ry);
-                        s.m_raw[(size_t)slot * 3 + 1] = angle_between(hx, hy, rx, ry);
-                        s.m_raw[(size_t)slot * 3 + 2] = ro;
-                    }
-                    cnt = min(s.max_m, cnt + __popc(mask));
-                }
-            }
-            if (lane == 0) s.m_cnt[r] = cnt;
-        }
-        // ---- agent <-> agent, pass 1: neighbour bitmap ------------------------------------------------------
-        {
-            int cnt = 0;
-            for (int w = 0; w < nwords; ++w) {
-                const int j = w * 32 + lane;
-                bool ok = false;
-                if (inter && j < n && j != i) {
-                    const int rj = r0 + j;
-                    if (s.interact[(size_t)rj * T + col]) {
-                        const float dx = __fsub_rn(px, s.pos[((size_t)rj * T + col) * 2]);
-                        const float dy = __fsub_rn(py, s.pos[((size_t)rj * T + col) * 2 + 1]);
-                        ok = dist2(dx, dy) < s.r_a2;
-                    }
-                }
-                const unsigned mask = __ballot_sync(0xffffffffu, ok);
-                if (lane == 0) s_amask[i][w] = mask;
-                cnt += __popc(mask);
-            }
-            if (lane == 0) s_acnt[i] = cnt;
-        }
-    }
-    __syncthreads();
-    if (warp == 0) {                                   // exclusive scan of the per-row a2a degrees
-        int carry = 0;
-        for (int i0 = 0; i0 < n; i0 += 32) {
-            const int i = i0 + lane;
-            const int v = i < n ? s_acnt[i] : 0;
-            int x = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int y = __shfl_up_sync(0xffffffffu, x, o);
-                if (lane >= o) x += y;
-            }
-            if (i < n) s_astart[i] = carry + x - v;
-            carry += __shfl_sync(0xffffffffu, x, 31);
-        }
-        if (lane == 0) s.a_total[b] = carry;
-    }
-    __syncthreads();
-    for (int i = warp; i < n; i += NWARP) {
-        const int r = r0 + i;
-        const int base = b * s.cap * s.cap + s_astart[i];
-        if (lane == 0) { s.a_start[r] = base; s.a_cnt[r] = s_acnt[i]; }
-        if (s_acnt[i] == 0) continue;
-        const float px = s.pos[((size_t)r * T + col) * 2], py = s.pos[((size_t)r * T + col) * 2 + 1];
-        const float hd = s.head[(size_t)r * T + col];
-        const float hx = cosf(hd), hy = sinf(hd);
-        const bool inv_d = s.state[(size_t)r * T + col] == ST_INVALID;
-        int run = 0;
-        for (int w = 0; w < nwords; ++w) {
-            const unsigned mask = s_amask[i][w];
-            if (mask & (1u << lane)) {
-                const int rj = r0 + w * 32 + lane;
-                const int slot = base + run + __popc(mask & lanemask_lt());
-                const bool inv_s = s.state[(size_t)rj * T + col] == ST_INVALID;
-                float rx = __fsub_rn(s.pos[((size_t)rj * T + col) * 2], px);
-                float ry = __fsub_rn(s.pos[((size_t)rj * T + col) * 2 + 1], py);
-                float rh = wrap_angle(__fsub_rn(s.head[(size_t)rj * T + col], hd));
-                if (inv_s && !inv_d) { rx = -1.f; ry = -1.f; rh = -1.f; }               // :647-653
+    const float px = s.pos[((size_t)r * T + col) * 2], py = s.pos[((size_t)r * T + col) * 2 + 1];
+    const float hd = s.head[(size_t)r * T + col];
+    const float hx = cosf(hd), hy = sinf(hd);
+    const bool inv_d = s.state[(size_t)r * T + col] == ST_INVALID;
+    const bool inter = s.interact[(size_t)r * T + col] != 0;
+    if (kind == 0) {
+        // ---- temporal: (r, c) -> (r, col), 0 < col - c <= W ------------------------------------------------------
+        int cnt = 0;
+        if (i < n - s.q_rows) {
+            const int c = col - s.W + lane;
+            const bool ok = lane < s.W && c >= 0 && s.tsrc[(size_t)r * T + c] != 0;
+            const unsigned mask = __ballot_sync(0xffffffffu, ok);
+            if (ok) {
+                const int slot = r * s.W + __popc(mask & lanemask_lt());
+                const bool inv_s = s.state[(size_t)r * T + c] == ST_INVALID;
+                float rx = __fsub_rn(s.pos[((size_t)r * T + c) * 2], px);
+                float ry = __fsub_rn(s.pos[((size_t)r * T + c) * 2 + 1], py);
+                float rh = wrap_angle(__fsub_rn(s.head[(size_t)r * T + c], hd));
+                if (inv_s && !inv_d) { rx = -1.f; ry = -1.f; rh = -1.f; }       // :595-601 sentinels
                 if (!inv_s && inv_d) { rx = 1.f; ry = 1.f; }
                 if (inv_s && inv_d) { rx = -2.f; ry = -2.f; rh = -2.f; }
-                s.a_src[slot] = rj;
-                s.a_raw[(size_t)slot * 3 + 0] = norm2(rx, ry);
-                s.a_raw[(size_t)slot * 3 + 1] = angle_between(hx, hy, rx, ry);
-                s.a_raw[(size_t)slot * 3 + 2] = rh;
+                s.t_src[slot] = r * RING + (c & (RING - 1));
+                float4 raw = make_float4(norm2(rx, ry), angle_between(hx, hy, rx, ry), rh, (float)(c - col));
+                st4(s.t_raw + (size_t)slot * 4, raw);
             }
-            run += __popc(mask);
+            cnt = __popc(mask);
         }
+        if (lane == 0) s.t_cnt[r] = cnt;
+    } else if (kind == 1) {
+        // ---- map -> agent: first max_m tokens within the radius -------------------------------------------------
+        const int pt0 = s.pt_ptr[b], pt1 = s.pt_ptr[b + 1];
+        int cnt = 0;
+        if (inter) {
+            for (int p0 = pt0; p0 < pt1 && cnt < s.max_m; p0 += 32) {
+                const int p = p0 + lane;
+                float dx = 0.f, dy = 0.f;
+                bool ok = false;
+                if (p < pt1) {
+                    dx = __fsub_rn(px, s.pt_pos[(size_t)p * 2]);
+                    dy = __fsub_rn(py, s.pt_pos[(size_t)p * 2 + 1]);
+                    ok = dist2(dx, dy) < s.r_m2;
+                }
+                const unsigned mask = __ballot_sync(0xffffffffu, ok);
+                const int rank = cnt + __popc(mask & lanemask_lt());
+                if (ok && rank < s.max_m) {
+                    const int slot = r * s.max_m + rank;
+                    float rx = -dx, ry = -dy;
+                    float ro = wrap_angle(__fsub_rn(s.pt_ori[p], hd));
+                    if (inv_d) { rx = 1.f; ry = 1.f; ro = 1.f; }                    // :722-723
+                    s.m_src[slot] = p;
+                    s.m_raw[(size_t)slot * 3 + 0] = norm2(rx, ry);
+                    s.m_raw[(size_t)slot * 3 + 1] = angle_between(hx, hy, rx, ry);
+                    s.m_raw[(size_t)slot * 3 + 2] = ro;
+                }
+                cnt = min(s.max_m, cnt + __popc(mask));
+            }
+        }
+        if (lane == 0) s.m_cnt[r] = cnt;
+    } else {
+        // ---- agent <-> agent: every interacting row of the scene within the radius, ascending row order ---------
+        int cnt = 0;
+        const int base = r * s.cap;
+        if (inter) {
+            for (int j0 = 0; j0 < n; j0 += 32) {
+                const int j = j0 + lane;
+                const int rj = r0 + j;
+                bool ok = false;
+                float rx = 0.f, ry = 0.f;
+                if (j < n && j != i && s.interact[(size_t)rj * T + col]) {
+                    rx = __fsub_rn(s.pos[((size_t)rj * T + col) * 2], px);
+                    ry = __fsub_rn(s.pos[((size_t)rj * T + col) * 2 + 1], py);
+                    // radius_graph tests |p_i - p_j|^2 < r^2 with the difference taken as (dst - src)
+                    const float dx = __fsub_rn(px, s.pos[((size_t)rj * T + col) * 2]);
+                    const float dy = __fsub_rn(py, s.pos[((size_t)rj * T + col) * 2 + 1]);
+                    ok = dist2(dx, dy) < s.r_a2;
+                }
+                const unsigned mask = __ballot_sync(0xffffffffu, ok);
+                if (ok) {
+                    const int slot = base + cnt + __popc(mask & lanemask_lt());
+                    const bool inv_s = s.state[(size_t)rj * T + col] == ST_INVALID;
+                    float rh = wrap_angle(__fsub_rn(s.head[(size_t)rj * T + col], hd));
+                    if (inv_s && !inv_d) { rx = -1.f; ry = -1.f; rh = -1.f; }               // :647-653
+                    if (!inv_s && inv_d) { rx = 1.f; ry = 1.f; }
+                    if (inv_s && inv_d) { rx = -2.f; ry = -2.f; rh = -2.f; }
+                    s.a_src[slot] = rj;
+                    s.a_raw[(size_t)slot * 3 + 0] = norm2(rx, ry);
+                    s.a_raw[(size_t)slot * 3 + 1] = angle_between(hx, hy, rx, ry);
+                    s.a_raw[(size_t)slot * 3 + 2] = rh;
+                }
+                cnt += __popc(mask);
+            }
+        }
+        if (lane == 0) { s.a_cnt[r] = cnt; s.a_start[r] = base; }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// inputs of the column embedding (agent_decoder.py:426-447 _build_vector_a, :449-509 / :2265-2287)
+// inputs of the column embedding (agent_decoder.py:426-447 _build_vector_a, :449-509 / :2265-2287) of one row
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void k_embed_inputs(const DecState s, int col_add) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    const int R = s.n_scenes * s.cap;
-    if (r >= R || (r % s.cap) >= s.n_rows[r / s.cap]) return;
-    const int col = *s.col + col_add, T = s.T;
+struct EmbedIn {
+    float xa0, xa1;                // |motion vector|, angle(heading, motion vector)
+    int tok_row, state_idx, grid_row, cat_idx;
+};
+__device__ __forceinline__ EmbedIn embed_inputs_row(const DecState &s, int r, int col) {
+    const int T = s.T, R = s.n_scenes * s.cap;
     const int st = s.state[(size_t)r * T + col];
     const bool inv = st == ST_INVALID;
     float mx = 0.f, my = 0.f;
@@ -216,17 +183,19 @@ __global__ void k_embed_inputs(const DecState s, int col_add) {
     if (last_inv) { mx = 1.f; my = 1.f; }
     if (last_val) { mx = -1.f; my = -1.f; }
     const float hd = s.head[(size_t)r * T + col];
-    s.xa_raw[(size_t)r * 2] = norm2(mx, my);
-    s.xa_raw[(size_t)r * 2 + 1] = angle_between(cosf(hd), sinf(hd), mx, my);
+    EmbedIn o;
+    o.xa0 = norm2(mx, my);
+    o.xa1 = angle_between(cosf(hd), sinf(hd), mx, my);
     const int tok = s.token[(size_t)r * T + col];
-    s.tok_row[r] = s.type[r] * (s.V + 2) + (tok < 0 ? s.V + 2 + tok : tok);   // [-2] = BOS row, [-1] = no-token row
-    s.state_idx[r] = st;
+    o.tok_row = s.type[r] * (s.V + 2) + (tok < 0 ? s.V + 2 + tok : tok);   // [-2] = BOS row, [-1] = no-token row
+    o.state_idx = st;
     const int g = s.grid[(size_t)r * T + col];
-    s.grid_row[r] = g < 0 ? s.G : g;                                            // [-1] = invalid-offset row
+    o.grid_row = g < 0 ? s.G : g;                                            // [-1] = invalid-offset row
     // row R = seed type + 0.1 shape.  The reference builds the categorical embeddings once, while every future
     // column is still 'invalid' (agent_decoder.py:1653-1657, 458-470), and later only rewrites them for steps that
     // turn invalid (:2235-2239): every generated column therefore carries the seed/0.1 row, valid or not.
-    s.cat_idx[r] = (inv || col >= s.HC) ? R : r;
+    o.cat_idx = (inv || col >= s.HC) ? R : r;
+    return o;
 }
 
 // counter-based uniform in [0,1): mirrors oracle.agent_decoder_oracle.uniform01
@@ -237,91 +206,112 @@ __device__ __forceinline__ float uniform01(unsigned seed, unsigned scene, unsign
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// sampling + state update + token->pose advance + grid token (agent_decoder.py:2160-2262). One CTA per scene.
+// sampling + state update + token->pose advance + grid token (agent_decoder.py:2160-2262).  One warp per row; every
+// warp first re-derives the ego row's new pose (the grid token is ego-relative, attr_tokenizer.py:77-89).
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT) k_advance(const DecState s) {
-    const int b = blockIdx.x, n = s.n_rows[b], col = *s.col, t = *s.iter, T = s.T, nxt = col + 1;
-    const int r0 = b * s.cap;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ego = s.ego_row[b];
-    for (int i = threadIdx.x; i < n; i += NT) {
-        const int r = r0 + i;
-        // ---- merge the per-slice candidates: global max, softmax denominator, top-KTOP ----------------------
-        float gmax = -INFINITY;
-        for (int k = 0; k < NSLICE; ++k) gmax = fmaxf(gmax, s.part_m[(size_t)r * NSLICE + k]);
-        float den = 0.f;
-        for (int k = 0; k < NSLICE; ++k)
-            den += s.part_s[(size_t)r * NSLICE + k] * expf(s.part_m[(size_t)r * NSLICE + k] - gmax);
-        float cv[KTOP]; int ci[KTOP];
-        unsigned long long taken = 0ull;
-        for (int k = 0; k < KTOP; ++k) {
-            float bv = -INFINITY; int bi = 0x7fffffff, bj = -1;
-            for (int j = 0; j < NSLICE * KTOP; ++j) {
-                if (taken >> j & 1ull) continue;
-                const float v = s.part_v[(size_t)r * NSLICE * KTOP + j];
-                const int id = s.part_i[(size_t)r * NSLICE * KTOP + j];
-                if (v > bv || (v == bv && id < bi)) { bv = v; bi = id; bj = j; }
-            }
-            taken |= 1ull << bj;
-            cv[k] = bv; ci[k] = bi;
-        }
-        int tok = ci[0];
-        if (s.beam > 1) {                      // softmax -> top-k -> multinomial over the k probabilities (:2162-2163, 2194)
-            float p[KTOP], total = 0.f;
-            for (int k = 0; k < s.beam; ++k) { p[k] = expf(cv[k] - gmax) / den; total += p[k]; }
-            const float thr = uniform01(s.seed, (unsigned)s.scene_id[b], (unsigned)i, (unsigned)t) * total;
-            float c = 0.f; int pick = s.beam - 1;
-            for (int k = 0; k < s.beam; ++k) { c += p[k]; if (thr < c) { pick = k; break; } }
-            tok = ci[pick];
-        }
-        if (s.forced_tok) tok = s.forced_tok[(size_t)r * s.S + t];
-        // ---- state (:2166-2173) -------------------------------------------------------------------------------
-        int st;
-        {
-            const float l0 = s.state_logits[(size_t)r * 4], l1 = s.state_logits[(size_t)r * 4 + 1],
-                        l2 = s.state_logits[(size_t)r * 4 + 2];
-            const float m = fmaxf(l0, fmaxf(l1, l2));
-            const float e0 = expf(l0 - m), e1 = expf(l1 - m), e2 = expf(l2 - m);
-            const float sum = e0 + e1 + e2;
-            const float p0 = e0 / sum, p1 = e1 / sum, p2 = e2 / sum;
-            st = 0; float bp = p0;
-            if (p1 > bp) { bp = p1; st = 1; }
-            if (p2 > bp) { bp = p2; st = 2; }
-            if (st == 2) st = ST_EXIT;
-            if (i == ego) st = ST_VALID;
-            if (!s.use_state_token && st == ST_EXIT) st = ST_VALID;
-            if (s.disable_insertion) st = ST_VALID;
-        }
-        if (s.forced_state) st = s.forced_state[(size_t)r * s.S + t];
-        // ---- token -> pose (:2175-2211) -----------------------------------------------------------------------
-        const int ty = min(s.type[r], 2);
-        const int tk = tok < 0 ? tok + s.V : tok;
-        const float *box = s.vocab + ((size_t)ty * s.V + tk) * 48;
-        const float px = s.pos[((size_t)r * T + col) * 2], py = s.pos[((size_t)r * T + col) * 2 + 1];
-        const float th = s.head[(size_t)r * T + col];
-        const float c = cosf(th), sn = sinf(th);
-        float lx = 0.f, ly = 0.f, lh = 0.f;
-        for (int k = 1; k < 6; ++k) {
-            float wx[4], wy[4];
+struct AdvOut {
+    int tok, st;
+    float lx, ly, lh;              // pose at column nxt
+};
+// warp-cooperative; all lanes return the same values.  write: store the row's results.
+__device__ __forceinline__ AdvOut advance_row(const DecState &s, int b, int i, int col, int t, bool write) {
+    const int lane = threadIdx.x & 31;
+    const int T = s.T, nxt = col + 1;
+    const int r = b * s.cap + i;
+    // ---- merge the per-slice candidates: global max, softmax denominator, top-KTOP ------------------------------
+    const float pm = lane < NSLICE ? s.part_m[(size_t)r * NSLICE + lane] : -INFINITY;
+    const float gmax = warp_max(pm);
+    const float pd = lane < NSLICE ? s.part_s[(size_t)r * NSLICE + lane] * expf(pm - gmax) : 0.f;
+    float den = 0.f;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float bx = box[(k * 4 + q) * 2], by = box[(k * 4 + q) * 2 + 1];
-                wx[q] = __fadd_rn(__fadd_rn(__fmul_rn(bx, c), __fmul_rn(by, -sn)), px);
-                wy[q] = __fadd_rn(__fadd_rn(__fmul_rn(bx, sn), __fmul_rn(by, c)), py);
-            }
-            const float mx = (((wx[0] + wx[1]) + wx[2]) + wx[3]) * 0.25f;
-            const float my = (((wy[0] + wy[1]) + wy[2]) + wy[3]) * 0.25f;
-            const float hh = atan2f(__fsub_rn(wy[0], wy[3]), __fsub_rn(wx[0], wx[3]));
+    for (int k = 0; k < NSLICE; ++k) den += __shfl_sync(0xffffffffu, pd, k);      // slice order, as a serial loop
+    constexpr int NC = NSLICE * KTOP;                                           // 40 candidates, <= 2 per lane
+    float v0 = s.part_v[(size_t)r * NC + lane];
+    int i0 = s.part_i[(size_t)r * NC + lane];
+    float v1 = -INFINITY;
+    int i1 = 0x7fffffff;
+    if (lane + 32 < NC) { v1 = s.part_v[(size_t)r * NC + lane + 32]; i1 = s.part_i[(size_t)r * NC + lane + 32]; }
+    float cv[KTOP];
+    int ci[KTOP];
+#pragma unroll
+    for (int k = 0; k < KTOP; ++k) {
+        float bv = v0; int bi = i0;
+        if (v1 > bv || (v1 == bv && i1 < bi)) { bv = v1; bi = i1; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        cv[k] = bv; ci[k] = bi;
+        if (i0 == bi) { v0 = -INFINITY; i0 = 0x7fffffff; }                      // token ids are unique
+        if (i1 == bi) { v1 = -INFINITY; i1 = 0x7fffffff; }
+    }
+    int tok = ci[0];
+    if (s.beam > 1) {                      // softmax -> top-k -> multinomial over the k probabilities (:2162-2163, 2194)
+        float p[KTOP], total = 0.f;
+        for (int k = 0; k < s.beam; ++k) { p[k] = expf(cv[k] - gmax) / den; total += p[k]; }
+        const float thr = uniform01(s.seed, (unsigned)s.scene_id[b], (unsigned)i, (unsigned)t) * total;
+        float c = 0.f; int pick = s.beam - 1;
+        for (int k = 0; k < s.beam; ++k) { c += p[k]; if (thr < c) { pick = k; break; } }
+        tok = ci[pick];
+    }
+    if (s.forced_tok) tok = s.forced_tok[(size_t)r * s.S + t];
+    // ---- state (:2166-2173) -------------------------------------------------------------------------------------
+    int st;
+    {
+        const float l0 = s.state_logits[(size_t)r * 4], l1 = s.state_logits[(size_t)r * 4 + 1],
+                    l2 = s.state_logits[(size_t)r * 4 + 2];
+        const float m = fmaxf(l0, fmaxf(l1, l2));
+        const float e0 = expf(l0 - m), e1 = expf(l1 - m), e2 = expf(l2 - m);
+        const float sum = e0 + e1 + e2;
+        const float p0 = e0 / sum, p1 = e1 / sum, p2 = e2 / sum;
+        st = 0; float bp = p0;
+        if (p1 > bp) { bp = p1; st = 1; }
+        if (p2 > bp) { bp = p2; st = 2; }
+        if (st == 2) st = ST_EXIT;
+        if (i == s.ego_row[b]) st = ST_VALID;
+        if (!s.use_state_token && st == ST_EXIT) st = ST_VALID;
+        if (s.disable_insertion) st = ST_VALID;
+    }
+    if (s.forced_state) st = s.forced_state[(size_t)r * s.S + t];
+    // ---- token -> pose (:2175-2211): lane k computes sub-step k of the token's box track ------------------------
+    const int ty = min(s.type[r], 2);
+    const int tk = tok < 0 ? tok + s.V : tok;
+    const float *box = s.vocab + ((size_t)ty * s.V + tk) * 48;
+    const float px = s.pos[((size_t)r * T + col) * 2], py = s.pos[((size_t)r * T + col) * 2 + 1];
+    const float th = s.head[(size_t)r * T + col];
+    const float c = cosf(th), sn = sinf(th);
+    float mx = 0.f, my = 0.f, hh = 0.f;
+    if (lane >= 1 && lane < 6) {
+        const int k = lane;
+        float wx[4], wy[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float bx = box[(k * 4 + q) * 2], by = box[(k * 4 + q) * 2 + 1];
+            wx[q] = __fadd_rn(__fadd_rn(__fmul_rn(bx, c), __fmul_rn(by, -sn)), px);
+            wy[q] = __fadd_rn(__fadd_rn(__fmul_rn(bx, sn), __fmul_rn(by, c)), py);
+        }
+        mx = (((wx[0] + wx[1]) + wx[2]) + wx[3]) * 0.25f;
+        my = (((wy[0] + wy[1]) + wy[2]) + wy[3]) * 0.25f;
+        hh = atan2f(__fsub_rn(wy[0], wy[3]), __fsub_rn(wx[0], wx[3]));
+        if (write) {
             const size_t o = (size_t)r * (5 * s.S) + t * 5 + (k - 1);
             s.pred_traj[o * 2] = mx; s.pred_traj[o * 2 + 1] = my;
             s.pred_head[o] = hh;
             s.pred_state[o] = (float)st;
-            lx = mx; ly = my; lh = hh;
         }
-        const bool inv = st == ST_INVALID;
-        if (inv) { tok = -1; lx = 0.f; ly = 0.f; lh = 0.f; }                              // :2221-2239
-        s.pos[((size_t)r * T + nxt) * 2] = lx; s.pos[((size_t)r * T + nxt) * 2 + 1] = ly;
-        s.head[(size_t)r * T + nxt] = lh;
+    }
+    AdvOut out;
+    out.lx = __shfl_sync(0xffffffffu, mx, 5);
+    out.ly = __shfl_sync(0xffffffffu, my, 5);
+    out.lh = __shfl_sync(0xffffffffu, hh, 5);
+    const bool inv = st == ST_INVALID;
+    if (inv) { tok = -1; out.lx = 0.f; out.ly = 0.f; out.lh = 0.f; }                      // :2221-2239
+    out.tok = tok; out.st = st;
+    if (write && lane == 0) {
+        s.pos[((size_t)r * T + nxt) * 2] = out.lx; s.pos[((size_t)r * T + nxt) * 2 + 1] = out.ly;
+        s.head[(size_t)r * T + nxt] = out.lh;
         s.state[(size_t)r * T + nxt] = st;
         s.token[(size_t)r * T + nxt] = tok;
         s.interact[(size_t)r * T + nxt] = inv ? 0 : 1;
@@ -329,32 +319,122 @@ __global__ void __launch_bounds__(NT) k_advance(const DecState s) {
         s.next_state[(size_t)r * T + nxt] = st;
         if (inv) s.grid[(size_t)r * T + nxt] = -1;
     }
-    __syncthreads();
-    // ---- ego-centric grid token of the new position (attr_tokenizer.py:77-89, agent_decoder.py:2214) -----------
-    const int re = r0 + ego;
-    const float ex = s.pos[((size_t)re * T + nxt) * 2], ey = s.pos[((size_t)re * T + nxt) * 2 + 1];
-    const float eth = -__fsub_rn(s.head[(size_t)re * T + nxt], 1.5707963267948966f);
+    return out;
+}
+
+__global__ void __launch_bounds__(NT) k_advance(const DecState s) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * NWARP + warp;
+    const int R = s.n_scenes * s.cap;
+    if (r >= R) return;
+    const int b = r / s.cap, i = r - b * s.cap;
+    if (i >= s.n_rows[b]) return;
+    const int col = *s.col, t = *s.iter, T = s.T, nxt = col + 1;
+    const int ego = s.ego_row[b];
+    const AdvOut eo = advance_row(s, b, ego, col, t, false);
+    const AdvOut me = (i == ego) ? eo : advance_row(s, b, i, col, t, true);
+    if (i == ego) advance_row(s, b, i, col, t, true);
+    if (me.st == ST_INVALID) return;
+    // ---- ego-centric grid token of the new position (attr_tokenizer.py:77-89, agent_decoder.py:2214) ------------
+    const float eth = -__fsub_rn(eo.lh, 1.5707963267948966f);
     const float ec = cosf(eth), es = sinf(eth);
-    for (int i = warp; i < n; i += NWARP) {
-        const int r = r0 + i;
-        if (s.state[(size_t)r * T + nxt] == ST_INVALID) continue;
-        const float rx = __fsub_rn(s.pos[((size_t)r * T + nxt) * 2], ex);
-        const float ry = __fsub_rn(s.pos[((size_t)r * T + nxt) * 2 + 1], ey);
-        const float qx = __fadd_rn(__fmul_rn(rx, ec), __fmul_rn(ry, -es));
-        const float qy = __fadd_rn(__fmul_rn(rx, es), __fmul_rn(ry, ec));
-        float bd = INFINITY; int bi = 0x7fffffff;
-        for (int g = lane; g < s.G; g += 32) {
-            const float d = norm2(__fsub_rn(qx, s.grid_cells[(size_t)g * 2]), __fsub_rn(qy, s.grid_cells[(size_t)g * 2 + 1]));
-            if (d < bd) { bd = d; bi = g; }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float od = __shfl_xor_sync(0xffffffffu, bd, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
-        }
-        if (lane == 0) s.grid[(size_t)r * T + nxt] = bi;
+    const float rx = __fsub_rn(me.lx, eo.lx), ry = __fsub_rn(me.ly, eo.ly);
+    const float qx = __fadd_rn(__fmul_rn(rx, ec), __fmul_rn(ry, -es));
+    const float qy = __fadd_rn(__fmul_rn(rx, es), __fmul_rn(ry, ec));
+    float bd = INFINITY; int bi = 0x7fffffff;
+    for (int g = lane; g < s.G; g += 32) {
+        const float d = norm2(__fsub_rn(qx, s.grid_cells[(size_t)g * 2]), __fsub_rn(qy, s.grid_cells[(size_t)g * 2 + 1]));
+        if (d < bd) { bd = d; bi = g; }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+    }
+    if (lane == 0) s.grid[(size_t)r * T + nxt] = bi;
+}
+
+// ===============================================================================================================
+// Column embedding (agent_decoder.py:449-509 / 2265-2287): x_a_emb (Fourier, D=2, categorical seed) -> concat
+// [token_emb | x_a_emb | state_emb | grid_emb] -> fusion_emb (512 -> 128 -> 128 -> 128), tiles of EM rows
+// ===============================================================================================================
+struct ColEmbArgs {
+    RowSpace rows;
+    FourierW fx;               // x_a_emb
+    MlpEmbW fusion;
+    DecState s;                // decode state: the embedded column is *s.col + col_add
+    int col_add;
+    const float *cat_tab;      // [R+1][128] type + shape embedding rows
+    const float *tok_tab;      // [3][token_size+2][128]
+    const float *state_tab;    // [4][128]
+    const float *grid_tab;     // [grid_size+1][128]
+    float *out;                // [R][128]
+};
+constexpr int XLD = 516;       // leading dimension of the 512-wide fusion input
+constexpr int COLEMB_SMEM_FLOATS = WS_SMEM_FLOATS + EM * XLD + EM * FLD + 2 * EM * HLD + EM * 4;
+constexpr size_t COLEMB_SMEM = (size_t)COLEMB_SMEM_FLOATS * sizeof(float);
+
+__global__ void __launch_bounds__(NT_S) k_embed_column(const ColEmbArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    WsSmem wsm(smem);
+    float *sX = smem + WS_SMEM_FLOATS;       // [EM][XLD]
+    float *sF = sX + EM * XLD;               // [EM][132]
+    float *sH = sF + EM * FLD;               // [EM][HLD]
+    float *sA = sH + EM * HLD;               // [EM][HLD]
+    float *sraw = sA + EM * HLD;             // [EM][4]
+    __shared__ EmbedIn s_in[EM];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row0 = blockIdx.x * EM;
+    bool any = false;
+    for (int m = 0; m < EM; ++m) any |= a.rows.active(row0 + m);
+    if (!any) return;
+    if (tid < EM) {                          // inputs of the embedding (also kept in global memory for the debug tools)
+        const int r = row0 + tid;
+        EmbedIn in;
+        in.xa0 = 0.f; in.xa1 = 0.f; in.tok_row = 0; in.state_idx = 0; in.grid_row = 0; in.cat_idx = 0;
+        if (a.rows.active(r)) {
+            in = embed_inputs_row(a.s, r, *a.s.col + a.col_add);
+            a.s.xa_raw[(size_t)r * 2] = in.xa0; a.s.xa_raw[(size_t)r * 2 + 1] = in.xa1;
+            a.s.tok_row[r] = in.tok_row; a.s.state_idx[r] = in.state_idx; a.s.grid_row[r] = in.grid_row;
+            a.s.cat_idx[r] = in.cat_idx;
+        }
+        s_in[tid] = in;
+        sraw[tid * 4 + 0] = in.xa0; sraw[tid * 4 + 1] = in.xa1; sraw[tid * 4 + 2] = 0.f; sraw[tid * 4 + 3] = 0.f;
+    }
+    ws_init(wsm);
+    if (warp == NWARP) {
+        if (lane < WS_STAGES) {
+            WSeg segs[WS_MAX_SEGS];
+            int n = fourier_segs(a.fx, 2, segs);
+            n += mlp3_segs(a.fusion, 128, segs + n);
+            ws_produce(wsm, segs, n);
+        }
+        return;
+    }
+    WsCons ws(wsm);
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int m = warp; m < EM; m += NWARP) {
+        const int r = row0 + m;
+        float4 c = z4, t = z4, s = z4, g = z4;
+        if (a.rows.active(r)) {
+            c = ld4(a.cat_tab + (size_t)s_in[m].cat_idx * 128 + 4 * lane);
+            t = ld4(a.tok_tab + (size_t)s_in[m].tok_row * 128 + 4 * lane);
+            s = ld4(a.state_tab + (size_t)s_in[m].state_idx * 128 + 4 * lane);
+            g = ld4(a.grid_tab + (size_t)s_in[m].grid_row * 128 + 4 * lane);
+        }
+        st4(sA + m * HLD + 4 * lane, c);
+        st4(sX + m * XLD + 4 * lane, t);
+        st4(sX + m * XLD + 256 + 4 * lane, s);
+        st4(sX + m * XLD + 384 + 4 * lane, g);
+    }
+    fourier_body<EM>(ws, a.fx, 2, sraw, sF, sH, sA);
+    for (int m = warp; m < EM; m += NWARP) st4(sX + m * XLD + 128 + 4 * lane, ld4(sH + m * HLD + 4 * lane));
+    csync();
+    mlp3_body<EM>(ws, a.fusion, sX, XLD, 128, sH, sA, [&](int m, int n, float v) {
+        const int r = row0 + m;
+        if (a.rows.active(r)) a.out[(size_t)r * 128 + n] = v;
+    });
 }
 
 __global__ void k_next_iter(int *col, int *iter) { *col += 1; *iter += 1; }

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -321,11 +322,9 @@ static float *fbuf(infgen_engine *e, const char *name) { return (float *)e->bufs
 static inline void count_launch(infgen_engine *e) { if (!e->capturing) e->launches++; }
 
 // per-kernel-class device timing (bench.py roofline leg): event pairs around every launch, plain launches only
-enum KClass { KC_EDGE_BUILD, KC_FOURIER_T, KC_FOURIER_M, KC_FOURIER_A, KC_FOURIER_X, KC_FUSION, KC_LAYER_TM, KC_LAYER_A,
-              KC_HEADS, KC_ADVANCE, KC_MISC, KC_COUNT };
-static const char *KCLASS_NAME[KC_COUNT] = {"k_edge_build", "k_fourier<4>:temporal", "k_fourier<3>:map", "k_fourier<3>:agent",
-                                            "k_fourier<2>:x_a", "k_mlp_embed:fusion", "k_layer:temporal+map", "k_layer:agent",
-                                            "k_heads", "k_advance", "misc"};
+enum KClass { KC_EDGE_BUILD, KC_FOURIER, KC_EMBED, KC_LAYER_TM, KC_LAYER_A, KC_HEADS, KC_ADVANCE, KC_MISC, KC_COUNT };
+static const char *KCLASS_NAME[KC_COUNT] = {"k_edge_build", "k_fourier:edges", "k_embed_column", "k_layer:temporal+map",
+                                            "k_layer:agent", "k_heads", "k_advance", "misc"};
 struct ProfScope {
     infgen_engine *e;
     bool on;
@@ -343,7 +342,13 @@ struct ProfScope {
 // ---------------------------------------------------------------------------------------------------------------
 // launch helpers
 // ---------------------------------------------------------------------------------------------------------------
-static int launch_layer(infgen_engine *e, const LayerArgs &a, int cls) {
+// B200: at most 15 clusters of 8 CTAs with ~211 KB of shared memory are co-resident (cudaOccupancyMaxActiveClusters,
+// tools/probe/cluster_occ.cu); a 16th cluster costs a whole second wave
+static const int MAX_CLUSTERS = 15;
+static int launch_layer(infgen_engine *e, const LayerArgs &a_in, int cls) {
+    LayerArgs a = a_in;
+    if (e->bufs.count("tstamp") && e->bufs["tstamp"].p)
+        a.tstamp = (long long *)e->bufs["tstamp"].p + (cls == KC_LAYER_A ? 32 : 0);
     ProfScope ps(e, cls);
     const int M = e->row_tile;
     const int clusters = (a.rows.n_total + M - 1) / M;
@@ -361,16 +366,24 @@ static PreArgs make_pre(const AttnW &w, bool pre_kv, float *kv_out, bool kv_ring
     p.to_global = to_global ? 1 : 0;
     return p;
 }
-static int launch_fourier(infgen_engine *e, const FourierArgs &a, int d, int cls = KC_MISC) {
-    int grid = (a.n_slots + FM - 1) / FM;
-    if (grid == 0) return 0;
-    ProfScope ps(e, cls);
-    switch (d) {
-        case 2: k_fourier<2><<<grid, NT, FOURIER_SMEM, e->stream>>>(a); break;
-        case 3: k_fourier<3><<<grid, NT, FOURIER_SMEM, e->stream>>>(a); break;
-        case 4: k_fourier<4><<<grid, NT, FOURIER_SMEM, e->stream>>>(a); break;
-        default: return fail(INFGEN_ERR_INVALID_ARG, "FourierEmbedding input_dim %d unsupported", d);
+static int fourier_tiles(const FourierArgs &a) { return (a.n_slots + FM - 1) / FM; }
+// up to three FourierEmbeddings in one launch
+static int launch_fourier(infgen_engine *e, const FourierArgs *jobs, int n_jobs, int cls = KC_MISC) {
+    FourierBatch fb;
+    memset(&fb, 0, sizeof(fb));
+    int tiles = 0;
+    for (int j = 0; j < n_jobs; ++j) {
+        if (jobs[j].dim < 1 || jobs[j].dim > 4) return fail(INFGEN_ERR_INVALID_ARG, "FourierEmbedding input_dim %d unsupported", jobs[j].dim);
+        if (fourier_tiles(jobs[j]) == 0) continue;
+        fb.job[fb.n_jobs] = jobs[j];
+        fb.tile0[fb.n_jobs] = tiles;
+        tiles += fourier_tiles(jobs[j]);
+        fb.n_jobs++;
     }
+    fb.tile0[fb.n_jobs] = tiles;
+    if (tiles == 0) return 0;
+    ProfScope ps(e, cls);
+    k_fourier<<<tiles, NT_S, FOURIER_SMEM, e->stream>>>(fb);
     CKL();
     count_launch(e);
     return 0;
@@ -379,7 +392,7 @@ static int launch_mlp_embed(infgen_engine *e, const MlpEmbArgs &a, int cls = KC_
     int grid = (a.rows.n_total + EM - 1) / EM;
     if (grid == 0) return 0;
     ProfScope ps(e, cls);
-    k_mlp_embed<<<grid, NT, mlp_embed_smem(a.k4), e->stream>>>(a);
+    k_mlp_embed<<<grid, NT_S, mlp_embed_smem(a.k4), e->stream>>>(a);
     CKL();
     count_launch(e);
     return 0;
@@ -400,23 +413,16 @@ static RowSpace flat_rows(int n) {
 static int enqueue_embed_column(infgen_engine *e, int col_add) {
     DecState &s = e->st;
     const int R = e->R;
+    ColEmbArgs ca;
+    memset(&ca, 0, sizeof(ca));
+    ca.rows = scene_rows(e); ca.fx = e->f_x; ca.fusion = e->e_fusion;
+    ca.s = s; ca.col_add = col_add; ca.cat_tab = fbuf(e, "cat_tab");
+    ca.tok_tab = e->tok_tab; ca.state_tab = e->state_emb; ca.grid_tab = e->grid_tab; ca.out = fbuf(e, "x");
     {
-        ProfScope ps(e, KC_MISC);
-        k_embed_inputs<<<(R + 127) / 128, 128, 0, e->stream>>>(s, col_add);
+        ProfScope ps(e, KC_EMBED);
+        k_embed_column<<<(R + EM - 1) / EM, NT_S, COLEMB_SMEM, e->stream>>>(ca);
     }
     CKL(); count_launch(e);
-    FourierArgs fa;
-    memset(&fa, 0, sizeof(fa));
-    fa.n_slots = R; fa.cnt = s.n_rows; fa.stride = e->cap; fa.raw = s.xa_raw; fa.w = e->f_x;
-    fa.cat_tab = fbuf(e, "cat_tab"); fa.cat_idx = s.cat_idx; fa.out = fbuf(e, "xa"); fa.normalize = 0;
-    RET(launch_fourier(e, fa, 2, KC_FOURIER_X));
-    MlpEmbArgs ma;
-    memset(&ma, 0, sizeof(ma));
-    ma.rows = scene_rows(e); ma.w = e->e_fusion; ma.kin = 512; ma.k4 = 128; ma.fusion = 1;
-    ma.tok_tab = e->tok_tab; ma.tok_row = s.tok_row; ma.xa = fbuf(e, "xa"); ma.state_tab = e->state_emb;
-    ma.state_idx = s.state_idx; ma.grid_tab = e->grid_tab; ma.grid_row = s.grid_row;
-    ma.out = fbuf(e, "x"); ma.out_ld = 128;
-    RET(launch_mlp_embed(e, ma, KC_FUSION));
     return 0;
 }
 
@@ -468,19 +474,21 @@ static int enqueue_iteration(infgen_engine *e, int trace_iter) {
     const int R = e->R;
     {
         ProfScope ps(e, KC_EDGE_BUILD);
-        k_edge_build<<<e->n_scenes, NT, 0, e->stream>>>(s);
+        k_edge_build<<<(R * 3 + NWARP - 1) / NWARP, NT, 0, e->stream>>>(s);
     }
     CKL(); count_launch(e);
-    FourierArgs fa;
-    memset(&fa, 0, sizeof(fa));
-    fa.normalize = 1;
-    fa.n_slots = R * s.W; fa.cnt = s.t_cnt; fa.stride = s.W; fa.raw = s.t_raw; fa.w = e->f_t; fa.out = fbuf(e, "rhat_t");
-    RET(launch_fourier(e, fa, 4, KC_FOURIER_T));
-    fa.n_slots = R * s.max_m; fa.cnt = s.m_cnt; fa.stride = s.max_m; fa.raw = s.m_raw; fa.w = e->f_m; fa.out = fbuf(e, "rhat_m");
-    RET(launch_fourier(e, fa, 3, KC_FOURIER_M));
-    fa.n_slots = e->n_scenes * e->cap * e->cap; fa.cnt = s.a_total; fa.stride = e->cap * e->cap; fa.raw = s.a_raw;
-    fa.w = e->f_a; fa.out = fbuf(e, "rhat_a");
-    RET(launch_fourier(e, fa, 3, KC_FOURIER_A));
+    FourierArgs fj[3];
+    memset(fj, 0, sizeof(fj));
+    fj[0].normalize = 1; fj[0].dim = 3;       // the large one first: agent<->agent
+    fj[0].n_slots = R * e->cap; fj[0].cnt = s.a_cnt; fj[0].stride = e->cap;
+    fj[0].raw = s.a_raw; fj[0].w = e->f_a; fj[0].out = fbuf(e, "rhat_a");
+    fj[1].normalize = 1; fj[1].dim = 4;
+    fj[1].n_slots = R * s.W; fj[1].cnt = s.t_cnt; fj[1].stride = s.W; fj[1].raw = s.t_raw; fj[1].w = e->f_t;
+    fj[1].out = fbuf(e, "rhat_t");
+    fj[2].normalize = 1; fj[2].dim = 3;
+    fj[2].n_slots = R * s.max_m; fj[2].cnt = s.m_cnt; fj[2].stride = s.max_m; fj[2].raw = s.m_raw; fj[2].w = e->f_m;
+    fj[2].out = fbuf(e, "rhat_m");
+    RET(launch_fourier(e, fj, 3, KC_FOURIER));
     RET(enqueue_layers(e, true, trace_iter));
     HeadArgs ha;
     memset(&ha, 0, sizeof(ha));
@@ -494,12 +502,12 @@ static int enqueue_iteration(infgen_engine *e, int trace_iter) {
     }
     {
         ProfScope ps(e, KC_HEADS);
-        k_heads<<<dim3((R + HM - 1) / HM, NSLICE), NT, 0, e->stream>>>(ha);
+        k_heads<<<dim3((R + HM - 1) / HM, NSLICE + 1), NT_S, HEADS_SMEM, e->stream>>>(ha);
     }
     CKL(); count_launch(e);
     {
         ProfScope ps(e, KC_ADVANCE);
-        k_advance<<<e->n_scenes, NT, 0, e->stream>>>(s);
+        k_advance<<<(R + NWARP - 1) / NWARP, NT, 0, e->stream>>>(s);
     }
     CKL(); count_launch(e);
     RET(enqueue_embed_column(e, 1));
@@ -611,10 +619,11 @@ int32_t infgen_create(const infgen_config *cfg, const float *weights, int64_t n_
     // kernels that need more than 48 KB of dynamic shared memory
     CK(cudaFuncSetAttribute(k_layer<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LayerSmem<4>::BYTES));
     CK(cudaFuncSetAttribute(k_layer<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LayerSmem<8>::BYTES));
-    CK(cudaFuncSetAttribute(k_fourier<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FOURIER_SMEM));
-    CK(cudaFuncSetAttribute(k_fourier<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FOURIER_SMEM));
-    CK(cudaFuncSetAttribute(k_fourier<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FOURIER_SMEM));
+    CK(cudaFuncSetAttribute(k_fourier, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FOURIER_SMEM));
     CK(cudaFuncSetAttribute(k_mlp_embed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mlp_embed_smem(128)));
+    CK(cudaFuncSetAttribute(k_embed_column, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COLEMB_SMEM));
+    CK(cudaFuncSetAttribute(k_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEADS_SMEM));
+    CK(cudaFuncSetAttribute(k_mlp_layer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_LAYER_SMEM));
     RET(build_tables(e));
     CK(cudaStreamSynchronize(e->stream));
     *out = e;
@@ -686,7 +695,7 @@ int32_t infgen_load_scenes(infgen_engine *e, const infgen_scene_batch *b, int32_
     if (b->pt_ptr[0] != 0 || P < 0) return fail(INFGEN_ERR_INVALID_ARG, "pt_ptr must start at 0");
     if (e->n_scenes != ns || e->cap != cap || e->T != T || e->S != S || e->P != P) drop_graph(e);
     e->n_scenes = ns; e->cap = cap; e->R = R; e->T = T; e->S = S; e->P = P; e->n_rows_sum = sum; e->max_rows = mx;
-    e->row_tile = sum > 512 ? 8 : 4;
+    e->row_tile = (R + 3) / 4 <= MAX_CLUSTERS ? 4 : 8;
     e->iters_done = 0; e->prefilled = 0; e->forcing = false;
     const int W = e->cfg.window, MM = e->cfg.max_pl2a_neighbors, V = e->cfg.token_size;
     DecState &s = e->st;
@@ -770,6 +779,7 @@ int32_t infgen_load_scenes(infgen_engine *e, const infgen_scene_batch *b, int32_
     RET(ensure_t(e, "rhat_a", (size_t)R * cap * 128, &tmp));
     RET(ensure_t(e, "cat_tab", (size_t)(R + 1) * 128, &tmp)); RET(ensure_t(e, "shape_rows", (size_t)(R + 1) * 4, &tmp));
     RET(ensure_t(e, "hist_traj", (size_t)R * HC * 5 * 2, &tmp)); RET(ensure_t(e, "hist_head", (size_t)R * HC * 5, &tmp));
+    if (getenv("INFGEN_TSTAMP")) { long long *ts; RET(ensure_t(e, "tstamp", 64, &ts)); }
     if (e->cfg.trace && S > 0) {
         RET(ensure_t(e, "trace_head_in", (size_t)S * R * 128, &tmp));
         RET(ensure_t(e, "trace_token_logits", (size_t)S * R * V, &tmp));
@@ -1008,7 +1018,7 @@ int32_t infgen_op_attention_layer(infgen_engine *e, const char *layer, const flo
     }
     if (!d_x || !d_out || !d_kv || !d_src) return fail(INFGEN_ERR_CUDA, "temporary allocation failed");
     const int saved_tile = e->row_tile;
-    e->row_tile = n_dst > 512 ? 8 : 4;
+    e->row_tile = (n_dst + 3) / 4 <= MAX_CLUSTERS ? 4 : 8;
     // launch 1: projections of every row (K/V of all rows must exist before any row attends)
     LayerArgs la;
     memset(&la, 0, sizeof(la));
@@ -1053,11 +1063,11 @@ int32_t infgen_op_fourier_embedding(infgen_engine *e, const char *name, const fl
     TmpDev tmp;
     FourierArgs fa;
     memset(&fa, 0, sizeof(fa));
-    fa.n_slots = n; fa.raw = tmp.upload(x, (size_t)n * dim); fa.w = make_fourier(e, p, dim);
+    fa.n_slots = n; fa.dim = dim; fa.raw = tmp.upload(x, (size_t)n * dim); fa.w = make_fourier(e, p, dim);
     fa.cat_tab = cat ? tmp.upload(cat, (size_t)n * 128) : nullptr;
     float *d_out = tmp.alloc<float>((size_t)n * 128);
     fa.out = d_out; fa.normalize = 0;
-    RET(launch_fourier(e, fa, dim));
+    RET(launch_fourier(e, &fa, 1));
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaMemcpy(out, d_out, (size_t)n * 128 * sizeof(float), cudaMemcpyDeviceToHost));
     return 0;
@@ -1104,7 +1114,7 @@ int32_t infgen_op_mlp_layer(infgen_engine *e, const char *name, const float *x, 
     la.n = n; la.x = tmp.upload(x, (size_t)n * 128); la.w = make_head(e, p, 128, n_out);
     float *d_out = tmp.alloc<float>((size_t)n * n_out);
     la.out = d_out;
-    k_mlp_layer<<<dim3((n + HM - 1) / HM, std::min(la.w.n_pad / 128, 16)), NT, 0, e->stream>>>(la);
+    k_mlp_layer<<<dim3((n + HM - 1) / HM, la.w.n_pad / 128), NT_S, MLP_LAYER_SMEM, e->stream>>>(la);
     CKL(); count_launch(e);
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaMemcpy(out, d_out, (size_t)n * n_out * sizeof(float), cudaMemcpyDeviceToHost));

@@ -93,6 +93,7 @@ struct LayerArgs {
     PreArgs pre0;              // optional projections run before the first layer (else q/s/qr come from global)
     int n_sub;
     SubArgs sub[2];
+    long long *tstamp;         // optional [32] clock64 stamps of CTA 0 (debug: phase breakdown)
 };
 
 template <int M>
@@ -117,49 +118,6 @@ struct LayerSmem {
     static constexpr int TOTAL = MBAR + 4;
     static constexpr size_t BYTES = (size_t)TOTAL * sizeof(float);
 };
-
-// ---- mbarrier / bulk-copy primitives ----------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *b, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *b, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *b) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(b))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_u32(b)),
-        "r"(parity)
-        : "memory");
-}
-// one thread: request `floats` floats from global into shared memory, completion on `b`
-__device__ __forceinline__ void chunk_request(float *dst, const float *src, int floats, uint64_t *b) {
-    fence_proxy_async();
-    uint32_t bytes = (uint32_t)floats * 4u;
-    mbar_expect_tx(b, bytes);
-    const char *s = reinterpret_cast<const char *>(src);
-    char *d = reinterpret_cast<char *>(dst);
-    while (bytes) {
-        const uint32_t n = bytes < 32768u ? bytes : 32768u;
-        bulk_g2s(d, s, n, b);
-        d += n; s += n; bytes -= n;
-    }
-}
 
 // LayerNorm of a 128-vector (4 channels per lane) with the affine vectors in shared (or any generic) memory
 __device__ __forceinline__ float4 ln128s(const float4 v, const float *g, const float *b, int lane) {
@@ -218,6 +176,7 @@ template <int M>
 __device__ __forceinline__ void attn_phase(const SubArgs &A, const RowSpace &rows, int row0, int c, const float *sq,
                                            const float *sqr, float *sagg, float *sragg, float *ssal, float *smerge) {
     constexpr int WPR = NWARP / M;
+    constexpr int CH = 8;                                 // edges in flight per warp
     static_assert(WPR == 1 || WPR == 2, "1 or 2 warps per row");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m = warp / WPR, part = warp % WPR;
@@ -228,52 +187,56 @@ __device__ __forceinline__ void attn_phase(const SubArgs &A, const RowSpace &row
         n = A.cnt[r];
         e0 = A.start ? A.start[r] : r * A.stride;
     }
+    // this warp's contiguous share of the row's edges
+    const int share = WPR == 1 ? n : (((n + WPR - 1) / WPR + 3) & ~3);
+    const int eb0 = part * share, eb1 = min(n, eb0 + share);
     const float4 qr4 = ld4(sqr + m * 128 + 4 * lane);
     const float4 q4 = lane < 4 ? ld4(sq + m * 16 + 4 * lane) : z4;
     float mx = -INFINITY, den = 0.f;
     float4 ra = z4, av = z4;
     const float *kvb = A.kv + 16 * c + 4 * (lane & 3);
-    for (int eb = part * 4; eb < n; eb += 4 * WPR) {
-        float p[4];
-        float4 rh[4], v4[4];
+    for (int blk = eb0; blk < eb1; blk += 32) {           // source rows of 32 edges with one coalesced load
+        const int my_src = (blk + lane < eb1) ? A.src[e0 + blk + lane] : 0;
+        const int blk_end = min(eb1, blk + 32);
+        for (int eb = blk; eb < blk_end; eb += CH) {
+            float p[CH];
+            float4 rh[CH], v4[CH];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int e = eb + j;
-            p[j] = 0.f; rh[j] = z4; v4[j] = z4;
-            if (e < n) {
-                if (A.has_pos) {
-                    rh[j] = ld4(A.rhat + (size_t)(e0 + e) * 128 + 4 * lane);
-                    p[j] = dot4(qr4, rh[j]);
-                }
-                if (lane < 4) {
-                    const size_t s = (size_t)A.src[e0 + e];
-                    p[j] += dot4(q4, ld4(kvb + s * 256));
-                    v4[j] = ld4(kvb + s * 256 + 128);
+            for (int j = 0; j < CH; ++j) {
+                const int e = eb + j;
+                const int sj = __shfl_sync(0xffffffffu, my_src, (e - blk) & 31);
+                p[j] = 0.f; rh[j] = z4; v4[j] = z4;
+                if (e < blk_end) {
+                    if (A.has_pos) rh[j] = ld4(A.rhat + (size_t)(e0 + e) * 128 + 4 * lane);
+                    if (lane < 4) {
+                        p[j] = dot4(q4, ld4(kvb + (size_t)sj * 256));
+                        v4[j] = ld4(kvb + (size_t)sj * 256 + 128);
+                    }
                 }
             }
-        }
-        float pm = -INFINITY;
+            float pm = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            p[j] = warp_sum(p[j]) * 0.25f;               // head_dim ** -0.5
-            if (eb + j >= n) p[j] = -INFINITY;
-            pm = fmaxf(pm, p[j]);
-        }
-        const float mn = fmaxf(mx, pm);                   // finite: edge eb exists
-        const float sc = expf(mx - mn);                   // 0 on the first chunk
-        den *= sc;
-        ra.x *= sc; ra.y *= sc; ra.z *= sc; ra.w *= sc;
-        av.x *= sc; av.y *= sc; av.z *= sc; av.w *= sc;
+            for (int j = 0; j < CH; ++j) {
+                p[j] = warp_sum(p[j] + dot4(qr4, rh[j])) * 0.25f;      // head_dim ** -0.5
+                if (eb + j >= blk_end) p[j] = -INFINITY;
+                pm = fmaxf(pm, p[j]);
+            }
+            const float mn = fmaxf(mx, pm);                   // finite: edge eb exists
+            const float sc = expf(mx - mn);                   // 0 on the first chunk
+            den *= sc;
+            ra.x *= sc; ra.y *= sc; ra.z *= sc; ra.w *= sc;
+            av.x *= sc; av.y *= sc; av.z *= sc; av.w *= sc;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float w = expf(p[j] - mn);              // 0 for padded edges
-            den += w;
-            ra.x = fmaf(w, rh[j].x, ra.x); ra.y = fmaf(w, rh[j].y, ra.y);
-            ra.z = fmaf(w, rh[j].z, ra.z); ra.w = fmaf(w, rh[j].w, ra.w);
-            av.x = fmaf(w, v4[j].x, av.x); av.y = fmaf(w, v4[j].y, av.y);
-            av.z = fmaf(w, v4[j].z, av.z); av.w = fmaf(w, v4[j].w, av.w);
+            for (int j = 0; j < CH; ++j) {
+                const float w = expf(p[j] - mn);              // 0 for padded edges
+                den += w;
+                ra.x = fmaf(w, rh[j].x, ra.x); ra.y = fmaf(w, rh[j].y, ra.y);
+                ra.z = fmaf(w, rh[j].z, ra.z); ra.w = fmaf(w, rh[j].w, ra.w);
+                av.x = fmaf(w, v4[j].x, av.x); av.y = fmaf(w, v4[j].y, av.y);
+                av.z = fmaf(w, v4[j].z, av.z); av.w = fmaf(w, v4[j].w, av.w);
+            }
+            mx = mn;
         }
-        mx = mn;
     }
     if (WPR == 2) {
         float *mg = smerge + warp * 160;
@@ -322,6 +285,11 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
 #pragma unroll
     for (int m = 0; m < M; ++m) any |= a.rows.active(row0 + m);
     if (!any) return;                                              // uniform over the whole cluster
+    int ts_n = 0;
+    auto stamp = [&]() {
+        if (a.tstamp && blockIdx.x == 0 && tid == 0 && ts_n < 32) a.tstamp[ts_n++] = clock64();
+    };
+    stamp();
 
     float *wpost = smem + L::WPOST, *wpre = smem + L::WPRE, *sx = smem + L::X, *scat = smem + L::CAT,
           *su = smem + L::U, *so = smem + L::O, *sh = smem + L::H, *sy = smem + L::Y, *sred = smem + L::RED,
@@ -364,6 +332,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
     }
     // peers must be resident before anyone writes into their shared memory
     cluster.sync();
+    stamp();
 
     // ---- LayerNorm + q/s/k/v projections + relative-query fold of one layer (layers.py:65-71, 106-108) ----------
     auto do_pre = [&](const PreArgs &P) {
@@ -428,14 +397,17 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
     };
 
     if (a.pre0.w) do_pre(a.pre0);
+    stamp();
 
     for (int si = 0; si < a.n_sub; ++si) {
         const SubArgs &A = a.sub[si];
         // ---- edge attention of head c ------------------------------------------------------------------------
         attn_phase<M>(A, a.rows, row0, c, sq, sqr, sagg, sragg, ssal, smerge);
+        stamp();
         mbar_wait(&mbar[0], post_par);
         post_par ^= 1;
         __syncthreads();
+        stamp();
         // xd = LN_dst(x) (every CTA, full rows);  ragg' = g_r * ragg + b_r * sal (own head)
         for (int m = warp; m < M; m += NWARP) {
             st4(scat + m * 256 + 128 + 4 * lane,
@@ -464,6 +436,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
             }
         }
         cluster.sync();
+        stamp();
         // ---- gate: g = sigmoid(Wg [agg | xd] + bg);  u = agg + g * (s - agg) ----------------------------------
         slice_gemm<M, 16, 16>(scat, 256, wpost + cs_post::WG, 64, sred, [&](int m, int n, float v) {
             const float g = sigmoidf(v + wpost[cs_post::BG + n]);
@@ -473,6 +446,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
             for (int p = 0; p < CL; ++p) cluster.map_shared_rank(su, p)[m * 128 + 16 * c + n] = u;
         });
         cluster.sync();
+        stamp();
         // ---- to_out ------------------------------------------------------------------------------------------
         slice_gemm<M, 16, 16>(su, 128, wpost + cs_post::WO, 32, sred, [&](int m, int n, float v) {
             v += wpost[cs_post::BO + n];
@@ -480,6 +454,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
             for (int p = 0; p < CL; ++p) cluster.map_shared_rank(so, p)[m * 128 + 16 * c + n] = v;
         });
         cluster.sync();
+        stamp();
         // x1 = x + LN_post(o);  so = LN_ffpre(x1)
         for (int m = warp; m < M; m += NWARP) {
             float4 o = ld4(so + m * 128 + 4 * lane);
@@ -496,12 +471,14 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
             for (int p = 0; p < CL; ++p) cluster.map_shared_rank(sh, p)[m * 512 + 64 * c + n] = v;
         });
         cluster.sync();
+        stamp();
         slice_gemm<M, 16, 16>(sh, 512, wpost + cs_post::W2, 128, sred, [&](int m, int n, float v) {
             v += wpost[cs_post::B2 + n];
 #pragma unroll
             for (int p = 0; p < CL; ++p) cluster.map_shared_rank(sy, p)[m * 128 + 16 * c + n] = v;
         });
         cluster.sync();
+        stamp();
         // x2 = x1 + LN_ffpost(y)
         const bool last = si + 1 == a.n_sub;
         for (int m = warp; m < M; m += NWARP) {
@@ -518,7 +495,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
         __syncthreads();
         if (tid == 0 && !last)
             chunk_request(wpost, a.sub[si + 1].w + (size_t)c * cs_post::FLOATS, cs_post::FLOATS, &mbar[0]);
+        stamp();
         if (A.pre.w) do_pre(A.pre);
+        stamp();
     }
     // no CTA may exit while a peer can still write into its shared memory
     cluster.sync();

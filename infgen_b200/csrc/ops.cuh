@@ -17,6 +17,7 @@
 // so the per-edge 128x128 projections become per-node ones and edges only see dot products with rhat.
 #pragma once
 #include "common.cuh"
+#include "stream.cuh"
 
 namespace infgen {
 
@@ -95,57 +96,51 @@ __global__ void __launch_bounds__(NT) k_kv_project(const KvArgs a) {
 }
 
 // ===============================================================================================================
-// FourierEmbedding over tiles of FM slots.  slot s is valid iff cnt == NULL ? s < n_slots : (s % stride) < cnt[s / stride]
+// FourierEmbedding (layers.py:142-160) over tiles of FM slots, weights streamed (stream.cuh).
+// slot s is valid iff cnt == NULL ? s < n_slots : (s % stride) < cnt[s / stride]
 // ===============================================================================================================
-constexpr int FM = 32;
+constexpr int FM = 16;
 constexpr int FLD = 132;       // 129 Fourier features padded to a multiple of 4
+constexpr int HLD = 132;       // leading dimension of 128-wide activation tiles (132 % 32 == 4: conflict-free row lanes)
 
 struct FourierArgs {
     int n_slots;
     const int *cnt;
     int stride;
-    const float *raw;          // [slots][D]
+    int dim;                   // input_dim (2..4)
+    const float *raw;          // [slots][dim]
     FourierW w;
     const float *cat_tab;      // optional categorical sum rows [.][128]
     const int *cat_idx;        // [slots] row of cat_tab (when cat_tab != NULL; NULL -> row = slot)
     float *out;                // [slots][128]
     int normalize;             // 1: store (y - mean) / std of the output (input of every layer's attn_prenorm_r)
 };
+// several embeddings in one launch: CTA b serves job j with tile0[j] <= b < tile0[j+1]
+struct FourierBatch {
+    int n_jobs;
+    int tile0[4];
+    FourierArgs job[3];
+};
 
-template <int D>
-__global__ void __launch_bounds__(NT) k_fourier(const FourierArgs a) {
-    extern __shared__ __align__(16) float smem[];
-    float *sF = smem;                       // [FM][132]
-    float *sH = sF + FM * FLD;              // [FM][128]
-    float *sA = sH + FM * 128;              // [FM][128]
-    float *sred = sA + FM * 128;            // [FM][128]
-    float *sraw = sred + FM * 128;          // [FM][4]
-    __shared__ int s_valid[FM];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int s0 = blockIdx.x * FM;
-    int v = 0;
-    if (tid < FM) {
-        const int s = s0 + tid;
-        if (s < a.n_slots) v = a.cnt ? ((s % a.stride) < a.cnt[s / a.stride]) : 1;
-        s_valid[tid] = v;
-#pragma unroll
-        for (int d = 0; d < D; ++d) sraw[tid * 4 + d] = v ? a.raw[(size_t)s * D + d] : 0.f;
+__device__ __forceinline__ int fourier_segs(const FourierW &w, int dim, WSeg *segs) {
+    int n = 0;
+    for (int d = 0; d < dim; ++d) {
+        segs[n++] = WSeg{w.w0[d], 33, 512};
+        segs[n++] = WSeg{w.w3[d], 32, 512};
     }
-    if (!__syncthreads_or(v)) return;
-    // categorical sum seeds the accumulator (layers.py:156-159)
-    for (int m = warp; m < FM; m += NWARP) {
-        float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a.cat_tab && s_valid[m]) {
-            const int row = a.cat_idx ? a.cat_idx[s0 + m] : (s0 + m);
-            c = ld4(a.cat_tab + (size_t)row * 128 + 4 * lane);
-        }
-        st4(sA + m * 128 + 4 * lane, c);
-    }
-    const FourierW &w = a.w;
-#pragma unroll 1
-    for (int d = 0; d < D; ++d) {
-        __syncthreads();
-        for (int i = tid; i < FM * 64; i += NT) {
+    segs[n++] = WSeg{w.w_out, 32, 512};
+    return n;
+}
+
+// consumers: embedding of M rows whose raw inputs sit in sraw[m][4]; sA ([M][HLD], as sH) must hold the categorical seed (or
+// zeros); the result (before any standardisation) is left in sH.  Ends with a csync().
+template <int M>
+__device__ __forceinline__ void fourier_body(WsCons &ws, const FourierW &w, int dim, const float *sraw, float *sF,
+                                             float *sH, float *sA) {
+    const int tid = threadIdx.x;
+    for (int d = 0; d < dim; ++d) {
+        csync();
+        for (int i = tid; i < M * 64; i += NT) {
             const int m = i >> 6, j = i & 63;
             const float x = sraw[m * 4 + d];
             // x.unsqueeze(-1) * freqs * 2 * math.pi, evaluated left to right in fp32 (layers.py:151)
@@ -155,28 +150,71 @@ __global__ void __launch_bounds__(NT) k_fourier(const FourierArgs a) {
             sF[m * FLD + j] = cs;
             sF[m * FLD + 64 + j] = sn;
         }
-        if (tid < FM) {
+        if (tid < M) {
             sF[tid * FLD + 128] = sraw[tid * 4 + d];
             sF[tid * FLD + 129] = 0.f; sF[tid * FLD + 130] = 0.f; sF[tid * FLD + 131] = 0.f;
         }
-        __syncthreads();
-        block_gemm<FM, 128>(sF, FLD, w.w0[d], 128, 33, sred,
-                            [&](int m, int n, float v2) { sH[m * 128 + n] = v2 + __ldg(w.b0[d] + n); });
-        __syncthreads();
-        rows_layernorm<FM, true>(sH, 128, w.ln_g[d], w.ln_b[d]);
-        __syncthreads();
-        block_gemm<FM, 128>(sH, 128, w.w3[d], 128, 32, sred,
-                            [&](int m, int n, float v2) { sA[m * 128 + n] += v2 + __ldg(w.b3[d] + n); });
+        csync();
+        stream_gemm<M>(ws, sF, FLD, 33, [&](int m, int n, float v) { sH[m * HLD + n] = v + __ldg(w.b0[d] + n); });
+        csync();
+        rows_layernorm_c<M, true>(sH, HLD, w.ln_g[d], w.ln_b[d]);
+        csync();
+        stream_gemm<M>(ws, sH, HLD, 32, [&](int m, int n, float v) { sA[m * HLD + n] += v + __ldg(w.b3[d] + n); });
     }
-    __syncthreads();
-    rows_layernorm<FM, true>(sA, 128, w.out_ln_g, w.out_ln_b);
-    __syncthreads();
-    block_gemm<FM, 128>(sA, 128, w.w_out, 128, 32, sred,
-                        [&](int m, int n, float v2) { sH[m * 128 + n] = v2 + __ldg(w.b_out + n); });
-    __syncthreads();
+    csync();
+    rows_layernorm_c<M, true>(sA, HLD, w.out_ln_g, w.out_ln_b);
+    csync();
+    stream_gemm<M>(ws, sA, HLD, 32, [&](int m, int n, float v) { sH[m * HLD + n] = v + __ldg(w.b_out + n); });
+    csync();
+}
+
+constexpr int FOURIER_SMEM_FLOATS = WS_SMEM_FLOATS + FM * FLD + 2 * FM * HLD + FM * 4 + FM;
+constexpr size_t FOURIER_SMEM = (size_t)FOURIER_SMEM_FLOATS * sizeof(float);
+
+__global__ void __launch_bounds__(NT_S) k_fourier(const FourierBatch fb) {
+    extern __shared__ __align__(16) float smem[];
+    WsSmem wsm(smem);
+    float *sF = smem + WS_SMEM_FLOATS;      // [FM][132]
+    float *sH = sF + FM * FLD;              // [FM][HLD]
+    float *sA = sH + FM * HLD;              // [FM][HLD]
+    float *sraw = sA + FM * HLD;            // [FM][4]
+    int *s_valid = reinterpret_cast<int *>(sraw + FM * 4);
+    int j = 0;
+    while (j + 1 < fb.n_jobs && (int)blockIdx.x >= fb.tile0[j + 1]) ++j;
+    const FourierArgs &a = fb.job[j];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int s0 = ((int)blockIdx.x - fb.tile0[j]) * FM;
+    int v = 0;
+    if (tid < FM) {
+        const int s = s0 + tid;
+        if (s < a.n_slots) v = a.cnt ? ((s % a.stride) < a.cnt[s / a.stride]) : 1;
+        s_valid[tid] = v;
+        for (int d = 0; d < 4; ++d) sraw[tid * 4 + d] = (v && d < a.dim) ? a.raw[(size_t)s * a.dim + d] : 0.f;
+    }
+    if (!__syncthreads_or(v)) return;
+    ws_init(wsm);
+    if (warp == NWARP) {
+        if (lane < WS_STAGES) {
+            WSeg segs[WS_MAX_SEGS];
+            const int n = fourier_segs(a.w, a.dim, segs);
+            ws_produce(wsm, segs, n);
+        }
+        return;
+    }
+    WsCons ws(wsm);
+    // categorical sum seeds the accumulator (layers.py:156-159)
+    for (int m = warp; m < FM; m += NWARP) {
+        float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.cat_tab && s_valid[m]) {
+            const int row = a.cat_idx ? a.cat_idx[s0 + m] : (s0 + m);
+            c = ld4(a.cat_tab + (size_t)row * 128 + 4 * lane);
+        }
+        st4(sA + m * HLD + 4 * lane, c);
+    }
+    fourier_body<FM>(ws, a.w, a.dim, sraw, sF, sH, sA);
     for (int m = warp; m < FM; m += NWARP) {
         if (!s_valid[m]) continue;
-        float4 y = ld4(sH + m * 128 + 4 * lane);
+        float4 y = ld4(sH + m * HLD + 4 * lane);
         if (a.normalize) {
             float mean, rstd;
             ln_stats(y, mean, rstd);
@@ -185,90 +223,83 @@ __global__ void __launch_bounds__(NT) k_fourier(const FourierArgs a) {
         st4(a.out + (size_t)(s0 + m) * 128 + 4 * lane, y);
     }
 }
-constexpr size_t FOURIER_SMEM = (size_t)(FM * FLD + 3 * FM * 128 + FM * 4) * sizeof(float);
 
 // ===============================================================================================================
-// MLPEmbedding: x[n][kin] -> 128 (LN, ReLU) -> 128 (LN, ReLU) -> 128.  Fusion mode gathers the four 128-blocks
-// [token_emb | x_a_emb | state_emb | grid_emb] of agent_decoder.py:503-507 / 2282-2286 instead of reading x.
+// MLPEmbedding (layers.py:170-189): x[n][kin] -> 128 (LN, ReLU) -> 128 (LN, ReLU) -> 128, tiles of EM rows
 // ===============================================================================================================
 constexpr int EM = 16;
+
+__device__ __forceinline__ int mlp3_segs(const MlpEmbW &w, int k4, WSeg *segs) {
+    segs[0] = WSeg{w.w0, k4, 512};
+    segs[1] = WSeg{w.w3, 32, 512};
+    segs[2] = WSeg{w.w6, 32, 512};
+    return 3;
+}
+// consumers: sX [M][ldx] -> epi(m, n, value); sH, sG: [M][HLD] scratch.  The caller csync()s after filling sX.
+template <int M, typename Epi>
+__device__ __forceinline__ void mlp3_body(WsCons &ws, const MlpEmbW &w, const float *sX, int ldx, int k4, float *sH,
+                                          float *sG, Epi epi) {
+    stream_gemm<M>(ws, sX, ldx, k4, [&](int m, int n, float v) { sH[m * HLD + n] = v + __ldg(w.b0 + n); });
+    csync();
+    rows_layernorm_c<M, true>(sH, HLD, w.ln1_g, w.ln1_b);
+    csync();
+    stream_gemm<M>(ws, sH, HLD, 32, [&](int m, int n, float v) { sG[m * HLD + n] = v + __ldg(w.b3 + n); });
+    csync();
+    rows_layernorm_c<M, true>(sG, HLD, w.ln4_g, w.ln4_b);
+    csync();
+    stream_gemm<M>(ws, sG, HLD, 32, [&](int m, int n, float v) { epi(m, n, v + __ldg(w.b6 + n)); });
+}
+// leading dimension of a [rows][4*k4] input tile: padded so that it is 4 (mod 32) floats when wide
+__host__ __device__ __forceinline__ int mlp_ldx(int k4) { return k4 * 4 + ((k4 * 4) % 32 == 0 ? 4 : 0); }
 
 struct MlpEmbArgs {
     RowSpace rows;
     MlpEmbW w;
     int kin;                   // real input width
     int k4;                    // packed K4 of the first Linear
-    const float *x;            // [n][kin] (plain mode), row stride x_ld floats
+    const float *x;            // [n][kin], row stride x_ld floats
     int x_ld;
-    // fusion mode
-    int fusion;
-    const float *tok_tab;      // [3][token_size+2][128]
-    const int *tok_row;        // [R] row in tok_tab (type*(token_size+2) + index)
-    const float *xa;           // [R][128]
-    const float *state_tab;    // [4][128]
-    const int *state_idx;      // [R]
-    const float *grid_tab;     // [grid_size+1][128]
-    const int *grid_row;       // [R]
     float *out;                // [n][128]
     int out_ld;                // floats between output rows (128, or more to scatter into a wider table)
 };
 
-__global__ void __launch_bounds__(NT) k_mlp_embed(const MlpEmbArgs a) {
+__global__ void __launch_bounds__(NT_S) k_mlp_embed(const MlpEmbArgs a) {
     extern __shared__ __align__(16) float smem[];
-    const int ldx = a.k4 * 4;
-    float *sX = smem;                        // [EM][ldx]
-    float *sH = sX + EM * ldx;               // [EM][128]
-    float *sG = sH + EM * 128;               // [EM][128]
-    float *sred = sG + EM * 128;             // [EM][128]
+    WsSmem wsm(smem);
+    const int ldx = mlp_ldx(a.k4);
+    float *sX = smem + WS_SMEM_FLOATS;       // [EM][ldx]
+    float *sH = sX + EM * ldx;               // [EM][HLD]
+    float *sG = sH + EM * HLD;               // [EM][HLD]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row0 = blockIdx.x * EM;
     bool any = false;
     for (int m = 0; m < EM; ++m) any |= a.rows.active(row0 + m);
     if (!any) return;
-    if (a.fusion) {
-        for (int m = warp; m < EM; m += NWARP) {
-            const int r = row0 + m;
-            float4 t = make_float4(0.f, 0.f, 0.f, 0.f), x = t, s = t, g = t;
-            if (a.rows.active(r)) {
-                t = ld4(a.tok_tab + (size_t)a.tok_row[r] * 128 + 4 * lane);
-                x = ld4(a.xa + (size_t)r * 128 + 4 * lane);
-                s = ld4(a.state_tab + (size_t)a.state_idx[r] * 128 + 4 * lane);
-                g = ld4(a.grid_tab + (size_t)a.grid_row[r] * 128 + 4 * lane);
-            }
-            st4(sX + m * ldx + 4 * lane, t);
-            st4(sX + m * ldx + 128 + 4 * lane, x);
-            st4(sX + m * ldx + 256 + 4 * lane, s);
-            st4(sX + m * ldx + 384 + 4 * lane, g);
+    ws_init(wsm);
+    if (warp == NWARP) {
+        if (lane < WS_STAGES) {
+            WSeg segs[3];
+            ws_produce(wsm, segs, mlp3_segs(a.w, a.k4, segs));
         }
-    } else {
-        for (int i = tid; i < EM * ldx; i += NT) {
-            const int m = i / ldx, k = i % ldx;
-            const int r = row0 + m;
-            sX[i] = (k < a.kin && a.rows.active(r)) ? a.x[(size_t)r * a.x_ld + k] : 0.f;
-        }
+        return;
     }
-    __syncthreads();
-    const MlpEmbW &w = a.w;
-    block_gemm<EM, 128>(sX, ldx, w.w0, 128, a.k4, sred,
-                        [&](int m, int n, float v) { sH[m * 128 + n] = v + __ldg(w.b0 + n); });
-    __syncthreads();
-    rows_layernorm<EM, true>(sH, 128, w.ln1_g, w.ln1_b);
-    __syncthreads();
-    block_gemm<EM, 128>(sH, 128, w.w3, 128, 32, sred,
-                        [&](int m, int n, float v) { sG[m * 128 + n] = v + __ldg(w.b3 + n); });
-    __syncthreads();
-    rows_layernorm<EM, true>(sG, 128, w.ln4_g, w.ln4_b);
-    __syncthreads();
-    block_gemm<EM, 128>(sG, 128, w.w6, 128, 32, sred, [&](int m, int n, float v) {
+    WsCons ws(wsm);
+    for (int i = tid; i < EM * ldx; i += NT) {
+        const int m = i / ldx, k = i % ldx;
         const int r = row0 + m;
-        if (a.rows.active(r)) a.out[(size_t)r * a.out_ld + n] = v + __ldg(w.b6 + n);
+        sX[i] = (k < a.kin && a.rows.active(r)) ? a.x[(size_t)r * a.x_ld + k] : 0.f;
+    }
+    csync();
+    mlp3_body<EM>(ws, a.w, sX, ldx, a.k4, sH, sG, [&](int m, int n, float v) {
+        const int r = row0 + m;
+        if (a.rows.active(r)) a.out[(size_t)r * a.out_ld + n] = v;
     });
 }
-static inline size_t mlp_embed_smem(int k4) { return (size_t)(EM * k4 * 4 + 3 * EM * 128) * sizeof(float); }
+static inline size_t mlp_embed_smem(int k4) { return (size_t)(WS_SMEM_FLOATS + EM * mlp_ldx(k4) + 2 * EM * HLD) * sizeof(float); }
 
 // ===============================================================================================================
-// heads: token_predict_head logits for one 256-wide vocabulary slice + per-slice top-KTOP / max / sum-exp, and
-// (slice 0) the state head.  grid = (row tiles, vocab slices)
+// heads (agent_decoder.py:2160-2167): grid = (row tiles of HM, NSLICE + 1).  y < NSLICE: token_predict_head hidden
+// layer + the logits of vocabulary slice y (256 wide) + per-slice top-KTOP / max / sum-exp;  y == NSLICE: state head.
 // ===============================================================================================================
 constexpr int HM = 8;          // rows per CTA
 constexpr int KTOP = 5;        // candidates kept per slice (>= motion_beam_size)
@@ -286,17 +317,38 @@ struct HeadArgs {
     float *trace_logits;       // optional [R][2048]
     float *trace_state;        // optional [R][3]
 };
+constexpr size_t HEADS_SMEM = (size_t)(WS_SMEM_FLOATS + 2 * HM * HLD + HM * 256) * sizeof(float);
 
-__global__ void __launch_bounds__(NT) k_heads(const HeadArgs a) {
-    __shared__ __align__(16) float sx[HM * 128];
-    __shared__ __align__(16) float sh[HM * 128];
-    __shared__ __align__(16) float sred[HM * 128];
-    __shared__ __align__(16) float slog[HM * 256];
+__global__ void __launch_bounds__(NT_S) k_heads(const HeadArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    WsSmem wsm(smem);
+    float *sx = smem + WS_SMEM_FLOATS;       // [HM][HLD]
+    float *sh = sx + HM * HLD;               // [HM][HLD]
+    float *slog = sh + HM * HLD;             // [HM][256]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row0 = blockIdx.x * HM, slice = blockIdx.y;
+    const bool is_state = slice == NSLICE;
+    const MlpHeadW &hw = is_state ? a.st : a.tok;
     bool any = false;
     for (int m = 0; m < HM; ++m) any |= a.rows.active(row0 + m);
     if (!any) return;
+    ws_init(wsm);
+    if (warp == NWARP) {
+        if (lane < WS_STAGES) {
+            WSeg segs[3];
+            segs[0] = WSeg{hw.w0, 32, 512};
+            int n = 1;
+            if (is_state) {
+                segs[n++] = WSeg{hw.w3, 32, hw.n_pad * 4};
+            } else {
+                segs[n++] = WSeg{hw.w3 + (size_t)slice * 256 * 4, 32, hw.n_pad * 4};
+                segs[n++] = WSeg{hw.w3 + (size_t)(slice * 256 + 128) * 4, 32, hw.n_pad * 4};
+            }
+            ws_produce(wsm, segs, n);
+        }
+        return;
+    }
+    WsCons ws(wsm);
     for (int m = warp; m < HM; m += NWARP) {
         const int r = row0 + m;
         float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -304,21 +356,34 @@ __global__ void __launch_bounds__(NT) k_heads(const HeadArgs a) {
             x = ld4(a.x + (size_t)r * 128 + 4 * lane);
             if (slice == 0 && a.trace_head_in) st4(a.trace_head_in + (size_t)r * 128 + 4 * lane, x);
         }
-        st4(sx + m * 128 + 4 * lane, x);
+        st4(sx + m * HLD + 4 * lane, x);
     }
-    __syncthreads();
-    block_gemm<HM, 128>(sx, 128, a.tok.w0, 128, 32, sred,
-                        [&](int m, int n, float v) { sh[m * 128 + n] = v + __ldg(a.tok.b0 + n); });
-    __syncthreads();
-    rows_layernorm<HM, true>(sh, 128, a.tok.ln_g, a.tok.ln_b);
-    __syncthreads();
-    block_gemm<HM, 256>(sh, 128, a.tok.w3 + (size_t)slice * 256 * 4, a.tok.n_pad, 32, sred, [&](int m, int n, float v) {
-        v += __ldg(a.tok.b3 + slice * 256 + n);
-        slog[m * 256 + n] = v;
-        const int r = row0 + m;
-        if (a.trace_logits && a.rows.active(r)) a.trace_logits[(size_t)r * a.tok.n_out + slice * 256 + n] = v;
-    });
-    __syncthreads();
+    csync();
+    stream_gemm<HM>(ws, sx, HLD, 32, [&](int m, int n, float v) { sh[m * HLD + n] = v + __ldg(hw.b0 + n); });
+    csync();
+    rows_layernorm_c<HM, true>(sh, HLD, hw.ln_g, hw.ln_b);
+    csync();
+    if (is_state) {                          // agent_decoder.py:2166
+        stream_gemm<HM>(ws, sh, HLD, 32, [&](int m, int n, float v) {
+            const int r = row0 + m;
+            if (n < hw.n_out && a.rows.active(r)) {
+                v += __ldg(hw.b3 + n);
+                a.state_logits[(size_t)r * 4 + n] = v;
+                if (a.trace_state) a.trace_state[(size_t)r * 3 + n] = v;
+            }
+        });
+        return;
+    }
+    for (int half = 0; half < 2; ++half) {
+        stream_gemm<HM>(ws, sh, HLD, 32, [&](int m, int n, float v) {
+            const int col = half * 128 + n;
+            v += __ldg(hw.b3 + slice * 256 + col);
+            slog[m * 256 + col] = v;
+            const int r = row0 + m;
+            if (a.trace_logits && a.rows.active(r)) a.trace_logits[(size_t)r * hw.n_out + slice * 256 + col] = v;
+        });
+    }
+    csync();
     // per-row top-KTOP of the slice: one warp per row, 8 values per lane
     for (int m = warp; m < HM; m += NWARP) {
         const int r = row0 + m;
@@ -362,22 +427,6 @@ __global__ void __launch_bounds__(NT) k_heads(const HeadArgs a) {
             a.part_s[(size_t)r * NSLICE + slice] = ssum;
         }
     }
-    if (slice != 0) return;
-    // state head (agent_decoder.py:2166)
-    __syncthreads();
-    block_gemm<HM, 128>(sx, 128, a.st.w0, 128, 32, sred,
-                        [&](int m, int n, float v) { sh[m * 128 + n] = v + __ldg(a.st.b0 + n); });
-    __syncthreads();
-    rows_layernorm<HM, true>(sh, 128, a.st.ln_g, a.st.ln_b);
-    __syncthreads();
-    block_gemm<HM, 128>(sh, 128, a.st.w3, 128, 32, sred, [&](int m, int n, float v) {
-        const int r = row0 + m;
-        if (n < a.st.n_out && a.rows.active(r)) {
-            v += __ldg(a.st.b3 + n);
-            a.state_logits[(size_t)r * 4 + n] = v;
-            if (a.trace_state) a.trace_state[(size_t)r * 3 + n] = v;
-        }
-    });
 }
 
 // rhat = (r - mean) / sqrt(var + eps): the layer-independent part of every attn_prenorm_r (one warp per row)
@@ -391,36 +440,44 @@ __global__ void k_standardize(const float *r, float *out, int n) {
         make_float4((y.x - mean) * rstd, (y.y - mean) * rstd, (y.z - mean) * rstd, (y.w - mean) * rstd));
 }
 
-// Generic MLPLayer for operator-level parity (any n_out that is a multiple of 128 after padding)
+// Generic MLPLayer (layers.py:206-215) for operator-level parity: grid = (row tiles of HM, 128-column tiles)
 struct MlpLayerArgs {
     int n;
     const float *x;
     MlpHeadW w;
     float *out;                // [n][n_out]
 };
-__global__ void __launch_bounds__(NT) k_mlp_layer(const MlpLayerArgs a) {
-    __shared__ __align__(16) float sx[HM * 128];
-    __shared__ __align__(16) float sh[HM * 128];
-    __shared__ __align__(16) float sred[HM * 128];
+constexpr size_t MLP_LAYER_SMEM = (size_t)(WS_SMEM_FLOATS + 2 * HM * HLD) * sizeof(float);
+__global__ void __launch_bounds__(NT_S) k_mlp_layer(const MlpLayerArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    WsSmem wsm(smem);
+    float *sx = smem + WS_SMEM_FLOATS, *sh = sx + HM * HLD;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row0 = blockIdx.x * HM;
+    const int row0 = blockIdx.x * HM, n0 = blockIdx.y * 128;
+    ws_init(wsm);
+    if (warp == NWARP) {
+        if (lane < WS_STAGES) {
+            WSeg segs[2];
+            segs[0] = WSeg{a.w.w0, a.w.k4_in, 512};
+            segs[1] = WSeg{a.w.w3 + (size_t)n0 * 4, 32, a.w.n_pad * 4};
+            ws_produce(wsm, segs, 2);
+        }
+        return;
+    }
+    WsCons ws(wsm);
     for (int m = warp; m < HM; m += NWARP) {
         const int r = row0 + m;
-        st4(sx + m * 128 + 4 * lane, r < a.n ? ld4(a.x + (size_t)r * 128 + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f));
+        st4(sx + m * HLD + 4 * lane, r < a.n ? ld4(a.x + (size_t)r * 128 + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f));
     }
-    __syncthreads();
-    block_gemm<HM, 128>(sx, 128, a.w.w0, 128, a.w.k4_in, sred,
-                        [&](int m, int n, float v) { sh[m * 128 + n] = v + __ldg(a.w.b0 + n); });
-    __syncthreads();
-    rows_layernorm<HM, true>(sh, 128, a.w.ln_g, a.w.ln_b);
-    __syncthreads();
-    for (int n0 = blockIdx.y * 128; n0 < a.w.n_pad; n0 += gridDim.y * 128) {
-        block_gemm<HM, 128>(sh, 128, a.w.w3 + (size_t)n0 * 4, a.w.n_pad, 32, sred, [&](int m, int n, float v) {
-            const int r = row0 + m;
-            if (r < a.n && n0 + n < a.w.n_out) a.out[(size_t)r * a.w.n_out + n0 + n] = v + __ldg(a.w.b3 + n0 + n);
-        });
-        __syncthreads();
-    }
+    csync();
+    stream_gemm<HM>(ws, sx, HLD, a.w.k4_in, [&](int m, int n, float v) { sh[m * HLD + n] = v + __ldg(a.w.b0 + n); });
+    csync();
+    rows_layernorm_c<HM, true>(sh, HLD, a.w.ln_g, a.w.ln_b);
+    csync();
+    stream_gemm<HM>(ws, sh, HLD, 32, [&](int m, int n, float v) {
+        const int r = row0 + m;
+        if (r < a.n && n0 + n < a.w.n_out) a.out[(size_t)r * a.w.n_out + n0 + n] = v + __ldg(a.w.b3 + n0 + n);
+    });
 }
 
 }  // namespace infgen
