@@ -322,9 +322,10 @@ static float *fbuf(infgen_engine *e, const char *name) { return (float *)e->bufs
 static inline void count_launch(infgen_engine *e) { if (!e->capturing) e->launches++; }
 
 // per-kernel-class device timing (bench.py roofline leg): event pairs around every launch, plain launches only
-enum KClass { KC_EDGE_BUILD, KC_FOURIER, KC_EMBED, KC_LAYER_TM, KC_LAYER_A, KC_HEADS, KC_ADVANCE, KC_MISC, KC_COUNT };
-static const char *KCLASS_NAME[KC_COUNT] = {"k_edge_build", "k_fourier:edges", "k_embed_column", "k_layer:temporal+map",
-                                            "k_layer:agent", "k_heads", "k_advance", "misc"};
+enum KClass { KC_EDGE_BUILD, KC_FOURIER, KC_EMBED, KC_LAYER_STACK, KC_LAYER_TM, KC_LAYER_A, KC_HEADS, KC_ADVANCE, KC_MISC,
+              KC_COUNT };
+static const char *KCLASS_NAME[KC_COUNT] = {"k_edge_build", "k_fourier:edges", "k_embed_column", "k_layer:stack18",
+                                            "k_layer:temporal+map", "k_layer:agent", "k_heads", "k_advance", "misc"};
 struct ProfScope {
     infgen_engine *e;
     bool on;
@@ -348,7 +349,7 @@ static const int MAX_CLUSTERS = 15;
 static int launch_layer(infgen_engine *e, const LayerArgs &a_in, int cls) {
     LayerArgs a = a_in;
     if (e->bufs.count("tstamp") && e->bufs["tstamp"].p)
-        a.tstamp = (long long *)e->bufs["tstamp"].p + (cls == KC_LAYER_A ? 32 : 0);
+        a.tstamp = (long long *)e->bufs["tstamp"].p + (cls == KC_LAYER_A ? 256 : 0);
     ProfScope ps(e, cls);
     const int M = e->row_tile;
     const int clusters = (a.rows.n_total + M - 1) / M;
@@ -426,45 +427,54 @@ static int enqueue_embed_column(infgen_engine *e, int col_add) {
     return 0;
 }
 
-// the 18-layer stack for the current column: per layer index i one launch for temporal + map->agent (their K/V are
-// cached) and one for agent<->agent (its K/V rows come from every row of the scene, written by the launch before).
-// with_edges=false: history columns that receive no edges (prefill).
+// the 18-layer stack for the current column.  When every cluster of the launch is co-resident (<= MAX_CLUSTERS, i.e. up
+// to 120 rows) ONE launch runs all 18 layers with a grid barrier before each agent<->agent attention (its K/V rows come
+// from every row of the scene); otherwise one launch per {temporal + map} and per {agent} layer, whose K/V exchange is
+// the launch boundary.  with_edges=false: history columns that receive no edges (prefill).
 static int enqueue_layers(infgen_engine *e, bool with_edges, int trace_iter) {
     DecState &s = e->st;
     const int R = e->R;
     float *kv_t = fbuf(e, "kv_t"), *kv_m = fbuf(e, "kv_m"), *kv_a = fbuf(e, "kv_a");
-    const size_t kv_t_layer = (size_t)R * RING * 256, kv_m_layer = (size_t)e->P * 256;
+    const size_t kv_t_layer = (size_t)R * RING * 256, kv_m_layer = (size_t)e->P * 256, kv_a_buf = (size_t)R * 256;
     LayerArgs base;
     memset(&base, 0, sizeof(base));
     base.rows = scene_rows(e); base.x = fbuf(e, "x"); base.q = fbuf(e, "q"); base.s = fbuf(e, "s"); base.qr = fbuf(e, "qr");
-    base.col_ptr = s.col; base.ring = RING;
+    base.col_ptr = s.col; base.ring = RING; base.grid_bar = (unsigned *)e->bufs["grid_bar"].p;
+    const bool fused = (R + e->row_tile - 1) / e->row_tile <= MAX_CLUSTERS;
+    auto fill = [&](int i, SubArgs &t, SubArgs &m, SubArgs &g) {
+        float *kva = kv_a + (size_t)(i & 1) * kv_a_buf;
+        t.w = e->t[i].cs_post; t.has_attn = with_edges; t.has_pos = 1; t.elist = 0;
+        t.kv = kv_t + i * kv_t_layer; t.cnt = s.t_cnt; t.start = nullptr; t.stride = s.W; t.src = s.t_src;
+        t.rhat = fbuf(e, "rhat_t");
+        t.pre = make_pre(e->m[i], false, nullptr, false, 0, false);
+        m.w = e->m[i].cs_post; m.has_attn = with_edges; m.has_pos = 1; m.elist = 1;
+        m.kv = kv_m + i * kv_m_layer; m.cnt = s.m_cnt; m.start = nullptr; m.stride = s.max_m; m.src = s.m_src;
+        m.rhat = fbuf(e, "rhat_m");
+        m.pre = make_pre(e->a[i], true, kva, false, 0, !fused);
+        g.w = e->a[i].cs_post; g.has_attn = with_edges; g.has_pos = 1; g.elist = 2;
+        g.kv = kva; g.cnt = s.a_cnt; g.start = s.a_start; g.stride = 0; g.src = s.a_src; g.rhat = fbuf(e, "rhat_a");
+        g.grid_sync = fused ? 1 : 0;
+        if (i < 5) g.pre = make_pre(e->t[i + 1], true, kv_t + (i + 1) * kv_t_layer, true, 0, !fused);
+        if (trace_iter >= 0 && e->cfg.trace)
+            g.trace_out = fbuf(e, "trace_layer_out") + ((size_t)trace_iter * 6 + i) * R * 128;
+    };
+    if (fused) {
+        LayerArgs la = base;
+        la.pre0 = make_pre(e->t[0], true, kv_t, true, 0, false);
+        la.n_sub = 18;
+        for (int i = 0; i < 6; ++i) fill(i, la.sub[3 * i], la.sub[3 * i + 1], la.sub[3 * i + 2]);
+        CK(cudaMemsetAsync(base.grid_bar, 0, sizeof(unsigned), e->stream));
+        RET(launch_layer(e, la, KC_LAYER_STACK));
+        return 0;
+    }
     for (int i = 0; i < 6; ++i) {
-        {   // temporal layer i, map->agent layer i, projections of agent<->agent layer i
-            LayerArgs la = base;
-            if (i == 0) la.pre0 = make_pre(e->t[0], true, kv_t, true, 0, false);
-            la.n_sub = 2;
-            SubArgs &t = la.sub[0], &m = la.sub[1];
-            t.w = e->t[i].cs_post; t.has_attn = with_edges; t.has_pos = 1;
-            t.kv = kv_t + i * kv_t_layer; t.cnt = s.t_cnt; t.start = nullptr; t.stride = s.W; t.src = s.t_src;
-            t.rhat = fbuf(e, "rhat_t");
-            t.pre = make_pre(e->m[i], false, nullptr, false, 0, false);
-            m.w = e->m[i].cs_post; m.has_attn = with_edges; m.has_pos = 1;
-            m.kv = kv_m + i * kv_m_layer; m.cnt = s.m_cnt; m.start = nullptr; m.stride = s.max_m; m.src = s.m_src;
-            m.rhat = fbuf(e, "rhat_m");
-            m.pre = make_pre(e->a[i], true, kv_a, false, 0, true);
-            RET(launch_layer(e, la, KC_LAYER_TM));
-        }
-        {   // agent<->agent layer i, projections of temporal layer i+1
-            LayerArgs la = base;
-            la.n_sub = 1;
-            SubArgs &g = la.sub[0];
-            g.w = e->a[i].cs_post; g.has_attn = with_edges; g.has_pos = 1;
-            g.kv = kv_a; g.cnt = s.a_cnt; g.start = s.a_start; g.stride = 0; g.src = s.a_src; g.rhat = fbuf(e, "rhat_a");
-            if (i < 5) g.pre = make_pre(e->t[i + 1], true, kv_t + (i + 1) * kv_t_layer, true, 0, true);
-            if (trace_iter >= 0 && e->cfg.trace)
-                g.trace_out = fbuf(e, "trace_layer_out") + ((size_t)trace_iter * 6 + i) * R * 128;
-            RET(launch_layer(e, la, KC_LAYER_A));
-        }
+        LayerArgs tm = base, ag = base;
+        if (i == 0) tm.pre0 = make_pre(e->t[0], true, kv_t, true, 0, false);
+        tm.n_sub = 2; ag.n_sub = 1;
+        fill(i, tm.sub[0], tm.sub[1], ag.sub[0]);
+        ag.sub[0].elist = 0;
+        RET(launch_layer(e, tm, KC_LAYER_TM));
+        RET(launch_layer(e, ag, KC_LAYER_A));
     }
     return 0;
 }
@@ -773,13 +783,14 @@ int32_t infgen_load_scenes(infgen_engine *e, const infgen_scene_batch *b, int32_
     RET(ensure_t(e, "qr", (size_t)R * 1024, &tmp)); RET(ensure_t(e, "agg", (size_t)R * 128, &tmp));
     RET(ensure_t(e, "ragg", (size_t)R * 1024, &tmp)); RET(ensure_t(e, "sal", (size_t)R * 8, &tmp));
     RET(ensure_t(e, "zero", (size_t)R * 1024, &tmp)); RET(ensure_t(e, "xa", (size_t)R * 128, &tmp));
-    RET(ensure_t(e, "kv_t", (size_t)6 * R * RING * 256, &tmp)); RET(ensure_t(e, "kv_a", (size_t)R * 256, &tmp));
+    RET(ensure_t(e, "kv_t", (size_t)6 * R * RING * 256, &tmp)); RET(ensure_t(e, "kv_a", (size_t)2 * R * 256, &tmp));
+    { unsigned *gb; RET(ensure_t(e, "grid_bar", 4, &gb)); }
     RET(ensure_t(e, "kv_m", (size_t)6 * std::max(P, 1) * 256, &tmp));
     RET(ensure_t(e, "rhat_t", (size_t)R * W * 128, &tmp)); RET(ensure_t(e, "rhat_m", (size_t)R * MM * 128, &tmp));
     RET(ensure_t(e, "rhat_a", (size_t)R * cap * 128, &tmp));
     RET(ensure_t(e, "cat_tab", (size_t)(R + 1) * 128, &tmp)); RET(ensure_t(e, "shape_rows", (size_t)(R + 1) * 4, &tmp));
     RET(ensure_t(e, "hist_traj", (size_t)R * HC * 5 * 2, &tmp)); RET(ensure_t(e, "hist_head", (size_t)R * HC * 5, &tmp));
-    if (getenv("INFGEN_TSTAMP")) { long long *ts; RET(ensure_t(e, "tstamp", 64, &ts)); }
+    if (getenv("INFGEN_TSTAMP")) { long long *ts; RET(ensure_t(e, "tstamp", 512, &ts)); }
     if (e->cfg.trace && S > 0) {
         RET(ensure_t(e, "trace_head_in", (size_t)S * R * 128, &tmp));
         RET(ensure_t(e, "trace_token_logits", (size_t)S * R * V, &tmp));

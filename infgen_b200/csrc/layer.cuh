@@ -83,7 +83,11 @@ struct SubArgs {
     const float *rhat;         // [slots][128]
     PreArgs pre;               // projections of the following layer
     float *trace_out;          // optional copy of the layer output [R][128]
+    int elist;                 // which of the (up to 3) distinct edge lists of the launch this layer uses
+    int grid_sync;             // wait for every CTA of the grid before the attention (K/V written by other clusters in
+                               // this launch); only legal when the whole grid is co-resident
 };
+constexpr int MAX_SUB = 18;
 struct LayerArgs {
     RowSpace rows;
     float *x;                  // [R][128] residual stream, updated in place
@@ -92,23 +96,30 @@ struct LayerArgs {
     int ring;                  // ring depth
     PreArgs pre0;              // optional projections run before the first layer (else q/s/qr come from global)
     int n_sub;
-    SubArgs sub[2];
-    long long *tstamp;         // optional [32] clock64 stamps of CTA 0 (debug: phase breakdown)
+    SubArgs sub[MAX_SUB];
+    unsigned *grid_bar;        // zeroed counter for the grid barriers (grid_sync)
+    long long *tstamp;         // optional [256] clock64 stamps of CTA 0 (debug: phase breakdown)
 };
+
+// leading dimensions of the activation tiles: 4 (mod 32) floats so that the row lanes of slice_gemm hit distinct banks
+constexpr int LD1 = 132;       // 128-wide tiles
+constexpr int LD2 = 260;       // [agg | x_dst]
+constexpr int LD5 = 516;       // FFN hidden
+constexpr int RED_FLOATS = 16 * (NT + 16);   // k-split partials: up to 16 registers x (NT + pad) floats
 
 template <int M>
 struct LayerSmem {
     static constexpr int WPOST = 0;
     static constexpr int WPRE = WPOST + cs_post::FLOATS;
-    static constexpr int X = WPRE + cs_pre::FLOATS;       // [M][128] residual
-    static constexpr int CAT = X + M * 128;               // [M][256] agg | LN_dst(x)
-    static constexpr int U = CAT + M * 256;               // [M][128]
-    static constexpr int O = U + M * 128;                 // [M][128]
-    static constexpr int H = O + M * 128;                 // [M][512]
-    static constexpr int Y = H + M * 512;                 // [M][128]
-    static constexpr int RED = Y + M * 128;               // k-split partials
-    static constexpr int RAGG = RED + M * 256 + 256;      // [M][128] own head
-    static constexpr int QR = RAGG + M * 128;             // [M][128] own head
+    static constexpr int X = WPRE + cs_pre::FLOATS;       // [M][LD1] residual
+    static constexpr int CAT = X + M * LD1;               // [M][LD2] agg | LN_dst(x)
+    static constexpr int U = CAT + M * LD2;               // [M][LD1]
+    static constexpr int O = U + M * LD1;                 // [M][LD1]
+    static constexpr int H = O + M * LD1;                 // [M][LD5]
+    static constexpr int Y = H + M * LD5;                 // [M][LD1]
+    static constexpr int RED = Y + M * LD1;               // k-split partials
+    static constexpr int RAGG = RED + RED_FLOATS;         // [M][LD1] own head
+    static constexpr int QR = RAGG + M * LD1;             // [M][128] own head
     static constexpr int Q = QR + M * 128;                // [M][16]
     static constexpr int S = Q + M * 16;                  // [M][16]
     static constexpr int AGG = S + M * 16;                // [M][16]
@@ -117,6 +128,7 @@ struct LayerSmem {
     static constexpr int MBAR = MERGE + NWARP * 160;      // 2 x uint64
     static constexpr int TOTAL = MBAR + 4;
     static constexpr size_t BYTES = (size_t)TOTAL * sizeof(float);
+    static_assert(BYTES <= 227 * 1024, "shared memory budget");
 };
 
 // LayerNorm of a 128-vector (4 channels per lane) with the affine vectors in shared (or any generic) memory
@@ -133,92 +145,143 @@ __device__ __forceinline__ float dot4(const float4 a, const float4 b) {
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Column-slice GEMM:  Y[m][n] = sum_k X[m][k] W[k][n],  m < M, n < NL, k < 4*K4.
-//   X  shared, row-major, leading dimension ldx;  W shared, [K4][NL][4];  the K range is split over KS thread groups
-//   (NL * KS == NT) and reduced through `red`;  epi(m, n, value) runs once per output.  Contains one __syncthreads().
+//   X  shared, row-major, leading dimension ldx (4 mod 32);  W shared, [K4][NL][4].
+//   A thread owns a 4 x TN register tile (rows 4*rg + i, columns cg + NCG*j) for one of KS k-slices - shared-memory
+//   bandwidth, not FFMA issue, bounds these tiny GEMMs, and the tile cuts the loads per FMA to (4 + TN) / (16 TN) -
+//   and the KS partial tiles are reduced through `red` ([register][thread] layout, conflict-free both ways).
+//   epi(m, n, value) runs once per output.  Contains one __syncthreads().
 // ---------------------------------------------------------------------------------------------------------------------
-template <int M, int NL, int KS, typename Epi>
+template <int M, int NL, int TN, typename Epi>
 __device__ __forceinline__ void slice_gemm(const float *xs, int ldx, const float *w, int K4, float *red, Epi epi) {
-    static_assert(NL * KS == NT, "thread mapping");
-    constexpr int PAD = (NL == 16) ? 16 : 0;             // de-conflict the two k-groups of a warp
-    constexpr int KSTRIDE = M * NL + PAD;
-    static_assert(KS * KSTRIDE <= M * 256 + 256, "reduction scratch too small");
-    const int tid = threadIdx.x, col = tid % NL, ks = tid / NL;
-    float acc[M];
+    constexpr int NCG = NL / TN, RG = M / 4, KS = NT / (NCG * RG);
+    constexpr int RSTR = NT + NCG;                         // floats per register row of the partial buffer
+    static_assert(NCG * RG * KS == NT && M % 4 == 0, "thread mapping");
+    static_assert(4 * TN * RSTR <= RED_FLOATS, "reduction scratch too small");
+    const int tid = threadIdx.x, cg = tid % NCG, rg = (tid / NCG) % RG, ks = tid / (NCG * RG);
+    float acc[4][TN];
 #pragma unroll
-    for (int m = 0; m < M; ++m) acc[m] = 0.f;
-#pragma unroll 4
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    const float *xr = xs + (size_t)(4 * rg) * ldx;
+#pragma unroll 2
     for (int k4 = ks; k4 < K4; k4 += KS) {
-        const float4 wv = ld4(w + (k4 * NL + col) * 4);
+        float4 wv[TN];
 #pragma unroll
-        for (int m = 0; m < M; ++m) {
-            const float4 x = ld4(xs + m * ldx + 4 * k4);
-            acc[m] = fmaf(x.x, wv.x, acc[m]);
-            acc[m] = fmaf(x.y, wv.y, acc[m]);
-            acc[m] = fmaf(x.z, wv.z, acc[m]);
-            acc[m] = fmaf(x.w, wv.w, acc[m]);
+        for (int j = 0; j < TN; ++j) wv[j] = ld4(w + (k4 * NL + cg + NCG * j) * 4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 x = ld4(xr + i * ldx + 4 * k4);
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                acc[i][j] = fmaf(x.x, wv[j].x, acc[i][j]);
+                acc[i][j] = fmaf(x.y, wv[j].y, acc[i][j]);
+                acc[i][j] = fmaf(x.z, wv[j].z, acc[i][j]);
+                acc[i][j] = fmaf(x.w, wv[j].w, acc[i][j]);
+            }
         }
     }
 #pragma unroll
-    for (int m = 0; m < M; ++m) red[ks * KSTRIDE + m * NL + col] = acc[m];
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) red[(i * TN + j) * RSTR + tid] = acc[i][j];
     __syncthreads();
     for (int o = tid; o < M * NL; o += NT) {
+        const int m = o / NL, n = o % NL;
+        const float *p = red + ((m & 3) * TN + n / NCG) * RSTR + (n % NCG) + NCG * (m >> 2);
         float v = 0.f;
-#pragma unroll
-        for (int k = 0; k < KS; ++k) v += red[k * KSTRIDE + o];
-        epi(o / NL, o % NL, v);
+#pragma unroll 8
+        for (int k = 0; k < KS; ++k) v += p[k * NCG * RG];
+        epi(m, n, v);
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// edge attention of head `c` for the M rows of the cluster (layers.py:78-92), online softmax, NWARP / M warps per row
+// edge attention of head `c` for the M rows of the cluster (layers.py:78-92): online softmax, NWARP / M warps per row,
+// chunks of 8 edges, two chunks in flight (the loads of chunk i+1 are issued before chunk i is reduced).
+//   lane l loads float4 #l of every rhat row of the chunk (a 512-byte coalesced row per edge) and, for ONE edge of the
+//   chunk (l >> 2), quarter (l & 3) of the 16-wide K and V head slices, so a chunk costs 40 registers.
 // ---------------------------------------------------------------------------------------------------------------------
+struct AttnPre {               // per warp: its share of the row's edges, source rows of the first 64 of them
+    int e0, eb0, eb1;          // first slot of the row; [eb0, eb1) = this warp's edges (relative to e0)
+    int src0, src1;
+};
 template <int M>
-__device__ __forceinline__ void attn_phase(const SubArgs &A, const RowSpace &rows, int row0, int c, const float *sq,
-                                           const float *sqr, float *sagg, float *sragg, float *ssal, float *smerge) {
+__device__ __forceinline__ AttnPre attn_prefetch(const SubArgs &A, const RowSpace &rows, int row0) {
     constexpr int WPR = NWARP / M;
-    constexpr int CH = 8;                                 // edges in flight per warp
-    static_assert(WPR == 1 || WPR == 2, "1 or 2 warps per row");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m = warp / WPR, part = warp % WPR;
     const int r = row0 + m;
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    int n = 0, e0 = 0;
+    AttnPre p;
+    int n = 0;
+    p.e0 = 0;
     if (A.has_attn && rows.active(r)) {
         n = A.cnt[r];
-        e0 = A.start ? A.start[r] : r * A.stride;
+        p.e0 = A.start ? A.start[r] : r * A.stride;
     }
-    // this warp's contiguous share of the row's edges
-    const int share = WPR == 1 ? n : (((n + WPR - 1) / WPR + 3) & ~3);
-    const int eb0 = part * share, eb1 = min(n, eb0 + share);
+    const int share = WPR == 1 ? n : (((n + WPR - 1) / WPR + 7) & ~7);
+    p.eb0 = min(n, part * share);
+    p.eb1 = min(n, p.eb0 + share);
+    p.src0 = (p.eb0 + lane < p.eb1) ? A.src[p.e0 + p.eb0 + lane] : 0;
+    p.src1 = (p.eb0 + 32 + lane < p.eb1) ? A.src[p.e0 + p.eb0 + 32 + lane] : 0;
+    return p;
+}
+
+struct AttnChunk {
+    float4 rh[8];
+    float4 k, v;
+};
+
+template <int M>
+__device__ __forceinline__ void attn_phase(const SubArgs &A, const AttnPre &P, int c, const float *sq, const float *sqr,
+                                           float *sagg, float *sragg, float *ssal, float *smerge) {
+    constexpr int WPR = NWARP / M;
+    static_assert(WPR == 1 || WPR == 2, "1 or 2 warps per row");
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m = warp / WPR, part = warp % WPR;
+    const int eq = lane >> 2, qd = lane & 3;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 qr4 = ld4(sqr + m * 128 + 4 * lane);
-    const float4 q4 = lane < 4 ? ld4(sq + m * 16 + 4 * lane) : z4;
+    const float4 q4 = ld4(sq + m * 16 + 4 * qd);
     float mx = -INFINITY, den = 0.f;
     float4 ra = z4, av = z4;
-    const float *kvb = A.kv + 16 * c + 4 * (lane & 3);
-    for (int blk = eb0; blk < eb1; blk += 32) {           // source rows of 32 edges with one coalesced load
-        const int my_src = (blk + lane < eb1) ? A.src[e0 + blk + lane] : 0;
-        const int blk_end = min(eb1, blk + 32);
-        for (int eb = blk; eb < blk_end; eb += CH) {
-            float p[CH];
-            float4 rh[CH], v4[CH];
+    const float *kvb = A.kv + 16 * c + 4 * qd;
+    const float *rhb = A.rhat + (size_t)P.e0 * 128 + 4 * lane;
+
+    for (int sb = P.eb0; sb < P.eb1; sb += 64) {          // super-block of 64 edges: source rows held in two registers
+        int src0 = P.src0, src1 = P.src1;
+        if (sb != P.eb0) {
+            src0 = (sb + lane < P.eb1) ? A.src[P.e0 + sb + lane] : 0;
+            src1 = (sb + 32 + lane < P.eb1) ? A.src[P.e0 + sb + 32 + lane] : 0;
+        }
+        const int send = min(P.eb1, sb + 64);
+        const int nch = (send - sb + 7) >> 3;
+        auto load = [&](AttnChunk &ck, int ch) {
+            const int eb = sb + 8 * ch;
 #pragma unroll
-            for (int j = 0; j < CH; ++j) {
-                const int e = eb + j;
-                const int sj = __shfl_sync(0xffffffffu, my_src, (e - blk) & 31);
-                p[j] = 0.f; rh[j] = z4; v4[j] = z4;
-                if (e < blk_end) {
-                    if (A.has_pos) rh[j] = ld4(A.rhat + (size_t)(e0 + e) * 128 + 4 * lane);
-                    if (lane < 4) {
-                        p[j] = dot4(q4, ld4(kvb + (size_t)sj * 256));
-                        v4[j] = ld4(kvb + (size_t)sj * 256 + 128);
-                    }
-                }
+            for (int j = 0; j < 8; ++j)
+                ck.rh[j] = (A.has_pos && eb + j < send) ? ld4(rhb + (size_t)(eb + j) * 128) : z4;
+            const int idx = 8 * ch + eq;
+            const int s0 = __shfl_sync(0xffffffffu, src0, idx & 31), s1 = __shfl_sync(0xffffffffu, src1, idx & 31);
+            const size_t sj = (size_t)(idx < 32 ? s0 : s1);
+            ck.k = z4; ck.v = z4;
+            if (eb + eq < send) {
+                ck.k = __ldcg(reinterpret_cast<const float4 *>(kvb + sj * 256));
+                ck.v = __ldcg(reinterpret_cast<const float4 *>(kvb + sj * 256 + 128));
             }
+        };
+        auto compute = [&](const AttnChunk &ck, int ch) {
+            const int eb = sb + 8 * ch;
+            float pk = dot4(q4, ck.k);
+            pk += __shfl_xor_sync(0xffffffffu, pk, 1);
+            pk += __shfl_xor_sync(0xffffffffu, pk, 2);
+            float p[8];
             float pm = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < CH; ++j) {
-                p[j] = warp_sum(p[j] + dot4(qr4, rh[j])) * 0.25f;      // head_dim ** -0.5
-                if (eb + j >= blk_end) p[j] = -INFINITY;
+            for (int j = 0; j < 8; ++j) {
+                const float pr = warp_sum(dot4(qr4, ck.rh[j]));
+                p[j] = (pr + __shfl_sync(0xffffffffu, pk, 4 * j)) * 0.25f;       // head_dim ** -0.5
+                if (eb + j >= send) p[j] = -INFINITY;
                 pm = fmaxf(pm, p[j]);
             }
             const float mn = fmaxf(mx, pm);                   // finite: edge eb exists
@@ -226,17 +289,33 @@ __device__ __forceinline__ void attn_phase(const SubArgs &A, const RowSpace &row
             den *= sc;
             ra.x *= sc; ra.y *= sc; ra.z *= sc; ra.w *= sc;
             av.x *= sc; av.y *= sc; av.z *= sc; av.w *= sc;
+            float wmine = 0.f;
 #pragma unroll
-            for (int j = 0; j < CH; ++j) {
+            for (int j = 0; j < 8; ++j) {
                 const float w = expf(p[j] - mn);              // 0 for padded edges
                 den += w;
-                ra.x = fmaf(w, rh[j].x, ra.x); ra.y = fmaf(w, rh[j].y, ra.y);
-                ra.z = fmaf(w, rh[j].z, ra.z); ra.w = fmaf(w, rh[j].w, ra.w);
-                av.x = fmaf(w, v4[j].x, av.x); av.y = fmaf(w, v4[j].y, av.y);
-                av.z = fmaf(w, v4[j].z, av.z); av.w = fmaf(w, v4[j].w, av.w);
+                ra.x = fmaf(w, ck.rh[j].x, ra.x); ra.y = fmaf(w, ck.rh[j].y, ra.y);
+                ra.z = fmaf(w, ck.rh[j].z, ra.z); ra.w = fmaf(w, ck.rh[j].w, ra.w);
+                if (j == eq) wmine = w;
             }
+            av.x = fmaf(wmine, ck.v.x, av.x); av.y = fmaf(wmine, ck.v.y, av.y);
+            av.z = fmaf(wmine, ck.v.z, av.z); av.w = fmaf(wmine, ck.v.w, av.w);
             mx = mn;
+        };
+        AttnChunk ca, cb;
+        if (nch > 0) load(ca, 0);
+        for (int ch = 0; ch < nch; ch += 2) {
+            if (ch + 1 < nch) load(cb, ch + 1);
+            compute(ca, ch);
+            if (ch + 2 < nch) load(ca, ch + 2);
+            if (ch + 1 < nch) compute(cb, ch + 1);
         }
+    }
+    // V partial sums live per edge group: fold the 8 groups (lanes with equal l & 3)
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+        av.x += __shfl_xor_sync(0xffffffffu, av.x, o); av.y += __shfl_xor_sync(0xffffffffu, av.y, o);
+        av.z += __shfl_xor_sync(0xffffffffu, av.z, o); av.w += __shfl_xor_sync(0xffffffffu, av.w, o);
     }
     if (WPR == 2) {
         float *mg = smerge + warp * 160;
@@ -253,7 +332,7 @@ __device__ __forceinline__ void attn_phase(const SubArgs &A, const RowSpace &row
             if (mn > -INFINITY) {
                 const float f0 = expf(mx - mn), f1 = expf(mx1 - mn);
                 const float4 ra1 = ld4(og + 32 + 4 * lane);
-                const float4 av1 = lane < 4 ? ld4(og + 4 + 4 * lane) : z4;
+                const float4 av1 = ld4(og + 4 + 4 * qd);
                 den = den * f0 + den1 * f1;
                 ra = make_float4(ra.x * f0 + ra1.x * f1, ra.y * f0 + ra1.y * f1, ra.z * f0 + ra1.z * f1,
                                  ra.w * f0 + ra1.w * f1);
@@ -265,7 +344,7 @@ __device__ __forceinline__ void attn_phase(const SubArgs &A, const RowSpace &row
     if (part == 0) {
         const float inv = 1.0f / (den + 1e-16f);          // torch_geometric.utils.softmax denominator
         if (lane < 4) st4(sagg + m * 16 + 4 * lane, make_float4(av.x * inv, av.y * inv, av.z * inv, av.w * inv));
-        st4(sragg + m * 128 + 4 * lane, make_float4(ra.x * inv, ra.y * inv, ra.z * inv, ra.w * inv));
+        st4(sragg + m * LD1 + 4 * lane, make_float4(ra.x * inv, ra.y * inv, ra.z * inv, ra.w * inv));
         if (lane == 0) ssal[m] = den * inv;
     }
 }
@@ -287,7 +366,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
     if (!any) return;                                              // uniform over the whole cluster
     int ts_n = 0;
     auto stamp = [&]() {
-        if (a.tstamp && blockIdx.x == 0 && tid == 0 && ts_n < 32) a.tstamp[ts_n++] = clock64();
+        if (a.tstamp && blockIdx.x == 0 && tid == 0 && ts_n < 256) a.tstamp[ts_n++] = clock64();
     };
     stamp();
 
@@ -300,12 +379,14 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
     // the sequence of PRE chunks this launch consumes: pre0, sub[0].pre, sub[1].pre (those that exist)
-    const float *pre_seq[3];
-    int n_pre = 0;
-    if (a.pre0.w) pre_seq[n_pre++] = a.pre0.w;
-    for (int i = 0; i < a.n_sub; ++i)
-        if (a.sub[i].pre.w) pre_seq[n_pre++] = a.sub[i].pre.w;
-    int pre_next = 0;                                              // next PRE chunk to request
+    // PRE chunks are consumed in the order pre0, sub[0].pre, sub[1].pre, ... (those that exist); `pre_cursor` is the
+    // position (-1 = pre0, i = sub[i].pre) of the next one to request
+    auto pre_at = [&](int pos) -> const float * { return pos < 0 ? a.pre0.w : a.sub[pos].pre.w; };
+    auto pre_advance = [&](int pos) {
+        while (pos < a.n_sub && pre_at(pos) == nullptr) ++pos;
+        return pos;
+    };
+    int pre_cursor = pre_advance(-1);
 
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
@@ -315,21 +396,35 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
     __syncthreads();
     if (tid == 0) {
         if (a.n_sub > 0) chunk_request(wpost, a.sub[0].w + (size_t)c * cs_post::FLOATS, cs_post::FLOATS, &mbar[0]);
-        if (n_pre > 0) chunk_request(wpre, pre_seq[0] + (size_t)c * cs_pre::FLOATS, cs_pre::FLOATS, &mbar[1]);
+        if (pre_cursor < a.n_sub) chunk_request(wpre, pre_at(pre_cursor) + (size_t)c * cs_pre::FLOATS, cs_pre::FLOATS, &mbar[1]);
     }
-    pre_next = n_pre > 0 ? 1 : 0;
+    if (pre_cursor < a.n_sub) pre_cursor = pre_advance(pre_cursor + 1);
 
     // ---- residual rows; q / s / qr of the first layer when they come from an earlier launch ----------------------
     for (int m = warp; m < M; m += NWARP) {
         const int r = row0 + m;
         const bool act = a.rows.active(r);
-        st4(sx + m * 128 + 4 * lane, act ? ld4(a.x + (size_t)r * 128 + 4 * lane) : z4);
+        st4(sx + m * LD1 + 4 * lane, act ? ld4(a.x + (size_t)r * 128 + 4 * lane) : z4);
         if (!a.pre0.w) {
             st4(sqr + m * 128 + 4 * lane, act ? ld4(a.qr + (size_t)r * 1024 + c * 128 + 4 * lane) : z4);
             if (lane < 4) st4(sq + m * 16 + 4 * lane, act ? ld4(a.q + (size_t)r * 128 + 16 * c + 4 * lane) : z4);
             else if (lane < 8) st4(ss + m * 16 + 4 * (lane - 4), act ? ld4(a.s + (size_t)r * 128 + 16 * c + 4 * (lane - 4)) : z4);
         }
     }
+    // edge lists of every layer of this launch (they do not depend on anything computed here)
+    AttnPre apre0, apre1, apre2;
+    {
+        int f0 = -1, f1 = -1, f2 = -1;
+        for (int i = a.n_sub - 1; i >= 0; --i) {
+            if (a.sub[i].elist == 0) f0 = i;
+            else if (a.sub[i].elist == 1) f1 = i;
+            else f2 = i;
+        }
+        apre0 = attn_prefetch<M>(a.sub[f0 < 0 ? 0 : f0], a.rows, row0);
+        apre1 = attn_prefetch<M>(a.sub[f1 < 0 ? 0 : f1], a.rows, row0);
+        apre2 = attn_prefetch<M>(a.sub[f2 < 0 ? 0 : f2], a.rows, row0);
+    }
+    unsigned bar_target = 0;
     // peers must be resident before anyone writes into their shared memory
     cluster.sync();
     stamp();
@@ -339,10 +434,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
         mbar_wait(&mbar[1], pre_par);
         pre_par ^= 1;
         for (int m = warp; m < M; m += NWARP)
-            st4(su + m * 128 + 4 * lane,
-                ln128s(ld4(sx + m * 128 + 4 * lane), wpre + cs_pre::LN_DST_G, wpre + cs_pre::LN_DST_B, lane));
+            st4(su + m * LD1 + 4 * lane,
+                ln128s(ld4(sx + m * LD1 + 4 * lane), wpre + cs_pre::LN_DST_G, wpre + cs_pre::LN_DST_B, lane));
         __syncthreads();
-        slice_gemm<M, 32, 8>(su, 128, wpre + cs_pre::WQS, 32, sred, [&](int m, int n, float v) {
+        slice_gemm<M, 32, 4>(su, LD1, wpre + cs_pre::WQS, 32, sred, [&](int m, int n, float v) {
             v += wpre[cs_pre::BQS + n];
             const int r = row0 + m;
             const bool st = P.to_global && a.rows.active(r);
@@ -357,7 +452,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
         __syncthreads();
         if (P.pre_kv) {
             const int col = a.col_ptr ? (*a.col_ptr + P.col_add) : 0;
-            slice_gemm<M, 32, 8>(su, 128, wpre + cs_pre::WKV, 32, sred, [&](int m, int n, float v) {
+            slice_gemm<M, 32, 4>(su, LD1, wpre + cs_pre::WKV, 32, sred, [&](int m, int n, float v) {
                 const int r = row0 + m;
                 if (a.rows.active(r)) {
                     const size_t slot = P.kv_ring ? ((size_t)r * a.ring + (col & (a.ring - 1))) : (size_t)r;
@@ -391,9 +486,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
             }
         }
         __syncthreads();
-        if (tid == 0 && pre_next < n_pre)
-            chunk_request(wpre, pre_seq[pre_next] + (size_t)c * cs_pre::FLOATS, cs_pre::FLOATS, &mbar[1]);
-        if (pre_next < n_pre) ++pre_next;
+        if (tid == 0 && pre_cursor < a.n_sub)
+            chunk_request(wpre, pre_at(pre_cursor) + (size_t)c * cs_pre::FLOATS, cs_pre::FLOATS, &mbar[1]);
+        if (pre_cursor < a.n_sub) pre_cursor = pre_advance(pre_cursor + 1);
     };
 
     if (a.pre0.w) do_pre(a.pre0);
@@ -402,7 +497,20 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
     for (int si = 0; si < a.n_sub; ++si) {
         const SubArgs &A = a.sub[si];
         // ---- edge attention of head c ------------------------------------------------------------------------
-        attn_phase<M>(A, a.rows, row0, c, sq, sqr, sagg, sragg, ssal, smerge);
+        if (A.grid_sync) {                                         // K/V rows of other clusters must have landed
+            bar_target += gridDim.x;
+            __syncthreads();
+            if (tid == 0) {
+                __threadfence();
+                atomicAdd(a.grid_bar, 1u);
+                unsigned seen;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.grid_bar) : "memory");
+                } while (seen < bar_target);
+            }
+            __syncthreads();
+        }
+        attn_phase<M>(A, A.elist == 0 ? apre0 : (A.elist == 1 ? apre1 : apre2), c, sq, sqr, sagg, sragg, ssal, smerge);
         stamp();
         mbar_wait(&mbar[0], post_par);
         post_par ^= 1;
@@ -410,72 +518,72 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
         stamp();
         // xd = LN_dst(x) (every CTA, full rows);  ragg' = g_r * ragg + b_r * sal (own head)
         for (int m = warp; m < M; m += NWARP) {
-            st4(scat + m * 256 + 128 + 4 * lane,
-                ln128s(ld4(sx + m * 128 + 4 * lane), wpost + cs_post::LN_DST_G, wpost + cs_post::LN_DST_B, lane));
+            st4(scat + m * LD2 + 128 + 4 * lane,
+                ln128s(ld4(sx + m * LD1 + 4 * lane), wpost + cs_post::LN_DST_G, wpost + cs_post::LN_DST_B, lane));
             if (A.has_pos) {
-                const float4 v = ld4(sragg + m * 128 + 4 * lane);
+                const float4 v = ld4(sragg + m * LD1 + 4 * lane);
                 const float4 g = ld4(wpost + cs_post::LN_R_G + 4 * lane), b = ld4(wpost + cs_post::LN_R_B + 4 * lane);
                 const float sa = ssal[m];
-                st4(sragg + m * 128 + 4 * lane, make_float4(fmaf(g.x, v.x, b.x * sa), fmaf(g.y, v.y, b.y * sa),
+                st4(sragg + m * LD1 + 4 * lane, make_float4(fmaf(g.x, v.x, b.x * sa), fmaf(g.y, v.y, b.y * sa),
                                                             fmaf(g.z, v.z, b.z * sa), fmaf(g.w, v.w, b.w * sa)));
             }
         }
         __syncthreads();
         // ---- agg2 = agg + Wvr ragg' + bvr * sal  -> all CTAs ---------------------------------------------------
         if (A.has_pos) {
-            slice_gemm<M, 16, 16>(sragg, 128, wpost + cs_post::WVR, 32, sred, [&](int m, int n, float v) {
+            slice_gemm<M, 16, (M == 4 ? 2 : 4)>(sragg, LD1, wpost + cs_post::WVR, 32, sred, [&](int m, int n, float v) {
                 v += sagg[m * 16 + n] + wpost[cs_post::BVR + n] * ssal[m];
 #pragma unroll
-                for (int p = 0; p < CL; ++p) cluster.map_shared_rank(scat, p)[m * 256 + 16 * c + n] = v;
+                for (int p = 0; p < CL; ++p) cluster.map_shared_rank(scat, p)[m * LD2 + 16 * c + n] = v;
             });
         } else {
             for (int o = tid; o < M * 16; o += NT) {
                 const float v = sagg[o];
 #pragma unroll
-                for (int p = 0; p < CL; ++p) cluster.map_shared_rank(scat, p)[(o >> 4) * 256 + 16 * c + (o & 15)] = v;
+                for (int p = 0; p < CL; ++p) cluster.map_shared_rank(scat, p)[(o >> 4) * LD2 + 16 * c + (o & 15)] = v;
             }
         }
         cluster.sync();
         stamp();
         // ---- gate: g = sigmoid(Wg [agg | xd] + bg);  u = agg + g * (s - agg) ----------------------------------
-        slice_gemm<M, 16, 16>(scat, 256, wpost + cs_post::WG, 64, sred, [&](int m, int n, float v) {
+        slice_gemm<M, 16, (M == 4 ? 2 : 4)>(scat, LD2, wpost + cs_post::WG, 64, sred, [&](int m, int n, float v) {
             const float g = sigmoidf(v + wpost[cs_post::BG + n]);
-            const float ag = scat[m * 256 + 16 * c + n];
+            const float ag = scat[m * LD2 + 16 * c + n];
             const float u = ag + g * (ss[m * 16 + n] - ag);
 #pragma unroll
-            for (int p = 0; p < CL; ++p) cluster.map_shared_rank(su, p)[m * 128 + 16 * c + n] = u;
+            for (int p = 0; p < CL; ++p) cluster.map_shared_rank(su, p)[m * LD1 + 16 * c + n] = u;
         });
         cluster.sync();
         stamp();
         // ---- to_out ------------------------------------------------------------------------------------------
-        slice_gemm<M, 16, 16>(su, 128, wpost + cs_post::WO, 32, sred, [&](int m, int n, float v) {
+        slice_gemm<M, 16, (M == 4 ? 2 : 4)>(su, LD1, wpost + cs_post::WO, 32, sred, [&](int m, int n, float v) {
             v += wpost[cs_post::BO + n];
 #pragma unroll
-            for (int p = 0; p < CL; ++p) cluster.map_shared_rank(so, p)[m * 128 + 16 * c + n] = v;
+            for (int p = 0; p < CL; ++p) cluster.map_shared_rank(so, p)[m * LD1 + 16 * c + n] = v;
         });
         cluster.sync();
         stamp();
         // x1 = x + LN_post(o);  so = LN_ffpre(x1)
         for (int m = warp; m < M; m += NWARP) {
-            float4 o = ld4(so + m * 128 + 4 * lane);
+            float4 o = ld4(so + m * LD1 + 4 * lane);
             o = ln128s(o, wpost + cs_post::LN_POST_G, wpost + cs_post::LN_POST_B, lane);
-            const float4 x1 = add4(ld4(sx + m * 128 + 4 * lane), o);
-            st4(sx + m * 128 + 4 * lane, x1);
-            st4(so + m * 128 + 4 * lane, ln128s(x1, wpost + cs_post::LN_FFPRE_G, wpost + cs_post::LN_FFPRE_B, lane));
+            const float4 x1 = add4(ld4(sx + m * LD1 + 4 * lane), o);
+            st4(sx + m * LD1 + 4 * lane, x1);
+            st4(so + m * LD1 + 4 * lane, ln128s(x1, wpost + cs_post::LN_FFPRE_G, wpost + cs_post::LN_FFPRE_B, lane));
         }
         __syncthreads();
         // ---- FFN ---------------------------------------------------------------------------------------------
-        slice_gemm<M, 64, 4>(so, 128, wpost + cs_post::W1, 32, sred, [&](int m, int n, float v) {
+        slice_gemm<M, 64, 4>(so, LD1, wpost + cs_post::W1, 32, sred, [&](int m, int n, float v) {
             v = fmaxf(v + wpost[cs_post::B1 + n], 0.f);
 #pragma unroll
-            for (int p = 0; p < CL; ++p) cluster.map_shared_rank(sh, p)[m * 512 + 64 * c + n] = v;
+            for (int p = 0; p < CL; ++p) cluster.map_shared_rank(sh, p)[m * LD5 + 64 * c + n] = v;
         });
         cluster.sync();
         stamp();
-        slice_gemm<M, 16, 16>(sh, 512, wpost + cs_post::W2, 128, sred, [&](int m, int n, float v) {
+        slice_gemm<M, 16, (M == 4 ? 2 : 4)>(sh, LD5, wpost + cs_post::W2, 128, sred, [&](int m, int n, float v) {
             v += wpost[cs_post::B2 + n];
 #pragma unroll
-            for (int p = 0; p < CL; ++p) cluster.map_shared_rank(sy, p)[m * 128 + 16 * c + n] = v;
+            for (int p = 0; p < CL; ++p) cluster.map_shared_rank(sy, p)[m * LD1 + 16 * c + n] = v;
         });
         cluster.sync();
         stamp();
@@ -483,10 +591,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
         const bool last = si + 1 == a.n_sub;
         for (int m = warp; m < M; m += NWARP) {
             const int r = row0 + m;
-            float4 f = ld4(sy + m * 128 + 4 * lane);
+            float4 f = ld4(sy + m * LD1 + 4 * lane);
             f = ln128s(f, wpost + cs_post::LN_FFPOST_G, wpost + cs_post::LN_FFPOST_B, lane);
-            const float4 x2 = add4(ld4(sx + m * 128 + 4 * lane), f);
-            st4(sx + m * 128 + 4 * lane, x2);
+            const float4 x2 = add4(ld4(sx + m * LD1 + 4 * lane), f);
+            st4(sx + m * LD1 + 4 * lane, x2);
             if ((m & (CL - 1)) == c && a.rows.active(r)) {         // row m is stored by CTA m % 8
                 if (last) st4(a.x + (size_t)r * 128 + 4 * lane, x2);
                 if (A.trace_out) st4(A.trace_out + (size_t)r * 128 + 4 * lane, x2);

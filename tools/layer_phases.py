@@ -17,10 +17,12 @@ scenes = [make_scene(13 + i, num_agents=64, num_map_tokens=2048, num_steps=91, r
           for i in range(n_scenes)]
 for rep in range(2):
     dec.inference_batch(scenes, [s['map_enc'] for s in scenes])
-ts = dec.debug_read('tstamp', (64,), np.int64)
-for name, off in (('temporal+map', 0), ('agent', 32)):
-    t = ts[off:off + 32]
+ts = dec.debug_read('tstamp', (512,), np.int64)
+for name, off in (('stack / temporal+map', 0), ('agent', 256)):
+    t = ts[off:off + 256]
     t = t[t > 0]
+    if len(t) < 2:
+        continue
     d = np.diff(t)
     print(name, 'total cycles', int(t[-1] - t[0]), 'phases', d.tolist())
 dec.close()
