@@ -286,23 +286,29 @@ def run_ours(args, rank, world, local_rank):
         rows = sum(h.n_rows for h in hosts)
         iters = S
         # algorithmic work per launch, averaged over the iterations of a rollout (fp32; DESIGN.md "roofline accounting")
-        # k_layer (layer.cuh): one launch = whole AttentionLayers for every row.  Algorithmic bytes: per edge K row + V row +
-        # rhat row + source index; per row the residual in/out and the q/s/qr/kv hand-over; the layer weights once per
-        # launch.  Algorithmic flops: folded formulation, 2*MAC.
+        # k_layer (layer.cuh): whole AttentionLayers per launch (all 18 of an iteration when the grid is co-resident).
+        # Algorithmic bytes: per edge K row + V row + rhat row + source index (1,540 B); per row and layer the
+        # residual in/out and the q/s/qr/kv hand-over; the layer weights once per launch.  Algorithmic flops: folded
+        # formulation, 2*MAC.
         per_edge = 512 + 512 + 512 + 4
         post_mac, pre_mac, pre_kv_mac = 196608, 49152, 32768     # Wvr+gate+out+ffn | q,s,Wkr fold | k,v
         w_layer = 1.125e6 + 0.17e6                                # post + pre chunks of one layer (fp32 bytes)
         edge_flops = 2.0 * 2 * (128 + 16) * 8                     # score + weighted sum, 8 heads
-        tm_bytes = rows * (1024 + 5120 + 1024 + 1024) + (e_t + e_m) / iters * per_edge + 2 * w_layer
-        a_bytes = rows * (1024 + 5120 + 5120 + 1024) + e_a / iters * per_edge + w_layer
-        tm_flops = rows * 2.0 * (2 * post_mac + 2 * pre_mac + pre_kv_mac) + (e_t + e_m) / iters * edge_flops
-        a_flops = rows * 2.0 * (post_mac + pre_mac + pre_kv_mac) + e_a / iters * edge_flops
+        et, em, ea = e_t / iters, e_m / iters, e_a / iters
+        tm_bytes = rows * (1024 + 5120 + 1024 + 1024) + (et + em) * per_edge + 2 * w_layer
+        a_bytes = rows * (1024 + 5120 + 5120 + 1024) + ea * per_edge + w_layer
+        tm_flops = rows * 2.0 * (2 * post_mac + 2 * pre_mac + pre_kv_mac) + (et + em) * edge_flops
+        a_flops = rows * 2.0 * (post_mac + pre_mac + pre_kv_mac) + ea * edge_flops
+        # the fused stack keeps x/q/s/qr on chip: per row only x in/out, 6 temporal ring rows and 6 agent K|V rows leave
+        st_bytes = rows * (1024 + 12 * 1024) + 6 * (et + em + ea) * per_edge + 18 * w_layer
+        st_flops = 6 * (tm_flops + a_flops)
         model = {
+            'k_layer:stack18': ('hbm', st_bytes, st_flops),
             'k_layer:temporal+map': ('hbm', tm_bytes, tm_flops),
             'k_layer:agent': ('hbm', a_bytes, a_flops),
-            'k_fourier<4>:temporal': ('tensor', e_t / iters * 2.0 * (4 * (132 * 128 + 128 * 128) + 128 * 128)),
-            'k_fourier<3>:map': ('tensor', e_m / iters * 2.0 * (3 * (132 * 128 + 128 * 128) + 128 * 128)),
-            'k_fourier<3>:agent': ('tensor', e_a / iters * 2.0 * (3 * (132 * 128 + 128 * 128) + 128 * 128)),
+            'k_fourier:edges': ('tensor', (et * (4 * (132 * 128 + 128 * 128) + 128 * 128) +
+                                           (em + ea) * (3 * (132 * 128 + 128 * 128) + 128 * 128)) * 2.0),
+            'k_embed_column': ('tensor', rows * 2.0 * (2 * (132 * 128 + 128 * 128) + 128 * 128 + 512 * 128 + 2 * 128 * 128)),
             'k_heads': ('tensor', rows * 2.0 * (2 * 128 * 128 + 128 * 2048 + 128 * 128)),
         }
         tot = sum(v['ms'] for v in prof.values())

@@ -331,9 +331,12 @@ __global__ void __launch_bounds__(NT) k_advance(const DecState s) {
     if (i >= s.n_rows[b]) return;
     const int col = *s.col, t = *s.iter, T = s.T, nxt = col + 1;
     const int ego = s.ego_row[b];
-    const AdvOut eo = advance_row(s, b, ego, col, t, false);
-    const AdvOut me = (i == ego) ? eo : advance_row(s, b, i, col, t, true);
-    if (i == ego) advance_row(s, b, i, col, t, true);
+    AdvOut eo, me;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {                 // pass 0: the ego row (no stores), pass 1: this row
+        const AdvOut o = advance_row(s, b, pass == 0 ? ego : i, col, t, pass == 1);
+        if (pass == 0) eo = o; else me = o;
+    }
     if (me.st == ST_INVALID) return;
     // ---- ego-centric grid token of the new position (attr_tokenizer.py:77-89, agent_decoder.py:2214) ------------
     const float eth = -__fsub_rn(eo.lh, 1.5707963267948966f);

@@ -360,10 +360,12 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
     const int c = (int)cluster.block_rank();                       // head / column slice of this CTA
     const int row0 = (int)(blockIdx.x / CL) * M;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    bool any = false;
+    unsigned act_mask = 0;                                         // bit m: row row0 + m is active
 #pragma unroll
-    for (int m = 0; m < M; ++m) any |= a.rows.active(row0 + m);
-    if (!any) return;                                              // uniform over the whole cluster
+    for (int m = 0; m < M; ++m) act_mask |= a.rows.active(row0 + m) ? (1u << m) : 0u;
+    if (!act_mask) return;                                         // uniform over the whole cluster
+    auto active = [&](int m) { return (act_mask >> m) & 1u; };
+    const int col_now = a.col_ptr ? *a.col_ptr : 0;
     int ts_n = 0;
     auto stamp = [&]() {
         if (a.tstamp && blockIdx.x == 0 && tid == 0 && ts_n < 256) a.tstamp[ts_n++] = clock64();
@@ -403,7 +405,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
     // ---- residual rows; q / s / qr of the first layer when they come from an earlier launch ----------------------
     for (int m = warp; m < M; m += NWARP) {
         const int r = row0 + m;
-        const bool act = a.rows.active(r);
+        const bool act = active(m);
         st4(sx + m * LD1 + 4 * lane, act ? ld4(a.x + (size_t)r * 128 + 4 * lane) : z4);
         if (!a.pre0.w) {
             st4(sqr + m * 128 + 4 * lane, act ? ld4(a.qr + (size_t)r * 1024 + c * 128 + 4 * lane) : z4);
@@ -440,7 +442,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
         slice_gemm<M, 32, 4>(su, LD1, wpre + cs_pre::WQS, 32, sred, [&](int m, int n, float v) {
             v += wpre[cs_pre::BQS + n];
             const int r = row0 + m;
-            const bool st = P.to_global && a.rows.active(r);
+            const bool st = P.to_global && active(m);
             if (n < 16) {
                 sq[m * 16 + n] = v;
                 if (st) a.q[(size_t)r * 128 + 16 * c + n] = v;
@@ -451,10 +453,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
         });
         __syncthreads();
         if (P.pre_kv) {
-            const int col = a.col_ptr ? (*a.col_ptr + P.col_add) : 0;
+            const int col = col_now + P.col_add;
             slice_gemm<M, 32, 4>(su, LD1, wpre + cs_pre::WKV, 32, sred, [&](int m, int n, float v) {
                 const int r = row0 + m;
-                if (a.rows.active(r)) {
+                if (active(m)) {
                     const size_t slot = P.kv_ring ? ((size_t)r * a.ring + (col & (a.ring - 1))) : (size_t)r;
                     const int o = n < 16 ? 16 * c + n : 128 + 16 * c + (n - 16);
                     P.kv_out[slot * 256 + o] = v + wpre[cs_pre::BKV + n];
@@ -482,7 +484,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
                 acc *= g;
                 sqr[m * 128 + ch] = acc;
                 const int r = row0 + m;
-                if (P.to_global && a.rows.active(r)) a.qr[(size_t)r * 1024 + c * 128 + ch] = acc;
+                if (P.to_global && active(m)) a.qr[(size_t)r * 1024 + c * 128 + ch] = acc;
             }
         }
         __syncthreads();
@@ -595,7 +597,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
             f = ln128s(f, wpost + cs_post::LN_FFPOST_G, wpost + cs_post::LN_FFPOST_B, lane);
             const float4 x2 = add4(ld4(sx + m * LD1 + 4 * lane), f);
             st4(sx + m * LD1 + 4 * lane, x2);
-            if ((m & (CL - 1)) == c && a.rows.active(r)) {         // row m is stored by CTA m % 8
+            if ((m & (CL - 1)) == c && active(m)) {                // row m is stored by CTA m % 8
                 if (last) st4(a.x + (size_t)r * 128 + 4 * lane, x2);
                 if (A.trace_out) st4(A.trace_out + (size_t)r * 128 + 4 * lane, x2);
             }
