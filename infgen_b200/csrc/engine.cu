@@ -970,6 +970,14 @@ int64_t infgen_debug_read(infgen_engine *e, const char *name, void *dst, int64_t
     return n;
 }
 
+#ifdef INFGEN_WS_TRACE
+int32_t infgen_debug_ws_trace(long long *dst /* [2][256] */, int32_t *n /* [2] */) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(dst, g_ws_trace, sizeof(long long) * 512);
+    cudaMemcpyFromSymbol(n, g_ws_trace_n, sizeof(int) * 2);
+    return 0;
+}
+#endif
 // ---------------------------------------------------------------------------------------------------------------
 // operator level
 // ---------------------------------------------------------------------------------------------------------------

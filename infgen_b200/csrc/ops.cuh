@@ -155,16 +155,16 @@ __device__ __forceinline__ void fourier_body(WsCons &ws, const FourierW &w, int 
             sF[tid * FLD + 129] = 0.f; sF[tid * FLD + 130] = 0.f; sF[tid * FLD + 131] = 0.f;
         }
         csync();
-        stream_gemm<M>(ws, sF, FLD, 33, [&](int m, int n, float v) { sH[m * HLD + n] = v + __ldg(w.b0[d] + n); });
+        tile_gemm<M>(ws, sF, FLD, 33, [&](int m, int n, float v) { sH[m * HLD + n] = v + __ldg(w.b0[d] + n); });
         csync();
         rows_layernorm_c<M, true>(sH, HLD, w.ln_g[d], w.ln_b[d]);
         csync();
-        stream_gemm<M>(ws, sH, HLD, 32, [&](int m, int n, float v) { sA[m * HLD + n] += v + __ldg(w.b3[d] + n); });
+        tile_gemm<M>(ws, sH, HLD, 32, [&](int m, int n, float v) { sA[m * HLD + n] += v + __ldg(w.b3[d] + n); });
     }
     csync();
     rows_layernorm_c<M, true>(sA, HLD, w.out_ln_g, w.out_ln_b);
     csync();
-    stream_gemm<M>(ws, sA, HLD, 32, [&](int m, int n, float v) { sH[m * HLD + n] = v + __ldg(w.b_out + n); });
+    tile_gemm<M>(ws, sA, HLD, 32, [&](int m, int n, float v) { sH[m * HLD + n] = v + __ldg(w.b_out + n); });
     csync();
 }
 
@@ -239,15 +239,15 @@ __device__ __forceinline__ int mlp3_segs(const MlpEmbW &w, int k4, WSeg *segs) {
 template <int M, typename Epi>
 __device__ __forceinline__ void mlp3_body(WsCons &ws, const MlpEmbW &w, const float *sX, int ldx, int k4, float *sH,
                                           float *sG, Epi epi) {
-    stream_gemm<M>(ws, sX, ldx, k4, [&](int m, int n, float v) { sH[m * HLD + n] = v + __ldg(w.b0 + n); });
+    tile_gemm<M>(ws, sX, ldx, k4, [&](int m, int n, float v) { sH[m * HLD + n] = v + __ldg(w.b0 + n); });
     csync();
     rows_layernorm_c<M, true>(sH, HLD, w.ln1_g, w.ln1_b);
     csync();
-    stream_gemm<M>(ws, sH, HLD, 32, [&](int m, int n, float v) { sG[m * HLD + n] = v + __ldg(w.b3 + n); });
+    tile_gemm<M>(ws, sH, HLD, 32, [&](int m, int n, float v) { sG[m * HLD + n] = v + __ldg(w.b3 + n); });
     csync();
     rows_layernorm_c<M, true>(sG, HLD, w.ln4_g, w.ln4_b);
     csync();
-    stream_gemm<M>(ws, sG, HLD, 32, [&](int m, int n, float v) { epi(m, n, v + __ldg(w.b6 + n)); });
+    tile_gemm<M>(ws, sG, HLD, 32, [&](int m, int n, float v) { epi(m, n, v + __ldg(w.b6 + n)); });
 }
 // leading dimension of a [rows][4*k4] input tile: padded so that it is 4 (mod 32) floats when wide
 __host__ __device__ __forceinline__ int mlp_ldx(int k4) { return k4 * 4 + ((k4 * 4) % 32 == 0 ? 4 : 0); }
@@ -359,12 +359,12 @@ __global__ void __launch_bounds__(NT_S) k_heads(const HeadArgs a) {
         st4(sx + m * HLD + 4 * lane, x);
     }
     csync();
-    stream_gemm<HM>(ws, sx, HLD, 32, [&](int m, int n, float v) { sh[m * HLD + n] = v + __ldg(hw.b0 + n); });
+    tile_gemm<HM>(ws, sx, HLD, 32, [&](int m, int n, float v) { sh[m * HLD + n] = v + __ldg(hw.b0 + n); });
     csync();
     rows_layernorm_c<HM, true>(sh, HLD, hw.ln_g, hw.ln_b);
     csync();
     if (is_state) {                          // agent_decoder.py:2166
-        stream_gemm<HM>(ws, sh, HLD, 32, [&](int m, int n, float v) {
+        tile_gemm<HM>(ws, sh, HLD, 32, [&](int m, int n, float v) {
             const int r = row0 + m;
             if (n < hw.n_out && a.rows.active(r)) {
                 v += __ldg(hw.b3 + n);
@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(NT_S) k_heads(const HeadArgs a) {
         return;
     }
     for (int half = 0; half < 2; ++half) {
-        stream_gemm<HM>(ws, sh, HLD, 32, [&](int m, int n, float v) {
+        tile_gemm<HM>(ws, sh, HLD, 32, [&](int m, int n, float v) {
             const int col = half * 128 + n;
             v += __ldg(hw.b3 + slice * 256 + col);
             slog[m * 256 + col] = v;
@@ -470,11 +470,11 @@ __global__ void __launch_bounds__(NT_S) k_mlp_layer(const MlpLayerArgs a) {
         st4(sx + m * HLD + 4 * lane, r < a.n ? ld4(a.x + (size_t)r * 128 + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f));
     }
     csync();
-    stream_gemm<HM>(ws, sx, HLD, a.w.k4_in, [&](int m, int n, float v) { sh[m * HLD + n] = v + __ldg(a.w.b0 + n); });
+    tile_gemm<HM>(ws, sx, HLD, a.w.k4_in, [&](int m, int n, float v) { sh[m * HLD + n] = v + __ldg(a.w.b0 + n); });
     csync();
     rows_layernorm_c<HM, true>(sh, HLD, a.w.ln_g, a.w.ln_b);
     csync();
-    stream_gemm<HM>(ws, sh, HLD, 32, [&](int m, int n, float v) {
+    tile_gemm<HM>(ws, sh, HLD, 32, [&](int m, int n, float v) {
         const int r = row0 + m;
         if (r < a.n && n0 + n < a.w.n_out) a.out[(size_t)r * a.w.n_out + n0 + n] = v + __ldg(a.w.b3 + n0 + n);
     });

@@ -21,6 +21,21 @@ constexpr int WS_SMEM_FLOATS = WS_RING_FLOATS + 4 * WS_STAGES;   // + full/empty
 constexpr int NT_S = NT + 32;
 constexpr int WS_MAX_SEGS = 12;
 
+#ifdef INFGEN_WS_TRACE
+// debug: clock64 of every chunk issue (producer) / acquire completion (consumer warp 0) of CTA 0 of the last kernel
+__device__ long long g_ws_trace[2][256];
+__device__ int g_ws_trace_n[2];
+#define WS_TRACE(which)                                                                                       \
+    do {                                                                                                      \
+        if (blockIdx.x == 0 && blockIdx.y == 0) {                                                             \
+            const int _i = g_ws_trace_n[which]++;                                                             \
+            if (_i < 256) g_ws_trace[which][_i] = clock64();                                                  \
+        }                                                                                                     \
+    } while (0)
+#else
+#define WS_TRACE(which) do {} while (0)
+#endif
+
 // one Linear (or a 128-column slice of one): `k4` packed rows, `ld` floats between consecutive k4 rows (512 when the
 // matrix is exactly 128 columns wide, i.e. contiguous)
 struct WSeg {
@@ -40,6 +55,9 @@ struct WsSmem {
 
 // all threads, before the roles split (contains __syncthreads)
 __device__ __forceinline__ void ws_init(const WsSmem &ws) {
+#ifdef INFGEN_WS_TRACE
+    if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) { g_ws_trace_n[0] = 0; g_ws_trace_n[1] = 0; }
+#endif
     if (threadIdx.x == 0) {
         for (int i = 0; i < WS_STAGES; ++i) {
             mbar_init(&ws.full[i], 1);
@@ -64,6 +82,7 @@ __device__ __forceinline__ void ws_produce(const WsSmem &ws, const WSeg *segs, i
                 mbar_wait(&ws.empty[stage], phase ^ 1u);
                 float *dst = ws.ring + stage * WS_STAGE_FLOATS;
                 mbar_expect_tx(&ws.full[stage], (uint32_t)rows * 2048u);
+                WS_TRACE(0);
                 if (sg.ld == 512) {
                     bulk_g2s(dst, sg.p + (size_t)r0 * 512, (uint32_t)rows * 2048u, &ws.full[stage]);
                 } else {
@@ -85,6 +104,7 @@ struct WsCons {
     __device__ __forceinline__ explicit WsCons(const WsSmem &ws) : ring(ws.ring), full(ws.full), empty(ws.empty), stage(0), phase(0) {}
     __device__ __forceinline__ const float *acquire() {
         mbar_wait(&full[stage], phase);
+        if (threadIdx.x == 0) WS_TRACE(1);
         return ring + stage * WS_STAGE_FLOATS;
     }
     __device__ __forceinline__ void release() {
@@ -145,6 +165,109 @@ __device__ __forceinline__ void stream_gemm(WsCons &ws, const float *xs, int ldx
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < NTT; ++j) epi(rl + RLN * i, c0 + CLN * j, acc[i][j]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Tensor-core variant of stream_gemm for M = 16 / 32 row tiles: mma.sync m16n8k8 TF32 with the 3xTF32 error-compensated
+// split (x = hi + lo, both TF32; D += A_lo B_hi + A_hi B_lo + A_hi B_hi, fp32 accumulate), which keeps fp32-level
+// accuracy (the dropped lo*lo term is 2^-22 relative) - the decode loop is closed: a plain TF32 product would flip
+// near-tie token arg-maxes.  Operand fragments come straight from the activation tile and the weight ring with
+// conflict-free 32-bit loads (12 per k-step of 8 for M = 32, against 8 x 128-bit per 4 k in the FFMA tile), which is
+// what bounds these GEMMs.  Same contract as stream_gemm; warp w owns columns [16w, 16w+16).
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t f2tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) {
+    hi = f2tf32(x);
+    lo = f2tf32(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <int M, typename Epi>
+__device__ __forceinline__ void stream_gemm_mma(WsCons &ws, const float *xs, int ldx, int K4, Epi epi) {
+    static_assert(M == 16 || M == 32, "tile rows");
+    constexpr int MT = M / 16;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    float acc[MT][2][4];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+    const float *xa = xs + (size_t)g * ldx + t;
+    const int nb = (16 * warp + g) * 4 + t;                // float offset of (n = 16w + g, element t) inside a k4 row
+    auto kstep = [&](const float *w, int kk, int k4, bool full) {
+        // B fragments: b0 = W[4*k4 + t][n], b1 = W[4*(k4+1) + t][n]
+        uint32_t bh[2][2], bl[2][2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float b0 = w[kk * 512 + nb + 32 * j];
+            const float b1 = full ? w[(kk + 1) * 512 + nb + 32 * j] : 0.f;
+            split_tf32(b0, bh[j][0], bl[j][0]);
+            split_tf32(b1, bh[j][1], bl[j][1]);
+        }
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+            const float *xr = xa + (size_t)(16 * i) * ldx + 4 * k4;
+            const float a0 = xr[0], a1 = xr[8 * ldx];
+            const float a2 = full ? xr[4] : 0.f, a3 = full ? xr[8 * ldx + 4] : 0.f;
+            uint32_t ah[4], al[4];
+            split_tf32(a0, ah[0], al[0]); split_tf32(a1, ah[1], al[1]);
+            split_tf32(a2, ah[2], al[2]); split_tf32(a3, ah[3], al[3]);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                mma_tf32(acc[i][j], al, bh[j]);
+                mma_tf32(acc[i][j], ah, bl[j]);
+                mma_tf32(acc[i][j], ah, bh[j]);
+            }
+        }
+    };
+    for (int kb = 0; kb < K4; kb += WS_ROWS) {
+        const int rows = min(WS_ROWS, K4 - kb);
+        const float *w = ws.acquire();
+        if (rows == WS_ROWS) {
+#pragma unroll
+            for (int kk = 0; kk < WS_ROWS; kk += 2) kstep(w, kk, kb + kk, true);
+        } else {
+            for (int kk = 0; kk < rows; kk += 2) kstep(w, kk, kb + kk, kk + 1 < rows);
+        }
+        ws.release();
+    }
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int m = 16 * i + g, n = 16 * warp + 8 * j + 2 * t;
+            epi(m, n, acc[i][j][0]);
+            epi(m, n + 1, acc[i][j][1]);
+            epi(m + 8, n, acc[i][j][2]);
+            epi(m + 8, n + 1, acc[i][j][3]);
+        }
+}
+
+// dispatcher.  The FFMA tile is the default: on B200 the legacy mma.sync TF32 path measured ~170 MAC/clk/SM (k_embed_column,
+// 1150 cycles per 16 KB weight stage at M = 16, tools/probe/ws_trace.py), i.e. after the 3x split it is no faster than
+// FFMA (128 MAC/clk/SM) - only tcgen05 would be, and that needs 64/128-row tiles a single scene does not have.
+// Build with -DINFGEN_MMA to use the tensor-core variant for the 16/32-row tiles (parity-tested, same tolerances).
+template <int M, typename Epi>
+__device__ __forceinline__ void tile_gemm(WsCons &ws, const float *xs, int ldx, int K4, Epi epi) {
+#ifdef INFGEN_MMA
+    if constexpr (M == 16 || M == 32) {
+        stream_gemm_mma<M>(ws, xs, ldx, K4, epi);
+        return;
+    }
+#endif
+    stream_gemm<M>(ws, xs, ldx, K4, epi);
 }
 
 // In-place LayerNorm (+ optional ReLU) of M rows, one warp per row; callers csync() before and after
