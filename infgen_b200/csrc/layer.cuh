@@ -275,31 +275,48 @@ __device__ __forceinline__ void attn_phase(const SubArgs &A, const AttnPre &P, i
             float pk = dot4(q4, ck.k);
             pk += __shfl_xor_sync(0xffffffffu, pk, 1);
             pk += __shfl_xor_sync(0xffffffffu, pk, 2);
-            float p[8];
-            float pm = -INFINITY;
+            // 8 rhat dot products, 32 partial sums each: butterfly reduce-scatter (9 shuffles) that leaves the score of
+            // edge l >> 2 in lane l - the lane group that also holds that edge's K/V quarter
+            float v[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float pr = warp_sum(dot4(qr4, ck.rh[j]));
-                p[j] = (pr + __shfl_sync(0xffffffffu, pk, 4 * j)) * 0.25f;       // head_dim ** -0.5
-                if (eb + j >= send) p[j] = -INFINITY;
-                pm = fmaxf(pm, p[j]);
+            for (int j = 0; j < 8; ++j) v[j] = dot4(qr4, ck.rh[j]);
+            const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float recv = __shfl_xor_sync(0xffffffffu, b4 ? v[i] : v[i + 4], 16);
+                v[i] = (b4 ? v[i + 4] : v[i]) + recv;
             }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const float recv = __shfl_xor_sync(0xffffffffu, b3 ? v[i] : v[i + 2], 8);
+                v[i] = (b3 ? v[i + 2] : v[i]) + recv;
+            }
+            {
+                const float recv = __shfl_xor_sync(0xffffffffu, b2 ? v[0] : v[1], 4);
+                v[0] = (b2 ? v[1] : v[0]) + recv;
+            }
+            float pr = v[0];
+            pr += __shfl_xor_sync(0xffffffffu, pr, 1);
+            pr += __shfl_xor_sync(0xffffffffu, pr, 2);
+            float p = (pr + pk) * 0.25f;                      // head_dim ** -0.5
+            if (eb + eq >= send) p = -INFINITY;
+            float pm = p;
+            pm = fmaxf(pm, __shfl_xor_sync(0xffffffffu, pm, 4));
+            pm = fmaxf(pm, __shfl_xor_sync(0xffffffffu, pm, 8));
+            pm = fmaxf(pm, __shfl_xor_sync(0xffffffffu, pm, 16));
             const float mn = fmaxf(mx, pm);                   // finite: edge eb exists
             const float sc = expf(mx - mn);                   // 0 on the first chunk
-            den *= sc;
+            const float wmine = expf(p - mn);                 // 0 for padded edges
+            den = fmaf(den, sc, wmine);                       // per lane group; folded over the groups after the loop
             ra.x *= sc; ra.y *= sc; ra.z *= sc; ra.w *= sc;
-            av.x *= sc; av.y *= sc; av.z *= sc; av.w *= sc;
-            float wmine = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float w = expf(p[j] - mn);              // 0 for padded edges
-                den += w;
+                const float w = __shfl_sync(0xffffffffu, wmine, 4 * j);
                 ra.x = fmaf(w, ck.rh[j].x, ra.x); ra.y = fmaf(w, ck.rh[j].y, ra.y);
                 ra.z = fmaf(w, ck.rh[j].z, ra.z); ra.w = fmaf(w, ck.rh[j].w, ra.w);
-                if (j == eq) wmine = w;
             }
-            av.x = fmaf(wmine, ck.v.x, av.x); av.y = fmaf(wmine, ck.v.y, av.y);
-            av.z = fmaf(wmine, ck.v.z, av.z); av.w = fmaf(wmine, ck.v.w, av.w);
+            av.x = fmaf(av.x, sc, wmine * ck.v.x); av.y = fmaf(av.y, sc, wmine * ck.v.y);
+            av.z = fmaf(av.z, sc, wmine * ck.v.z); av.w = fmaf(av.w, sc, wmine * ck.v.w);
             mx = mn;
         };
         AttnChunk ca, cb;
@@ -311,9 +328,10 @@ __device__ __forceinline__ void attn_phase(const SubArgs &A, const AttnPre &P, i
             if (ch + 1 < nch) compute(cb, ch + 1);
         }
     }
-    // V partial sums live per edge group: fold the 8 groups (lanes with equal l & 3)
+    // V partial sums and the softmax denominator live per edge group: fold the 8 groups (lanes with equal l & 3)
 #pragma unroll
     for (int o = 4; o < 32; o <<= 1) {
+        den += __shfl_xor_sync(0xffffffffu, den, o);
         av.x += __shfl_xor_sync(0xffffffffu, av.x, o); av.y += __shfl_xor_sync(0xffffffffu, av.y, o);
         av.z += __shfl_xor_sync(0xffffffffu, av.z, o); av.w += __shfl_xor_sync(0xffffffffu, av.w, o);
     }
