@@ -304,22 +304,102 @@ def map_edges(W, cfg, pos, head, state, hv, interact_mask, inference_mask, pt_po
 
 
 # ------------------------------------------------------------------------------------------------------------
+# insertion stage helpers (agent_decoder.py:449-509, 760-904, attr_tokenizer.py:91-110)
+# ------------------------------------------------------------------------------------------------------------
+def decode_pos(grid, index, y, theta_y):
+    """attr_tokenizer.py:91-99: grid cell -> world position in the frame of ego (y [2], heading theta_y scalar)."""
+    cx = grid[index.long()]                                    # [N,2]
+    th = (theta_y - math.pi / 2).expand(cx.shape[0])
+    c, s = th.cos(), th.sin()
+    rot = torch.zeros(cx.shape[0], 2, 2)
+    rot[:, 0, 0], rot[:, 0, 1], rot[:, 1, 0], rot[:, 1, 1] = c, s, -s, c
+    cx = torch.bmm(cx[:, None], rot)[:, 0]
+    return (cx + y).float()
+
+
+def decode_heading(index, angle_interval=3.0):
+    """attr_tokenizer.py:106-110."""
+    ang = index * angle_interval - 180
+    return (ang / 360 * (2 * math.pi)).float()
+
+
+def seed_query_feature(W, T, grid_tab, G):
+    """`_build_agent_feature(num_step, device, None, None, state_index=invalid, n=1)` (agent_decoder.py:449-509) as the
+    insertion stage calls it (:1817-1821): no-token embedding, centre-cell grid embedding, all-invalid motion,
+    seed type / 0.1 shape, invalid state."""
+    tok = W['no_token_emb.weight'][0][None, None].repeat(1, T, 1)
+    gemb = grid_tab[G // 2][None, None].repeat(1, T, 1)
+    mv, hv = build_vector_a(torch.zeros(1, T, 2), torch.zeros(1, T), torch.full((1, T), INVALID))
+    cat = W['type_a_emb.weight'][SEED_TYPE][None] + mlp_embedding(W, 'shape_emb', torch.full((1, 3), 0.1))
+    state = torch.full((1, T), INVALID)
+    return embed_columns(W, tok, mv, hv, cat.expand(T, H).reshape(1, T, H), state, gemb)
+
+
+def a2sa_edges(W, emb, pos_p, head_p, hv_p, mask_a, mask_sa, cur, r, max_nb):
+    """`_build_a2sa_edge` (agent_decoder.py:760-849) with the inference masks restricted to column `cur`.
+    pos_p/head_p/hv_p: [N,T,*] (N rows incl. the query row(s)); mask_a, mask_sa: [N] booleans AT column cur.
+    Flat index = c*N + a.  Returns src, dst (flat), r embedding."""
+    N, T = head_p.shape
+    pc = pos_p[:, cur]
+    q_rows = mask_sa.nonzero().flatten()
+    srcs, dsts = [], []
+    for qi in q_rows.tolist():
+        d = pc - pc[qi]
+        within = (d * d).sum(-1) < r * r
+        within &= within.cumsum(0) <= max_nb                   # torch_cluster.radius: first max_num_neighbors by index
+        cand = within.nonzero().flatten()
+        cand = cand[~mask_sa[cand] & mask_a[cand]]
+        srcs.append(cur * N + cand)
+        dsts.append(torch.full_like(cand, cur * N + qi))
+    src = torch.cat(srcs) if srcs else torch.zeros(0, dtype=torch.long)
+    dst = torch.cat(dsts) if dsts else torch.zeros(0, dtype=torch.long)
+    ps, hs, hvs = pos_p.transpose(0, 1).reshape(-1, 2), head_p.t().reshape(-1), hv_p.transpose(0, 1).reshape(-1, 2)
+    rp = ps[src] - ps[dst]
+    rh = wrap_angle(hs[src] - hs[dst])
+    raw = torch.stack([rp.norm(p=2, dim=-1), angle_between(hvs[dst], rp), rh], dim=-1)
+    return src, dst, raw, fourier_embedding(W, emb, raw)
+
+
+def map2sa_edges(W, emb, pos_p, head_p, hv_p, mask_sa, cur, r, max_nb, pt_pos, pt_ori):
+    """`_build_map2sa_edge` (agent_decoder.py:851-904). src flat = c*P + p, dst flat = c*N + a."""
+    N, T = head_p.shape
+    P = pt_pos.shape[0]
+    q_rows = mask_sa.nonzero().flatten()
+    srcs, dsts = [], []
+    for qi in q_rows.tolist():
+        d = pt_pos[:, :2] - pos_p[qi, cur]
+        within = (d * d).sum(-1) < r * r
+        within &= within.cumsum(0) <= max_nb
+        cand = within.nonzero().flatten()
+        srcs.append(cur * P + cand)
+        dsts.append(torch.full_like(cand, cur * N + qi))
+    src = torch.cat(srcs) if srcs else torch.zeros(0, dtype=torch.long)
+    dst = torch.cat(dsts) if dsts else torch.zeros(0, dtype=torch.long)
+    ps, hs, hvs = pos_p.transpose(0, 1).reshape(-1, 2), head_p.t().reshape(-1), hv_p.transpose(0, 1).reshape(-1, 2)
+    rp = pt_pos[src % P, :2] - ps[dst]
+    ro = wrap_angle(pt_ori[src % P] - hs[dst])
+    raw = torch.stack([rp.norm(p=2, dim=-1), angle_between(hvs[dst], rp), ro], dim=-1)
+    return src, dst, raw, fourier_embedding(W, emb, raw)
+
+
+# ------------------------------------------------------------------------------------------------------------
 # the rollout
 # ------------------------------------------------------------------------------------------------------------
 @torch.no_grad()
 def rollout(scene: Dict, W: Dict[str, torch.Tensor], cfg, seed: int = 2024, scene_id: int = 0,
             forced_tokens: Optional[torch.Tensor] = None, forced_states: Optional[torch.Tensor] = None,
             collect_trace: bool = False, max_iters: Optional[int] = None,
-            assume_no_insertion: bool = False) -> Dict:
-    """Closed-loop decode of one scene (motion stage of agent_decoder.py:1605-2389).
+            assume_no_insertion: bool = False, debug_force_enter: bool = False) -> Dict:
+    """Closed-loop decode of one scene (agent_decoder.py:1605-2389): insertion stage :1744-2114 (when enabled) and
+    motion stage :2116-2301.  debug_force_enter mirrors the reference's `DEBUG=1` switch (:1888-1889), which makes
+    the seed head answer 'enter' - the only way to exercise insertion with random-init weights.
 
     forced_tokens / forced_states: optional [A, S] int64 teacher-forcing overrides of the sampled motion token /
     predicted state per iteration (used to compare implementations step by step without divergence).
     """
-    if not cfg.disable_insertion and not assume_no_insertion:
-        # assume_no_insertion: the caller knows (from a golden log / a biased seed head) that the insertion stage
-        # inserts nobody; it then has no effect on the motion stage, whose state head stays live.
-        raise NotImplementedError('insertion stage lives in oracle/insertion_oracle.py')
+    # assume_no_insertion: the caller knows (from a golden log / a biased seed head) that the insertion stage inserts
+    # nobody; it then has no effect on the motion stage (whose state head stays live) and is skipped.
+    run_insertion = not cfg.disable_insertion and not assume_no_insertion
     ag = scene['agent']
     HC = cfg.hist_cols
     nh = cfg.num_historical_steps
@@ -409,20 +489,168 @@ def rollout(scene: Dict, W: Dict[str, torch.Tensor], cfg, seed: int = 2024, scen
     interact_mask[:, HC:] = True
 
     S = n_rec // cfg.shift
+    A0 = A
+    G = grid.shape[0]
     pred_traj = torch.zeros(A, n_rec, 2)
     pred_head = torch.zeros(A, n_rec)
     pred_state = torch.zeros(A, n_rec)
     pred_type = type_a.clone()
     pred_shape = shape_a[:, HC - 1]
+    vtype = type_a.clone()                                                # vocabulary (box-track table) of each row
+    max_agent_id = int(agent_id.max())
     next_token_list = [hist_token[:, i:i + 1] for i in range(HC)]
     next_state_list = [hist_state[:, i:i + 1] for i in range(HC)]
+    seed_state_prob, seed_pos_prob, seed_agent_occ, seed_pt_occ, seed_occ_gt = [], [], [], [], []
+    insert_log: List[Dict] = []
     cache: Dict[int, torch.Tensor] = {}
     trace: List[Dict] = []
-    x_pt_tiled = x_pt.repeat(T, 1)                                        # [T*P,128], index c*P+p (:2143)
+    insert_limit = 10
 
     n_iter = S if max_iters is None else min(S, max_iters)
     for t in range(n_iter):
         cur, nxt = HC - 1 + t, HC + t
+        A = pos.shape[0]
+        # ================= 1. insertion stage (agent_decoder.py:1744-2114) ====================================
+        st_prob = torch.zeros(11, 1)
+        pos_prob, ag_occ, pt_occ, occ_gt = (torch.zeros(11, 1, G) for _ in range(4))
+        n_new = 0
+        p_pass = 0
+        while run_insertion:
+            p_pass += 1
+            if t == 0 or p_pass - 1 >= insert_limit:
+                break
+            A = pos.shape[0]
+            # the query ("seed") row is a copy of the ego row (`_pad_feat`, :511-526)
+            pos_p = torch.cat([pos, pos[av:av + 1]])
+            head_p = torch.cat([head, head[av:av + 1]])
+            hv_p = torch.cat([hv, hv[av:av + 1]])
+            is_seed = torch.zeros(A + 1, dtype=torch.bool)
+            is_seed[-1] = True
+            inter_p = torch.cat([interact_mask[:, cur], torch.ones(1, dtype=torch.bool)])
+            feat_seed = seed_query_feature(W, T, grid_tab, G)
+            raw_feat = feat0.clone()
+            feat = torch.cat([feat0, feat_seed])
+            e_a2s = a2sa_edges(W, 'r_a2sa_emb', pos_p, head_p, hv_p, inter_p, is_seed, cur, cfg.pl2seed_radius, 300)
+            e_p2s = map2sa_edges(W, 'r_pt2sa_emb', pos_p, head_p, hv_p, is_seed, cur, cfg.pl2seed_radius, 2048,
+                                 pt_pos, pt_ori)
+            occ = torch.zeros(G, dtype=torch.long)
+            g_cur = grid_a[:, cur]
+            occ[g_cur[g_cur != -1]] = 1
+            occ_emb = mlp_layer(W, 'seed_agent_occ_embed', occ.reshape(1, G).float())          # [1,128]
+            occ_src = torch.zeros(1, dtype=torch.long)
+            occ_dst = torch.tensor([cur * (A + 1) + A])
+            x_pt_t = x_pt.repeat(T, 1)
+            for i in range(3):
+                x = feat.transpose(0, 1).reshape(-1, H)
+                x = attention_layer(W, f'occ2sa_attn_layers.{i}', occ_emb, x, None, occ_src, occ_dst, True)
+                x = attention_layer(W, f'pt2sa_attn_layers.{i}', x_pt_t, x, e_p2s[3], e_p2s[0], e_p2s[1], True)
+                x = attention_layer(W, f'a2sa_attn_layers.{i}', x, x, e_a2s[3], e_a2s[0], e_a2s[1], False)
+                feat = x.view(T, A + 1, H).transpose(0, 1)
+            q = feat[-1:, cur]                                                               # [1,128]
+            ego_pos, ego_head = pos[av, cur], head[av, cur]
+            g_ag = mlp_layer(W, 'grid_agent_occ_head', q)
+            g_pt = mlp_layer(W, 'grid_pt_occ_head', q)
+            s_prob = mlp_layer(W, 'seed_state_predict_head', q)
+            s_idx = s_prob.softmax(-1).argmax(-1, keepdim=True)
+            s_idx = torch.where(s_idx == 1, torch.tensor(ENTER), torch.tensor(INVALID))
+            if debug_force_enter:
+                s_idx = torch.full_like(s_idx, ENTER)
+            ty_idx = mlp_layer(W, 'seed_type_predict_head', q).softmax(-1).argmax(-1, keepdim=True)
+            shp = mlp_layer(W, 'seed_shape_predict_head', q)
+            p_soft = torch.softmax(mlp_layer(W, 'seed_pos_rel_token_predict_head', q), dim=-1)
+            top_p, top_i = torch.topk(p_soft, k=cfg.insert_beam_size, dim=-1)
+            if cfg.insert_beam_size > 1:
+                raise NotImplementedError('insert_beam_size > 1 needs the shared sampler (reference: torch.multinomial)')
+            cell = top_i[:, :1]
+            new_pos = decode_pos(grid, cell[..., 0], ego_pos, ego_head)
+            if bool(occ[cell[0, 0]]):                                                        # overlap filter (:1906-1909)
+                feat0 = raw_feat
+                continue
+            if bool((s_idx == INVALID).all()) or n_new + 1 > insert_limit:
+                feat0 = raw_feat
+                break
+            n_new += 1
+            # ---- 1.5 append the new agent (:1923-1995) -------------------------------------------------------
+            agent_id = torch.cat([agent_id, torch.tensor([max_agent_id + 1], dtype=agent_id.dtype)])
+            max_agent_id += 1
+            mask = torch.cat([mask, torch.ones(1, T, dtype=torch.bool)])
+            temporal_mask = torch.cat([temporal_mask, torch.ones(1, T, dtype=torch.bool)])
+            interact_mask = torch.cat([interact_mask, torch.ones(1, T, dtype=torch.bool)])
+            n_pos, n_head = torch.zeros(1, T, 2), torch.zeros(1, T)
+            n_grid = torch.full((1, T), -1, dtype=grid_a.dtype)
+            n_state = torch.full((1, T), INVALID, dtype=state.dtype)
+            n_shape = torch.full((1, T, 3), 0.1)
+            n_type = torch.full((1, T), SEED_TYPE, dtype=torch.long)
+            n_pos[:, cur] = new_pos
+            n_head[:, cur] = ego_head                                                        # dummy value
+            n_grid[:, cur] = cell[0, 0]
+            n_type[:, cur:] = ty_idx[0, 0]
+            n_shape[:, cur:] = shp[:, None]
+            n_state[:, cur] = s_idx[0, 0]
+            pos, head, grid_a, state = torch.cat([pos, n_pos]), torch.cat([head, n_head]), \
+                torch.cat([grid_a, n_grid]), torch.cat([state, n_state])
+            pred_type = torch.cat([pred_type, n_type[:, cur].to(pred_type.dtype)])
+            pred_shape = torch.cat([pred_shape, n_shape[:, cur]])
+            vtype = torch.cat([vtype, ty_idx[0].to(vtype.dtype)])
+            mask[-1:, :cur + 1] = False
+            interact_mask[-1:, :cur] = False
+            npt, nph, nps = torch.zeros(1, n_rec, 2), torch.zeros(1, n_rec), torch.zeros(1, n_rec)
+            npt[:, (t - 1) * 5:t * 5] = n_pos[:, cur, None].repeat(1, 5, 1)
+            nph[:, (t - 1) * 5:t * 5] = n_head[:, cur, None].repeat(1, 5)
+            nps[:, (t - 1) * 5:t * 5] = s_idx.repeat(1, 5).float()
+            pred_traj, pred_head, pred_state = torch.cat([pred_traj, npt]), torch.cat([pred_head, nph]), \
+                torch.cat([pred_state, nps])
+            n_tok = W['no_token_emb.weight'][0][None, None].repeat(1, T, 1)
+            n_tok[:, cur] = W['bos_token_emb.weight'][0]
+            tok_emb = torch.cat([tok_emb, n_tok])
+            n_type_emb = W['type_a_emb.weight'][n_type]                                      # [1,T,128]
+            n_shape_emb = mlp_embedding(W, 'shape_emb', n_shape.reshape(-1, 3)).view(1, T, H)
+            type_emb, shape_emb = torch.cat([type_emb, n_type_emb]), torch.cat([shape_emb, n_shape_emb])
+            # ---- 2. heading of the new agent (:2003-2074) ----------------------------------------------------
+            mv_s, hv_s = build_vector_a(pos[-1:], head[-1:], state[-1:])
+            assert bool((mv_s[:, :cur] == -2.0).all()) and bool((mv_s[:, cur] == 1.0).all())
+            mv_s[:, cur + 2:] = 0.0
+            hv_s[:, cur + 2:] = 0.0
+            mv, hv = torch.cat([mv, mv_s]), torch.cat([hv, hv_s])
+            n_gemb = grid_tab[n_grid]
+            feat_s = embed_columns(W, n_tok, mv_s, hv_s, n_type_emb + n_shape_emb, n_state, n_gemb)
+            feat = torch.cat([raw_feat, feat_s])
+            is_new = torch.zeros(A + 1, dtype=torch.bool)
+            is_new[-1] = True
+            e_a = a2sa_edges(W, 'r_a2a_emb', pos, head, hv, interact_mask[:, cur], is_new, cur, cfg.a2sa_radius, 24)
+            e_p = map2sa_edges(W, 'r_pt2a_emb', pos, head, hv, is_new, cur, cfg.pl2sa_radius, 128, pt_pos, pt_ori)
+            for i in range(3):
+                x = feat.transpose(0, 1).reshape(-1, H)
+                x = attention_layer(W, f'pt2a_attn_layers.{i}', x_pt_t, x, e_p[3], e_p[0], e_p[1], True)
+                x = attention_layer(W, f'a2a_attn_layers.{i}', x, x, e_a[3], e_a[0], e_a[1], False)
+                feat = x.view(T, A + 1, H).transpose(0, 1)
+            hq = feat[-1:, cur]
+            h_idx = mlp_layer(W, 'seed_heading_rel_token_predict_head', hq).softmax(-1).argmax(-1, keepdim=True)
+            new_head = wrap_angle(decode_heading(h_idx, cfg.angle_interval) + ego_head)
+            head[-1:, cur] = new_head[:, 0]
+            off = torch.tanh(mlp_layer(W, 'seed_offset_xy_predict_head', hq)) * 2
+            pos[-1:, cur] += off
+            mv_s, hv_s = build_vector_a(pos[-1:], head[-1:], state[-1:])
+            mv_s[:, cur + 2:] = 0.0
+            hv_s[:, cur + 2:] = 0.0
+            mv[-1:] = mv_s
+            hv[-n_new:] = hv_s                                 # sic (:2083): every agent inserted this iteration
+            feat_s = embed_columns(W, n_tok, mv_s, hv_s, n_type_emb + n_shape_emb, state[-1:], n_gemb)
+            feat0 = torch.cat([raw_feat, feat_s])
+            occ_gt[n_new], ag_occ[n_new], pt_occ[n_new], pos_prob[n_new] = occ.float(), g_ag, g_pt, p_soft
+            st_prob[n_new] = s_prob.softmax(-1)[:, -1]
+            insert_log.append({'t': t, 'cell': int(cell[0, 0]), 'type': int(ty_idx[0, 0]), 'pos': pos[-1, cur].clone(),
+                               'head': head[-1, cur].clone(), 'shape': shp[0].clone(), 'heading_token': int(h_idx[0, 0])})
+        seed_state_prob.append(st_prob)
+        seed_pos_prob.append(pos_prob)
+        seed_agent_occ.append(ag_occ)
+        seed_pt_occ.append(pt_occ)
+        seed_occ_gt.append(occ_gt)
+        next_state_list[-1] = torch.cat([next_state_list[-1], torch.full((n_new, 1), ENTER, dtype=torch.long)])
+
+        # ================= 3. motion stage (agent_decoder.py:2116-2301) =======================================
+        A = pos.shape[0]
+        x_pt_tiled = x_pt.repeat(T, 1)                                        # [T*P,128], index c*P+p (:2143)
         # the t==0 mask built at :1760-1764 is overwritten at :2119-2121 before the motion edges are built, so the
         # only destination column is `cur` in every iteration (column 0 runs through the layers edge-less at t=0)
         inf_mask = torch.zeros_like(temporal_mask)
@@ -445,7 +673,10 @@ def rollout(scene: Dict, W: Dict[str, torch.Tensor], cfg, seed: int = 2024, scen
             if t == 0:
                 cache[i + 1] = feat.clone()
             else:
-                cache[i + 1][:, cur] = feat[:, cur]
+                n = cache[i + 1].shape[0]
+                cache[i + 1][:n, cur] = feat[:n, cur]
+                if A > n:                                       # rows inserted this iteration: all their columns (:2156-2158)
+                    cache[i + 1] = torch.cat([cache[i + 1], feat[n:]])
             if collect_trace:
                 layer_out.append(feat[:, cur].clone())
 
@@ -461,12 +692,12 @@ def rollout(scene: Dict, W: Dict[str, torch.Tensor], cfg, seed: int = 2024, scen
             nstate[:] = VALID
         ntoken = sample_topk(logits, cfg.motion_beam_size, seed, scene_id, t)
         if forced_tokens is not None:
-            ntoken = forced_tokens[:, t].clone()
+            ntoken = forced_tokens[:A, t].clone()
         if forced_states is not None:
-            nstate = forced_states[:, t].clone()
+            nstate = forced_states[:A, t].clone()
 
         # ---- advance (agent_decoder.py:2175-2239) -----------------------------------------------------------
-        box = vocab[type_a.clamp(max=2), ntoken]                                            # [A,6,4,2]
+        box = vocab[vtype.clamp(max=2), ntoken]                                             # [A,6,4,2]
         th = head[:, cur]
         c, s = th.cos(), th.sin()
         rot = torch.zeros(A, 2, 2)
@@ -490,10 +721,11 @@ def rollout(scene: Dict, W: Dict[str, torch.Tensor], cfg, seed: int = 2024, scen
         grid_a[inv_n, nxt] = -1
         mask[inv_n, nxt] = False
         interact_mask[inv_n, nxt] = False
+        tok_emb[inv_n, nxt] = W['no_token_emb.weight'][0]
         type_emb[inv_n, nxt] = seed_type_emb
         shape_emb[inv_n, nxt] = inv_shape_emb
         for ti in range(3):
-            m = type_a == ti
+            m = vtype == ti
             tok_emb[m, nxt] = tok_tab[ti][ntoken[m]]
 
         # ---- re-embed (agent_decoder.py:2265-2287) ------------------------------------------------------------
@@ -506,7 +738,8 @@ def rollout(scene: Dict, W: Dict[str, torch.Tensor], cfg, seed: int = 2024, scen
         if collect_trace:
             def _dst_only(e, div):
                 return {'src': e[0].clone(), 'dst': e[1].clone(), 'raw': e[2].clone(), 'emb': e[3].clone()}
-            trace.append({'t': t, 'cur': cur, 'edges_t': _dst_only(e_t, T), 'edges_a': _dst_only(e_a, A),
+            trace.append({'t': t, 'cur': cur, 'n_rows': A, 'n_new': n_new, 'edges_t': _dst_only(e_t, T),
+                          'edges_a': _dst_only(e_a, A),
                           'edges_m': _dst_only(e_m, A), 'layer_out': torch.stack(layer_out), 'head_in': hin.clone(),
                           'token_logits': logits.clone(), 'state_logits': s_logits.clone(),
                           'token': ntoken.clone(), 'state': nstate.clone(), 'pos_next': pos[:, nxt].clone(),
@@ -514,33 +747,44 @@ def rollout(scene: Dict, W: Dict[str, torch.Tensor], cfg, seed: int = 2024, scen
                           'feat_next': feat0[:, nxt].clone()})
 
     # ---- outputs (agent_decoder.py:2303-2389) ---------------------------------------------------------------
+    A = pos.shape[0]
+    for i in range(len(next_token_list)):
+        k = A - next_token_list[i].shape[0]
+        next_token_list[i] = torch.cat([next_token_list[i], torch.full((k, 1), -1, dtype=torch.long)]).long()
+        k = A - next_state_list[i].shape[0]
+        next_state_list[i] = torch.cat([next_state_list[i], torch.zeros(k, 1, dtype=torch.long)]).long()
     pred_traj = torch.cat([torch.zeros(A, nh, 2), pred_traj], 1)
     pred_head = torch.cat([torch.zeros(A, nh), pred_head], 1)
     pred_state = torch.cat([torch.zeros(A, nh), pred_state], 1)
-    pred_traj[:, 0] = ag['position'][filt, 0, :2]
-    pred_head[:, 0] = ag['heading'][filt, 0]
-    pred_state[:, 1:nh] = hist_state[:, :HC].repeat_interleave(cfg.shift, dim=1).float()
+    pred_traj[:A0, 0] = ag['position'][filt, 0, :2]
+    pred_head[:A0, 0] = ag['heading'][filt, 0]
+    pred_state[:A0, 1:nh] = hist_state[:, :HC].repeat_interleave(cfg.shift, dim=1).float()
     htok = hist_token[:, :HC].clone()
     htok[htok < 0] = 0
-    hbox = vocab[type_a.clamp(max=2)[:, None].expand(A, HC), htok]                          # [A,HC,6,4,2]
-    th = head[:, 0]
+    hbox = vocab[type_a.clamp(max=2)[:, None].expand(A0, HC), htok]                         # [A0,HC,6,4,2]
+    th = head[:A0, 0]
     c, s = th.cos(), th.sin()
-    rot = torch.zeros(A, 2, 2)
+    rot = torch.zeros(A0, 2, 2)
     rot[:, 0, 0], rot[:, 0, 1], rot[:, 1, 0], rot[:, 1, 1] = c, s, -s, c
-    hworld = torch.bmm(hbox.reshape(A, HC * 24, 2), rot).view(A, HC, 6, 4, 2) + pos[:, 0][:, None, None, None]
-    pred_traj[:, 1:nh] = hworld[:, :, 1:].mean(dim=3).reshape(A, -1, 2)
+    hworld = torch.bmm(hbox.reshape(A0, HC * 24, 2), rot).view(A0, HC, 6, 4, 2) + pos[:A0, 0][:, None, None, None]
+    pred_traj[:A0, 1:nh] = hworld[:, :, 1:].mean(dim=3).reshape(A0, -1, 2)
     d = hworld[:, :, 1:, 0] - hworld[:, :, 1:, 3]
-    pred_head[:, 1:nh] = torch.atan2(d[..., 1], d[..., 0]).reshape(A, -1)
+    pred_head[:A0, 1:nh] = torch.atan2(d[..., 1], d[..., 0]).reshape(A0, -1)
     pred_valid = (pred_state != INVALID) & (pred_state != ENTER)
     eval_shape = torch.zeros_like(pred_shape)
     for ti, key in enumerate(('vehicle', 'pedstrain', 'cyclist')):
         from infgen_b200.config import AGENT_SHAPE
-        eval_shape[type_a == ti] = torch.tensor(AGENT_SHAPE[key])
+        eval_shape[vtype == ti] = torch.tensor(AGENT_SHAPE[key])
     out = {
         'ego_index': av, 'agent_id': agent_id, 'valid_mask': valid, 'pos_a': pos, 'head_a': head, 'gt_traj': gt_traj,
         'pred_traj': pred_traj, 'pred_head': pred_head, 'pred_type': pred_type, 'pred_state': pred_state,
         'pred_z': torch.zeros_like(pred_traj[..., 0]), 'pred_shape': pred_shape, 'eval_shape': eval_shape,
         'pred_valid': pred_valid,
         'next_token_idx': torch.cat(next_token_list, dim=-1), 'next_state_idx': torch.cat(next_state_list, dim=-1),
+        'next_state_prob_seed': torch.cat(seed_state_prob, dim=1) if seed_state_prob else None,
+        'next_pos_rel_prob_seed': torch.cat(seed_pos_prob, dim=1) if seed_pos_prob else None,
+        'grid_agent_occ_seed': torch.cat(seed_agent_occ, dim=1) if seed_agent_occ else None,
+        'grid_pt_occ_seed': torch.cat(seed_pt_occ, dim=1) if seed_pt_occ else None,
+        'grid_agent_occ_gt_seed': torch.cat(seed_occ_gt, dim=1) if seed_occ_gt else None,
     }
-    return {'out': out, 'trace': trace}
+    return {'out': out, 'trace': trace, 'insert_log': insert_log}

@@ -13,6 +13,10 @@ CASES = {
                        disable_insertion=False, no_insert_bias=True),
     'std_a64': dict(scene_seed=13, agents=64, map_tokens=2048, steps=91, ragged=0.2, ego=5, weight_seed=0,
                     disable_insertion=True),
+    # insertion stage (agent_decoder.py:1744-2114) live: the reference's DEBUG=1 switch (:1888-1889) forces the seed
+    # head to 'enter' (random-init weights never insert otherwise); 12 agents grow to 27 rows over 16 iterations
+    'insert_a12': dict(scene_seed=21, agents=12, map_tokens=512, steps=91, ragged=0.3, ego=2, weight_seed=2,
+                       disable_insertion=False, debug_force_enter=True),
 }
 
 

@@ -12,6 +12,9 @@ Cases (see `CASES` in tests/golden/cases.py):
   ragged_a24 24 agents, half of them entering/exiting, ego at index 3 with filtered rows before it; the state
              head is live (insertion enabled but the seed head is biased so the reference inserts nobody).
   std_a64    64 agents, 2048 map tokens, 16 iterations greedy (the headline shape).
+  insert_a12 12 agents, insertion stage live (reference run with DEBUG=1): one agent inserted per iteration.
+
+    python tests/golden/make_golden.py [case ...]   # default: all cases
 """
 import os
 import sys
@@ -27,16 +30,30 @@ from tests.golden.cases import CASES, build_case          # noqa: E402
 from oracle.ref_runner import run_reference                # noqa: E402
 
 
+def _stack_ragged(xs):
+    """Per-iteration tensors whose row count grows (insertion): pad with NaN to the final row count."""
+    n = max(x.shape[0] for x in xs)
+    return torch.stack([torch.cat([x, x.new_full((n - x.shape[0], *x.shape[1:]), float('nan'))]) for x in xs])
+
+
 def main():
     torch.manual_seed(0)
-    for name in CASES:
+    names = sys.argv[1:] or list(CASES)
+    for name in names:
         scene, sd, cfg, spec = build_case(name)
         t0 = time.time()
-        r = run_reference(scene, sd, cfg)
+        if spec.get('debug_force_enter'):
+            os.environ['DEBUG'] = '1'                               # agent_decoder.py:1888-1889
+        try:
+            r = run_reference(scene, sd, cfg)
+        finally:
+            os.environ.pop('DEBUG', None)
         out, tr = r['out'], r['trace']
         S = len(tr['token_logits'])
-        logits = torch.stack(tr['token_logits'])                    # [S,A,2048]
-        top_v, top_i = logits.topk(8, dim=-1)
+        logits = _stack_ragged(tr['token_logits'])                  # [S,A,2048]
+        top_v, top_i = logits.nan_to_num(-1e30).topk(8, dim=-1)
+        tr['head_in'] = list(_stack_ragged(tr['head_in']))
+        tr['state_logits'] = list(_stack_ragged(tr['state_logits']))
         save = {
             'next_token_idx': out['next_token_idx'].numpy(), 'next_state_idx': out['next_state_idx'].numpy(),
             'pos_a': out['pos_a'].numpy(), 'head_a': out['head_a'].numpy(),
@@ -51,6 +68,11 @@ def main():
         }
         if spec.get('full_logits'):
             save['token_logits'] = logits.numpy()
+        if not spec['disable_insertion']:
+            save['n_rows'] = np.array([x.shape[0] for x in r['trace']['token_logits']])
+            for k in ('next_state_prob_seed', 'next_pos_rel_prob_seed', 'grid_agent_occ_seed', 'grid_pt_occ_seed',
+                      'grid_agent_occ_gt_seed'):
+                save[k] = out[k].numpy()
         path = os.path.join(os.path.dirname(os.path.abspath(__file__)), f'case_{name}.npz')
         np.savez_compressed(path, **save)
         print(f'{name}: {S} iterations, A={logits.shape[1]}, {time.time() - t0:.1f}s reference CPU, '
