@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define INFGEN_ABI_VERSION 3
+#define INFGEN_ABI_VERSION 4
 
 typedef enum {
     INFGEN_OK = 0,
@@ -63,6 +63,13 @@ typedef struct {
     uint32_t seed;                /* sampler seed (counter-based; see DESIGN.md "sampler") */
     int32_t use_cuda_graph;       /* replay one captured decode iteration per step */
     int32_t trace;                /* keep per-iteration head inputs / logits / layer outputs for parity tests */
+    /* insertion stage (agent_decoder.py:1744-2114); only read when disable_insertion == 0 */
+    int32_t insert_beam_size;     /* 10  top-k of the position sampler, 1 = greedy (agent_decoder.py:301, 1899) */
+    int32_t debug_force_enter;    /* the reference's DEBUG=1 switch: the seed head always answers 'enter' (:1888-1889) */
+    float pl2seed_radius;         /* 75  radius of the seed query (agent_decoder.py:1837, 1846) */
+    float a2sa_radius;            /* 10  heading stage, agents (agent_decoder.py:2028) */
+    float pl2sa_radius;           /* 10  heading stage, map tokens (agent_decoder.py:2034) */
+    float angle_interval;         /* 3   degrees per heading token (attr_tokenizer.py:20) */
 } infgen_config;
 
 /* One batch of scenes, already filtered/padded as agent_decoder.py:1609-1657 does (host side: infgen_b200/host.py). */
@@ -102,6 +109,15 @@ typedef struct {
     int32_t *next_state;          /* [R][T]      */
     float *hist_traj;             /* [R][hist_cols*5][2] raw steps 1..10 rebuilt from history tokens (:2311-2335) */
     float *hist_head;             /* [R][hist_cols*5] */
+    /* insertion stage (NULL when not wanted; zero-filled when the stage is disabled) */
+    int32_t *n_rows_final;        /* [n_scenes] rows of each scene after the rollout (appended agents included) */
+    int32_t *pred_type;           /* [R] predicted type of appended rows (:1955) */
+    float *pred_shape;            /* [R][3] predicted shape of appended rows (:1956) */
+    float *state_prob_seed;       /* [n_scenes][11][S]        next_state_prob_seed (:2105) */
+    float *pos_prob_seed;         /* [n_scenes][11][S][grid]  next_pos_rel_prob_seed (:2104) */
+    float *agent_occ_seed;        /* [n_scenes][11][S][grid]  grid_agent_occ_seed (:2102) */
+    float *pt_occ_seed;           /* [n_scenes][11][S][grid]  grid_pt_occ_seed (:2103) */
+    float *occ_gt_seed;           /* [n_scenes][11][S][grid]  grid_agent_occ_gt_seed (:2101) */
 } infgen_outputs;
 
 /* ---- library ------------------------------------------------------------------------------------------- */

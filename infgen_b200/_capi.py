@@ -9,7 +9,7 @@ import os
 from typing import Optional
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib', 'libinfgen_b200.so')
-ABI_VERSION = 3
+ABI_VERSION = 4
 HOST, DEVICE = 0, 1
 
 c_f32p = C.POINTER(C.c_float)
@@ -25,6 +25,8 @@ class Config(C.Structure):
         ('max_a2a_neighbors', C.c_int32), ('pl2a_radius', C.c_float), ('a2a_radius', C.c_float),
         ('use_state_token', C.c_int32), ('disable_insertion', C.c_int32), ('motion_beam_size', C.c_int32),
         ('seed', C.c_uint32), ('use_cuda_graph', C.c_int32), ('trace', C.c_int32),
+        ('insert_beam_size', C.c_int32), ('debug_force_enter', C.c_int32), ('pl2seed_radius', C.c_float),
+        ('a2sa_radius', C.c_float), ('pl2sa_radius', C.c_float), ('angle_interval', C.c_float),
     ]
 
 
@@ -42,6 +44,8 @@ class Outputs(C.Structure):
     _fields_ = [
         ('pos', c_f32p), ('head', c_f32p), ('pred_traj', c_f32p), ('pred_head', c_f32p), ('pred_state', c_f32p),
         ('next_token', c_i32p), ('next_state', c_i32p), ('hist_traj', c_f32p), ('hist_head', c_f32p),
+        ('n_rows_final', c_i32p), ('pred_type', c_i32p), ('pred_shape', c_f32p), ('state_prob_seed', c_f32p),
+        ('pos_prob_seed', c_f32p), ('agent_occ_seed', c_f32p), ('pt_occ_seed', c_f32p), ('occ_gt_seed', c_f32p),
     ]
 
 

@@ -50,7 +50,10 @@ class B200AgentDecoder:
             pl2a_radius=self.cfg.pl2a_radius, a2a_radius=self.cfg.a2a_radius,
             use_state_token=int(self.cfg.use_state_token), disable_insertion=int(self.cfg.disable_insertion),
             motion_beam_size=self.cfg.motion_beam_size, seed=seed, use_cuda_graph=int(use_cuda_graph),
-            trace=int(trace))
+            trace=int(trace), insert_beam_size=self.cfg.insert_beam_size,
+            debug_force_enter=int(self.cfg.debug_force_enter), pl2seed_radius=self.cfg.pl2seed_radius,
+            a2sa_radius=self.cfg.a2sa_radius, pl2sa_radius=self.cfg.pl2sa_radius,
+            angle_interval=self.cfg.angle_interval)
         h = C.c_void_p()
         _capi.check(self.lib.infgen_create(C.byref(c), _capi.f32p(blob), blob.size, _capi.f32p(cells),
                                            _capi.f32p(vocab_arr), C.byref(h)))
@@ -123,7 +126,13 @@ class B200AgentDecoder:
             pos=_capi.f32p(b.out_pos), head=_capi.f32p(b.out_head), pred_traj=_capi.f32p(b.out_pred_traj),
             pred_head=_capi.f32p(b.out_pred_head), pred_state=_capi.f32p(b.out_pred_state),
             next_token=_capi.i32p(b.out_next_token), next_state=_capi.i32p(b.out_next_state),
-            hist_traj=_capi.f32p(b.out_hist_traj), hist_head=_capi.f32p(b.out_hist_head))
+            hist_traj=_capi.f32p(b.out_hist_traj), hist_head=_capi.f32p(b.out_hist_head),
+            n_rows_final=_capi.i32p(b.out_n_rows))
+        if b.insertion:
+            o.pred_type, o.pred_shape = _capi.i32p(b.out_pred_type), _capi.f32p(b.out_pred_shape)
+            o.state_prob_seed, o.pos_prob_seed = _capi.f32p(b.out_state_prob_seed), _capi.f32p(b.out_pos_prob_seed)
+            o.agent_occ_seed, o.pt_occ_seed = _capi.f32p(b.out_agent_occ_seed), _capi.f32p(b.out_pt_occ_seed)
+            o.occ_gt_seed = _capi.f32p(b.out_occ_gt_seed)
         loc = _capi.DEVICE if getattr(b, 'on_device', False) else _capi.HOST
         _capi.check(self.lib.infgen_read(self._h, C.byref(o), loc))
 
@@ -172,9 +181,8 @@ class B200AgentDecoder:
                         scene_ids: Optional[Sequence[int]] = None, motion_only: bool = False) -> List[Dict]:
         """Closed-loop rollout of several independent scenes in one launch sequence (a capability the reference
         lacks: its inference is batch-size-1, agent_decoder.py:1631; the oracle is one reference call per scene)."""
-        if not self.cfg.disable_insertion and not motion_only:
-            raise NotImplementedError('the agent-insertion stage (agent_decoder.py:1773-2114) is not built yet: '
-                                      'construct with disable_insertion=True or pass motion_only=True')
+        if motion_only and not self.cfg.disable_insertion:
+            raise ValueError('motion_only needs an engine built with disable_insertion=True')
         self._check_vocab(datas[0])
         scenes = [prepare_scene(d, m, self.cfg) for d, m in zip(datas, map_encs)]
         batch = self._host_cache

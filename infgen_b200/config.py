@@ -45,6 +45,8 @@ class DecoderConfig:
     use_state_token: bool = True
     motion_beam_size: int = 5           # agent_decoder.py:300 (1 = greedy)
     insert_beam_size: int = 10          # agent_decoder.py:301
+    debug_force_enter: bool = False     # the reference's DEBUG=1 env switch: seed head forced to 'enter' (:1888-1889)
+    insert_row_reserve: int = 64        # rows kept free per scene for agents the insertion stage appends
     num_seed_feature: int = 10          # agent_decoder.py:292 (the "last 10 rows" temporal-edge quirk)
     max_pl2a_neighbors: int = 5         # agent_decoder.py:711
     max_a2a_neighbors: int = 300        # agent_decoder.py:633

@@ -23,7 +23,8 @@ struct DecState {
     float *pos, *head;             // [R][T][2], [R][T]
     int *state, *token, *grid;     // [R][T]
     uint8_t *interact, *tsrc;      // [R][T]
-    const int *type;               // [R]
+    const int *type;               // [R] (rows appended by the insertion stage get their predicted type)
+    const int *ins_col;            // [R] insertion column of appended rows, -1 for the scene's own agents (NULL: none)
     const int *pt_ptr;
     const float *pt_pos, *pt_ori;
     const float *grid_cells;       // [G][2]
@@ -194,7 +195,9 @@ __device__ __forceinline__ EmbedIn embed_inputs_row(const DecState &s, int r, in
     // row R = seed type + 0.1 shape.  The reference builds the categorical embeddings once, while every future
     // column is still 'invalid' (agent_decoder.py:1653-1657, 458-470), and later only rewrites them for steps that
     // turn invalid (:2235-2239): every generated column therefore carries the seed/0.1 row, valid or not.
-    o.cat_idx = (inv || col >= s.HC) ? R : r;
+    // Rows appended by the insertion stage carry their predicted type / shape from the insertion column on (:1953-1954).
+    const bool inserted = s.ins_col != nullptr && s.ins_col[r] >= 0;
+    o.cat_idx = (inv || (col >= s.HC && !inserted)) ? R : r;
     return o;
 }
 

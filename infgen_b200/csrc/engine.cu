@@ -16,6 +16,7 @@
 #include "ops.cuh"
 #include "layer.cuh"
 #include "decode.cuh"
+#include "insert.cuh"
 
 using namespace infgen;
 
@@ -145,6 +146,13 @@ struct infgen_engine {
     float *grid_cells = nullptr, *vocab = nullptr;
     float *tok_tab = nullptr, *grid_tab = nullptr;      // [3][V+2][128], [G+1][128]
     AttnW t[6], m[6], a[6];
+    AttnW occ2sa[3], pt2sa[3], a2sa[3];                 // insertion stage (agent_decoder.py:235-247)
+    FourierW f_ps, f_as;                                // r_pt2sa_emb, r_a2sa_emb
+    MlpHeadW h_seed_state, h_seed_type, h_seed_shape, h_seed_pos, h_seed_heading, h_seed_offset, h_occ_embed,
+        h_ag_occ, h_pt_occ;
+    float *seed_feat = nullptr;                         // [128] input feature of the seed query row
+    InsState ins;
+    bool ins_ready = false;
     FourierW f_t, f_m, f_a, f_x;
     MlpEmbW e_shape, e_fusion, e_tok[3], e_grid;
     MlpHeadW h_tok, h_state;
@@ -159,6 +167,7 @@ struct infgen_engine {
     int *d_err = nullptr;
     // forcing
     bool forcing = false;
+    bool forcing_no_insert = false;
     // graph
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
@@ -322,10 +331,11 @@ static float *fbuf(infgen_engine *e, const char *name) { return (float *)e->bufs
 static inline void count_launch(infgen_engine *e) { if (!e->capturing) e->launches++; }
 
 // per-kernel-class device timing (bench.py roofline leg): event pairs around every launch, plain launches only
-enum KClass { KC_EDGE_BUILD, KC_FOURIER, KC_EMBED, KC_LAYER_STACK, KC_LAYER_TM, KC_LAYER_A, KC_HEADS, KC_ADVANCE, KC_MISC,
-              KC_COUNT };
+enum KClass { KC_EDGE_BUILD, KC_FOURIER, KC_EMBED, KC_LAYER_STACK, KC_LAYER_TM, KC_LAYER_A, KC_HEADS, KC_ADVANCE, KC_INSERT,
+              KC_MISC, KC_COUNT };
 static const char *KCLASS_NAME[KC_COUNT] = {"k_edge_build", "k_fourier:edges", "k_embed_column", "k_layer:stack18",
-                                            "k_layer:temporal+map", "k_layer:agent", "k_heads", "k_advance", "misc"};
+                                            "k_layer:temporal+map", "k_layer:agent", "k_heads", "k_advance",
+                                            "insertion stage", "misc"};
 struct ProfScope {
     infgen_engine *e;
     bool on;
@@ -401,12 +411,12 @@ static int launch_mlp_embed(infgen_engine *e, const MlpEmbArgs &a, int cls = KC_
 
 static RowSpace scene_rows(infgen_engine *e) {
     RowSpace r;
-    r.n_total = e->R; r.cap = e->cap; r.n_rows = e->st.n_rows;
+    r.n_total = e->R; r.cap = e->cap; r.n_rows = e->st.n_rows; r.row_lo = nullptr;
     return r;
 }
 static RowSpace flat_rows(int n) {
     RowSpace r;
-    r.n_total = n; r.cap = 0; r.n_rows = nullptr;
+    r.n_total = n; r.cap = 0; r.n_rows = nullptr; r.row_lo = nullptr;
     return r;
 }
 
@@ -422,6 +432,21 @@ static int enqueue_embed_column(infgen_engine *e, int col_add) {
     {
         ProfScope ps(e, KC_EMBED);
         k_embed_column<<<(R + EM - 1) / EM, NT_S, COLEMB_SMEM, e->stream>>>(ca);
+    }
+    CKL(); count_launch(e);
+    return 0;
+}
+
+static int enqueue_embed_rows(infgen_engine *e, const int *row_lo) {
+    DecState &s = e->st;
+    ColEmbArgs ca;
+    memset(&ca, 0, sizeof(ca));
+    ca.rows = scene_rows(e); ca.rows.row_lo = row_lo; ca.fx = e->f_x; ca.fusion = e->e_fusion;
+    ca.s = s; ca.col_add = 0; ca.cat_tab = fbuf(e, "cat_tab");
+    ca.tok_tab = e->tok_tab; ca.state_tab = e->state_emb; ca.grid_tab = e->grid_tab; ca.out = fbuf(e, "x");
+    {
+        ProfScope ps(e, KC_INSERT);
+        k_embed_column<<<(e->R + EM - 1) / EM, NT_S, COLEMB_SMEM, e->stream>>>(ca);
     }
     CKL(); count_launch(e);
     return 0;
@@ -476,6 +501,210 @@ static int enqueue_layers(infgen_engine *e, bool with_edges, int trace_iter) {
         RET(launch_layer(e, tm, KC_LAYER_TM));
         RET(launch_layer(e, ag, KC_LAYER_A));
     }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// insertion stage (agent_decoder.py:1744-2114), host-driven: the number of passes is data dependent
+// ---------------------------------------------------------------------------------------------------------------
+static int launch_mlp_layer(infgen_engine *e, const MlpHeadW &w, const float *x, int n, float *out) {
+    MlpLayerArgs la;
+    memset(&la, 0, sizeof(la));
+    la.n = n; la.x = x; la.w = w; la.out = out;
+    ProfScope ps(e, KC_INSERT);
+    k_mlp_layer<<<dim3((n + HM - 1) / HM, w.n_pad / 128), NT_S, MLP_LAYER_SMEM, e->stream>>>(la);
+    CKL(); count_launch(e);
+    return 0;
+}
+// every active row >= row_lo through a stack of layers WITHOUT edges, keeping the K|V rows of the non-bipartite ones
+static int enqueue_edgeless(infgen_engine *e, const int *row_lo, float *x, bool seed_stack) {
+    LayerArgs la;
+    memset(&la, 0, sizeof(la));
+    la.rows = scene_rows(e); la.rows.row_lo = row_lo; la.x = x; la.ring = RING; la.col_ptr = e->st.col;
+    const size_t kvl = (size_t)e->R * 256;
+    int n = 0;
+    if (seed_stack) {                                   // 3 x {occ2sa, pt2sa, a2sa}: K|V of the a2sa layers
+        float *kv = fbuf(e, "kv_sa");
+        la.pre0 = make_pre(e->occ2sa[0], false, nullptr, false, 0, false);
+        for (int i = 0; i < 3; ++i) {
+            SubArgs &o = la.sub[n++]; o.w = e->occ2sa[i].cs_post; o.has_pos = 0;
+            o.pre = make_pre(e->pt2sa[i], false, nullptr, false, 0, false);
+            SubArgs &p = la.sub[n++]; p.w = e->pt2sa[i].cs_post; p.has_pos = 1;
+            p.pre = make_pre(e->a2sa[i], true, kv + i * kvl, false, 0, false);
+            if (i == 2) break;                          // the agents' a2sa.2 output is never used
+            SubArgs &g = la.sub[n++]; g.w = e->a2sa[i].cs_post; g.has_pos = 1;
+            g.pre = make_pre(e->occ2sa[i + 1], false, nullptr, false, 0, false);
+        }
+    } else {                                            // 3 x {pt2a, a2a} (motion layers 0..2): K|V of a2a
+        float *kv = fbuf(e, "kv_ha");
+        la.pre0 = make_pre(e->m[0], false, nullptr, false, 0, false);
+        for (int i = 0; i < 3; ++i) {
+            SubArgs &p = la.sub[n++]; p.w = e->m[i].cs_post; p.has_pos = 1;
+            p.pre = make_pre(e->a[i], true, kv + i * kvl, false, 0, false);
+            if (i == 2) break;
+            SubArgs &g = la.sub[n++]; g.w = e->a[i].cs_post; g.has_pos = 1;
+            g.pre = make_pre(e->m[i + 1], false, nullptr, false, 0, false);
+        }
+    }
+    la.n_sub = n;
+    return launch_layer(e, la, KC_INSERT);
+}
+static int enqueue_embed_rows(infgen_engine *e, const int *row_lo);
+
+static int run_insertion(infgen_engine *e) {
+    DecState &s = e->st;
+    InsState &q = e->ins;
+    const int ns = e->n_scenes, R = e->R, cap = e->cap, G = e->cfg.grid_size;
+    cudaStream_t st = e->stream;
+    float *x = fbuf(e, "x"), *x_sa = fbuf(e, "x_sa"), *x_ha = fbuf(e, "x_ha");
+    {
+        ProfScope ps(e, KC_INSERT);
+        k_ins_begin<<<ns, NT, 0, st>>>(s, q);
+    }
+    CKL(); count_launch(e);
+    // agents through the seed stack without edges -> K|V of the a2sa layers
+    CK(cudaMemcpyAsync(x_sa, x, (size_t)R * 128 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    RET(enqueue_edgeless(e, nullptr, x_sa, true));
+    // relative embeddings of the map -> seed edges (the seed pose is the ego pose for every pass of the iteration)
+    FourierArgs fj;
+    memset(&fj, 0, sizeof(fj));
+    fj.normalize = 1; fj.dim = 3; fj.n_slots = ns * SEED_MAP_MAX; fj.cnt = q.ps_cnt; fj.stride = SEED_MAP_MAX;
+    fj.raw = q.ps_raw; fj.w = e->f_ps; fj.out = fbuf(e, "rhat_ps");
+    RET(launch_fourier(e, &fj, 1, KC_INSERT));
+    bool heading_ready = false;
+    for (int pass = 0; pass < INSERT_LIMIT; ++pass) {
+        SeedPrepArgs pa;
+        memset(&pa, 0, sizeof(pa));
+        pa.s = s; pa.q = q; pa.occ_embed = e->h_occ_embed;
+        for (int i = 0; i < 3; ++i) pa.occ2sa[i] = e->occ2sa[i];
+        {
+            ProfScope ps(e, KC_INSERT);
+            k_seed_prepare<<<ns, NT, 0, st>>>(pa);
+        }
+        CKL(); count_launch(e);
+        memset(&fj, 0, sizeof(fj));
+        fj.normalize = 1; fj.dim = 3; fj.n_slots = ns * cap; fj.cnt = q.as_cnt; fj.stride = cap;
+        fj.raw = q.as_raw; fj.w = e->f_as; fj.out = fbuf(e, "rhat_as");
+        RET(launch_fourier(e, &fj, 1, KC_INSERT));
+        {   // the query rows: 3 x {occ2sa, pt2sa, a2sa} with their edges
+            LayerArgs la;
+            memset(&la, 0, sizeof(la));
+            la.rows.n_total = ns; la.rows.cap = 1; la.rows.n_rows = q.active; la.rows.row_lo = nullptr;
+            la.x = q.x_seed; la.ring = RING;
+            la.pre0 = make_pre(e->occ2sa[0], false, nullptr, false, 0, false);
+            const size_t kvl = (size_t)R * 256, kvm = (size_t)e->P * 256;
+            int n = 0;
+            for (int i = 0; i < 3; ++i) {
+                SubArgs &o = la.sub[n++];
+                o.w = e->occ2sa[i].cs_post; o.has_attn = 1; o.has_pos = 0; o.elist = 0;
+                o.kv = q.kv_occ + (size_t)i * ns * 256; o.cnt = q.one_cnt; o.start = nullptr; o.stride = 1; o.src = q.occ_src;
+                o.pre = make_pre(e->pt2sa[i], false, nullptr, false, 0, false);
+                SubArgs &p = la.sub[n++];
+                p.w = e->pt2sa[i].cs_post; p.has_attn = 1; p.has_pos = 1; p.elist = 1;
+                p.kv = fbuf(e, "kv_ms") + i * kvm; p.cnt = q.ps_cnt; p.start = nullptr; p.stride = SEED_MAP_MAX;
+                p.src = q.ps_src; p.rhat = fbuf(e, "rhat_ps");
+                p.pre = make_pre(e->a2sa[i], false, nullptr, false, 0, false);
+                SubArgs &g = la.sub[n++];
+                g.w = e->a2sa[i].cs_post; g.has_attn = 1; g.has_pos = 1; g.elist = 2;
+                g.kv = fbuf(e, "kv_sa") + i * kvl; g.cnt = q.as_cnt; g.start = nullptr; g.stride = cap;
+                g.src = q.as_src; g.rhat = fbuf(e, "rhat_as");
+                if (i < 2) g.pre = make_pre(e->occ2sa[i + 1], false, nullptr, false, 0, false);
+            }
+            la.n_sub = n;
+            const int saved = e->row_tile;
+            e->row_tile = 4;
+            int rc = launch_layer(e, la, KC_INSERT);
+            e->row_tile = saved;
+            RET(rc);
+        }
+        RET(launch_mlp_layer(e, e->h_seed_pos, q.x_seed, ns, q.pos_logits));
+        RET(launch_mlp_layer(e, e->h_ag_occ, q.x_seed, ns, q.ag_occ_logits));
+        RET(launch_mlp_layer(e, e->h_pt_occ, q.x_seed, ns, q.pt_occ_logits));
+        SeedDecideArgs da;
+        memset(&da, 0, sizeof(da));
+        da.s = s; da.q = q; da.h_state = e->h_seed_state; da.h_type = e->h_seed_type; da.h_shape = e->h_seed_shape;
+        {
+            ProfScope ps(e, KC_INSERT);
+            k_ins_clear_new_flag<<<1, 1, 0, st>>>(q);
+            k_seed_decide<<<ns, NT, 0, st>>>(da);
+            k_ins_flags<<<1, 1, 0, st>>>(q, ns);
+        }
+        CKL(); count_launch(e); count_launch(e); count_launch(e);
+        int flags[2] = {0, 0};
+        CK(cudaMemcpyAsync(flags, q.flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (flags[1]) {
+            // ---- heading stage of the appended rows (:2003-2074) ----
+            if (!heading_ready) {
+                CK(cudaMemcpyAsync(x_ha, x, (size_t)R * 128 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+                RET(enqueue_edgeless(e, nullptr, x_ha, false));
+                heading_ready = true;
+            }
+            // categorical embedding row of the new agent: type_a_emb[type] + shape_emb(shape)
+            MlpEmbArgs ma;
+            memset(&ma, 0, sizeof(ma));
+            ma.rows = scene_rows(e); ma.rows.row_lo = q.row_lo; ma.w = e->e_shape; ma.kin = 3; ma.k4 = 1;
+            ma.x = q.shape_rows; ma.x_ld = 3; ma.out = fbuf(e, "cat_tab"); ma.out_ld = 128;
+            RET(launch_mlp_embed(e, ma, KC_INSERT));
+            k_add_type_emb_rows<<<R, 128, 0, st>>>(s, q.row_lo, fbuf(e, "cat_tab"), e->type_emb);
+            CKL(); count_launch(e);
+            RET(enqueue_embed_rows(e, q.row_lo));       // feature of the new row with the dummy heading
+            {
+                ProfScope ps(e, KC_INSERT);
+                k_new_edges<<<ns, 64, 0, st>>>(s, q);
+            }
+            CKL(); count_launch(e);
+            FourierArgs hj[2];
+            memset(hj, 0, sizeof(hj));
+            hj[0].normalize = 1; hj[0].dim = 3; hj[0].n_slots = ns * NEW_MAP_MAX; hj[0].cnt = q.hp_cnt_s; hj[0].stride = NEW_MAP_MAX;
+            hj[0].raw = q.hp_raw; hj[0].w = e->f_m; hj[0].out = fbuf(e, "rhat_hp");
+            hj[1].normalize = 1; hj[1].dim = 3; hj[1].n_slots = ns * NEW_AGENT_MAX; hj[1].cnt = q.ha_cnt_s; hj[1].stride = NEW_AGENT_MAX;
+            hj[1].raw = q.ha_raw; hj[1].w = e->f_a; hj[1].out = fbuf(e, "rhat_ha");
+            RET(launch_fourier(e, hj, 2, KC_INSERT));
+            {   // the new rows through 3 x {pt2a, a2a} with their 10 m neighbourhoods
+                LayerArgs la;
+                memset(&la, 0, sizeof(la));
+                la.rows = scene_rows(e); la.rows.row_lo = q.row_lo; la.x = x; la.ring = RING; la.col_ptr = s.col;
+                la.pre0 = make_pre(e->m[0], false, nullptr, false, 0, false);
+                const size_t kvl = (size_t)R * 256, kvm = (size_t)e->P * 256;
+                int n = 0;
+                for (int i = 0; i < 3; ++i) {
+                    SubArgs &p = la.sub[n++];
+                    p.w = e->m[i].cs_post; p.has_attn = 1; p.has_pos = 1; p.elist = 0;
+                    p.kv = fbuf(e, "kv_m") + i * kvm; p.cnt = q.hp_cnt; p.start = q.hp_start; p.src = q.hp_src;
+                    p.rhat = fbuf(e, "rhat_hp");
+                    p.pre = make_pre(e->a[i], false, nullptr, false, 0, false);
+                    SubArgs &g = la.sub[n++];
+                    g.w = e->a[i].cs_post; g.has_attn = 1; g.has_pos = 1; g.elist = 1;
+                    g.kv = fbuf(e, "kv_ha") + i * kvl; g.cnt = q.ha_cnt; g.start = q.ha_start; g.src = q.ha_src;
+                    g.rhat = fbuf(e, "rhat_ha");
+                    if (i < 2) g.pre = make_pre(e->m[i + 1], false, nullptr, false, 0, false);
+                }
+                la.n_sub = n;
+                RET(launch_layer(e, la, KC_INSERT));
+            }
+            HeadFinalArgs ha;
+            memset(&ha, 0, sizeof(ha));
+            ha.s = s; ha.q = q; ha.x = x; ha.h_heading = e->h_seed_heading; ha.h_offset = e->h_seed_offset;
+            {
+                ProfScope ps(e, KC_INSERT);
+                k_head_finalize<<<ns, NT, 0, st>>>(ha);
+            }
+            CKL(); count_launch(e);
+            RET(enqueue_embed_rows(e, q.row_lo));       // final feature of the new row (:2086-2097)
+            // the new rows become sources of later passes: their edge-less K|V rows of both stacks
+            k_copy_new_rows<<<R, 128, 0, st>>>(s, q.row_lo, x, x_sa);
+            k_copy_new_rows<<<R, 128, 0, st>>>(s, q.row_lo, x, x_ha);
+            CKL(); count_launch(e); count_launch(e);
+            RET(enqueue_edgeless(e, q.row_lo, x_sa, true));
+            RET(enqueue_edgeless(e, q.row_lo, x_ha, false));
+        }
+        if (!flags[0]) break;
+    }
+    int err = 0;
+    CK(cudaMemcpyAsync(&err, q.err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (err == 2) return fail(INFGEN_ERR_CAPACITY, "insertion stage ran out of rows (row_capacity %d)", cap);
     return 0;
 }
 
@@ -580,6 +809,45 @@ static int build_tables(infgen_engine *e) {
     return 0;
 }
 
+// input feature of the seed query row: `_build_agent_feature(num_step, device, None, None, state_index=invalid)`
+// (agent_decoder.py:449-509 as called at :1817-1821) - no-token embedding, all-invalid motion vector, seed type / 0.1
+// shape, invalid state, the CENTRE cell's grid embedding; the same for every scene, pass and column
+__global__ void k_seed_raw(float *raw) {
+    raw[0] = norm2(-2.f, -2.f);
+    raw[1] = angle_between(cosf(0.f), sinf(0.f), -2.f, -2.f);
+}
+static int build_seed_feature(infgen_engine *e) {
+    const int V = e->cfg.token_size, G = e->cfg.grid_size;
+    cudaStream_t st = e->stream;
+    float *tmp = nullptr;                                // [shape row 4 | cat 128 | raw 2(+2) | xa 128 | fused in 512]
+    CK(cudaMalloc(&tmp, 1024 * sizeof(float)));
+    CK(cudaMalloc(&e->seed_feat, 128 * sizeof(float)));
+    float *shape_row = tmp, *cat = tmp + 4, *raw = tmp + 132, *xa = tmp + 136, *fin = tmp + 264;
+    k_fill_shape_rows<<<1, 32, 0, st>>>(shape_row, nullptr, 0);          // one row of 0.1
+    MlpEmbArgs ma;
+    memset(&ma, 0, sizeof(ma));
+    ma.rows = flat_rows(1); ma.w = e->e_shape; ma.kin = 3; ma.k4 = 1; ma.x = shape_row; ma.x_ld = 3; ma.out = cat; ma.out_ld = 128;
+    RET(launch_mlp_embed(e, ma));
+    k_add_type_emb<<<1, 128, 0, st>>>(cat, e->type_emb, nullptr, 0, 3);  // + type_a_emb['seed']
+    k_seed_raw<<<1, 1, 0, st>>>(raw);
+    FourierArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.n_slots = 1; fa.dim = 2; fa.raw = raw; fa.w = e->f_x; fa.cat_tab = cat; fa.out = xa; fa.normalize = 0;
+    RET(launch_fourier(e, &fa, 1));
+    CK(cudaMemcpyAsync(fin, e->tok_tab + (size_t)(V + 1) * 128, 128 * sizeof(float), cudaMemcpyDeviceToDevice, st));   // no-token
+    CK(cudaMemcpyAsync(fin + 128, xa, 128 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(fin + 256, e->state_emb, 128 * sizeof(float), cudaMemcpyDeviceToDevice, st));                   // invalid = 0
+    CK(cudaMemcpyAsync(fin + 384, e->grid_tab + (size_t)(G / 2) * 128, 128 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    memset(&ma, 0, sizeof(ma));
+    ma.rows = flat_rows(1); ma.w = e->e_fusion; ma.kin = 512; ma.k4 = 128; ma.x = fin; ma.x_ld = 512; ma.out = e->seed_feat;
+    ma.out_ld = 128;
+    RET(launch_mlp_embed(e, ma));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaFree(tmp));
+    CKL();
+    return 0;
+}
+
 int32_t infgen_create(const infgen_config *cfg, const float *weights, int64_t n_floats, const float *grid_cells,
                       const float *vocab, infgen_engine **out) {
     build_layout();
@@ -588,6 +856,10 @@ int32_t infgen_create(const infgen_config *cfg, const float *weights, int64_t n_
         return fail(INFGEN_ERR_INVALID_ARG, "ABI version %d != library %d", cfg->abi_version, INFGEN_ABI_VERSION);
     if (n_floats != g_total) return fail(INFGEN_ERR_INVALID_ARG, "weight blob has %lld floats, expected %lld",
                                           (long long)n_floats, (long long)g_total);
+    if (!cfg->disable_insertion && (cfg->grid_size != GRID_SIZE || cfg->insert_beam_size < 1 ||
+                                    cfg->insert_beam_size > INSERT_LIMIT || cfg->angle_interval <= 0.f))
+        return fail(INFGEN_ERR_INVALID_ARG, "unsupported insertion configuration (grid=%d insert_beam=%d)",
+                    cfg->grid_size, cfg->insert_beam_size);
     if (cfg->num_layers != 6 || cfg->token_size != TOKEN_SIZE || cfg->window + 1 > RING || cfg->window > 32 ||
         cfg->hist_cols < 1 || cfg->motion_beam_size < 1 || cfg->motion_beam_size > KTOP || cfg->max_pl2a_neighbors > 32)
         return fail(INFGEN_ERR_INVALID_ARG, "unsupported configuration (layers=%d tokens=%d window=%d beam=%d)",
@@ -626,6 +898,21 @@ int32_t infgen_create(const infgen_config *cfg, const float *weights, int64_t n_
     e->h_tok = make_head(e, "token_predict_head", 128, cfg->token_size);
     e->h_state = make_head(e, "state_predict_head", 128, 3);
     e->type_emb = W(e, "type_a_emb"); e->state_emb = W(e, "state_a_emb");
+    for (int i = 0; i < 3; ++i) {
+        e->occ2sa[i] = make_attn(e, "occ2sa_attn_layers." + std::to_string(i), false);
+        e->pt2sa[i] = make_attn(e, "pt2sa_attn_layers." + std::to_string(i), true);
+        e->a2sa[i] = make_attn(e, "a2sa_attn_layers." + std::to_string(i), true);
+    }
+    e->f_ps = make_fourier(e, "r_pt2sa_emb", 3); e->f_as = make_fourier(e, "r_a2sa_emb", 3);
+    e->h_seed_state = make_head(e, "seed_state_predict_head", 128, 2);
+    e->h_seed_type = make_head(e, "seed_type_predict_head", 128, 3);
+    e->h_seed_shape = make_head(e, "seed_shape_predict_head", 128, 3);
+    e->h_seed_pos = make_head(e, "seed_pos_rel_token_predict_head", 128, cfg->grid_size);
+    e->h_seed_heading = make_head(e, "seed_heading_rel_token_predict_head", 128, ANGLE_SIZE);
+    e->h_seed_offset = make_head(e, "seed_offset_xy_predict_head", 128, 2);
+    e->h_occ_embed = make_head(e, "seed_agent_occ_embed", cfg->grid_size, 128);
+    e->h_ag_occ = make_head(e, "grid_agent_occ_head", 128, cfg->grid_size);
+    e->h_pt_occ = make_head(e, "grid_pt_occ_head", 128, cfg->grid_size);
     // kernels that need more than 48 KB of dynamic shared memory
     CK(cudaFuncSetAttribute(k_layer<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LayerSmem<4>::BYTES));
     CK(cudaFuncSetAttribute(k_layer<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LayerSmem<8>::BYTES));
@@ -635,6 +922,7 @@ int32_t infgen_create(const infgen_config *cfg, const float *weights, int64_t n_
     CK(cudaFuncSetAttribute(k_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEADS_SMEM));
     CK(cudaFuncSetAttribute(k_mlp_layer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_LAYER_SMEM));
     RET(build_tables(e));
+    if (!cfg->disable_insertion) RET(build_seed_feature(e));
     CK(cudaStreamSynchronize(e->stream));
     *out = e;
     return 0;
@@ -649,7 +937,7 @@ int32_t infgen_destroy(infgen_engine *e) {
     for (auto &kv : e->bufs)
         if (kv.second.p) cudaFree(kv.second.p);
     cudaFree(e->blob); cudaFree(e->cs_blob); cudaFree(e->grid_cells); cudaFree(e->vocab); cudaFree(e->tok_tab); cudaFree(e->grid_tab);
-    cudaFree(e->d_err);
+    cudaFree(e->d_err); cudaFree(e->seed_feat);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
     return 0;
@@ -797,6 +1085,59 @@ int32_t infgen_load_scenes(infgen_engine *e, const infgen_scene_batch *b, int32_
         RET(ensure_t(e, "trace_state_logits", (size_t)S * R * 3, &tmp));
         RET(ensure_t(e, "trace_layer_out", (size_t)S * 6 * R * 128, &tmp));
     }
+    // ---- insertion stage ----
+    e->ins_ready = false;
+    s.ins_col = nullptr;
+    if (!e->cfg.disable_insertion) {
+        InsState &q = e->ins;
+        memset(&q, 0, sizeof(q));
+        const int G = e->cfg.grid_size;
+        q.beam = e->cfg.insert_beam_size; q.force_enter = e->cfg.debug_force_enter; q.seed = e->cfg.seed;
+        q.r_seed2 = e->cfg.pl2seed_radius * e->cfg.pl2seed_radius;
+        q.r_new_a2 = e->cfg.a2sa_radius * e->cfg.a2sa_radius; q.r_new_m2 = e->cfg.pl2sa_radius * e->cfg.pl2sa_radius;
+        q.angle_interval = e->cfg.angle_interval;
+        RET(ensure_t(e, "ins_active", ns, &q.active)); RET(ensure_t(e, "ins_n_new", ns, &q.n_new));
+        RET(ensure_t(e, "ins_pass", ns, &q.pass)); RET(ensure_t(e, "ins_new_row", ns, &q.new_row));
+        RET(ensure_t(e, "ins_row_lo", ns, &q.row_lo)); RET(ensure_t(e, "ins_flags", 4, &q.flags));
+        RET(ensure_t(e, "ps_cnt", ns, &q.ps_cnt)); RET(ensure_t(e, "ps_src", (size_t)ns * SEED_MAP_MAX, &q.ps_src));
+        RET(ensure_t(e, "ps_raw", (size_t)ns * SEED_MAP_MAX * 3, &q.ps_raw));
+        RET(ensure_t(e, "as_cnt", ns, &q.as_cnt)); RET(ensure_t(e, "as_src", (size_t)ns * cap, &q.as_src));
+        RET(ensure_t(e, "as_raw", (size_t)ns * cap * 3, &q.as_raw));
+        RET(ensure_t(e, "one_cnt", ns, &q.one_cnt)); RET(ensure_t(e, "occ_src", ns, &q.occ_src));
+        RET(ensure_t(e, "hp_cnt", R, &q.hp_cnt)); RET(ensure_t(e, "hp_start", R, &q.hp_start));
+        RET(ensure_t(e, "hp_src", (size_t)ns * NEW_MAP_MAX, &q.hp_src)); RET(ensure_t(e, "hp_raw", (size_t)ns * NEW_MAP_MAX * 3, &q.hp_raw));
+        RET(ensure_t(e, "ha_cnt", R, &q.ha_cnt)); RET(ensure_t(e, "ha_start", R, &q.ha_start));
+        RET(ensure_t(e, "ha_src", (size_t)ns * NEW_AGENT_MAX, &q.ha_src)); RET(ensure_t(e, "ha_raw", (size_t)ns * NEW_AGENT_MAX * 3, &q.ha_raw));
+        RET(ensure_t(e, "hp_cnt_s", ns, &q.hp_cnt_s)); RET(ensure_t(e, "ha_cnt_s", ns, &q.ha_cnt_s));
+        RET(ensure_t(e, "occ", (size_t)ns * G, &q.occ)); RET(ensure_t(e, "occ_emb", (size_t)ns * 128, &q.occ_emb));
+        RET(ensure_t(e, "kv_occ", (size_t)3 * ns * 256, &q.kv_occ)); RET(ensure_t(e, "x_seed", (size_t)ns * 128, &q.x_seed));
+        RET(ensure_t(e, "pos_logits", (size_t)ns * G, &q.pos_logits));
+        RET(ensure_t(e, "ag_occ_logits", (size_t)ns * G, &q.ag_occ_logits));
+        RET(ensure_t(e, "pt_occ_logits", (size_t)ns * G, &q.pt_occ_logits));
+        RET(ensure_t(e, "ins_col", R, &q.ins_col)); RET(ensure_t(e, "pred_type", R, &q.pred_type));
+        RET(ensure_t(e, "pred_shape", (size_t)R * 3, &q.pred_shape));
+        const size_t nso = (size_t)ns * SEED_SLOTS * std::max(S, 1);
+        RET(ensure_t(e, "o_state_prob", nso, &q.o_state_prob)); RET(ensure_t(e, "o_pos_prob", nso * G, &q.o_pos_prob));
+        RET(ensure_t(e, "o_ag_occ", nso * G, &q.o_ag_occ)); RET(ensure_t(e, "o_pt_occ", nso * G, &q.o_pt_occ));
+        RET(ensure_t(e, "o_occ_gt", nso * G, &q.o_occ_gt));
+        RET(ensure_t(e, "x_sa", (size_t)R * 128, &tmp)); RET(ensure_t(e, "x_ha", (size_t)R * 128, &tmp));
+        RET(ensure_t(e, "kv_sa", (size_t)3 * R * 256, &tmp)); RET(ensure_t(e, "kv_ha", (size_t)3 * R * 256, &tmp));
+        RET(ensure_t(e, "kv_ms", (size_t)3 * std::max(P, 1) * 256, &tmp));
+        RET(ensure_t(e, "rhat_ps", (size_t)ns * SEED_MAP_MAX * 128, &tmp)); RET(ensure_t(e, "rhat_as", (size_t)ns * cap * 128, &tmp));
+        RET(ensure_t(e, "rhat_hp", (size_t)ns * NEW_MAP_MAX * 128, &tmp)); RET(ensure_t(e, "rhat_ha", (size_t)ns * NEW_AGENT_MAX * 128, &tmp));
+        q.shape_rows = fbuf(e, "shape_rows");
+        q.seed_feat = e->seed_feat; q.err = e->d_err;
+        s.ins_col = q.ins_col;
+        CK(cudaMemsetAsync(q.ins_col, 0xff, (size_t)R * sizeof(int), e->stream));
+        CK(cudaMemsetAsync(q.pred_type, 0, (size_t)R * sizeof(int), e->stream));
+        CK(cudaMemsetAsync(q.pred_shape, 0, (size_t)R * 3 * sizeof(float), e->stream));
+        CK(cudaMemsetAsync(q.o_state_prob, 0, nso * sizeof(float), e->stream));
+        CK(cudaMemsetAsync(q.o_pos_prob, 0, nso * G * sizeof(float), e->stream));
+        CK(cudaMemsetAsync(q.o_ag_occ, 0, nso * G * sizeof(float), e->stream));
+        CK(cudaMemsetAsync(q.o_pt_occ, 0, nso * G * sizeof(float), e->stream));
+        CK(cudaMemsetAsync(q.o_occ_gt, 0, nso * G * sizeof(float), e->stream));
+        e->ins_ready = true;
+    }
     if (memcmp(&old, &s, sizeof(s)) != 0) drop_graph(e);
     // ---- expand history into the state arrays, zero counters ----
     SetupArgs sa;
@@ -825,6 +1166,13 @@ int32_t infgen_load_scenes(infgen_engine *e, const infgen_scene_batch *b, int32_
         for (int i = 0; i < 6; ++i) { ka.w[i] = e->m[i]; ka.out[i] = fbuf(e, "kv_m") + (size_t)i * P * 256; }
         k_kv_project<16><<<dim3((P + 15) / 16, 6), NT, 0, st>>>(ka);
         CKL(); count_launch(e);
+        if (e->ins_ready) {                              // ... and of the three pt2sa layers of the insertion stage
+            memset(&ka, 0, sizeof(ka));
+            ka.n = P; ka.x = d_x_pt;
+            for (int i = 0; i < 3; ++i) { ka.w[i] = e->pt2sa[i]; ka.out[i] = fbuf(e, "kv_ms") + (size_t)i * P * 256; }
+            k_kv_project<16><<<dim3((P + 15) / 16, 3), NT, 0, st>>>(ka);
+            CKL(); count_launch(e);
+        }
     }
     e->loaded = true;
     return 0;
@@ -872,6 +1220,7 @@ int32_t infgen_step(infgen_engine *e, int32_t n_iters) {
         return fail(INFGEN_ERR_INVALID_ARG, "%d iterations requested, %d of %d already done", n_iters, e->iters_done, e->S);
     const bool use_graph = e->cfg.use_cuda_graph && !e->cfg.trace && !e->profile;
     for (int i = 0; i < n_iters; ++i) {
+        if (e->ins_ready && e->iters_done > 0 && !e->forcing_no_insert) RET(run_insertion(e));
         if (use_graph) {
             if (!e->graph_exec) {
                 CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
@@ -924,6 +1273,19 @@ int32_t infgen_read(infgen_engine *e, const infgen_outputs *o, int32_t loc) {
     if (o->next_state) CK(cudaMemcpyAsync(o->next_state, s.next_state, R * T * sizeof(int), k, st));
     if (o->hist_traj) CK(cudaMemcpyAsync(o->hist_traj, fbuf(e, "hist_traj"), R * HC * 5 * 2 * sizeof(float), k, st));
     if (o->hist_head) CK(cudaMemcpyAsync(o->hist_head, fbuf(e, "hist_head"), R * HC * 5 * sizeof(float), k, st));
+    const size_t ns = e->n_scenes;
+    if (o->n_rows_final) CK(cudaMemcpyAsync(o->n_rows_final, s.n_rows, ns * sizeof(int), k, st));
+    if (e->ins_ready) {
+        const InsState &q = e->ins;
+        const size_t nso = ns * SEED_SLOTS * (size_t)std::max(e->S, 1), G = e->cfg.grid_size;
+        if (o->pred_type) CK(cudaMemcpyAsync(o->pred_type, q.pred_type, R * sizeof(int), k, st));
+        if (o->pred_shape) CK(cudaMemcpyAsync(o->pred_shape, q.pred_shape, R * 3 * sizeof(float), k, st));
+        if (o->state_prob_seed) CK(cudaMemcpyAsync(o->state_prob_seed, q.o_state_prob, nso * sizeof(float), k, st));
+        if (o->pos_prob_seed) CK(cudaMemcpyAsync(o->pos_prob_seed, q.o_pos_prob, nso * G * sizeof(float), k, st));
+        if (o->agent_occ_seed) CK(cudaMemcpyAsync(o->agent_occ_seed, q.o_ag_occ, nso * G * sizeof(float), k, st));
+        if (o->pt_occ_seed) CK(cudaMemcpyAsync(o->pt_occ_seed, q.o_pt_occ, nso * G * sizeof(float), k, st));
+        if (o->occ_gt_seed) CK(cudaMemcpyAsync(o->occ_gt_seed, q.o_occ_gt, nso * G * sizeof(float), k, st));
+    }
     if (loc == INFGEN_HOST) {
         CK(cudaStreamSynchronize(st));
         int err = 0;

@@ -1,0 +1,530 @@
+// Insertion stage of `InfGenAgentDecoder.inference` (agent_decoder.py:1744-2114): the kernels that are not
+// AttentionLayer / FourierEmbedding / MLPLayer calls (those reuse k_layer / k_fourier / k_mlp_layer).
+//
+// Per decode iteration t > 0 and per pass p (up to insert_limit = 10, :1737-1738) a "seed" query row - a copy of the ego
+// row at column cur (`_pad_feat`, :511-526) - attends to an occupancy node, to the map tokens within pl2seed_radius and
+// to the agents within pl2seed_radius through 3 x {occ2sa, pt2sa, a2sa} layers (:1861-1871); heads on the result decide
+// whether / where / what to insert (:1884-1911).  A new agent then gets its heading and a position offset from
+// 3 x {pt2a, a2a} layers over its own 10 m neighbourhood (:2037-2074).
+//
+// KV-cache formulation (checked by parity, like the motion stage): every agent row runs through the seed stack and the
+// heading stack WITHOUT edges in the reference (only the query row has incoming edges), so their K/V rows per layer
+// depend only on the column's input feature and are computed once per iteration (and once more for each inserted row).
+#pragma once
+#include "common.cuh"
+#include "ops.cuh"
+#include "decode.cuh"
+
+namespace infgen {
+
+constexpr int SEED_MAP_MAX = 2048;     // max_num_neighbors of the pl2seed radius query (:1847)
+constexpr int SEED_AGENT_MAX = 300;    // (:1838)
+constexpr int NEW_MAP_MAX = 128;       // (:2035)
+constexpr int NEW_AGENT_MAX = 24;      // (:2029)
+constexpr int INSERT_LIMIT = 10;       // (:1738)
+constexpr int SEED_SLOTS = INSERT_LIMIT + 1;
+
+struct InsState {
+    int beam;                          // insert_beam_size
+    int force_enter;                   // the reference's DEBUG=1 switch (:1888-1889)
+    unsigned seed;
+    float r_seed2, r_new_a2, r_new_m2; // squared radii: pl2seed (75 m), a2sa (10 m), pl2sa (10 m)
+    float angle_interval;
+    // per scene
+    int *active;                       // still inserting in this iteration
+    int *n_new;                        // agents inserted in this iteration
+    int *pass;                         // passes done in this iteration
+    int *new_row;                      // row (within the scene) appended by the last pass, -1 if none
+    int *row_lo;                       // first row the "new rows only" launches process (= new_row or n_rows)
+    int *flags;                        // [2]: any scene still active, any scene appended a row (host loop control)
+    // seed query edges: one destination (the seed row) per scene
+    int *ps_cnt, *ps_src; float *ps_raw;   // map -> seed   [ns], [ns*SEED_MAP_MAX], [..][3]
+    int *as_cnt, *as_src; float *as_raw;   // agent -> seed [ns], [ns*cap], [..][3]
+    int *one_cnt, *occ_src;                // occupancy node -> seed: always one edge, source = scene
+    // new-agent edges: destination = the appended row; indexed by global row
+    int *hp_cnt, *hp_start, *hp_src; float *hp_raw;   // map -> new agent   [R], [R], [ns*NEW_MAP_MAX], [..][3]
+    int *ha_cnt, *ha_start, *ha_src; float *ha_raw;   // agent -> new agent [R], [R], [ns*NEW_AGENT_MAX], [..][3]
+    int *hp_cnt_s, *ha_cnt_s;                          // [ns] the same counts per scene (slot validity of the embeddings)
+    // occupancy
+    float *occ;                        // [ns][G] 0/1 occupancy of the ego-centric grid at column cur
+    float *occ_emb;                    // [ns][128] seed_agent_occ_embed(occ)
+    float *kv_occ;                     // [3][ns][256] K|V of the occupancy node for the three occ2sa layers
+    // query row
+    float *x_seed;                     // [ns][128]
+    const float *seed_feat;            // [128] `_build_agent_feature(..., state_index=invalid)` - a constant
+    // head outputs of the query row
+    float *pos_logits, *ag_occ_logits, *pt_occ_logits;   // [ns][G]
+    // per row
+    int *ins_col;                      // [R] column at which the row was inserted, -1 for the scene's own agents
+    float *shape_rows;                 // [R+1][3] shape fed to shape_emb (row R = 0.1)
+    int *pred_type;                    // [R]
+    float *pred_shape;                 // [R][3]
+    // outputs [ns][SEED_SLOTS][S] (+[G])
+    float *o_state_prob, *o_pos_prob, *o_ag_occ, *o_pt_occ, *o_occ_gt;
+    int *err;
+};
+
+// y[n] = b[n] + sum_k x[k] W[k][n], n < N, one row; x: shared [4*K4]; W packed [K4][ldn][4]
+__device__ __forceinline__ void gemv_row(const float *xs, const float *__restrict__ wp, int ldn, int K4,
+                                         const float *__restrict__ bias, int N, float *out) {
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        float acc = 0.f;
+        for (int k4 = 0; k4 < K4; ++k4) {
+            const float4 w = ldg4(wp + ((size_t)k4 * ldn + n) * 4);
+            const float4 x = ld4(xs + 4 * k4);
+            acc = fmaf(x.x, w.x, acc); acc = fmaf(x.y, w.y, acc); acc = fmaf(x.z, w.z, acc); acc = fmaf(x.w, w.w, acc);
+        }
+        out[n] = acc + (bias ? __ldg(bias + n) : 0.f);
+    }
+}
+// in-place LayerNorm (+ReLU) of one 128-vector in shared memory by warp 0
+__device__ __forceinline__ void ln_row(float *s, const float *g, const float *b, bool relu) {
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        float4 v = ln128(ld4(s + 4 * lane), g, b, lane);
+        if (relu) v = relu4(v);
+        st4(s + 4 * lane, v);
+    }
+}
+// MLPLayer (layers.py:206-215) on one row held in shared memory: out[n_out] (shared or global)
+__device__ __forceinline__ void mlp_head_row(const float *sx, const MlpHeadW &w, float *sh, float *out) {
+    gemv_row(sx, w.w0, 128, 32, w.b0, 128, sh);
+    __syncthreads();
+    ln_row(sh, w.ln_g, w.ln_b, true);
+    __syncthreads();
+    gemv_row(sh, w.w3, w.n_pad, 32, w.b3, w.n_out, out);
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// start of an iteration's insertion stage: reset the per-scene flags; map -> seed edges (the seed sits on the ego's
+// pose at column cur for every pass of the iteration).  One CTA per scene.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) k_ins_begin(const DecState s, const InsState q) {
+    const int b = blockIdx.x, col = *s.col, T = s.T;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        q.active[b] = 1; q.n_new[b] = 0; q.pass[b] = 0; q.new_row[b] = -1; q.row_lo[b] = s.n_rows[b];
+        q.one_cnt[b] = 1; q.occ_src[b] = b;
+        if (b == 0) { q.flags[0] = 1; q.flags[1] = 0; }
+    }
+    if (warp != 0) return;
+    const int re = b * s.cap + s.ego_row[b];
+    const float px = s.pos[((size_t)re * T + col) * 2], py = s.pos[((size_t)re * T + col) * 2 + 1];
+    const float hd = s.head[(size_t)re * T + col];
+    const float hx = cosf(hd), hy = sinf(hd);
+    const int pt0 = s.pt_ptr[b], pt1 = s.pt_ptr[b + 1];
+    int cnt = 0;
+    for (int p0 = pt0; p0 < pt1 && cnt < SEED_MAP_MAX; p0 += 32) {
+        const int p = p0 + lane;
+        float dx = 0.f, dy = 0.f;
+        bool ok = false;
+        if (p < pt1) {
+            dx = __fsub_rn(s.pt_pos[(size_t)p * 2], px);
+            dy = __fsub_rn(s.pt_pos[(size_t)p * 2 + 1], py);
+            ok = dist2(dx, dy) < q.r_seed2;
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, ok);
+        const int rank = cnt + __popc(mask & lanemask_lt());
+        if (ok && rank < SEED_MAP_MAX) {
+            const int slot = b * SEED_MAP_MAX + rank;
+            q.ps_src[slot] = p;
+            q.ps_raw[(size_t)slot * 3 + 0] = norm2(dx, dy);
+            q.ps_raw[(size_t)slot * 3 + 1] = angle_between(hx, hy, dx, dy);
+            q.ps_raw[(size_t)slot * 3 + 2] = wrap_angle(__fsub_rn(s.pt_ori[p], hd));
+        }
+        cnt = min(SEED_MAP_MAX, cnt + __popc(mask));
+    }
+    if (lane == 0) q.ps_cnt[b] = cnt;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// per pass: occupancy of the grid at column cur -> seed_agent_occ_embed -> K|V of the three occ2sa layers (:1850-1859);
+// agent -> seed edges (:1833-1841); the query row's input feature.  One CTA per scene.
+// ---------------------------------------------------------------------------------------------------------------
+struct SeedPrepArgs {
+    DecState s;
+    InsState q;
+    MlpHeadW occ_embed;        // seed_agent_occ_embed: G -> 128 -> 128
+    AttnW occ2sa[3];
+};
+__global__ void __launch_bounds__(NT) k_seed_prepare(const SeedPrepArgs a) {
+    __shared__ __align__(16) float sh[128];
+    __shared__ __align__(16) float se[128];
+    __shared__ __align__(16) float sn[128];
+    const DecState &s = a.s;
+    const InsState &q = a.q;
+    const int b = blockIdx.x, col = *s.col, T = s.T, G = s.G;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (!q.active[b]) return;
+    const int n = s.n_rows[b], r0 = b * s.cap;
+    if (tid == 0) { q.new_row[b] = -1; q.row_lo[b] = n; }
+    // ---- occupancy (:1851-1853) ----
+    float *occ = q.occ + (size_t)b * G;
+    for (int g = tid; g < G; g += NT) occ[g] = 0.f;
+    __syncthreads();
+    for (int i = tid; i < n; i += NT) {
+        const int g = s.grid[(size_t)(r0 + i) * T + col];
+        if (g >= 0) occ[g] = 1.f;
+    }
+    __syncthreads();
+    // ---- first Linear of seed_agent_occ_embed on a 0/1 vector: bias + the columns of the occupied cells ----
+    if (tid < 128) {
+        float acc = 0.f;
+        for (int g = 0; g < G; ++g)
+            if (occ[g] != 0.f) acc += __ldg(a.occ_embed.w0 + ((size_t)(g >> 2) * 128 + tid) * 4 + (g & 3));
+        sh[tid] = acc + __ldg(a.occ_embed.b0 + tid);
+    }
+    __syncthreads();
+    ln_row(sh, a.occ_embed.ln_g, a.occ_embed.ln_b, true);
+    __syncthreads();
+    gemv_row(sh, a.occ_embed.w3, a.occ_embed.n_pad, 32, a.occ_embed.b3, 128, se);
+    __syncthreads();
+    if (tid < 128) q.occ_emb[(size_t)b * 128 + tid] = se[tid];
+    for (int i = 0; i < 3; ++i) {                       // K|V of the occupancy node (layers.py:65-71, 107-108)
+        if (tid < 32) st4(sn + 4 * lane, ln128(ld4(se + 4 * lane), a.occ2sa[i].ln_src_g, a.occ2sa[i].ln_src_b, lane));
+        __syncthreads();
+        gemv_row(sn, a.occ2sa[i].w_kv, 256, 32, a.occ2sa[i].b_kv, 256,
+                 q.kv_occ + ((size_t)i * gridDim.x + b) * 256);
+        __syncthreads();
+    }
+    // ---- query row feature ----
+    if (tid < 128) q.x_seed[(size_t)b * 128 + tid] = q.seed_feat[tid];
+    // ---- agent -> seed edges: rows within the radius of the ego pose (first SEED_AGENT_MAX by index, the query row
+    //      itself being the last index), kept if they interact at column cur ----
+    if (warp != 0) return;
+    const int re = r0 + s.ego_row[b];
+    const float px = s.pos[((size_t)re * T + col) * 2], py = s.pos[((size_t)re * T + col) * 2 + 1];
+    const float hd = s.head[(size_t)re * T + col];
+    const float hx = cosf(hd), hy = sinf(hd);
+    int cnt = 0, seen = 0;
+    for (int j0 = 0; j0 < n; j0 += 32) {
+        const int j = j0 + lane, rj = r0 + j;
+        float dx = 0.f, dy = 0.f;
+        bool within = false;
+        if (j < n) {
+            dx = __fsub_rn(s.pos[((size_t)rj * T + col) * 2], px);
+            dy = __fsub_rn(s.pos[((size_t)rj * T + col) * 2 + 1], py);
+            within = dist2(dx, dy) < q.r_seed2;
+        }
+        const unsigned wm = __ballot_sync(0xffffffffu, within);
+        const bool in_first = within && (seen + __popc(wm & lanemask_lt())) < SEED_AGENT_MAX;
+        const bool ok = in_first && s.interact[(size_t)rj * T + col] != 0;
+        const unsigned mask = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+            const int slot = b * s.cap + cnt + __popc(mask & lanemask_lt());
+            q.as_src[slot] = rj;
+            q.as_raw[(size_t)slot * 3 + 0] = norm2(dx, dy);
+            q.as_raw[(size_t)slot * 3 + 1] = angle_between(hx, hy, dx, dy);
+            q.as_raw[(size_t)slot * 3 + 2] = wrap_angle(__fsub_rn(s.head[(size_t)rj * T + col], hd));
+        }
+        cnt += __popc(mask);
+        seen += __popc(wm);
+    }
+    if (lane == 0) q.as_cnt[b] = cnt;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// per pass: small heads of the query row, the decision (:1884-1911) and, on 'enter', the new row (:1913-1995).
+// The three grid-sized heads (position, agent / map occupancy) were computed by k_mlp_layer.  One CTA per scene.
+// ---------------------------------------------------------------------------------------------------------------
+struct SeedDecideArgs {
+    DecState s;
+    InsState q;
+    MlpHeadW h_state, h_type, h_shape;
+};
+__global__ void __launch_bounds__(NT) k_seed_decide(const SeedDecideArgs a) {
+    __shared__ __align__(16) float sx[128];
+    __shared__ __align__(16) float sh[128];
+    __shared__ float s_small[8];                        // state[2] type[3] shape[3]
+    __shared__ float s_red[NT];
+    __shared__ int s_redi[NT];
+    __shared__ float s_topv[INSERT_LIMIT];
+    __shared__ int s_topi[INSERT_LIMIT];
+    const DecState &s = a.s;
+    const InsState &q = a.q;
+    const int b = blockIdx.x, col = *s.col, t = *s.iter, T = s.T, G = s.G, S = s.S;
+    const int tid = threadIdx.x;
+    if (!q.active[b]) return;
+    if (tid < 128) sx[tid] = q.x_seed[(size_t)b * 128 + tid];
+    __syncthreads();
+    mlp_head_row(sx, a.h_state, sh, s_small);
+    mlp_head_row(sx, a.h_type, sh, s_small + 2);
+    mlp_head_row(sx, a.h_shape, sh, s_small + 5);
+    // ---- position: softmax over the grid, top-k, draw (:1896-1902) ----
+    const float *lg = q.pos_logits + (size_t)b * G;
+    float mxv = -INFINITY;
+    for (int g = tid; g < G; g += NT) mxv = fmaxf(mxv, lg[g]);
+    s_red[tid] = mxv;
+    __syncthreads();
+    for (int o = NT / 2; o > 0; o >>= 1) { if (tid < o) s_red[tid] = fmaxf(s_red[tid], s_red[tid + o]); __syncthreads(); }
+    const float gmax = s_red[0];
+    __syncthreads();
+    float sum = 0.f;
+    for (int g = tid; g < G; g += NT) sum += expf(lg[g] - gmax);
+    s_red[tid] = sum;
+    __syncthreads();
+    for (int o = NT / 2; o > 0; o >>= 1) { if (tid < o) s_red[tid] += s_red[tid + o]; __syncthreads(); }
+    const float den = s_red[0];
+    __syncthreads();
+    for (int k = 0; k < q.beam; ++k) {                  // k-th largest logit, ties to the lower index
+        float bv = -INFINITY; int bi = 0x7fffffff;
+        for (int g = tid; g < G; g += NT) {
+            bool taken = false;
+            for (int j = 0; j < k; ++j) taken |= s_topi[j] == g;
+            const float v = lg[g];
+            if (!taken && (v > bv || (v == bv && g < bi))) { bv = v; bi = g; }
+        }
+        s_red[tid] = bv; s_redi[tid] = bi;
+        __syncthreads();
+        for (int o = NT / 2; o > 0; o >>= 1) {
+            if (tid < o) {
+                const float ov = s_red[tid + o]; const int oi = s_redi[tid + o];
+                if (ov > s_red[tid] || (ov == s_red[tid] && oi < s_redi[tid])) { s_red[tid] = ov; s_redi[tid] = oi; }
+            }
+            __syncthreads();
+        }
+        if (tid == 0) { s_topv[k] = s_red[0]; s_topi[k] = s_redi[0]; }
+        __syncthreads();
+    }
+    if (tid != 0) {
+        // the remaining threads only help with the (grid-sized) output rows below
+    }
+    __shared__ int s_cell, s_append, s_row;
+    if (tid == 0) {
+        int cell = s_topi[0];
+        if (q.beam > 1) {
+            float p[INSERT_LIMIT], total = 0.f;
+            for (int k = 0; k < q.beam; ++k) { p[k] = expf(s_topv[k] - gmax) / den; total += p[k]; }
+            const float thr = uniform01(q.seed ^ 0x5EEDu, (unsigned)s.scene_id[b], (unsigned)q.pass[b], (unsigned)t) * total;
+            float c = 0.f; int pick = q.beam - 1;
+            for (int k = 0; k < q.beam; ++k) { c += p[k]; if (thr < c) { pick = k; break; } }
+            cell = s_topi[pick];
+        }
+        s_cell = cell;
+        int append = 0;
+        const int pass = q.pass[b] + 1;
+        q.pass[b] = pass;
+        const float *occ = q.occ + (size_t)b * G;
+        // state (:1884-1889): argmax of the 2-way softmax, index 1 = 'enter'
+        int enter = s_small[1] > s_small[0] ? 1 : 0;
+        if (q.force_enter) enter = 1;
+        if (occ[cell] != 0.f) {                         // overlap filter (:1906-1909): retry
+            // with a deterministic choice (beam 1) every retry repeats this pass: the reference spins until the limit
+            if (q.beam == 1 || pass >= INSERT_LIMIT) q.active[b] = 0;
+        } else if (!enter || q.n_new[b] + 1 > INSERT_LIMIT) {
+            q.active[b] = 0;
+        } else if (s.n_rows[b] >= s.cap) {
+            *q.err = 2;                                  // row capacity exhausted
+            q.active[b] = 0;
+        } else {
+            append = 1;
+            if (pass >= INSERT_LIMIT) q.active[b] = 0;
+        }
+        s_append = append;
+        s_row = s.n_rows[b];
+    }
+    __syncthreads();
+    if (!s_append) return;
+    // ---- 1.5 append the new row (:1913-1995) ----
+    const int i_new = s_row, r = b * s.cap + i_new, cell = s_cell;
+    const int re = b * s.cap + s.ego_row[b];
+    const float ex = s.pos[((size_t)re * T + col) * 2], ey = s.pos[((size_t)re * T + col) * 2 + 1];
+    const float eh = s.head[(size_t)re * T + col];
+    for (int c = tid; c < T; c += NT) {
+        const size_t o = (size_t)r * T + c;
+        s.pos[o * 2] = 0.f; s.pos[o * 2 + 1] = 0.f; s.head[o] = 0.f;
+        s.state[o] = ST_INVALID; s.token[o] = -1; s.grid[o] = -1;
+        s.interact[o] = c >= col ? 1 : 0;
+        s.tsrc[o] = c >= col ? 1 : 0;                    // temporal_mask all true, sources from the BOS column on (:547-552)
+        s.next_token[o] = -1; s.next_state[o] = 0;
+    }
+    for (int k = tid; k < 5 * S; k += NT) {
+        const size_t o = (size_t)r * (5 * S) + k;
+        s.pred_traj[o * 2] = 0.f; s.pred_traj[o * 2 + 1] = 0.f; s.pred_head[o] = 0.f; s.pred_state[o] = 0.f;
+    }
+    __syncthreads();
+    const int n_new = q.n_new[b] + 1;
+    if (tid == 0) {
+        // decode_pos (attr_tokenizer.py:91-99): grid cell in the ego frame -> world
+        const float th = __fsub_rn(eh, 1.5707963267948966f);
+        const float c = cosf(th), sn = sinf(th);
+        const float gx = s.grid_cells[(size_t)cell * 2], gy = s.grid_cells[(size_t)cell * 2 + 1];
+        const float nx = __fadd_rn(__fadd_rn(__fmul_rn(gx, c), __fmul_rn(gy, -sn)), ex);
+        const float ny = __fadd_rn(__fadd_rn(__fmul_rn(gx, sn), __fmul_rn(gy, c)), ey);
+        const size_t o = (size_t)r * T + col;
+        s.pos[o * 2] = nx; s.pos[o * 2 + 1] = ny;
+        s.head[o] = eh;                                  // dummy value until the heading stage (:1948)
+        s.grid[o] = cell;
+        s.state[o] = ST_ENTER;
+        s.token[o] = -2;                                 // BOS embedding at the insertion column (:1976)
+        s.next_state[o] = ST_ENTER;                      // (:2114)
+        int ty = 0;                                      // type (:1892-1893): argmax of the 3-way softmax
+        if (s_small[3] > s_small[2]) ty = 1;
+        if (s_small[4] > s_small[2 + ty]) ty = 2;
+        const_cast<int *>(s.type)[r] = ty;
+        q.pred_type[r] = ty;
+        for (int k = 0; k < 3; ++k) { q.pred_shape[(size_t)r * 3 + k] = s_small[5 + k]; q.shape_rows[(size_t)r * 3 + k] = s_small[5 + k]; }
+        q.ins_col[r] = col;
+        if (t > 0)
+            for (int k = 0; k < 5; ++k) {                // placeholders of the previous 0.5 s (:1967-1970)
+                const size_t p = (size_t)r * (5 * S) + (size_t)(t - 1) * 5 + k;
+                s.pred_traj[p * 2] = nx; s.pred_traj[p * 2 + 1] = ny; s.pred_head[p] = eh; s.pred_state[p] = (float)ST_ENTER;
+            }
+        const_cast<int *>(s.n_rows)[b] = i_new + 1;
+        q.n_new[b] = n_new;
+        q.new_row[b] = i_new;
+        q.row_lo[b] = i_new;
+        q.flags[1] = 1;
+        // P(enter) of this query (:2105)
+        const float m2 = fmaxf(s_small[0], s_small[1]);
+        const float e0 = expf(s_small[0] - m2), e1 = expf(s_small[1] - m2);
+        q.o_state_prob[((size_t)b * SEED_SLOTS + n_new) * S + t] = e1 / (e0 + e1);
+    }
+    // grid-sized records of this insertion (:2099-2104)
+    const size_t ob = (((size_t)b * SEED_SLOTS + n_new) * S + t) * G;
+    for (int g = tid; g < G; g += NT) {
+        q.o_pos_prob[ob + g] = expf(lg[g] - gmax) / den;
+        q.o_ag_occ[ob + g] = q.ag_occ_logits[(size_t)b * G + g];
+        q.o_pt_occ[ob + g] = q.pt_occ_logits[(size_t)b * G + g];
+        q.o_occ_gt[ob + g] = q.occ[(size_t)b * G + g];
+    }
+}
+
+// after k_seed_decide of every scene: summarise for the host loop (one thread)
+__global__ void k_ins_flags(const InsState q, int n_scenes) {
+    int any = 0;
+    for (int b = 0; b < n_scenes; ++b) any |= q.active[b];
+    q.flags[0] = any;
+}
+__global__ void k_ins_clear_new_flag(const InsState q) { q.flags[1] = 0; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// heading stage, edges of the appended rows (:2024-2035): agents within a2sa_radius (first NEW_AGENT_MAX by index)
+// that interact at column cur, map tokens within pl2sa_radius (first NEW_MAP_MAX).  One CTA (two warps) per scene.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) k_new_edges(const DecState s, const InsState q) {
+    const int b = blockIdx.x, col = *s.col, T = s.T;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i_new = q.new_row[b];
+    if (i_new < 0) {
+        if (threadIdx.x == 0) { q.hp_cnt_s[b] = 0; q.ha_cnt_s[b] = 0; }
+        return;
+    }
+    const int r0 = b * s.cap, r = r0 + i_new, n = s.n_rows[b];
+    const float px = s.pos[((size_t)r * T + col) * 2], py = s.pos[((size_t)r * T + col) * 2 + 1];
+    const float hd = s.head[(size_t)r * T + col];
+    const float hx = cosf(hd), hy = sinf(hd);
+    if (warp == 0) {
+        int cnt = 0, seen = 0;
+        const int base = b * NEW_AGENT_MAX;
+        for (int j0 = 0; j0 < n; j0 += 32) {
+            const int j = j0 + lane, rj = r0 + j;
+            float dx = 0.f, dy = 0.f;
+            bool within = false;
+            if (j < n) {
+                dx = __fsub_rn(s.pos[((size_t)rj * T + col) * 2], px);
+                dy = __fsub_rn(s.pos[((size_t)rj * T + col) * 2 + 1], py);
+                within = dist2(dx, dy) < q.r_new_a2;
+            }
+            const unsigned wm = __ballot_sync(0xffffffffu, within);
+            const bool in_first = within && (seen + __popc(wm & lanemask_lt())) < NEW_AGENT_MAX;
+            const bool ok = in_first && j != i_new && s.interact[(size_t)rj * T + col] != 0;
+            const unsigned mask = __ballot_sync(0xffffffffu, ok);
+            if (ok) {
+                const int slot = base + cnt + __popc(mask & lanemask_lt());
+                q.ha_src[slot] = rj;
+                q.ha_raw[(size_t)slot * 3 + 0] = norm2(dx, dy);
+                q.ha_raw[(size_t)slot * 3 + 1] = angle_between(hx, hy, dx, dy);
+                q.ha_raw[(size_t)slot * 3 + 2] = wrap_angle(__fsub_rn(s.head[(size_t)rj * T + col], hd));
+            }
+            cnt += __popc(mask);
+            seen += __popc(wm);
+        }
+        if (lane == 0) { q.ha_cnt[r] = cnt; q.ha_start[r] = base; q.ha_cnt_s[b] = cnt; }
+    } else {
+        const int pt0 = s.pt_ptr[b], pt1 = s.pt_ptr[b + 1];
+        const int base = b * NEW_MAP_MAX;
+        int cnt = 0;
+        for (int p0 = pt0; p0 < pt1 && cnt < NEW_MAP_MAX; p0 += 32) {
+            const int p = p0 + lane;
+            float dx = 0.f, dy = 0.f;
+            bool ok = false;
+            if (p < pt1) {
+                dx = __fsub_rn(s.pt_pos[(size_t)p * 2], px);
+                dy = __fsub_rn(s.pt_pos[(size_t)p * 2 + 1], py);
+                ok = dist2(dx, dy) < q.r_new_m2;
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, ok);
+            const int rank = cnt + __popc(mask & lanemask_lt());
+            if (ok && rank < NEW_MAP_MAX) {
+                const int slot = base + rank;
+                q.hp_src[slot] = p;
+                q.hp_raw[(size_t)slot * 3 + 0] = norm2(dx, dy);
+                q.hp_raw[(size_t)slot * 3 + 1] = angle_between(hx, hy, dx, dy);
+                q.hp_raw[(size_t)slot * 3 + 2] = wrap_angle(__fsub_rn(s.pt_ori[p], hd));
+            }
+            cnt = min(NEW_MAP_MAX, cnt + __popc(mask));
+        }
+        if (lane == 0) { q.hp_cnt[r] = cnt; q.hp_start[r] = base; q.hp_cnt_s[b] = cnt; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// heading stage, heads of the appended row and its final pose (:2060-2074).  One CTA per scene.
+// ---------------------------------------------------------------------------------------------------------------
+struct HeadFinalArgs {
+    DecState s;
+    InsState q;
+    const float *x;            // [R][128] output of the heading stack
+    MlpHeadW h_heading, h_offset;
+};
+__global__ void __launch_bounds__(NT) k_head_finalize(const HeadFinalArgs a) {
+    __shared__ __align__(16) float sx[128];
+    __shared__ __align__(16) float sh[128];
+    __shared__ float s_out[128];
+    const DecState &s = a.s;
+    const InsState &q = a.q;
+    const int b = blockIdx.x, col = *s.col, T = s.T;
+    const int tid = threadIdx.x;
+    const int i_new = q.new_row[b];
+    if (i_new < 0) return;
+    const int r = b * s.cap + i_new, re = b * s.cap + s.ego_row[b];
+    if (tid < 128) sx[tid] = a.x[(size_t)r * 128 + tid];
+    __syncthreads();
+    mlp_head_row(sx, a.h_heading, sh, s_out);           // 120 heading bins
+    __shared__ int s_bin;
+    if (tid == 0) {
+        int bi = 0; float bv = s_out[0];
+        for (int k = 1; k < a.h_heading.n_out; ++k) if (s_out[k] > bv) { bv = s_out[k]; bi = k; }
+        s_bin = bi;
+    }
+    __syncthreads();
+    mlp_head_row(sx, a.h_offset, sh, s_out);            // 2 offsets
+    if (tid == 0) {
+        const float eh = s.head[(size_t)re * T + col];
+        // decode_heading (attr_tokenizer.py:106-110) + wrap (:2063)
+        float ang = __fsub_rn(__fmul_rn((float)s_bin, q.angle_interval), 180.f);
+        ang = __fmul_rn(__fdiv_rn(ang, 360.f), 6.283185307179586f);
+        const size_t o = (size_t)r * T + col;
+        s.head[o] = wrap_angle(__fadd_rn(ang, eh));
+        s.pos[o * 2] = __fadd_rn(s.pos[o * 2], __fmul_rn(tanhf(s_out[0]), 2.f));
+        s.pos[o * 2 + 1] = __fadd_rn(s.pos[o * 2 + 1], __fmul_rn(tanhf(s_out[1]), 2.f));
+    }
+}
+
+// cat[r] += type_a_emb[type[r]] for the rows [row_lo[b], n_rows[b]) (their shape embedding was just written)
+__global__ void k_add_type_emb_rows(const DecState s, const int *row_lo, float *cat, const float *type_emb) {
+    const int r = blockIdx.x, b = r / s.cap, i = r - b * s.cap;
+    if (i < row_lo[b] || i >= s.n_rows[b]) return;
+    cat[(size_t)r * 128 + threadIdx.x] += type_emb[s.type[r] * 128 + threadIdx.x];
+}
+
+// copy rows [row_lo[b], n_rows[b]) of every scene from one [R][128] buffer to another
+__global__ void k_copy_new_rows(const DecState s, const int *row_lo, const float *src, float *dst) {
+    const int r = blockIdx.x, b = r / s.cap, i = r - b * s.cap;
+    if (i < row_lo[b] || i >= s.n_rows[b]) return;
+    dst[(size_t)r * 128 + threadIdx.x] = src[(size_t)r * 128 + threadIdx.x];
+}
+
+}  // namespace infgen

@@ -444,7 +444,26 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
         apre1 = attn_prefetch<M>(a.sub[f1 < 0 ? 0 : f1], a.rows, row0);
         apre2 = attn_prefetch<M>(a.sub[f2 < 0 ? 0 : f2], a.rows, row0);
     }
-    unsigned bar_target = 0;
+    // grid barriers count the CTAs that own at least one active row (the others returned above)
+    unsigned bar_target = 0, bar_step = 0;
+    {
+        bool any_sync = false;
+        for (int i = 0; i < a.n_sub; ++i) any_sync |= a.sub[i].grid_sync != 0;
+        if (any_sync) {
+            __shared__ unsigned s_bar_step;
+            if (tid == 0) {
+                unsigned n = 0;
+                for (int r0 = 0; r0 < a.rows.n_total; r0 += M) {
+                    bool act = false;
+                    for (int m = 0; m < M; ++m) act |= a.rows.active(r0 + m);
+                    n += act ? CL : 0;
+                }
+                s_bar_step = n;
+            }
+            __syncthreads();
+            bar_step = s_bar_step;
+        }
+    }
     // peers must be resident before anyone writes into their shared memory
     cluster.sync();
     stamp();
@@ -518,7 +537,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
         const SubArgs &A = a.sub[si];
         // ---- edge attention of head c ------------------------------------------------------------------------
         if (A.grid_sync) {                                         // K/V rows of other clusters must have landed
-            bar_target += gridDim.x;
+            bar_target += bar_step;
             __syncthreads();
             if (tid == 0) {
                 __threadfence();

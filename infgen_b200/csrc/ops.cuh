@@ -58,10 +58,13 @@ struct RowSpace {
     int n_total;               // rows in the space (n_scenes * cap, or n for operator-level calls)
     int cap;                   // 0: all rows < n_total are active
     const int *n_rows;         // [n_scenes] device
+    const int *row_lo;         // optional [n_scenes]: rows below it are skipped ("new rows only" launches)
     __device__ __forceinline__ bool active(int r) const {
         if (r >= n_total) return false;
         if (cap == 0) return true;
-        return (r % cap) < __ldg(n_rows + r / cap);
+        const int b = r / cap, i = r - b * cap;
+        if (row_lo && i < row_lo[b]) return false;
+        return i < n_rows[b];
     }
 };
 

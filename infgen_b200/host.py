@@ -125,7 +125,10 @@ class HostBatch:
         assert len(scenes) > 0
         T, S = scenes[0].n_cols, scenes[0].n_iters
         HC = cfg.hist_cols
-        cap = row_capacity or max(s.n_rows for s in scenes)
+        self.insertion = not cfg.disable_insertion
+        # rows the insertion stage may append (at most 10 per iteration, agent_decoder.py:1738) need room
+        self.reserve = min(cfg.insert_row_reserve, 10 * S) if self.insertion else 0
+        cap = row_capacity or (max(s.n_rows for s in scenes) + self.reserve)
         cap = (cap + 3) // 4 * 4
         ns = len(scenes)
         R = ns * cap
@@ -165,11 +168,20 @@ class HostBatch:
         self.out_next_state = buf((R, T), torch.int32)
         self.out_hist_traj = buf((R, HC * 5, 2), torch.float32)
         self.out_hist_head = buf((R, HC * 5), torch.float32)
+        self.out_n_rows = buf((ns,), torch.int32)
+        if self.insertion:
+            from .weights import GRID_SIZE
+            self.out_pred_type = buf((R,), torch.int32)
+            self.out_pred_shape = buf((R, 3), torch.float32)
+            self.out_state_prob_seed = buf((ns, 11, max(S, 1)), torch.float32)
+            for name in ('out_pos_prob_seed', 'out_agent_occ_seed', 'out_pt_occ_seed', 'out_occ_gt_seed'):
+                setattr(self, name, buf((ns, 11, max(S, 1), GRID_SIZE), torch.float32))
         self.fill(scenes, scene_ids)
 
     def fits(self, scenes: Sequence[SceneHost]) -> bool:
         return (len(scenes) == self.n_scenes and all(s.n_cols == self.T and s.n_iters == self.S for s in scenes)
-                and max(s.n_rows for s in scenes) <= self.cap and (max(s.n_rows for s in scenes) + 3) // 4 * 4 == self.cap
+                and max(s.n_rows for s in scenes) + self.reserve <= self.cap
+                and (max(s.n_rows for s in scenes) + self.reserve + 3) // 4 * 4 == self.cap
                 and sum(s.pt_pos.shape[0] for s in scenes) <= self.p_alloc)
 
     def fill(self, scenes: Sequence[SceneHost], scene_ids: Optional[Sequence[int]] = None):
@@ -206,7 +218,9 @@ class HostBatch:
 IN_NAMES = ('pos_hist', 'head_hist', 'state_hist', 'token_hist', 'grid_hist', 'tsrc_hist', 'interact_hist', 'type',
             'shape', 'pt_pos', 'pt_ori', 'x_pt')
 OUT_NAMES = ('out_pos', 'out_head', 'out_pred_traj', 'out_pred_head', 'out_pred_state', 'out_next_token',
-             'out_next_state', 'out_hist_traj', 'out_hist_head')
+             'out_next_state', 'out_hist_traj', 'out_hist_head', 'out_n_rows')
+INS_OUT_NAMES = ('out_pred_type', 'out_pred_shape', 'out_state_prob_seed', 'out_pos_prob_seed', 'out_agent_occ_seed',
+                 'out_pt_occ_seed', 'out_occ_gt_seed')
 
 
 class DeviceBatch:
@@ -214,8 +228,12 @@ class DeviceBatch:
     per-scene descriptors n_rows / ego_row / scene_id / pt_ptr stay on the host, as the C ABI requires)."""
 
     def __init__(self, hb: HostBatch, device):
-        for k in ('n_scenes', 'cap', 'T', 'S', 'R', 'P', 'p_alloc', 'n_rows', 'ego_row', 'scene_id', 'pt_ptr'):
+        for k in ('n_scenes', 'cap', 'T', 'S', 'R', 'P', 'p_alloc', 'n_rows', 'ego_row', 'scene_id', 'pt_ptr',
+                  'insertion', 'reserve'):
             setattr(self, k, getattr(hb, k))
+        if hb.insertion:
+            for k in INS_OUT_NAMES:
+                setattr(self, k, torch.zeros_like(getattr(hb, k), device=device))
         for k in IN_NAMES:
             setattr(self, k, getattr(hb, k).to(device, non_blocking=True))
         for k in OUT_NAMES:
@@ -224,39 +242,58 @@ class DeviceBatch:
 
 
 def assemble_outputs(batch: HostBatch, scenes: Sequence[SceneHost], cfg: DecoderConfig) -> List[Dict]:
-    """agent_decoder.py:2303-2389: the per-scene output dict (keys/dtypes/shapes of the reference; motion stage)."""
+    """agent_decoder.py:2303-2389: the per-scene output dict (keys/dtypes/shapes of the reference).  Rows appended by the
+    insertion stage follow the scene's own rows; history-derived fields cover the scene's own rows only, as in the
+    reference (`num_init_agent`, :2310)."""
     outs = []
     nh, HC = cfg.num_historical_steps, cfg.hist_cols
     for b, s in enumerate(scenes):
-        r0, n = b * batch.cap, s.n_rows
+        r0, n0 = b * batch.cap, s.n_rows
+        n = int(batch.out_n_rows[b]) if batch.insertion else n0
         sl = slice(r0, r0 + n)
         n_rec = s.n_rec
         pred_traj = torch.zeros(n, nh + n_rec, 2)
         pred_head = torch.zeros(n, nh + n_rec)
         pred_state = torch.zeros(n, nh + n_rec)
-        pred_traj[:, 0] = s.pos0
-        pred_head[:, 0] = s.head0
-        pred_traj[:, 1:nh] = batch.out_hist_traj[sl]
-        pred_head[:, 1:nh] = batch.out_hist_head[sl]
-        pred_state[:, 1:nh] = s.hist_state_full.repeat_interleave(cfg.shift, dim=1).float()
+        pred_traj[:n0, 0] = s.pos0
+        pred_head[:n0, 0] = s.head0
+        pred_traj[:n0, 1:nh] = batch.out_hist_traj[r0:r0 + n0]
+        pred_head[:n0, 1:nh] = batch.out_hist_head[r0:r0 + n0]
+        pred_state[:n0, 1:nh] = s.hist_state_full.repeat_interleave(cfg.shift, dim=1).float()
         if n_rec:
             pred_traj[:, nh:] = batch.out_pred_traj[sl, :n_rec]
             pred_head[:, nh:] = batch.out_pred_head[sl, :n_rec]
             pred_state[:, nh:] = batch.out_pred_state[sl, :n_rec]
         pred_valid = (pred_state != INVALID) & (pred_state != ENTER)
         type_a = torch.from_numpy(s.type).long()
-        eval_shape = torch.zeros_like(s.pred_shape)
+        pred_shape = s.pred_shape
+        agent_id = s.agent_id
+        if n > n0:                                              # appended agents (:1916-1918, 1955-1956)
+            type_a = torch.cat([type_a, batch.out_pred_type[r0 + n0:r0 + n].long()])
+            pred_shape = torch.cat([pred_shape, batch.out_pred_shape[r0 + n0:r0 + n].clone()])
+            agent_id = torch.cat([agent_id, int(agent_id.max()) + 1 + torch.arange(n - n0, dtype=agent_id.dtype)])
+        eval_shape = torch.zeros_like(pred_shape)
         for ti, key in enumerate(('vehicle', 'pedstrain', 'cyclist')):
             eval_shape[type_a == ti] = torch.tensor(AGENT_SHAPE[key])
         ncol = HC + s.n_iters
-        outs.append({
-            'ego_index': s.ego_row, 'agent_id': s.agent_id, 'valid_mask': s.valid_mask,
+        out = {
+            'ego_index': s.ego_row, 'agent_id': agent_id, 'valid_mask': s.valid_mask,
             'pos_a': batch.out_pos[sl].clone(), 'head_a': batch.out_head[sl].clone(), 'gt_traj': s.gt_traj,
             'pred_traj': pred_traj, 'pred_head': pred_head, 'pred_type': type_a.clone(), 'pred_state': pred_state,
-            'pred_z': torch.zeros_like(pred_traj[..., 0]), 'pred_shape': s.pred_shape, 'eval_shape': eval_shape,
+            'pred_z': torch.zeros_like(pred_traj[..., 0]), 'pred_shape': pred_shape, 'eval_shape': eval_shape,
             'pred_valid': pred_valid,
             'next_token_idx': batch.out_next_token[sl, :ncol].long(),
             'next_state_idx': batch.out_next_state[sl, :ncol].long(),
-            'agent_labels': [], 'log_message': 'No agents inserted!',
-        })
+            'agent_labels': [],
+            'log_message': (f'Number of total inserted agents: {n - n0}' if n > n0 else 'No agents inserted!'),
+        }
+        if batch.insertion:
+            out.update({
+                'next_state_prob_seed': batch.out_state_prob_seed[b, :, :s.n_iters].clone(),
+                'next_pos_rel_prob_seed': batch.out_pos_prob_seed[b, :, :s.n_iters].clone(),
+                'grid_agent_occ_seed': batch.out_agent_occ_seed[b, :, :s.n_iters].clone(),
+                'grid_pt_occ_seed': batch.out_pt_occ_seed[b, :, :s.n_iters].clone(),
+                'grid_agent_occ_gt_seed': batch.out_occ_gt_seed[b, :, :s.n_iters].clone(),
+            })
+        outs.append(out)
     return outs

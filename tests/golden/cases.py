@@ -22,7 +22,8 @@ CASES = {
 
 def build_case(name: str):
     spec = CASES[name]
-    cfg = DecoderConfig(motion_beam_size=1, insert_beam_size=1, disable_insertion=spec['disable_insertion'])
+    cfg = DecoderConfig(motion_beam_size=1, insert_beam_size=1, disable_insertion=spec['disable_insertion'],
+                        debug_force_enter=bool(spec.get('debug_force_enter', False)))
     sd = make_state_dict(spec['weight_seed'])
     if spec.get('no_insert_bias'):
         # make the seed-state head answer 'invalid' for every query: the insertion stage then runs in the reference

@@ -78,15 +78,18 @@ def test_teacher_forced_matches_reference_golden(name):
     dec.close()
 
 
-@pytest.mark.parametrize('name', MOTION_CASES)
+@pytest.mark.parametrize('name', list(CASES))
 @pytest.mark.parametrize('graph', [False, True])
 def test_free_running_matches_reference_golden(name, graph):
-    """The call a user makes: `inference(data, map_enc)`, greedy, against the reference's outputs."""
+    """The call a user makes: `inference(data, map_enc)`, greedy, against the reference's outputs.  `ragged_a24` runs
+    the insertion stage with a seed head that inserts nobody, `insert_a12` with one that always inserts (the
+    reference's DEBUG=1 switch): rows appended by the CUDA path must be the reference's, in order."""
     scene, sd, cfg, spec = build_case(name)
     z = np.load(os.path.join(GOLD, f'case_{name}.npz'))
     dec = _make_decoder(sd, cfg, use_cuda_graph=graph)
-    out = dec.inference(scene, scene['map_enc'], motion_only=True)
+    out = dec.inference(scene, scene['map_enc'])
     dec.close()
+    assert out['pos_a'].shape[0] == z['pos_a'].shape[0], f"rows {out['pos_a'].shape[0]} vs reference {z['pos_a'].shape[0]}"
     assert out['ego_index'] == int(z['ego_index'])
     div = _first_divergence(out['next_token_idx'].numpy(), z['next_token_idx'], cfg.hist_cols)
     assert div is None, f'{name}: greedy tokens diverge from the reference at iteration {div[0]}, rows {div[1]}'
@@ -94,6 +97,10 @@ def test_free_running_matches_reference_golden(name, graph):
         assert np.array_equal(out[k].numpy(), z[k]), k
     for k in ('pos_a', 'head_a', 'pred_traj', 'pred_head', 'pred_state', 'pred_shape', 'eval_shape'):
         _close(out[k].numpy(), z[k], f'{name} {k}')
+    if 'next_state_prob_seed' in z:
+        for k in ('next_state_prob_seed', 'next_pos_rel_prob_seed', 'grid_agent_occ_seed', 'grid_pt_occ_seed',
+                  'grid_agent_occ_gt_seed'):
+            _close(out[k].numpy(), z[k], f'{name} {k}')
 
 
 def test_topk_sampling_matches_oracle():
