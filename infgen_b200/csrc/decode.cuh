@@ -25,6 +25,9 @@ struct DecState {
     uint8_t *interact, *tsrc;      // [R][T]
     const int *type;               // [R] (rows appended by the insertion stage get their predicted type)
     const int *ins_col;            // [R] insertion column of appended rows, -1 for the scene's own agents (NULL: none)
+    int *hv_src;                   // [R] row whose heading gives this row's heading VECTOR during the current iteration,
+                                   // -1 = its own (agent_decoder.py:2083 overwrites the vectors of every agent inserted
+                                   // in an iteration with the newest one's until they are rebuilt at :2265)
     const int *pt_ptr;
     const float *pt_pos, *pt_ori;
     const float *grid_cells;       // [G][2]
@@ -63,7 +66,8 @@ __global__ void __launch_bounds__(NT) k_edge_build(const DecState s) {
     const int r0 = b * s.cap;
     const float px = s.pos[((size_t)r * T + col) * 2], py = s.pos[((size_t)r * T + col) * 2 + 1];
     const float hd = s.head[(size_t)r * T + col];
-    const float hx = cosf(hd), hy = sinf(hd);
+    const float hd_v = (s.hv_src && s.hv_src[r] >= 0) ? s.head[(size_t)s.hv_src[r] * T + col] : hd;
+    const float hx = cosf(hd_v), hy = sinf(hd_v);
     const bool inv_d = s.state[(size_t)r * T + col] == ST_INVALID;
     const bool inter = s.interact[(size_t)r * T + col] != 0;
     if (kind == 0) {

@@ -1087,7 +1087,7 @@ int32_t infgen_load_scenes(infgen_engine *e, const infgen_scene_batch *b, int32_
     }
     // ---- insertion stage ----
     e->ins_ready = false;
-    s.ins_col = nullptr;
+    s.ins_col = nullptr; s.hv_src = nullptr;
     if (!e->cfg.disable_insertion) {
         InsState &q = e->ins;
         memset(&q, 0, sizeof(q));
@@ -1128,6 +1128,8 @@ int32_t infgen_load_scenes(infgen_engine *e, const infgen_scene_batch *b, int32_
         q.shape_rows = fbuf(e, "shape_rows");
         q.seed_feat = e->seed_feat; q.err = e->d_err;
         s.ins_col = q.ins_col;
+        RET(ensure_t(e, "hv_src", R, &s.hv_src));
+        CK(cudaMemsetAsync(s.hv_src, 0xff, (size_t)R * sizeof(int), e->stream));
         CK(cudaMemsetAsync(q.ins_col, 0xff, (size_t)R * sizeof(int), e->stream));
         CK(cudaMemsetAsync(q.pred_type, 0, (size_t)R * sizeof(int), e->stream));
         CK(cudaMemsetAsync(q.pred_shape, 0, (size_t)R * 3 * sizeof(float), e->stream));

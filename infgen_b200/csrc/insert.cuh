@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(NT) k_ins_begin(const DecState s, const InsSta
         q.one_cnt[b] = 1; q.occ_src[b] = b;
         if (b == 0) { q.flags[0] = 1; q.flags[1] = 0; }
     }
+    for (int i = threadIdx.x; i < s.n_rows[b]; i += NT) s.hv_src[b * s.cap + i] = -1;   // vectors were rebuilt (:2265)
     if (warp != 0) return;
     const int re = b * s.cap + s.ego_row[b];
     const float px = s.pos[((size_t)re * T + col) * 2], py = s.pos[((size_t)re * T + col) * 2 + 1];
@@ -510,6 +511,8 @@ __global__ void __launch_bounds__(NT) k_head_finalize(const HeadFinalArgs a) {
         s.head[o] = wrap_angle(__fadd_rn(ang, eh));
         s.pos[o * 2] = __fadd_rn(s.pos[o * 2], __fmul_rn(tanhf(s_out[0]), 2.f));
         s.pos[o * 2 + 1] = __fadd_rn(s.pos[o * 2 + 1], __fmul_rn(tanhf(s_out[1]), 2.f));
+        // sic (:2083): the heading vectors of EVERY agent inserted in this iteration become the newest one's
+        for (int k = 0; k < q.n_new[b]; ++k) s.hv_src[b * s.cap + i_new - k] = r;
     }
 }
 

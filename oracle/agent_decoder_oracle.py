@@ -560,8 +560,22 @@ def rollout(scene: Dict, W: Dict[str, torch.Tensor], cfg, seed: int = 2024, scen
             p_soft = torch.softmax(mlp_layer(W, 'seed_pos_rel_token_predict_head', q), dim=-1)
             top_p, top_i = torch.topk(p_soft, k=cfg.insert_beam_size, dim=-1)
             if cfg.insert_beam_size > 1:
-                raise NotImplementedError('insert_beam_size > 1 needs the shared sampler (reference: torch.multinomial)')
-            cell = top_i[:, :1]
+                # reference: torch.multinomial(topk_prob, 1) (:1900); here the counter-based draw shared with the
+                # CUDA path, keyed by (scene, pass, iteration) - same distribution
+                tp = top_p[0].to(torch.float32)
+                total = torch.tensor(0.0)
+                for j in range(cfg.insert_beam_size):
+                    total = total + tp[j]
+                thr = torch.tensor(uniform01(seed ^ 0x5EED, scene_id, p_pass - 1, t), dtype=torch.float32) * total
+                c_acc, pick = torch.tensor(0.0), cfg.insert_beam_size - 1
+                for j in range(cfg.insert_beam_size):
+                    c_acc = c_acc + tp[j]
+                    if bool(thr < c_acc):
+                        pick = j
+                        break
+                cell = top_i[:, pick:pick + 1]
+            else:
+                cell = top_i[:, :1]
             new_pos = decode_pos(grid, cell[..., 0], ego_pos, ego_head)
             if bool(occ[cell[0, 0]]):                                                        # overlap filter (:1906-1909)
                 feat0 = raw_feat
