@@ -371,6 +371,33 @@ def run_ours(args, rank, world, local_rank):
         except Exception as ex:      # the headline line must still be printed
             extra = {'error': repr(ex)[:200]}
 
+    # ---- optional side measurement: the same scene with the insertion stage live (agent_decoder.py:1744-2114) -----------
+    ins_extra = None
+    if rank == 0 and world == 1 and args.scenes == 1 and not args.no_extra:
+        try:
+            ins_extra = {}
+            for label, force in (('query_only', False), ('one_insert_per_iteration', True)):
+                icfg = DecoderConfig(motion_beam_size=5, insert_beam_size=1, disable_insertion=False,
+                                     debug_force_enter=force)
+                idec = B200AgentDecoder(sd, icfg, device=local_rank, seed=2024, use_cuda_graph=True)
+                for _ in range(3):
+                    out_i = idec.inference_batch(scenes[:1], maps[:1])
+                torch.cuda.synchronize(dev)
+                ts = []
+                for _ in range(5):
+                    t0 = time.perf_counter()
+                    out_i = idec.inference_batch(scenes[:1], maps[:1])
+                    ts.append(time.perf_counter() - t0)
+                idec.close()
+                rows_final = int(out_i[0]['pos_a'].shape[0])
+                ins_extra[label] = {'ms_per_rollout_e2e': statistics.mean(ts) * 1e3, 'rows_final': rows_final,
+                                    'value': N_AGENTS * N_STEPS / statistics.mean(ts), 'unit': UNIT}
+            ins_extra['workload'] = ('configs[1] scene with the insertion stage enabled (random-init weights never insert: '
+                                     'one seed query per iteration; debug_force_enter: one agent inserted per iteration), '
+                                     'public call with host tensors')
+        except Exception as ex:
+            ins_extra = {'error': repr(ex)[:200]}
+
     # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -398,6 +425,8 @@ def run_ours(args, rank, world, local_rank):
         }
         if extra:
             line['batch32'] = extra
+        if ins_extra:
+            line['insertion'] = ins_extra
         print(json.dumps(line), flush=True)
     dec.close()
     if world > 1:

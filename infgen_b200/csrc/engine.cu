@@ -589,23 +589,24 @@ static int run_insertion(infgen_engine *e) {
         {   // the query rows: 3 x {occ2sa, pt2sa, a2sa} with their edges
             LayerArgs la;
             memset(&la, 0, sizeof(la));
-            la.rows.n_total = ns; la.rows.cap = 1; la.rows.n_rows = q.active; la.rows.row_lo = nullptr;
+            la.rows.n_total = ns * SEED_ROW_STRIDE; la.rows.cap = SEED_ROW_STRIDE; la.rows.n_rows = q.active;
+            la.rows.row_lo = nullptr;
             la.x = q.x_seed; la.ring = RING;
             la.pre0 = make_pre(e->occ2sa[0], false, nullptr, false, 0, false);
             const size_t kvl = (size_t)R * 256, kvm = (size_t)e->P * 256;
             int n = 0;
             for (int i = 0; i < 3; ++i) {
                 SubArgs &o = la.sub[n++];
-                o.w = e->occ2sa[i].cs_post; o.has_attn = 1; o.has_pos = 0; o.elist = 0;
+                o.w = e->occ2sa[i].cs_post; o.has_attn = 1; o.has_pos = 0; o.elist = 0; o.row_shift = 2; o.wide = 1;
                 o.kv = q.kv_occ + (size_t)i * ns * 256; o.cnt = q.one_cnt; o.start = nullptr; o.stride = 1; o.src = q.occ_src;
                 o.pre = make_pre(e->pt2sa[i], false, nullptr, false, 0, false);
                 SubArgs &p = la.sub[n++];
-                p.w = e->pt2sa[i].cs_post; p.has_attn = 1; p.has_pos = 1; p.elist = 1;
+                p.w = e->pt2sa[i].cs_post; p.has_attn = 1; p.has_pos = 1; p.elist = 1; p.row_shift = 2; p.wide = 1;
                 p.kv = fbuf(e, "kv_ms") + i * kvm; p.cnt = q.ps_cnt; p.start = nullptr; p.stride = SEED_MAP_MAX;
                 p.src = q.ps_src; p.rhat = fbuf(e, "rhat_ps");
                 p.pre = make_pre(e->a2sa[i], false, nullptr, false, 0, false);
                 SubArgs &g = la.sub[n++];
-                g.w = e->a2sa[i].cs_post; g.has_attn = 1; g.has_pos = 1; g.elist = 2;
+                g.w = e->a2sa[i].cs_post; g.has_attn = 1; g.has_pos = 1; g.elist = 2; g.row_shift = 2; g.wide = 1;
                 g.kv = fbuf(e, "kv_sa") + i * kvl; g.cnt = q.as_cnt; g.start = nullptr; g.stride = cap;
                 g.src = q.as_src; g.rhat = fbuf(e, "rhat_as");
                 if (i < 2) g.pre = make_pre(e->occ2sa[i + 1], false, nullptr, false, 0, false);
@@ -617,9 +618,9 @@ static int run_insertion(infgen_engine *e) {
             e->row_tile = saved;
             RET(rc);
         }
-        RET(launch_mlp_layer(e, e->h_seed_pos, q.x_seed, ns, q.pos_logits));
-        RET(launch_mlp_layer(e, e->h_ag_occ, q.x_seed, ns, q.ag_occ_logits));
-        RET(launch_mlp_layer(e, e->h_pt_occ, q.x_seed, ns, q.pt_occ_logits));
+        RET(launch_mlp_layer(e, e->h_seed_pos, q.x_seed, ns * SEED_ROW_STRIDE, q.pos_logits));
+        RET(launch_mlp_layer(e, e->h_ag_occ, q.x_seed, ns * SEED_ROW_STRIDE, q.ag_occ_logits));
+        RET(launch_mlp_layer(e, e->h_pt_occ, q.x_seed, ns * SEED_ROW_STRIDE, q.pt_occ_logits));
         SeedDecideArgs da;
         memset(&da, 0, sizeof(da));
         da.s = s; da.q = q; da.h_state = e->h_seed_state; da.h_type = e->h_seed_type; da.h_shape = e->h_seed_shape;
@@ -1110,10 +1111,10 @@ int32_t infgen_load_scenes(infgen_engine *e, const infgen_scene_batch *b, int32_
         RET(ensure_t(e, "ha_src", (size_t)ns * NEW_AGENT_MAX, &q.ha_src)); RET(ensure_t(e, "ha_raw", (size_t)ns * NEW_AGENT_MAX * 3, &q.ha_raw));
         RET(ensure_t(e, "hp_cnt_s", ns, &q.hp_cnt_s)); RET(ensure_t(e, "ha_cnt_s", ns, &q.ha_cnt_s));
         RET(ensure_t(e, "occ", (size_t)ns * G, &q.occ)); RET(ensure_t(e, "occ_emb", (size_t)ns * 128, &q.occ_emb));
-        RET(ensure_t(e, "kv_occ", (size_t)3 * ns * 256, &q.kv_occ)); RET(ensure_t(e, "x_seed", (size_t)ns * 128, &q.x_seed));
-        RET(ensure_t(e, "pos_logits", (size_t)ns * G, &q.pos_logits));
-        RET(ensure_t(e, "ag_occ_logits", (size_t)ns * G, &q.ag_occ_logits));
-        RET(ensure_t(e, "pt_occ_logits", (size_t)ns * G, &q.pt_occ_logits));
+        RET(ensure_t(e, "kv_occ", (size_t)3 * ns * 256, &q.kv_occ)); RET(ensure_t(e, "x_seed", (size_t)ns * SEED_ROW_STRIDE * 128, &q.x_seed));
+        RET(ensure_t(e, "pos_logits", (size_t)ns * SEED_ROW_STRIDE * G, &q.pos_logits));
+        RET(ensure_t(e, "ag_occ_logits", (size_t)ns * SEED_ROW_STRIDE * G, &q.ag_occ_logits));
+        RET(ensure_t(e, "pt_occ_logits", (size_t)ns * SEED_ROW_STRIDE * G, &q.pt_occ_logits));
         RET(ensure_t(e, "ins_col", R, &q.ins_col)); RET(ensure_t(e, "pred_type", R, &q.pred_type));
         RET(ensure_t(e, "pred_shape", (size_t)R * 3, &q.pred_shape));
         const size_t nso = (size_t)ns * SEED_SLOTS * std::max(S, 1);

@@ -23,6 +23,8 @@ constexpr int NEW_MAP_MAX = 128;       // (:2035)
 constexpr int NEW_AGENT_MAX = 24;      // (:2029)
 constexpr int INSERT_LIMIT = 10;       // (:1738)
 constexpr int SEED_SLOTS = INSERT_LIMIT + 1;
+constexpr int SEED_ROW_STRIDE = 4;     // the query row of scene b is row 4b of its own row space: alone in its tile, so that
+                                       // all warps of the CTA share its (up to 2048) edges
 
 struct InsState {
     int beam;                          // insert_beam_size
@@ -50,10 +52,10 @@ struct InsState {
     float *occ_emb;                    // [ns][128] seed_agent_occ_embed(occ)
     float *kv_occ;                     // [3][ns][256] K|V of the occupancy node for the three occ2sa layers
     // query row
-    float *x_seed;                     // [ns][128]
+    float *x_seed;                     // [ns*SEED_ROW_STRIDE][128], row 4b
     const float *seed_feat;            // [128] `_build_agent_feature(..., state_index=invalid)` - a constant
     // head outputs of the query row
-    float *pos_logits, *ag_occ_logits, *pt_occ_logits;   // [ns][G]
+    float *pos_logits, *ag_occ_logits, *pt_occ_logits;   // [ns*SEED_ROW_STRIDE][G], row 4b
     // per row
     int *ins_col;                      // [R] column at which the row was inserted, -1 for the scene's own agents
     float *shape_rows;                 // [R+1][3] shape fed to shape_emb (row R = 0.1)
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(NT) k_seed_prepare(const SeedPrepArgs a) {
         __syncthreads();
     }
     // ---- query row feature ----
-    if (tid < 128) q.x_seed[(size_t)b * 128 + tid] = q.seed_feat[tid];
+    if (tid < 128) q.x_seed[(size_t)b * SEED_ROW_STRIDE * 128 + tid] = q.seed_feat[tid];
     // ---- agent -> seed edges: rows within the radius of the ego pose (first SEED_AGENT_MAX by index, the query row
     //      itself being the last index), kept if they interact at column cur ----
     if (warp != 0) return;
@@ -247,13 +249,13 @@ __global__ void __launch_bounds__(NT) k_seed_decide(const SeedDecideArgs a) {
     const int b = blockIdx.x, col = *s.col, t = *s.iter, T = s.T, G = s.G, S = s.S;
     const int tid = threadIdx.x;
     if (!q.active[b]) return;
-    if (tid < 128) sx[tid] = q.x_seed[(size_t)b * 128 + tid];
+    if (tid < 128) sx[tid] = q.x_seed[(size_t)b * SEED_ROW_STRIDE * 128 + tid];
     __syncthreads();
     mlp_head_row(sx, a.h_state, sh, s_small);
     mlp_head_row(sx, a.h_type, sh, s_small + 2);
     mlp_head_row(sx, a.h_shape, sh, s_small + 5);
     // ---- position: softmax over the grid, top-k, draw (:1896-1902) ----
-    const float *lg = q.pos_logits + (size_t)b * G;
+    const float *lg = q.pos_logits + (size_t)b * SEED_ROW_STRIDE * G;
     float mxv = -INFINITY;
     for (int g = tid; g < G; g += NT) mxv = fmaxf(mxv, lg[g]);
     s_red[tid] = mxv;
@@ -386,8 +388,8 @@ __global__ void __launch_bounds__(NT) k_seed_decide(const SeedDecideArgs a) {
     const size_t ob = (((size_t)b * SEED_SLOTS + n_new) * S + t) * G;
     for (int g = tid; g < G; g += NT) {
         q.o_pos_prob[ob + g] = expf(lg[g] - gmax) / den;
-        q.o_ag_occ[ob + g] = q.ag_occ_logits[(size_t)b * G + g];
-        q.o_pt_occ[ob + g] = q.pt_occ_logits[(size_t)b * G + g];
+        q.o_ag_occ[ob + g] = q.ag_occ_logits[(size_t)b * SEED_ROW_STRIDE * G + g];
+        q.o_pt_occ[ob + g] = q.pt_occ_logits[(size_t)b * SEED_ROW_STRIDE * G + g];
         q.o_occ_gt[ob + g] = q.occ[(size_t)b * G + g];
     }
 }

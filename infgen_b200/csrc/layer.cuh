@@ -83,6 +83,8 @@ struct SubArgs {
     const float *rhat;         // [slots][128]
     PreArgs pre;               // projections of the following layer
     float *trace_out;          // optional copy of the layer output [R][128]
+    int row_shift;             // edge lists are indexed by (row >> row_shift) (query rows that sit alone in their tile)
+    int wide;                  // 1: only the first row of each tile has edges and all warps of the CTA share them
     int elist;                 // which of the (up to 3) distinct edge lists of the launch this layer uses
     int grid_sync;             // wait for every CTA of the grid before the attention (K/V written by other clusters in
                                // this launch); only legal when the whole grid is co-resident
@@ -208,18 +210,19 @@ struct AttnPre {               // per warp: its share of the row's edges, source
 };
 template <int M>
 __device__ __forceinline__ AttnPre attn_prefetch(const SubArgs &A, const RowSpace &rows, int row0) {
-    constexpr int WPR = NWARP / M;
+    const int nparts = A.wide ? NWARP : NWARP / M;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m = warp / WPR, part = warp % WPR;
+    const int m = A.wide ? 0 : warp / nparts, part = A.wide ? warp : warp % nparts;
     const int r = row0 + m;
     AttnPre p;
     int n = 0;
     p.e0 = 0;
     if (A.has_attn && rows.active(r)) {
-        n = A.cnt[r];
-        p.e0 = A.start ? A.start[r] : r * A.stride;
+        const int ri = r >> A.row_shift;
+        n = A.cnt[ri];
+        p.e0 = A.start ? A.start[ri] : ri * A.stride;
     }
-    const int share = WPR == 1 ? n : (((n + WPR - 1) / WPR + 7) & ~7);
+    const int share = nparts == 1 ? n : (((n + nparts - 1) / nparts + 7) & ~7);
     p.eb0 = min(n, part * share);
     p.eb1 = min(n, p.eb0 + share);
     p.src0 = (p.eb0 + lane < p.eb1) ? A.src[p.e0 + p.eb0 + lane] : 0;
@@ -235,10 +238,9 @@ struct AttnChunk {
 template <int M>
 __device__ __forceinline__ void attn_phase(const SubArgs &A, const AttnPre &P, int c, const float *sq, const float *sqr,
                                            float *sagg, float *sragg, float *ssal, float *smerge) {
-    constexpr int WPR = NWARP / M;
-    static_assert(WPR == 1 || WPR == 2, "1 or 2 warps per row");
+    const int nparts = A.wide ? NWARP : NWARP / M;      // warps sharing one row's edges
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m = warp / WPR, part = warp % WPR;
+    const int m = A.wide ? 0 : warp / nparts, part = A.wide ? warp : warp % nparts;
     const int eq = lane >> 2, qd = lane & 3;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 qr4 = ld4(sqr + m * 128 + 4 * lane);
@@ -335,29 +337,37 @@ __device__ __forceinline__ void attn_phase(const SubArgs &A, const AttnPre &P, i
         av.x += __shfl_xor_sync(0xffffffffu, av.x, o); av.y += __shfl_xor_sync(0xffffffffu, av.y, o);
         av.z += __shfl_xor_sync(0xffffffffu, av.z, o); av.w += __shfl_xor_sync(0xffffffffu, av.w, o);
     }
-    if (WPR == 2) {
+    if (nparts > 1) {                                    // fold the partial softmax states of the row's warps
         float *mg = smerge + warp * 160;
-        if (part == 1) {
+        if (part != 0) {
             if (lane == 0) { mg[0] = mx; mg[1] = den; }
             if (lane < 4) st4(mg + 4 + 4 * lane, av);
             st4(mg + 32 + 4 * lane, ra);
         }
         __syncthreads();
         if (part == 0) {
-            const float *og = smerge + (warp + 1) * 160;
-            const float mx1 = og[0], den1 = og[1];
-            const float mn = fmaxf(mx, mx1);
-            if (mn > -INFINITY) {
-                const float f0 = expf(mx - mn), f1 = expf(mx1 - mn);
-                const float4 ra1 = ld4(og + 32 + 4 * lane);
-                const float4 av1 = ld4(og + 4 + 4 * qd);
-                den = den * f0 + den1 * f1;
-                ra = make_float4(ra.x * f0 + ra1.x * f1, ra.y * f0 + ra1.y * f1, ra.z * f0 + ra1.z * f1,
-                                 ra.w * f0 + ra1.w * f1);
-                av = make_float4(av.x * f0 + av1.x * f1, av.y * f0 + av1.y * f1, av.z * f0 + av1.z * f1,
-                                 av.w * f0 + av1.w * f1);
+            for (int k = 1; k < nparts; ++k) {
+                const float *og = smerge + (warp + k) * 160;
+                const float mx1 = og[0], den1 = og[1];
+                const float mn = fmaxf(mx, mx1);
+                if (mn > -INFINITY) {
+                    const float f0 = expf(mx - mn), f1 = expf(mx1 - mn);
+                    const float4 ra1 = ld4(og + 32 + 4 * lane);
+                    const float4 av1 = ld4(og + 4 + 4 * qd);
+                    den = den * f0 + den1 * f1;
+                    ra = make_float4(ra.x * f0 + ra1.x * f1, ra.y * f0 + ra1.y * f1, ra.z * f0 + ra1.z * f1,
+                                     ra.w * f0 + ra1.w * f1);
+                    av = make_float4(av.x * f0 + av1.x * f1, av.y * f0 + av1.y * f1, av.z * f0 + av1.z * f1,
+                                     av.w * f0 + av1.w * f1);
+                    mx = mn;
+                }
             }
         }
+    }
+    if (A.wide && warp > 0 && warp < M) {                // the other rows of a query tile have no edges
+        if (lane < 4) st4(sagg + warp * 16 + 4 * lane, z4);
+        st4(sragg + warp * LD1 + 4 * lane, z4);
+        if (lane == 0) ssal[warp] = 0.f;
     }
     if (part == 0) {
         const float inv = 1.0f / (den + 1e-16f);          // torch_geometric.utils.softmax denominator

@@ -128,8 +128,13 @@ class HostBatch:
         self.insertion = not cfg.disable_insertion
         # rows the insertion stage may append (at most 10 per iteration, agent_decoder.py:1738) need room
         self.reserve = min(cfg.insert_row_reserve, 10 * S) if self.insertion else 0
-        cap = row_capacity or (max(s.n_rows for s in scenes) + self.reserve)
+        most = max(s.n_rows for s in scenes)
+        cap = row_capacity or (most + self.reserve)
         cap = (cap + 3) // 4 * 4
+        # a single scene of up to 120 rows runs all 18 layers of an iteration in ONE launch (15 co-resident clusters of
+        # 8 rows): do not let the reserve push a scene that fits out of that regime
+        if row_capacity is None and len(scenes) == 1 and self.reserve and cap > 120 >= most + 16:
+            cap = 120
         ns = len(scenes)
         R = ns * cap
         P = sum(s.pt_pos.shape[0] for s in scenes)
@@ -180,8 +185,8 @@ class HostBatch:
 
     def fits(self, scenes: Sequence[SceneHost]) -> bool:
         return (len(scenes) == self.n_scenes and all(s.n_cols == self.T and s.n_iters == self.S for s in scenes)
-                and max(s.n_rows for s in scenes) + self.reserve <= self.cap
-                and (max(s.n_rows for s in scenes) + self.reserve + 3) // 4 * 4 == self.cap
+                and max(s.n_rows for s in scenes) + (16 if self.reserve else 0) <= self.cap
+                and self.cap <= (max(s.n_rows for s in scenes) + self.reserve + 3) // 4 * 4
                 and sum(s.pt_pos.shape[0] for s in scenes) <= self.p_alloc)
 
     def fill(self, scenes: Sequence[SceneHost], scene_ids: Optional[Sequence[int]] = None):
