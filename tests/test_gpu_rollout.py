@@ -231,3 +231,23 @@ def test_insertion_batch_equals_single():
             assert torch.equal(x[k], y[k]), (b, k)
         for k in ('pos_a', 'head_a', 'pred_traj', 'pred_head'):
             _close(x[k].numpy(), y[k].numpy(), f'scene {b} {k}')
+
+
+def test_long_horizon_matches_oracle():
+    """A horizon longer than the scene (num_recurrent_steps_val = 150 -> 30 iterations, 32 columns): the temporal K/V ring
+    (16 slots for a 12-column window) wraps twice; greedy tokens and trajectories against the oracle."""
+    from oracle.agent_decoder_oracle import rollout
+    from infgen_b200.weights import make_state_dict
+    from infgen_b200.synth import make_scene
+    cfg = DecoderConfig(motion_beam_size=1, disable_insertion=True, num_recurrent_steps_val=150)
+    sd = make_state_dict(4)
+    scene = make_scene(31, num_agents=14, num_map_tokens=384, num_steps=91, ragged=0.3, ego_index=1, cfg=cfg)
+    want = rollout(scene, sd, cfg)['out']
+    dec = _make_decoder(sd, cfg, use_cuda_graph=True)
+    got = dec.inference(scene, scene['map_enc'])
+    dec.close()
+    assert got['next_token_idx'].shape == want['next_token_idx'].shape and got['next_token_idx'].shape[1] == 32
+    div = _first_divergence(got['next_token_idx'].numpy(), want['next_token_idx'].numpy(), cfg.hist_cols)
+    assert div is None, f'greedy tokens diverge from the oracle at iteration {div[0]}, rows {div[1]}'
+    for k in ('pos_a', 'head_a', 'pred_traj', 'pred_head'):
+        _close(got[k].numpy(), want[k].numpy(), k)
