@@ -129,6 +129,11 @@ def run_reference(args, rank, world):
     cfg = DecoderConfig(motion_beam_size=5, disable_insertion=True)
     sd = make_state_dict(0)
     scene = make_workload(0, 1, cfg)[0]
+    # torchrun pins OMP_NUM_THREADS=1 for multi-process launches; the reference arm uses every host core it may run on
+    try:
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
     cores = torch.get_num_threads()
     # calibrate the per-step sample so that the whole run stays within ~3 minutes
     dt, it, S = cpu_rollout_timing(scene, sd, cfg, 1)
