@@ -127,11 +127,23 @@ struct LayerSmem {
     static constexpr int AGG = S + M * 16;                // [M][16]
     static constexpr int SAL = AGG + M * 16;              // [M] (padded to 16)
     static constexpr int MERGE = SAL + 16;                // [NWARP][160]
-    static constexpr int MBAR = MERGE + NWARP * 160;      // 2 x uint64
-    static constexpr int TOTAL = MBAR + 4;
+    static constexpr int MBAR = MERGE + NWARP * 160;      // 2 x uint64 (weight chunks) + 5 x uint64 (exchanges)
+    static constexpr int TOTAL = MBAR + 16;
     static constexpr size_t BYTES = (size_t)TOTAL * sizeof(float);
     static_assert(BYTES <= 227 * 1024, "shared memory budget");
 };
+
+// DSMEM exchange without a cluster-wide barrier: a remote store that signals the DESTINATION CTA's mbarrier with its byte
+// count (st.async ... mbarrier::complete_tx::bytes); the consumer posts the expected bytes and waits on its own barrier.
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_async_f32(uint32_t raddr, float v, uint32_t rmbar) {
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];" ::"r"(raddr), "f"(v), "r"(rmbar)
+                 : "memory");
+}
 
 // LayerNorm of a 128-vector (4 channels per lane) with the affine vectors in shared (or any generic) memory
 __device__ __forceinline__ float4 ln128s(const float4 v, const float *g, const float *b, int lane) {
@@ -405,7 +417,25 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
           *sragg = smem + L::RAGG, *sqr = smem + L::QR, *sq = smem + L::Q, *ss = smem + L::S, *sagg = smem + L::AGG,
           *ssal = smem + L::SAL, *smerge = smem + L::MERGE;
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + L::MBAR);  // [0] post buffer, [1] pre buffer
-    uint32_t post_par = 0, pre_par = 0;
+    uint64_t *xbar = mbar + 2;                                      // [5] exchange barriers: agg, u, o, h, y
+    uint32_t post_par = 0, pre_par = 0, xpar = 0;                   // xpar: parity bit per exchange barrier
+    const uint32_t sbase = smem_u32(smem);
+    uint32_t rbase[CL];                                             // this CTA's shared window as seen ... of every peer
+#pragma unroll
+    for (int p = 0; p < CL; ++p) rbase[p] = mapa_u32(sbase, (uint32_t)p);
+    // send one float to the same shared-memory location of all CL CTAs, completing `bytes` on their exchange barrier xb
+    auto xsend = [&](const float *dst, int xb, float v) {
+        const uint32_t off = smem_u32(dst) - sbase, boff = smem_u32(&xbar[xb]) - sbase;
+#pragma unroll
+        for (int p = 0; p < CL; ++p) st_async_f32(rbase[p] + off, v, rbase[p] + boff);
+    };
+    auto xexpect = [&](int xb, uint32_t bytes) {                   // once per exchange, any time before the wait
+        if (tid == 0) mbar_expect_tx(&xbar[xb], bytes);
+    };
+    auto xwait = [&](int xb) {
+        mbar_wait(&xbar[xb], (xpar >> xb) & 1u);
+        xpar ^= 1u << xb;
+    };
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
     // the sequence of PRE chunks this launch consumes: pre0, sub[0].pre, sub[1].pre (those that exist)
@@ -421,6 +451,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
         mbar_init(&mbar[1], 1);
+        for (int i = 0; i < 5; ++i) mbar_init(&xbar[i], 1);
         fence_mbar_init();
     }
     __syncthreads();
@@ -579,38 +610,33 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
         }
         __syncthreads();
         // ---- agg2 = agg + Wvr ragg' + bvr * sal  -> all CTAs ---------------------------------------------------
+        xexpect(0, M * 128 * 4);
         if (A.has_pos) {
             slice_gemm<M, 16, (M == 4 ? 2 : 4)>(sragg, LD1, wpost + cs_post::WVR, 32, sred, [&](int m, int n, float v) {
                 v += sagg[m * 16 + n] + wpost[cs_post::BVR + n] * ssal[m];
-#pragma unroll
-                for (int p = 0; p < CL; ++p) cluster.map_shared_rank(scat, p)[m * LD2 + 16 * c + n] = v;
+                xsend(scat + m * LD2 + 16 * c + n, 0, v);
             });
         } else {
-            for (int o = tid; o < M * 16; o += NT) {
-                const float v = sagg[o];
-#pragma unroll
-                for (int p = 0; p < CL; ++p) cluster.map_shared_rank(scat, p)[(o >> 4) * LD2 + 16 * c + (o & 15)] = v;
-            }
+            for (int o = tid; o < M * 16; o += NT) xsend(scat + (o >> 4) * LD2 + 16 * c + (o & 15), 0, sagg[o]);
         }
-        cluster.sync();
+        xwait(0);
         stamp();
         // ---- gate: g = sigmoid(Wg [agg | xd] + bg);  u = agg + g * (s - agg) ----------------------------------
+        xexpect(1, M * 128 * 4);
         slice_gemm<M, 16, (M == 4 ? 2 : 4)>(scat, LD2, wpost + cs_post::WG, 64, sred, [&](int m, int n, float v) {
             const float g = sigmoidf(v + wpost[cs_post::BG + n]);
             const float ag = scat[m * LD2 + 16 * c + n];
             const float u = ag + g * (ss[m * 16 + n] - ag);
-#pragma unroll
-            for (int p = 0; p < CL; ++p) cluster.map_shared_rank(su, p)[m * LD1 + 16 * c + n] = u;
+            xsend(su + m * LD1 + 16 * c + n, 1, u);
         });
-        cluster.sync();
+        xwait(1);
         stamp();
         // ---- to_out ------------------------------------------------------------------------------------------
+        xexpect(2, M * 128 * 4);
         slice_gemm<M, 16, (M == 4 ? 2 : 4)>(su, LD1, wpost + cs_post::WO, 32, sred, [&](int m, int n, float v) {
-            v += wpost[cs_post::BO + n];
-#pragma unroll
-            for (int p = 0; p < CL; ++p) cluster.map_shared_rank(so, p)[m * LD1 + 16 * c + n] = v;
+            xsend(so + m * LD1 + 16 * c + n, 2, v + wpost[cs_post::BO + n]);
         });
-        cluster.sync();
+        xwait(2);
         stamp();
         // x1 = x + LN_post(o);  so = LN_ffpre(x1)
         for (int m = warp; m < M; m += NWARP) {
@@ -622,19 +648,17 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
         }
         __syncthreads();
         // ---- FFN ---------------------------------------------------------------------------------------------
+        xexpect(3, M * 512 * 4);
         slice_gemm<M, 64, 4>(so, LD1, wpost + cs_post::W1, 32, sred, [&](int m, int n, float v) {
-            v = fmaxf(v + wpost[cs_post::B1 + n], 0.f);
-#pragma unroll
-            for (int p = 0; p < CL; ++p) cluster.map_shared_rank(sh, p)[m * LD5 + 64 * c + n] = v;
+            xsend(sh + m * LD5 + 64 * c + n, 3, fmaxf(v + wpost[cs_post::B1 + n], 0.f));
         });
-        cluster.sync();
+        xwait(3);
         stamp();
+        xexpect(4, M * 128 * 4);
         slice_gemm<M, 16, (M == 4 ? 2 : 4)>(sh, LD5, wpost + cs_post::W2, 128, sred, [&](int m, int n, float v) {
-            v += wpost[cs_post::B2 + n];
-#pragma unroll
-            for (int p = 0; p < CL; ++p) cluster.map_shared_rank(sy, p)[m * LD1 + 16 * c + n] = v;
+            xsend(sy + m * LD1 + 16 * c + n, 4, v + wpost[cs_post::B2 + n]);
         });
-        cluster.sync();
+        xwait(4);
         stamp();
         // x2 = x1 + LN_ffpost(y)
         const bool last = si + 1 == a.n_sub;

@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(NT_S) k_fourier(const FourierBatch fb) {
 // ===============================================================================================================
 // MLPEmbedding (layers.py:170-189): x[n][kin] -> 128 (LN, ReLU) -> 128 (LN, ReLU) -> 128, tiles of EM rows
 // ===============================================================================================================
-constexpr int EM = 16;
+constexpr int EM = 8;
 
 __device__ __forceinline__ int mlp3_segs(const MlpEmbW &w, int k4, WSeg *segs) {
     segs[0] = WSeg{w.w0, k4, 512};
