@@ -1149,6 +1149,7 @@ int32_t infgen_load_scenes(infgen_engine *e, const infgen_scene_batch *b, int32_
     k_setup_state<<<(R * T + 255) / 256, 256, 0, st>>>(sa);
     CKL(); count_launch(e);
     CK(cudaMemsetAsync(s.a_total, 0, ns * sizeof(int), st));
+    CK(cudaMemsetAsync(e->d_err, 0, sizeof(int), st));
     CK(cudaMemsetAsync(s.col, 0, 2 * sizeof(int), st));
     // ---- categorical embedding rows (type + shape, agent_decoder.py:449-478) ----
     float *shape_rows = fbuf(e, "shape_rows"), *cat_tab = fbuf(e, "cat_tab");

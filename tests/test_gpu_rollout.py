@@ -251,3 +251,22 @@ def test_long_horizon_matches_oracle():
     assert div is None, f'greedy tokens diverge from the oracle at iteration {div[0]}, rows {div[1]}'
     for k in ('pos_a', 'head_a', 'pred_traj', 'pred_head'):
         _close(got[k].numpy(), want[k].numpy(), k)
+
+
+def test_insertion_capacity_error_is_reported():
+    """Rows appended beyond the reserved capacity must surface as an error of the call, not as silent truncation; the
+    engine stays usable afterwards."""
+    from infgen_b200.weights import make_state_dict
+    from infgen_b200.synth import make_scene
+    cfg = DecoderConfig(motion_beam_size=1, insert_beam_size=10, disable_insertion=False, debug_force_enter=True,
+                        insert_row_reserve=6)
+    sd = make_state_dict(3)
+    scene = make_scene(23, num_agents=12, num_map_tokens=512, num_steps=91, ragged=0.3, ego_index=2, cfg=cfg)
+    dec = _make_decoder(sd, cfg, use_cuda_graph=True)
+    with pytest.raises(RuntimeError, match='ran out of rows'):
+        dec.inference(scene, scene['map_enc'])
+    dec.cfg.insert_row_reserve = 128
+    dec._host_cache = None
+    out = dec.inference(scene, scene['map_enc'])
+    dec.close()
+    assert out['pos_a'].shape[0] > 60
