@@ -71,6 +71,7 @@ __device__ __forceinline__ void gemv_row(const float *xs, const float *__restric
                                          const float *__restrict__ bias, int N, float *out) {
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
         float acc = 0.f;
+#pragma unroll 8
         for (int k4 = 0; k4 < K4; ++k4) {
             const float4 w = ldg4(wp + ((size_t)k4 * ldn + n) * 4);
             const float4 x = ld4(xs + 4 * k4);
@@ -111,18 +112,34 @@ __global__ void __launch_bounds__(NT) k_ins_begin(const DecState s, const InsSta
         if (b == 0) { q.flags[0] = 1; q.flags[1] = 0; }
     }
     for (int i = threadIdx.x; i < s.n_rows[b]; i += NT) s.hv_src[b * s.cap + i] = -1;   // vectors were rebuilt (:2265)
-    if (warp != 0) return;
     const int re = b * s.cap + s.ego_row[b];
     const float px = s.pos[((size_t)re * T + col) * 2], py = s.pos[((size_t)re * T + col) * 2 + 1];
     const float hd = s.head[(size_t)re * T + col];
     const float hx = cosf(hd), hy = sinf(hd);
     const int pt0 = s.pt_ptr[b], pt1 = s.pt_ptr[b + 1];
-    int cnt = 0;
-    for (int p0 = pt0; p0 < pt1 && cnt < SEED_MAP_MAX; p0 += 32) {
+    // every warp scans a contiguous eighth of the scene's map tokens; counts first, then an ordered write
+    __shared__ int s_wcnt[NWARP];
+    const int per = ((pt1 - pt0 + NWARP - 1) / NWARP + 31) & ~31;
+    const int w0 = pt0 + warp * per, w1 = min(pt1, w0 + per);
+    int mine = 0;
+    for (int p0 = w0; p0 < w1; p0 += 32) {
+        const int p = p0 + lane;
+        bool ok = false;
+        if (p < w1) {
+            const float dx = __fsub_rn(s.pt_pos[(size_t)p * 2], px), dy = __fsub_rn(s.pt_pos[(size_t)p * 2 + 1], py);
+            ok = dist2(dx, dy) < q.r_seed2;
+        }
+        mine += __popc(__ballot_sync(0xffffffffu, ok));
+    }
+    if (lane == 0) s_wcnt[warp] = mine;
+    __syncthreads();
+    int cnt = 0, total = 0;
+    for (int w = 0; w < NWARP; ++w) { if (w < warp) cnt += s_wcnt[w]; total += s_wcnt[w]; }
+    for (int p0 = w0; p0 < w1; p0 += 32) {
         const int p = p0 + lane;
         float dx = 0.f, dy = 0.f;
         bool ok = false;
-        if (p < pt1) {
+        if (p < w1) {
             dx = __fsub_rn(s.pt_pos[(size_t)p * 2], px);
             dy = __fsub_rn(s.pt_pos[(size_t)p * 2 + 1], py);
             ok = dist2(dx, dy) < q.r_seed2;
@@ -136,9 +153,9 @@ __global__ void __launch_bounds__(NT) k_ins_begin(const DecState s, const InsSta
             q.ps_raw[(size_t)slot * 3 + 1] = angle_between(hx, hy, dx, dy);
             q.ps_raw[(size_t)slot * 3 + 2] = wrap_angle(__fsub_rn(s.pt_ori[p], hd));
         }
-        cnt = min(SEED_MAP_MAX, cnt + __popc(mask));
+        cnt += __popc(mask);
     }
-    if (lane == 0) q.ps_cnt[b] = cnt;
+    if (threadIdx.x == 0) q.ps_cnt[b] = min(total, SEED_MAP_MAX);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -172,10 +189,26 @@ __global__ void __launch_bounds__(NT) k_seed_prepare(const SeedPrepArgs a) {
     }
     __syncthreads();
     // ---- first Linear of seed_agent_occ_embed on a 0/1 vector: bias + the columns of the occupied cells ----
+    __shared__ int s_cells[MAX_CAP];                    // occupied cells, ascending
+    __shared__ int s_ncell;
+    if (warp == 0) {
+        int cnt = 0;
+        for (int g0 = 0; g0 < G; g0 += 32) {
+            const int g = g0 + lane;
+            const bool ok = g < G && occ[g] != 0.f;
+            const unsigned mask = __ballot_sync(0xffffffffu, ok);
+            if (ok) s_cells[cnt + __popc(mask & lanemask_lt())] = g;
+            cnt += __popc(mask);
+        }
+        if (lane == 0) s_ncell = cnt;
+    }
+    __syncthreads();
     if (tid < 128) {
         float acc = 0.f;
-        for (int g = 0; g < G; ++g)
-            if (occ[g] != 0.f) acc += __ldg(a.occ_embed.w0 + ((size_t)(g >> 2) * 128 + tid) * 4 + (g & 3));
+        for (int k = 0; k < s_ncell; ++k) {
+            const int g = s_cells[k];
+            acc += __ldg(a.occ_embed.w0 + ((size_t)(g >> 2) * 128 + tid) * 4 + (g & 3));
+        }
         sh[tid] = acc + __ldg(a.occ_embed.b0 + tid);
     }
     __syncthreads();
