@@ -1,17 +1,15 @@
-// Operator kernels: the reference's layers.py modules as sm_100a CUDA.
+// Operator kernels: the reference's layers.py modules as sm_100a CUDA (the AttentionLayer itself lives in layer.cuh).
 //
-//   k_node_update   AttentionLayer minus the edge part (layers.py:61-76, 94-113): the "post" half of one layer
-//                   (relative-value projection, gate, to_out, LayerNorm, FFN) fused with the "pre" half of the
-//                   next one (LayerNorm, q/s/k/v projections, relative-query fold), one CTA per tile of rows.
-//   k_edge_attn     AttentionLayer.message + segment softmax + aggregation (layers.py:78-92), one warp per
-//                   destination row, K/V rows gathered from the KV caches.
 //   k_kv_project    LayerNorm + to_k/to_v of source-only nodes (map tokens; layers.py:65-71, 107-108).
-//   k_fourier       FourierEmbedding (layers.py:142-160) over edge/agent tiles, output optionally standardised.
-//   k_mlp_embed     MLPEmbedding (layers.py:170-189), optionally gathering the 4x128 fusion input.
+//   k_fourier       FourierEmbedding (layers.py:142-160) over tiles of edge slots, several embeddings per launch, output
+//                   optionally standardised (the layer-independent part of every attn_prenorm_r).
+//   k_mlp_embed     MLPEmbedding (layers.py:170-189).
 //   k_heads         MLPLayer token head + per-slice top-k / softmax statistics, state head (layers.py:206-215,
 //                   agent_decoder.py:2160-2167).
+//   k_mlp_layer     generic MLPLayer (insertion-stage heads, operator-level parity).
+// All of them stream their weights through the shared-memory ring of stream.cuh (cp.async.bulk + mbarriers).
 //
-// Algebra used by node_update/edge_attn: with rn_e = LN_r(r_e) = g*rhat_e + b,
+// Algebra shared with layer.cuh: with rn_e = LN_r(r_e) = g*rhat_e + b,
 //   q_h.(k_j,h + Wkr_h rn_e)       = q_h.k_j,h + (g * Wkr_h^T q_h).rhat_e + const(i,h)   (const drops out of softmax)
 //   sum_e a_e (v_j + Wvr rn_e + b) = sum_e a_e v_j + Wvr_h (g * sum_e a_e rhat_e + b * sum_e a_e) + bvr * sum_e a_e
 // so the per-edge 128x128 projections become per-node ones and edges only see dot products with rhat.

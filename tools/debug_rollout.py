@@ -108,9 +108,11 @@ def main():
         type_a = ag['type'][filt].long(); shp = ag['shape'][filt][:, cfg.num_historical_steps - 1]
         cat = sd['type_a_emb.weight'][type_a] + mlp_embedding(sd, 'shape_emb', shp)
         rep('cat_tab', dec.debug_read('cat_tab', (R + 1, 128))[:A], cat.numpy())
-        rep('cat_idx', dec.debug_read('cat_idx', (R,), np.int32)[:A], np.arange(A), 0)
-        xa = fourier_embedding(sd, 'x_a_emb', feat, cat)
-        rep('xa', dec.debug_read('xa', (R, 128))[:A], xa.numpy(), 1e-3)
+        # generated columns carry the seed-type / 0.1-shape categorical row
+        rep('cat_idx', dec.debug_read('cat_idx', (R,), np.int32)[:A], np.full(A, R), 0)
+        cat_seed = sd['type_a_emb.weight'][3][None] + mlp_embedding(sd, 'shape_emb', torch.full((1, 3), 0.1))
+        xa = fourier_embedding(sd, 'x_a_emb', feat, cat_seed.expand(A, 128))
+        # (x_a_emb itself stays on chip inside k_embed_column; it is checked through the fused feature below)
         vocab = torch.stack([ag['trajectory_token_veh'], ag['trajectory_token_ped'], ag['trajectory_token_cyc']])
         tok_row = dec.debug_read('tok_row', (R,), np.int32)[:A]
         rep('tok_row', tok_row, (type_a * 2050 + torch.from_numpy(token[:A, nxt]).long()).numpy(), 0)
