@@ -54,7 +54,7 @@ __device__ __forceinline__ unsigned lanemask_lt() { return (1u << (threadIdx.x &
 // the first max_num_neighbors sources by ascending index; edges ordered by destination then source.
 // Slots: temporal r*W + k, map r*max_m + k, agent r*cap + k (k-th neighbour by ascending source row).
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT) k_edge_build(const DecState s) {
+__global__ void __launch_bounds__(NT) k_edge_build(const DecState s, int col_add) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gw = blockIdx.x * NWARP + warp;
     const int r = gw / 3, kind = gw - 3 * r;
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(NT) k_edge_build(const DecState s) {
     if (r >= R) return;
     const int b = r / s.cap, i = r - b * s.cap, n = s.n_rows[b];
     if (i >= n) return;
-    const int col = *s.col, T = s.T;
+    const int col = *s.col + col_add, T = s.T;
     const int r0 = b * s.cap;
     const float px = s.pos[((size_t)r * T + col) * 2], py = s.pos[((size_t)r * T + col) * 2 + 1];
     const float hd = s.head[(size_t)r * T + col];

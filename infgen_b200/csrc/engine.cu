@@ -140,6 +140,9 @@ struct infgen_engine {
     bool profile = false;
     std::vector<ProfRec> prof;
     cudaStream_t stream = nullptr, own_stream = nullptr;
+    cudaStream_t side_stream = nullptr;                 // edges of the next column, concurrent with its embedding
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool early_edges = false;                           // motion-only engines build the next column's edges early
     float *blob = nullptr;
     float *cs_blob = nullptr;                           // cluster-sliced AttentionLayer chunks (layer.cuh)
     std::unordered_map<std::string, std::pair<const float *, const float *>> cs;   // layer -> (post, pre) chunks
@@ -709,12 +712,13 @@ static int run_insertion(infgen_engine *e) {
     return 0;
 }
 
-static int enqueue_iteration(infgen_engine *e, int trace_iter) {
+// edges whose destination is column col + col_add and their relative embeddings
+static int enqueue_edges(infgen_engine *e, int col_add) {
     DecState &s = e->st;
     const int R = e->R;
     {
         ProfScope ps(e, KC_EDGE_BUILD);
-        k_edge_build<<<(R * 3 + NWARP - 1) / NWARP, NT, 0, e->stream>>>(s);
+        k_edge_build<<<(R * 3 + NWARP - 1) / NWARP, NT, 0, e->stream>>>(s, col_add);
     }
     CKL(); count_launch(e);
     FourierArgs fj[3];
@@ -728,7 +732,16 @@ static int enqueue_iteration(infgen_engine *e, int trace_iter) {
     fj[2].normalize = 1; fj[2].dim = 3;
     fj[2].n_slots = R * s.max_m; fj[2].cnt = s.m_cnt; fj[2].stride = s.max_m; fj[2].raw = s.m_raw; fj[2].w = e->f_m;
     fj[2].out = fbuf(e, "rhat_m");
-    RET(launch_fourier(e, fj, 3, KC_FOURIER));
+    return launch_fourier(e, fj, 3, KC_FOURIER);
+}
+
+// One decode iteration.  With the insertion stage enabled the edges of column cur are built first (rows may have been
+// appended since the last iteration).  Motion-only engines build the edges of the NEXT column right after the advance,
+// on a side stream, concurrently with that column's embedding (8 CTAs): both only depend on the new poses.
+static int enqueue_iteration(infgen_engine *e, int trace_iter) {
+    DecState &s = e->st;
+    const int R = e->R;
+    if (!e->early_edges) RET(enqueue_edges(e, 0));
     RET(enqueue_layers(e, true, trace_iter));
     HeadArgs ha;
     memset(&ha, 0, sizeof(ha));
@@ -750,7 +763,21 @@ static int enqueue_iteration(infgen_engine *e, int trace_iter) {
         k_advance<<<(R + NWARP - 1) / NWARP, NT, 0, e->stream>>>(s);
     }
     CKL(); count_launch(e);
-    RET(enqueue_embed_column(e, 1));
+    if (e->early_edges && !e->profile) {
+        cudaStream_t main = e->stream;
+        CK(cudaEventRecord(e->ev_fork, main));
+        CK(cudaStreamWaitEvent(e->side_stream, e->ev_fork, 0));
+        e->stream = e->side_stream;
+        int rc = enqueue_edges(e, 1);
+        e->stream = main;
+        RET(rc);
+        CK(cudaEventRecord(e->ev_join, e->side_stream));
+        RET(enqueue_embed_column(e, 1));
+        CK(cudaStreamWaitEvent(main, e->ev_join, 0));
+    } else {
+        RET(enqueue_embed_column(e, 1));
+        if (e->early_edges) RET(enqueue_edges(e, 1));
+    }
     {
         ProfScope ps(e, KC_MISC);
         k_next_iter<<<1, 1, 0, e->stream>>>(s.col, s.iter);
@@ -875,6 +902,10 @@ int32_t infgen_create(const infgen_config *cfg, const float *weights, int64_t n_
     e->cfg = *cfg;
     CK(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
     e->stream = e->own_stream;
+    CK(cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+    e->early_edges = cfg->disable_insertion != 0 && !getenv("INFGEN_NO_EARLY_EDGES");   // (debug tools compare per-iteration edges)
     CK(cudaMalloc(&e->blob, (size_t)g_total * sizeof(float)));
     CK(cudaMemcpyAsync(e->blob, weights, (size_t)g_total * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     CK(cudaMalloc(&e->grid_cells, (size_t)cfg->grid_size * 2 * sizeof(float)));
@@ -940,6 +971,9 @@ int32_t infgen_destroy(infgen_engine *e) {
     cudaFree(e->blob); cudaFree(e->cs_blob); cudaFree(e->grid_cells); cudaFree(e->vocab); cudaFree(e->tok_tab); cudaFree(e->grid_tab);
     cudaFree(e->d_err); cudaFree(e->seed_feat);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    if (e->side_stream) cudaStreamDestroy(e->side_stream);
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_join) cudaEventDestroy(e->ev_join);
     delete e;
     return 0;
 }
@@ -1213,6 +1247,7 @@ int32_t infgen_prefill(infgen_engine *e) {
         CKL(); count_launch(e);
     }
     RET(enqueue_embed_column(e, 0));
+    if (e->early_edges) RET(enqueue_edges(e, 0));
     e->prefilled = 1;
     return 0;
 }

@@ -1,6 +1,7 @@
 """Step the CUDA engine one iteration at a time and compare every intermediate buffer with the oracle trace.
 Debug aid (run on the GPU box):  python tools/debug_rollout.py [case] [max_iters]"""
 import os, sys
+os.environ['INFGEN_NO_EARLY_EDGES'] = '1'     # keep the edge buffers of iteration t readable after iteration t
 import numpy as np
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
