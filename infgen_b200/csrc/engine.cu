@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "ops.cuh"
 #include "layer.cuh"
+#include "fourier_tc.cuh"
 #include "decode.cuh"
 #include "insert.cuh"
 
@@ -145,6 +146,9 @@ struct infgen_engine {
     bool early_edges = false;                           // motion-only engines build the next column's edges early
     float *blob = nullptr;
     float *cs_blob = nullptr;                           // cluster-sliced AttentionLayer chunks (layer.cuh)
+    std::unordered_map<std::string, FourierW> fourier_cache;
+    std::vector<float *> wimgs;                         // FourierEmbedding tensor-core weight images (fourier_tc.cuh)
+    bool fourier_tc = true;                             // INFGEN_FOURIER=ffma selects the FFMA row-tile kernel instead
     std::unordered_map<std::string, std::pair<const float *, const float *>> cs;   // layer -> (post, pre) chunks
     float *grid_cells = nullptr, *vocab = nullptr;
     float *tok_tab = nullptr, *grid_tab = nullptr;      // [3][V+2][128], [G+1][128]
@@ -280,6 +284,9 @@ static int build_cluster_weights(infgen_engine *e, const float *hw) {
     return 0;
 }
 static FourierW make_fourier(infgen_engine *e, const std::string &p, int d) {
+    const std::string key = p + "#" + std::to_string(d);
+    auto hit = e->fourier_cache.find(key);
+    if (hit != e->fourier_cache.end()) return hit->second;
     FourierW w;
     memset(&w, 0, sizeof(w));
     w.freqs = W(e, p + ".freqs");
@@ -290,6 +297,22 @@ static FourierW make_fourier(infgen_engine *e, const std::string &p, int d) {
     }
     w.out_ln_g = W(e, p + ".out_ln.g"); w.out_ln_b = W(e, p + ".out_ln.b");
     w.w_out = W(e, p + ".w_out"); w.b_out = W(e, p + ".b_out");
+    // tensor-core image: the (2 d + 1) packed matrices split into hi / lo TF32 chunks, in the GEMM order of k_fourier_tc
+    float *img = nullptr;
+    if (cudaMalloc(&img, ftc::wimg_floats(d) * sizeof(float)) != cudaSuccess) {
+        fprintf(stderr, "infgen_b200: cudaMalloc of a FourierEmbedding weight image failed\n");
+        abort();
+    }
+    e->wimgs.push_back(img);
+    int jt[9], jd[9];
+    const int nj = ftc::job_list(d, jt, jd);
+    for (int j = 0; j < nj; ++j) {
+        const float *src = jt[j] == 0 ? w.w0[jd[j]] : (jt[j] == 1 ? w.w3[jd[j]] : w.w_out);
+        k_wimg_split<<<64, 256, 0, e->stream>>>(src, img + (size_t)j * 4 * ftc::CHUNK);
+    }
+    for (int i = 0; i < d; ++i) k_wimg_xrow<<<1, 128, 0, e->stream>>>(w.w0[i], img + (size_t)nj * 4 * ftc::CHUNK + (size_t)i * 128);
+    w.wimg = img;
+    e->fourier_cache[key] = w;
     return w;
 }
 static MlpEmbW make_mlp_emb(infgen_engine *e, const std::string &p) {
@@ -380,24 +403,31 @@ static PreArgs make_pre(const AttnW &w, bool pre_kv, float *kv_out, bool kv_ring
     p.to_global = to_global ? 1 : 0;
     return p;
 }
-static int fourier_tiles(const FourierArgs &a) { return (a.n_slots + FM - 1) / FM; }
-// up to three FourierEmbeddings in one launch
+// up to three FourierEmbeddings in one launch.  Embeddings without a categorical seed run on the tensor cores
+// (k_fourier_tc, tiles of 128 slots); the FFMA row-tile kernel (tiles of 16) serves the rest and INFGEN_FOURIER=ffma.
 static int launch_fourier(infgen_engine *e, const FourierArgs *jobs, int n_jobs, int cls = KC_MISC) {
     FourierBatch fb;
     memset(&fb, 0, sizeof(fb));
-    int tiles = 0;
+    bool tc = e->fourier_tc;
     for (int j = 0; j < n_jobs; ++j) {
         if (jobs[j].dim < 1 || jobs[j].dim > 4) return fail(INFGEN_ERR_INVALID_ARG, "FourierEmbedding input_dim %d unsupported", jobs[j].dim);
-        if (fourier_tiles(jobs[j]) == 0) continue;
+        if (jobs[j].cat_tab || !jobs[j].w.wimg) tc = false;
+    }
+    const int tm = tc ? ftc::TM : FM;
+    int tiles = 0;
+    for (int j = 0; j < n_jobs; ++j) {
+        const int t = (jobs[j].n_slots + tm - 1) / tm;
+        if (t == 0) continue;
         fb.job[fb.n_jobs] = jobs[j];
         fb.tile0[fb.n_jobs] = tiles;
-        tiles += fourier_tiles(jobs[j]);
+        tiles += t;
         fb.n_jobs++;
     }
     fb.tile0[fb.n_jobs] = tiles;
     if (tiles == 0) return 0;
     ProfScope ps(e, cls);
-    k_fourier<<<tiles, NT_S, FOURIER_SMEM, e->stream>>>(fb);
+    if (tc) k_fourier_tc<<<tiles, ftc::THREADS, ftc::SMEM, e->stream>>>(fb);
+    else k_fourier<<<tiles, NT_S, FOURIER_SMEM, e->stream>>>(fb);
     CKL();
     count_launch(e);
     return 0;
@@ -949,6 +979,11 @@ int32_t infgen_create(const infgen_config *cfg, const float *weights, int64_t n_
     CK(cudaFuncSetAttribute(k_layer<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LayerSmem<4>::BYTES));
     CK(cudaFuncSetAttribute(k_layer<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LayerSmem<8>::BYTES));
     CK(cudaFuncSetAttribute(k_fourier, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FOURIER_SMEM));
+    CK(cudaFuncSetAttribute(k_fourier_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ftc::SMEM));
+    {
+        const char *fm = getenv("INFGEN_FOURIER");
+        e->fourier_tc = !(fm && !strcmp(fm, "ffma"));
+    }
     CK(cudaFuncSetAttribute(k_mlp_embed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mlp_embed_smem(128)));
     CK(cudaFuncSetAttribute(k_embed_column, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COLEMB_SMEM));
     CK(cudaFuncSetAttribute(k_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEADS_SMEM));
@@ -970,6 +1005,7 @@ int32_t infgen_destroy(infgen_engine *e) {
         if (kv.second.p) cudaFree(kv.second.p);
     cudaFree(e->blob); cudaFree(e->cs_blob); cudaFree(e->grid_cells); cudaFree(e->vocab); cudaFree(e->tok_tab); cudaFree(e->grid_tab);
     cudaFree(e->d_err); cudaFree(e->seed_feat);
+    for (float *p : e->wimgs) cudaFree(p);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->side_stream) cudaStreamDestroy(e->side_stream);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);

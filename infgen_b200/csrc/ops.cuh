@@ -39,6 +39,7 @@ struct FourierW {              // one FourierEmbedding
     const float *freqs;        // [D][64]
     const float *w0[4], *b0[4], *ln_g[4], *ln_b[4], *w3[4], *b3[4];
     const float *out_ln_g, *out_ln_b, *w_out, *b_out;
+    const float *wimg;         // tensor-core weight image (fourier_tc.cuh): hi/lo TF32 chunks in consumption order
 };
 
 struct MlpEmbW {               // one MLPEmbedding

@@ -40,14 +40,17 @@ def test_mlp_embedding(dec_and_sd, name, dim):
     _close(ops.mlp_embedding(dec, name, x), mlp_embedding(sd, name, x), name)
 
 
-@pytest.mark.parametrize('name,dim,with_cat', [('x_a_emb', 2, True), ('r_t_emb', 4, False), ('r_pt2a_emb', 3, False),
-                                              ('r_a2a_emb', 3, False)])
-def test_fourier_embedding(dec_and_sd, name, dim, with_cat):
+@pytest.mark.parametrize('name,dim,with_cat,n', [('x_a_emb', 2, True, 75), ('r_t_emb', 4, False, 75),
+                                                ('r_pt2a_emb', 3, False, 75), ('r_a2a_emb', 3, False, 75),
+                                                ('x_a_emb', 2, False, 128), ('r_t_emb', 4, False, 300),
+                                                ('r_a2a_emb', 3, False, 1000)])
+def test_fourier_embedding(dec_and_sd, name, dim, with_cat, n):
+    """FourierEmbedding (layers.py:142-160).  Without a categorical seed the tcgen05 kernel (tiles of 128 slots) runs;
+    75 / 300 / 1000 rows exercise partial tiles, 128 an exact one."""
     from infgen_b200 import ops
     from oracle.agent_decoder_oracle import fourier_embedding
     dec, sd = dec_and_sd
     g = torch.Generator().manual_seed(2)
-    n = 75
     x = torch.randn(n, dim, generator=g)
     x[:, 0] = x[:, 0].abs() * 30.0          # distances up to tens of metres
     x[::7] = -2.0                            # the invalid sentinels of agent_decoder.py:595-601
