@@ -308,7 +308,7 @@ static FourierW make_fourier(infgen_engine *e, const std::string &p, int d) {
     const int nj = ftc::job_list(d, jt, jd);
     for (int j = 0; j < nj; ++j) {
         const float *src = jt[j] == 0 ? w.w0[jd[j]] : (jt[j] == 1 ? w.w3[jd[j]] : w.w_out);
-        k_wimg_split<<<64, 256, 0, e->stream>>>(src, img + (size_t)j * 4 * ftc::CHUNK);
+        k_wimg_split<<<64, 256, 0, e->stream>>>(src, img + (size_t)j * 4 * ftc::CHUNK, jt[j] == 0 ? 1 : 0);
     }
     for (int i = 0; i < d; ++i) k_wimg_xrow<<<1, 128, 0, e->stream>>>(w.w0[i], img + (size_t)nj * 4 * ftc::CHUNK + (size_t)i * 128);
     w.wimg = img;
@@ -402,6 +402,18 @@ static PreArgs make_pre(const AttnW &w, bool pre_kv, float *kv_out, bool kv_ring
     p.w = w.cs_pre; p.pre_kv = pre_kv ? 1 : 0; p.kv_out = kv_out; p.kv_ring = kv_ring ? 1 : 0; p.col_add = col_add;
     p.to_global = to_global ? 1 : 0;
     return p;
+}
+// watchdog record of k_fourier_tc (fourier_tc.cuh:ftc_wait): non-zero = an mbarrier wait timed out
+static int check_ftc_watchdog() {
+    int h[8] = {0};
+    CK(cudaMemcpyFromSymbol(h, g_ftc_hang, sizeof(h)));
+    if (h[0]) {
+        int z[8] = {0};
+        cudaMemcpyToSymbol(g_ftc_hang, z, sizeof(z));
+        return fail(INFGEN_ERR_CUDA, "k_fourier_tc: %d mbarrier waits timed out (first code*1000+thread per class: weights %d, "
+                    "mma/A %d, mma/B %d, A stage %d, accumulator %d)", h[0], h[1], h[2], h[3], h[4], h[5]);
+    }
+    return 0;
 }
 // up to three FourierEmbeddings in one launch.  Embeddings without a categorical seed run on the tensor cores
 // (k_fourier_tc, tiles of 128 slots); the FFMA row-tile kernel (tiles of 16) serves the rest and INFGEN_FOURIER=ffma.
@@ -1366,6 +1378,7 @@ int32_t infgen_read(infgen_engine *e, const infgen_outputs *o, int32_t loc) {
         int err = 0;
         CK(cudaMemcpy(&err, e->d_err, sizeof(int), cudaMemcpyDeviceToHost));
         if (err) return fail(INFGEN_ERR_CAPACITY, "an attention row exceeded its edge capacity");
+        RET(check_ftc_watchdog());
     }
     return 0;
 }
@@ -1407,6 +1420,13 @@ int64_t infgen_debug_read(infgen_engine *e, const char *name, void *dst, int64_t
     return n;
 }
 
+#ifdef INFGEN_FTC_TRACE
+int32_t infgen_debug_ftc_trace(long long *dst /* [2][3][64] */) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(dst, g_ftc_trace, sizeof(long long) * 2 * 3 * 64);
+    return 0;
+}
+#endif
 #ifdef INFGEN_WS_TRACE
 int32_t infgen_debug_ws_trace(long long *dst /* [2][256] */, int32_t *n /* [2] */) {
     cudaDeviceSynchronize();
@@ -1526,6 +1546,7 @@ int32_t infgen_op_fourier_embedding(infgen_engine *e, const char *name, const fl
     RET(launch_fourier(e, &fa, 1));
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaMemcpy(out, d_out, (size_t)n * 128 * sizeof(float), cudaMemcpyDeviceToHost));
+    RET(check_ftc_watchdog());
     return 0;
 }
 

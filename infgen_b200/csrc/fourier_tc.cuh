@@ -2,7 +2,8 @@
 // 3xTF32 error-compensated split, accumulators in TMEM.
 //
 // One CTA embeds a tile of 128 edge slots.  Every Linear of the module is a [128 slots x 128] x [128 x 128] GEMM:
-//     per input dim d:  G1_d = [cos(2 pi f x_d) | sin(2 pi f x_d)] W0_d[0:128]     (+ x_d W0_d[128] + b0_d in the epilogue)
+//     per input dim d:  G1_d = [cos(2 pi f x_d) | sin(2 pi f x_d)] W0_d[0:128]     (+ x_d W0_d[128] + b0_d in the epilogue;
+//                              K permuted so that a 32-k chunk holds cos and sin of the same 16 frequencies)
 //                       G2_d = relu(LN(G1_d)) W3_d, summed over d IN TMEM (the accumulator is simply not cleared)
 //     output:           G3   = relu(LN(sum_d G2_d + b3_d)) Wout + bout             (optionally standardised -> rhat)
 //
@@ -10,19 +11,28 @@
 // x = hi + lo (both TF32, cvt.rna) and D += A_lo B_hi + A_hi B_lo + A_hi B_hi (fp32 accumulate); measured error of this
 // scheme on B200: 1.4e-6 against fp64 for K = 64, |D| <= 2.3 (tools/probe/umma_probe.cu), the same as an fp32 FMA chain.
 //
-// Operand layout (measured in the probe): NO-swizzle K-major core matrices, element (row r, k) of a [128 x 32] chunk at
-// float offset (k / 4) * 512 + r * 4 + (k % 4), i.e. LBO (K direction) = 2048 B, SBO (8-row groups) = 128 B.  For the
-// weights this is exactly the packed [K/4][128][4] layout of the blob, so the B images are the blob matrices split into
-// hi / lo and cut into 32-k chunks of [hi 16 KB | lo 16 KB], stored in consumption order: one 32 KB cp.async.bulk each.
+// Operands.  A (features / normalised activations) lives in TENSOR MEMORY: tcgen05.mma with the A matrix in TMEM, lane =
+// row, one 32-bit column per k; four 64-column stages [hi 32 | lo 32], written by the row threads with tcgen05.st - no
+// shared-memory staging, no proxy fence.  B (weights) comes from shared memory in the NO-swizzle K-major core-matrix
+// layout measured in the probe: element (n, k) of a [128 x 32] chunk at float offset (k / 4) * 512 + n * 4 + (k % 4), i.e.
+// LBO (K direction) = 2048 B, SBO (8-row groups) = 128 B.  That is exactly the packed [K/4][128][4] layout of the weight
+// blob, so the B images are the blob matrices split into hi / lo and cut into 32-k chunks of [hi 16 KB | lo 16 KB], stored
+// in consumption order: one 32 KB cp.async.bulk per chunk into a 6-stage ring.
+// TMEM columns: [0,128) G1 / G3 accumulator, [128,256) dim-sum accumulator, [256,512) the four A stages.
 //
-// Roles (320 threads):
-//   warps 0-7  row threads: thread (r = 32 (w & 3) + lane, half h = w >> 2) owns slot r and 64 of its 128 columns (TMEM
-//              lanes are only visible to warps with the same w & 3).  They generate the Fourier features and run the
-//              epilogues (TMEM -> registers -> bias / LayerNorm / ReLU -> hi/lo A chunks in the A ring).
-//   warp 8     one lane issues the MMAs (12 per chunk) and commits to the ring / accumulator mbarriers.
-//   warp 9     streams the weight chunks through the B ring (one lane per stage).
-// G1_{d+1} is issued before the epilogue of G1_d (two G1 accumulators), so the tensor core works while the row threads
-// normalise; the three accumulators take 384 TMEM columns (512 allocated).
+// Roles (576 threads):
+//   warp 0     MMA issuer (12 tcgen05.mma per chunk + commits to the ring / accumulator mbarriers).  It is warp 0 - the
+//              oldest warp of its scheduler partition - and runs in uniform control flow with elect.sync, because as the
+//              youngest warp, issuing from one divergent lane, it was starved by the row warps (110-145 cycles per MMA
+//              against 68 at peak; 88-99 now).
+//   warps 1-16 row threads: thread (r = 32 (w & 3) + lane, quarter qd = (w - 1) >> 2) owns slot r and 32 of its 128
+//              columns - one 32-k chunk of every A operand (TMEM lanes are only visible to warps with the same w & 3).
+//              They generate the Fourier features and run the epilogues (TMEM -> registers -> bias / LayerNorm / ReLU
+//              -> hi/lo split -> TMEM).  This part, not the tensor core, bounds the kernel (sincosf, LayerNorm).
+//   warp 17    streams the weight chunks through the B ring.
+// G1_{d+1} is issued as soon as the row threads have loaded the result of G1_d into registers (acc_free), so the tensor
+// core works while they normalise.  Every mbarrier wait is bounded (ftc_wait): a protocol bug becomes an error code, not
+// a hung GPU.
 #pragma once
 #include "common.cuh"
 #include "ops.cuh"
@@ -30,17 +40,23 @@
 namespace infgen {
 namespace ftc {
 constexpr int TM = 128;                          // slots per tile
-constexpr int NA = 3, NB = 3;                    // ring depths (32 KB stages)
+// A operands live in TMEM (tcgen05.mma with the A matrix in tensor memory): 4 stages of 64 columns [hi 32 | lo 32], one
+// per quarter of the row threads.  NA must be 4: quarter q then always writes A stage q, so every parity wait is exactly
+// one phase ahead of the last phase that thread observed (with a 3-deep ring a quarter that skipped a stage's previous
+// use raced two phases ahead and mbarrier.try_wait.parity aliased - found by the watchdog below).
+// B (weights): NB stages of 32 KB in shared memory.
+constexpr int NA = 4, NB = 6;
+static_assert(NA == 4, "A-ring protocol: one stage per quarter");
+constexpr uint32_t TC_ACC_H = 0, TC_ACC_S = 128, TC_A = 256;    // TMEM columns: G1/G3 accumulator, dim-sum accumulator, A stages
 constexpr int CHUNK = 8192;                      // floats per chunk: [hi 4096 | lo 4096]
-constexpr int RT = 256;                          // row threads
+constexpr int RT = 512;                          // row threads
 constexpr int THREADS = RT + 64;
-constexpr int SM_A = 0;
-constexpr int SM_B = SM_A + NA * CHUNK;
-constexpr int SM_EX = SM_B + NB * CHUNK;         // [2 buffers][2 halves][128] LayerNorm partials
-constexpr int SM_RAW = SM_EX + 512;              // [128][4]
+constexpr int SM_B = 0;
+constexpr int SM_EX = SM_B + NB * CHUNK;         // [2 buffers][4 quarters][128] LayerNorm partials
+constexpr int SM_RAW = SM_EX + 1024;              // [128][4]
 constexpr int SM_VALID = SM_RAW + 512;           // [128] int
-constexpr int SM_BAR = SM_VALID + 128;           // full_a[NA] empty_a[NA] full_b[NB] empty_b[NB] g1[4] g2 g3 (uint64 each)
-constexpr int N_BAR = 2 * NA + 2 * NB + 6;
+constexpr int SM_BAR = SM_VALID + 128;           // full_a[NA] empty_a[NA] full_b[NB] empty_b[NB] g1[4] g2 g3 acc_free (uint64 each)
+constexpr int N_BAR = 2 * NA + 2 * NB + 7;
 constexpr int SM_TMEM = SM_BAR + 2 * N_BAR;
 constexpr int SM_FLOATS = SM_TMEM + 4;
 constexpr size_t SMEM = (size_t)SM_FLOATS * sizeof(float);
@@ -74,6 +90,32 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
         "l"(da), "l"(db), "r"(ftc::IDESC), "r"(accumulate)
         : "memory");
 }
+// A from tensor memory (lane = row, one 32-bit column per k), B from shared memory.  Called by the WHOLE warp with
+// warp-uniform operands; one elected lane issues (keeps the issue loop in uniform control flow: no per-lane waterfall).
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, pe;\n\telect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(db), "r"(ftc::IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t *b) {
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(smem_u32(b))
+        : "memory");
+}
+// 32 consecutive columns of this thread's TMEM lane <- registers
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float *v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+        "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]), "f"(v[10]),
+        "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]), "f"(v[16]), "f"(v[17]), "f"(v[18]), "f"(v[19]), "f"(v[20]),
+        "f"(v[21]), "f"(v[22]), "f"(v[23]), "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]), "f"(v[28]), "f"(v[29]), "f"(v[30]),
+        "f"(v[31])
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t *b) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(b)) : "memory");
 }
@@ -94,18 +136,66 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// x = hi + lo with hi = x rounded to TF32 (nearest, ties away: integer add + mask, full-rate ALU instead of cvt.rna);
+// lo = x - hi is exact in fp32 and the tensor core ignores its low 13 mantissa bits (2^-21 |x| at most)
+__device__ __forceinline__ void split_tf32x2(float x, float &hi, float &lo) {
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+    lo = x - hi;
+}
 __device__ __forceinline__ float tf32_rna(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
 
-// weight image builder: 4 chunks of one packed [32 k4][128][4] matrix -> [hi | lo] chunks
-__global__ void k_wimg_split(const float *__restrict__ src, float *__restrict__ dst) {
+// Bounded mbarrier wait: a protocol bug must not hang the GPU.  After ~10 ms (2e7 cycles) the wait gives up, records
+// the first (code, thread) of each wait class in g_ftc_hang and execution continues with whatever is there, so the kernel always terminates;
+// the engine reports a non-zero g_ftc_hang[0] as an error (infgen_op_fourier_embedding, tests).
+__device__ int g_ftc_hang[8];
+template <bool BACKOFF = false>
+__device__ __forceinline__ void ftc_wait(uint64_t *b, uint32_t parity, int code) {
+    const uint32_t addr = smem_u32(b);
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (BACKOFF) __nanosleep(64);             // pollers must not take issue slots from the MMA warp
+        if (clock64() - t0 > 20000000ll) {
+            atomicAdd(&g_ftc_hang[0], 1);
+            atomicCAS(&g_ftc_hang[code / 100], 0, code * 1000 + (int)threadIdx.x);   // first of each class: code, thread
+            return;
+        }
+    }
+}
+
+#ifdef INFGEN_FTC_TRACE
+// debug: clock64 stamps of [traced block 0/1][stream: 0 = row thread 0, 1 = MMA lane, 2 = row thread 128][64]
+__device__ long long g_ftc_trace[2][3][64];
+#define FTC_STAMP(stream)                                                                                     \
+    do {                                                                                                      \
+        if (trace_blk >= 0 && trace_n < 64) g_ftc_trace[trace_blk][stream][trace_n++] = clock64();           \
+    } while (0)
+#else
+#define FTC_STAMP(stream) do {} while (0)
+#endif
+
+// weight image builder: 4 chunks of one packed [32 k4][128][4] matrix -> [hi | lo] chunks.  fourier_order: the K order of
+// G1 (chunk c = k4 rows 4c .. 4c+3 (cos of 16 freqs) then 16+4c .. 16+4c+3 (their sin)); else K in natural order
+__global__ void k_wimg_split(const float *__restrict__ src, float *__restrict__ dst, int fourier_order) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 4 * 4096) return;
-    const float x = src[i], hi = tf32_rna(x), lo = tf32_rna(x - hi);
     const int c = i >> 12, o = i & 4095;
+    int si = i;
+    if (fourier_order) {
+        const int q = o >> 9;                     // k4 group inside the chunk
+        si = ((q < 4 ? 4 * c + q : 16 + 4 * c + (q - 4)) << 9) + (o & 511);
+    }
+    const float x = src[si], hi = tf32_rna(x), lo = tf32_rna(x - hi);
     dst[c * ftc::CHUNK + o] = hi;
     dst[c * ftc::CHUNK + 4096 + o] = lo;
 }
@@ -118,11 +208,11 @@ __global__ void __launch_bounds__(ftc::THREADS, 1) k_fourier_tc(const FourierBat
     using namespace ftc;
     extern __shared__ __align__(128) float smem_tc[];
     float *smem = smem_tc;
-    float *sA = smem + SM_A, *sB = smem + SM_B, *sex = smem + SM_EX, *sraw = smem + SM_RAW;
+    float *sB = smem + SM_B, *sex = smem + SM_EX, *sraw = smem + SM_RAW;
     int *s_valid = reinterpret_cast<int *>(smem + SM_VALID);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM_BAR);
     uint64_t *full_a = bars, *empty_a = full_a + NA, *full_b = empty_a + NA, *empty_b = full_b + NB, *g1_done = empty_b + NB,
-             *g2_done = g1_done + 4, *g3_done = g2_done + 1;
+             *g2_done = g1_done + 4, *g3_done = g2_done + 1, *acc_free = g3_done + 1;
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + SM_TMEM);
 
     int j = 0;
@@ -131,6 +221,10 @@ __global__ void __launch_bounds__(ftc::THREADS, 1) k_fourier_tc(const FourierBat
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int s0 = ((int)blockIdx.x - fb.tile0[j]) * TM;
     const int D = a.dim;
+#ifdef INFGEN_FTC_TRACE
+    const int trace_blk = blockIdx.x == 0 ? 0 : ((fb.n_jobs > 1 && (int)blockIdx.x == fb.tile0[1]) ? 1 : -1);
+    int trace_n = 0;
+#endif
     int v = 0;
     if (tid < TM) {
         const int s = s0 + tid;
@@ -141,9 +235,10 @@ __global__ void __launch_bounds__(ftc::THREADS, 1) k_fourier_tc(const FourierBat
     if (!__syncthreads_or(v)) return;
 
     if (tid == 0) {
-        for (int i = 0; i < NA; ++i) { mbar_init(&full_a[i], RT / 2); mbar_init(&empty_a[i], 1); }
+        for (int i = 0; i < NA; ++i) { mbar_init(&full_a[i], 4); mbar_init(&empty_a[i], 1); }   // one arrival per warp of a quarter
         for (int i = 0; i < NB; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
         for (int i = 0; i < 6; ++i) mbar_init(&g1_done[i], 1);
+        mbar_init(acc_free, RT / 32);
         fence_mbar_init();
     }
     if (warp == 0) {
@@ -157,138 +252,182 @@ __global__ void __launch_bounds__(ftc::THREADS, 1) k_fourier_tc(const FourierBat
     const uint32_t tmem = *s_tmem;
     const int n_jobs = 2 * D + 1, n_chunks = 4 * n_jobs;
 
-    if (warp == 9) {
-        // ---- weight producer: lane s owns ring stage s ---------------------------------------------------------------
-        if (lane < NB) {
-            for (int i = lane; i < n_chunks; i += NB) {
-                const int use = i / NB;
-                if (use > 0) mbar_wait(&empty_b[lane], (uint32_t)(use - 1) & 1u);
-                mbar_expect_tx(&full_b[lane], CHUNK * 4u);
-                bulk_g2s(sB + lane * CHUNK, a.w.wimg + (size_t)i * CHUNK, CHUNK * 4u, &full_b[lane]);
+    if (warp == RT / 32 + 1) {
+        // ---- weight producer (warp 17) ------------------------------------------------------------------------------------------
+        // (the whole warp walks the loop and one lane issues, so that the warp reaches the final barrier converged)
+        for (int i = 0; i < n_chunks; ++i) {
+            const int st = i % NB, use = i / NB;
+            if (lane == 0) {
+                if (use > 0) ftc_wait(&empty_b[st], (uint32_t)(use - 1) & 1u, 100 + i);
+                mbar_expect_tx(&full_b[st], CHUNK * 4u);
+                bulk_g2s(sB + st * CHUNK, a.w.wimg + (size_t)i * CHUNK, CHUNK * 4u, &full_b[st]);
             }
+            __syncwarp();
         }
-    } else if (warp == 8) {
-        // ---- MMA issuer -------------------------------------------------------------------------------------------------
-        if (lane == 0) {
-            int jt[9], jd[9];
-            job_list(D, jt, jd);
-            int ci = 0;
-            for (int jb = 0; jb < n_jobs; ++jb) {
-                const int type = jt[jb], d = jd[jb];
-                const uint32_t acc = tmem + (type == 1 ? 256u : (uint32_t)(((type == 0 ? d : D) & 1) * 128));
-                for (int c = 0; c < 4; ++c, ++ci) {
-                    const int sa = ci % NA, sb = ci % NB;
-                    mbar_wait(&full_a[sa], (uint32_t)(ci / NA) & 1u);
-                    mbar_wait(&full_b[sb], (uint32_t)(ci / NB) & 1u);
-                    tc_fence_after();
-                    const uint32_t ab = smem_u32(sA + sa * CHUNK), bb = smem_u32(sB + sb * CHUNK);
+    } else if (warp == 0) {
+        // ---- MMA issuer: warp 0, the oldest warp of its scheduler partition, so that it wins the issue slot whenever it
+        // is ready (as the youngest warp it was starved by the row warps: 110-145 cycles per MMA instead of 68).  The whole
+        // warp runs the loop in uniform control flow; one elected lane issues each tcgen05 instruction.
+        int jt[9], jd[9];
+        job_list(D, jt, jd);
+        int ci = 0, n_h = 0;                      // n_h: uses of the G1/G3 accumulator so far
+        if (lane == 0) FTC_STAMP(1);
+        for (int jb = 0; jb < n_jobs; ++jb) {
+            const int type = jt[jb], d = jd[jb];
+            const uint32_t acc = tmem + (type == 1 ? TC_ACC_S : TC_ACC_H);
+            if (type != 1) {
+                // the single G1/G3 accumulator is free again once every row warp has loaded the previous G1 result
+                if (jb > 0) ftc_wait(acc_free, (uint32_t)(n_h - 1) & 1u, 600 + n_h);
+                ++n_h;
+            }
+            for (int c = 0; c < 4; ++c, ++ci) {
+                const int sb = ci % NB;
+                ftc_wait(&full_a[c], (uint32_t)(ci / NA) & 1u, 200 + ci);
+                ftc_wait(&full_b[sb], (uint32_t)(ci / NB) & 1u, 300 + ci);
+                tc_fence_after();
+                const uint32_t at = tmem + TC_A + 64u * (uint32_t)c;
+                const uint64_t b0 = umma_desc(smem_u32(sB + sb * CHUNK));
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const uint32_t off = (uint32_t)ks * 4096u;                  // 8 k = two 2 KB core-matrix columns
-                        const uint64_t ah = umma_desc(ab + off), al = umma_desc(ab + 16384u + off);
-                        const uint64_t bh = umma_desc(bb + off), bl = umma_desc(bb + 16384u + off);
-                        const uint32_t keep = (type == 1 ? (d > 0) : 0) | (c > 0) | (ks > 0);
-                        umma_tf32(acc, al, bh, keep);
-                        umma_tf32(acc, ah, bl, 1u);
-                        umma_tf32(acc, ah, bh, 1u);
-                    }
-                    umma_commit(&empty_a[sa]);
-                    umma_commit(&empty_b[sb]);
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint32_t ah = at + 8u * ks, al = at + 32u + 8u * ks;      // 8 k = 8 TMEM columns
+                    const uint64_t bh = b0 + (uint64_t)(ks * (4096 >> 4)), bl = bh + (16384 >> 4);   // 8 k = 4 KB of B
+                    const uint32_t keep = (type == 1 ? (d > 0) : 0) | (c > 0) | (ks > 0);
+                    umma_tf32_ts(acc, al, bh, keep);
+                    umma_tf32_ts(acc, ah, bl, 1u);
+                    umma_tf32_ts(acc, ah, bh, 1u);
                 }
-                if (type == 0) umma_commit(&g1_done[d]);
-                else if (type == 1 && d == D - 1) umma_commit(g2_done);
-                else if (type == 2) umma_commit(g3_done);
+                umma_commit_elect(&empty_a[c]);
+                umma_commit_elect(&empty_b[sb]);
+                if (c == 3) {
+                    if (type == 0) umma_commit_elect(&g1_done[d]);
+                    else if (type == 1 && d == D - 1) umma_commit_elect(g2_done);
+                    else if (type == 2) umma_commit_elect(g3_done);
+                }
+                if (lane == 0) FTC_STAMP(1);
             }
         }
     } else {
         // ---- row threads ---------------------------------------------------------------------------------------------
-        const int h = warp >> 2, r = 32 * (warp & 3) + lane;
-        const uint32_t trow = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+        const int qd = (warp - 1) >> 2, r = 32 * (warp & 3) + lane;    // warps 1..16; TMEM lane group = warp % 4
+        const uint32_t trow = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(32 * qd);
+#ifdef INFGEN_FTC_TRACE
+        const int rt_stream = tid == 32 ? 0 : 2;
+#define RT_STAMP() do { if (tid == 32 || tid == 160) FTC_STAMP(rt_stream); } while (0)
+#else
+#define RT_STAMP() do {} while (0)
+#endif
         auto rt_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(RT) : "memory"); };
-        // write 32 consecutive k of row r into chunk ci of the A ring (hi / lo split) and publish it
-        auto put_chunk = [&](int ci, const float *val) {
-            const int s = ci % NA, use = ci / NA;
-            if (use > 0) mbar_wait(&empty_a[s], (uint32_t)(use - 1) & 1u);
-            float *p = sA + s * CHUNK + r * 4;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                float4 hi, lo;
-                hi.x = tf32_rna(val[4 * q + 0]); lo.x = tf32_rna(val[4 * q + 0] - hi.x);
-                hi.y = tf32_rna(val[4 * q + 1]); lo.y = tf32_rna(val[4 * q + 1] - hi.y);
-                hi.z = tf32_rna(val[4 * q + 2]); lo.z = tf32_rna(val[4 * q + 2] - hi.z);
-                hi.w = tf32_rna(val[4 * q + 3]); lo.w = tf32_rna(val[4 * q + 3] - hi.w);
-                st4(p + q * 512, hi);
-                st4(p + 4096 + q * 512, lo);
-            }
-            fence_proxy_async();                  // generic-proxy stores -> visible to the tensor core (async proxy)
-            tc_fence_before();
-            mbar_arrive(&full_a[s]);
+        const uint32_t ta = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + TC_A + 64u * (uint32_t)qd;   // this thread's A stage
+        // A stage qd is free again once the MMAs of its previous chunk have completed
+        // one lane per warp polls (with back-off): 512 spinning threads took the issue slots the MMA warp needs
+        auto warp_wait = [&](uint64_t *b, uint32_t parity, int code) {
+            if (lane == 0) ftc_wait<true>(b, parity, code);
+            __syncwarp();
+            tc_fence_after();
         };
-        // sum over the 128 columns of the row from the two halves' partial sums
+        auto a_acquire = [&](int ci) {
+            const int use = ci / NA;
+            if (use > 0) warp_wait(&empty_a[qd], (uint32_t)(use - 1) & 1u, 400 + ci);
+        };
+        auto a_publish = [&]() {
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_a[qd]);
+        };
+        // this thread's 32 k of the row -> [hi | lo] columns of A stage qd
+        auto put_chunk = [&](int ci, const float *val) {
+            a_acquire(ci);
+            float t[32];                          // hi, then lo (one at a time: 96 live values would spill)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t[i] = __uint_as_float((__float_as_uint(val[i]) + 0x1000u) & 0xFFFFE000u);
+            tmem_st32(ta, t);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t[i] = val[i] - t[i];
+            tmem_st32(ta + 32u, t);
+            a_publish();
+        };
+        // sum over the 128 columns of the row from the four quarters' partial sums
         int exb = 0;
         auto row_sum = [&](float part) {
-            float *e = sex + exb * 256;
+            float *e = sex + exb * 512;
             exb ^= 1;
-            e[h * 128 + r] = part;
+            e[qd * 128 + r] = part;
             rt_sync();
-            return e[r] + e[128 + r];
+            return (e[r] + e[128 + r]) + (e[256 + r] + e[384 + r]);
         };
-        // features of dim d: cos -> chunk ci0 + h, sin -> chunk ci0 + 2 + h (freqs 32h .. 32h + 31)
-        auto features = [&](int d, int ci0) {
+        // features of dim d.  K order of G1: chunk c = [cos(f_16c .. f_16c+15) | sin(f_16c .. f_16c+15)], so a chunk is
+        // 16 sincosf of one thread (quarter qd fills chunk ci0 + qd).  The sincosf loop stays rolled: with all of them
+        // inlined the kernel was 168 KB of SASS and the row warps thrashed the instruction cache.
+        auto features = [&](int d, int ci0, float *val) {
             const float x = sraw[r * 4 + d];
-            float cs[32], sn[32];
-            const float *fq = a.w.freqs + d * 64 + 32 * h;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
+            const float *fq = a.w.freqs + d * 64 + 16 * qd;
+#pragma unroll 1
+            for (int q = 0; q < 4; ++q) {
                 const float4 f4 = ldg4(fq + 4 * q);
                 const float f[4] = {f4.x, f4.y, f4.z, f4.w};
+                float cs[4], sn[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     // x.unsqueeze(-1) * freqs * 2 * math.pi, evaluated left to right in fp32 (layers.py:151)
                     const float arg = __fmul_rn(__fmul_rn(__fmul_rn(x, f[i]), 2.0f), 3.14159265358979323846f);
-                    sincosf(arg, &sn[4 * q + i], &cs[4 * q + i]);
+                    sincosf(arg, &sn[i], &cs[i]);
+                }
+                // (the switch keeps val[] in registers although q is a loop variable)
+                switch (q) {
+                case 0: val[0] = cs[0]; val[1] = cs[1]; val[2] = cs[2]; val[3] = cs[3]; val[16] = sn[0]; val[17] = sn[1]; val[18] = sn[2]; val[19] = sn[3]; break;
+                case 1: val[4] = cs[0]; val[5] = cs[1]; val[6] = cs[2]; val[7] = cs[3]; val[20] = sn[0]; val[21] = sn[1]; val[22] = sn[2]; val[23] = sn[3]; break;
+                case 2: val[8] = cs[0]; val[9] = cs[1]; val[10] = cs[2]; val[11] = cs[3]; val[24] = sn[0]; val[25] = sn[1]; val[26] = sn[2]; val[27] = sn[3]; break;
+                default: val[12] = cs[0]; val[13] = cs[1]; val[14] = cs[2]; val[15] = cs[3]; val[28] = sn[0]; val[29] = sn[1]; val[30] = sn[2]; val[31] = sn[3]; break;
                 }
             }
-            put_chunk(ci0 + h, cs);
-            put_chunk(ci0 + 2 + h, sn);
+            put_chunk(ci0 + qd, val);
         };
-        // LayerNorm + ReLU of the row (this thread: columns 64h .. 64h+63 in val) -> chunks ci0 + 2h, ci0 + 2h + 1
-        auto norm_relu_put = [&](float *val, const float *g, const float *b, int ci0) {
+        // two-pass mean / rstd of the row (this thread holds 32 of its 128 values)
+        auto row_stats = [&](const float *val, float &mean, float &rstd) {
             float s = 0.f;
 #pragma unroll
-            for (int i = 0; i < 64; ++i) s += val[i];
-            const float mean = row_sum(s) * (1.0f / HID);
+            for (int i = 0; i < 32; ++i) s += val[i];
+            mean = row_sum(s) * (1.0f / HID);
             float q = 0.f;
 #pragma unroll
-            for (int i = 0; i < 64; ++i) { const float c = val[i] - mean; q = fmaf(c, c, q); }
-            const float rstd = 1.0f / sqrtf(row_sum(q) * (1.0f / HID) + LN_EPS);
+            for (int i = 0; i < 32; ++i) { const float c = val[i] - mean; q = fmaf(c, c, q); }
+            rstd = 1.0f / sqrtf(row_sum(q) * (1.0f / HID) + LN_EPS);
+        };
+        // LayerNorm + ReLU of the row -> chunk ci0 + qd
+        auto norm_relu_put = [&](float *val, const float *g, const float *b, int ci0) {
+            float mean, rstd;
+            row_stats(val, mean, rstd);
 #pragma unroll
-            for (int i4 = 0; i4 < 16; ++i4) {
-                const float4 g4 = ldg4(g + 64 * h + 4 * i4), b4 = ldg4(b + 64 * h + 4 * i4);
+            for (int i4 = 0; i4 < 8; ++i4) {
+                const float4 g4 = ldg4(g + 32 * qd + 4 * i4), b4 = ldg4(b + 32 * qd + 4 * i4);
                 val[4 * i4 + 0] = fmaxf((val[4 * i4 + 0] - mean) * rstd * g4.x + b4.x, 0.f);
                 val[4 * i4 + 1] = fmaxf((val[4 * i4 + 1] - mean) * rstd * g4.y + b4.y, 0.f);
                 val[4 * i4 + 2] = fmaxf((val[4 * i4 + 2] - mean) * rstd * g4.z + b4.z, 0.f);
                 val[4 * i4 + 3] = fmaxf((val[4 * i4 + 3] - mean) * rstd * g4.w + b4.w, 0.f);
             }
-            put_chunk(ci0 + 2 * h, val);
-            put_chunk(ci0 + 2 * h + 1, val + 32);
+            put_chunk(ci0 + qd, val);
         };
         const float *xrow = a.w.wimg + (size_t)n_chunks * CHUNK;      // [D][128]
-        float val[64];
+        float val[32];
         int ci = 0;
-        features(0, ci);
+        RT_STAMP();
+        features(0, ci, val);
         ci += 4;
+        RT_STAMP();
         for (int d = 0; d < D; ++d) {
-            if (d + 1 < D) { features(d + 1, ci); ci += 4; }
-            mbar_wait(&g1_done[d], 0);
-            tc_fence_after();
-            const uint32_t t = trow + (uint32_t)((d & 1) * 128 + 64 * h);
-            tmem_ld32(t, val);
-            tmem_ld32(t + 32, val + 32);
+            if (d + 1 < D) { features(d + 1, ci, val); ci += 4; }
+            RT_STAMP();
+            warp_wait(&g1_done[d], 0, 500 + d);
+            RT_STAMP();
+            tmem_ld32(trow + TC_ACC_H, val);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_free);  // G1_{d+1} / G3 may overwrite the accumulator
             const float x = sraw[r * 4 + d];
 #pragma unroll
-            for (int i4 = 0; i4 < 16; ++i4) {
-                const float4 b4 = ldg4(a.w.b0[d] + 64 * h + 4 * i4), w4 = ldg4(xrow + d * 128 + 64 * h + 4 * i4);
+            for (int i4 = 0; i4 < 8; ++i4) {
+                const float4 b4 = ldg4(a.w.b0[d] + 32 * qd + 4 * i4), w4 = ldg4(xrow + d * 128 + 32 * qd + 4 * i4);
                 val[4 * i4 + 0] += fmaf(x, w4.x, b4.x);
                 val[4 * i4 + 1] += fmaf(x, w4.y, b4.y);
                 val[4 * i4 + 2] += fmaf(x, w4.z, b4.z);
@@ -296,50 +435,42 @@ __global__ void __launch_bounds__(ftc::THREADS, 1) k_fourier_tc(const FourierBat
             }
             norm_relu_put(val, a.w.ln_g[d], a.w.ln_b[d], ci);
             ci += 4;
+            RT_STAMP();
         }
         // sum over dims (accumulated in TMEM) + biases -> LN -> ReLU -> A of the output Linear
-        mbar_wait(g2_done, 0);
-        tc_fence_after();
-        tmem_ld32(trow + 256u + (uint32_t)(64 * h), val);
-        tmem_ld32(trow + 256u + (uint32_t)(64 * h) + 32, val + 32);
+        warp_wait(g2_done, 0, 504);
+        RT_STAMP();
+        tmem_ld32(trow + TC_ACC_S, val);
         for (int d = 0; d < D; ++d) {
 #pragma unroll
-            for (int i4 = 0; i4 < 16; ++i4) {
-                const float4 b4 = ldg4(a.w.b3[d] + 64 * h + 4 * i4);
+            for (int i4 = 0; i4 < 8; ++i4) {
+                const float4 b4 = ldg4(a.w.b3[d] + 32 * qd + 4 * i4);
                 val[4 * i4 + 0] += b4.x; val[4 * i4 + 1] += b4.y; val[4 * i4 + 2] += b4.z; val[4 * i4 + 3] += b4.w;
             }
         }
         norm_relu_put(val, a.w.out_ln_g, a.w.out_ln_b, ci);
         ci += 4;
-        mbar_wait(g3_done, 0);
-        tc_fence_after();
-        {
-            const uint32_t t = trow + (uint32_t)((D & 1) * 128 + 64 * h);
-            tmem_ld32(t, val);
-            tmem_ld32(t + 32, val + 32);
-        }
+        RT_STAMP();
+        warp_wait(g3_done, 0, 505);
+        RT_STAMP();
+        tmem_ld32(trow + TC_ACC_H, val);
 #pragma unroll
-        for (int i4 = 0; i4 < 16; ++i4) {
-            const float4 b4 = ldg4(a.w.b_out + 64 * h + 4 * i4);
+        for (int i4 = 0; i4 < 8; ++i4) {
+            const float4 b4 = ldg4(a.w.b_out + 32 * qd + 4 * i4);
             val[4 * i4 + 0] += b4.x; val[4 * i4 + 1] += b4.y; val[4 * i4 + 2] += b4.z; val[4 * i4 + 3] += b4.w;
         }
         if (a.normalize) {                        // (y - mean) / sqrt(var + eps): input of every layer's attn_prenorm_r
-            float s = 0.f;
+            float mean, rstd;
+            row_stats(val, mean, rstd);
 #pragma unroll
-            for (int i = 0; i < 64; ++i) s += val[i];
-            const float mean = row_sum(s) * (1.0f / HID);
-            float q = 0.f;
-#pragma unroll
-            for (int i = 0; i < 64; ++i) { const float c = val[i] - mean; q = fmaf(c, c, q); }
-            const float rstd = 1.0f / sqrtf(row_sum(q) * (1.0f / HID) + LN_EPS);
-#pragma unroll
-            for (int i = 0; i < 64; ++i) val[i] = (val[i] - mean) * rstd;
+            for (int i = 0; i < 32; ++i) val[i] = (val[i] - mean) * rstd;
         }
         if (s_valid[r]) {
-            float *o = a.out + (size_t)(s0 + r) * 128 + 64 * h;
+            float *o = a.out + (size_t)(s0 + r) * 128 + 32 * qd;
 #pragma unroll
-            for (int i4 = 0; i4 < 16; ++i4) st4(o + 4 * i4, make_float4(val[4 * i4], val[4 * i4 + 1], val[4 * i4 + 2], val[4 * i4 + 3]));
+            for (int i4 = 0; i4 < 8; ++i4) st4(o + 4 * i4, make_float4(val[4 * i4], val[4 * i4 + 1], val[4 * i4 + 2], val[4 * i4 + 3]));
         }
+        RT_STAMP();
         tc_fence_before();
     }
     __syncthreads();
