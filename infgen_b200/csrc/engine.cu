@@ -16,6 +16,7 @@
 #include "ops.cuh"
 #include "layer.cuh"
 #include "fourier_tc.cuh"
+#include "node.cuh"
 #include "decode.cuh"
 #include "insert.cuh"
 
@@ -148,6 +149,8 @@ struct infgen_engine {
     float *cs_blob = nullptr;                           // cluster-sliced AttentionLayer chunks (layer.cuh)
     std::unordered_map<std::string, FourierW> fourier_cache;
     std::vector<float *> wimgs;                         // FourierEmbedding tensor-core weight images (fourier_tc.cuh)
+    float *np_blob = nullptr;                           // node-packed motion layers (node.cuh), [18][np::FLOATS]
+    int layer_path = 0;                                 // 0 auto, 1 cluster kernels only, 2 row-tile (k_attn + k_node) only
     bool fourier_tc = true;                             // INFGEN_FOURIER=ffma selects the FFMA row-tile kernel instead
     std::unordered_map<std::string, std::pair<const float *, const float *>> cs;   // layer -> (post, pre) chunks
     float *grid_cells = nullptr, *vocab = nullptr;
@@ -358,10 +361,10 @@ static inline void count_launch(infgen_engine *e) { if (!e->capturing) e->launch
 
 // per-kernel-class device timing (bench.py roofline leg): event pairs around every launch, plain launches only
 enum KClass { KC_EDGE_BUILD, KC_FOURIER, KC_EMBED, KC_LAYER_STACK, KC_LAYER_TM, KC_LAYER_A, KC_HEADS, KC_ADVANCE, KC_INSERT,
-              KC_MISC, KC_COUNT };
+              KC_MISC, KC_ATTN, KC_NODE, KC_COUNT };
 static const char *KCLASS_NAME[KC_COUNT] = {"k_edge_build", "k_fourier:edges", "k_embed_column", "k_layer:stack18",
                                             "k_layer:temporal+map", "k_layer:agent", "k_heads", "k_advance",
-                                            "insertion stage", "misc"};
+                                            "insertion stage", "misc", "k_attn", "k_node"};
 struct ProfScope {
     infgen_engine *e;
     bool on;
@@ -501,6 +504,52 @@ static int enqueue_embed_rows(infgen_engine *e, const int *row_lo) {
 // to 120 rows) ONE launch runs all 18 layers with a grid barrier before each agent<->agent attention (its K/V rows come
 // from every row of the scene); otherwise one launch per {temporal + map} and per {agent} layer, whose K/V exchange is
 // the launch boundary.  with_edges=false: history columns that receive no edges (prefill).
+// node-packed copies of the 18 motion layers (node.cuh): every Linear cut into contiguous 128-column blocks
+static int build_node_weights(infgen_engine *e) {
+    CK(cudaMalloc(&e->np_blob, (size_t)18 * np::FLOATS * sizeof(float)));
+    AttnW *stacks[3] = {e->t, e->m, e->a};
+    for (int s = 0; s < 3; ++s)
+        for (int i = 0; i < 6; ++i) {
+            AttnW &w = stacks[s][i];
+            float *d = e->np_blob + (size_t)(s * 6 + i) * np::FLOATS;
+            auto pack = [&](const float *src, int off, int K4, int N) {
+                k_node_pack<<<(K4 * N + 255) / 256, 256, 0, e->stream>>>(src, d + off, K4, N);
+            };
+            pack(w.w_vr, np::VR, 32, 128); pack(w.w_g, np::G, 64, 128); pack(w.w_out, np::OUT, 32, 128);
+            pack(w.w_ff1, np::FF1, 32, 512); pack(w.w_ff2, np::FF2, 128, 128);
+            pack(w.w_qs, np::QS, 32, 256); pack(w.w_kv, np::KV, 32, 256);
+            CKL();
+            w.npk = d;
+        }
+    return 0;
+}
+static int launch_attn(infgen_engine *e, const RowSpace &rows, const SubArgs &sub) {
+    AttnArgs a;
+    memset(&a, 0, sizeof(a));
+    a.rows = rows; a.sub = sub; a.q = fbuf(e, "q"); a.qr = fbuf(e, "qr");
+    a.agg = fbuf(e, "agg"); a.ragg = fbuf(e, "ragg"); a.sal = fbuf(e, "sal");
+    ProfScope ps(e, KC_ATTN);
+    k_attn<<<dim3((rows.n_total + AM - 1) / AM, NHEAD), NT, 0, e->stream>>>(a);
+    CKL(); count_launch(e);
+    return 0;
+}
+// finish layer `lw` (NULL: nothing to finish) and project the inputs of layer `pw` (NULL: none)
+static int launch_node(infgen_engine *e, const RowSpace &rows, const AttnW *lw, const AttnW *pw, bool pre_kv, float *kv_out,
+                       bool kv_ring, float *trace_out) {
+    NodeArgs a;
+    memset(&a, 0, sizeof(a));
+    a.rows = rows; a.x = fbuf(e, "x"); a.agg = fbuf(e, "agg"); a.ragg = fbuf(e, "ragg"); a.sal = fbuf(e, "sal");
+    a.q = fbuf(e, "q"); a.s = fbuf(e, "s"); a.qr = fbuf(e, "qr");
+    if (lw) { a.w_post = lw->npk; a.lw = *lw; }
+    if (pw) { a.w_pre = pw->npk; a.pw = *pw; }
+    a.pre_kv = pre_kv ? 1 : 0; a.kv_out = kv_out; a.kv_ring = kv_ring ? 1 : 0; a.col_add = 0; a.ring = RING;
+    a.col_ptr = e->st.col; a.trace_out = trace_out;
+    ProfScope ps(e, KC_NODE);
+    k_node<<<(rows.n_total + NM - 1) / NM, NT_S, NodeSmem::BYTES, e->stream>>>(a);
+    CKL(); count_launch(e);
+    return 0;
+}
+
 static int enqueue_layers(infgen_engine *e, bool with_edges, int trace_iter) {
     DecState &s = e->st;
     const int R = e->R;
@@ -511,6 +560,31 @@ static int enqueue_layers(infgen_engine *e, bool with_edges, int trace_iter) {
     base.rows = scene_rows(e); base.x = fbuf(e, "x"); base.q = fbuf(e, "q"); base.s = fbuf(e, "s"); base.qr = fbuf(e, "qr");
     base.col_ptr = s.col; base.ring = RING; base.grid_bar = (unsigned *)e->bufs["grid_bar"].p;
     const bool fused = (R + e->row_tile - 1) / e->row_tile <= MAX_CLUSTERS;
+    // batches beyond one wave of clusters: the row-tile throughput path (node.cuh), two grid-wide kernels per layer
+    if (e->layer_path == 2 || (e->layer_path == 0 && !fused)) {
+        const RowSpace rows = scene_rows(e);
+        RET(launch_node(e, rows, nullptr, &e->t[0], true, kv_t, true, nullptr));
+        for (int i = 0; i < 6; ++i) {
+            float *kva = kv_a + (size_t)(i & 1) * kv_a_buf;
+            SubArgs t, m, g;
+            memset(&t, 0, sizeof(t)); memset(&m, 0, sizeof(m)); memset(&g, 0, sizeof(g));
+            t.has_attn = with_edges; t.has_pos = 1; t.kv = kv_t + i * kv_t_layer; t.cnt = s.t_cnt; t.stride = s.W;
+            t.src = s.t_src; t.rhat = fbuf(e, "rhat_t");
+            m.has_attn = with_edges; m.has_pos = 1; m.kv = kv_m + i * kv_m_layer; m.cnt = s.m_cnt; m.stride = s.max_m;
+            m.src = s.m_src; m.rhat = fbuf(e, "rhat_m");
+            g.has_attn = with_edges; g.has_pos = 1; g.kv = kva; g.cnt = s.a_cnt; g.start = s.a_start; g.src = s.a_src;
+            g.rhat = fbuf(e, "rhat_a");
+            float *trace = (trace_iter >= 0 && e->cfg.trace) ? fbuf(e, "trace_layer_out") + ((size_t)trace_iter * 6 + i) * R * 128
+                                                             : nullptr;
+            RET(launch_attn(e, rows, t));
+            RET(launch_node(e, rows, &e->t[i], &e->m[i], false, nullptr, false, nullptr));
+            RET(launch_attn(e, rows, m));
+            RET(launch_node(e, rows, &e->m[i], &e->a[i], true, kva, false, nullptr));
+            RET(launch_attn(e, rows, g));
+            RET(launch_node(e, rows, &e->a[i], i < 5 ? &e->t[i + 1] : nullptr, true, kv_t + (size_t)(i + 1) * kv_t_layer, true, trace));
+        }
+        return 0;
+    }
     auto fill = [&](int i, SubArgs &t, SubArgs &m, SubArgs &g) {
         float *kva = kv_a + (size_t)(i & 1) * kv_a_buf;
         t.w = e->t[i].cs_post; t.has_attn = with_edges; t.has_pos = 1; t.elist = 0;
@@ -992,6 +1066,12 @@ int32_t infgen_create(const infgen_config *cfg, const float *weights, int64_t n_
     CK(cudaFuncSetAttribute(k_layer<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LayerSmem<8>::BYTES));
     CK(cudaFuncSetAttribute(k_fourier, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FOURIER_SMEM));
     CK(cudaFuncSetAttribute(k_fourier_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ftc::SMEM));
+    CK(cudaFuncSetAttribute(k_node, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NodeSmem::BYTES));
+    RET(build_node_weights(e));
+    {
+        const char *lp = getenv("INFGEN_LAYER_PATH");          // "cluster" | "rows": force one of the two layer paths
+        e->layer_path = lp ? (!strcmp(lp, "cluster") ? 1 : (!strcmp(lp, "rows") ? 2 : 0)) : 0;
+    }
     {
         const char *fm = getenv("INFGEN_FOURIER");
         e->fourier_tc = !(fm && !strcmp(fm, "ffma"));
@@ -1018,6 +1098,7 @@ int32_t infgen_destroy(infgen_engine *e) {
     cudaFree(e->blob); cudaFree(e->cs_blob); cudaFree(e->grid_cells); cudaFree(e->vocab); cudaFree(e->tok_tab); cudaFree(e->grid_tab);
     cudaFree(e->d_err); cudaFree(e->seed_feat);
     for (float *p : e->wimgs) cudaFree(p);
+    cudaFree(e->np_blob);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->side_stream) cudaStreamDestroy(e->side_stream);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);

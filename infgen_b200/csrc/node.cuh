@@ -1,0 +1,273 @@
+// Throughput path of the AttentionLayer (reference layers.py:61-113) for batches whose row tiles no longer fit one wave of
+// clusters (layer.cuh is the latency path: 8-CTA clusters, 8 rows each, at most 15 of them co-resident on a B200, so a
+// batch of 32 scenes needs 18 waves of latency-bound phases per layer).  Here a layer is two grid-wide kernels:
+//
+//   k_attn    edge attention (layers.py:78-92) of ALL rows and heads: one CTA = 8 rows x 1 head, one warp per (row, head),
+//             thousands of warps in flight - the gather of K/V rows and relative embeddings is bound by L2/HBM bandwidth,
+//             not by a dependent chain.  Writes the per-head softmax-weighted sums agg / ragg / sal to global memory.
+//             Same code as the attention phase of k_layer (attn_phase<8>): identical numerics.
+//   k_node    everything else of the layer for a tile of 16 rows per CTA, whole rows local to the CTA (no cluster, no
+//             DSMEM exchange): to_v_r fold -> gate -> to_out -> LN -> FFN -> LN (layers.py:74-75, 94-99), then the
+//             LayerNorm + q/s/k/v projections and the relative-query fold of the NEXT layer (layers.py:65-71, 106-108).
+//             The weights of both halves are streamed through the shared-memory ring of stream.cuh (cp.async.bulk +
+//             mbarriers) from "node-packed" copies: every Linear cut into 128-column blocks stored contiguously in
+//             consumption order, so the whole layer is two linear streams.
+//
+// The kernel boundary between k_node (writes K/V of the rows) and the next k_attn (reads K/V of any row of the scene)
+// is the grid-wide dependency of the agent<->agent layers.
+#pragma once
+#include "common.cuh"
+#include "stream.cuh"
+#include "ops.cuh"
+#include "layer.cuh"
+
+namespace infgen {
+
+// node-packed weights of one AttentionLayer (float offsets); every block is [k4][128][4]
+namespace np {
+constexpr int VR = 0;                       // [32]   to_v_r
+constexpr int G = VR + 16384;               // [64]   to_g
+constexpr int OUT = G + 32768;              // [32]   to_out
+constexpr int FF1 = OUT + 16384;            // 4 x [32]  ff_mlp.0 columns 128j..
+constexpr int FF2 = FF1 + 65536;            // [128]  ff_mlp.3
+constexpr int QS = FF2 + 65536;             // 2 x [32]  to_q | to_s
+constexpr int KV = QS + 32768;              // 2 x [32]  to_k | to_v
+constexpr int FLOATS = KV + 32768;          // 262,144 floats = 1 MB
+}  // namespace np
+
+// dst[j][k4][n][4] = src[k4][128 j + n][4]: a packed [K4][N][4] matrix cut into 128-column blocks
+__global__ void k_node_pack(const float *__restrict__ src, float *__restrict__ dst, int K4, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K4 * N) return;
+    const int k4 = i / N, n = i % N, j = n >> 7, nl = n & 127;
+    const float4 v = *reinterpret_cast<const float4 *>(src + (size_t)i * 4);
+    *reinterpret_cast<float4 *>(dst + (((size_t)j * K4 + k4) * 128 + nl) * 4) = v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+struct AttnArgs {
+    RowSpace rows;
+    SubArgs sub;               // kv, cnt, start, stride, src, rhat, has_attn, has_pos
+    const float *q, *qr;       // [R][128], [R][8][128]
+    float *agg, *ragg, *sal;   // [R][128], [R][8][128], [R][8]
+};
+constexpr int AM = 8;          // rows per CTA (one warp per row)
+
+__global__ void __launch_bounds__(NT) k_attn(const AttnArgs a) {
+    __shared__ __align__(16) float sq[AM * 16], sqr[AM * 128], sagg[AM * 16], sragg[AM * LD1], ssal[16], smerge[NWARP * 160];
+    const int c = blockIdx.y, row0 = blockIdx.x * AM;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    bool any = false;
+#pragma unroll
+    for (int m = 0; m < AM; ++m) any |= a.rows.active(row0 + m);
+    if (!any) return;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    {
+        const int m = warp, r = row0 + m;
+        const bool act = a.rows.active(r);
+        st4(sqr + m * 128 + 4 * lane, act ? ld4(a.qr + ((size_t)r * 8 + c) * 128 + 4 * lane) : z4);
+        if (lane < 4) st4(sq + m * 16 + 4 * lane, act ? ld4(a.q + (size_t)r * 128 + 16 * c + 4 * lane) : z4);
+    }
+    __syncthreads();
+    const AttnPre p = attn_prefetch<AM>(a.sub, a.rows, row0);
+    attn_phase<AM>(a.sub, p, c, sq, sqr, sagg, sragg, ssal, smerge);
+    __syncwarp();
+    {
+        const int m = warp, r = row0 + m;
+        if (a.rows.active(r)) {
+            st4(a.ragg + ((size_t)r * 8 + c) * 128 + 4 * lane, ld4(sragg + m * LD1 + 4 * lane));
+            if (lane < 4) st4(a.agg + (size_t)r * 128 + 16 * c + 4 * lane, ld4(sagg + m * 16 + 4 * lane));
+            if (lane == 0) a.sal[(size_t)r * 8 + c] = ssal[m];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+struct NodeArgs {
+    RowSpace rows;
+    float *x;                  // [R][128] residual stream, updated in place
+    const float *agg, *ragg, *sal;
+    float *q, *s, *qr;         // hand-over: s of the post layer is read, q / s / qr of the pre layer are written
+    const float *w_post;       // node-packed weights of the layer being finished (NULL: only the pre half runs)
+    AttnW lw;                  // its bias / LayerNorm vectors
+    const float *w_pre;        // node-packed weights of the following layer (NULL: none)
+    AttnW pw;
+    int pre_kv;                // also project k|v of these rows (non-bipartite layers)
+    float *kv_out;
+    int kv_ring, col_add, ring;
+    const int *col_ptr;
+    float *trace_out;          // optional copy of the layer output [R][128]
+};
+constexpr int NM = 16;         // rows per CTA
+
+struct NodeSmem {
+    static constexpr int RING = 0;
+    static constexpr int X = RING + WS_SMEM_FLOATS;     // [NM][LD1] residual
+    static constexpr int S = X + NM * LD1;              // [NM][LD1] skip projection of the post layer
+    static constexpr int CAT = S + NM * LD1;            // [NM][LD2] agg2 | LN_dst(x)
+    static constexpr int U = CAT + NM * LD2;            // [NM][LD1]
+    static constexpr int O = U + NM * LD1;              // [NM][LD1]
+    static constexpr int Y = O + NM * LD1;              // [NM][LD1]
+    static constexpr int SAL = Y + NM * LD1;            // [NM][8]
+    static constexpr int RAGG = SAL + NM * 8;           // [8 heads][NM][LD1] normalised relative sums; later the FFN hidden
+    static constexpr int TOTAL = RAGG + 8 * NM * LD1;   //                      tile [NM][LD5] and the q tile [NM][LD1]
+    static constexpr size_t BYTES = (size_t)TOTAL * sizeof(float);
+    static_assert(NM * LD5 <= 8 * NM * LD1, "FFN hidden tile must fit the ragg region");
+    static_assert(BYTES <= 227 * 1024, "shared memory budget");
+};
+
+__global__ void __launch_bounds__(NT_S) k_node(const NodeArgs a) {
+    extern __shared__ __align__(16) float smem_n[];
+    using L = NodeSmem;
+    float *smem = smem_n;
+    WsSmem wsm(smem + L::RING);
+    float *sx = smem + L::X, *ss = smem + L::S, *scat = smem + L::CAT, *su = smem + L::U, *so = smem + L::O, *sy = smem + L::Y,
+          *ssal = smem + L::SAL, *sr = smem + L::RAGG, *sh = smem + L::RAGG, *sq = smem + L::RAGG;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row0 = blockIdx.x * NM;
+    unsigned act_mask = 0;
+#pragma unroll
+    for (int m = 0; m < NM; ++m) act_mask |= a.rows.active(row0 + m) ? (1u << m) : 0u;
+    if (!act_mask) return;
+    auto active = [&](int m) { return (act_mask >> m) & 1u; };
+    const bool post = a.w_post != nullptr, pre = a.w_pre != nullptr;
+    const int has_pos = a.lw.has_pos;
+    ws_init(wsm);
+    if (warp == NWARP) {
+        if (lane < WS_STAGES) {
+            WSeg segs[2];
+            int n = 0;
+            if (post) segs[n++] = WSeg{a.w_post + (has_pos ? np::VR : np::G), has_pos ? 384 : 352, 512};
+            if (pre) segs[n++] = WSeg{a.w_pre + np::QS, a.pre_kv ? 128 : 64, 512};
+            ws_produce(wsm, segs, n);
+        }
+        return;
+    }
+    WsCons ws(wsm);
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    // ---- residual rows, skip projection, attention sums -----------------------------------------------------------------
+    for (int m = warp; m < NM; m += NWARP) {
+        const int r = row0 + m;
+        const bool act = active(m);
+        const float4 x = act ? ld4(a.x + (size_t)r * 128 + 4 * lane) : z4;
+        st4(sx + m * LD1 + 4 * lane, x);
+        if (post) {
+            st4(ss + m * LD1 + 4 * lane, act ? ld4(a.s + (size_t)r * 128 + 4 * lane) : z4);
+            st4(scat + m * LD2 + 4 * lane, act ? ld4(a.agg + (size_t)r * 128 + 4 * lane) : z4);
+            st4(scat + m * LD2 + 128 + 4 * lane, ln128(x, a.lw.ln_dst_g, a.lw.ln_dst_b, lane));
+            if (lane < 8) ssal[m * 8 + lane] = act ? a.sal[(size_t)r * 8 + lane] : 0.f;
+            if (has_pos) {
+                const float4 g = ldg4(a.lw.ln_r_g + 4 * lane), b = ldg4(a.lw.ln_r_b + 4 * lane);
+#pragma unroll
+                for (int h = 0; h < 8; ++h) {
+                    // ragg' = g_r * ragg + b_r * sal (the LayerNorm affine of attn_prenorm_r folded after the sum)
+                    const float4 v = act ? ld4(a.ragg + ((size_t)r * 8 + h) * 128 + 4 * lane) : z4;
+                    const float sa = act ? a.sal[(size_t)r * 8 + h] : 0.f;
+                    st4(sr + (h * NM + m) * LD1 + 4 * lane, make_float4(fmaf(g.x, v.x, b.x * sa), fmaf(g.y, v.y, b.y * sa),
+                                                                         fmaf(g.z, v.z, b.z * sa), fmaf(g.w, v.w, b.w * sa)));
+                }
+            }
+        }
+    }
+    csync();
+    if (post) {
+        // ---- agg2 = agg + Wvr ragg' + bvr * sal: warp w owns columns 16w.. = head w, so its A operand is ragg'[w] ---------
+        if (has_pos) {
+            stream_gemm<NM>(ws, sr + warp * NM * LD1, LD1, 32, [&](int m, int n, float v) {
+                scat[m * LD2 + n] += v + __ldg(a.lw.b_vr + n) * ssal[m * 8 + (n >> 4)];
+            });
+            csync();
+        }
+        // ---- gate: g = sigmoid(Wg [agg2 | xd] + bg);  u = agg2 + g * (s - agg2) ---------------------------------------------
+        stream_gemm<NM>(ws, scat, LD2, 64, [&](int m, int n, float v) {
+            const float g = sigmoidf(v + __ldg(a.lw.b_g + n));
+            const float ag = scat[m * LD2 + n];
+            su[m * LD1 + n] = ag + g * (ss[m * LD1 + n] - ag);
+        });
+        csync();
+        // ---- to_out -------------------------------------------------------------------------------------------------------
+        stream_gemm<NM>(ws, su, LD1, 32, [&](int m, int n, float v) { so[m * LD1 + n] = v + __ldg(a.lw.b_out + n); });
+        csync();
+        // x1 = x + LN_post(o);  so = LN_ffpre(x1)
+        for (int m = warp; m < NM; m += NWARP) {
+            float4 o = ld4(so + m * LD1 + 4 * lane);
+            o = ln128(o, a.lw.ln_post_g, a.lw.ln_post_b, lane);
+            const float4 x1 = add4(ld4(sx + m * LD1 + 4 * lane), o);
+            st4(sx + m * LD1 + 4 * lane, x1);
+            st4(so + m * LD1 + 4 * lane, ln128(x1, a.lw.ln_ffpre_g, a.lw.ln_ffpre_b, lane));
+        }
+        csync();
+        // ---- FFN ----------------------------------------------------------------------------------------------------------
+        for (int j = 0; j < 4; ++j)
+            stream_gemm<NM>(ws, so, LD1, 32, [&](int m, int n, float v) {
+                sh[m * LD5 + 128 * j + n] = fmaxf(v + __ldg(a.lw.b_ff1 + 128 * j + n), 0.f);
+            });
+        csync();
+        stream_gemm<NM>(ws, sh, LD5, 128, [&](int m, int n, float v) { sy[m * LD1 + n] = v + __ldg(a.lw.b_ff2 + n); });
+        csync();
+        // x2 = x1 + LN_ffpost(y)
+        for (int m = warp; m < NM; m += NWARP) {
+            const int r = row0 + m;
+            float4 f = ld4(sy + m * LD1 + 4 * lane);
+            f = ln128(f, a.lw.ln_ffpost_g, a.lw.ln_ffpost_b, lane);
+            const float4 x2 = add4(ld4(sx + m * LD1 + 4 * lane), f);
+            st4(sx + m * LD1 + 4 * lane, x2);
+            if (active(m)) {
+                st4(a.x + (size_t)r * 128 + 4 * lane, x2);
+                if (a.trace_out) st4(a.trace_out + (size_t)r * 128 + 4 * lane, x2);
+            }
+        }
+        csync();
+    }
+    if (!pre) return;
+    // ---- LayerNorm + q/s/k/v projections + relative-query fold of the next layer (layers.py:65-71, 106-108) ---------------
+    for (int m = warp; m < NM; m += NWARP)
+        st4(su + m * LD1 + 4 * lane, ln128(ld4(sx + m * LD1 + 4 * lane), a.pw.ln_dst_g, a.pw.ln_dst_b, lane));
+    csync();
+    stream_gemm<NM>(ws, su, LD1, 32, [&](int m, int n, float v) {
+        v += __ldg(a.pw.b_qs + n);
+        sq[m * LD1 + n] = v;
+        if (active(m)) a.q[(size_t)(row0 + m) * 128 + n] = v;
+    });
+    stream_gemm<NM>(ws, su, LD1, 32, [&](int m, int n, float v) {
+        if (active(m)) a.s[(size_t)(row0 + m) * 128 + n] = v + __ldg(a.pw.b_qs + 128 + n);
+    });
+    if (a.pre_kv) {
+        const int col = (a.col_ptr ? *a.col_ptr : 0) + a.col_add;
+        for (int j = 0; j < 2; ++j)
+            stream_gemm<NM>(ws, su, LD1, 32, [&](int m, int n, float v) {
+                if (active(m)) {
+                    const int r = row0 + m;
+                    const size_t slot = a.kv_ring ? ((size_t)r * a.ring + (col & (a.ring - 1))) : (size_t)r;
+                    a.kv_out[slot * 256 + 128 * j + n] = v + __ldg(a.pw.b_kv + 128 * j + n);
+                }
+            });
+    }
+    csync();
+    // qr[m][h][ch] = g_r[ch] * sum_d q[m][16h+d] * Wkr[16h+d][ch]
+    if (a.pw.has_pos) {
+        const int ch = tid & 127;
+        const float g = __ldg(a.pw.ln_r_g + ch);
+        for (int h = tid >> 7; h < 8; h += 2) {
+            float wk[16];
+#pragma unroll
+            for (int d = 0; d < 16; ++d) wk[d] = __ldg(a.pw.w_kr + (size_t)(16 * h + d) * 128 + ch);
+            for (int m = 0; m < NM; ++m) {
+                if (!active(m)) continue;
+                float acc = 0.f;
+#pragma unroll
+                for (int d4 = 0; d4 < 4; ++d4) {
+                    const float4 qv = ld4(sq + m * LD1 + 16 * h + 4 * d4);
+                    acc = fmaf(qv.x, wk[4 * d4 + 0], acc);
+                    acc = fmaf(qv.y, wk[4 * d4 + 1], acc);
+                    acc = fmaf(qv.z, wk[4 * d4 + 2], acc);
+                    acc = fmaf(qv.w, wk[4 * d4 + 3], acc);
+                }
+                a.qr[((size_t)(row0 + m) * 8 + h) * 128 + ch] = acc * g;
+            }
+        }
+    }
+}
+
+}  // namespace infgen

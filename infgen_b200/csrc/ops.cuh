@@ -33,6 +33,7 @@ struct AttnW {                 // one AttentionLayer, pointers into the packed w
     const float *ln_ffpost_g, *ln_ffpost_b;
     int has_pos;               // has_pos_emb
     const float *cs_post, *cs_pre;   // cluster-sliced chunks of this layer (layer.cuh), [8][FLOATS] each
+    const float *npk;                // node-packed copy (node.cuh), NULL when the layer has none
 };
 
 struct FourierW {              // one FourierEmbedding

@@ -103,6 +103,24 @@ def test_free_running_matches_reference_golden(name, graph):
             _close(out[k].numpy(), z[k], f'{name} {k}')
 
 
+@pytest.mark.parametrize('name', MOTION_CASES)
+def test_row_tile_layer_path_matches_reference_golden(name, monkeypatch):
+    """The throughput path of the AttentionLayer (k_attn + k_node, selected automatically for batches beyond one wave of
+    clusters) forced on the single-scene golden cases: exact greedy tokens / states, trajectories within tolerance."""
+    monkeypatch.setenv('INFGEN_LAYER_PATH', 'rows')
+    scene, sd, cfg, spec = build_case(name)
+    z = np.load(os.path.join(GOLD, f'case_{name}.npz'))
+    dec = _make_decoder(sd, cfg, use_cuda_graph=True)
+    out = dec.inference(scene, scene['map_enc'])
+    dec.close()
+    div = _first_divergence(out['next_token_idx'].numpy(), z['next_token_idx'], cfg.hist_cols)
+    assert div is None, f'{name}: greedy tokens diverge from the reference at iteration {div[0]}, rows {div[1]}'
+    for k in ('next_token_idx', 'next_state_idx', 'pred_valid'):
+        assert np.array_equal(out[k].numpy(), z[k]), k
+    for k in ('pos_a', 'head_a', 'pred_traj', 'pred_head', 'pred_state'):
+        _close(out[k].numpy(), z[k], f'{name} {k}')
+
+
 def test_topk_sampling_matches_oracle():
     """top-5 sampling (configs[1] of BASELINE.json) with the shared counter-based sampler: same tokens as the oracle."""
     from infgen_b200.synth import make_scene
