@@ -267,28 +267,27 @@ def run_ours(args, rank, world, local_rank):
         summary_all = [float(summary.item())]
 
     # ---- roofline: profiled replay (events around every launch; no graph) ------------------------------------------
-    roof, klist = None, []
-    if rank == 0:
+    def kernel_profile(hb_, hosts_, n_prof=3):
+        """Per-kernel-class CUDA-event timing of profiled rollouts + the algorithmic work of each class per launch."""
         pk = peaks()
         dec.set_profile(True)
-        dec.load(hb, hosts)
+        dec.load(hb_, hosts_)
         dec.prefill()
-        S = hb.S
-        n_prof = 3
+        S = hb_.S
         e_t = e_m = e_a = 0
         for rep in range(n_prof):
             if rep:
-                dec.load(hb, hosts)
+                dec.load(hb_, hosts_)
                 dec.prefill()
             for it in range(S):
                 dec.step(1)
                 if rep == 0:
-                    e_t += int(dec.debug_read('t_cnt', (hb.R,), np.int32).sum())
-                    e_m += int(dec.debug_read('m_cnt', (hb.R,), np.int32).sum())
-                    e_a += int(dec.debug_read('a_cnt', (hb.R,), np.int32).sum())
+                    e_t += int(dec.debug_read('t_cnt', (hb_.R,), np.int32).sum())
+                    e_m += int(dec.debug_read('m_cnt', (hb_.R,), np.int32).sum())
+                    e_a += int(dec.debug_read('a_cnt', (hb_.R,), np.int32).sum())
         prof = dec.profile()
         dec.set_profile(False)
-        rows = sum(h.n_rows for h in hosts)
+        rows = sum(h.n_rows for h in hosts_)
         iters = S
         # algorithmic work per launch, averaged over the iterations of a rollout (fp32; DESIGN.md "roofline accounting")
         # k_layer (layer.cuh): whole AttentionLayers per launch (all 18 of an iteration when the grid is co-resident).
@@ -307,15 +306,27 @@ def run_ours(args, rank, world, local_rank):
         # the fused stack keeps x/q/s/qr on chip: per row only x in/out, 6 temporal ring rows and 6 agent K|V rows leave
         st_bytes = rows * (1024 + 12 * 1024) + 6 * (et + em + ea) * per_edge + 18 * w_layer
         st_flops = 6 * (tm_flops + a_flops)
+        # row-tile path (node.cuh), 18 launches of each per iteration, averaged over the three layer types:
+        #   k_attn: per edge K row + V row + rhat row + source index; per row q, qr in and agg, ragg, sal out
+        #   k_node: the dense half; weights (1 MB node-packed) once per launch, per row x in/out and the hand-over buffers
+        attn_bytes = (et + em + ea) / 3.0 * per_edge + rows * (512 + 4096 + 512 + 4096 + 32)
+        attn_flops = (et + em + ea) / 3.0 * edge_flops
+        node_flops = rows * 2.0 * (post_mac + pre_mac + pre_kv_mac * 2.0 / 3.0)
+        node_bytes = 1.05e6 + rows * (1024 + 512 + 4096 + 32 + 512 + 512 + 512 + 4096 + 1024 * 2.0 / 3.0)
         model = {
             'k_layer:stack18': ('hbm', st_bytes, st_flops),
             'k_layer:temporal+map': ('hbm', tm_bytes, tm_flops),
             'k_layer:agent': ('hbm', a_bytes, a_flops),
+            'k_attn': ('hbm', attn_bytes, attn_flops),
+            'k_node': ('tensor', node_flops, node_bytes),
             'k_fourier:edges': ('tensor', (et * (4 * (132 * 128 + 128 * 128) + 128 * 128) +
                                            (em + ea) * (3 * (132 * 128 + 128 * 128) + 128 * 128)) * 2.0),
             'k_embed_column': ('tensor', rows * 2.0 * (2 * (132 * 128 + 128 * 128) + 128 * 128 + 512 * 128 + 2 * 128 * 128)),
             'k_heads': ('tensor', rows * 2.0 * (2 * 128 * 128 + 128 * 2048 + 128 * 128)),
         }
+        pipes = {'k_fourier:edges': 'tcgen05.mma kind::tf32, 3xTF32 split (3 tensor-core passes per algorithmic flop), fp32 '
+                                    'accumulate in TMEM'}
+        klist_ = []
         tot = sum(v['ms'] for v in prof.values())
         for name, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms']):
             avg_us = v['ms'] * 1e3 / v['launches']
@@ -334,9 +345,17 @@ def run_ours(args, rank, world, local_rank):
                     ach = work / (avg_us * 1e-6) / 1e12
                     ent.update({'bound': 'tensor', 'achieved': ach, 'peak': pk['bf16_tflops_sustained'],
                                 'unit': 'TFLOP/s', 'frac': ach / pk['bf16_tflops_sustained'],
-                                'algorithmic_flops_per_launch': work, 'pipe': 'fp32 FFMA (reference numerics are fp32)',
+                                'algorithmic_flops_per_launch': work,
+                                'pipe': pipes.get(name, 'fp32 FFMA (reference numerics are fp32)'),
                                 'frac_of_fp32_ffma_peak': ach / 72.0})
-            klist.append(ent)
+                    if len(model[name]) > 2:
+                        ent['algorithmic_bytes_per_launch'] = model[name][2]
+            klist_.append(ent)
+        return klist_, pk
+
+    roof, klist = None, []
+    if rank == 0:
+        klist, pk = kernel_profile(hb, hosts)
         top = next((k for k in klist if 'bound' in k), None)
         traffic = None
         tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
@@ -370,9 +389,12 @@ def run_ours(args, rank, world, local_rank):
                     torch.cuda.synchronize(dev)
                     ms.append(e0.elapsed_time(e1))
             dec.set_stream(None)
-            extra = {'workload': '32 scenes x 64 agents x 91 steps per step (configs[2] shape), inputs in HBM',
+            k32, _ = kernel_profile(hb32, h32, n_prof=2)
+            extra = {'workload': '32 scenes x 64 agents x 91 steps per step (configs[2] shape), inputs in HBM; the '
+                                 'AttentionLayers run on the row-tile path (k_attn + k_node)',
                      'ms_per_step': statistics.mean(ms),
-                     'value': 32 * N_AGENTS * N_STEPS / (statistics.mean(ms) * 1e-3), 'unit': UNIT}
+                     'value': 32 * N_AGENTS * N_STEPS / (statistics.mean(ms) * 1e-3), 'unit': UNIT,
+                     'roofline_kernels': k32}
         except Exception as ex:      # the headline line must still be printed
             extra = {'error': repr(ex)[:200]}
 

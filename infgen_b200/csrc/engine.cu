@@ -150,6 +150,7 @@ struct infgen_engine {
     std::unordered_map<std::string, FourierW> fourier_cache;
     std::vector<float *> wimgs;                         // FourierEmbedding tensor-core weight images (fourier_tc.cuh)
     float *np_blob = nullptr;                           // node-packed motion layers (node.cuh), [18][np::FLOATS]
+    bool node_mma = false;                              // k_node GEMMs on mma.sync 3xTF32 (INFGEN_NODE_GEMM=mma)
     int layer_path = 0;                                 // 0 auto, 1 cluster kernels only, 2 row-tile (k_attn + k_node) only
     bool fourier_tc = true;                             // INFGEN_FOURIER=ffma selects the FFMA row-tile kernel instead
     std::unordered_map<std::string, std::pair<const float *, const float *>> cs;   // layer -> (post, pre) chunks
@@ -529,7 +530,7 @@ static int launch_attn(infgen_engine *e, const RowSpace &rows, const SubArgs &su
     a.rows = rows; a.sub = sub; a.q = fbuf(e, "q"); a.qr = fbuf(e, "qr");
     a.agg = fbuf(e, "agg"); a.ragg = fbuf(e, "ragg"); a.sal = fbuf(e, "sal");
     ProfScope ps(e, KC_ATTN);
-    k_attn<<<dim3((rows.n_total + AM - 1) / AM, NHEAD), NT, 0, e->stream>>>(a);
+    k_attn<<<(rows.n_total + AW - 1) / AW, AW * 32, 0, e->stream>>>(a);
     CKL(); count_launch(e);
     return 0;
 }
@@ -545,7 +546,8 @@ static int launch_node(infgen_engine *e, const RowSpace &rows, const AttnW *lw, 
     a.pre_kv = pre_kv ? 1 : 0; a.kv_out = kv_out; a.kv_ring = kv_ring ? 1 : 0; a.col_add = 0; a.ring = RING;
     a.col_ptr = e->st.col; a.trace_out = trace_out;
     ProfScope ps(e, KC_NODE);
-    k_node<<<(rows.n_total + NM - 1) / NM, NT_S, NodeSmem::BYTES, e->stream>>>(a);
+    if (e->node_mma) k_node<true><<<(rows.n_total + NM - 1) / NM, NT_S, NodeSmem::BYTES, e->stream>>>(a);
+    else k_node<false><<<(rows.n_total + NM - 1) / NM, NT_S, NodeSmem::BYTES, e->stream>>>(a);
     CKL(); count_launch(e);
     return 0;
 }
@@ -1066,7 +1068,13 @@ int32_t infgen_create(const infgen_config *cfg, const float *weights, int64_t n_
     CK(cudaFuncSetAttribute(k_layer<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LayerSmem<8>::BYTES));
     CK(cudaFuncSetAttribute(k_fourier, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FOURIER_SMEM));
     CK(cudaFuncSetAttribute(k_fourier_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ftc::SMEM));
-    CK(cudaFuncSetAttribute(k_node, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NodeSmem::BYTES));
+    CK(cudaFuncSetAttribute(k_node<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NodeSmem::BYTES));
+    CK(cudaFuncSetAttribute(k_node<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NodeSmem::BYTES));
+    {
+        const char *ng = getenv("INFGEN_NODE_GEMM");            // "mma": 3xTF32 mma.sync tiles in k_node instead of FFMA
+        e->node_mma = ng && !strcmp(ng, "mma");
+        if (getenv("INFGEN_VERBOSE")) fprintf(stderr, "infgen_b200: node_mma=%d layer_path=%d fourier_tc=%d\n", (int)e->node_mma, e->layer_path, (int)e->fourier_tc);
+    }
     RET(build_node_weights(e));
     {
         const char *lp = getenv("INFGEN_LAYER_PATH");          // "cluster" | "rows": force one of the two layer paths

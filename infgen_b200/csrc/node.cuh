@@ -2,10 +2,11 @@
 // clusters (layer.cuh is the latency path: 8-CTA clusters, 8 rows each, at most 15 of them co-resident on a B200, so a
 // batch of 32 scenes needs 18 waves of latency-bound phases per layer).  Here a layer is two grid-wide kernels:
 //
-//   k_attn    edge attention (layers.py:78-92) of ALL rows and heads: one CTA = 8 rows x 1 head, one warp per (row, head),
-//             thousands of warps in flight - the gather of K/V rows and relative embeddings is bound by L2/HBM bandwidth,
-//             not by a dependent chain.  Writes the per-head softmax-weighted sums agg / ragg / sal to global memory.
-//             Same code as the attention phase of k_layer (attn_phase<8>): identical numerics.
+//   k_attn    edge attention (layers.py:78-92) of ALL rows: one warp per destination row serves all 8 heads, thousands of
+//             warps in flight - the gather of K/V rows and relative embeddings (1.5 KB per edge, each byte read once) is
+//             bound by L2/HBM bandwidth, not by a dependent chain.  Writes the per-head softmax-weighted sums agg / ragg /
+//             sal to global memory.  Same algebra as the attention phase of k_layer (relative-projection fold, online
+//             softmax, + 1e-16 denominator).
 //   k_node    everything else of the layer for a tile of 16 rows per CTA, whole rows local to the CTA (no cluster, no
 //             DSMEM exchange): to_v_r fold -> gate -> to_out -> LN -> FFN -> LN (layers.py:74-75, 94-99), then the
 //             LayerNorm + q/s/k/v projections and the relative-query fold of the NEXT layer (layers.py:65-71, 106-108).
@@ -51,34 +52,111 @@ struct AttnArgs {
     const float *q, *qr;       // [R][128], [R][8][128]
     float *agg, *ragg, *sal;   // [R][128], [R][8][128], [R][8]
 };
-constexpr int AM = 8;          // rows per CTA (one warp per row)
+constexpr int AW = 4;          // warps (= rows) per CTA
 
-__global__ void __launch_bounds__(NT) k_attn(const AttnArgs a) {
-    __shared__ __align__(16) float sq[AM * 16], sqr[AM * 128], sagg[AM * 16], sragg[AM * LD1], ssal[16], smerge[NWARP * 160];
-    const int c = blockIdx.y, row0 = blockIdx.x * AM;
+// One warp per destination row, ALL 8 heads: lane l holds float4 #l of every 128-vector, i.e. dims 4(l&3).. of head l>>2.
+// An edge costs one coalesced 512-byte row each of rhat, K and V (1.5 KB - the head-per-CTA variant re-read rhat for every
+// head: 5 KB per edge).  The eight relative scores (one per head) are reduced with the butterfly reduce-scatter of
+// attn_phase, which leaves head h's score in lane group h, next to its K/V slice; each lane group runs its own online
+// softmax.  Loads of the next two edges are in flight while two are reduced.
+struct EdgeLd {
+    float4 rh, k, v;
+};
+__global__ void __launch_bounds__(AW * 32) k_attn(const AttnArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    bool any = false;
-#pragma unroll
-    for (int m = 0; m < AM; ++m) any |= a.rows.active(row0 + m);
-    if (!any) return;
+    const int r = blockIdx.x * AW + warp;
+    if (!a.rows.active(r)) return;
+    const SubArgs &A = a.sub;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    {
-        const int m = warp, r = row0 + m;
-        const bool act = a.rows.active(r);
-        st4(sqr + m * 128 + 4 * lane, act ? ld4(a.qr + ((size_t)r * 8 + c) * 128 + 4 * lane) : z4);
-        if (lane < 4) st4(sq + m * 16 + 4 * lane, act ? ld4(a.q + (size_t)r * 128 + 16 * c + 4 * lane) : z4);
+    const float4 q4 = ld4(a.q + (size_t)r * 128 + 4 * lane);
+    float4 qr4[8], ra[8];
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+        qr4[h] = A.has_pos ? ld4(a.qr + ((size_t)r * 8 + h) * 128 + 4 * lane) : z4;
+        ra[h] = z4;
     }
-    __syncthreads();
-    const AttnPre p = attn_prefetch<AM>(a.sub, a.rows, row0);
-    attn_phase<AM>(a.sub, p, c, sq, sqr, sagg, sragg, ssal, smerge);
-    __syncwarp();
-    {
-        const int m = warp, r = row0 + m;
-        if (a.rows.active(r)) {
-            st4(a.ragg + ((size_t)r * 8 + c) * 128 + 4 * lane, ld4(sragg + m * LD1 + 4 * lane));
-            if (lane < 4) st4(a.agg + (size_t)r * 128 + 16 * c + 4 * lane, ld4(sagg + m * 16 + 4 * lane));
-            if (lane == 0) a.sal[(size_t)r * 8 + c] = ssal[m];
+    const int n = A.has_attn ? A.cnt[r] : 0;
+    const int e0 = A.start ? A.start[r] : r * A.stride;
+    const float *rhb = A.rhat + (size_t)e0 * 128 + 4 * lane;
+    const float *kvb = A.kv + 4 * lane;
+    float mx = -INFINITY, den = 0.f;
+    float4 av = z4;
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+
+    for (int blk = 0; blk < n; blk += 32) {
+        const int m = min(32, n - blk);
+        const int srcreg = (lane < m) ? A.src[e0 + blk + lane] : 0;
+        auto load = [&](EdgeLd &L, int i) {                  // edge blk + i (i < 32)
+            const int sj = __shfl_sync(0xffffffffu, srcreg, i & 31);
+            if (i < m) {
+                L.rh = A.has_pos ? ld4(rhb + (size_t)(blk + i) * 128) : z4;
+                const float4 *p = reinterpret_cast<const float4 *>(kvb + (size_t)sj * 256);
+                L.k = __ldcg(p);
+                L.v = __ldcg(p + 32);
+            }
+        };
+        auto compute = [&](const EdgeLd &L) {
+            float pk = dot4(q4, L.k);
+            pk += __shfl_xor_sync(0xffffffffu, pk, 1);
+            pk += __shfl_xor_sync(0xffffffffu, pk, 2);
+            float v[8];
+#pragma unroll
+            for (int h = 0; h < 8; ++h) v[h] = dot4(qr4[h], L.rh);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float recv = __shfl_xor_sync(0xffffffffu, b4 ? v[i] : v[i + 4], 16);
+                v[i] = (b4 ? v[i + 4] : v[i]) + recv;
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const float recv = __shfl_xor_sync(0xffffffffu, b3 ? v[i] : v[i + 2], 8);
+                v[i] = (b3 ? v[i + 2] : v[i]) + recv;
+            }
+            {
+                const float recv = __shfl_xor_sync(0xffffffffu, b2 ? v[0] : v[1], 4);
+                v[0] = (b2 ? v[1] : v[0]) + recv;
+            }
+            float pr = v[0];
+            pr += __shfl_xor_sync(0xffffffffu, pr, 1);
+            pr += __shfl_xor_sync(0xffffffffu, pr, 2);
+            const float p = (pr + pk) * 0.25f;               // head_dim ** -0.5
+            const float mn = fmaxf(mx, p);
+            const float sc = expf(mx - mn);                  // 0 for the first edge
+            const float w = expf(p - mn);
+            den = fmaf(den, sc, w);
+            av.x = fmaf(av.x, sc, w * L.v.x); av.y = fmaf(av.y, sc, w * L.v.y);
+            av.z = fmaf(av.z, sc, w * L.v.z); av.w = fmaf(av.w, sc, w * L.v.w);
+            mx = mn;
+            if (A.has_pos) {
+#pragma unroll
+                for (int h = 0; h < 8; ++h) {
+                    const float sh = __shfl_sync(0xffffffffu, sc, 4 * h), wh = __shfl_sync(0xffffffffu, w, 4 * h);
+                    ra[h].x = fmaf(ra[h].x, sh, wh * L.rh.x); ra[h].y = fmaf(ra[h].y, sh, wh * L.rh.y);
+                    ra[h].z = fmaf(ra[h].z, sh, wh * L.rh.z); ra[h].w = fmaf(ra[h].w, sh, wh * L.rh.w);
+                }
+            }
+        };
+        EdgeLd a0, a1, c0, c1;
+        load(a0, 0);
+        load(a1, 1);
+        for (int i = 0; i < m; i += 4) {
+            load(c0, i + 2);
+            load(c1, i + 3);
+            compute(a0);
+            if (i + 1 < m) compute(a1);
+            load(a0, i + 4);
+            load(a1, i + 5);
+            if (i + 2 < m) compute(c0);
+            if (i + 3 < m) compute(c1);
         }
+    }
+    const float inv = 1.0f / (den + 1e-16f);                 // torch_geometric.utils.softmax denominator
+    st4(a.agg + (size_t)r * 128 + 4 * lane, make_float4(av.x * inv, av.y * inv, av.z * inv, av.w * inv));
+    if ((lane & 3) == 0) a.sal[(size_t)r * 8 + (lane >> 2)] = den * inv;
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+        const float ih = __shfl_sync(0xffffffffu, inv, 4 * h);
+        st4(a.ragg + ((size_t)r * 8 + h) * 128 + 4 * lane, make_float4(ra[h].x * ih, ra[h].y * ih, ra[h].z * ih, ra[h].w * ih));
     }
 }
 
@@ -99,30 +177,34 @@ struct NodeArgs {
     float *trace_out;          // optional copy of the layer output [R][128]
 };
 constexpr int NM = 16;         // rows per CTA
+constexpr int NODE_STAGES = 4;  // weight ring depth (see stream.cuh)
 
 struct NodeSmem {
     static constexpr int RING = 0;
-    static constexpr int X = RING + WS_SMEM_FLOATS;     // [NM][LD1] residual
+    static constexpr int X = RING + ws_smem_floats<NODE_STAGES>();     // [NM][LD1] residual
     static constexpr int S = X + NM * LD1;              // [NM][LD1] skip projection of the post layer
     static constexpr int CAT = S + NM * LD1;            // [NM][LD2] agg2 | LN_dst(x)
     static constexpr int U = CAT + NM * LD2;            // [NM][LD1]
     static constexpr int O = U + NM * LD1;              // [NM][LD1]
     static constexpr int Y = O + NM * LD1;              // [NM][LD1]
     static constexpr int SAL = Y + NM * LD1;            // [NM][8]
-    static constexpr int RAGG = SAL + NM * 8;           // [8 heads][NM][LD1] normalised relative sums; later the FFN hidden
+    static constexpr int RED = SAL + NM * 8;            // [NM][RED_LD] k-split partial sums
+    static constexpr int RAGG = RED + NM * RED_LD;      // [8 heads][NM][LD1] normalised relative sums; later the FFN hidden
     static constexpr int TOTAL = RAGG + 8 * NM * LD1;   //                      tile [NM][LD5] and the q tile [NM][LD1]
     static constexpr size_t BYTES = (size_t)TOTAL * sizeof(float);
     static_assert(NM * LD5 <= 8 * NM * LD1, "FFN hidden tile must fit the ragg region");
     static_assert(BYTES <= 227 * 1024, "shared memory budget");
 };
 
+// MMA: the Linears run on mma.sync TF32 with the 3xTF32 split (stream_gemm_mma) instead of the FFMA register tile
+template <bool MMA>
 __global__ void __launch_bounds__(NT_S) k_node(const NodeArgs a) {
     extern __shared__ __align__(16) float smem_n[];
     using L = NodeSmem;
     float *smem = smem_n;
-    WsSmem wsm(smem + L::RING);
+    WsSmemT<NODE_STAGES> wsm(smem + L::RING);
     float *sx = smem + L::X, *ss = smem + L::S, *scat = smem + L::CAT, *su = smem + L::U, *so = smem + L::O, *sy = smem + L::Y,
-          *ssal = smem + L::SAL, *sr = smem + L::RAGG, *sh = smem + L::RAGG, *sq = smem + L::RAGG;
+          *ssal = smem + L::SAL, *sred = smem + L::RED, *sr = smem + L::RAGG, *sh = smem + L::RAGG, *sq = smem + L::RAGG;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row0 = blockIdx.x * NM;
     unsigned act_mask = 0;
@@ -134,7 +216,7 @@ __global__ void __launch_bounds__(NT_S) k_node(const NodeArgs a) {
     const int has_pos = a.lw.has_pos;
     ws_init(wsm);
     if (warp == NWARP) {
-        if (lane < WS_STAGES) {
+        if (lane < NODE_STAGES) {
             WSeg segs[2];
             int n = 0;
             if (post) segs[n++] = WSeg{a.w_post + (has_pos ? np::VR : np::G), has_pos ? 384 : 352, 512};
@@ -143,8 +225,12 @@ __global__ void __launch_bounds__(NT_S) k_node(const NodeArgs a) {
         }
         return;
     }
-    WsCons ws(wsm);
+    WsConsT<NODE_STAGES> ws(wsm);
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto gemm = [&](const float *xs, int ldx, int K4, auto epi) {
+        if constexpr (MMA) stream_gemm_mma<NM>(ws, xs, ldx, K4, epi);
+        else stream_gemm_ks16(ws, xs, ldx, K4, sred, epi);
+    };
 
     // ---- residual rows, skip projection, attention sums -----------------------------------------------------------------
     for (int m = warp; m < NM; m += NWARP) {
@@ -180,14 +266,14 @@ __global__ void __launch_bounds__(NT_S) k_node(const NodeArgs a) {
             csync();
         }
         // ---- gate: g = sigmoid(Wg [agg2 | xd] + bg);  u = agg2 + g * (s - agg2) ---------------------------------------------
-        stream_gemm<NM>(ws, scat, LD2, 64, [&](int m, int n, float v) {
+        gemm(scat, LD2, 64, [&](int m, int n, float v) {
             const float g = sigmoidf(v + __ldg(a.lw.b_g + n));
             const float ag = scat[m * LD2 + n];
             su[m * LD1 + n] = ag + g * (ss[m * LD1 + n] - ag);
         });
         csync();
         // ---- to_out -------------------------------------------------------------------------------------------------------
-        stream_gemm<NM>(ws, su, LD1, 32, [&](int m, int n, float v) { so[m * LD1 + n] = v + __ldg(a.lw.b_out + n); });
+        gemm(su, LD1, 32, [&](int m, int n, float v) { so[m * LD1 + n] = v + __ldg(a.lw.b_out + n); });
         csync();
         // x1 = x + LN_post(o);  so = LN_ffpre(x1)
         for (int m = warp; m < NM; m += NWARP) {
@@ -200,11 +286,11 @@ __global__ void __launch_bounds__(NT_S) k_node(const NodeArgs a) {
         csync();
         // ---- FFN ----------------------------------------------------------------------------------------------------------
         for (int j = 0; j < 4; ++j)
-            stream_gemm<NM>(ws, so, LD1, 32, [&](int m, int n, float v) {
+            gemm(so, LD1, 32, [&](int m, int n, float v) {
                 sh[m * LD5 + 128 * j + n] = fmaxf(v + __ldg(a.lw.b_ff1 + 128 * j + n), 0.f);
             });
         csync();
-        stream_gemm<NM>(ws, sh, LD5, 128, [&](int m, int n, float v) { sy[m * LD1 + n] = v + __ldg(a.lw.b_ff2 + n); });
+        gemm(sh, LD5, 128, [&](int m, int n, float v) { sy[m * LD1 + n] = v + __ldg(a.lw.b_ff2 + n); });
         csync();
         // x2 = x1 + LN_ffpost(y)
         for (int m = warp; m < NM; m += NWARP) {
@@ -225,18 +311,18 @@ __global__ void __launch_bounds__(NT_S) k_node(const NodeArgs a) {
     for (int m = warp; m < NM; m += NWARP)
         st4(su + m * LD1 + 4 * lane, ln128(ld4(sx + m * LD1 + 4 * lane), a.pw.ln_dst_g, a.pw.ln_dst_b, lane));
     csync();
-    stream_gemm<NM>(ws, su, LD1, 32, [&](int m, int n, float v) {
+    gemm(su, LD1, 32, [&](int m, int n, float v) {
         v += __ldg(a.pw.b_qs + n);
         sq[m * LD1 + n] = v;
         if (active(m)) a.q[(size_t)(row0 + m) * 128 + n] = v;
     });
-    stream_gemm<NM>(ws, su, LD1, 32, [&](int m, int n, float v) {
+    gemm(su, LD1, 32, [&](int m, int n, float v) {
         if (active(m)) a.s[(size_t)(row0 + m) * 128 + n] = v + __ldg(a.pw.b_qs + 128 + n);
     });
     if (a.pre_kv) {
         const int col = (a.col_ptr ? *a.col_ptr : 0) + a.col_add;
         for (int j = 0; j < 2; ++j)
-            stream_gemm<NM>(ws, su, LD1, 32, [&](int m, int n, float v) {
+            gemm(su, LD1, 32, [&](int m, int n, float v) {
                 if (active(m)) {
                     const int r = row0 + m;
                     const size_t slot = a.kv_ring ? ((size_t)r * a.ring + (col & (a.ring - 1))) : (size_t)r;

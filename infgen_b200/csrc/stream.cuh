@@ -25,9 +25,17 @@ constexpr int WS_MAX_SEGS = 12;
 // debug: clock64 of every chunk issue (producer) / acquire completion (consumer warp 0) of CTA 0 of the last kernel
 __device__ long long g_ws_trace[2][256];
 __device__ int g_ws_trace_n[2];
+#ifndef INFGEN_WS_TRACE_SMEM
+#define INFGEN_WS_TRACE_SMEM 0u          // trace only the kernel launched with this much dynamic shared memory (0: all)
+#endif
+__device__ __forceinline__ bool ws_trace_on() {
+    unsigned v;
+    asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(v));
+    return INFGEN_WS_TRACE_SMEM == 0u || v == INFGEN_WS_TRACE_SMEM;
+}
 #define WS_TRACE(which)                                                                                       \
     do {                                                                                                      \
-        if (blockIdx.x == 0 && blockIdx.y == 0) {                                                             \
+        if (blockIdx.x == 0 && blockIdx.y == 0 && ws_trace_on()) {                                                             \
             const int _i = g_ws_trace_n[which]++;                                                             \
             if (_i < 256) g_ws_trace[which][_i] = clock64();                                                  \
         }                                                                                                     \
@@ -45,21 +53,29 @@ struct WSeg {
 
 __device__ __forceinline__ void csync() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
 
-struct WsSmem {
+// ring depth S.  Measured (tools/probe/ws_trace.py, k_embed_column; bench with 3 vs 6 stages): the consumers, not the ring,
+// bound these kernels - the producer runs a full ring ahead and a stage is consumed in ~1.28 k cycles at M = 8 (40 LDS.128
+// per warp and stage x 4 wavefronts x 8 warps), ~1.5 k at M = 16 - so 3 stages are enough and 6 change nothing.
+template <int S>
+__host__ __device__ constexpr int ws_smem_floats() { return S * WS_STAGE_FLOATS + 4 * S; }
+template <int S = WS_STAGES>
+struct WsSmemT {
     float *ring;
     uint64_t *full, *empty;
-    __device__ __forceinline__ explicit WsSmem(float *base)
-        : ring(base), full(reinterpret_cast<uint64_t *>(base + WS_RING_FLOATS)),
-          empty(reinterpret_cast<uint64_t *>(base + WS_RING_FLOATS) + WS_STAGES) {}
+    __device__ __forceinline__ explicit WsSmemT(float *base)
+        : ring(base), full(reinterpret_cast<uint64_t *>(base + S * WS_STAGE_FLOATS)),
+          empty(reinterpret_cast<uint64_t *>(base + S * WS_STAGE_FLOATS) + S) {}
 };
+using WsSmem = WsSmemT<WS_STAGES>;
 
 // all threads, before the roles split (contains __syncthreads)
-__device__ __forceinline__ void ws_init(const WsSmem &ws) {
+template <int S>
+__device__ __forceinline__ void ws_init(const WsSmemT<S> &ws) {
 #ifdef INFGEN_WS_TRACE
-    if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) { g_ws_trace_n[0] = 0; g_ws_trace_n[1] = 0; }
+    if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && ws_trace_on()) { g_ws_trace_n[0] = 0; g_ws_trace_n[1] = 0; }
 #endif
     if (threadIdx.x == 0) {
-        for (int i = 0; i < WS_STAGES; ++i) {
+        for (int i = 0; i < S; ++i) {
             mbar_init(&ws.full[i], 1);
             mbar_init(&ws.empty[i], NWARP);
         }
@@ -70,7 +86,8 @@ __device__ __forceinline__ void ws_init(const WsSmem &ws) {
 
 // producers: lanes 0..WS_STAGES-1 of the producer warp; lane s owns ring stage s and issues every chunk that lands in
 // it (the issue latency of one bulk copy, ~450 cycles from one thread, is spread over the lanes)
-__device__ __forceinline__ void ws_produce(const WsSmem &ws, const WSeg *segs, int n_seg) {
+template <int S>
+__device__ __forceinline__ void ws_produce(const WsSmemT<S> &ws, const WSeg *segs, int n_seg) {
     const int my_stage = threadIdx.x & 31;
     int stage = 0;
     uint32_t phase = 0;
@@ -90,18 +107,19 @@ __device__ __forceinline__ void ws_produce(const WsSmem &ws, const WSeg *segs, i
                         bulk_g2s(dst + i * 512, sg.p + (size_t)(r0 + i) * sg.ld, 2048u, &ws.full[stage]);
                 }
             }
-            if (++stage == WS_STAGES) { stage = 0; phase ^= 1u; }
+            if (++stage == S) { stage = 0; phase ^= 1u; }
         }
     }
 }
 
 // consumer-side cursor (same walk as the producer)
-struct WsCons {
+template <int S = WS_STAGES>
+struct WsConsT {
     float *ring;
     uint64_t *full, *empty;
     int stage;
     uint32_t phase;
-    __device__ __forceinline__ explicit WsCons(const WsSmem &ws) : ring(ws.ring), full(ws.full), empty(ws.empty), stage(0), phase(0) {}
+    __device__ __forceinline__ explicit WsConsT(const WsSmemT<S> &ws) : ring(ws.ring), full(ws.full), empty(ws.empty), stage(0), phase(0) {}
     __device__ __forceinline__ const float *acquire() {
         mbar_wait(&full[stage], phase);
         if (threadIdx.x == 0) WS_TRACE(1);
@@ -110,9 +128,10 @@ struct WsCons {
     __device__ __forceinline__ void release() {
         __syncwarp();
         if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[stage]);
-        if (++stage == WS_STAGES) { stage = 0; phase ^= 1u; }
+        if (++stage == S) { stage = 0; phase ^= 1u; }
     }
 };
+using WsCons = WsConsT<WS_STAGES>;
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Y[m][n] = sum_k X[m][k] W[k][n] for a tile of M rows (8, 16 or 32) and 128 columns; W streamed (next segment of the
@@ -121,8 +140,8 @@ struct WsCons {
 // lanes, RL = 32/CL row lanes.  X: shared, row-major, leading dimension ldx; ldx % 32 == 4 keeps the row-lane loads
 // bank-conflict free.  epi(m, n, value) once per output.  No barrier inside: the caller csync()s before.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int M, typename Epi>
-__device__ __forceinline__ void stream_gemm(WsCons &ws, const float *xs, int ldx, int K4, Epi epi) {
+template <int M, typename Cons, typename Epi>
+__device__ __forceinline__ void stream_gemm(Cons &ws, const float *xs, int ldx, int K4, Epi epi) {
     static_assert(M == 8 || M == 16 || M == 32, "tile rows");
     constexpr int NTT = M / 8, CLN = 16 / NTT, RLN = 32 / CLN;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -168,6 +187,82 @@ __device__ __forceinline__ void stream_gemm(WsCons &ws, const float *xs, int ldx
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// k-split variant for 16-row tiles.  The row-tile GEMMs are bound by shared-memory operand loads (an LDS.128 costs four
+// wavefronts whatever its broadcast degree): the 4 x 2 register tile of stream_gemm<16> needs 6 LDS.128 per 32 FMA.  Here
+// warps 0-3 take the even k4 rows of every stage and warps 4-7 the odd ones, each warp owning 32 columns, so a thread
+// holds a 4 x 4 tile (8 LDS.128 per 64 FMA: 1,024 instead of 1,536 LSU cycles per 16 KB stage) and the two k-halves are
+// added through `red` ([16][RED_LD] floats): each half finalises two of its four row groups.
+// Contains two csync()s; the caller csync()s before (X visible) as for stream_gemm.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int RED_LD = 132;
+template <typename Cons, typename Epi>
+__device__ __forceinline__ void stream_gemm_ks16(Cons &ws, const float *xs, int ldx, int K4, float *red, Epi epi) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kh = warp >> 2, c0 = 32 * (warp & 3) + (lane & 7), rl = lane >> 3;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const float *xr = xs + (size_t)rl * ldx;
+    for (int kb = 0; kb < K4; kb += WS_ROWS) {
+        const float *w = ws.acquire();
+#pragma unroll
+        for (int kk2 = 0; kk2 < WS_ROWS / 2; ++kk2) {
+            const int kk = 2 * kk2 + kh;
+            float4 wv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) wv[j] = ld4(w + (kk * 128 + c0 + 8 * j) * 4);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 x = ld4(xr + (size_t)(4 * i) * ldx + 4 * (kb + kk));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    acc[i][j] = fmaf(x.x, wv[j].x, acc[i][j]);
+                    acc[i][j] = fmaf(x.y, wv[j].y, acc[i][j]);
+                    acc[i][j] = fmaf(x.z, wv[j].z, acc[i][j]);
+                    acc[i][j] = fmaf(x.w, wv[j].w, acc[i][j]);
+                }
+            }
+        }
+        ws.release();
+    }
+    // the half kh hands its partial sums of row groups {2, 3} (kh = 0) / {0, 1} (kh = 1) to the other half (the branches
+    // keep every acc index a compile-time constant: registers, not local memory).  The first csync() orders these
+    // writes after the epilogue reads of a previous call that was not followed by a barrier.
+    csync();
+    if (kh == 0) {
+#pragma unroll
+        for (int i = 2; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) red[(rl + 4 * i) * RED_LD + c0 + 8 * j] = acc[i][j];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) red[(rl + 4 * i) * RED_LD + c0 + 8 * j] = acc[i][j];
+    }
+    csync();
+    if (kh == 0) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int m = rl + 4 * i, n = c0 + 8 * j;
+                epi(m, n, acc[i][j] + red[m * RED_LD + n]);
+            }
+    } else {
+#pragma unroll
+        for (int i = 2; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int m = rl + 4 * i, n = c0 + 8 * j;
+                epi(m, n, red[m * RED_LD + n] + acc[i][j]);
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Tensor-core variant of stream_gemm for M = 16 / 32 row tiles: mma.sync m16n8k8 TF32 with the 3xTF32 error-compensated
 // split (x = hi + lo, both TF32; D += A_lo B_hi + A_hi B_lo + A_hi B_hi, fp32 accumulate), which keeps fp32-level
 // accuracy (the dropped lo*lo term is 2^-22 relative) - the decode loop is closed: a plain TF32 product would flip
@@ -191,8 +286,8 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-template <int M, typename Epi>
-__device__ __forceinline__ void stream_gemm_mma(WsCons &ws, const float *xs, int ldx, int K4, Epi epi) {
+template <int M, typename Cons, typename Epi>
+__device__ __forceinline__ void stream_gemm_mma(Cons &ws, const float *xs, int ldx, int K4, Epi epi) {
     static_assert(M == 16 || M == 32, "tile rows");
     constexpr int MT = M / 16;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -259,8 +354,8 @@ __device__ __forceinline__ void stream_gemm_mma(WsCons &ws, const float *xs, int
 // 1150 cycles per 16 KB weight stage at M = 16, tools/probe/ws_trace.py), i.e. after the 3x split it is no faster than
 // FFMA (128 MAC/clk/SM) - only tcgen05 would be, and that needs 64/128-row tiles a single scene does not have.
 // Build with -DINFGEN_MMA to use the tensor-core variant for the 16/32-row tiles (parity-tested, same tolerances).
-template <int M, typename Epi>
-__device__ __forceinline__ void tile_gemm(WsCons &ws, const float *xs, int ldx, int K4, Epi epi) {
+template <int M, typename Cons, typename Epi>
+__device__ __forceinline__ void tile_gemm(Cons &ws, const float *xs, int ldx, int K4, Epi epi) {
 #ifdef INFGEN_MMA
     if constexpr (M == 16 || M == 32) {
         stream_gemm_mma<M>(ws, xs, ldx, K4, epi);
