@@ -207,21 +207,31 @@ __device__ __forceinline__ void stream_gemm_ks16(Cons &ws, const float *xs, int 
     const float *xr = xs + (size_t)rl * ldx;
     for (int kb = 0; kb < K4; kb += WS_ROWS) {
         const float *w = ws.acquire();
+        // operands of the next k4 row are loaded while the current one is multiplied (the kernel runs 2 warps per
+        // scheduler: without the overlap neither the LSU nor the FMA pipe is half busy).  Fully unrolled: a rolled body
+        // measured 74 instead of 65 us per k_node launch.
+        float4 wv[2][4], xv[2][4];
+        auto load = [&](int b, int kk2) {
+            const int kk = 2 * kk2 + kh;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) wv[b][j] = ld4(w + (kk * 128 + c0 + 8 * j) * 4);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) xv[b][i] = ld4(xr + (size_t)(4 * i) * ldx + 4 * (kb + kk));
+        };
+        load(0, 0);
 #pragma unroll
         for (int kk2 = 0; kk2 < WS_ROWS / 2; ++kk2) {
-            const int kk = 2 * kk2 + kh;
-            float4 wv[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) wv[j] = ld4(w + (kk * 128 + c0 + 8 * j) * 4);
+            const int b = kk2 & 1;
+            if (kk2 + 1 < WS_ROWS / 2) load(b ^ 1, kk2 + 1);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float4 x = ld4(xr + (size_t)(4 * i) * ldx + 4 * (kb + kk));
+                const float4 x = xv[b][i];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    acc[i][j] = fmaf(x.x, wv[j].x, acc[i][j]);
-                    acc[i][j] = fmaf(x.y, wv[j].y, acc[i][j]);
-                    acc[i][j] = fmaf(x.z, wv[j].z, acc[i][j]);
-                    acc[i][j] = fmaf(x.w, wv[j].w, acc[i][j]);
+                    acc[i][j] = fmaf(x.x, wv[b][j].x, acc[i][j]);
+                    acc[i][j] = fmaf(x.y, wv[b][j].y, acc[i][j]);
+                    acc[i][j] = fmaf(x.z, wv[b][j].z, acc[i][j]);
+                    acc[i][j] = fmaf(x.w, wv[b][j].w, acc[i][j]);
                 }
             }
         }
