@@ -361,6 +361,8 @@ def run_ours(args, rank, world, local_rank):
         tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
         if top and os.path.exists(tpath):
             traffic = json.load(open(tpath)).get(top['kernel'])
+            if isinstance(traffic, dict):
+                traffic = traffic.get('agent')
         if top:
             roof = {'kernel': top['kernel'], 'bound': top['bound'], 'achieved': top['achieved'], 'peak': top['peak'],
                     'unit': top['unit'], 'frac': top['frac'], 'traffic': traffic, 'peak_source': pk['source'],

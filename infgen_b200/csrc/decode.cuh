@@ -338,12 +338,10 @@ __global__ void __launch_bounds__(NT) k_advance(const DecState s) {
     if (i >= s.n_rows[b]) return;
     const int col = *s.col, t = *s.iter, T = s.T, nxt = col + 1;
     const int ego = s.ego_row[b];
-    AdvOut eo, me;
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {                 // pass 0: the ego row (no stores), pass 1: this row
-        const AdvOut o = advance_row(s, b, pass == 0 ? ego : i, col, t, pass == 1);
-        if (pass == 0) eo = o; else me = o;
-    }
+    // the ego row (no stores) and this row: two independent chains of dependent loads, inlined back to back so that the
+    // scheduler can overlap them (a rolled two-pass loop serialised them)
+    const AdvOut eo = advance_row(s, b, ego, col, t, false);
+    const AdvOut me = advance_row(s, b, i, col, t, true);
     if (me.st == ST_INVALID) return;
     // ---- ego-centric grid token of the new position (attr_tokenizer.py:77-89, agent_decoder.py:2214) ------------
     const float eth = -__fsub_rn(eo.lh, 1.5707963267948966f);
@@ -352,6 +350,7 @@ __global__ void __launch_bounds__(NT) k_advance(const DecState s) {
     const float qx = __fadd_rn(__fmul_rn(rx, ec), __fmul_rn(ry, -es));
     const float qy = __fadd_rn(__fmul_rn(rx, es), __fmul_rn(ry, ec));
     float bd = INFINITY; int bi = 0x7fffffff;
+#pragma unroll 8
     for (int g = lane; g < s.G; g += 32) {
         const float d = norm2(__fsub_rn(qx, s.grid_cells[(size_t)g * 2]), __fsub_rn(qy, s.grid_cells[(size_t)g * 2 + 1]));
         if (d < bd) { bd = d; bi = g; }

@@ -52,6 +52,8 @@ def _t(x):
 def _np(x) -> np.ndarray:
     """Zero-copy view of a CPU tensor (device tensors are brought to the host first)."""
     if isinstance(x, torch.Tensor):
+        if x.device.type == 'cpu' and not x.requires_grad:
+            return x.numpy()                     # (detach().cpu() alone costs ~7 us per tensor, 16 tensors per scene)
         return x.detach().cpu().numpy()
     return np.asarray(x)
 
@@ -63,15 +65,17 @@ def prepare_scene(data: Dict, map_enc: Dict, cfg: DecoderConfig) -> SceneHost:
     HC, nh = cfg.hist_cols, cfg.num_historical_steps
     state_all = _np(ag['state_idx'])
     filt = state_all[:, HC - 1] != INVALID
-    eval_mask = _np(ag['valid_mask'])[filt, nh - 1]
-    valid = _np(ag['raw_agent_valid_mask'])[filt].copy()
-    pos = _np(ag['token_pos'])[filt]
-    token = _np(ag['token_idx'])[filt]
-    state = state_all[filt]
-    head = _np(ag['token_heading'])[filt]
-    shape = _np(ag['shape'])[filt]
-    type_a = _np(ag['type'])[filt]
-    grid = _np(ag['grid_token_idx'])[filt]
+    # the usual scene keeps every row: skip the boolean-mask gathers then (a copy of each tensor, ~5 us apiece)
+    sel = (lambda a: a) if bool(filt.all()) else (lambda a: a[filt])
+    eval_mask = sel(_np(ag['valid_mask']))[:, nh - 1]
+    valid = sel(_np(ag['raw_agent_valid_mask'])).copy()
+    pos = sel(_np(ag['token_pos']))
+    token = sel(_np(ag['token_idx']))
+    state = sel(state_all)
+    head = sel(_np(ag['token_heading']))
+    shape = sel(_np(ag['shape']))
+    type_a = sel(_np(ag['type']))
+    grid = sel(_np(ag['grid_token_idx']))
     position = _np(ag['position'])
     n_rec = cfg.num_recurrent_steps_val
     if n_rec == -1:
@@ -119,9 +123,9 @@ def prepare_scene(data: Dict, map_enc: Dict, cfg: DecoderConfig) -> SceneHost:
         grid_hist=i32(grid[:, :HC]), tsrc_hist=u8(tsrc), interact_hist=u8(interact_mask), type=i32(type_a),
         shape=f32(shape[:, nh - 1]), pt_pos=f32(pt_pos), pt_ori=f32(_np(data['pt_token']['orientation'])),
         x_pt=f32(_np(map_enc['x_pt'])),
-        agent_id=tt(_np(ag['id'])[filt].copy()), valid_mask=tt(valid), gt_traj=tt(np.ascontiguousarray(position[filt, nh:, :2])),
-        pred_shape=tt(f32(shape[:, HC - 1]).copy()), pos0=tt(f32(position[filt, 0, :2]).copy()),
-        head0=tt(f32(_np(ag['heading'])[filt, 0]).copy()), hist_state_full=tt(np.ascontiguousarray(state[:, :HC], dtype=np.int64)))
+        agent_id=tt(sel(_np(ag['id'])).copy()), valid_mask=tt(valid), gt_traj=tt(np.ascontiguousarray(sel(position)[:, nh:, :2])),
+        pred_shape=tt(f32(shape[:, HC - 1]).copy()), pos0=tt(f32(sel(position)[:, 0, :2]).copy()),
+        head0=tt(f32(sel(_np(ag['heading']))[:, 0]).copy()), hist_state_full=tt(np.ascontiguousarray(state[:, :HC], dtype=np.int64)))
 
 
 class HostBatch:
