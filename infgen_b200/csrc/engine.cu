@@ -1509,6 +1509,13 @@ int64_t infgen_debug_read(infgen_engine *e, const char *name, void *dst, int64_t
     return n;
 }
 
+#ifdef INFGEN_NODE_TRACE
+int32_t infgen_debug_node_trace(long long *dst /* [32] */) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(dst, g_node_trace, sizeof(long long) * 32);
+    return 0;
+}
+#endif
 #ifdef INFGEN_FTC_TRACE
 int32_t infgen_debug_ftc_trace(long long *dst /* [2][3][64] */) {
     cudaDeviceSynchronize();

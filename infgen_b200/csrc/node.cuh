@@ -176,6 +176,12 @@ struct NodeArgs {
     const int *col_ptr;
     float *trace_out;          // optional copy of the layer output [R][128]
 };
+#ifdef INFGEN_NODE_TRACE
+__device__ long long g_node_trace[32];   // debug: clock64 stamps of consumer thread 0 of CTA 0 at the phase boundaries
+#define NODE_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_node_trace[i] = clock64(); } while (0)
+#else
+#define NODE_STAMP(i) do {} while (0)
+#endif
 constexpr int NM = 16;         // rows per CTA
 constexpr int NODE_STAGES = 4;  // weight ring depth (see stream.cuh)
 
@@ -188,8 +194,8 @@ struct NodeSmem {
     static constexpr int O = U + NM * LD1;              // [NM][LD1]
     static constexpr int Y = O + NM * LD1;              // [NM][LD1]
     static constexpr int SAL = Y + NM * LD1;            // [NM][8]
-    static constexpr int RED = SAL + NM * 8;            // [NM][RED_LD] k-split partial sums
-    static constexpr int RAGG = RED + NM * RED_LD;      // [8 heads][NM][LD1] normalised relative sums; later the FFN hidden
+    static constexpr int RED = SAL + NM * 8;            // 2 x [NM][RED_LD] k-split partial sums (alternating)
+    static constexpr int RAGG = RED + 2 * NM * RED_LD;      // [8 heads][NM][LD1] normalised relative sums; later the FFN hidden
     static constexpr int TOTAL = RAGG + 8 * NM * LD1;   //                      tile [NM][LD5] and the q tile [NM][LD1]
     static constexpr size_t BYTES = (size_t)TOTAL * sizeof(float);
     static_assert(NM * LD5 <= 8 * NM * LD1, "FFN hidden tile must fit the ragg region");
@@ -214,6 +220,7 @@ __global__ void __launch_bounds__(NT_S) k_node(const NodeArgs a) {
     auto active = [&](int m) { return (act_mask >> m) & 1u; };
     const bool post = a.w_post != nullptr, pre = a.w_pre != nullptr;
     const int has_pos = a.lw.has_pos;
+    NODE_STAMP(0);
     ws_init(wsm);
     if (warp == NWARP) {
         if (lane < NODE_STAGES) {
@@ -227,9 +234,13 @@ __global__ void __launch_bounds__(NT_S) k_node(const NodeArgs a) {
     }
     WsConsT<NODE_STAGES> ws(wsm);
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    int red_sel = 0;
     auto gemm = [&](const float *xs, int ldx, int K4, auto epi) {
         if constexpr (MMA) stream_gemm_mma<NM>(ws, xs, ldx, K4, epi);
-        else stream_gemm_ks16(ws, xs, ldx, K4, sred, epi);
+        else {
+            stream_gemm_ks16(ws, xs, ldx, K4, sred + red_sel * NM * RED_LD, epi);
+            red_sel ^= 1;
+        }
     };
 
     // ---- residual rows, skip projection, attention sums -----------------------------------------------------------------
@@ -257,6 +268,7 @@ __global__ void __launch_bounds__(NT_S) k_node(const NodeArgs a) {
         }
     }
     csync();
+    NODE_STAMP(1);
     if (post) {
         // ---- agg2 = agg + Wvr ragg' + bvr * sal: warp w owns columns 16w.. = head w, so its A operand is ragg'[w] ---------
         if (has_pos) {
@@ -265,6 +277,7 @@ __global__ void __launch_bounds__(NT_S) k_node(const NodeArgs a) {
             });
             csync();
         }
+        NODE_STAMP(2);
         // ---- gate: g = sigmoid(Wg [agg2 | xd] + bg);  u = agg2 + g * (s - agg2) ---------------------------------------------
         gemm(scat, LD2, 64, [&](int m, int n, float v) {
             const float g = sigmoidf(v + __ldg(a.lw.b_g + n));
@@ -272,9 +285,11 @@ __global__ void __launch_bounds__(NT_S) k_node(const NodeArgs a) {
             su[m * LD1 + n] = ag + g * (ss[m * LD1 + n] - ag);
         });
         csync();
+        NODE_STAMP(3);
         // ---- to_out -------------------------------------------------------------------------------------------------------
         gemm(su, LD1, 32, [&](int m, int n, float v) { so[m * LD1 + n] = v + __ldg(a.lw.b_out + n); });
         csync();
+        NODE_STAMP(4);
         // x1 = x + LN_post(o);  so = LN_ffpre(x1)
         for (int m = warp; m < NM; m += NWARP) {
             float4 o = ld4(so + m * LD1 + 4 * lane);
@@ -284,14 +299,17 @@ __global__ void __launch_bounds__(NT_S) k_node(const NodeArgs a) {
             st4(so + m * LD1 + 4 * lane, ln128(x1, a.lw.ln_ffpre_g, a.lw.ln_ffpre_b, lane));
         }
         csync();
+        NODE_STAMP(5);
         // ---- FFN ----------------------------------------------------------------------------------------------------------
         for (int j = 0; j < 4; ++j)
             gemm(so, LD1, 32, [&](int m, int n, float v) {
                 sh[m * LD5 + 128 * j + n] = fmaxf(v + __ldg(a.lw.b_ff1 + 128 * j + n), 0.f);
             });
         csync();
+        NODE_STAMP(6);
         gemm(sh, LD5, 128, [&](int m, int n, float v) { sy[m * LD1 + n] = v + __ldg(a.lw.b_ff2 + n); });
         csync();
+        NODE_STAMP(7);
         // x2 = x1 + LN_ffpost(y)
         for (int m = warp; m < NM; m += NWARP) {
             const int r = row0 + m;
@@ -306,6 +324,7 @@ __global__ void __launch_bounds__(NT_S) k_node(const NodeArgs a) {
         }
         csync();
     }
+    NODE_STAMP(8);
     if (!pre) return;
     // ---- LayerNorm + q/s/k/v projections + relative-query fold of the next layer (layers.py:65-71, 106-108) ---------------
     for (int m = warp; m < NM; m += NWARP)
@@ -319,6 +338,14 @@ __global__ void __launch_bounds__(NT_S) k_node(const NodeArgs a) {
     gemm(su, LD1, 32, [&](int m, int n, float v) {
         if (active(m)) a.s[(size_t)(row0 + m) * 128 + n] = v + __ldg(a.pw.b_qs + 128 + n);
     });
+    NODE_STAMP(9);
+    // slice of Wkr for the relative-query fold below (thread = head `warp`, channels 4 lane ..): requested now, so that
+    // the loads are in flight during the k/v projections
+    float4 wk[16];
+    if (a.pw.has_pos) {
+#pragma unroll
+        for (int d = 0; d < 16; ++d) wk[d] = ldg4(a.pw.w_kr + (size_t)(16 * warp + d) * 128 + 4 * lane);
+    }
     if (a.pre_kv) {
         const int col = (a.col_ptr ? *a.col_ptr : 0) + a.col_add;
         for (int j = 0; j < 2; ++j)
@@ -331,29 +358,33 @@ __global__ void __launch_bounds__(NT_S) k_node(const NodeArgs a) {
             });
     }
     csync();
+    NODE_STAMP(10);
     // qr[m][h][ch] = g_r[ch] * sum_d q[m][16h+d] * Wkr[16h+d][ch]
+    // thread = (head h = warp, channels 4 lane .. 4 lane + 3): the 16 x 4 slice of Wkr stays in registers and a row costs
+    // 4 broadcast LDS.128 of q for 64 FMA (one thread per channel needed 4 LDS.128 per 16 FMA and was LSU-bound:
+    // 13-15 k cycles for 262 k MAC, now ~3 k)
     if (a.pw.has_pos) {
-        const int ch = tid & 127;
-        const float g = __ldg(a.pw.ln_r_g + ch);
-        for (int h = tid >> 7; h < 8; h += 2) {
-            float wk[16];
+        const int h = warp;
+        const float4 g4 = ldg4(a.pw.ln_r_g + 4 * lane);
+        for (int m = 0; m < NM; ++m) {
+            if (!active(m)) continue;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int d = 0; d < 16; ++d) wk[d] = __ldg(a.pw.w_kr + (size_t)(16 * h + d) * 128 + ch);
-            for (int m = 0; m < NM; ++m) {
-                if (!active(m)) continue;
-                float acc = 0.f;
+            for (int d4 = 0; d4 < 4; ++d4) {
+                const float4 qv = ld4(sq + m * LD1 + 16 * h + 4 * d4);
+                const float qd[4] = {qv.x, qv.y, qv.z, qv.w};
 #pragma unroll
-                for (int d4 = 0; d4 < 4; ++d4) {
-                    const float4 qv = ld4(sq + m * LD1 + 16 * h + 4 * d4);
-                    acc = fmaf(qv.x, wk[4 * d4 + 0], acc);
-                    acc = fmaf(qv.y, wk[4 * d4 + 1], acc);
-                    acc = fmaf(qv.z, wk[4 * d4 + 2], acc);
-                    acc = fmaf(qv.w, wk[4 * d4 + 3], acc);
+                for (int i = 0; i < 4; ++i) {
+                    const float4 w = wk[4 * d4 + i];
+                    acc.x = fmaf(qd[i], w.x, acc.x); acc.y = fmaf(qd[i], w.y, acc.y);
+                    acc.z = fmaf(qd[i], w.z, acc.z); acc.w = fmaf(qd[i], w.w, acc.w);
                 }
-                a.qr[((size_t)(row0 + m) * 8 + h) * 128 + ch] = acc * g;
             }
+            st4(a.qr + ((size_t)(row0 + m) * 8 + h) * 128 + 4 * lane,
+                make_float4(acc.x * g4.x, acc.y * g4.y, acc.z * g4.z, acc.w * g4.w));
         }
     }
+    NODE_STAMP(11);
 }
 
 }  // namespace infgen

@@ -192,7 +192,7 @@ __device__ __forceinline__ void stream_gemm(Cons &ws, const float *xs, int ldx, 
 // warps 0-3 take the even k4 rows of every stage and warps 4-7 the odd ones, each warp owning 32 columns, so a thread
 // holds a 4 x 4 tile (8 LDS.128 per 64 FMA: 1,024 instead of 1,536 LSU cycles per 16 KB stage) and the two k-halves are
 // added through `red` ([16][RED_LD] floats): each half finalises two of its four row groups.
-// Contains two csync()s; the caller csync()s before (X visible) as for stream_gemm.
+// Contains one csync(); the caller csync()s before (X visible) as for stream_gemm and alternates `red` between two buffers.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int RED_LD = 132;
 template <typename Cons, typename Epi>
@@ -238,9 +238,9 @@ __device__ __forceinline__ void stream_gemm_ks16(Cons &ws, const float *xs, int 
         ws.release();
     }
     // the half kh hands its partial sums of row groups {2, 3} (kh = 0) / {0, 1} (kh = 1) to the other half (the branches
-    // keep every acc index a compile-time constant: registers, not local memory).  The first csync() orders these
-    // writes after the epilogue reads of a previous call that was not followed by a barrier.
-    csync();
+    // keep every acc index a compile-time constant: registers, not local memory).  Callers alternate between two `red`
+    // buffers from call to call, so these writes cannot overtake the epilogue reads of the previous call (a thread can be
+    // at most one call ahead: the csync() below needs every thread).
     if (kh == 0) {
 #pragma unroll
         for (int i = 2; i < 4; ++i)
