@@ -149,6 +149,7 @@ struct infgen_engine {
     float *cs_blob = nullptr;                           // cluster-sliced AttentionLayer chunks (layer.cuh)
     std::unordered_map<std::string, FourierW> fourier_cache;
     std::vector<float *> wimgs;                         // FourierEmbedding tensor-core weight images (fourier_tc.cuh)
+    std::unordered_map<std::string, const float *> npk;   // layer prefix -> node-packed copy
     float *np_blob = nullptr;                           // node-packed motion layers (node.cuh), [18][np::FLOATS]
     bool node_mma = false;                              // k_node GEMMs on mma.sync 3xTF32 (INFGEN_NODE_GEMM=mma)
     int layer_path = 0;                                 // 0 auto, 1 cluster kernels only, 2 row-tile (k_attn + k_node) only
@@ -213,6 +214,8 @@ static AttnW make_attn(infgen_engine *e, const std::string &p, bool has_pos) {
     w.has_pos = has_pos ? 1 : 0;
     auto it = e->cs.find(p);
     if (it != e->cs.end()) { w.cs_post = it->second.first; w.cs_pre = it->second.second; }
+    auto nt = e->npk.find(p);
+    if (nt != e->npk.end()) w.npk = nt->second;
     return w;
 }
 
@@ -521,14 +524,23 @@ static int build_node_weights(infgen_engine *e) {
             pack(w.w_qs, np::QS, 32, 256); pack(w.w_kv, np::KV, 32, 256);
             CKL();
             w.npk = d;
+            static const char *names[3] = {"t_attn_layers.", "pt2a_attn_layers.", "a2a_attn_layers."};
+            e->npk[std::string(names[s]) + std::to_string(i)] = d;
         }
     return 0;
 }
-static int launch_attn(infgen_engine *e, const RowSpace &rows, const SubArgs &sub) {
+struct NodeBufs {              // hand-over buffers of the row-tile path
+    float *x, *q, *s, *qr, *agg, *ragg, *sal;
+};
+static NodeBufs scene_node_bufs(infgen_engine *e) {
+    return NodeBufs{fbuf(e, "x"), fbuf(e, "q"), fbuf(e, "s"), fbuf(e, "qr"), fbuf(e, "agg"), fbuf(e, "ragg"), fbuf(e, "sal")};
+}
+static int launch_attn(infgen_engine *e, const RowSpace &rows, const SubArgs &sub, const NodeBufs *nb = nullptr) {
+    const NodeBufs b = nb ? *nb : scene_node_bufs(e);
     AttnArgs a;
     memset(&a, 0, sizeof(a));
-    a.rows = rows; a.sub = sub; a.q = fbuf(e, "q"); a.qr = fbuf(e, "qr");
-    a.agg = fbuf(e, "agg"); a.ragg = fbuf(e, "ragg"); a.sal = fbuf(e, "sal");
+    a.rows = rows; a.sub = sub; a.q = b.q; a.qr = b.qr;
+    a.agg = b.agg; a.ragg = b.ragg; a.sal = b.sal;
     ProfScope ps(e, KC_ATTN);
     k_attn<<<(rows.n_total + AW - 1) / AW, AW * 32, 0, e->stream>>>(a);
     CKL(); count_launch(e);
@@ -536,11 +548,12 @@ static int launch_attn(infgen_engine *e, const RowSpace &rows, const SubArgs &su
 }
 // finish layer `lw` (NULL: nothing to finish) and project the inputs of layer `pw` (NULL: none)
 static int launch_node(infgen_engine *e, const RowSpace &rows, const AttnW *lw, const AttnW *pw, bool pre_kv, float *kv_out,
-                       bool kv_ring, float *trace_out) {
+                       bool kv_ring, float *trace_out, const NodeBufs *nb = nullptr) {
+    const NodeBufs b = nb ? *nb : scene_node_bufs(e);
     NodeArgs a;
     memset(&a, 0, sizeof(a));
-    a.rows = rows; a.x = fbuf(e, "x"); a.agg = fbuf(e, "agg"); a.ragg = fbuf(e, "ragg"); a.sal = fbuf(e, "sal");
-    a.q = fbuf(e, "q"); a.s = fbuf(e, "s"); a.qr = fbuf(e, "qr");
+    a.rows = rows; a.x = b.x; a.agg = b.agg; a.ragg = b.ragg; a.sal = b.sal;
+    a.q = b.q; a.s = b.s; a.qr = b.qr;
     if (lw) { a.w_post = lw->npk; a.lw = *lw; }
     if (pw) { a.w_pre = pw->npk; a.pw = *pw; }
     a.pre_kv = pre_kv ? 1 : 0; a.kv_out = kv_out; a.kv_ring = kv_ring ? 1 : 0; a.col_add = 0; a.ring = RING;
@@ -1589,6 +1602,31 @@ int32_t infgen_op_attention_layer(infgen_engine *e, const char *layer, const flo
         }
     }
     if (!d_x || !d_out || !d_kv || !d_src) return fail(INFGEN_ERR_CUDA, "temporary allocation failed");
+    if (e->layer_path == 2 && w.npk) {
+        // row-tile path (node.cuh): projections -> k_attn -> k_node, on a copy of x
+        NodeBufs nb{d_out, d_q, d_s, d_qr, tmp.alloc<float>((size_t)n_dst * 128), tmp.alloc<float>((size_t)n_dst * 1024),
+                    tmp.alloc<float>((size_t)n_dst * 8)};
+        if (!nb.agg || !nb.ragg || !nb.sal) return fail(INFGEN_ERR_CUDA, "temporary allocation failed");
+        CK(cudaMemcpyAsync(d_out, d_x, (size_t)n_dst * 128 * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
+        const RowSpace rows = flat_rows(n_dst);
+        RET(launch_node(e, rows, nullptr, &w, !bip, d_kv, false, nullptr, &nb));
+        if (bip) {
+            float *d_xs = tmp.upload(x_src, (size_t)n_src * 128);
+            KvArgs ka;
+            memset(&ka, 0, sizeof(ka));
+            ka.n = n_src; ka.x = d_xs; ka.w[0] = w; ka.out[0] = d_kv;
+            k_kv_project<16><<<dim3((n_src + 15) / 16, 1), NT, 0, e->stream>>>(ka);
+            CKL(); count_launch(e);
+        }
+        SubArgs g;
+        memset(&g, 0, sizeof(g));
+        g.has_attn = 1; g.has_pos = has_pos ? 1 : 0; g.kv = d_kv; g.cnt = d_cnt; g.start = d_start; g.src = d_src; g.rhat = d_rhat;
+        RET(launch_attn(e, rows, g, &nb));
+        RET(launch_node(e, rows, &w, nullptr, false, nullptr, false, nullptr, &nb));
+        CK(cudaStreamSynchronize(e->stream));
+        CK(cudaMemcpy(out, d_out, (size_t)n_dst * 128 * sizeof(float), cudaMemcpyDeviceToHost));
+        return 0;
+    }
     const int saved_tile = e->row_tile;
     e->row_tile = (n_dst + 3) / 4 <= MAX_CLUSTERS ? 4 : 8;
     // launch 1: projections of every row (K/V of all rows must exist before any row attends)

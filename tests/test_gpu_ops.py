@@ -68,6 +68,25 @@ def test_mlp_layer(dec_and_sd, name, n_out):
     _close(ops.mlp_layer(dec, name, x, n_out), mlp_layer(sd, name, x), name)
 
 
+@pytest.fixture(scope='module')
+def dec_rows_and_sd():
+    """An engine whose AttentionLayers run on the row-tile path (k_attn + k_node): the switch is read at creation."""
+    import os
+    from infgen_b200.agent_decoder import B200AgentDecoder
+    old = os.environ.get('INFGEN_LAYER_PATH')
+    os.environ['INFGEN_LAYER_PATH'] = 'rows'
+    try:
+        sd = make_state_dict(3)
+        dec = B200AgentDecoder(sd, DecoderConfig(disable_insertion=True), use_cuda_graph=False)
+    finally:
+        if old is None:
+            del os.environ['INFGEN_LAYER_PATH']
+        else:
+            os.environ['INFGEN_LAYER_PATH'] = old
+    yield dec, sd
+    dec.close()
+
+
 def _random_graph(n_src, n_dst, max_deg, g, bipartite):
     src, dst = [], []
     for i in range(n_dst):
@@ -91,6 +110,24 @@ def test_attention_layer(dec_and_sd, layer, bipartite, n_dst, n_src, max_deg):
     from oracle.agent_decoder_oracle import attention_layer
     dec, sd = dec_and_sd
     g = torch.Generator().manual_seed(4)
+    x_dst = torch.randn(n_dst, 128, generator=g)
+    x_src = torch.randn(n_src, 128, generator=g) if bipartite else x_dst
+    ei = _random_graph(n_src, n_dst, max_deg, g, bipartite)
+    r = torch.randn(ei.shape[1], 128, generator=g)
+    want = attention_layer(sd, layer, x_src, x_dst, r, ei[0], ei[1], bipartite)
+    got = ops.attention_layer(dec, layer, (x_src, x_dst) if bipartite else x_dst, r, ei)
+    _close(got, want, layer)
+
+
+@pytest.mark.parametrize('layer,bipartite,n_dst,n_src,max_deg', [
+    ('t_attn_layers.0', False, 37, 37, 12), ('pt2a_attn_layers.5', True, 41, 300, 5), ('a2a_attn_layers.1', False, 600, 600, 70)])
+def test_attention_layer_row_tile_path(dec_rows_and_sd, layer, bipartite, n_dst, n_src, max_deg):
+    """The same operator through k_attn (one warp per row, all heads) + k_node (16-row tiles): ragged tiles, rows without
+    edges, more than 64 edges per row (two source blocks), bipartite sources."""
+    from infgen_b200 import ops
+    from oracle.agent_decoder_oracle import attention_layer
+    dec, sd = dec_rows_and_sd
+    g = torch.Generator().manual_seed(5)
     x_dst = torch.randn(n_dst, 128, generator=g)
     x_src = torch.randn(n_src, 128, generator=g) if bipartite else x_dst
     ei = _random_graph(n_src, n_dst, max_deg, g, bipartite)
