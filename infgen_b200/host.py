@@ -265,39 +265,46 @@ def assemble_outputs(batch: HostBatch, scenes: Sequence[SceneHost], cfg: Decoder
     reference (`num_init_agent`, :2310)."""
     outs = []
     nh, HC = cfg.num_historical_steps, cfg.hist_cols
+    tt = torch.from_numpy
+    # numpy views of the (pinned) result buffers: assembling with numpy costs ~1 us per op against 5-8 us for torch
+    o_hist_traj, o_hist_head = batch.out_hist_traj.numpy(), batch.out_hist_head.numpy()
+    o_traj, o_head, o_state = batch.out_pred_traj.numpy(), batch.out_pred_head.numpy(), batch.out_pred_state.numpy()
+    shape_tab = np.zeros((4, 3), dtype=np.float32)               # eval shape per predicted type; other types stay zero
+    for ti, key in enumerate(('vehicle', 'pedstrain', 'cyclist')):
+        shape_tab[ti] = AGENT_SHAPE[key]
     for b, s in enumerate(scenes):
         r0, n0 = b * batch.cap, s.n_rows
         n = int(batch.out_n_rows[b]) if batch.insertion else n0
         sl = slice(r0, r0 + n)
         n_rec = s.n_rec
-        pred_traj = torch.zeros(n, nh + n_rec, 2)
-        pred_head = torch.zeros(n, nh + n_rec)
-        pred_state = torch.zeros(n, nh + n_rec)
-        pred_traj[:n0, 0] = s.pos0
-        pred_head[:n0, 0] = s.head0
-        pred_traj[:n0, 1:nh] = batch.out_hist_traj[r0:r0 + n0]
-        pred_head[:n0, 1:nh] = batch.out_hist_head[r0:r0 + n0]
-        pred_state[:n0, 1:nh] = s.hist_state_full.repeat_interleave(cfg.shift, dim=1).float()
+        pred_traj = np.zeros((n, nh + n_rec, 2), dtype=np.float32)
+        pred_head = np.zeros((n, nh + n_rec), dtype=np.float32)
+        pred_state = np.zeros((n, nh + n_rec), dtype=np.float32)
+        pred_traj[:n0, 0] = s.pos0.numpy()
+        pred_head[:n0, 0] = s.head0.numpy()
+        pred_traj[:n0, 1:nh] = o_hist_traj[r0:r0 + n0]
+        pred_head[:n0, 1:nh] = o_hist_head[r0:r0 + n0]
+        pred_state[:n0, 1:nh] = np.repeat(s.hist_state_full.numpy(), cfg.shift, axis=1)
         if n_rec:
-            pred_traj[:, nh:] = batch.out_pred_traj[sl, :n_rec]
-            pred_head[:, nh:] = batch.out_pred_head[sl, :n_rec]
-            pred_state[:, nh:] = batch.out_pred_state[sl, :n_rec]
+            pred_traj[:, nh:] = o_traj[sl, :n_rec]
+            pred_head[:, nh:] = o_head[sl, :n_rec]
+            pred_state[:, nh:] = o_state[sl, :n_rec]
         pred_valid = (pred_state != INVALID) & (pred_state != ENTER)
-        type_a = torch.from_numpy(s.type).long()
+        type_np = s.type.astype(np.int64)
         pred_shape = s.pred_shape
         agent_id = s.agent_id
         if n > n0:                                              # appended agents (:1916-1918, 1955-1956)
-            type_a = torch.cat([type_a, batch.out_pred_type[r0 + n0:r0 + n].long()])
+            type_np = np.concatenate([type_np, batch.out_pred_type[r0 + n0:r0 + n].numpy().astype(np.int64)])
             pred_shape = torch.cat([pred_shape, batch.out_pred_shape[r0 + n0:r0 + n].clone()])
             agent_id = torch.cat([agent_id, int(agent_id.max()) + 1 + torch.arange(n - n0, dtype=agent_id.dtype)])
-        eval_shape = torch.zeros_like(pred_shape)
-        for ti, key in enumerate(('vehicle', 'pedstrain', 'cyclist')):
-            eval_shape[type_a == ti] = torch.tensor(AGENT_SHAPE[key])
+        eval_shape = tt(shape_tab[np.clip(type_np, 0, 3)])
+        type_a = tt(type_np)
+        pred_traj, pred_head, pred_state, pred_valid = tt(pred_traj), tt(pred_head), tt(pred_state), tt(pred_valid)
         ncol = HC + s.n_iters
         out = {
             'ego_index': s.ego_row, 'agent_id': agent_id, 'valid_mask': s.valid_mask,
             'pos_a': batch.out_pos[sl].clone(), 'head_a': batch.out_head[sl].clone(), 'gt_traj': s.gt_traj,
-            'pred_traj': pred_traj, 'pred_head': pred_head, 'pred_type': type_a.clone(), 'pred_state': pred_state,
+            'pred_traj': pred_traj, 'pred_head': pred_head, 'pred_type': type_a, 'pred_state': pred_state,
             'pred_z': torch.zeros_like(pred_traj[..., 0]), 'pred_shape': pred_shape, 'eval_shape': eval_shape,
             'pred_valid': pred_valid,
             'next_token_idx': batch.out_next_token[sl, :ncol].long(),
