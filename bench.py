@@ -441,8 +441,10 @@ def run_ours(args, rank, world, local_rank):
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': max(3, args.warmup), 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': f'configs[1]: {args.scenes} scene(s)/GPU x 64 agents x 91 steps (16 decode '
-                                   'iterations), top-5 sampling, 2048 map tokens/scene, random-init weights',
+            'config': {'workload': (('configs[1]: 1 scene/GPU' if args.scenes == 1 else
+                                     f'configs[2]/[3] shape: {args.scenes} scenes/GPU') +
+                                    ' x 64 agents x 91 steps (16 decode iterations), top-5 sampling, 2048 map '
+                                    'tokens/scene, random-init weights'),
                        'parallelism': f'scenes sharded 1 rollout stream per GPU x {world}', 'l2': 'flushed between '
                        'steps (256 MiB write)', 'timed_region': 'load_scenes (device copies + map K/V cache) + prefill '
                        '+ 16 iterations (CUDA graph) + result copies'},
