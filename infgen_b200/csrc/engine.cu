@@ -857,6 +857,13 @@ static int enqueue_edges(infgen_engine *e, int col_add) {
     fj[0].normalize = 1; fj[0].dim = 3;       // the large one first: agent<->agent
     fj[0].n_slots = R * e->cap; fj[0].cnt = s.a_cnt; fj[0].stride = e->cap;
     fj[0].raw = s.a_raw; fj[0].w = e->f_a; fj[0].out = fbuf(e, "rhat_a");
+    if (e->fourier_tc && (R * e->cap + ftc::TM - 1) / ftc::TM > 148) {
+        // batches: walk a compact list of the valid agent<->agent slots (a single scene's tiles fit one wave anyway)
+        int *list = (int *)e->bufs["a_slots"].p, *n_list = list + (size_t)R * e->cap;
+        k_slot_compact<<<1, 1024, 0, e->stream>>>(s.a_cnt, R, e->cap, list, n_list);
+        CKL(); count_launch(e);
+        fj[0].slot_list = list; fj[0].n_list = n_list;
+    }
     fj[1].normalize = 1; fj[1].dim = 4;
     fj[1].n_slots = R * s.W; fj[1].cnt = s.t_cnt; fj[1].stride = s.W; fj[1].raw = s.t_raw; fj[1].w = e->f_t;
     fj[1].out = fbuf(e, "rhat_t");
@@ -1261,6 +1268,7 @@ int32_t infgen_load_scenes(infgen_engine *e, const infgen_scene_batch *b, int32_
     RET(ensure_t(e, "kv_m", (size_t)6 * std::max(P, 1) * 256, &tmp));
     RET(ensure_t(e, "rhat_t", (size_t)R * W * 128, &tmp)); RET(ensure_t(e, "rhat_m", (size_t)R * MM * 128, &tmp));
     RET(ensure_t(e, "rhat_a", (size_t)R * cap * 128, &tmp));
+    { int *itmp; RET(ensure_t(e, "a_slots", (size_t)R * cap + 4, &itmp)); }
     RET(ensure_t(e, "cat_tab", (size_t)(R + 1) * 128, &tmp)); RET(ensure_t(e, "shape_rows", (size_t)(R + 1) * 4, &tmp));
     RET(ensure_t(e, "hist_traj", (size_t)R * HC * 5 * 2, &tmp)); RET(ensure_t(e, "hist_head", (size_t)R * HC * 5, &tmp));
     if (getenv("INFGEN_TSTAMP")) { long long *ts; RET(ensure_t(e, "tstamp", 512, &ts)); }

@@ -55,7 +55,8 @@ constexpr int SM_B = 0;
 constexpr int SM_EX = SM_B + NB * CHUNK;         // [2 buffers][4 quarters][128] LayerNorm partials
 constexpr int SM_RAW = SM_EX + 1024;              // [128][4]
 constexpr int SM_VALID = SM_RAW + 512;           // [128] int
-constexpr int SM_BAR = SM_VALID + 128;           // full_a[NA] empty_a[NA] full_b[NB] empty_b[NB] g1[4] g2 g3 acc_free (uint64 each)
+constexpr int SM_SLOT = SM_VALID + 128;          // [128] int: slot of every row of the tile
+constexpr int SM_BAR = SM_SLOT + 128;           // full_a[NA] empty_a[NA] full_b[NB] empty_b[NB] g1[4] g2 g3 acc_free (uint64 each)
 constexpr int N_BAR = 2 * NA + 2 * NB + 7;
 constexpr int SM_TMEM = SM_BAR + 2 * N_BAR;
 constexpr int SM_FLOATS = SM_TMEM + 4;
@@ -184,6 +185,46 @@ __device__ long long g_ftc_trace[2][3][64];
 #define FTC_STAMP(stream) do {} while (0)
 #endif
 
+// Compact list of the valid slots of a strided slot space [n_rows][stride] (slot valid iff k < cnt[row]): one CTA, block
+// scan over the rows.  list[off(row) + k] = row * stride + k, *n_list = total.  Batches only: a2a rows hold ~40 valid of 64
+// slots, so the strided walk spends a third of the 128-slot tiles on padding.
+__global__ void __launch_bounds__(1024) k_slot_compact(const int *__restrict__ cnt, int n_rows, int stride, int *__restrict__ list,
+                                                        int *__restrict__ n_list) {
+    __shared__ int s_warp[32];
+    __shared__ int s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int r0 = 0; r0 < n_rows; r0 += 1024) {
+        const int r = r0 + tid;
+        const int c = r < n_rows ? min(cnt[r], stride) : 0;
+        int x = c;                                           // inclusive scan inside the warp
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += y;
+            }
+            s_warp[lane] = w;                                // inclusive prefix of the warp totals
+        }
+        __syncthreads();
+        const int off = s_base + (warp ? s_warp[warp - 1] : 0) + x - c;
+        for (int k = 0; k < c; ++k) list[off + k] = r * stride + k;
+        __syncthreads();
+        if (tid == 0) s_base += s_warp[31];
+        __syncthreads();
+    }
+    if (tid == 0) *n_list = s_base;
+}
+
 // weight image builder: 4 chunks of one packed [32 k4][128][4] matrix -> [hi | lo] chunks.  fourier_order: the K order of
 // G1 (chunk c = k4 rows 4c .. 4c+3 (cos of 16 freqs) then 16+4c .. 16+4c+3 (their sin)); else K in natural order
 __global__ void k_wimg_split(const float *__restrict__ src, float *__restrict__ dst, int fourier_order) {
@@ -226,10 +267,17 @@ __global__ void __launch_bounds__(ftc::THREADS, 1) k_fourier_tc(const FourierBat
     int trace_n = 0;
 #endif
     int v = 0;
+    int *s_slot = reinterpret_cast<int *>(smem + SM_SLOT);
     if (tid < TM) {
-        const int s = s0 + tid;
-        if (s < a.n_slots) v = a.cnt ? ((s % a.stride) < a.cnt[s / a.stride]) : 1;
+        int s = s0 + tid;
+        if (a.slot_list) {                        // compact list of valid slots: no tile is spent on padding
+            v = s < *a.n_list;
+            s = v ? a.slot_list[s] : 0;
+        } else if (s < a.n_slots) {
+            v = a.cnt ? ((s % a.stride) < a.cnt[s / a.stride]) : 1;
+        }
         s_valid[tid] = v;
+        s_slot[tid] = s;
         for (int d = 0; d < 4; ++d) sraw[tid * 4 + d] = (v && d < D) ? a.raw[(size_t)s * D + d] : 0.f;
     }
     if (!__syncthreads_or(v)) return;
@@ -466,7 +514,7 @@ __global__ void __launch_bounds__(ftc::THREADS, 1) k_fourier_tc(const FourierBat
             for (int i = 0; i < 32; ++i) val[i] = (val[i] - mean) * rstd;
         }
         if (s_valid[r]) {
-            float *o = a.out + (size_t)(s0 + r) * 128 + 32 * qd;
+            float *o = a.out + (size_t)s_slot[r] * 128 + 32 * qd;
 #pragma unroll
             for (int i4 = 0; i4 < 8; ++i4) st4(o + 4 * i4, make_float4(val[4 * i4], val[4 * i4 + 1], val[4 * i4 + 2], val[4 * i4 + 3]));
         }

@@ -117,6 +117,8 @@ struct FourierArgs {
     const int *cat_idx;        // [slots] row of cat_tab (when cat_tab != NULL; NULL -> row = slot)
     float *out;                // [slots][128]
     int normalize;             // 1: store (y - mean) / std of the output (input of every layer's attn_prenorm_r)
+    const int *slot_list;      // optional compact list of the valid slots (k_slot_compact); tiles walk it instead of
+    const int *n_list;         //   the strided slot space: *n_list entries (k_fourier_tc only)
 };
 // several embeddings in one launch: CTA b serves job j with tile0[j] <= b < tile0[j+1]
 struct FourierBatch {
