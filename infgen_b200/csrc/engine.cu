@@ -893,7 +893,8 @@ static int enqueue_iteration(infgen_engine *e, int trace_iter) {
     }
     {
         ProfScope ps(e, KC_HEADS);
-        k_heads<<<dim3((R + HM - 1) / HM, NSLICE + 1), NT_S, HEADS_SMEM, e->stream>>>(ha);
+        if (R > 512) k_heads<16><<<dim3((R + 15) / 16, NSLICE + 1), NT_S, heads_smem<16>(), e->stream>>>(ha);
+        else k_heads<HM><<<dim3((R + HM - 1) / HM, NSLICE + 1), NT_S, HEADS_SMEM, e->stream>>>(ha);
     }
     CKL(); count_launch(e);
     {
@@ -1106,7 +1107,8 @@ int32_t infgen_create(const infgen_config *cfg, const float *weights, int64_t n_
     }
     CK(cudaFuncSetAttribute(k_mlp_embed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mlp_embed_smem(128)));
     CK(cudaFuncSetAttribute(k_embed_column, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COLEMB_SMEM));
-    CK(cudaFuncSetAttribute(k_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEADS_SMEM));
+    CK(cudaFuncSetAttribute(k_heads<HM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEADS_SMEM));
+    CK(cudaFuncSetAttribute(k_heads<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heads_smem<16>()));
     CK(cudaFuncSetAttribute(k_mlp_layer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_LAYER_SMEM));
     RET(build_tables(e));
     if (!cfg->disable_insertion) RET(build_seed_feature(e));

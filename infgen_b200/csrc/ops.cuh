@@ -322,20 +322,25 @@ struct HeadArgs {
     float *trace_logits;       // optional [R][2048]
     float *trace_state;        // optional [R][3]
 };
-constexpr size_t HEADS_SMEM = (size_t)(WS_SMEM_FLOATS + 2 * HM * HLD + HM * 256) * sizeof(float);
+// HT rows per CTA: 8 for a single scene (latency), 16 for batches (the weight stream and its LSU cost per stage are
+// amortised over twice the rows)
+template <int HT>
+constexpr size_t heads_smem() { return (size_t)(WS_SMEM_FLOATS + 2 * HT * HLD + HT * 256) * sizeof(float); }
+constexpr size_t HEADS_SMEM = heads_smem<HM>();
 
+template <int HT>
 __global__ void __launch_bounds__(NT_S) k_heads(const HeadArgs a) {
     extern __shared__ __align__(16) float smem[];
     WsSmem wsm(smem);
-    float *sx = smem + WS_SMEM_FLOATS;       // [HM][HLD]
-    float *sh = sx + HM * HLD;               // [HM][HLD]
-    float *slog = sh + HM * HLD;             // [HM][256]
+    float *sx = smem + WS_SMEM_FLOATS;       // [HT][HLD]
+    float *sh = sx + HT * HLD;               // [HT][HLD]
+    float *slog = sh + HT * HLD;             // [HT][256]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int row0 = blockIdx.x * HM, slice = blockIdx.y;
+    const int row0 = blockIdx.x * HT, slice = blockIdx.y;
     const bool is_state = slice == NSLICE;
     const MlpHeadW &hw = is_state ? a.st : a.tok;
     bool any = false;
-    for (int m = 0; m < HM; ++m) any |= a.rows.active(row0 + m);
+    for (int m = 0; m < HT; ++m) any |= a.rows.active(row0 + m);
     if (!any) return;
     ws_init(wsm);
     if (warp == NWARP) {
@@ -354,7 +359,7 @@ __global__ void __launch_bounds__(NT_S) k_heads(const HeadArgs a) {
         return;
     }
     WsCons ws(wsm);
-    for (int m = warp; m < HM; m += NWARP) {
+    for (int m = warp; m < HT; m += NWARP) {
         const int r = row0 + m;
         float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
         if (a.rows.active(r)) {
@@ -364,12 +369,12 @@ __global__ void __launch_bounds__(NT_S) k_heads(const HeadArgs a) {
         st4(sx + m * HLD + 4 * lane, x);
     }
     csync();
-    tile_gemm<HM>(ws, sx, HLD, 32, [&](int m, int n, float v) { sh[m * HLD + n] = v + __ldg(hw.b0 + n); });
+    tile_gemm<HT>(ws, sx, HLD, 32, [&](int m, int n, float v) { sh[m * HLD + n] = v + __ldg(hw.b0 + n); });
     csync();
-    rows_layernorm_c<HM, true>(sh, HLD, hw.ln_g, hw.ln_b);
+    rows_layernorm_c<HT, true>(sh, HLD, hw.ln_g, hw.ln_b);
     csync();
     if (is_state) {                          // agent_decoder.py:2166
-        tile_gemm<HM>(ws, sh, HLD, 32, [&](int m, int n, float v) {
+        tile_gemm<HT>(ws, sh, HLD, 32, [&](int m, int n, float v) {
             const int r = row0 + m;
             if (n < hw.n_out && a.rows.active(r)) {
                 v += __ldg(hw.b3 + n);
@@ -380,7 +385,7 @@ __global__ void __launch_bounds__(NT_S) k_heads(const HeadArgs a) {
         return;
     }
     for (int half = 0; half < 2; ++half) {
-        tile_gemm<HM>(ws, sh, HLD, 32, [&](int m, int n, float v) {
+        tile_gemm<HT>(ws, sh, HLD, 32, [&](int m, int n, float v) {
             const int col = half * 128 + n;
             v += __ldg(hw.b3 + slice * 256 + col);
             slog[m * 256 + col] = v;
@@ -390,7 +395,7 @@ __global__ void __launch_bounds__(NT_S) k_heads(const HeadArgs a) {
     }
     csync();
     // per-row top-KTOP of the slice: one warp per row, 8 values per lane
-    for (int m = warp; m < HM; m += NWARP) {
+    for (int m = warp; m < HT; m += NWARP) {
         const int r = row0 + m;
         if (!a.rows.active(r)) continue;
         float v[8];
