@@ -366,7 +366,10 @@ def run_ours(args, rank, world, local_rank):
         if top:
             roof = {'kernel': top['kernel'], 'bound': top['bound'], 'achieved': top['achieved'], 'peak': top['peak'],
                     'unit': top['unit'], 'frac': top['frac'], 'traffic': traffic, 'peak_source': pk['source'],
-                    'share_of_step': top['share'], 'avg_launch_us': top['avg_us']}
+                    'share_of_step': top['share'], 'avg_launch_us': top['avg_us'],
+                    'note': ('one 64-agent scene is latency-bound (108 dependent exchange phases per launch on 64 SMs, '
+                             'DESIGN.md section 8); the bandwidth-bound form of the same attention is k_attn in '
+                             'batch32.roofline_kernels') if top['kernel'].startswith('k_layer') else None}
 
     # ---- optional side measurement: 32 scenes per step (configs[2] shape) -----------------------------------------
     extra = None

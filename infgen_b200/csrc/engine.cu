@@ -860,7 +860,7 @@ static int enqueue_edges(infgen_engine *e, int col_add) {
     if (e->fourier_tc && (R * e->cap + ftc::TM - 1) / ftc::TM > 148) {
         // batches: walk a compact list of the valid agent<->agent slots (a single scene's tiles fit one wave anyway)
         int *list = (int *)e->bufs["a_slots"].p, *n_list = list + (size_t)R * e->cap;
-        k_slot_compact<<<1, 1024, 0, e->stream>>>(s.a_cnt, R, e->cap, list, n_list);
+        k_slot_compact<<<1, 1024, 0, e->stream>>>(s.a_cnt, R, e->cap, list, n_list, n_list + 4);
         CKL(); count_launch(e);
         fj[0].slot_list = list; fj[0].n_list = n_list;
     }
@@ -1270,7 +1270,7 @@ int32_t infgen_load_scenes(infgen_engine *e, const infgen_scene_batch *b, int32_
     RET(ensure_t(e, "kv_m", (size_t)6 * std::max(P, 1) * 256, &tmp));
     RET(ensure_t(e, "rhat_t", (size_t)R * W * 128, &tmp)); RET(ensure_t(e, "rhat_m", (size_t)R * MM * 128, &tmp));
     RET(ensure_t(e, "rhat_a", (size_t)R * cap * 128, &tmp));
-    { int *itmp; RET(ensure_t(e, "a_slots", (size_t)R * cap + 4, &itmp)); }
+    { int *itmp; RET(ensure_t(e, "a_slots", (size_t)R * cap + 4 + R, &itmp)); }   // slot list, count, row offsets
     RET(ensure_t(e, "cat_tab", (size_t)(R + 1) * 128, &tmp)); RET(ensure_t(e, "shape_rows", (size_t)(R + 1) * 4, &tmp));
     RET(ensure_t(e, "hist_traj", (size_t)R * HC * 5 * 2, &tmp)); RET(ensure_t(e, "hist_head", (size_t)R * HC * 5, &tmp));
     if (getenv("INFGEN_TSTAMP")) { long long *ts; RET(ensure_t(e, "tstamp", 512, &ts)); }

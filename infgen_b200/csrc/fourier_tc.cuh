@@ -189,13 +189,13 @@ __device__ long long g_ftc_trace[2][3][64];
 // scan over the rows.  list[off(row) + k] = row * stride + k, *n_list = total.  Batches only: a2a rows hold ~40 valid of 64
 // slots, so the strided walk spends a third of the 128-slot tiles on padding.
 __global__ void __launch_bounds__(1024) k_slot_compact(const int *__restrict__ cnt, int n_rows, int stride, int *__restrict__ list,
-                                                        int *__restrict__ n_list) {
+                                                        int *__restrict__ n_list, int *__restrict__ row_off) {
     __shared__ int s_warp[32];
     __shared__ int s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_base = 0;
     __syncthreads();
-    for (int r0 = 0; r0 < n_rows; r0 += 1024) {
+    for (int r0 = 0; r0 < n_rows; r0 += 1024) {             // exclusive scan of the row counts -> row_off
         const int r = r0 + tid;
         const int c = r < n_rows ? min(cnt[r], stride) : 0;
         int x = c;                                           // inclusive scan inside the warp
@@ -216,13 +216,17 @@ __global__ void __launch_bounds__(1024) k_slot_compact(const int *__restrict__ c
             s_warp[lane] = w;                                // inclusive prefix of the warp totals
         }
         __syncthreads();
-        const int off = s_base + (warp ? s_warp[warp - 1] : 0) + x - c;
-        for (int k = 0; k < c; ++k) list[off + k] = r * stride + k;
+        if (r < n_rows) row_off[r] = s_base + (warp ? s_warp[warp - 1] : 0) + x - c;
         __syncthreads();
         if (tid == 0) s_base += s_warp[31];
         __syncthreads();
     }
     if (tid == 0) *n_list = s_base;
+    // one warp per row writes its slots (a serial loop per thread cost 32 us at 2,048 rows)
+    for (int r = warp; r < n_rows; r += 32) {
+        const int c = min(cnt[r], stride), off = row_off[r];
+        for (int k = lane; k < c; k += 32) list[off + k] = r * stride + k;
+    }
 }
 
 // weight image builder: 4 chunks of one packed [32 k4][128][4] matrix -> [hi | lo] chunks.  fourier_order: the K order of
