@@ -166,6 +166,8 @@ struct infgen_engine {
     InsState ins;
     bool ins_ready = false;
     FourierW f_t, f_m, f_a, f_x;
+    FourierW f_t3;                                      // r_t_emb restricted to its first three input dims (tensor-core path)
+    float *t_dim_table = nullptr;                       // [window][128] per-dim MLP output of the 4th temporal input (-1 .. -window)
     MlpEmbW e_shape, e_fusion, e_tok[3], e_grid;
     MlpHeadW h_tok, h_state;
     const float *type_emb = nullptr, *state_emb = nullptr;
@@ -866,6 +868,10 @@ static int enqueue_edges(infgen_engine *e, int col_add) {
     }
     fj[1].normalize = 1; fj[1].dim = 4;
     fj[1].n_slots = R * s.W; fj[1].cnt = s.t_cnt; fj[1].stride = s.W; fj[1].raw = s.t_raw; fj[1].w = e->f_t;
+    if (e->fourier_tc && s.W <= 16 && !getenv("INFGEN_NO_DIM_TABLE")) {
+        // three input dims through the tensor core, the column offset from the table
+        fj[1].dim = 3; fj[1].raw_stride = 4; fj[1].w = e->f_t3; fj[1].dim_table = e->t_dim_table; fj[1].table_n = 16;
+    }
     fj[1].out = fbuf(e, "rhat_t");
     fj[2].normalize = 1; fj[2].dim = 3;
     fj[2].n_slots = R * s.max_m; fj[2].cnt = s.m_cnt; fj[2].stride = s.max_m; fj[2].raw = s.m_raw; fj[2].w = e->f_m;
@@ -1063,6 +1069,11 @@ int32_t infgen_create(const infgen_config *cfg, const float *weights, int64_t n_
     }
     e->f_t = make_fourier(e, "r_t_emb", 4); e->f_m = make_fourier(e, "r_pt2a_emb", 3);
     e->f_a = make_fourier(e, "r_a2a_emb", 3); e->f_x = make_fourier(e, "x_a_emb", 2);
+    // the 4th temporal input is the column offset -1 .. -12 (agent_decoder.py:607): its per-dim MLP is a 12-row table
+    e->f_t3 = make_fourier(e, "r_t_emb", 3);
+    CK(cudaMalloc(&e->t_dim_table, (size_t)16 * 128 * sizeof(float)));
+    k_fourier_dim_table<<<16, 128, 0, e->stream>>>(e->f_t, 3, e->t_dim_table);
+    CKL();
     e->e_shape = make_mlp_emb(e, "shape_emb"); e->e_fusion = make_mlp_emb(e, "fusion_emb");
     e->e_tok[0] = make_mlp_emb(e, "token_emb_veh"); e->e_tok[1] = make_mlp_emb(e, "token_emb_ped");
     e->e_tok[2] = make_mlp_emb(e, "token_emb_cyc"); e->e_grid = make_mlp_emb(e, "token_emb_grid");
@@ -1128,7 +1139,7 @@ int32_t infgen_destroy(infgen_engine *e) {
     cudaFree(e->blob); cudaFree(e->cs_blob); cudaFree(e->grid_cells); cudaFree(e->vocab); cudaFree(e->tok_tab); cudaFree(e->grid_tab);
     cudaFree(e->d_err); cudaFree(e->seed_feat);
     for (float *p : e->wimgs) cudaFree(p);
-    cudaFree(e->np_blob);
+    cudaFree(e->np_blob); cudaFree(e->t_dim_table);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->side_stream) cudaStreamDestroy(e->side_stream);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);

@@ -229,6 +229,40 @@ __global__ void __launch_bounds__(1024) k_slot_compact(const int *__restrict__ c
     }
 }
 
+// Per-dim MLP output of input dim d (layers.py:152-155: Linear(129,128) -> LN -> ReLU -> Linear(128,128)) for the inputs
+// x = -1, -2, .. (one block per value), plain fp32 FMA from the packed [K/4][128][4] weights.  Run once at infgen_create.
+__global__ void __launch_bounds__(128) k_fourier_dim_table(const FourierW w, int d, float *__restrict__ out) {
+    __shared__ float feat[132], hid[128], red[8];
+    const int n = threadIdx.x, lane = n & 31, warp = n >> 5;
+    const float x = -(float)(blockIdx.x + 1);
+    if (n < 64) {
+        const float arg = __fmul_rn(__fmul_rn(__fmul_rn(x, __ldg(w.freqs + d * 64 + n)), 2.0f), 3.14159265358979323846f);
+        float sn, cs;
+        sincosf(arg, &sn, &cs);
+        feat[n] = cs;
+        feat[64 + n] = sn;
+    }
+    if (n == 0) { feat[128] = x; feat[129] = 0.f; feat[130] = 0.f; feat[131] = 0.f; }
+    __syncthreads();
+    float y = __ldg(w.b0[d] + n);
+    for (int k = 0; k < 129; ++k) y = fmaf(feat[k], __ldg(w.w0[d] + ((size_t)(k >> 2) * 128 + n) * 4 + (k & 3)), y);
+    // LayerNorm over the 128 outputs (two passes, as torch)
+    float s = warp_sum(y);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    const float mean = (red[0] + red[1] + red[2] + red[3]) * (1.0f / HID);
+    const float c = y - mean;
+    float q = warp_sum(c * c);
+    if (lane == 0) red[4 + warp] = q;
+    __syncthreads();
+    const float rstd = 1.0f / sqrtf((red[4] + red[5] + red[6] + red[7]) * (1.0f / HID) + LN_EPS);
+    hid[n] = fmaxf(c * rstd * __ldg(w.ln_g[d] + n) + __ldg(w.ln_b[d] + n), 0.f);
+    __syncthreads();
+    float z = __ldg(w.b3[d] + n);
+    for (int k = 0; k < 128; ++k) z = fmaf(hid[k], __ldg(w.w3[d] + ((size_t)(k >> 2) * 128 + n) * 4 + (k & 3)), z);
+    out[(size_t)blockIdx.x * 128 + n] = z;
+}
+
 // weight image builder: 4 chunks of one packed [32 k4][128][4] matrix -> [hi | lo] chunks.  fourier_order: the K order of
 // G1 (chunk c = k4 rows 4c .. 4c+3 (cos of 16 freqs) then 16+4c .. 16+4c+3 (their sin)); else K in natural order
 __global__ void k_wimg_split(const float *__restrict__ src, float *__restrict__ dst, int fourier_order) {
@@ -282,7 +316,8 @@ __global__ void __launch_bounds__(ftc::THREADS, 1) k_fourier_tc(const FourierBat
         }
         s_valid[tid] = v;
         s_slot[tid] = s;
-        for (int d = 0; d < 4; ++d) sraw[tid * 4 + d] = (v && d < D) ? a.raw[(size_t)s * D + d] : 0.f;
+        const int rs = a.raw_stride ? a.raw_stride : D;
+        for (int d = 0; d < 4; ++d) sraw[tid * 4 + d] = (v && d < rs) ? a.raw[(size_t)s * rs + d] : 0.f;
     }
     if (!__syncthreads_or(v)) return;
 
@@ -498,6 +533,17 @@ __global__ void __launch_bounds__(ftc::THREADS, 1) k_fourier_tc(const FourierBat
             for (int i4 = 0; i4 < 8; ++i4) {
                 const float4 b4 = ldg4(a.w.b3[d] + 32 * qd + 4 * i4);
                 val[4 * i4 + 0] += b4.x; val[4 * i4 + 1] += b4.y; val[4 * i4 + 2] += b4.z; val[4 * i4 + 3] += b4.w;
+            }
+        }
+        if (a.dim_table) {
+            // input dim D takes only the values -1 .. -table_n (the column offset of a temporal edge, agent_decoder.py:607):
+            // its per-dim MLP output comes from a table built at infgen_create instead of two more GEMMs per tile
+            const int k = min(max((int)lrintf(-sraw[r * 4 + D]) - 1, 0), a.table_n - 1);
+            const float *tb = a.dim_table + (size_t)k * 128 + 32 * qd;
+#pragma unroll
+            for (int i4 = 0; i4 < 8; ++i4) {
+                const float4 t4 = ldg4(tb + 4 * i4);
+                val[4 * i4 + 0] += t4.x; val[4 * i4 + 1] += t4.y; val[4 * i4 + 2] += t4.z; val[4 * i4 + 3] += t4.w;
             }
         }
         norm_relu_put(val, a.w.out_ln_g, a.w.out_ln_b, ci);

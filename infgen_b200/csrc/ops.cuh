@@ -119,6 +119,9 @@ struct FourierArgs {
     int normalize;             // 1: store (y - mean) / std of the output (input of every layer's attn_prenorm_r)
     const int *slot_list;      // optional compact list of the valid slots (k_slot_compact); tiles walk it instead of
     const int *n_list;         //   the strided slot space: *n_list entries (k_fourier_tc only)
+    int raw_stride;            // floats per slot in `raw` (0: dim)
+    const float *dim_table;    // optional [table_n][128]: the per-dim MLP output of input dim `dim` (the one after the
+    int table_n;               //   last tensor-core dim) for the inputs -1, -2, .. -table_n (k_fourier_tc only)
 };
 // several embeddings in one launch: CTA b serves job j with tile0[j] <= b < tile0[j+1]
 struct FourierBatch {
