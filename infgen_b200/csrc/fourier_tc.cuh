@@ -84,13 +84,6 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {      // no swizz
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(2048u >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) |
            ((uint64_t)1 << 46);
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-        "l"(da), "l"(db), "r"(ftc::IDESC), "r"(accumulate)
-        : "memory");
-}
 // A from tensor memory (lane = row, one 32-bit column per k), B from shared memory.  Called by the WHOLE warp with
 // warp-uniform operands; one elected lane issues (keeps the issue loop in uniform control flow: no per-lane waterfall).
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t accumulate) {
@@ -116,9 +109,6 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float *v) {
         "f"(v[21]), "f"(v[22]), "f"(v[23]), "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]), "f"(v[28]), "f"(v[29]), "f"(v[30]),
         "f"(v[31])
         : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t *b) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(b)) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
