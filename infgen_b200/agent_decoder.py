@@ -89,14 +89,17 @@ class B200AgentDecoder:
 
     def load(self, batch: HostBatch, scenes: Optional[Sequence[SceneHost]] = None):
         b = batch
-        sb = _capi.SceneBatch(
-            n_scenes=b.n_scenes, row_capacity=b.cap, n_cols=b.T, n_iters=b.S,
-            n_rows=_capi.i32p(b.n_rows), ego_row=_capi.i32p(b.ego_row), scene_id=_capi.i32p(b.scene_id),
-            pos_hist=_capi.f32p(b.pos_hist), head_hist=_capi.f32p(b.head_hist), state_hist=_capi.i32p(b.state_hist),
-            token_hist=_capi.i32p(b.token_hist), grid_hist=_capi.i32p(b.grid_hist), tsrc_hist=_capi.u8p(b.tsrc_hist),
-            interact_hist=_capi.u8p(b.interact_hist), type=_capi.i32p(b.type), shape=_capi.f32p(b.shape),
-            pt_ptr=_capi.i32p(b.pt_ptr), pt_pos=_capi.f32p(b.pt_pos), pt_ori=_capi.f32p(b.pt_ori),
-            x_pt=_capi.f32p(b.x_pt))
+        # the staging buffers of a HostBatch keep their addresses: build the ctypes descriptor once per batch object
+        sb = getattr(b, '_capi_scene_batch', None)
+        if sb is None:
+            sb = b._capi_scene_batch = _capi.SceneBatch(
+                n_scenes=b.n_scenes, row_capacity=b.cap, n_cols=b.T, n_iters=b.S,
+                n_rows=_capi.i32p(b.n_rows), ego_row=_capi.i32p(b.ego_row), scene_id=_capi.i32p(b.scene_id),
+                pos_hist=_capi.f32p(b.pos_hist), head_hist=_capi.f32p(b.head_hist), state_hist=_capi.i32p(b.state_hist),
+                token_hist=_capi.i32p(b.token_hist), grid_hist=_capi.i32p(b.grid_hist), tsrc_hist=_capi.u8p(b.tsrc_hist),
+                interact_hist=_capi.u8p(b.interact_hist), type=_capi.i32p(b.type), shape=_capi.f32p(b.shape),
+                pt_ptr=_capi.i32p(b.pt_ptr), pt_pos=_capi.f32p(b.pt_pos), pt_ori=_capi.f32p(b.pt_ori),
+                x_pt=_capi.f32p(b.x_pt))
         loc = _capi.DEVICE if getattr(b, 'on_device', False) else _capi.HOST
         _capi.check(self.lib.infgen_load_scenes(self._h, C.byref(sb), loc))
         self._batch, self._scenes = batch, scenes
@@ -122,17 +125,19 @@ class B200AgentDecoder:
 
     def read(self):
         b = self._batch
-        o = _capi.Outputs(
-            pos=_capi.f32p(b.out_pos), head=_capi.f32p(b.out_head), pred_traj=_capi.f32p(b.out_pred_traj),
-            pred_head=_capi.f32p(b.out_pred_head), pred_state=_capi.f32p(b.out_pred_state),
-            next_token=_capi.i32p(b.out_next_token), next_state=_capi.i32p(b.out_next_state),
-            hist_traj=_capi.f32p(b.out_hist_traj), hist_head=_capi.f32p(b.out_hist_head),
-            n_rows_final=_capi.i32p(b.out_n_rows))
-        if b.insertion:
-            o.pred_type, o.pred_shape = _capi.i32p(b.out_pred_type), _capi.f32p(b.out_pred_shape)
-            o.state_prob_seed, o.pos_prob_seed = _capi.f32p(b.out_state_prob_seed), _capi.f32p(b.out_pos_prob_seed)
-            o.agent_occ_seed, o.pt_occ_seed = _capi.f32p(b.out_agent_occ_seed), _capi.f32p(b.out_pt_occ_seed)
-            o.occ_gt_seed = _capi.f32p(b.out_occ_gt_seed)
+        o = getattr(b, '_capi_outputs', None)
+        if o is None:
+            o = b._capi_outputs = _capi.Outputs(
+                pos=_capi.f32p(b.out_pos), head=_capi.f32p(b.out_head), pred_traj=_capi.f32p(b.out_pred_traj),
+                pred_head=_capi.f32p(b.out_pred_head), pred_state=_capi.f32p(b.out_pred_state),
+                next_token=_capi.i32p(b.out_next_token), next_state=_capi.i32p(b.out_next_state),
+                hist_traj=_capi.f32p(b.out_hist_traj), hist_head=_capi.f32p(b.out_hist_head),
+                n_rows_final=_capi.i32p(b.out_n_rows))
+            if b.insertion:
+                o.pred_type, o.pred_shape = _capi.i32p(b.out_pred_type), _capi.f32p(b.out_pred_shape)
+                o.state_prob_seed, o.pos_prob_seed = _capi.f32p(b.out_state_prob_seed), _capi.f32p(b.out_pos_prob_seed)
+                o.agent_occ_seed, o.pt_occ_seed = _capi.f32p(b.out_agent_occ_seed), _capi.f32p(b.out_pt_occ_seed)
+                o.occ_gt_seed = _capi.f32p(b.out_occ_gt_seed)
         loc = _capi.DEVICE if getattr(b, 'on_device', False) else _capi.HOST
         _capi.check(self.lib.infgen_read(self._h, C.byref(o), loc))
 
