@@ -1575,7 +1575,11 @@ struct TmpDev {
     template <typename Tp> Tp *alloc(size_t n) {
         void *p = nullptr;
         if (cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(Tp)) != cudaSuccess) return nullptr;
+        // the memset runs on the legacy default stream, asynchronously to the host, and the engine stream is non-blocking:
+        // without the synchronisation it can land AFTER the kernels of the operator call have written the buffer (found as an
+        // order-dependent failure of test_attention_layer: zeroed K/V rows)
         cudaMemset(p, 0, std::max<size_t>(n, 1) * sizeof(Tp));
+        cudaStreamSynchronize(cudaStreamLegacy);
         ptrs.push_back(p);
         return (Tp *)p;
     }
