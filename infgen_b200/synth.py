@@ -204,3 +204,25 @@ def expand_token_traj_all(scene: Dict) -> torch.Tensor:
     ag = scene['agent']
     tables = torch.stack([ag['trajectory_token_veh'], ag['trajectory_token_ped'], ag['trajectory_token_cyc']])
     return tables[ag['type'].long()].contiguous()
+
+
+def make_map_tokens(scene, seed: int = 0, n_polygons: int = 64):
+    """Synthetic categorical fields of the map tokens of `scene` (schema of `TokenProcessor._tokenize_map`,
+    reference preprocess.py:693-761, consumed by `InfGenMapDecoder.forward`, map_decoder.py:70-90): token type (17
+    classes), polygon type (4), vocabulary index (1024), the owning polygon and its light type (4), prediction masks.
+    numpy PCG64, so the values are bit-identical in every container."""
+    import numpy as np
+    rng = np.random.default_rng(10_000 + seed)
+    P = int(scene['pt_token']['position'].shape[0])
+    poly = np.sort(rng.integers(0, n_polygons, size=P))
+    pred = rng.random(P) < 0.3
+    return {
+        'position': scene['pt_token']['position'], 'orientation': scene['pt_token']['orientation'],
+        'type': torch.from_numpy(rng.integers(0, 17, size=P).astype(np.uint8)),
+        'pl_type': torch.from_numpy(rng.integers(0, 4, size=P).astype(np.uint8)),
+        'token_idx': torch.from_numpy(rng.integers(0, 1024, size=P).astype(np.int64)),
+        'polygon': torch.from_numpy(poly.astype(np.int64)),
+        'polygon_light_type': torch.from_numpy(rng.integers(0, 4, size=n_polygons).astype(np.uint8)),
+        'pt_pred_mask': torch.from_numpy(pred), 'pt_valid_mask': torch.ones(P, dtype=torch.bool),
+        'pt_target_mask': torch.from_numpy(pred.copy()),
+    }

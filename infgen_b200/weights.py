@@ -120,6 +120,53 @@ def agent_decoder_spec() -> "OrderedDict[str, Tuple[Tuple[int, ...], str]]":
     return s
 
 
+def map_decoder_spec() -> "OrderedDict[str, Tuple[Tuple[int, ...], str]]":
+    """Every key of `InfGenMapDecoder.state_dict()` (map_decoder.py:46-64; ours_standard.yaml: input_dim 2, 3 layers), in
+    module order.  SURVEY.md section 8f row f1: the next row after the decode path."""
+    s = OrderedDict()
+    s['type_pt_emb.weight'] = ((17, HIDDEN), 'emb')
+    s['side_pt_emb.weight'] = ((4, HIDDEN), 'emb')
+    s['polygon_type_emb.weight'] = ((4, HIDDEN), 'emb')
+    s['light_pl_emb.weight'] = ((4, HIDDEN), 'emb')
+    _fourier(s, 'r_pt2pt_emb', 3)
+    for i in range(3):
+        _attention_layer(s, f'pt2pt_layers.{i}', has_pos_emb=True)
+    _mlp_layer(s, 'token_predict_head', HIDDEN, 1024)
+    _mlp_embedding(s, 'token_emb', 22)
+    return s
+
+
+def _fill(spec, seed: int, perturb: bool) -> Dict[str, torch.Tensor]:
+    rng = np.random.default_rng(seed)
+    sd = OrderedDict()
+    for name, (shape, kind) in spec.items():
+        if kind == 'linear_w':
+            fan_out, fan_in = shape
+            bound = float(np.sqrt(6.0 / (fan_in + fan_out)))
+            a = rng.uniform(-bound, bound, size=shape)
+        elif kind == 'emb':
+            a = rng.normal(0.0, 0.02, size=shape)
+        elif kind == 'bias':
+            a = rng.normal(0.0, 0.05, size=shape) if perturb else np.zeros(shape)
+        elif kind == 'ln_w':
+            a = 1.0 + rng.normal(0.0, 0.1, size=shape) if perturb else np.ones(shape)
+        elif kind == 'ln_b':
+            a = rng.normal(0.0, 0.05, size=shape) if perturb else np.zeros(shape)
+        else:
+            raise ValueError(kind)
+        sd[name] = torch.from_numpy(np.asarray(a, dtype=np.float32))
+    return sd
+
+
+def make_map_state_dict(seed: int = 0, perturb: bool = True) -> Dict[str, torch.Tensor]:
+    """Seed-fixed synthetic `InfGenMapDecoder` weights (same distributions as `make_state_dict`)."""
+    sd = _fill(map_decoder_spec(), seed, perturb)
+    for i in range(3):                     # pt2pt layers are not bipartite: the dst norm aliases the src norm
+        for leaf in ('weight', 'bias'):
+            sd[f'pt2pt_layers.{i}.attn_prenorm_x_dst.{leaf}'] = sd[f'pt2pt_layers.{i}.attn_prenorm_x_src.{leaf}'].clone()
+    return sd
+
+
 def make_state_dict(seed: int = 0, perturb: bool = True) -> Dict[str, torch.Tensor]:
     """Seed-fixed synthetic weights with the reference's names/shapes (there are no checkpoints offline).
 
