@@ -1,7 +1,7 @@
 """Golden vectors of the reference MAP ENCODER (`InfGenMapDecoder.forward`, map_decoder.py:70-130), written by running the
 UNMODIFIED reference on CPU through oracle/shims (build container only):
 
-    python tests/golden/make_golden_map.py        # writes tests/golden/case_map_p384.npz
+    python tests/golden/make_golden_map.py        # writes tests/golden/case_map_*.npz
 
 Inputs are regenerated from seeds (`infgen_b200.synth.make_scene` / `make_map_tokens`, `weights.make_map_state_dict`), so only
 outputs are stored: x_pt [P,128], the token-head logits of the predicted tokens and the pt2pt edge list.
@@ -19,15 +19,23 @@ from infgen_b200.config import DecoderConfig                             # noqa:
 from infgen_b200.synth import make_scene, make_map_tokens               # noqa: E402
 from infgen_b200.weights import make_map_state_dict                     # noqa: E402
 
-MAP_CASE = {'scene_seed': 41, 'num_map_tokens': 384, 'weights_seed': 7, 'tokens_seed': 3}
+MAP_CASES = {
+    # sparse lanes: ~3 neighbours per token inside the 10 m radius
+    'map_p384': {'scene_seed': 41, 'num_map_tokens': 384, 'weights_seed': 7, 'tokens_seed': 3, 'shrink': 1.0},
+    # the same tokens pulled towards the origin (positions x 0.08): most tokens have more than 100 candidates, so the
+    # max_num_neighbors truncation and its self-loop quirk decide the graph
+    'map_dense_p384': {'scene_seed': 41, 'num_map_tokens': 384, 'weights_seed': 8, 'tokens_seed': 4, 'shrink': 0.08},
+}
 
 
-def build_map_case():
+def build_map_case(name='map_p384'):
+    c = MAP_CASES[name]
     cfg = DecoderConfig()
-    scene = make_scene(MAP_CASE['scene_seed'], num_agents=8, num_map_tokens=MAP_CASE['num_map_tokens'], num_steps=91,
+    scene = make_scene(c['scene_seed'], num_agents=8, num_map_tokens=c['num_map_tokens'], num_steps=91,
                        ragged=0.0, ego_index=0, cfg=cfg)
-    pt = make_map_tokens(scene, MAP_CASE['tokens_seed'])
-    sd = make_map_state_dict(MAP_CASE['weights_seed'])
+    pt = make_map_tokens(scene, c['tokens_seed'])
+    pt['position'] = (pt['position'] * c['shrink']).contiguous()
+    sd = make_map_state_dict(c['weights_seed'])
     traj = torch.from_numpy(np.load(os.path.join(ROOT, 'infgen_b200', 'tokens', 'map_traj_token5.npz'))['traj_src'])
     return pt, sd, traj
 
@@ -62,12 +70,15 @@ def run_reference_map(pt, sd, traj):
 
 def main():
     torch.manual_seed(0)
-    pt, sd, traj = build_map_case()
-    out, ei = run_reference_map(pt, sd, traj)
-    path = os.path.join(os.path.dirname(__file__), 'case_map_p384.npz')
-    np.savez_compressed(path, x_pt=out['x_pt'].numpy(), map_next_token_prob=out['map_next_token_prob'].numpy(),
-                        map_next_token_idx=out['map_next_token_idx'].numpy(), edge_src=ei[0].numpy(), edge_dst=ei[1].numpy())
-    print('wrote', path, {k: tuple(v.shape) for k, v in out.items() if isinstance(v, torch.Tensor)}, 'edges', ei.shape[1])
+    for name in (sys.argv[1:] or list(MAP_CASES)):
+        pt, sd, traj = build_map_case(name)
+        out, ei = run_reference_map(pt, sd, traj)
+        path = os.path.join(os.path.dirname(__file__), f'case_{name}.npz')
+        np.savez_compressed(path, x_pt=out['x_pt'].numpy(), map_next_token_prob=out['map_next_token_prob'].numpy(),
+                            map_next_token_idx=out['map_next_token_idx'].numpy(), edge_src=ei[0].numpy(),
+                            edge_dst=ei[1].numpy())
+        print('wrote', path, {k: tuple(v.shape) for k, v in out.items() if isinstance(v, torch.Tensor)}, 'edges',
+              ei.shape[1])
 
 
 if __name__ == '__main__':

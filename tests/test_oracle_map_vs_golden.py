@@ -3,17 +3,19 @@ vectors written by the UNMODIFIED reference `InfGenMapDecoder.forward` (tests/go
 This pins the oracle of the NEXT row; the CUDA path for it is not built yet."""
 import os
 import numpy as np
+import pytest
 import torch
 
-from tests.golden.make_golden_map import build_map_case
+from tests.golden.make_golden_map import build_map_case, MAP_CASES
 
-GOLD = os.path.join(os.path.dirname(__file__), 'golden', 'case_map_p384.npz')
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
 
 
-def test_map_encoder_oracle_matches_reference_golden():
+@pytest.mark.parametrize('name', list(MAP_CASES))
+def test_map_encoder_oracle_matches_reference_golden(name):
     from oracle.map_decoder_oracle import map_encode
-    pt, sd, traj = build_map_case()
-    z = np.load(GOLD)
+    pt, sd, traj = build_map_case(name)
+    z = np.load(os.path.join(GOLD, f'case_{name}.npz'))
     pt = dict(pt)
     pt['light_type'] = pt['polygon_light_type'][pt['polygon']]           # map_decoder.py:85-86
     with torch.no_grad():
