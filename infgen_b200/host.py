@@ -261,6 +261,27 @@ class DeviceBatch:
         self.on_device = True
 
 
+_ZERO_SEED_CACHE: Dict[int, Dict[str, torch.Tensor]] = {}
+
+
+def _zero_seed_records(n_iters: int) -> Dict[str, torch.Tensor]:
+    """The five insertion-stage outputs of a rollout whose insertion stage is disabled: zeros of the reference shapes
+    [11, S] / [11, S, grid].  Allocated once per horizon and shared between calls (5.5 MB of zeros per 16-iteration
+    scene would otherwise be written on every call); consumers only read them (infgen.py:742-777)."""
+    rec = _ZERO_SEED_CACHE.get(n_iters)
+    if rec is None:
+        from .weights import GRID_SIZE
+        S = max(n_iters, 0)
+        rec = _ZERO_SEED_CACHE[n_iters] = {
+            'next_state_prob_seed': torch.zeros(11, S),
+            'next_pos_rel_prob_seed': torch.zeros(11, S, GRID_SIZE),
+            'grid_agent_occ_seed': torch.zeros(11, S, GRID_SIZE),
+            'grid_pt_occ_seed': torch.zeros(11, S, GRID_SIZE),
+            'grid_agent_occ_gt_seed': torch.zeros(11, S, GRID_SIZE),
+        }
+    return dict(rec)
+
+
 def assemble_outputs(batch: HostBatch, scenes: Sequence[SceneHost], cfg: DecoderConfig) -> List[Dict]:
     """agent_decoder.py:2303-2389: the per-scene output dict (keys/dtypes/shapes of the reference).  Rows appended by the
     insertion stage follow the scene's own rows; history-derived fields cover the scene's own rows only, as in the
@@ -322,5 +343,9 @@ def assemble_outputs(batch: HostBatch, scenes: Sequence[SceneHost], cfg: Decoder
                 'grid_pt_occ_seed': batch.out_pt_occ_seed[b, :, :s.n_iters].clone(),
                 'grid_agent_occ_gt_seed': batch.out_occ_gt_seed[b, :, :s.n_iters].clone(),
             })
+        else:
+            # the reference appends zero [11,1(,G)] records every iteration whether or not the stage runs
+            # (agent_decoder.py:2099-2113) and `validation_step` indexes them unconditionally (infgen.py:742-777)
+            out.update(_zero_seed_records(s.n_iters))
         outs.append(out)
     return outs

@@ -38,11 +38,10 @@ def _check(cfg, scene, want):
     hb.out_next_state[:n, :ncol] = want['next_state_idx'].to(torch.int32)
     hb.out_n_rows[0] = n
     got = assemble_outputs(hb, [sh], cfg)[0]
-    # the five insertion-stage outputs exist only when the insertion stage runs (motion-only engines: disable_insertion)
-    seed_keys = {'next_state_prob_seed', 'next_pos_rel_prob_seed', 'grid_agent_occ_seed', 'grid_pt_occ_seed',
-                 'grid_agent_occ_gt_seed'}
-    tensor_keys = [k for k, v in want.items() if isinstance(v, torch.Tensor) and k not in seed_keys]
+    tensor_keys = [k for k, v in want.items() if isinstance(v, torch.Tensor)]
     assert set(tensor_keys) <= set(got), sorted(set(tensor_keys) - set(got))
+    # the oracle leaves out the two non-tensor log fields of the reference dict (agent_decoder.py:2387-2388)
+    assert set(got) - {'agent_labels', 'log_message'} == set(want), sorted(set(got) ^ set(want))
     for k in tensor_keys:
         g, w = got[k], want[k]
         assert tuple(g.shape) == tuple(w.shape), (k, g.shape, w.shape)
