@@ -108,9 +108,25 @@ def load() -> C.CDLL:
     return _lib
 
 
+ERR_CAPACITY = -2
+
+
+class InfgenError(RuntimeError):
+    """A call into libinfgen_b200.so returned a negative `infgen_status` (`code`)."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f'infgen_b200 error {code}: {message}')
+        self.code = code
+
+
+class CapacityError(InfgenError):
+    """INFGEN_ERR_CAPACITY: the batch does not fit the row space it was loaded with."""
+
+
 def check(rc: int) -> None:
     if rc != 0:
-        raise RuntimeError(f'infgen_b200 error {rc}: {load().infgen_last_error().decode()}')
+        msg = load().infgen_last_error().decode()
+        raise (CapacityError if rc == ERR_CAPACITY else InfgenError)(rc, msg)
 
 
 def f32p(t):

@@ -195,9 +195,21 @@ class B200AgentDecoder:
             batch.fill(scenes, scene_ids)              # reuse the pinned staging buffers
         else:
             batch = self._host_cache = HostBatch(scenes, self.cfg, scene_ids)
-        self.load(batch, scenes)
-        self.rollout()
-        self.read()
+        while True:
+            try:
+                self.load(batch, scenes)
+                self.rollout()
+                self.read()
+                break
+            except _capi.CapacityError:
+                # The insertion stage appended more rows than the row space holds.  The reference grows its tensors
+                # without bound (torch.cat per inserted agent, agent_decoder.py:1923-1995); here the rollout is rerun
+                # from the start in a row space twice as large - it is deterministic (counter-based sampler), so this
+                # is the rollout the reference-sized row space would have produced.  most + 10 S rows always suffice.
+                if not batch.insertion or batch.cap >= batch.max_rows:
+                    raise
+                new_cap = min(max(2 * batch.cap, batch.cap + 64), (batch.max_rows + 3) // 4 * 4)
+                batch = self._host_cache = HostBatch(scenes, self.cfg, scene_ids, row_capacity=new_cap)
         return assemble_outputs(batch, scenes, self.cfg)
 
     def inference(self, data: Dict, map_enc: Dict, motion_only: bool = False) -> Dict:

@@ -199,7 +199,11 @@ __device__ __forceinline__ float wrap_angle(float a) {
 // infgen/utils/func.py:30-34 angle_between_2d_vectors(ctr, nbr)
 __device__ __forceinline__ float angle_between(float cx, float cy, float nx, float ny) {
     float cross = __fsub_rn(__fmul_rn(cx, ny), __fmul_rn(cy, nx));
-    float dot = __fadd_rn(__fmul_rn(cx, nx), __fmul_rn(cy, ny));
+    // the reference takes the dot product as `(ctr * nbr).sum(-1)`, a reduction that starts from +0: for a zero
+    // neighbour vector (the ego -> seed edge of every insertion pass: the query row sits on the ego, agent_decoder.py:
+    // 1796-1797) and a heading in the third quadrant both products are -0 and the sum is +0, not -0 - and
+    // atan2(+0, -0) would be pi instead of 0
+    float dot = __fadd_rn(__fadd_rn(0.0f, __fmul_rn(cx, nx)), __fmul_rn(cy, ny));
     return atan2f(cross, dot);
 }
 __device__ __forceinline__ float norm2(float x, float y) {

@@ -7,7 +7,6 @@
 namespace infgen {
 
 constexpr int ST_INVALID = 0, ST_VALID = 1, ST_ENTER = 2, ST_EXIT = 3;
-constexpr int MAX_CAP = 256;       // rows per scene supported by k_edge_build's shared bitmaps
 constexpr int RING = 16;           // temporal K/V ring depth (>= window + 1, power of two)
 
 struct DecState {
@@ -15,6 +14,8 @@ struct DecState {
     int q_rows;                    // num_seed_feature: tail rows without temporal edges (agent_decoder.py:553-556)
     int G, V;                      // grid cells, motion-token vocabulary
     int max_m;                     // max_pl2a_neighbors
+    int max_a;                     // max_a2a_neighbors (agent_decoder.py:633)
+    int a_stride;                  // agent<->agent slots per row: min(cap, max_a + 1)
     float r_m2, r_a2;              // squared radii
     int use_state_token, disable_insertion, beam;
     unsigned seed;
@@ -35,7 +36,7 @@ struct DecState {
     // edges
     int *t_cnt, *t_src; float *t_raw;                    // [R], [R*W], [R*W][4]
     int *m_cnt, *m_src; float *m_raw;                    // [R], [R*max_m], [R*max_m][3]
-    int *a_cnt, *a_start, *a_total, *a_src; float *a_raw; // [R], [R], [n_scenes], [n_scenes*cap*cap], [..][3]
+    int *a_cnt, *a_start, *a_total, *a_src; float *a_raw; // [R], [R], [n_scenes], [R*a_stride], [..][3]
     // next-column embedding inputs
     float *xa_raw;                 // [R][2]
     int *tok_row, *state_idx, *grid_row, *cat_idx;       // [R]
@@ -52,7 +53,7 @@ __device__ __forceinline__ unsigned lanemask_lt() { return (1u << (threadIdx.x &
 // edges whose destination is column `cur` (agent_decoder.py:540-610, 612-681, 683-758 with the inference masks of
 // :2119-2121).  One warp per (row, edge type).  Semantics of the third-party calls (oracle/shims): radius = strict `<`,
 // the first max_num_neighbors sources by ascending index; edges ordered by destination then source.
-// Slots: temporal r*W + k, map r*max_m + k, agent r*cap + k (k-th neighbour by ascending source row).
+// Slots: temporal r*W + k, map r*max_m + k, agent r*a_stride + k (k-th neighbour by ascending source row).
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT) k_edge_build(const DecState s, int col_add) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -124,23 +125,29 @@ __global__ void __launch_bounds__(NT) k_edge_build(const DecState s, int col_add
         }
         if (lane == 0) s.m_cnt[r] = cnt;
     } else {
-        // ---- agent <-> agent: every interacting row of the scene within the radius, ascending row order ---------
-        int cnt = 0;
-        const int base = r * s.cap;
+        // ---- agent <-> agent (:632-634): radius_graph over ALL rows of the scene = the first max_a + 1 rows within the
+        //      radius by ascending index, the row itself included, then minus the self loop (torch_cluster.radius_graph
+        //      queries max_num_neighbors + 1 and drops loops afterwards); `subgraph` then keeps the edges whose two ends
+        //      interact at this column.  Rows that do not interact therefore still count towards the limit.
+        int cnt = 0, seen = 0;
+        const int base = r * s.a_stride;
         if (inter) {
-            for (int j0 = 0; j0 < n; j0 += 32) {
+            for (int j0 = 0; j0 < n && seen <= s.max_a; j0 += 32) {
                 const int j = j0 + lane;
                 const int rj = r0 + j;
-                bool ok = false;
+                bool within = false;
                 float rx = 0.f, ry = 0.f;
-                if (j < n && j != i && s.interact[(size_t)rj * T + col]) {
+                if (j < n) {
                     rx = __fsub_rn(s.pos[((size_t)rj * T + col) * 2], px);
                     ry = __fsub_rn(s.pos[((size_t)rj * T + col) * 2 + 1], py);
                     // radius_graph tests |p_i - p_j|^2 < r^2 with the difference taken as (dst - src)
                     const float dx = __fsub_rn(px, s.pos[((size_t)rj * T + col) * 2]);
                     const float dy = __fsub_rn(py, s.pos[((size_t)rj * T + col) * 2 + 1]);
-                    ok = dist2(dx, dy) < s.r_a2;
+                    within = dist2(dx, dy) < s.r_a2;
                 }
+                const unsigned wm = __ballot_sync(0xffffffffu, within);
+                const bool in_first = within && (seen + __popc(wm & lanemask_lt())) <= s.max_a;
+                const bool ok = in_first && j != i && s.interact[(size_t)rj * T + col] != 0;
                 const unsigned mask = __ballot_sync(0xffffffffu, ok);
                 if (ok) {
                     const int slot = base + cnt + __popc(mask & lanemask_lt());
@@ -155,6 +162,7 @@ __global__ void __launch_bounds__(NT) k_edge_build(const DecState s, int col_add
                     s.a_raw[(size_t)slot * 3 + 2] = rh;
                 }
                 cnt += __popc(mask);
+                seen += __popc(wm);
             }
         }
         if (lane == 0) { s.a_cnt[r] = cnt; s.a_start[r] = base; }

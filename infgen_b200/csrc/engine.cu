@@ -104,6 +104,9 @@ static void w_head(const std::string &p, int kin, int nout) {
     w_add(p + ".w3", gemm_numel(128, pad128(nout))); w_add(p + ".b3", pad128(nout));
 }
 static const int GRID_SIZE = 1961, ANGLE_SIZE = 120, TOKEN_SIZE = 2048;
+// rows per scene: the scene's own agents plus everything the insertion stage may append (the reference never compacts:
+// up to 10 rows per iteration, agent_decoder.py:1738, i.e. 3,000 over a 150 s rollout)
+static const int MAX_ROW_CAPACITY = 8192;
 static void build_layout() {
     if (!g_layout.empty()) return;
     w_add("type_a_emb", 4 * 128); w_add("state_a_emb", 4 * 128);
@@ -182,11 +185,13 @@ struct infgen_engine {
     // forcing
     bool forcing = false;
     bool forcing_no_insert = false;
-    // graph
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t graph_exec = nullptr;
-    size_t graph_nodes = 0;
+    // graphs: [0] one motion iteration, [1] insertion stage (WHILE / IF conditional nodes) + motion iteration
+    cudaGraph_t graph[2] = {nullptr, nullptr};
+    cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
+    size_t graph_nodes[2] = {0, 0};
+    size_t pass_nodes = 0, heading_nodes = 0;           // kernel nodes of the WHILE / IF bodies of graph [1]
     int64_t launches = 0;
+    int64_t ins_replays = 0;                            // replays of graph [1] since the counters were last folded in
     bool capturing = false;
 };
 
@@ -339,6 +344,12 @@ static MlpHeadW make_head(infgen_engine *e, const std::string &p, int kin, int n
     return w;
 }
 
+static void drop_graph(infgen_engine *e) {
+    for (int i = 0; i < 2; ++i) {
+        if (e->graph_exec[i]) { cudaGraphExecDestroy(e->graph_exec[i]); e->graph_exec[i] = nullptr; }
+        if (e->graph[i]) { cudaGraphDestroy(e->graph[i]); e->graph[i] = nullptr; }
+    }
+}
 static int ensure(infgen_engine *e, const char *name, size_t bytes, void **out) {
     DevBuf &b = e->bufs[name];
     if (b.bytes < bytes) {
@@ -348,8 +359,7 @@ static int ensure(infgen_engine *e, const char *name, size_t bytes, void **out) 
         CK(cudaMalloc(&b.p, alloc));
         CK(cudaMemsetAsync(b.p, 0, alloc, e->stream));
         b.bytes = alloc;
-        if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
-        if (e->graph) { cudaGraphDestroy(e->graph); e->graph = nullptr; }
+        drop_graph(e);
     }
     *out = b.p;
     return 0;
@@ -641,17 +651,15 @@ static int enqueue_layers(infgen_engine *e, bool with_edges, int trace_iter) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// insertion stage (agent_decoder.py:1744-2114), host-driven: the number of passes is data dependent
+// insertion stage (agent_decoder.py:1744-2114).  The number of passes per iteration is data dependent (up to 10, each
+// of which may append a row and then runs the heading stage for it).  Three enqueue functions hold the launches:
+//     enqueue_insertion_begin   once per iteration
+//     enqueue_insertion_pass    the seed query + decision (+ row append) of one pass
+//     enqueue_heading_stage     heading / offset of the rows appended by the last pass
+// and two drivers sequence them: the host-driven loop of run_insertion (plain launches: traced / profiled runs; one
+// 8-byte flag read per pass) and the captured iteration graph, where the loop is a WHILE node and the heading stage an
+// IF node inside its body whose condition values k_ins_begin / k_seed_decide set on the device (no host round trip).
 // ---------------------------------------------------------------------------------------------------------------
-static int launch_mlp_layer(infgen_engine *e, const MlpHeadW &w, const float *x, int n, float *out) {
-    MlpLayerArgs la;
-    memset(&la, 0, sizeof(la));
-    la.n = n; la.x = x; la.w = w; la.out = out;
-    ProfScope ps(e, KC_INSERT);
-    k_mlp_layer<<<dim3((n + HM - 1) / HM, w.n_pad / 128), NT_S, MLP_LAYER_SMEM, e->stream>>>(la);
-    CKL(); count_launch(e);
-    return 0;
-}
 // every active row >= row_lo through a stack of layers WITHOUT edges, keeping the K|V rows of the non-bipartite ones
 static int enqueue_edgeless(infgen_engine *e, const int *row_lo, float *x, bool seed_stack) {
     LayerArgs la;
@@ -687,162 +695,252 @@ static int enqueue_edgeless(infgen_engine *e, const int *row_lo, float *x, bool 
 }
 static int enqueue_embed_rows(infgen_engine *e, const int *row_lo);
 
-static int run_insertion(infgen_engine *e) {
+static int enqueue_insertion_begin(infgen_engine *e) {
     DecState &s = e->st;
     InsState &q = e->ins;
-    const int ns = e->n_scenes, R = e->R, cap = e->cap, G = e->cfg.grid_size;
+    const int ns = e->n_scenes, R = e->R;
     cudaStream_t st = e->stream;
-    float *x = fbuf(e, "x"), *x_sa = fbuf(e, "x_sa"), *x_ha = fbuf(e, "x_ha");
     {
         ProfScope ps(e, KC_INSERT);
         k_ins_begin<<<ns, NT, 0, st>>>(s, q);
     }
     CKL(); count_launch(e);
     // agents through the seed stack without edges -> K|V of the a2sa layers
-    CK(cudaMemcpyAsync(x_sa, x, (size_t)R * 128 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    RET(enqueue_edgeless(e, nullptr, x_sa, true));
+    k_copy_new_rows<<<R, 128, 0, st>>>(s, nullptr, fbuf(e, "x"), fbuf(e, "x_sa"));
+    CKL(); count_launch(e);
+    RET(enqueue_edgeless(e, nullptr, fbuf(e, "x_sa"), true));
     // relative embeddings of the map -> seed edges (the seed pose is the ego pose for every pass of the iteration)
     FourierArgs fj;
     memset(&fj, 0, sizeof(fj));
     fj.normalize = 1; fj.dim = 3; fj.n_slots = ns * SEED_MAP_MAX; fj.cnt = q.ps_cnt; fj.stride = SEED_MAP_MAX;
     fj.raw = q.ps_raw; fj.w = e->f_ps; fj.out = fbuf(e, "rhat_ps");
+    return launch_fourier(e, &fj, 1, KC_INSERT);
+}
+
+static int enqueue_insertion_pass(infgen_engine *e) {
+    DecState &s = e->st;
+    InsState &q = e->ins;
+    const int ns = e->n_scenes, R = e->R;
+    cudaStream_t st = e->stream;
+    SeedPrepArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.s = s; pa.q = q; pa.occ_embed = e->h_occ_embed;
+    for (int i = 0; i < 3; ++i) pa.occ2sa[i] = e->occ2sa[i];
+    {
+        ProfScope ps(e, KC_INSERT);
+        k_seed_prepare<<<ns, NT, 0, st>>>(pa);
+    }
+    CKL(); count_launch(e);
+    FourierArgs fj;
+    memset(&fj, 0, sizeof(fj));
+    fj.normalize = 1; fj.dim = 3; fj.n_slots = ns * q.as_stride; fj.cnt = q.as_cnt; fj.stride = q.as_stride;
+    fj.raw = q.as_raw; fj.w = e->f_as; fj.out = fbuf(e, "rhat_as");
     RET(launch_fourier(e, &fj, 1, KC_INSERT));
-    bool heading_ready = false;
-    for (int pass = 0; pass < INSERT_LIMIT; ++pass) {
-        SeedPrepArgs pa;
-        memset(&pa, 0, sizeof(pa));
-        pa.s = s; pa.q = q; pa.occ_embed = e->h_occ_embed;
-        for (int i = 0; i < 3; ++i) pa.occ2sa[i] = e->occ2sa[i];
-        {
-            ProfScope ps(e, KC_INSERT);
-            k_seed_prepare<<<ns, NT, 0, st>>>(pa);
+    {   // the query rows: 3 x {occ2sa, pt2sa, a2sa} with their edges
+        LayerArgs la;
+        memset(&la, 0, sizeof(la));
+        la.rows.n_total = ns * SEED_ROW_STRIDE; la.rows.cap = SEED_ROW_STRIDE; la.rows.n_rows = q.active;
+        la.rows.row_lo = nullptr;
+        la.x = q.x_seed; la.ring = RING;
+        la.pre0 = make_pre(e->occ2sa[0], false, nullptr, false, 0, false);
+        const size_t kvl = (size_t)R * 256, kvm = (size_t)e->P * 256;
+        int n = 0;
+        for (int i = 0; i < 3; ++i) {
+            SubArgs &o = la.sub[n++];
+            o.w = e->occ2sa[i].cs_post; o.has_attn = 1; o.has_pos = 0; o.elist = 0; o.row_shift = 2; o.wide = 1;
+            o.kv = q.kv_occ + (size_t)i * ns * 256; o.cnt = q.one_cnt; o.start = nullptr; o.stride = 1; o.src = q.occ_src;
+            o.pre = make_pre(e->pt2sa[i], false, nullptr, false, 0, false);
+            SubArgs &p = la.sub[n++];
+            p.w = e->pt2sa[i].cs_post; p.has_attn = 1; p.has_pos = 1; p.elist = 1; p.row_shift = 2; p.wide = 1;
+            p.kv = fbuf(e, "kv_ms") + i * kvm; p.cnt = q.ps_cnt; p.start = nullptr; p.stride = SEED_MAP_MAX;
+            p.src = q.ps_src; p.rhat = fbuf(e, "rhat_ps");
+            p.pre = make_pre(e->a2sa[i], false, nullptr, false, 0, false);
+            SubArgs &g = la.sub[n++];
+            g.w = e->a2sa[i].cs_post; g.has_attn = 1; g.has_pos = 1; g.elist = 2; g.row_shift = 2; g.wide = 1;
+            g.kv = fbuf(e, "kv_sa") + i * kvl; g.cnt = q.as_cnt; g.start = nullptr; g.stride = q.as_stride;
+            g.src = q.as_src; g.rhat = fbuf(e, "rhat_as");
+            if (i < 2) g.pre = make_pre(e->occ2sa[i + 1], false, nullptr, false, 0, false);
         }
+        la.n_sub = n;
+        const int saved = e->row_tile;
+        e->row_tile = 4;
+        int rc = launch_layer(e, la, KC_INSERT);
+        e->row_tile = saved;
+        RET(rc);
+    }
+    {   // the three grid-sized heads of the query rows in one launch
+        MlpLayerArgs la;
+        memset(&la, 0, sizeof(la));
+        la.n = ns * SEED_ROW_STRIDE; la.x = q.x_seed;
+        la.w = e->h_seed_pos; la.out = q.pos_logits;
+        la.w2 = e->h_ag_occ; la.out2 = q.ag_occ_logits;
+        la.w3 = e->h_pt_occ; la.out3 = q.pt_occ_logits;
+        const int npad = std::max(la.w.n_pad, std::max(la.w2.n_pad, la.w3.n_pad));
+        ProfScope ps(e, KC_INSERT);
+        k_mlp_layer<<<dim3((la.n + HM - 1) / HM, npad / 128, 3), NT_S, MLP_LAYER_SMEM, st>>>(la);
         CKL(); count_launch(e);
-        memset(&fj, 0, sizeof(fj));
-        fj.normalize = 1; fj.dim = 3; fj.n_slots = ns * cap; fj.cnt = q.as_cnt; fj.stride = cap;
-        fj.raw = q.as_raw; fj.w = e->f_as; fj.out = fbuf(e, "rhat_as");
-        RET(launch_fourier(e, &fj, 1, KC_INSERT));
-        {   // the query rows: 3 x {occ2sa, pt2sa, a2sa} with their edges
-            LayerArgs la;
-            memset(&la, 0, sizeof(la));
-            la.rows.n_total = ns * SEED_ROW_STRIDE; la.rows.cap = SEED_ROW_STRIDE; la.rows.n_rows = q.active;
-            la.rows.row_lo = nullptr;
-            la.x = q.x_seed; la.ring = RING;
-            la.pre0 = make_pre(e->occ2sa[0], false, nullptr, false, 0, false);
-            const size_t kvl = (size_t)R * 256, kvm = (size_t)e->P * 256;
-            int n = 0;
-            for (int i = 0; i < 3; ++i) {
-                SubArgs &o = la.sub[n++];
-                o.w = e->occ2sa[i].cs_post; o.has_attn = 1; o.has_pos = 0; o.elist = 0; o.row_shift = 2; o.wide = 1;
-                o.kv = q.kv_occ + (size_t)i * ns * 256; o.cnt = q.one_cnt; o.start = nullptr; o.stride = 1; o.src = q.occ_src;
-                o.pre = make_pre(e->pt2sa[i], false, nullptr, false, 0, false);
-                SubArgs &p = la.sub[n++];
-                p.w = e->pt2sa[i].cs_post; p.has_attn = 1; p.has_pos = 1; p.elist = 1; p.row_shift = 2; p.wide = 1;
-                p.kv = fbuf(e, "kv_ms") + i * kvm; p.cnt = q.ps_cnt; p.start = nullptr; p.stride = SEED_MAP_MAX;
-                p.src = q.ps_src; p.rhat = fbuf(e, "rhat_ps");
-                p.pre = make_pre(e->a2sa[i], false, nullptr, false, 0, false);
-                SubArgs &g = la.sub[n++];
-                g.w = e->a2sa[i].cs_post; g.has_attn = 1; g.has_pos = 1; g.elist = 2; g.row_shift = 2; g.wide = 1;
-                g.kv = fbuf(e, "kv_sa") + i * kvl; g.cnt = q.as_cnt; g.start = nullptr; g.stride = cap;
-                g.src = q.as_src; g.rhat = fbuf(e, "rhat_as");
-                if (i < 2) g.pre = make_pre(e->occ2sa[i + 1], false, nullptr, false, 0, false);
-            }
-            la.n_sub = n;
-            const int saved = e->row_tile;
-            e->row_tile = 4;
-            int rc = launch_layer(e, la, KC_INSERT);
-            e->row_tile = saved;
-            RET(rc);
+    }
+    SeedDecideArgs da;
+    memset(&da, 0, sizeof(da));
+    da.s = s; da.q = q; da.h_state = e->h_seed_state; da.h_type = e->h_seed_type; da.h_shape = e->h_seed_shape;
+    {
+        ProfScope ps(e, KC_INSERT);
+        k_seed_decide<<<ns, NT, 0, st>>>(da);
+    }
+    CKL(); count_launch(e);
+    return 0;
+}
+
+// heading stage of the rows appended by the last pass (:2003-2074)
+static int enqueue_heading_stage(infgen_engine *e) {
+    DecState &s = e->st;
+    InsState &q = e->ins;
+    const int ns = e->n_scenes, R = e->R;
+    cudaStream_t st = e->stream;
+    float *x = fbuf(e, "x"), *x_sa = fbuf(e, "x_sa"), *x_ha = fbuf(e, "x_ha");
+    // K|V of every row for the heading stack (motion layers 0..2 without edges): all rows on the first heading stage of
+    // the iteration (ha_lo = 0), none afterwards (k_new_edges raises ha_lo; appended rows are added at the end)
+    k_copy_new_rows<<<R, 128, 0, st>>>(s, q.ha_lo, x, x_ha);
+    CKL(); count_launch(e);
+    RET(enqueue_edgeless(e, q.ha_lo, x_ha, false));
+    // categorical embedding row of the new agent: type_a_emb[type] + shape_emb(shape)
+    MlpEmbArgs ma;
+    memset(&ma, 0, sizeof(ma));
+    ma.rows = scene_rows(e); ma.rows.row_lo = q.row_lo; ma.w = e->e_shape; ma.kin = 3; ma.k4 = 1;
+    ma.x = q.shape_rows; ma.x_ld = 3; ma.out = fbuf(e, "cat_tab"); ma.out_ld = 128;
+    RET(launch_mlp_embed(e, ma, KC_INSERT));
+    k_add_type_emb_rows<<<R, 128, 0, st>>>(s, q.row_lo, fbuf(e, "cat_tab"), e->type_emb);
+    CKL(); count_launch(e);
+    RET(enqueue_embed_rows(e, q.row_lo));       // feature of the new row with the dummy heading
+    {
+        ProfScope ps(e, KC_INSERT);
+        k_new_edges<<<ns, 64, 0, st>>>(s, q);
+    }
+    CKL(); count_launch(e);
+    FourierArgs hj[2];
+    memset(hj, 0, sizeof(hj));
+    hj[0].normalize = 1; hj[0].dim = 3; hj[0].n_slots = ns * NEW_MAP_MAX; hj[0].cnt = q.hp_cnt_s; hj[0].stride = NEW_MAP_MAX;
+    hj[0].raw = q.hp_raw; hj[0].w = e->f_m; hj[0].out = fbuf(e, "rhat_hp");
+    hj[1].normalize = 1; hj[1].dim = 3; hj[1].n_slots = ns * NEW_AGENT_MAX; hj[1].cnt = q.ha_cnt_s; hj[1].stride = NEW_AGENT_MAX;
+    hj[1].raw = q.ha_raw; hj[1].w = e->f_a; hj[1].out = fbuf(e, "rhat_ha");
+    RET(launch_fourier(e, hj, 2, KC_INSERT));
+    {   // the new rows through 3 x {pt2a, a2a} with their 10 m neighbourhoods
+        LayerArgs la;
+        memset(&la, 0, sizeof(la));
+        la.rows = scene_rows(e); la.rows.row_lo = q.row_lo; la.x = x; la.ring = RING; la.col_ptr = s.col;
+        la.pre0 = make_pre(e->m[0], false, nullptr, false, 0, false);
+        const size_t kvl = (size_t)R * 256, kvm = (size_t)e->P * 256;
+        int n = 0;
+        for (int i = 0; i < 3; ++i) {
+            SubArgs &p = la.sub[n++];
+            p.w = e->m[i].cs_post; p.has_attn = 1; p.has_pos = 1; p.elist = 0;
+            p.kv = fbuf(e, "kv_m") + i * kvm; p.cnt = q.hp_cnt; p.start = q.hp_start; p.src = q.hp_src;
+            p.rhat = fbuf(e, "rhat_hp");
+            p.pre = make_pre(e->a[i], false, nullptr, false, 0, false);
+            SubArgs &g = la.sub[n++];
+            g.w = e->a[i].cs_post; g.has_attn = 1; g.has_pos = 1; g.elist = 1;
+            g.kv = fbuf(e, "kv_ha") + i * kvl; g.cnt = q.ha_cnt; g.start = q.ha_start; g.src = q.ha_src;
+            g.rhat = fbuf(e, "rhat_ha");
+            if (i < 2) g.pre = make_pre(e->m[i + 1], false, nullptr, false, 0, false);
         }
-        RET(launch_mlp_layer(e, e->h_seed_pos, q.x_seed, ns * SEED_ROW_STRIDE, q.pos_logits));
-        RET(launch_mlp_layer(e, e->h_ag_occ, q.x_seed, ns * SEED_ROW_STRIDE, q.ag_occ_logits));
-        RET(launch_mlp_layer(e, e->h_pt_occ, q.x_seed, ns * SEED_ROW_STRIDE, q.pt_occ_logits));
-        SeedDecideArgs da;
-        memset(&da, 0, sizeof(da));
-        da.s = s; da.q = q; da.h_state = e->h_seed_state; da.h_type = e->h_seed_type; da.h_shape = e->h_seed_shape;
-        {
-            ProfScope ps(e, KC_INSERT);
-            k_ins_clear_new_flag<<<1, 1, 0, st>>>(q);
-            k_seed_decide<<<ns, NT, 0, st>>>(da);
-            k_ins_flags<<<1, 1, 0, st>>>(q, ns);
+        la.n_sub = n;
+        RET(launch_layer(e, la, KC_INSERT));
+    }
+    HeadFinalArgs ha;
+    memset(&ha, 0, sizeof(ha));
+    ha.s = s; ha.q = q; ha.x = x; ha.h_heading = e->h_seed_heading; ha.h_offset = e->h_seed_offset;
+    {
+        ProfScope ps(e, KC_INSERT);
+        k_head_finalize<<<ns, NT, 0, st>>>(ha);
+    }
+    CKL(); count_launch(e);
+    RET(enqueue_embed_rows(e, q.row_lo));       // final feature of the new row (:2086-2097)
+    // the new rows become sources of later passes: their edge-less K|V rows of both stacks
+    k_copy_new_rows<<<R, 128, 0, st>>>(s, q.row_lo, x, x_sa);
+    k_copy_new_rows<<<R, 128, 0, st>>>(s, q.row_lo, x, x_ha);
+    CKL(); count_launch(e); count_launch(e);
+    RET(enqueue_edgeless(e, q.row_lo, x_sa, true));
+    RET(enqueue_edgeless(e, q.row_lo, x_ha, false));
+    return 0;
+}
+
+// host-driven loop (plain launches)
+static int run_insertion(infgen_engine *e) {
+    InsState &q = e->ins;
+    cudaStream_t st = e->stream;
+    q.use_cond = 0;
+    RET(enqueue_insertion_begin(e));
+    // debug tools: INFGEN_DEBUG_STOP_PASS="<iteration>:<pass>" stops the rollout right after that pass's decision, so
+    // that the buffers of the seed query can be compared with the oracle (tools/debug_long_insertion.py)
+    int stop_iter = -1, stop_pass = -1;
+    if (const char *sp = getenv("INFGEN_DEBUG_STOP_PASS")) sscanf(sp, "%d:%d", &stop_iter, &stop_pass);
+    for (int pass = 0; pass < INSERT_LIMIT; ++pass) {
+        RET(enqueue_insertion_pass(e));
+        if (e->iters_done == stop_iter && pass == stop_pass) {
+            CK(cudaStreamSynchronize(st));
+            return fail(INFGEN_ERR_STATE, "debug stop after pass %d of iteration %d", pass, stop_iter);
         }
-        CKL(); count_launch(e); count_launch(e); count_launch(e);
         int flags[2] = {0, 0};
         CK(cudaMemcpyAsync(flags, q.flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        if (flags[1]) {
-            // ---- heading stage of the appended rows (:2003-2074) ----
-            if (!heading_ready) {
-                CK(cudaMemcpyAsync(x_ha, x, (size_t)R * 128 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-                RET(enqueue_edgeless(e, nullptr, x_ha, false));
-                heading_ready = true;
-            }
-            // categorical embedding row of the new agent: type_a_emb[type] + shape_emb(shape)
-            MlpEmbArgs ma;
-            memset(&ma, 0, sizeof(ma));
-            ma.rows = scene_rows(e); ma.rows.row_lo = q.row_lo; ma.w = e->e_shape; ma.kin = 3; ma.k4 = 1;
-            ma.x = q.shape_rows; ma.x_ld = 3; ma.out = fbuf(e, "cat_tab"); ma.out_ld = 128;
-            RET(launch_mlp_embed(e, ma, KC_INSERT));
-            k_add_type_emb_rows<<<R, 128, 0, st>>>(s, q.row_lo, fbuf(e, "cat_tab"), e->type_emb);
-            CKL(); count_launch(e);
-            RET(enqueue_embed_rows(e, q.row_lo));       // feature of the new row with the dummy heading
-            {
-                ProfScope ps(e, KC_INSERT);
-                k_new_edges<<<ns, 64, 0, st>>>(s, q);
-            }
-            CKL(); count_launch(e);
-            FourierArgs hj[2];
-            memset(hj, 0, sizeof(hj));
-            hj[0].normalize = 1; hj[0].dim = 3; hj[0].n_slots = ns * NEW_MAP_MAX; hj[0].cnt = q.hp_cnt_s; hj[0].stride = NEW_MAP_MAX;
-            hj[0].raw = q.hp_raw; hj[0].w = e->f_m; hj[0].out = fbuf(e, "rhat_hp");
-            hj[1].normalize = 1; hj[1].dim = 3; hj[1].n_slots = ns * NEW_AGENT_MAX; hj[1].cnt = q.ha_cnt_s; hj[1].stride = NEW_AGENT_MAX;
-            hj[1].raw = q.ha_raw; hj[1].w = e->f_a; hj[1].out = fbuf(e, "rhat_ha");
-            RET(launch_fourier(e, hj, 2, KC_INSERT));
-            {   // the new rows through 3 x {pt2a, a2a} with their 10 m neighbourhoods
-                LayerArgs la;
-                memset(&la, 0, sizeof(la));
-                la.rows = scene_rows(e); la.rows.row_lo = q.row_lo; la.x = x; la.ring = RING; la.col_ptr = s.col;
-                la.pre0 = make_pre(e->m[0], false, nullptr, false, 0, false);
-                const size_t kvl = (size_t)R * 256, kvm = (size_t)e->P * 256;
-                int n = 0;
-                for (int i = 0; i < 3; ++i) {
-                    SubArgs &p = la.sub[n++];
-                    p.w = e->m[i].cs_post; p.has_attn = 1; p.has_pos = 1; p.elist = 0;
-                    p.kv = fbuf(e, "kv_m") + i * kvm; p.cnt = q.hp_cnt; p.start = q.hp_start; p.src = q.hp_src;
-                    p.rhat = fbuf(e, "rhat_hp");
-                    p.pre = make_pre(e->a[i], false, nullptr, false, 0, false);
-                    SubArgs &g = la.sub[n++];
-                    g.w = e->a[i].cs_post; g.has_attn = 1; g.has_pos = 1; g.elist = 1;
-                    g.kv = fbuf(e, "kv_ha") + i * kvl; g.cnt = q.ha_cnt; g.start = q.ha_start; g.src = q.ha_src;
-                    g.rhat = fbuf(e, "rhat_ha");
-                    if (i < 2) g.pre = make_pre(e->m[i + 1], false, nullptr, false, 0, false);
-                }
-                la.n_sub = n;
-                RET(launch_layer(e, la, KC_INSERT));
-            }
-            HeadFinalArgs ha;
-            memset(&ha, 0, sizeof(ha));
-            ha.s = s; ha.q = q; ha.x = x; ha.h_heading = e->h_seed_heading; ha.h_offset = e->h_seed_offset;
-            {
-                ProfScope ps(e, KC_INSERT);
-                k_head_finalize<<<ns, NT, 0, st>>>(ha);
-            }
-            CKL(); count_launch(e);
-            RET(enqueue_embed_rows(e, q.row_lo));       // final feature of the new row (:2086-2097)
-            // the new rows become sources of later passes: their edge-less K|V rows of both stacks
-            k_copy_new_rows<<<R, 128, 0, st>>>(s, q.row_lo, x, x_sa);
-            k_copy_new_rows<<<R, 128, 0, st>>>(s, q.row_lo, x, x_ha);
-            CKL(); count_launch(e); count_launch(e);
-            RET(enqueue_edgeless(e, q.row_lo, x_sa, true));
-            RET(enqueue_edgeless(e, q.row_lo, x_ha, false));
-        }
+        if (flags[1]) RET(enqueue_heading_stage(e));
         if (!flags[0]) break;
     }
-    int err = 0;
-    CK(cudaMemcpyAsync(&err, q.err, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    if (err == 2) return fail(INFGEN_ERR_CAPACITY, "insertion stage ran out of rows (row_capacity %d)", cap);
     return 0;
+}
+
+// ---- conditional graph nodes populated by stream capture (tools/probe/cond_graph.cu is the stand-alone probe) ---------
+// While the engine stream is capturing, add_cond_node appends a WHILE / IF node behind the work captured so far and
+// queues its body; drain_cond_bodies captures the queued bodies (which may queue nested ones) once the enclosing
+// capture has ended.  Condition handles belong to the top-level graph.
+struct CondBody { cudaGraph_t graph; int (*fn)(infgen_engine *); };
+static thread_local std::vector<CondBody> g_cond_bodies;
+static int add_cond_node(infgen_engine *e, cudaGraphConditionalHandle h, cudaGraphConditionalNodeType type,
+                         int (*body)(infgen_engine *)) {
+    cudaStreamCaptureStatus status;
+    cudaGraph_t g = nullptr;
+    const cudaGraphNode_t *deps = nullptr;
+    size_t n_deps = 0;
+    CK(cudaStreamGetCaptureInfo(e->stream, &status, nullptr, &g, &deps, &n_deps));
+    if (status != cudaStreamCaptureStatusActive) return fail(INFGEN_ERR_STATE, "conditional node outside a stream capture");
+    cudaGraphNodeParams p = {};
+    p.type = cudaGraphNodeTypeConditional;
+    p.conditional.handle = h;
+    p.conditional.type = type;
+    p.conditional.size = 1;
+    cudaGraphNode_t node;
+    CK(cudaGraphAddNode(&node, g, deps, n_deps, &p));
+    CK(cudaStreamUpdateCaptureDependencies(e->stream, &node, 1, cudaStreamSetCaptureDependencies));
+    g_cond_bodies.push_back(CondBody{p.conditional.phGraph_out[0], body});
+    return 0;
+}
+// node_counts: nodes of every body in the order they were captured
+static int drain_cond_bodies(infgen_engine *e, std::vector<size_t> &node_counts) {
+    while (!g_cond_bodies.empty()) {
+        const CondBody b = g_cond_bodies.back();
+        g_cond_bodies.pop_back();
+        CK(cudaStreamBeginCaptureToGraph(e->stream, b.graph, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+        const int rc = b.fn(e);
+        const cudaError_t ce = cudaStreamEndCapture(e->stream, nullptr);
+        if (rc != 0) { g_cond_bodies.clear(); return rc; }
+        if (ce != cudaSuccess) {
+            g_cond_bodies.clear();
+            return fail(INFGEN_ERR_CUDA, "capture of a conditional body failed: %s", cudaGetErrorString(ce));
+        }
+        size_t n = 0;
+        CK(cudaGraphGetNodes(b.graph, nullptr, &n));
+        node_counts.push_back(n);
+    }
+    return 0;
+}
+static int cond_body_pass(infgen_engine *e) {
+    RET(enqueue_insertion_pass(e));
+    return add_cond_node(e, e->ins.h_new, cudaGraphCondTypeIf, enqueue_heading_stage);
+}
+// insertion stage inside the captured iteration graph
+static int enqueue_insertion_graph(infgen_engine *e) {
+    RET(enqueue_insertion_begin(e));
+    return add_cond_node(e, e->ins.h_pass, cudaGraphCondTypeWhile, cond_body_pass);
 }
 
 // edges whose destination is column col + col_add and their relative embeddings
@@ -857,12 +955,12 @@ static int enqueue_edges(infgen_engine *e, int col_add) {
     FourierArgs fj[3];
     memset(fj, 0, sizeof(fj));
     fj[0].normalize = 1; fj[0].dim = 3;       // the large one first: agent<->agent
-    fj[0].n_slots = R * e->cap; fj[0].cnt = s.a_cnt; fj[0].stride = e->cap;
+    fj[0].n_slots = R * s.a_stride; fj[0].cnt = s.a_cnt; fj[0].stride = s.a_stride;
     fj[0].raw = s.a_raw; fj[0].w = e->f_a; fj[0].out = fbuf(e, "rhat_a");
-    if (e->fourier_tc && (R * e->cap + ftc::TM - 1) / ftc::TM > 148) {
+    if (e->fourier_tc && (R * s.a_stride + ftc::TM - 1) / ftc::TM > 148) {
         // batches: walk a compact list of the valid agent<->agent slots (a single scene's tiles fit one wave anyway)
-        int *list = (int *)e->bufs["a_slots"].p, *n_list = list + (size_t)R * e->cap;
-        k_slot_compact<<<1, 1024, 0, e->stream>>>(s.a_cnt, R, e->cap, list, n_list, n_list + 4);
+        int *list = (int *)e->bufs["a_slots"].p, *n_list = list + (size_t)R * s.a_stride;
+        k_slot_compact<<<1, 1024, 0, e->stream>>>(s.a_cnt, R, s.a_stride, list, n_list, n_list + 4);
         CKL(); count_launch(e);
         fj[0].slot_list = list; fj[0].n_list = n_list;
     }
@@ -1131,8 +1229,7 @@ int32_t infgen_create(const infgen_config *cfg, const float *weights, int64_t n_
 int32_t infgen_destroy(infgen_engine *e) {
     if (!e) return 0;
     cudaStreamSynchronize(e->stream);
-    if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
-    if (e->graph) cudaGraphDestroy(e->graph);
+    drop_graph(e);
     for (auto &r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto &kv : e->bufs)
         if (kv.second.p) cudaFree(kv.second.p);
@@ -1146,11 +1243,6 @@ int32_t infgen_destroy(infgen_engine *e) {
     if (e->ev_join) cudaEventDestroy(e->ev_join);
     delete e;
     return 0;
-}
-
-static void drop_graph(infgen_engine *e) {
-    if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
-    if (e->graph) { cudaGraphDestroy(e->graph); e->graph = nullptr; }
 }
 
 int32_t infgen_set_stream(infgen_engine *e, void *cuda_stream) {
@@ -1168,10 +1260,24 @@ int32_t infgen_set_sampler(infgen_engine *e, int32_t beam, uint32_t seed) {
     e->st.beam = beam; e->st.seed = seed;
     return 0;
 }
+// device-side error flag (1: an attention row exceeded its edge slots, 2: the insertion stage ran out of rows) and the
+// mbarrier watchdog of k_fourier_tc; the stream must be idle
+static int check_device_errors(infgen_engine *e) {
+    int err = 0;
+    CK(cudaMemcpy(&err, e->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (err) {
+        CK(cudaMemset(e->d_err, 0, sizeof(int)));
+        if (err == 2)
+            return fail(INFGEN_ERR_CAPACITY, "insertion stage ran out of rows (row_capacity %d): reload the batch with a larger "
+                        "row_capacity", e->cap);
+        return fail(INFGEN_ERR_CAPACITY, "device error flag %d (an attention row exceeded its edge capacity)", err);
+    }
+    return check_ftc_watchdog();
+}
 int32_t infgen_synchronize(infgen_engine *e) {
     if (!e) return fail(INFGEN_ERR_INVALID_ARG, "null engine");
     CK(cudaStreamSynchronize(e->stream));
-    return 0;
+    return e->loaded ? check_device_errors(e) : 0;
 }
 
 static cudaMemcpyKind in_kind(int loc) { return loc == INFGEN_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice; }
@@ -1179,11 +1285,10 @@ static cudaMemcpyKind out_kind(int loc) { return loc == INFGEN_DEVICE ? cudaMemc
 
 int32_t infgen_load_scenes(infgen_engine *e, const infgen_scene_batch *b, int32_t loc) {
     if (!e || !b) return fail(INFGEN_ERR_INVALID_ARG, "null argument");
-    if (b->n_scenes < 1 || b->row_capacity < 1 || b->row_capacity % 4 != 0 || b->row_capacity > MAX_CAP)
-        return fail(INFGEN_ERR_CAPACITY, "row_capacity %d must be a multiple of 4 in [4,%d]", b->row_capacity, MAX_CAP);
-    if (b->row_capacity > e->cfg.max_a2a_neighbors)
-        return fail(INFGEN_ERR_CAPACITY, "row_capacity %d exceeds max_a2a_neighbors %d (neighbour truncation is not implemented)",
-                    b->row_capacity, e->cfg.max_a2a_neighbors);
+    if (b->n_scenes < 1 || b->row_capacity < 1 || b->row_capacity % 4 != 0 || b->row_capacity > MAX_ROW_CAPACITY)
+        return fail(INFGEN_ERR_CAPACITY, "row_capacity %d must be a multiple of 4 in [4,%d]", b->row_capacity, MAX_ROW_CAPACITY);
+    if ((int64_t)b->n_scenes * b->row_capacity > (int64_t)1 << 22)
+        return fail(INFGEN_ERR_CAPACITY, "%d scenes x %d rows exceed the row space (4 M rows)", b->n_scenes, b->row_capacity);
     const int HC = e->cfg.hist_cols;
     if (b->n_cols < HC + b->n_iters || b->n_iters < 0)
         return fail(INFGEN_ERR_INVALID_ARG, "n_cols %d < hist_cols %d + n_iters %d", b->n_cols, HC, b->n_iters);
@@ -1206,6 +1311,7 @@ int32_t infgen_load_scenes(infgen_engine *e, const infgen_scene_batch *b, int32_
     memset(&s, 0, sizeof(s));
     s.n_scenes = ns; s.cap = cap; s.T = T; s.S = S; s.HC = HC; s.W = W; s.q_rows = e->cfg.num_seed_feature;
     s.G = e->cfg.grid_size; s.V = V; s.max_m = MM;
+    s.max_a = e->cfg.max_a2a_neighbors; s.a_stride = std::min(cap, s.max_a + 1);
     s.r_m2 = e->cfg.pl2a_radius * e->cfg.pl2a_radius; s.r_a2 = e->cfg.a2a_radius * e->cfg.a2a_radius;
     s.use_state_token = e->cfg.use_state_token; s.disable_insertion = e->cfg.disable_insertion;
     s.beam = e->cfg.motion_beam_size; s.seed = e->cfg.seed;
@@ -1257,7 +1363,7 @@ int32_t infgen_load_scenes(infgen_engine *e, const infgen_scene_batch *b, int32_
     RET(ensure_t(e, "m_cnt", R, &s.m_cnt)); RET(ensure_t(e, "m_src", (size_t)R * MM, &s.m_src));
     RET(ensure_t(e, "m_raw", (size_t)R * MM * 3, &s.m_raw));
     RET(ensure_t(e, "a_cnt", R, &s.a_cnt)); RET(ensure_t(e, "a_start", R, &s.a_start)); RET(ensure_t(e, "a_total", ns, &s.a_total));
-    RET(ensure_t(e, "a_src", (size_t)R * cap, &s.a_src)); RET(ensure_t(e, "a_raw", (size_t)R * cap * 3, &s.a_raw));
+    RET(ensure_t(e, "a_src", (size_t)R * s.a_stride, &s.a_src)); RET(ensure_t(e, "a_raw", (size_t)R * s.a_stride * 3, &s.a_raw));
     RET(ensure_t(e, "xa_raw", (size_t)R * 2, &s.xa_raw));
     RET(ensure_t(e, "tok_row", R, &s.tok_row)); RET(ensure_t(e, "state_idx", R, &s.state_idx));
     RET(ensure_t(e, "grid_row", R, &s.grid_row)); RET(ensure_t(e, "cat_idx", R, &s.cat_idx));
@@ -1280,8 +1386,8 @@ int32_t infgen_load_scenes(infgen_engine *e, const infgen_scene_batch *b, int32_
     { unsigned *gb; RET(ensure_t(e, "grid_bar", 4, &gb)); }
     RET(ensure_t(e, "kv_m", (size_t)6 * std::max(P, 1) * 256, &tmp));
     RET(ensure_t(e, "rhat_t", (size_t)R * W * 128, &tmp)); RET(ensure_t(e, "rhat_m", (size_t)R * MM * 128, &tmp));
-    RET(ensure_t(e, "rhat_a", (size_t)R * cap * 128, &tmp));
-    { int *itmp; RET(ensure_t(e, "a_slots", (size_t)R * cap + 4 + R, &itmp)); }   // slot list, count, row offsets
+    RET(ensure_t(e, "rhat_a", (size_t)R * s.a_stride * 128, &tmp));
+    { int *itmp; RET(ensure_t(e, "a_slots", (size_t)R * s.a_stride + 4 + R, &itmp)); }   // slot list, count, row offsets
     RET(ensure_t(e, "cat_tab", (size_t)(R + 1) * 128, &tmp)); RET(ensure_t(e, "shape_rows", (size_t)(R + 1) * 4, &tmp));
     RET(ensure_t(e, "hist_traj", (size_t)R * HC * 5 * 2, &tmp)); RET(ensure_t(e, "hist_head", (size_t)R * HC * 5, &tmp));
     if (getenv("INFGEN_TSTAMP")) { long long *ts; RET(ensure_t(e, "tstamp", 512, &ts)); }
@@ -1305,10 +1411,13 @@ int32_t infgen_load_scenes(infgen_engine *e, const infgen_scene_batch *b, int32_
         RET(ensure_t(e, "ins_active", ns, &q.active)); RET(ensure_t(e, "ins_n_new", ns, &q.n_new));
         RET(ensure_t(e, "ins_pass", ns, &q.pass)); RET(ensure_t(e, "ins_new_row", ns, &q.new_row));
         RET(ensure_t(e, "ins_row_lo", ns, &q.row_lo)); RET(ensure_t(e, "ins_flags", 4, &q.flags));
+        RET(ensure_t(e, "ins_done_ctr", 4, &q.done_ctr)); RET(ensure_t(e, "ins_ha_lo", ns, &q.ha_lo));
+        RET(ensure_t(e, "ins_stat", 4, &q.stat));
+        q.as_stride = std::min(cap, SEED_AGENT_MAX);
         RET(ensure_t(e, "ps_cnt", ns, &q.ps_cnt)); RET(ensure_t(e, "ps_src", (size_t)ns * SEED_MAP_MAX, &q.ps_src));
         RET(ensure_t(e, "ps_raw", (size_t)ns * SEED_MAP_MAX * 3, &q.ps_raw));
-        RET(ensure_t(e, "as_cnt", ns, &q.as_cnt)); RET(ensure_t(e, "as_src", (size_t)ns * cap, &q.as_src));
-        RET(ensure_t(e, "as_raw", (size_t)ns * cap * 3, &q.as_raw));
+        RET(ensure_t(e, "as_cnt", ns, &q.as_cnt)); RET(ensure_t(e, "as_src", (size_t)ns * q.as_stride, &q.as_src));
+        RET(ensure_t(e, "as_raw", (size_t)ns * q.as_stride * 3, &q.as_raw));
         RET(ensure_t(e, "one_cnt", ns, &q.one_cnt)); RET(ensure_t(e, "occ_src", ns, &q.occ_src));
         RET(ensure_t(e, "hp_cnt", R, &q.hp_cnt)); RET(ensure_t(e, "hp_start", R, &q.hp_start));
         RET(ensure_t(e, "hp_src", (size_t)ns * NEW_MAP_MAX, &q.hp_src)); RET(ensure_t(e, "hp_raw", (size_t)ns * NEW_MAP_MAX * 3, &q.hp_raw));
@@ -1329,7 +1438,7 @@ int32_t infgen_load_scenes(infgen_engine *e, const infgen_scene_batch *b, int32_
         RET(ensure_t(e, "x_sa", (size_t)R * 128, &tmp)); RET(ensure_t(e, "x_ha", (size_t)R * 128, &tmp));
         RET(ensure_t(e, "kv_sa", (size_t)3 * R * 256, &tmp)); RET(ensure_t(e, "kv_ha", (size_t)3 * R * 256, &tmp));
         RET(ensure_t(e, "kv_ms", (size_t)3 * std::max(P, 1) * 256, &tmp));
-        RET(ensure_t(e, "rhat_ps", (size_t)ns * SEED_MAP_MAX * 128, &tmp)); RET(ensure_t(e, "rhat_as", (size_t)ns * cap * 128, &tmp));
+        RET(ensure_t(e, "rhat_ps", (size_t)ns * SEED_MAP_MAX * 128, &tmp)); RET(ensure_t(e, "rhat_as", (size_t)ns * q.as_stride * 128, &tmp));
         RET(ensure_t(e, "rhat_hp", (size_t)ns * NEW_MAP_MAX * 128, &tmp)); RET(ensure_t(e, "rhat_ha", (size_t)ns * NEW_AGENT_MAX * 128, &tmp));
         q.shape_rows = fbuf(e, "shape_rows");
         q.seed_feat = e->seed_feat; q.err = e->d_err;
@@ -1423,6 +1532,45 @@ int32_t infgen_prefill(infgen_engine *e) {
     return 0;
 }
 
+// capture one decode iteration (which = 1: preceded by the insertion stage) into e->graph[which]
+static int capture_iteration(infgen_engine *e, int which) {
+    CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    e->capturing = true;
+    int rc = 0;
+    if (which == 1) {
+        cudaStreamCaptureStatus status;
+        cudaGraph_t top = nullptr;
+        cudaError_t ce = cudaStreamGetCaptureInfo(e->stream, &status, nullptr, &top, nullptr, nullptr);
+        if (ce == cudaSuccess) ce = cudaGraphConditionalHandleCreate(&e->ins.h_pass, top, 0, cudaGraphCondAssignDefault);
+        if (ce == cudaSuccess) ce = cudaGraphConditionalHandleCreate(&e->ins.h_new, top, 0, cudaGraphCondAssignDefault);
+        if (ce != cudaSuccess) rc = fail(INFGEN_ERR_CUDA, "conditional handles: %s", cudaGetErrorString(ce));
+        e->ins.use_cond = 1;
+        if (rc == 0) rc = enqueue_insertion_graph(e);
+    }
+    if (rc == 0) rc = enqueue_iteration(e, -1);
+    cudaGraph_t g = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
+    if (rc == 0 && ce != cudaSuccess) rc = fail(INFGEN_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+    if (rc == 0 && which == 1) {
+        // bodies of the conditional nodes: the pass (WHILE) and, nested in it, the heading stage (IF)
+        std::vector<size_t> counts;
+        rc = drain_cond_bodies(e, counts);
+        if (rc == 0 && counts.size() == 2) {
+            e->pass_nodes = counts[0] - 1;               // minus the IF node
+            e->heading_nodes = counts[1];
+        }
+    } else {
+        g_cond_bodies.clear();
+    }
+    e->capturing = false;
+    e->ins.use_cond = 0;
+    if (rc != 0) { if (g) cudaGraphDestroy(g); return rc; }
+    e->graph[which] = g;
+    CK(cudaGraphGetNodes(g, nullptr, &e->graph_nodes[which]));
+    CK(cudaGraphInstantiate(&e->graph_exec[which], g, 0));
+    return 0;
+}
+
 int32_t infgen_step(infgen_engine *e, int32_t n_iters) {
     if (!e || !e->loaded) return fail(INFGEN_ERR_STATE, "no scenes loaded");
     if (!e->prefilled) return fail(INFGEN_ERR_STATE, "infgen_prefill has not run");
@@ -1430,24 +1578,16 @@ int32_t infgen_step(infgen_engine *e, int32_t n_iters) {
         return fail(INFGEN_ERR_INVALID_ARG, "%d iterations requested, %d of %d already done", n_iters, e->iters_done, e->S);
     const bool use_graph = e->cfg.use_cuda_graph && !e->cfg.trace && !e->profile;
     for (int i = 0; i < n_iters; ++i) {
-        if (e->ins_ready && e->iters_done > 0 && !e->forcing_no_insert) RET(run_insertion(e));
+        // the insertion stage runs from the second iteration on (agent_decoder.py:1773)
+        const bool ins = e->ins_ready && e->iters_done > 0 && !e->forcing_no_insert;
         if (use_graph) {
-            if (!e->graph_exec) {
-                CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
-                e->capturing = true;
-                int rc = enqueue_iteration(e, -1);
-                e->capturing = false;
-                cudaGraph_t g = nullptr;
-                cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
-                if (rc != 0) { if (g) cudaGraphDestroy(g); return rc; }
-                if (ce != cudaSuccess) return fail(INFGEN_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
-                e->graph = g;
-                CK(cudaGraphGetNodes(g, nullptr, &e->graph_nodes));
-                CK(cudaGraphInstantiate(&e->graph_exec, g, 0));
-            }
-            CK(cudaGraphLaunch(e->graph_exec, e->stream));
-            e->launches += (int64_t)e->graph_nodes;
+            const int which = ins ? 1 : 0;
+            if (!e->graph_exec[which]) RET(capture_iteration(e, which));
+            CK(cudaGraphLaunch(e->graph_exec[which], e->stream));
+            e->launches += (int64_t)e->graph_nodes[which] - (which == 1 ? 1 : 0);
+            if (which == 1) e->ins_replays++;
         } else {
+            if (ins) RET(run_insertion(e));
             RET(enqueue_iteration(e, e->iters_done));
         }
         e->iters_done++;
@@ -1462,7 +1602,21 @@ int32_t infgen_rollout(infgen_engine *e) {
 }
 
 int32_t infgen_iterations_done(infgen_engine *e) { return e ? e->iters_done : -1; }
-int64_t infgen_kernel_launches(infgen_engine *e) { return e ? e->launches : -1; }
+int64_t infgen_kernel_launches(infgen_engine *e) {
+    if (!e) return -1;
+    if (e->ins_replays > 0 && e->ins.stat) {
+        // launches inside the conditional bodies of the replayed insertion stage: counted on the device (passes, heading
+        // stages), folded in here
+        int h[2] = {0, 0};
+        if (cudaStreamSynchronize(e->stream) == cudaSuccess &&
+            cudaMemcpy(h, e->ins.stat, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            e->launches += (int64_t)h[0] * (int64_t)e->pass_nodes + (int64_t)h[1] * (int64_t)e->heading_nodes;
+            cudaMemset(e->ins.stat, 0, sizeof(h));
+        }
+        e->ins_replays = 0;
+    }
+    return e->launches;
+}
 
 int32_t infgen_read(infgen_engine *e, const infgen_outputs *o, int32_t loc) {
     if (!e || !e->loaded || !o) return fail(INFGEN_ERR_STATE, "no scenes loaded");
@@ -1496,12 +1650,11 @@ int32_t infgen_read(infgen_engine *e, const infgen_outputs *o, int32_t loc) {
         if (o->pt_occ_seed) CK(cudaMemcpyAsync(o->pt_occ_seed, q.o_pt_occ, nso * G * sizeof(float), k, st));
         if (o->occ_gt_seed) CK(cudaMemcpyAsync(o->occ_gt_seed, q.o_occ_gt, nso * G * sizeof(float), k, st));
     }
+    // results in host memory are complete when this returns, and so are the error checks; device-resident results are
+    // asynchronous: errors of that rollout surface at infgen_synchronize
     if (loc == INFGEN_HOST) {
         CK(cudaStreamSynchronize(st));
-        int err = 0;
-        CK(cudaMemcpy(&err, e->d_err, sizeof(int), cudaMemcpyDeviceToHost));
-        if (err) return fail(INFGEN_ERR_CAPACITY, "an attention row exceeded its edge capacity");
-        RET(check_ftc_watchdog());
+        RET(check_device_errors(e));
     }
     return 0;
 }

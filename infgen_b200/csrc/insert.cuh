@@ -38,10 +38,19 @@ struct InsState {
     int *pass;                         // passes done in this iteration
     int *new_row;                      // row (within the scene) appended by the last pass, -1 if none
     int *row_lo;                       // first row the "new rows only" launches process (= new_row or n_rows)
-    int *flags;                        // [2]: any scene still active, any scene appended a row (host loop control)
+    int *flags;                        // [2]: any scene still active, any scene appended a row (loop control)
+    int *stat;                         // [2] passes / heading stages executed by graph replays (launch accounting)
+    int *done_ctr;                     // CTAs of k_seed_decide that have finished (the last one summarises the pass)
+    int *ha_lo;                        // [ns] first row the heading-stack K/V pass of this iteration still has to cover:
+                                       //      0 until the first heading stage of the iteration ran, then "none"
+    int as_stride;                     // agent -> seed slots per scene: min(cap, SEED_AGENT_MAX)
+    // loop control without the host: condition handles of the CUDA-graph WHILE (another pass) / IF (a row was appended)
+    // nodes, set from k_ins_begin / k_seed_decide when the iteration is replayed as a graph (use_cond)
+    int use_cond;
+    cudaGraphConditionalHandle h_pass, h_new;
     // seed query edges: one destination (the seed row) per scene
     int *ps_cnt, *ps_src; float *ps_raw;   // map -> seed   [ns], [ns*SEED_MAP_MAX], [..][3]
-    int *as_cnt, *as_src; float *as_raw;   // agent -> seed [ns], [ns*cap], [..][3]
+    int *as_cnt, *as_src; float *as_raw;   // agent -> seed [ns], [ns*as_stride], [..][3]
     int *one_cnt, *occ_src;                // occupancy node -> seed: always one edge, source = scene
     // new-agent edges: destination = the appended row; indexed by global row
     int *hp_cnt, *hp_start, *hp_src; float *hp_raw;   // map -> new agent   [R], [R], [ns*NEW_MAP_MAX], [..][3]
@@ -108,8 +117,11 @@ __global__ void __launch_bounds__(NT) k_ins_begin(const DecState s, const InsSta
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         q.active[b] = 1; q.n_new[b] = 0; q.pass[b] = 0; q.new_row[b] = -1; q.row_lo[b] = s.n_rows[b];
-        q.one_cnt[b] = 1; q.occ_src[b] = b;
-        if (b == 0) { q.flags[0] = 1; q.flags[1] = 0; }
+        q.one_cnt[b] = 1; q.occ_src[b] = b; q.ha_lo[b] = 0;
+        if (b == 0) {
+            q.flags[0] = 1; q.flags[1] = 0; *q.done_ctr = 0;
+            if (q.use_cond) cudaGraphSetConditional(q.h_pass, 1u);
+        }
     }
     for (int i = threadIdx.x; i < s.n_rows[b]; i += NT) s.hv_src[b * s.cap + i] = -1;   // vectors were rebuilt (:2265)
     const int re = b * s.cap + s.ego_row[b];
@@ -176,9 +188,9 @@ __global__ void __launch_bounds__(NT) k_seed_prepare(const SeedPrepArgs a) {
     const InsState &q = a.q;
     const int b = blockIdx.x, col = *s.col, T = s.T, G = s.G;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (!q.active[b]) return;
     const int n = s.n_rows[b], r0 = b * s.cap;
     if (tid == 0) { q.new_row[b] = -1; q.row_lo[b] = n; }
+    if (!q.active[b]) return;
     // ---- occupancy (:1851-1853) ----
     float *occ = q.occ + (size_t)b * G;
     for (int g = tid; g < G; g += NT) occ[g] = 0.f;
@@ -189,7 +201,7 @@ __global__ void __launch_bounds__(NT) k_seed_prepare(const SeedPrepArgs a) {
     }
     __syncthreads();
     // ---- first Linear of seed_agent_occ_embed on a 0/1 vector: bias + the columns of the occupied cells ----
-    __shared__ int s_cells[MAX_CAP];                    // occupied cells, ascending
+    __shared__ int s_cells[2048];                       // occupied cells, ascending (G = 1961 cells at most)
     __shared__ int s_ncell;
     if (warp == 0) {
         int cnt = 0;
@@ -248,7 +260,7 @@ __global__ void __launch_bounds__(NT) k_seed_prepare(const SeedPrepArgs a) {
         const bool ok = in_first && s.interact[(size_t)rj * T + col] != 0;
         const unsigned mask = __ballot_sync(0xffffffffu, ok);
         if (ok) {
-            const int slot = b * s.cap + cnt + __popc(mask & lanemask_lt());
+            const int slot = b * q.as_stride + cnt + __popc(mask & lanemask_lt());
             q.as_src[slot] = rj;
             q.as_raw[(size_t)slot * 3 + 0] = norm2(dx, dy);
             q.as_raw[(size_t)slot * 3 + 1] = angle_between(hx, hy, dx, dy);
@@ -269,7 +281,7 @@ struct SeedDecideArgs {
     InsState q;
     MlpHeadW h_state, h_type, h_shape;
 };
-__global__ void __launch_bounds__(NT) k_seed_decide(const SeedDecideArgs a) {
+__device__ __forceinline__ void seed_decide_scene(const SeedDecideArgs &a) {
     __shared__ __align__(16) float sx[128];
     __shared__ __align__(16) float sh[128];
     __shared__ float s_small[8];                        // state[2] type[3] shape[3]
@@ -427,13 +439,34 @@ __global__ void __launch_bounds__(NT) k_seed_decide(const SeedDecideArgs a) {
     }
 }
 
-// after k_seed_decide of every scene: summarise for the host loop (one thread)
-__global__ void k_ins_flags(const InsState q, int n_scenes) {
-    int any = 0;
-    for (int b = 0; b < n_scenes; ++b) any |= q.active[b];
-    q.flags[0] = any;
+// One CTA per scene; the last CTA to finish summarises the pass for whoever drives the loop: flags[] for the host-driven
+// path, the condition values of the WHILE / IF graph nodes for the replayed one.
+__global__ void __launch_bounds__(NT) k_seed_decide(const SeedDecideArgs a) {
+    seed_decide_scene(a);
+    const InsState &q = a.q;
+    __shared__ int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(q.done_ctr, 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        int any = 0, any_new = 0;
+        for (int b = 0; b < (int)gridDim.x; ++b) {
+            any |= ((volatile int *)q.active)[b] != 0;
+            any_new |= ((volatile int *)q.new_row)[b] >= 0;
+        }
+        q.flags[0] = any; q.flags[1] = any_new;
+        *q.done_ctr = 0;
+        if (q.use_cond) {
+            cudaGraphSetConditional(q.h_pass, (unsigned)any);
+            cudaGraphSetConditional(q.h_new, (unsigned)any_new);
+            q.stat[0] += 1; q.stat[1] += any_new;
+        }
+    }
 }
-__global__ void k_ins_clear_new_flag(const InsState q) { q.flags[1] = 0; }
 
 // ---------------------------------------------------------------------------------------------------------------
 // heading stage, edges of the appended rows (:2024-2035): agents within a2sa_radius (first NEW_AGENT_MAX by index)
@@ -443,6 +476,7 @@ __global__ void __launch_bounds__(64) k_new_edges(const DecState s, const InsSta
     const int b = blockIdx.x, col = *s.col, T = s.T;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i_new = q.new_row[b];
+    if (threadIdx.x == 0) q.ha_lo[b] = 1 << 30;           // the heading-stack K|V rows of the old rows exist from now on
     if (i_new < 0) {
         if (threadIdx.x == 0) { q.hp_cnt_s[b] = 0; q.ha_cnt_s[b] = 0; }
         return;
@@ -561,7 +595,7 @@ __global__ void k_add_type_emb_rows(const DecState s, const int *row_lo, float *
 // copy rows [row_lo[b], n_rows[b]) of every scene from one [R][128] buffer to another
 __global__ void k_copy_new_rows(const DecState s, const int *row_lo, const float *src, float *dst) {
     const int r = blockIdx.x, b = r / s.cap, i = r - b * s.cap;
-    if (i < row_lo[b] || i >= s.n_rows[b]) return;
+    if ((row_lo && i < row_lo[b]) || i >= s.n_rows[b]) return;
     dst[(size_t)r * 128 + threadIdx.x] = src[(size_t)r * 128 + threadIdx.x];
 }
 

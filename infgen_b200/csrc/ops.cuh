@@ -459,6 +459,9 @@ struct MlpLayerArgs {
     const float *x;
     MlpHeadW w;
     float *out;                // [n][n_out]
+    // up to three heads over the same input rows in one launch (blockIdx.z): the grid-sized heads of the seed query
+    MlpHeadW w2, w3;
+    float *out2, *out3;
 };
 constexpr size_t MLP_LAYER_SMEM = (size_t)(WS_SMEM_FLOATS + 2 * HM * HLD) * sizeof(float);
 __global__ void __launch_bounds__(NT_S) k_mlp_layer(const MlpLayerArgs a) {
@@ -467,12 +470,15 @@ __global__ void __launch_bounds__(NT_S) k_mlp_layer(const MlpLayerArgs a) {
     float *sx = smem + WS_SMEM_FLOATS, *sh = sx + HM * HLD;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = blockIdx.x * HM, n0 = blockIdx.y * 128;
+    const MlpHeadW &hw = blockIdx.z == 0 ? a.w : (blockIdx.z == 1 ? a.w2 : a.w3);
+    float *out = blockIdx.z == 0 ? a.out : (blockIdx.z == 1 ? a.out2 : a.out3);
+    if (n0 >= hw.n_pad) return;
     ws_init(wsm);
     if (warp == NWARP) {
         if (lane < WS_STAGES) {
             WSeg segs[2];
-            segs[0] = WSeg{a.w.w0, a.w.k4_in, 512};
-            segs[1] = WSeg{a.w.w3 + (size_t)n0 * 4, 32, a.w.n_pad * 4};
+            segs[0] = WSeg{hw.w0, hw.k4_in, 512};
+            segs[1] = WSeg{hw.w3 + (size_t)n0 * 4, 32, hw.n_pad * 4};
             ws_produce(wsm, segs, 2);
         }
         return;
@@ -483,13 +489,13 @@ __global__ void __launch_bounds__(NT_S) k_mlp_layer(const MlpLayerArgs a) {
         st4(sx + m * HLD + 4 * lane, r < a.n ? ld4(a.x + (size_t)r * 128 + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f));
     }
     csync();
-    tile_gemm<HM>(ws, sx, HLD, a.w.k4_in, [&](int m, int n, float v) { sh[m * HLD + n] = v + __ldg(a.w.b0 + n); });
+    tile_gemm<HM>(ws, sx, HLD, hw.k4_in, [&](int m, int n, float v) { sh[m * HLD + n] = v + __ldg(hw.b0 + n); });
     csync();
-    rows_layernorm_c<HM, true>(sh, HLD, a.w.ln_g, a.w.ln_b);
+    rows_layernorm_c<HM, true>(sh, HLD, hw.ln_g, hw.ln_b);
     csync();
     tile_gemm<HM>(ws, sh, HLD, 32, [&](int m, int n, float v) {
         const int r = row0 + m;
-        if (r < a.n && n0 + n < a.w.n_out) a.out[(size_t)r * a.w.n_out + n0 + n] = v + __ldg(a.w.b3 + n0 + n);
+        if (r < a.n && n0 + n < hw.n_out) out[(size_t)r * hw.n_out + n0 + n] = v + __ldg(hw.b3 + n0 + n);
     });
 }
 

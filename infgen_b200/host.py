@@ -139,15 +139,20 @@ class HostBatch:
         T, S = scenes[0].n_cols, scenes[0].n_iters
         HC = cfg.hist_cols
         self.insertion = not cfg.disable_insertion
-        # rows the insertion stage may append (at most 10 per iteration, agent_decoder.py:1738) need room
-        self.reserve = min(cfg.insert_row_reserve, 10 * S) if self.insertion else 0
+        # Rows the insertion stage may append need room.  The reference never compacts and appends up to 10 rows per
+        # iteration (agent_decoder.py:1738), i.e. up to most + 10 S rows.  The first attempt reserves
+        # max(insert_row_reserve, 2 S) of them; `B200AgentDecoder.inference_batch` reloads with a larger row space
+        # when the engine reports INFGEN_ERR_CAPACITY (the rollout is deterministic, so the rerun is the same rollout).
         most = max(s.n_rows for s in scenes)
+        self.max_rows = most + 10 * S if self.insertion else most
+        self.reserve = min(max(cfg.insert_row_reserve, 2 * S), 10 * S) if self.insertion else 0
         cap = row_capacity or (most + self.reserve)
         cap = (cap + 3) // 4 * 4
         # a single scene of up to 120 rows runs all 18 layers of an iteration in ONE launch (15 co-resident clusters of
-        # 8 rows): do not let the reserve push a scene that fits out of that regime
-        if row_capacity is None and len(scenes) == 1 and self.reserve and cap > 120 >= most + 16:
+        # 8 rows): the first attempt does not let the reserve push a scene that fits out of that regime
+        if row_capacity is None and len(scenes) == 1 and self.reserve and S <= 24 and cap > 120 >= most + 16:
             cap = 120
+        self.auto_cap = row_capacity is None
         ns = len(scenes)
         R = ns * cap
         P = sum(s.pt_pos.shape[0] for s in scenes)
@@ -197,9 +202,12 @@ class HostBatch:
         self.fill(scenes, scene_ids)
 
     def fits(self, scenes: Sequence[SceneHost]) -> bool:
+        """Can these scenes reuse the staging buffers?  (A row space grown after a capacity error is kept as long as the
+        scenes are no larger than the ones it was grown for.)"""
+        most = max(s.n_rows for s in scenes)
         return (len(scenes) == self.n_scenes and all(s.n_cols == self.T and s.n_iters == self.S for s in scenes)
-                and max(s.n_rows for s in scenes) + (16 if self.reserve else 0) <= self.cap
-                and self.cap <= (max(s.n_rows for s in scenes) + self.reserve + 3) // 4 * 4
+                and most + (16 if self.reserve else 0) <= self.cap
+                and (not self.auto_cap or self.cap <= (most + self.reserve + 3) // 4 * 4)
                 and sum(s.pt_pos.shape[0] for s in scenes) <= self.p_alloc)
 
     def fill(self, scenes: Sequence[SceneHost], scene_ids: Optional[Sequence[int]] = None):

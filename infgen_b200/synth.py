@@ -68,11 +68,12 @@ def _match_token(vocab_end: np.ndarray, box0: np.ndarray, dx: float, dy: float, 
 
 
 def make_scene(seed: int, num_agents: int = 64, num_map_tokens: int = 2048, num_steps: int = 91,
-               ragged: float = 0.0, ego_index: int = 0, cfg: Optional[DecoderConfig] = None) -> Dict:
+               ragged: float = 0.0, ego_index: int = 0, cfg: Optional[DecoderConfig] = None, box: float = 60.0) -> Dict:
     """One synthetic scene.
 
     ragged: fraction of non-ego agents that enter late / exit early (state tokens enter/exit/invalid in history
     and beyond); 0 gives every agent [enter, valid, valid, ...] which is what a fully observed track tokenises to.
+    box: agents start on lanes within +-box metres of the ego (smaller = more crowded).
     """
     cfg = cfg or DecoderConfig()
     rng = np.random.default_rng(seed)
@@ -83,7 +84,7 @@ def make_scene(seed: int, num_agents: int = 64, num_map_tokens: int = 2048, num_
     P = pt_pos.shape[0]
 
     # --- agents on lanes near the ego -------------------------------------------------------------------
-    near = np.nonzero((np.abs(pt_pos[:, 0]) < 60.0) & (np.abs(pt_pos[:, 1]) < 60.0))[0]
+    near = np.nonzero((np.abs(pt_pos[:, 0]) < box) & (np.abs(pt_pos[:, 1]) < box))[0]
     anchor = rng.choice(near, size=A, replace=len(near) < A)
     a_type = rng.choice(3, size=A, p=[0.7, 0.2, 0.1]).astype(np.uint8)
     a_type[ego_index] = 0

@@ -502,6 +502,7 @@ def rollout(scene: Dict, W: Dict[str, torch.Tensor], cfg, seed: int = 2024, scen
     next_state_list = [hist_state[:, i:i + 1] for i in range(HC)]
     seed_state_prob, seed_pos_prob, seed_agent_occ, seed_pt_occ, seed_occ_gt = [], [], [], [], []
     insert_log: List[Dict] = []
+    pass_log: List[Dict] = []
     cache: Dict[int, torch.Tensor] = {}
     trace: List[Dict] = []
     insert_limit = 10
@@ -547,6 +548,11 @@ def rollout(scene: Dict, W: Dict[str, torch.Tensor], cfg, seed: int = 2024, scen
                 x = attention_layer(W, f'a2sa_attn_layers.{i}', x, x, e_a2s[3], e_a2s[0], e_a2s[1], False)
                 feat = x.view(T, A + 1, H).transpose(0, 1)
             q = feat[-1:, cur]                                                               # [1,128]
+            if collect_trace:                                      # seed-query taps of every pass (debug tools)
+                pass_log.append({'t': t, 'pass': p_pass - 1, 'q': q[0].clone(), 'occ': occ.clone(), 'occ_emb': occ_emb[0].clone(),
+                                 'as_src': (e_a2s[0] % (A + 1)).clone(), 'as_raw': e_a2s[2].clone(),
+                                 'ps_src': (e_p2s[0] % P).clone(), 'ps_raw': e_p2s[2].clone(),
+                                 'x_sa_in': feat0[:, cur].clone()})
             ego_pos, ego_head = pos[av, cur], head[av, cur]
             g_ag = mlp_layer(W, 'grid_agent_occ_head', q)
             g_pt = mlp_layer(W, 'grid_pt_occ_head', q)
@@ -654,7 +660,11 @@ def rollout(scene: Dict, W: Dict[str, torch.Tensor], cfg, seed: int = 2024, scen
             occ_gt[n_new], ag_occ[n_new], pt_occ[n_new], pos_prob[n_new] = occ.float(), g_ag, g_pt, p_soft
             st_prob[n_new] = s_prob.softmax(-1)[:, -1]
             insert_log.append({'t': t, 'cell': int(cell[0, 0]), 'type': int(ty_idx[0, 0]), 'pos': pos[-1, cur].clone(),
-                               'head': head[-1, cur].clone(), 'shape': shp[0].clone(), 'heading_token': int(h_idx[0, 0])})
+                               'head': head[-1, cur].clone(), 'shape': shp[0].clone(), 'heading_token': int(h_idx[0, 0]),
+                               # heading-stage taps (debug tools): agent / map neighbours of the new row, head input
+                               'ha_src': (e_a[0] % (A + 1)).clone(), 'ha_raw': e_a[2].clone(), 'hp_src': (e_p[0] % P).clone(),
+                               'hp_raw': e_p[2].clone(), 'hq': hq[0].clone(), 'offset': off[0].clone(), 'q': q[0].clone(),
+                               'as_src': (e_a2s[0] % (A + 1)).clone(), 'feat_in': feat_s[0, cur].clone()})
         seed_state_prob.append(st_prob)
         seed_pos_prob.append(pos_prob)
         seed_agent_occ.append(ag_occ)
@@ -801,4 +811,4 @@ def rollout(scene: Dict, W: Dict[str, torch.Tensor], cfg, seed: int = 2024, scen
         'grid_pt_occ_seed': torch.cat(seed_pt_occ, dim=1) if seed_pt_occ else None,
         'grid_agent_occ_gt_seed': torch.cat(seed_occ_gt, dim=1) if seed_occ_gt else None,
     }
-    return {'out': out, 'trace': trace, 'insert_log': insert_log}
+    return {'out': out, 'trace': trace, 'insert_log': insert_log, 'pass_log': pass_log}

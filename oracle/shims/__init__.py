@@ -22,7 +22,12 @@ import types
 import importlib.machinery
 from unittest import mock
 
+import os
+
+# the reference tree: where it lies in the build container, else the copy staged by oracle/make_ref.py (GPU box)
 REFERENCE_ROOT = '/root/reference'
+if not os.path.isdir(os.path.join(REFERENCE_ROOT, 'infgen', 'modules')):
+    REFERENCE_ROOT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), '_ref')
 
 
 def _module(name, **attrs):

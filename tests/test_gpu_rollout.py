@@ -271,20 +271,164 @@ def test_long_horizon_matches_oracle():
         _close(got[k].numpy(), want[k].numpy(), k)
 
 
-def test_insertion_capacity_error_is_reported():
-    """Rows appended beyond the reserved capacity must surface as an error of the call, not as silent truncation; the
-    engine stays usable afterwards."""
+def test_insertion_capacity_error_and_recovery():
+    """Rows appended beyond the row space must surface as INFGEN_ERR_CAPACITY through the C ABI (never as silent
+    truncation); `inference` then reruns the rollout in a larger row space, as the reference grows its tensors without
+    bound (agent_decoder.py:1923-1995), and returns the rollout a sufficiently large row space gives directly."""
+    from infgen_b200 import _capi
+    from infgen_b200.host import prepare_scene, HostBatch
     from infgen_b200.weights import make_state_dict
     from infgen_b200.synth import make_scene
-    cfg = DecoderConfig(motion_beam_size=1, insert_beam_size=10, disable_insertion=False, debug_force_enter=True,
-                        insert_row_reserve=6)
+    cfg = DecoderConfig(motion_beam_size=1, insert_beam_size=10, disable_insertion=False, debug_force_enter=True)
     sd = make_state_dict(3)
     scene = make_scene(23, num_agents=12, num_map_tokens=512, num_steps=91, ragged=0.3, ego_index=2, cfg=cfg)
     dec = _make_decoder(sd, cfg, use_cuda_graph=True)
-    with pytest.raises(RuntimeError, match='ran out of rows'):
-        dec.inference(scene, scene['map_enc'])
-    dec.cfg.insert_row_reserve = 128
-    dec._host_cache = None
+    sh = prepare_scene(scene, scene['map_enc'], cfg)
+    small = HostBatch([sh], cfg, [0], row_capacity=sh.n_rows + 8)
+    dec.load(small, [sh])
+    dec.rollout()
+    with pytest.raises(_capi.CapacityError, match='ran out of rows'):
+        dec.read()
+    big = HostBatch([sh], cfg, [0], row_capacity=256)
+    dec.load(big, [sh])
+    dec.rollout()
+    dec.read()
+    n_big = int(big.out_n_rows[0])
+    assert n_big > 60
+    # the public call starts from the default reserve (max(64, 2 S) rows, clamped to the 120-row single-launch regime
+    # for a short horizon) and must end with the same rollout however many times it had to grow
+    dec._host_cache = HostBatch([sh], cfg, [0], row_capacity=sh.n_rows + 8)
+    dec._host_cache.auto_cap = False
     out = dec.inference(scene, scene['map_enc'])
+    assert out['pos_a'].shape[0] == n_big
+    assert dec._batch.cap > sh.n_rows + 8
+    assert torch.equal(out['next_token_idx'], big.out_next_token[:n_big, :out['next_token_idx'].shape[1]].long())
     dec.close()
-    assert out['pos_a'].shape[0] > 60
+
+
+def _wrap_margin(trace):
+    """Distance of the relative headings of a rollout from the +-pi discontinuity of wrap_angle (see
+    test_insertion_topk_matches_oracle)."""
+    worst = np.pi
+    for w in trace:
+        for key in ('edges_a', 'edges_t'):
+            rh = w[key]['raw'][:, 2].abs()
+            rh = rh[rh < 3.2]
+            if rh.numel():
+                worst = min(worst, np.pi - float(rh.max()))
+    return worst
+
+
+@pytest.mark.parametrize('mode', ['greedy_forced', 'topk_natural'])
+def test_long_term_config_with_insertion_matches_oracle(mode):
+    """configs/ours_long_term.yaml (num_recurrent_steps_val = 300 -> S = 60 iterations, T = 62 columns) with the insertion
+    stage live, as the reference runs it: greedy with the seed head forced to 'enter' (one agent per iteration), and the
+    shipped samplers (top-5 motion tokens, top-10 insertion cells) with the seed head left to the random-init weights.
+    Rows, tokens and states exactly those of the oracle; trajectories within tolerance."""
+    from oracle.agent_decoder_oracle import rollout
+    from infgen_b200.weights import make_state_dict
+    from infgen_b200.synth import make_scene
+    if mode == 'greedy_forced':
+        cfg = DecoderConfig(motion_beam_size=1, insert_beam_size=1, disable_insertion=False, debug_force_enter=True,
+                            num_recurrent_steps_val=300)
+        sd, scene_seed = make_state_dict(2), 41
+    else:
+        cfg = DecoderConfig(motion_beam_size=5, insert_beam_size=10, disable_insertion=False, num_recurrent_steps_val=300)
+        sd, scene_seed = make_state_dict(0), 42
+    scene = make_scene(scene_seed, num_agents=8, num_map_tokens=256, num_steps=91, ragged=0.3, ego_index=1, cfg=cfg)
+    ref = rollout(scene, sd, cfg, seed=2024, scene_id=0, debug_force_enter=cfg.debug_force_enter, collect_trace=True)
+    want = ref['out']
+    assert _wrap_margin(ref['trace']) > 1e-5, 'test case hits the +-pi wrap discontinuity'
+    dec = _make_decoder(sd, cfg, use_cuda_graph=True, seed=2024)
+    got = dec.inference(scene, scene['map_enc'])
+    dec.close()
+    assert got['next_token_idx'].shape[1] == 62
+    assert got['pos_a'].shape == want['pos_a'].shape, f"rows {got['pos_a'].shape[0]} vs oracle {want['pos_a'].shape[0]}"
+    div = _first_divergence(got['next_token_idx'].numpy(), want['next_token_idx'].numpy(), cfg.hist_cols)
+    assert div is None, f'{mode}: tokens diverge from the oracle at iteration {div[0]}, rows {div[1]}'
+    for k in ('next_token_idx', 'next_state_idx', 'agent_id', 'pred_type', 'pred_valid'):
+        assert torch.equal(got[k], want[k]), k
+    for k in ('pos_a', 'head_a', 'pred_traj', 'pred_head', 'pred_state', 'pred_shape', 'next_state_prob_seed',
+              'next_pos_rel_prob_seed', 'grid_agent_occ_seed', 'grid_pt_occ_seed', 'grid_agent_occ_gt_seed'):
+        _close(got[k].numpy(), want[k].numpy(), f'{mode} {k}')
+
+
+def test_150s_rollout_with_insertion_properties():
+    """BASELINE configs[4] horizon: num_recurrent_steps_val = 1500 (S = 300 iterations, T = 302 columns) with the insertion
+    stage appending an agent in most iterations - far beyond what the CPU oracle finishes in minutes, so size-independent
+    properties: the row space grows (capacity reruns included) instead of failing; the replayed graph (WHILE / IF
+    conditional nodes driven from the device) and the host-driven loop produce the SAME rollout, bit for bit; rows only
+    ever grow; the 5th sub-step of iteration t is the position of column t + 2 for rows that stay valid."""
+    from infgen_b200.weights import make_state_dict
+    from infgen_b200.synth import make_scene
+    cfg = DecoderConfig(motion_beam_size=5, insert_beam_size=1, disable_insertion=False, debug_force_enter=True,
+                        num_recurrent_steps_val=1500)
+    sd = make_state_dict(2)
+    scene = make_scene(51, num_agents=8, num_map_tokens=256, num_steps=91, ragged=0.0, ego_index=1, cfg=cfg)
+    outs = []
+    for graph in (True, False):
+        dec = _make_decoder(sd, cfg, use_cuda_graph=graph, seed=7)
+        outs.append(dec.inference(scene, scene['map_enc']))
+        cap = dec._batch.cap
+        dec.close()
+    a, b = outs
+    S, nh, HC = 300, cfg.num_historical_steps, cfg.hist_cols
+    n = a['pos_a'].shape[0]
+    assert a['next_token_idx'].shape == (n, HC + S) and a['pred_traj'].shape == (n, nh + 5 * S, 2)
+    assert n > 100 and n <= cap, f'{n} rows after 300 iterations (row space {cap})'
+    for k in ('next_token_idx', 'next_state_idx', 'pos_a', 'head_a', 'pred_traj', 'pred_head', 'pred_type', 'agent_id'):
+        assert torch.equal(a[k], b[k]), f'graph replay and host-driven loop differ in {k}'
+    assert a['next_pos_rel_prob_seed'].shape == (11, S, 1961)
+    st = a['next_state_idx'][:, HC:]
+    for t in range(S):
+        ok = (st[:, t] == 1)
+        assert torch.allclose(a['pred_traj'][ok, nh + 5 * t + 4], a['pos_a'][ok, HC + t], atol=1e-5), t
+    # appended rows are invalid before their insertion column and enter exactly once
+    ins = (a['next_state_idx'] == 2)
+    assert bool((ins[8:].sum(1) == 1).all())
+
+
+def test_a2a_neighbour_limit_matches_oracle(monkeypatch):
+    """`radius_graph(max_num_neighbors=300)` (agent_decoder.py:632-634) truncates a crowded scene: each row keeps the first
+    301 rows within the radius by index, itself included, minus the self loop, and `subgraph` drops non-interacting ends
+    afterwards.  (a) A whole rollout with the limit lowered to 20 against the oracle; (b) the edge list of a 340-agent
+    scene packed into 40 m against the oracle's `interaction_edges` for the real limit."""
+    from oracle.agent_decoder_oracle import rollout
+    from infgen_b200.weights import make_state_dict
+    from infgen_b200.synth import make_scene
+    from infgen_b200.host import prepare_scene, HostBatch
+    sd = make_state_dict(1)
+    cfg = DecoderConfig(motion_beam_size=1, disable_insertion=True, max_a2a_neighbors=20)
+    scene = make_scene(61, num_agents=40, num_map_tokens=256, num_steps=91, ragged=0.3, ego_index=0, cfg=cfg)
+    want = rollout(scene, sd, cfg)['out']
+    dec = _make_decoder(sd, cfg)
+    got = dec.inference(scene, scene['map_enc'])
+    dec.close()
+    assert _first_divergence(got['next_token_idx'].numpy(), want['next_token_idx'].numpy(), cfg.hist_cols) is None
+    for k in ('pos_a', 'pred_traj', 'pred_head'):
+        _close(got[k].numpy(), want[k].numpy(), k)
+    # (b) edges of iteration 0 of a crowded scene, real limit
+    monkeypatch.setenv('INFGEN_NO_EARLY_EDGES', '1')
+    cfg = DecoderConfig(motion_beam_size=1, disable_insertion=True)
+    scene = make_scene(62, num_agents=340, num_map_tokens=256, num_steps=91, ragged=0.2, ego_index=0, cfg=cfg, box=40.0)
+    ref = rollout(scene, sd, cfg, max_iters=1, collect_trace=True)
+    e = ref['trace'][0]['edges_a']
+    A = ref['trace'][0]['n_rows']
+    src, dst = (e['src'] % A).numpy(), (e['dst'] % A).numpy()
+    dec = _make_decoder(sd, cfg, use_cuda_graph=False)
+    sh = prepare_scene(scene, scene['map_enc'], cfg)
+    hb = HostBatch([sh], cfg, [0])
+    dec.load(hb, [sh])
+    dec.prefill()
+    dec.step(1)
+    dec.synchronize()
+    stride = min(hb.cap, cfg.max_a2a_neighbors + 1)
+    cnt = dec.debug_read('a_cnt', (hb.R,), np.int32)
+    a_src = dec.debug_read('a_src', (hb.R, stride), np.int32)
+    dec.close()
+    assert A == sh.n_rows and A > 301
+    want_cnt = np.bincount(dst, minlength=A)
+    assert want_cnt.max() == 300 or want_cnt.max() == 301, 'the scene does not reach the neighbour limit'
+    assert np.array_equal(cnt[:A], want_cnt)
+    for i in range(A):
+        assert np.array_equal(a_src[i, :cnt[i]], np.sort(src[dst == i])), f'row {i}'
