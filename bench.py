@@ -1,22 +1,29 @@
 #!/usr/bin/env python
 """Benchmark of the closed-loop decode hot path (BASELINE.json metric: agent-steps/sec, 64 agents x 91 steps).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scenes B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 1|2|3|4] [--scenes B]
 
-A *step* is one closed-loop rollout (setup + prefill + 16 decode iterations + result read-back) of one batch of
-synthetic Waymo-shaped scenes.  At N=1 the workload is BASELINE.json configs[1]: one scene, 64 agents, 91 steps,
-top-5 sampling.  With N>1 every rank rolls out its own scenes (weak scaling, no collective on the data path; NCCL only
-gathers a tiny per-rank summary after the timed region).
+A *step* is one closed-loop rollout - `InfGenAgentDecoder.inference` (reference agent_decoder.py:1605-2389): setup,
+prefill, S decode iterations each with its insertion stage, read-back - of one batch of synthetic Waymo-shaped scenes.
+Every configuration runs the decoder the way the reference's shipped configs do: insertion stage ON (the reference
+cannot switch it off, infgen/model/infgen.py:75-76), top-5 motion tokens, top-10 insertion cells, random-init weights.
 
-  value       whole-job agent-steps/s with the scene tensors already resident in HBM, CUDA-event timed on the engine
-              stream, L2 flushed between steps, max over ranks
-  e2e         the same metric through the public call `B200AgentDecoder.inference(data, map_enc)` with host tensors:
-              host setup, pinned H2D, rollout, D2H, output dict - wall clock
-  roofline    dominant kernel class of a profiled replay of the same steps (CUDA events around every launch)
-  cpu_baseline the CPU oracle (a port of the reference path, oracle/agent_decoder_oracle.py) on the host cores
+  --config 1   BASELINE configs[1]: one scene, 64 agents, 91 steps (S = 16)                  (default at --gpus 1)
+  --config 2   BASELINE configs[2]: 32 scenes x 64 agents, 91 steps, one GPU
+  --config 3   BASELINE configs[3]: 32 scenes per GPU (256 at 8 GPUs), scenes dealt round-robin from ONE global list
+               (infgen_b200/sharding.py = Lightning's DistributedSampler, run.py:130-139), per-scene metrics gathered
+               over NCCL after the rollouts                                                  (default at --gpus > 1)
+  --config 4   BASELINE configs[4]: 150 s rollouts (num_recurrent_steps_val = 1500, S = 300), 8 scenes per GPU
 
-`--impl reference` times that CPU port alone (the reference itself is Python that needs /root/reference, which does not
-exist on the GPU box; see DESIGN.md "reference arm").
+  value        whole-job agent-steps/s (agents of the scenes x raw steps per rollout / time) with the scene tensors already
+               resident in HBM, CUDA-event timed on the engine stream, L2 flushed between steps, max over ranks
+  e2e          the same metric through the public call `B200AgentDecoder.inference_batch(data, map_enc)` with host
+               tensors: host setup, pinned H2D, rollout, D2H, output dicts - wall clock
+  roofline     dominant kernel class of a profiled replay of the same steps (CUDA events around every launch)
+  cpu_baseline the reference's own CPU implementation on the host cores (oracle/_ref through oracle/shims when staged,
+               else the CPU port oracle/agent_decoder_oracle.py), bounded sample
+
+`--impl reference` times that CPU implementation alone on the same configuration.
 """
 import argparse
 import json
@@ -31,8 +38,20 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 os.environ.setdefault('TQDM_DISABLE', '1')
 
-N_AGENTS, N_MAP, N_STEPS = 64, 2048, 91
+N_AGENTS, N_MAP, N_STEPS, NH = 64, 2048, 91, 11
 METRIC, UNIT = 'agent-steps/sec', 'agent-steps/s'
+SCENE_SEED0 = 13
+
+CONFIGS = {
+    1: dict(name='configs[1]', scenes_per_gpu=1, n_rec=-1,
+            text='1 scene x 64 agents x 91 steps (16 decode iterations)'),
+    2: dict(name='configs[2]', scenes_per_gpu=32, n_rec=-1,
+            text='32 scenes x 64 agents x 91 steps (16 decode iterations) on one GPU'),
+    3: dict(name='configs[3]', scenes_per_gpu=32, n_rec=-1,
+            text='32 scenes per GPU x 64 agents x 91 steps (16 decode iterations), one global scene list sharded round-robin'),
+    4: dict(name='configs[4]', scenes_per_gpu=8, n_rec=1500,
+            text='8 scenes per GPU x 64 agents, 150 s rollouts (num_recurrent_steps_val = 1500: 300 decode iterations)'),
+}
 
 
 def parse():
@@ -41,10 +60,34 @@ def parse():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--scenes', type=int, default=1, help='scenes per GPU per step (1 = BASELINE configs[1])')
+    ap.add_argument('--config', type=int, default=0, choices=[0, 1, 2, 3, 4], help='BASELINE.json configs[i]; 0 = 1 at --gpus 1, 3 otherwise')
+    ap.add_argument('--scenes', type=int, default=0, help='override the scenes per GPU of the configuration')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--no-extra', action='store_true', help='skip the batch-32 side measurement')
+    ap.add_argument('--no-extra', action='store_true', help='skip the side measurements (motion-only, configs[2], configs[4] shapes)')
     return ap.parse_args()
+
+
+def workload(args):
+    c = args.config or (1 if args.gpus == 1 else 3)
+    w = dict(CONFIGS[c])
+    w['id'] = c
+    if args.scenes:
+        w['scenes_per_gpu'] = args.scenes
+    return w
+
+
+def decoder_config(w, motion_only=False):
+    from infgen_b200.config import DecoderConfig
+    return DecoderConfig(motion_beam_size=5, insert_beam_size=10, disable_insertion=motion_only,
+                         num_recurrent_steps_val=w['n_rec'])
+
+
+def config_block(w, world):
+    """Identical in both arms (the driver compares it)."""
+    return {'workload': f"{w['name']}: {w['text']}; insertion stage on, top-5 motion / top-10 insertion sampling, 2048 map "
+                        f"tokens per scene, random-init weights (seed 0), scene seeds {SCENE_SEED0}+i",
+            'scenes_total': w['scenes_per_gpu'] * world, 'scenes_per_gpu': w['scenes_per_gpu'],
+            'raw_steps_per_agent': NH + (w['n_rec'] if w['n_rec'] > 0 else N_STEPS - NH)}
 
 
 def peaks():
@@ -61,10 +104,10 @@ def peaks():
             'source': 'fallback (B200_PROFILING.md)'}
 
 
-def make_workload(rank, n_scenes, cfg):
+def make_scenes(ids, cfg):
     from infgen_b200.synth import make_scene
-    return [make_scene(1000 * rank + 13 + i, num_agents=N_AGENTS, num_map_tokens=N_MAP, num_steps=N_STEPS, ragged=0.0,
-                       ego_index=5, cfg=cfg) for i in range(n_scenes)]
+    return [make_scene(SCENE_SEED0 + i, num_agents=N_AGENTS, num_map_tokens=N_MAP, num_steps=N_STEPS, ragged=0.0,
+                       ego_index=5, cfg=cfg) for i in ids]
 
 
 class ClockSampler:
@@ -108,98 +151,273 @@ class ClockSampler:
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
-def cpu_rollout_timing(scene, sd, cfg, n_iters=None):
-    """One oracle rollout (or its first n_iters iterations) on all host threads; returns (seconds, iterations)."""
+# ---------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's own CPU implementation of the path
+# ---------------------------------------------------------------------------------------------------------------------
+class CpuReference:
+    """`InfGenAgentDecoder.inference` on the host cores: the UNMODIFIED reference modules staged under oracle/_ref
+    (oracle/make_ref.py) run through oracle/shims when present (kind 'reference'), else the CPU port (kind 'port')."""
+
+    def __init__(self, sd, cfg):
+        import torch
+        self.sd, self.cfg = sd, cfg
+        try:
+            torch.set_num_threads(len(os.sched_getaffinity(0)))      # torchrun pins OMP_NUM_THREADS=1
+        except Exception:
+            pass
+        self.cores = torch.get_num_threads()
+        self.kind, self.dec = 'port', None
+        try:
+            from oracle import ref_runner
+            if ref_runner.reference_available():
+                self.dec = ref_runner.build_reference_decoder(sd, cfg)
+                self.run_reference = ref_runner.run_reference
+                self.kind = 'reference'
+        except Exception as ex:                                       # fall back to the port, say why
+            self.why_port = repr(ex)[:160]
+        self.detail = ('the unmodified reference modules (oracle/_ref: infgen/modules/agent_decoder.py et al., staged by '
+                       'oracle/make_ref.py) through the torch_geometric / torch_cluster stand-ins of oracle/shims'
+                       if self.kind == 'reference' else
+                       'CPU port of InfGenAgentDecoder.inference (oracle/agent_decoder_oracle.py, torch CPU ops)')
+
+    def rollout(self, scene, max_iters=None):
+        """One rollout (or its first max_iters iterations); returns seconds."""
+        import torch
+        t0 = time.perf_counter()
+        if self.kind == 'reference':
+            cfg = self.cfg
+            if max_iters is not None:
+                # the reference has no iteration limit: shorten the horizon instead (whole multiples of `shift` raw steps;
+                # it cannot run a horizon shorter than the scene, agent_decoder.py:1638, so the scene is cut to fit)
+                import copy, dataclasses
+                n_rec = max_iters * cfg.shift
+                cfg = dataclasses.replace(cfg, num_recurrent_steps_val=n_rec)
+                scene = _cut_scene(scene, NH + n_rec) if NH + n_rec < N_STEPS else scene
+                self.dec.num_recurrent_steps_val = n_rec
+            torch.manual_seed(2024)
+            self.run_reference(scene, self.sd, cfg, capture=False, decoder=self.dec)
+        else:
+            from oracle.agent_decoder_oracle import rollout
+            rollout(scene, self.sd, self.cfg, seed=2024, scene_id=0, max_iters=max_iters)
+        return time.perf_counter() - t0
+
+
+def _cut_scene(scene, n_steps):
+    """The first n_steps raw steps of a synthetic scene (token columns cut accordingly)."""
     import torch
-    from oracle.agent_decoder_oracle import rollout
-    S = (N_STEPS - cfg.num_historical_steps) // cfg.shift
-    it = S if n_iters is None else max(1, min(S, n_iters))
+    T = n_steps // 5
+    out = {k: (dict(v) if isinstance(v, dict) else v) for k, v in scene.items()}
+    ag = out['agent']
+    for k, v in list(ag.items()):
+        if isinstance(v, torch.Tensor) and v.dim() >= 2 and v.shape[0] == ag['token_idx'].shape[0]:
+            if v.shape[1] == scene['agent']['token_idx'].shape[1]:
+                ag[k] = v[:, :T].clone()
+            elif v.shape[1] == N_STEPS:
+                ag[k] = v[:, :n_steps].clone()
+    return out
+
+
+def cpu_measure(ref, scenes, S, steps, warmup, budget_s):
+    """Bounded sample: the first `iters` decode iterations of one scene per step, sized so that the whole run stays within
+    budget_s; throughput pro-rated to whole rollouts (early iterations have the fewest rows, which flatters the CPU)."""
+    dt = ref.rollout(scenes[0], 1)
+    iters = int(max(1, min(S, budget_s / max(1e-6, dt * (steps + warmup)))))
+    if iters < S:
+        dt2 = ref.rollout(scenes[0], min(S, 2 * iters))          # iterations get slower as columns fill: re-calibrate
+        iters = int(max(1, min(S, min(S, 2 * iters) * budget_s / max(1e-6, dt2 * (steps + warmup)))))
+    for i in range(warmup):
+        ref.rollout(scenes[i % len(scenes)], iters)
     t0 = time.perf_counter()
-    rollout(scene, sd, cfg, seed=2024, scene_id=0, max_iters=it)
-    return time.perf_counter() - t0, it, S
+    for i in range(steps):
+        ref.rollout(scenes[i % len(scenes)], iters)
+    total = time.perf_counter() - t0
+    return total, iters
 
 
 def run_reference(args, rank, world):
-    """Reference arm: the CPU port of the reference path (oracle) on the host cores, rank 0 only."""
+    """Reference arm: rank 0 alone runs the CPU implementation; the other ranks exit without work."""
     if rank != 0:
         return
-    import torch
-    from infgen_b200.config import DecoderConfig
     from infgen_b200.weights import make_state_dict
-    cfg = DecoderConfig(motion_beam_size=5, disable_insertion=True)
+    w = workload(args)
+    cfg = decoder_config(w)
     sd = make_state_dict(0)
-    scene = make_workload(0, 1, cfg)[0]
-    # torchrun pins OMP_NUM_THREADS=1 for multi-process launches; the reference arm uses every host core it may run on
-    try:
-        torch.set_num_threads(len(os.sched_getaffinity(0)))
-    except Exception:
-        pass
-    cores = torch.get_num_threads()
-    # calibrate the per-step sample so that the whole run stays within ~3 minutes
-    dt, it, S = cpu_rollout_timing(scene, sd, cfg, 1)
-    per_iter = dt
-    budget = 150.0
-    iters = int(max(1, min(S, budget / max(1e-6, per_iter * (args.steps + args.warmup)))))
-    for _ in range(args.warmup):
-        cpu_rollout_timing(scene, sd, cfg, iters)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_rollout_timing(scene, sd, cfg, iters)
-    total = time.perf_counter() - t0
-    agent_steps = N_AGENTS * N_STEPS * iters / S * args.steps       # pro-rated share of the 91-step rollout
+    n_sample = min(w['scenes_per_gpu'] * world, 4)
+    scenes = make_scenes(range(n_sample), cfg)
+    ref = CpuReference(sd, cfg)
+    steps_per_agent = NH + (w['n_rec'] if w['n_rec'] > 0 else N_STEPS - NH)
+    S = (steps_per_agent - NH) // 5
+    total, iters = cpu_measure(ref, scenes, S, args.steps, args.warmup, 150.0)
+    agent_steps = N_AGENTS * steps_per_agent * iters / S * args.steps
     value = agent_steps / total
-    sample = f'{iters} of {S} decode iterations of one 64-agent scene per step (pro-rated to 91 steps)'
+    sample = (f'{iters} of {S} decode iterations of one 64-agent scene per step (scenes {SCENE_SEED0}..{SCENE_SEED0 + n_sample - 1} of the '
+              f'workload in turn), pro-rated to whole rollouts')
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': total / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'configs[1]: 1 scene x 64 agents x 91 steps (16 decode iterations), top-5 sampling, '
-                               '2048 map tokens', 'impl_detail': 'CPU port of InfGenAgentDecoder.inference '
-                               '(oracle/agent_decoder_oracle.py, torch CPU ops); the Python reference needs '
-                               '/root/reference which is absent on the GPU box'},
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config_block(w, world),
+        'impl_detail': ref.detail,
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': ref.cores, 'kind': ref.kind, 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def kernel_models(dec, batch, scenes_rows):
-    """Algorithmic bytes / flops per launch of each kernel class (DESIGN.md section 'roofline accounting')."""
+# ---------------------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------------------
+def kernel_profile(dec, hb, hosts, n_prof=2):
+    """Per-kernel-class CUDA-event timing of profiled rollouts + the algorithmic work of each class per launch."""
     import numpy as np
-    R = batch.R
-    t = dec.debug_read('t_cnt', (R,), np.int32).sum()
-    m = dec.debug_read('m_cnt', (R,), np.int32).sum()
-    a = dec.debug_read('a_cnt', (R,), np.int32).sum()
-    return {'rows': scenes_rows, 'E_t_last': int(t), 'E_m_last': int(m), 'E_a_last': int(a)}
+    pk = peaks()
+    dec.set_profile(True)
+    S = hb.S
+    e_t = e_m = e_a = 0
+    rows_sum = 0
+    for rep in range(n_prof):
+        dec.load(hb, hosts)
+        dec.prefill()
+        for it in range(S):
+            dec.step(1)
+            if rep == 0 and (S <= 20 or it % max(1, S // 20) == 0):
+                e_t += int(dec.debug_read('t_cnt', (hb.R,), np.int32).sum())
+                e_m += int(dec.debug_read('m_cnt', (hb.R,), np.int32).sum())
+                e_a += int(dec.debug_read('a_cnt', (hb.R,), np.int32).sum())
+                rows_sum += int(dec.debug_read('n_rows', (hb.n_scenes,), np.int32).sum())
+                e_t, e_m, e_a = e_t, e_m, e_a
+        dec.synchronize()
+    prof = dec.profile()
+    dec.set_profile(False)
+    sampled = S if S <= 20 else len(range(0, S, max(1, S // 20)))
+    rows = rows_sum / max(1, sampled)                  # average active rows per iteration (inserted rows included)
+    et, em, ea = e_t / sampled, e_m / sampled, e_a / sampled
+    # algorithmic work per launch (fp32; DESIGN.md "roofline accounting", SURVEY.md 8d).  Attention gather: per edge the K
+    # row, the V row (512 B each) and the relative embedding row (512 B, recomputable but here materialised once per
+    # iteration and read by the six layers of its stack) + 4 B source index.  Dense half: folded formulation, 2 * MAC.
+    per_edge_kv, per_edge_all = 1024, 512 + 512 + 512 + 4
+    post_mac, pre_mac, pre_kv_mac = 196608, 49152, 32768     # Wvr+gate+out+ffn | q,s,Wkr fold | k,v
+    w_layer = 1.125e6 + 0.17e6                                # post + pre chunks of one layer (fp32 bytes)
+    edge_flops = 2.0 * 2 * (128 + 16) * 8                     # score + weighted sum, 8 heads
+    tm_bytes = rows * (1024 + 5120 + 1024 + 1024) + (et + em) * per_edge_all + 2 * w_layer
+    a_bytes = rows * (1024 + 5120 + 5120 + 1024) + ea * per_edge_all + w_layer
+    tm_flops = rows * 2.0 * (2 * post_mac + 2 * pre_mac + pre_kv_mac) + (et + em) * edge_flops
+    a_flops = rows * 2.0 * (post_mac + pre_mac + pre_kv_mac) + ea * edge_flops
+    st_bytes = rows * (1024 + 12 * 1024) + 6 * (et + em + ea) * per_edge_all + 18 * w_layer
+    st_flops = 6 * (tm_flops + a_flops)
+    e_avg = (et + em + ea) / 3.0
+    attn_kv_bytes = e_avg * per_edge_kv                       # SURVEY 8d's canonical figure: K, V rows only
+    attn_all_bytes = e_avg * per_edge_all + rows * (512 + 4096 + 512 + 4096 + 32)
+    attn_flops = e_avg * edge_flops
+    node_flops = rows * 2.0 * (post_mac + pre_mac + pre_kv_mac * 2.0 / 3.0)
+    node_bytes = 1.05e6 + rows * (1024 + 512 + 4096 + 32 + 512 + 512 + 512 + 4096 + 1024 * 2.0 / 3.0)
+    model = {
+        'k_layer:stack18': ('hbm', st_bytes, st_flops),
+        'k_layer:temporal+map': ('hbm', tm_bytes, tm_flops),
+        'k_layer:agent': ('hbm', a_bytes, a_flops),
+        'k_attn': ('hbm', attn_kv_bytes, attn_flops),
+        'k_node': ('tensor', node_flops, node_bytes),
+        'k_fourier:edges': ('tensor', (et * (4 * (132 * 128 + 128 * 128) + 128 * 128) +
+                                       (em + ea) * (3 * (132 * 128 + 128 * 128) + 128 * 128)) * 2.0),
+        'k_embed_column': ('tensor', rows * 2.0 * (2 * (132 * 128 + 128 * 128) + 128 * 128 + 512 * 128 + 2 * 128 * 128)),
+        'k_heads': ('tensor', rows * 2.0 * (2 * 128 * 128 + 128 * 2048 + 128 * 128)),
+    }
+    pipes = {'k_fourier:edges': 'tcgen05.mma kind::tf32, 3xTF32 split (3 tensor-core passes per algorithmic flop), fp32 '
+                                'accumulate in TMEM',
+             'k_node': getattr(dec, 'node_pipe', 'fp32 FFMA (reference numerics are fp32)')}
+    klist = []
+    tot = sum(v['ms'] for v in prof.values())
+    for name, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms']):
+        avg_us = v['ms'] * 1e3 / v['launches']
+        ent = {'kernel': name, 'share': v['ms'] / tot, 'avg_us': avg_us, 'launches_per_rollout': v['launches'] / n_prof}
+        if name in model:
+            bound, work = model[name][0], model[name][1]
+            if bound == 'hbm':
+                ach = work / (avg_us * 1e-6) / 1e9
+                ent.update({'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
+                            'frac': ach / pk['hbm_gbs'], 'algorithmic_bytes_per_launch': work})
+                if name == 'k_attn':
+                    ent['bytes_definition'] = 'K and V rows of every edge (1,024 B per edge, SURVEY.md 8d), nothing else'
+                    ent['achieved_incl_rhat_and_handover'] = attn_all_bytes / (avg_us * 1e-6) / 1e9
+                    ent['frac_incl_rhat_and_handover'] = ent['achieved_incl_rhat_and_handover'] / pk['hbm_gbs']
+                if len(model[name]) > 2:
+                    fl = model[name][2] / (avg_us * 1e-6) / 1e12
+                    ent.update({'algorithmic_flops_per_launch': model[name][2], 'fp32_tflops': fl,
+                                'frac_of_fp32_ffma_peak': fl / 72.0})
+            else:
+                ach = work / (avg_us * 1e-6) / 1e12
+                ent.update({'bound': 'tensor', 'achieved': ach, 'peak': pk['bf16_tflops_sustained'],
+                            'unit': 'TFLOP/s', 'frac': ach / pk['bf16_tflops_sustained'],
+                            'algorithmic_flops_per_launch': work,
+                            'pipe': pipes.get(name, 'fp32 FFMA (reference numerics are fp32)'),
+                            'frac_of_fp32_ffma_peak': ach / 72.0})
+                if len(model[name]) > 2:
+                    ent['algorithmic_bytes_per_launch'] = model[name][2]
+        klist.append(ent)
+    return klist, pk, {'rows_avg': rows, 'E_t_avg': et, 'E_m_avg': em, 'E_a_avg': ea}
+
+
+def ncu_traffic(kernel):
+    """dram bytes per launch of `kernel` from the round's ncu --set full capture (profiles/r2_ncu_traffic.json, written by
+    tools/ncu_traffic.py from the .ncu-rep), or None."""
+    path = os.path.join(ROOT, 'profiles', 'r2_ncu_traffic.json')
+    if not os.path.exists(path):
+        return None
+    try:
+        t = json.load(open(path))
+        for k, v in t.get('kernels', {}).items():
+            if kernel.split(':')[0] in k:
+                return v.get('dram_bytes_per_launch')
+    except Exception:
+        pass
+    return None
+
+
+def timed_device_rollouts(dec, db, hosts, steps, warmup, stream, flush, barrier):
+    """load + rollout + read with device-resident inputs / results, CUDA events on the engine stream."""
+    import torch
+    with torch.cuda.stream(stream):
+        for _ in range(max(3, warmup)):
+            dec.load(db, hosts); dec.rollout(); dec.read()
+        barrier()
+        l0 = dec.kernel_launches()
+        evs = []
+        for _ in range(steps):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            dec.load(db, hosts); dec.rollout(); dec.read()
+            e1.record(stream)
+            evs.append((e0, e1))
+        barrier()
+        dec.synchronize()                                 # surfaces device-side errors of the device-resident rollouts
+        launches = dec.kernel_launches() - l0
+    return [a.elapsed_time(b) for a, b in evs], launches
 
 
 def run_ours(args, rank, world, local_rank):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from infgen_b200.config import DecoderConfig
     from infgen_b200.weights import make_state_dict
     from infgen_b200.agent_decoder import B200AgentDecoder
     from infgen_b200.host import prepare_scene, HostBatch, DeviceBatch
+    from infgen_b200.sharding import shard_scenes, gather_scene_metrics
 
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    cfg = DecoderConfig(motion_beam_size=5, disable_insertion=True)
+    w = workload(args)
+    cfg = decoder_config(w)
     sd = make_state_dict(0)
-    dec = B200AgentDecoder(sd, cfg, device=local_rank, seed=2024, use_cuda_graph=True)
-    stream = torch.cuda.Stream(device=dev)
-    dec.set_stream(stream.cuda_stream)
-    scenes = make_workload(rank, args.scenes, cfg)
+    n_total = w['scenes_per_gpu'] * world
+    my_ids = shard_scenes(n_total, rank, world)                      # scene i -> rank i mod world
+    scenes = make_scenes(my_ids, cfg)
     maps = [s['map_enc'] for s in scenes]
-    hosts = [prepare_scene(s, m, cfg) for s, m in zip(scenes, maps)]
-    hb = HostBatch(hosts, cfg, scene_ids=list(range(len(hosts))))
-    with torch.cuda.stream(stream):
-        db = DeviceBatch(hb, dev)
+    steps_per_agent = NH + (w['n_rec'] if w['n_rec'] > 0 else N_STEPS - NH)
+    stream = torch.cuda.Stream(device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
-    agent_steps = sum(h.n_rows for h in hosts) * N_STEPS
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -207,262 +425,158 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def device_step():
-        dec.load(db, hosts)
-        dec.rollout()
-        dec.read()
-
-    # ---- value: inputs resident in HBM, CUDA events on the engine stream ---------------------------------------
-    with torch.cuda.stream(stream):
-        for _ in range(max(3, args.warmup)):
-            device_step()
-        barrier()
-        sampler = ClockSampler(local_rank) if rank == 0 else None
-        l0 = dec.kernel_launches()
-        evs = []
-        for _ in range(args.steps):
-            flush.fill_(1)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            device_step()
-            e1.record(stream)
-            evs.append((e0, e1))
-        barrier()
-        launches = dec.kernel_launches() - l0
+    def measure(dec_cfg, scn, mps, ids, steps, warmup, sampler_rank0=False, e2e=True):
+        """value (device-resident) and e2e (public call) of one decoder configuration on one list of scenes."""
+        dec = B200AgentDecoder(sd, dec_cfg, device=local_rank, seed=2024, use_cuda_graph=True)
+        # the public call first: it also settles the row capacity (the insertion stage may need capacity reruns)
+        for _ in range(2):
+            outs = dec.inference_batch(scn, mps, scene_ids=ids)
+        hosts = list(dec._scenes)
+        cap = dec._batch.cap
+        hb = HostBatch(hosts, dec_cfg, scene_ids=ids, row_capacity=cap)
+        dec.set_stream(stream.cuda_stream)
+        with torch.cuda.stream(stream):
+            db = DeviceBatch(hb, dev)
+        sampler = ClockSampler(local_rank) if sampler_rank0 and rank == 0 else None
+        step_ms, launches = timed_device_rollouts(dec, db, hosts, steps, warmup, stream, flush, barrier)
         clocks = sampler.stop() if sampler else None
-    step_ms = [a.elapsed_time(b) for a, b in evs]
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+        dec.set_stream(None)
+        res = {'dec': dec, 'hb': hb, 'hosts': hosts, 'outs': outs, 'step_ms': step_ms, 'launches': launches,
+               'clocks': clocks, 'cap': cap}
+        if e2e:
+            for _ in range(max(1, warmup - 2)):
+                dec.inference_batch(scn, mps, scene_ids=ids)
+            barrier()
+            ts = []
+            for _ in range(steps):
+                flush.fill_(1)
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                res['outs'] = dec.inference_batch(scn, mps, scene_ids=ids)
+                ts.append(time.perf_counter() - t0)
+            barrier()
+            res['e2e_s'] = ts
+            res['h2d'], res['d2h'] = dec._batch.h2d_bytes(), dec._batch.d2h_bytes()
+        return res
+
+    m = measure(cfg, scenes, maps, my_ids, args.steps, args.warmup, sampler_rank0=True)
+    dec = m['dec']
+    agent_steps = sum(h.n_rows for h in m['hosts']) * steps_per_agent
+    total_ms = torch.tensor([sum(m['step_ms'])], dtype=torch.float64, device=dev)
+    e2e_total = torch.tensor([sum(m['e2e_s'])], dtype=torch.float64, device=dev)
+    n_agent_steps = torch.tensor([float(agent_steps)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
-    value = agent_steps * world * args.steps / (total_ms * 1e-3)
-
-    # ---- e2e: the public call with host tensors, wall clock -----------------------------------------------------
-    dec.set_stream(None)
-    for _ in range(3):
-        dec.inference_batch(scenes, maps)
-    barrier()
-    e2e_t = []
-    for _ in range(args.steps):
-        flush.fill_(1)
-        torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
-        outs = dec.inference_batch(scenes, maps)
-        e2e_t.append(time.perf_counter() - t0)
-    barrier()
-    e2e_total = torch.tensor([sum(e2e_t)], dtype=torch.float64, device=dev)
-    if world > 1:
         dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
-    e2e_value = agent_steps * world * args.steps / float(e2e_total.item())
-    h2d, d2h = dec._batch.h2d_bytes(), dec._batch.d2h_bytes()
+        dist.all_reduce(n_agent_steps, op=dist.ReduceOp.SUM)
+    total_ms, e2e_total_s, all_agent_steps = float(total_ms.item()), float(e2e_total.item()), float(n_agent_steps.item())
+    value = all_agent_steps * args.steps / (total_ms * 1e-3)
+    e2e_value = all_agent_steps * args.steps / e2e_total_s
 
-    # ---- final metric gather (the only collective of the path) ---------------------------------------------------
-    summary = torch.tensor([float(np.mean([(o['pred_traj'][:, -1] - o['pred_traj'][:, 11]).norm(dim=-1).mean()
-                                           for o in outs]))], device=dev)
-    if world > 1:
-        gathered = [torch.zeros_like(summary) for _ in range(world)]
-        dist.all_gather(gathered, summary)
-        summary_all = [float(g.item()) for g in gathered]
-    else:
-        summary_all = [float(summary.item())]
+    # ---- final metric gather: one row per scene of the GLOBAL list (the only collective of the path) ------------------
+    nh = cfg.num_historical_steps
+    local = torch.tensor([[float((o['pred_traj'][:N_AGENTS, -1] - o['pred_traj'][:N_AGENTS, nh]).norm(dim=-1).mean()),
+                           float(o['pos_a'].shape[0]), float(o['pos_a'].shape[0] - h.n_rows)]
+                          for o, h in zip(m['outs'], m['hosts'])], device=dev)
+    full = gather_scene_metrics(my_ids, local, n_total)
+    gathered = {'scenes': n_total, 'mean_displacement_m': float(full[:, 0].mean()), 'rows_final_mean': float(full[:, 1].mean()),
+                'rows_final_max': int(full[:, 1].max()), 'inserted_agents_total': int(full[:, 2].sum()),
+                'collective': 'all_gather (NCCL)' if world > 1 else 'none (1 rank)'}
 
     # ---- roofline: profiled replay (events around every launch; no graph) ------------------------------------------
-    def kernel_profile(hb_, hosts_, n_prof=3):
-        """Per-kernel-class CUDA-event timing of profiled rollouts + the algorithmic work of each class per launch."""
-        pk = peaks()
-        dec.set_profile(True)
-        dec.load(hb_, hosts_)
-        dec.prefill()
-        S = hb_.S
-        e_t = e_m = e_a = 0
-        for rep in range(n_prof):
-            if rep:
-                dec.load(hb_, hosts_)
-                dec.prefill()
-            for it in range(S):
-                dec.step(1)
-                if rep == 0:
-                    e_t += int(dec.debug_read('t_cnt', (hb_.R,), np.int32).sum())
-                    e_m += int(dec.debug_read('m_cnt', (hb_.R,), np.int32).sum())
-                    e_a += int(dec.debug_read('a_cnt', (hb_.R,), np.int32).sum())
-        prof = dec.profile()
-        dec.set_profile(False)
-        rows = sum(h.n_rows for h in hosts_)
-        iters = S
-        # algorithmic work per launch, averaged over the iterations of a rollout (fp32; DESIGN.md "roofline accounting")
-        # k_layer (layer.cuh): whole AttentionLayers per launch (all 18 of an iteration when the grid is co-resident).
-        # Algorithmic bytes: per edge K row + V row + rhat row + source index (SURVEY 8d: 1,540 B); per row and layer the
-        # residual in/out and the q/s/qr/kv hand-over; the layer weights once per launch.  Algorithmic flops: folded
-        # formulation, 2*MAC.
-        per_edge = 512 + 512 + 512 + 4
-        post_mac, pre_mac, pre_kv_mac = 196608, 49152, 32768     # Wvr+gate+out+ffn | q,s,Wkr fold | k,v
-        w_layer = 1.125e6 + 0.17e6                                # post + pre chunks of one layer (fp32 bytes)
-        edge_flops = 2.0 * 2 * (128 + 16) * 8                     # score + weighted sum, 8 heads
-        et, em, ea = e_t / iters, e_m / iters, e_a / iters
-        tm_bytes = rows * (1024 + 5120 + 1024 + 1024) + (et + em) * per_edge + 2 * w_layer
-        a_bytes = rows * (1024 + 5120 + 5120 + 1024) + ea * per_edge + w_layer
-        tm_flops = rows * 2.0 * (2 * post_mac + 2 * pre_mac + pre_kv_mac) + (et + em) * edge_flops
-        a_flops = rows * 2.0 * (post_mac + pre_mac + pre_kv_mac) + ea * edge_flops
-        # the fused stack keeps x/q/s/qr on chip: per row only x in/out, 6 temporal ring rows and 6 agent K|V rows leave
-        st_bytes = rows * (1024 + 12 * 1024) + 6 * (et + em + ea) * per_edge + 18 * w_layer
-        st_flops = 6 * (tm_flops + a_flops)
-        # row-tile path (node.cuh), 18 launches of each per iteration, averaged over the three layer types:
-        #   k_attn: per edge K row + V row + rhat row + source index; per row q, qr in and agg, ragg, sal out
-        #   k_node: the dense half; weights (1 MB node-packed) once per launch, per row x in/out and the hand-over buffers
-        attn_bytes = (et + em + ea) / 3.0 * per_edge + rows * (512 + 4096 + 512 + 4096 + 32)
-        attn_flops = (et + em + ea) / 3.0 * edge_flops
-        node_flops = rows * 2.0 * (post_mac + pre_mac + pre_kv_mac * 2.0 / 3.0)
-        node_bytes = 1.05e6 + rows * (1024 + 512 + 4096 + 32 + 512 + 512 + 512 + 4096 + 1024 * 2.0 / 3.0)
-        model = {
-            'k_layer:stack18': ('hbm', st_bytes, st_flops),
-            'k_layer:temporal+map': ('hbm', tm_bytes, tm_flops),
-            'k_layer:agent': ('hbm', a_bytes, a_flops),
-            'k_attn': ('hbm', attn_bytes, attn_flops),
-            'k_node': ('tensor', node_flops, node_bytes),
-            'k_fourier:edges': ('tensor', (et * (4 * (132 * 128 + 128 * 128) + 128 * 128) +
-                                           (em + ea) * (3 * (132 * 128 + 128 * 128) + 128 * 128)) * 2.0),
-            'k_embed_column': ('tensor', rows * 2.0 * (2 * (132 * 128 + 128 * 128) + 128 * 128 + 512 * 128 + 2 * 128 * 128)),
-            'k_heads': ('tensor', rows * 2.0 * (2 * 128 * 128 + 128 * 2048 + 128 * 128)),
-        }
-        pipes = {'k_fourier:edges': 'tcgen05.mma kind::tf32, 3xTF32 split (3 tensor-core passes per algorithmic flop), fp32 '
-                                    'accumulate in TMEM'}
-        klist_ = []
-        tot = sum(v['ms'] for v in prof.values())
-        for name, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms']):
-            avg_us = v['ms'] * 1e3 / v['launches']
-            ent = {'kernel': name, 'share': v['ms'] / tot, 'avg_us': avg_us, 'launches_per_rollout': v['launches'] // n_prof}
-            if name in model:
-                bound, work = model[name][0], model[name][1]
-                if bound == 'hbm':
-                    ach = work / (avg_us * 1e-6) / 1e9
-                    ent.update({'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
-                                'frac': ach / pk['hbm_gbs'], 'algorithmic_bytes_per_launch': work})
-                    if len(model[name]) > 2:
-                        fl = model[name][2] / (avg_us * 1e-6) / 1e12
-                        ent.update({'algorithmic_flops_per_launch': model[name][2], 'fp32_tflops': fl,
-                                    'frac_of_fp32_ffma_peak': fl / 72.0})
-                else:
-                    ach = work / (avg_us * 1e-6) / 1e12
-                    ent.update({'bound': 'tensor', 'achieved': ach, 'peak': pk['bf16_tflops_sustained'],
-                                'unit': 'TFLOP/s', 'frac': ach / pk['bf16_tflops_sustained'],
-                                'algorithmic_flops_per_launch': work,
-                                'pipe': pipes.get(name, 'fp32 FFMA (reference numerics are fp32)'),
-                                'frac_of_fp32_ffma_peak': ach / 72.0})
-                    if len(model[name]) > 2:
-                        ent['algorithmic_bytes_per_launch'] = model[name][2]
-            klist_.append(ent)
-        return klist_, pk
-
-    roof, klist = None, []
+    roof, klist, wl_stats = None, [], None
     if rank == 0:
-        klist, pk = kernel_profile(hb, hosts)
+        klist, pk, wl_stats = kernel_profile(dec, m['hb'], m['hosts'], n_prof=2 if w['n_rec'] <= 0 else 1)
         top = next((k for k in klist if 'bound' in k), None)
-        traffic = None
-        tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
-        if top and os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(top['kernel'])
-            if isinstance(traffic, dict):
-                traffic = traffic.get('agent')
         if top:
             roof = {'kernel': top['kernel'], 'bound': top['bound'], 'achieved': top['achieved'], 'peak': top['peak'],
-                    'unit': top['unit'], 'frac': top['frac'], 'traffic': traffic, 'peak_source': pk['source'],
-                    'share_of_step': top['share'], 'avg_launch_us': top['avg_us'],
-                    'note': ('one 64-agent scene is latency-bound (108 dependent exchange phases per launch on 64 SMs, '
-                             'DESIGN.md section 8); the bandwidth-bound form of the same attention is k_attn in '
-                             'batch32.roofline_kernels') if top['kernel'].startswith('k_layer') else None}
+                    'unit': top['unit'], 'frac': top['frac'], 'traffic': ncu_traffic(top['kernel']),
+                    'peak_source': pk['source'], 'share_of_step': top['share'], 'avg_launch_us': top['avg_us'],
+                    'note': ('one 64-agent scene is latency-bound end to end (dependent exchange phases on 64 SMs, DESIGN.md); '
+                             'the bandwidth-bound form of the same attention is k_attn in configs2.roofline_kernels')
+                    if top['kernel'].startswith('k_layer') else None}
+    dec.close()
 
-    # ---- optional side measurement: 32 scenes per step (configs[2] shape) -----------------------------------------
-    extra = None
-    if rank == 0 and world == 1 and args.scenes == 1 and not args.no_extra:
-        try:
-            sc32 = [scenes[0]] + make_workload(7, 31, cfg)
-            h32 = [prepare_scene(s, s['map_enc'], cfg) for s in sc32]
-            hb32 = HostBatch(h32, cfg)
-            dec.set_stream(stream.cuda_stream)
-            with torch.cuda.stream(stream):
-                db32 = DeviceBatch(hb32, dev)
-                for _ in range(3):
-                    dec.load(db32, h32); dec.rollout(); dec.read()
-                torch.cuda.synchronize(dev)
-                ms = []
-                for _ in range(5):
-                    flush.fill_(1)
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record(stream)
-                    dec.load(db32, h32); dec.rollout(); dec.read()
-                    e1.record(stream)
-                    torch.cuda.synchronize(dev)
-                    ms.append(e0.elapsed_time(e1))
-            dec.set_stream(None)
-            k32, _ = kernel_profile(hb32, h32, n_prof=2)
-            extra = {'workload': '32 scenes x 64 agents x 91 steps per step (configs[2] shape), inputs in HBM; the '
-                                 'AttentionLayers run on the row-tile path (k_attn + k_node)',
-                     'ms_per_step': statistics.mean(ms),
-                     'value': 32 * N_AGENTS * N_STEPS / (statistics.mean(ms) * 1e-3), 'unit': UNIT,
-                     'roofline_kernels': k32}
-        except Exception as ex:      # the headline line must still be printed
-            extra = {'error': repr(ex)[:200]}
+    # ---- side measurements (rank 0, single GPU, default configuration only) -----------------------------------------
+    extra = {}
+    if rank == 0 and world == 1 and w['id'] == 1 and not args.no_extra:
+        def side(name, fn):
+            try:
+                extra[name] = fn()
+            except Exception as ex:          # the headline line must still be printed
+                extra[name] = {'error': repr(ex)[:300]}
 
-    # ---- optional side measurement: the same scene with the insertion stage live (agent_decoder.py:1744-2114) -----------
-    ins_extra = None
-    if rank == 0 and world == 1 and args.scenes == 1 and not args.no_extra:
-        try:
-            ins_extra = {}
-            for label, force in (('query_only', False), ('one_insert_per_iteration', True)):
-                icfg = DecoderConfig(motion_beam_size=5, insert_beam_size=1, disable_insertion=False,
-                                     debug_force_enter=force)
-                idec = B200AgentDecoder(sd, icfg, device=local_rank, seed=2024, use_cuda_graph=True)
-                for _ in range(3):
-                    out_i = idec.inference_batch(scenes[:1], maps[:1])
-                torch.cuda.synchronize(dev)
-                ts = []
-                for _ in range(5):
-                    t0 = time.perf_counter()
-                    out_i = idec.inference_batch(scenes[:1], maps[:1])
-                    ts.append(time.perf_counter() - t0)
-                idec.close()
-                rows_final = int(out_i[0]['pos_a'].shape[0])
-                ins_extra[label] = {'ms_per_rollout_e2e': statistics.mean(ts) * 1e3, 'rows_final': rows_final,
-                                    'value': N_AGENTS * N_STEPS / statistics.mean(ts), 'unit': UNIT}
-            ins_extra['workload'] = ('configs[1] scene with the insertion stage enabled (random-init weights never insert: '
-                                     'one seed query per iteration; debug_force_enter: one agent inserted per iteration), '
-                                     'public call with host tensors')
-        except Exception as ex:
-            ins_extra = {'error': repr(ex)[:200]}
+        def motion_only():
+            mo = measure(decoder_config(w, motion_only=True), scenes, maps, my_ids, max(5, args.steps // 2), 3)
+            mo['dec'].close()
+            a = sum(h.n_rows for h in mo['hosts']) * steps_per_agent
+            return {'workload': 'configs[1] scene with the insertion stage disabled (round-1 headline mode; the reference '
+                                'cannot run this mode through InfGen, infgen/model/infgen.py:75-76)',
+                    'value': a / (statistics.mean(mo['step_ms']) * 1e-3), 'ms_per_step': statistics.mean(mo['step_ms']),
+                    'e2e_value': a / statistics.mean(mo['e2e_s']), 'e2e_ms_per_step': statistics.mean(mo['e2e_s']) * 1e3,
+                    'unit': UNIT}
 
-    # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------------------------
+        def batch(cid, n_steps):
+            wc = dict(CONFIGS[cid]); wc['id'] = cid
+            ccfg = decoder_config(wc)
+            ids = list(range(wc['scenes_per_gpu']))
+            scn = make_scenes(ids, ccfg)
+            mps = [s['map_enc'] for s in scn]
+            mb = measure(ccfg, scn, mps, ids, n_steps, 3)
+            spa = NH + (wc['n_rec'] if wc['n_rec'] > 0 else N_STEPS - NH)
+            a = sum(h.n_rows for h in mb['hosts']) * spa
+            kl, _, st = kernel_profile(mb['dec'], mb['hb'], mb['hosts'], n_prof=1)
+            mb['dec'].close()
+            rows_final = [int(o['pos_a'].shape[0]) for o in mb['outs']]
+            return {'workload': f"{wc['name']} on one GPU: {wc['text']}; inputs in HBM for `value`, public call for `e2e_value`",
+                    'value': a / (statistics.mean(mb['step_ms']) * 1e-3), 'ms_per_step': statistics.mean(mb['step_ms']),
+                    'e2e_value': a / statistics.mean(mb['e2e_s']), 'e2e_ms_per_step': statistics.mean(mb['e2e_s']) * 1e3,
+                    'unit': UNIT, 'row_capacity': mb['cap'], 'rows_final_mean': statistics.mean(rows_final),
+                    'rows_final_max': max(rows_final), 'launches_per_step': mb['launches'] / n_steps,
+                    'workload_stats': st, 'roofline_kernels': kl}
+
+        side('motion_only', motion_only)
+        side('configs2', lambda: batch(2, 5))
+        side('configs4_one_gpu', lambda: batch(4, 2))
+
+    # ---- CPU baseline (rank 0, N=1 only): the reference's own implementation, bounded sample -----------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        dt, it, S = cpu_rollout_timing(scenes[0], sd, cfg, None)
-        dt2, _, _ = cpu_rollout_timing(scenes[0], sd, cfg, None)
-        dt = min(dt, dt2)
-        cpu = {'value': N_AGENTS * N_STEPS / dt, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
-               'sample': f'one full 64-agent 91-step rollout ({S} iterations), best of 2, {dt:.2f} s'}
+        try:
+            ref = CpuReference(sd, cfg)
+            S = (steps_per_agent - NH) // 5
+            total, iters = cpu_measure(ref, scenes[:1], S, 2, 0, 24.0)
+            cpu = {'value': N_AGENTS * steps_per_agent * iters / S * 2 / total, 'unit': UNIT, 'cores': ref.cores,
+                   'kind': ref.kind, 'sample': f'{iters} of {S} decode iterations of the first scene, 2 repetitions, '
+                   f'{total:.1f} s, pro-rated to whole rollouts', 'impl_detail': ref.detail}
+        except Exception as ex:
+            cpu = {'error': repr(ex)[:300]}
 
     if rank == 0:
+        rows_final = [int(o['pos_a'].shape[0]) for o in m['outs']]
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': max(3, args.warmup), 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': (('configs[1]: 1 scene/GPU' if args.scenes == 1 else
-                                     f'configs[2]/[3] shape: {args.scenes} scenes/GPU') +
-                                    ' x 64 agents x 91 steps (16 decode iterations), top-5 sampling, 2048 map '
-                                    'tokens/scene, random-init weights'),
-                       'parallelism': f'scenes sharded 1 rollout stream per GPU x {world}', 'l2': 'flushed between '
-                       'steps (256 MiB write)', 'timed_region': 'load_scenes (device copies + map K/V cache) + prefill '
-                       '+ 16 iterations (CUDA graph) + result copies'},
-            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'ms_per_step': float(e2e_total.item()) / args.steps * 1e3,
-                    'call': 'B200AgentDecoder.inference_batch(data, map_enc) incl. host setup and output dict'},
-            'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'roofline_kernels': klist,
-            'cpu_baseline': cpu, 'final_gather': summary_all,
+            'config': config_block(w, world),
+            'impl_detail': {'parallelism': f'scenes sharded round-robin over {world} rank(s), one rollout stream per GPU, no '
+                            'data-path collective', 'l2': 'flushed between steps (256 MiB write)',
+                            'timed_region': 'infgen_load_scenes (device copies, map K/V caches) + prefill + S iterations '
+                            '(one CUDA graph per iteration: insertion stage with WHILE / IF conditional nodes + motion '
+                            'stage) + result copies', 'row_capacity': m['cap'],
+                            'rows_final_rank0': rows_final[:8], 'agent_steps_counted': 'agents of the scenes at the current '
+                            'step x raw steps (agents appended by the insertion stage are extra work, not counted)'},
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': m['h2d'], 'd2h_bytes_per_step': m['d2h'],
+                    'ms_per_step': e2e_total_s / args.steps * 1e3,
+                    'call': 'B200AgentDecoder.inference_batch(data, map_enc) incl. host setup and output dicts'},
+            'gpu_launches': int(m['launches']), 'clocks': m['clocks'], 'roofline': roof, 'roofline_kernels': klist,
+            'workload_stats': wl_stats, 'cpu_baseline': cpu, 'final_gather': gathered,
         }
-        if extra:
-            line['batch32'] = extra
-        if ins_extra:
-            line['insertion'] = ins_extra
+        if world > 1:
+            line['weak_scaling_base'] = ('per-GPU work is fixed at %d scenes; the same workload on one GPU is the `configs2` block '
+                                         'of the --gpus 1 line (or `--gpus 1 --config 3`)' % w['scenes_per_gpu'])
+        line.update(extra)
         print(json.dumps(line), flush=True)
-    dec.close()
     if world > 1:
         dist.destroy_process_group()
 

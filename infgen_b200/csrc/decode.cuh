@@ -402,15 +402,20 @@ __global__ void __launch_bounds__(NT_S) k_embed_column(const ColEmbArgs a) {
     float *sraw = sA + EM * HLD;             // [EM][4]
     __shared__ EmbedIn s_in[EM];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int row0 = blockIdx.x * EM;
+    __shared__ int s_row[EM];                // global row of every tile position, -1 = inactive
+    if (tid < EM) {
+        const int r = a.rows.tile_row(blockIdx.x, tid, EM);
+        s_row[tid] = a.rows.active_row(r) ? r : -1;
+    }
+    __syncthreads();
     bool any = false;
-    for (int m = 0; m < EM; ++m) any |= a.rows.active(row0 + m);
+    for (int m = 0; m < EM; ++m) any |= s_row[m] >= 0;
     if (!any) return;
     if (tid < EM) {                          // inputs of the embedding (also kept in global memory for the debug tools)
-        const int r = row0 + tid;
+        const int r = s_row[tid];
         EmbedIn in;
         in.xa0 = 0.f; in.xa1 = 0.f; in.tok_row = 0; in.state_idx = 0; in.grid_row = 0; in.cat_idx = 0;
-        if (a.rows.active(r)) {
+        if (r >= 0) {
             in = embed_inputs_row(a.s, r, *a.s.col + a.col_add);
             a.s.xa_raw[(size_t)r * 2] = in.xa0; a.s.xa_raw[(size_t)r * 2 + 1] = in.xa1;
             a.s.tok_row[r] = in.tok_row; a.s.state_idx[r] = in.state_idx; a.s.grid_row[r] = in.grid_row;
@@ -432,9 +437,8 @@ __global__ void __launch_bounds__(NT_S) k_embed_column(const ColEmbArgs a) {
     WsCons ws(wsm);
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int m = warp; m < EM; m += NWARP) {
-        const int r = row0 + m;
         float4 c = z4, t = z4, s = z4, g = z4;
-        if (a.rows.active(r)) {
+        if (s_row[m] >= 0) {
             c = ld4(a.cat_tab + (size_t)s_in[m].cat_idx * 128 + 4 * lane);
             t = ld4(a.tok_tab + (size_t)s_in[m].tok_row * 128 + 4 * lane);
             s = ld4(a.state_tab + (size_t)s_in[m].state_idx * 128 + 4 * lane);
@@ -449,8 +453,8 @@ __global__ void __launch_bounds__(NT_S) k_embed_column(const ColEmbArgs a) {
     for (int m = warp; m < EM; m += NWARP) st4(sX + m * XLD + 128 + 4 * lane, ld4(sH + m * HLD + 4 * lane));
     csync();
     mlp3_body<EM>(ws, a.fusion, sX, XLD, 128, sH, sA, [&](int m, int n, float v) {
-        const int r = row0 + m;
-        if (a.rows.active(r)) a.out[(size_t)r * 128 + n] = v;
+        const int r = s_row[m];
+        if (r >= 0) a.out[(size_t)r * 128 + n] = v;
     });
 }
 

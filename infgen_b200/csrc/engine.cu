@@ -377,10 +377,13 @@ static inline void count_launch(infgen_engine *e) { if (!e->capturing) e->launch
 
 // per-kernel-class device timing (bench.py roofline leg): event pairs around every launch, plain launches only
 enum KClass { KC_EDGE_BUILD, KC_FOURIER, KC_EMBED, KC_LAYER_STACK, KC_LAYER_TM, KC_LAYER_A, KC_HEADS, KC_ADVANCE, KC_INSERT,
-              KC_MISC, KC_ATTN, KC_NODE, KC_COUNT };
+              KC_MISC, KC_ATTN, KC_NODE, KC_INS_LAYER_AGENTS, KC_INS_LAYER_QUERY, KC_INS_LAYER_NEW, KC_INS_FOURIER,
+              KC_INS_HEADS, KC_COUNT };
 static const char *KCLASS_NAME[KC_COUNT] = {"k_edge_build", "k_fourier:edges", "k_embed_column", "k_layer:stack18",
                                             "k_layer:temporal+map", "k_layer:agent", "k_heads", "k_advance",
-                                            "insertion stage", "misc", "k_attn", "k_node"};
+                                            "insertion:small kernels", "misc", "k_attn", "k_node",
+                                            "insertion:k_layer agents (edge-less K|V)", "insertion:k_layer seed query",
+                                            "insertion:k_layer new rows", "insertion:k_fourier", "insertion:k_mlp_layer heads"};
 struct ProfScope {
     infgen_engine *e;
     bool on;
@@ -401,13 +404,15 @@ struct ProfScope {
 // B200: at most 15 clusters of 8 CTAs with ~211 KB of shared memory are co-resident (cudaOccupancyMaxActiveClusters,
 // tools/probe/cluster_occ.cu); a 16th cluster costs a whole second wave
 static const int MAX_CLUSTERS = 15;
+// tiles of M rows a kernel launches for a row space (one per scene for per-scene row spaces)
+static int row_tiles(const RowSpace &r, int M) { return r.list ? (r.list_cap + M - 1) / M : (r.n_total + M - 1) / M; }
 static int launch_layer(infgen_engine *e, const LayerArgs &a_in, int cls) {
     LayerArgs a = a_in;
     if (e->bufs.count("tstamp") && e->bufs["tstamp"].p)
         a.tstamp = (long long *)e->bufs["tstamp"].p + (cls == KC_LAYER_A ? 256 : 0);
     ProfScope ps(e, cls);
     const int M = e->row_tile;
-    const int clusters = (a.rows.n_total + M - 1) / M;
+    const int clusters = row_tiles(a.rows, M);
     if (clusters == 0) return 0;
     if (M == 8) k_layer<8><<<clusters * CL, NT, LayerSmem<8>::BYTES, e->stream>>>(a);
     else k_layer<4><<<clusters * CL, NT, LayerSmem<4>::BYTES, e->stream>>>(a);
@@ -464,7 +469,7 @@ static int launch_fourier(infgen_engine *e, const FourierArgs *jobs, int n_jobs,
     return 0;
 }
 static int launch_mlp_embed(infgen_engine *e, const MlpEmbArgs &a, int cls = KC_MISC) {
-    int grid = (a.rows.n_total + EM - 1) / EM;
+    int grid = row_tiles(a.rows, EM);
     if (grid == 0) return 0;
     ProfScope ps(e, cls);
     k_mlp_embed<<<grid, NT_S, mlp_embed_smem(a.k4), e->stream>>>(a);
@@ -475,12 +480,20 @@ static int launch_mlp_embed(infgen_engine *e, const MlpEmbArgs &a, int cls = KC_
 
 static RowSpace scene_rows(infgen_engine *e) {
     RowSpace r;
-    r.n_total = e->R; r.cap = e->cap; r.n_rows = e->st.n_rows; r.row_lo = nullptr;
+    memset(&r, 0, sizeof(r));
+    r.n_total = e->R; r.cap = e->cap; r.n_rows = e->st.n_rows;
     return r;
 }
 static RowSpace flat_rows(int n) {
     RowSpace r;
-    r.n_total = n; r.cap = 0; r.n_rows = nullptr; r.row_lo = nullptr;
+    memset(&r, 0, sizeof(r));
+    r.n_total = n;
+    return r;
+}
+// the rows the last insertion pass appended (at most one per scene), as a compact row list written by k_seed_decide
+static RowSpace new_rows(infgen_engine *e) {
+    RowSpace r = scene_rows(e);
+    r.list = e->ins.new_list; r.n_list = e->ins.n_new_list; r.list_cap = e->n_scenes;
     return r;
 }
 
@@ -505,12 +518,12 @@ static int enqueue_embed_rows(infgen_engine *e, const int *row_lo) {
     DecState &s = e->st;
     ColEmbArgs ca;
     memset(&ca, 0, sizeof(ca));
-    ca.rows = scene_rows(e); ca.rows.row_lo = row_lo; ca.fx = e->f_x; ca.fusion = e->e_fusion;
+    ca.rows = new_rows(e); ca.fx = e->f_x; ca.fusion = e->e_fusion;
     ca.s = s; ca.col_add = 0; ca.cat_tab = fbuf(e, "cat_tab");
     ca.tok_tab = e->tok_tab; ca.state_tab = e->state_emb; ca.grid_tab = e->grid_tab; ca.out = fbuf(e, "x");
     {
         ProfScope ps(e, KC_INSERT);
-        k_embed_column<<<(e->R + EM - 1) / EM, NT_S, COLEMB_SMEM, e->stream>>>(ca);
+        k_embed_column<<<row_tiles(ca.rows, EM), NT_S, COLEMB_SMEM, e->stream>>>(ca);
     }
     CKL(); count_launch(e);
     return 0;
@@ -661,10 +674,12 @@ static int enqueue_layers(infgen_engine *e, bool with_edges, int trace_iter) {
 // IF node inside its body whose condition values k_ins_begin / k_seed_decide set on the device (no host round trip).
 // ---------------------------------------------------------------------------------------------------------------
 // every active row >= row_lo through a stack of layers WITHOUT edges, keeping the K|V rows of the non-bipartite ones
-static int enqueue_edgeless(infgen_engine *e, const int *row_lo, float *x, bool seed_stack) {
+static int enqueue_edgeless(infgen_engine *e, const int *row_lo, float *x, bool seed_stack, bool new_only = false) {
     LayerArgs la;
     memset(&la, 0, sizeof(la));
-    la.rows = scene_rows(e); la.rows.row_lo = row_lo; la.x = x; la.ring = RING; la.col_ptr = e->st.col;
+    la.rows = new_only ? new_rows(e) : scene_rows(e);
+    if (!new_only) la.rows.row_lo = row_lo;
+    la.x = x; la.ring = RING; la.col_ptr = e->st.col;
     const size_t kvl = (size_t)e->R * 256;
     int n = 0;
     if (seed_stack) {                                   // 3 x {occ2sa, pt2sa, a2sa}: K|V of the a2sa layers
@@ -691,9 +706,31 @@ static int enqueue_edgeless(infgen_engine *e, const int *row_lo, float *x, bool 
         }
     }
     la.n_sub = n;
-    return launch_layer(e, la, KC_INSERT);
+    return launch_layer(e, la, KC_INS_LAYER_AGENTS);
 }
 static int enqueue_embed_rows(infgen_engine *e, const int *row_lo);
+
+// Run `fn` on the side stream, concurrently with what the caller enqueues on the engine stream until side_join().  Works
+// the same inside a stream capture (parallel branches of the graph) and outside; profiled runs stay serial (the per-class
+// events are recorded on the engine stream).
+template <typename Fn>
+static int side_fork(infgen_engine *e, Fn fn) {
+    if (e->profile) return fn();
+    cudaStream_t main = e->stream;
+    CK(cudaEventRecord(e->ev_fork, main));
+    CK(cudaStreamWaitEvent(e->side_stream, e->ev_fork, 0));
+    e->stream = e->side_stream;
+    const int rc = fn();
+    e->stream = main;
+    RET(rc);
+    CK(cudaEventRecord(e->ev_join, e->side_stream));
+    return 0;
+}
+static int side_join(infgen_engine *e) {
+    if (e->profile) return 0;
+    CK(cudaStreamWaitEvent(e->stream, e->ev_join, 0));
+    return 0;
+}
 
 static int enqueue_insertion_begin(infgen_engine *e) {
     DecState &s = e->st;
@@ -706,15 +743,24 @@ static int enqueue_insertion_begin(infgen_engine *e) {
     }
     CKL(); count_launch(e);
     // agents through the seed stack without edges -> K|V of the a2sa layers
-    k_copy_new_rows<<<R, 128, 0, st>>>(s, nullptr, fbuf(e, "x"), fbuf(e, "x_sa"));
+    {
+        ProfScope ps(e, KC_INSERT);
+        k_copy_new_rows<<<R, 128, 0, st>>>(s, nullptr, fbuf(e, "x"), fbuf(e, "x_sa"));
+    }
     CKL(); count_launch(e);
+    // relative embeddings of the map -> seed and agent -> seed edges (the seed pose is the ego pose for every pass of the
+    // iteration; rows appended by a pass add their own edge), concurrently with the agents' edge-less stack
+    RET(side_fork(e, [&]() -> int {
+        FourierArgs fj[2];
+        memset(fj, 0, sizeof(fj));
+        fj[0].normalize = 1; fj[0].dim = 3; fj[0].n_slots = ns * SEED_MAP_MAX; fj[0].cnt = q.ps_cnt; fj[0].stride = SEED_MAP_MAX;
+        fj[0].raw = q.ps_raw; fj[0].w = e->f_ps; fj[0].out = fbuf(e, "rhat_ps");
+        fj[1].normalize = 1; fj[1].dim = 3; fj[1].n_slots = ns * q.as_stride; fj[1].cnt = q.as_cnt; fj[1].stride = q.as_stride;
+        fj[1].raw = q.as_raw; fj[1].w = e->f_as; fj[1].out = fbuf(e, "rhat_as");
+        return launch_fourier(e, fj, 2, KC_INS_FOURIER);
+    }));
     RET(enqueue_edgeless(e, nullptr, fbuf(e, "x_sa"), true));
-    // relative embeddings of the map -> seed edges (the seed pose is the ego pose for every pass of the iteration)
-    FourierArgs fj;
-    memset(&fj, 0, sizeof(fj));
-    fj.normalize = 1; fj.dim = 3; fj.n_slots = ns * SEED_MAP_MAX; fj.cnt = q.ps_cnt; fj.stride = SEED_MAP_MAX;
-    fj.raw = q.ps_raw; fj.w = e->f_ps; fj.out = fbuf(e, "rhat_ps");
-    return launch_fourier(e, &fj, 1, KC_INSERT);
+    return side_join(e);
 }
 
 static int enqueue_insertion_pass(infgen_engine *e) {
@@ -731,11 +777,6 @@ static int enqueue_insertion_pass(infgen_engine *e) {
         k_seed_prepare<<<ns, NT, 0, st>>>(pa);
     }
     CKL(); count_launch(e);
-    FourierArgs fj;
-    memset(&fj, 0, sizeof(fj));
-    fj.normalize = 1; fj.dim = 3; fj.n_slots = ns * q.as_stride; fj.cnt = q.as_cnt; fj.stride = q.as_stride;
-    fj.raw = q.as_raw; fj.w = e->f_as; fj.out = fbuf(e, "rhat_as");
-    RET(launch_fourier(e, &fj, 1, KC_INSERT));
     {   // the query rows: 3 x {occ2sa, pt2sa, a2sa} with their edges
         LayerArgs la;
         memset(&la, 0, sizeof(la));
@@ -764,7 +805,7 @@ static int enqueue_insertion_pass(infgen_engine *e) {
         la.n_sub = n;
         const int saved = e->row_tile;
         e->row_tile = 4;
-        int rc = launch_layer(e, la, KC_INSERT);
+        int rc = launch_layer(e, la, KC_INS_LAYER_QUERY);
         e->row_tile = saved;
         RET(rc);
     }
@@ -776,7 +817,7 @@ static int enqueue_insertion_pass(infgen_engine *e) {
         la.w2 = e->h_ag_occ; la.out2 = q.ag_occ_logits;
         la.w3 = e->h_pt_occ; la.out3 = q.pt_occ_logits;
         const int npad = std::max(la.w.n_pad, std::max(la.w2.n_pad, la.w3.n_pad));
-        ProfScope ps(e, KC_INSERT);
+        ProfScope ps(e, KC_INS_HEADS);
         k_mlp_layer<<<dim3((la.n + HM - 1) / HM, npad / 128, 3), NT_S, MLP_LAYER_SMEM, st>>>(la);
         CKL(); count_launch(e);
     }
@@ -800,16 +841,23 @@ static int enqueue_heading_stage(infgen_engine *e) {
     float *x = fbuf(e, "x"), *x_sa = fbuf(e, "x_sa"), *x_ha = fbuf(e, "x_ha");
     // K|V of every row for the heading stack (motion layers 0..2 without edges): all rows on the first heading stage of
     // the iteration (ha_lo = 0), none afterwards (k_new_edges raises ha_lo; appended rows are added at the end)
-    k_copy_new_rows<<<R, 128, 0, st>>>(s, q.ha_lo, x, x_ha);
+    {
+        ProfScope ps(e, KC_INSERT);
+        k_copy_new_rows<<<R, 128, 0, st>>>(s, q.ha_lo, x, x_ha);
+    }
     CKL(); count_launch(e);
-    RET(enqueue_edgeless(e, q.ha_lo, x_ha, false));
+    // (concurrently with the embedding / edges of the new row; k_head_finalize raises ha_lo after the join)
+    RET(side_fork(e, [&]() -> int { return enqueue_edgeless(e, q.ha_lo, x_ha, false); }));
     // categorical embedding row of the new agent: type_a_emb[type] + shape_emb(shape)
     MlpEmbArgs ma;
     memset(&ma, 0, sizeof(ma));
-    ma.rows = scene_rows(e); ma.rows.row_lo = q.row_lo; ma.w = e->e_shape; ma.kin = 3; ma.k4 = 1;
+    ma.rows = new_rows(e); ma.w = e->e_shape; ma.kin = 3; ma.k4 = 1;
     ma.x = q.shape_rows; ma.x_ld = 3; ma.out = fbuf(e, "cat_tab"); ma.out_ld = 128;
     RET(launch_mlp_embed(e, ma, KC_INSERT));
-    k_add_type_emb_rows<<<R, 128, 0, st>>>(s, q.row_lo, fbuf(e, "cat_tab"), e->type_emb);
+    {
+        ProfScope ps(e, KC_INSERT);
+        k_add_type_emb_rows<<<ns, 128, 0, st>>>(s, q.row_lo, fbuf(e, "cat_tab"), e->type_emb);
+    }
     CKL(); count_launch(e);
     RET(enqueue_embed_rows(e, q.row_lo));       // feature of the new row with the dummy heading
     {
@@ -823,11 +871,12 @@ static int enqueue_heading_stage(infgen_engine *e) {
     hj[0].raw = q.hp_raw; hj[0].w = e->f_m; hj[0].out = fbuf(e, "rhat_hp");
     hj[1].normalize = 1; hj[1].dim = 3; hj[1].n_slots = ns * NEW_AGENT_MAX; hj[1].cnt = q.ha_cnt_s; hj[1].stride = NEW_AGENT_MAX;
     hj[1].raw = q.ha_raw; hj[1].w = e->f_a; hj[1].out = fbuf(e, "rhat_ha");
-    RET(launch_fourier(e, hj, 2, KC_INSERT));
+    RET(launch_fourier(e, hj, 2, KC_INS_FOURIER));
+    RET(side_join(e));
     {   // the new rows through 3 x {pt2a, a2a} with their 10 m neighbourhoods
         LayerArgs la;
         memset(&la, 0, sizeof(la));
-        la.rows = scene_rows(e); la.rows.row_lo = q.row_lo; la.x = x; la.ring = RING; la.col_ptr = s.col;
+        la.rows = new_rows(e); la.x = x; la.ring = RING; la.col_ptr = s.col;
         la.pre0 = make_pre(e->m[0], false, nullptr, false, 0, false);
         const size_t kvl = (size_t)R * 256, kvm = (size_t)e->P * 256;
         int n = 0;
@@ -844,7 +893,7 @@ static int enqueue_heading_stage(infgen_engine *e) {
             if (i < 2) g.pre = make_pre(e->m[i + 1], false, nullptr, false, 0, false);
         }
         la.n_sub = n;
-        RET(launch_layer(e, la, KC_INSERT));
+        RET(launch_layer(e, la, KC_INS_LAYER_NEW));
     }
     HeadFinalArgs ha;
     memset(&ha, 0, sizeof(ha));
@@ -856,12 +905,23 @@ static int enqueue_heading_stage(infgen_engine *e) {
     CKL(); count_launch(e);
     RET(enqueue_embed_rows(e, q.row_lo));       // final feature of the new row (:2086-2097)
     // the new rows become sources of later passes: their edge-less K|V rows of both stacks
-    k_copy_new_rows<<<R, 128, 0, st>>>(s, q.row_lo, x, x_sa);
-    k_copy_new_rows<<<R, 128, 0, st>>>(s, q.row_lo, x, x_ha);
-    CKL(); count_launch(e); count_launch(e);
-    RET(enqueue_edgeless(e, q.row_lo, x_sa, true));
-    RET(enqueue_edgeless(e, q.row_lo, x_ha, false));
-    return 0;
+    {
+        ProfScope ps(e, KC_INSERT);
+        k_copy_new_rows2<<<ns, 128, 0, st>>>(s, q.row_lo, x, x_sa, x_ha);
+    }
+    CKL(); count_launch(e);
+    // off the critical path of the next pass (which needs the seed-stack K|V rows first): the heading-stack K|V rows of
+    // the new rows and the relative embedding of their edge towards the query row
+    RET(side_fork(e, [&]() -> int {
+        FourierArgs fj;
+        memset(&fj, 0, sizeof(fj));
+        fj.normalize = 1; fj.dim = 3; fj.n_slots = ns; fj.slot_list = q.as_new_list; fj.n_list = q.as_new_n;
+        fj.raw = q.as_raw; fj.w = e->f_as; fj.out = fbuf(e, "rhat_as");
+        RET(launch_fourier(e, &fj, 1, KC_INS_FOURIER));
+        return enqueue_edgeless(e, q.row_lo, x_ha, false, true);
+    }));
+    RET(enqueue_edgeless(e, q.row_lo, x_sa, true, true));
+    return side_join(e);
 }
 
 // host-driven loop (plain launches)
@@ -1413,6 +1473,9 @@ int32_t infgen_load_scenes(infgen_engine *e, const infgen_scene_batch *b, int32_
         RET(ensure_t(e, "ins_row_lo", ns, &q.row_lo)); RET(ensure_t(e, "ins_flags", 4, &q.flags));
         RET(ensure_t(e, "ins_done_ctr", 4, &q.done_ctr)); RET(ensure_t(e, "ins_ha_lo", ns, &q.ha_lo));
         RET(ensure_t(e, "ins_stat", 4, &q.stat));
+        RET(ensure_t(e, "as_seen", ns, &q.as_seen)); RET(ensure_t(e, "as_new_list", ns + 4, &q.as_new_list));
+        q.as_new_n = q.as_new_list + ns;
+        RET(ensure_t(e, "ins_new_list", ns + 4, &q.new_list)); q.n_new_list = q.new_list + ns;
         q.as_stride = std::min(cap, SEED_AGENT_MAX);
         RET(ensure_t(e, "ps_cnt", ns, &q.ps_cnt)); RET(ensure_t(e, "ps_src", (size_t)ns * SEED_MAP_MAX, &q.ps_src));
         RET(ensure_t(e, "ps_raw", (size_t)ns * SEED_MAP_MAX * 3, &q.ps_raw));

@@ -44,6 +44,9 @@ struct InsState {
     int *ha_lo;                        // [ns] first row the heading-stack K/V pass of this iteration still has to cover:
                                        //      0 until the first heading stage of the iteration ran, then "none"
     int as_stride;                     // agent -> seed slots per scene: min(cap, SEED_AGENT_MAX)
+    int *as_seen;                      // [ns] rows within the seed radius so far (the neighbour limit counts them all)
+    int *as_new_list, *as_new_n;       // slots appended by the last heading stage (their relative embedding is due)
+    int *new_list, *n_new_list;        // global rows appended by the last pass, compact (row-list launches of the heading stage)
     // loop control without the host: condition handles of the CUDA-graph WHILE (another pass) / IF (a row was appended)
     // nodes, set from k_ins_begin / k_seed_decide when the iteration is replayed as a graph (use_cond)
     int use_cond;
@@ -89,6 +92,47 @@ __device__ __forceinline__ void gemv_row(const float *xs, const float *__restric
         out[n] = acc + (bias ? __ldg(bias + n) : 0.f);
     }
 }
+// The per-scene kernels of the insertion stage are single-CTA latency chains: every GEMV below keeps all its weight loads
+// in flight at once (a rolled loop of dependent-looking L2 loads costs one round trip per trip).
+// y[n] = b[n] + sum_{k<128} x[k] W[k][n], n < N <= 128: all NT threads, the two k-halves of an output are added through
+// `red` ([2][128] floats, shared).  Contains two __syncthreads().  `out` may be shared or global.
+__device__ __forceinline__ void gemv128(const float *xs, const float *__restrict__ wp, int ldn,
+                                        const float *__restrict__ bias, int N, float *out, float *red) {
+    const int n = threadIdx.x & 127, kh = threadIdx.x >> 7;
+    float acc = 0.f;
+    if (n < N) {
+        float4 w[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = ldg4(wp + ((size_t)(16 * kh + i) * ldn + n) * 4);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float4 x = ld4(xs + 4 * (16 * kh + i));
+            acc = fmaf(x.x, w[i].x, acc); acc = fmaf(x.y, w[i].y, acc); acc = fmaf(x.z, w[i].z, acc); acc = fmaf(x.w, w[i].w, acc);
+        }
+    }
+    red[kh * 128 + n] = acc;
+    __syncthreads();
+    if (kh == 0 && n < N) out[n] = (red[n] + red[128 + n]) + (bias ? __ldg(bias + n) : 0.f);
+    __syncthreads();
+}
+// y[n] = b[n] + sum_{k<128} x[k] W[k][n], n < 256 = NT: one thread per output, 32 loads in flight
+__device__ __forceinline__ void gemv256(const float *xs, const float *__restrict__ wp, const float *__restrict__ bias,
+                                        float *out) {
+    const int n = threadIdx.x;
+    float acc = 0.f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float4 w[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = ldg4(wp + ((size_t)(16 * h + i) * 256 + n) * 4);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float4 x = ld4(xs + 4 * (16 * h + i));
+            acc = fmaf(x.x, w[i].x, acc); acc = fmaf(x.y, w[i].y, acc); acc = fmaf(x.z, w[i].z, acc); acc = fmaf(x.w, w[i].w, acc);
+        }
+    }
+    out[n] = acc + __ldg(bias + n);
+}
 // in-place LayerNorm (+ReLU) of one 128-vector in shared memory by warp 0
 __device__ __forceinline__ void ln_row(float *s, const float *g, const float *b, bool relu) {
     if (threadIdx.x < 32) {
@@ -99,13 +143,20 @@ __device__ __forceinline__ void ln_row(float *s, const float *g, const float *b,
     }
 }
 // MLPLayer (layers.py:206-215) on one row held in shared memory: out[n_out] (shared or global)
-__device__ __forceinline__ void mlp_head_row(const float *sx, const MlpHeadW &w, float *sh, float *out) {
-    gemv_row(sx, w.w0, 128, 32, w.b0, 128, sh);
-    __syncthreads();
+__device__ __forceinline__ void mlp_head_row(const float *sx, const MlpHeadW &w, float *sh, float *out, float *red) {
+    gemv128(sx, w.w0, 128, w.b0, 128, sh, red);
     ln_row(sh, w.ln_g, w.ln_b, true);
     __syncthreads();
-    gemv_row(sh, w.w3, w.n_pad, 32, w.b3, w.n_out, out);
-    __syncthreads();
+    gemv128(sh, w.w3, w.n_pad, w.b3, w.n_out, out, red);
+}
+
+// agent -> seed edge of row rj (scene b) towards the query row, which sits on the ego pose (px, py, hd): raw features
+__device__ __forceinline__ void seed_edge_write(const DecState &s, const InsState &q, int slot, int rj, int col, float dx,
+                                                float dy, float hd, float hx, float hy) {
+    q.as_src[slot] = rj;
+    q.as_raw[(size_t)slot * 3 + 0] = norm2(dx, dy);
+    q.as_raw[(size_t)slot * 3 + 1] = angle_between(hx, hy, dx, dy);
+    q.as_raw[(size_t)slot * 3 + 2] = wrap_angle(__fsub_rn(s.head[(size_t)rj * s.T + col], hd));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -168,11 +219,35 @@ __global__ void __launch_bounds__(NT) k_ins_begin(const DecState s, const InsSta
         cnt += __popc(mask);
     }
     if (threadIdx.x == 0) q.ps_cnt[b] = min(total, SEED_MAP_MAX);
+    // ---- agent -> seed edges (:1833-1841): rows within the radius of the ego pose (first SEED_AGENT_MAX by index, the
+    //      query row itself being the last index), kept if they interact at column cur.  Built once per iteration; a
+    //      row appended by a pass adds its edge in k_head_finalize (it is the last index) ----
+    if (warp != 0) return;
+    const int n = s.n_rows[b], r0 = b * s.cap;
+    int acnt = 0, seen = 0;
+    for (int j0 = 0; j0 < n; j0 += 32) {
+        const int j = j0 + lane, rj = r0 + j;
+        float dx = 0.f, dy = 0.f;
+        bool within = false;
+        if (j < n) {
+            dx = __fsub_rn(s.pos[((size_t)rj * T + col) * 2], px);
+            dy = __fsub_rn(s.pos[((size_t)rj * T + col) * 2 + 1], py);
+            within = dist2(dx, dy) < q.r_seed2;
+        }
+        const unsigned wm = __ballot_sync(0xffffffffu, within);
+        const bool in_first = within && (seen + __popc(wm & lanemask_lt())) < SEED_AGENT_MAX;
+        const bool ok = in_first && s.interact[(size_t)rj * T + col] != 0;
+        const unsigned mask = __ballot_sync(0xffffffffu, ok);
+        if (ok) seed_edge_write(s, q, b * q.as_stride + acnt + __popc(mask & lanemask_lt()), rj, col, dx, dy, hd, hx, hy);
+        acnt += __popc(mask);
+        seen += __popc(wm);
+    }
+    if (lane == 0) { q.as_cnt[b] = acnt; q.as_seen[b] = seen; }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // per pass: occupancy of the grid at column cur -> seed_agent_occ_embed -> K|V of the three occ2sa layers (:1850-1859);
-// agent -> seed edges (:1833-1841); the query row's input feature.  One CTA per scene.
+// the query row's input feature.  One CTA per scene.
 // ---------------------------------------------------------------------------------------------------------------
 struct SeedPrepArgs {
     DecState s;
@@ -183,7 +258,6 @@ struct SeedPrepArgs {
 __global__ void __launch_bounds__(NT) k_seed_prepare(const SeedPrepArgs a) {
     __shared__ __align__(16) float sh[128];
     __shared__ __align__(16) float se[128];
-    __shared__ __align__(16) float sn[128];
     const DecState &s = a.s;
     const InsState &q = a.q;
     const int b = blockIdx.x, col = *s.col, T = s.T, G = s.G;
@@ -215,61 +289,41 @@ __global__ void __launch_bounds__(NT) k_seed_prepare(const SeedPrepArgs a) {
         if (lane == 0) s_ncell = cnt;
     }
     __syncthreads();
-    if (tid < 128) {
-        float acc = 0.f;
-        for (int k = 0; k < s_ncell; ++k) {
-            const int g = s_cells[k];
-            acc += __ldg(a.occ_embed.w0 + ((size_t)(g >> 2) * 128 + tid) * 4 + (g & 3));
+    __shared__ float s_red2[256];
+    {   // two halves of the block take alternate cells, four loads in flight each
+        const int n = tid & 127, half = tid >> 7, nc = s_ncell;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        const float *w0 = a.occ_embed.w0;
+        int k = half;
+        for (; k + 6 < nc; k += 8) {
+            const int g0 = s_cells[k], g1 = s_cells[k + 2], g2 = s_cells[k + 4], g3 = s_cells[k + 6];
+            a0 += __ldg(w0 + ((size_t)(g0 >> 2) * 128 + n) * 4 + (g0 & 3));
+            a1 += __ldg(w0 + ((size_t)(g1 >> 2) * 128 + n) * 4 + (g1 & 3));
+            a2 += __ldg(w0 + ((size_t)(g2 >> 2) * 128 + n) * 4 + (g2 & 3));
+            a3 += __ldg(w0 + ((size_t)(g3 >> 2) * 128 + n) * 4 + (g3 & 3));
         }
-        sh[tid] = acc + __ldg(a.occ_embed.b0 + tid);
+        for (; k < nc; k += 2) {
+            const int g0 = s_cells[k];
+            a0 += __ldg(w0 + ((size_t)(g0 >> 2) * 128 + n) * 4 + (g0 & 3));
+        }
+        s_red2[tid] = (a0 + a1) + (a2 + a3);
     }
+    __syncthreads();
+    if (tid < 128) sh[tid] = (s_red2[tid] + s_red2[128 + tid]) + __ldg(a.occ_embed.b0 + tid);
     __syncthreads();
     ln_row(sh, a.occ_embed.ln_g, a.occ_embed.ln_b, true);
     __syncthreads();
-    gemv_row(sh, a.occ_embed.w3, a.occ_embed.n_pad, 32, a.occ_embed.b3, 128, se);
-    __syncthreads();
+    gemv128(sh, a.occ_embed.w3, a.occ_embed.n_pad, a.occ_embed.b3, 128, se, s_red2);
     if (tid < 128) q.occ_emb[(size_t)b * 128 + tid] = se[tid];
-    for (int i = 0; i < 3; ++i) {                       // K|V of the occupancy node (layers.py:65-71, 107-108)
-        if (tid < 32) st4(sn + 4 * lane, ln128(ld4(se + 4 * lane), a.occ2sa[i].ln_src_g, a.occ2sa[i].ln_src_b, lane));
-        __syncthreads();
-        gemv_row(sn, a.occ2sa[i].w_kv, 256, 32, a.occ2sa[i].b_kv, 256,
-                 q.kv_occ + ((size_t)i * gridDim.x + b) * 256);
-        __syncthreads();
-    }
+    // K|V of the occupancy node for the three occ2sa layers (layers.py:65-71, 107-108): three LayerNorms by three warps,
+    // then three independent 128 -> 256 GEMVs
+    __shared__ __align__(16) float sn3[3][128];
+    if (warp < 3) st4(sn3[warp] + 4 * lane, ln128(ld4(se + 4 * lane), a.occ2sa[warp].ln_src_g, a.occ2sa[warp].ln_src_b, lane));
+    __syncthreads();
+    for (int i = 0; i < 3; ++i)
+        gemv256(sn3[i], a.occ2sa[i].w_kv, a.occ2sa[i].b_kv, q.kv_occ + ((size_t)i * gridDim.x + b) * 256);
     // ---- query row feature ----
     if (tid < 128) q.x_seed[(size_t)b * SEED_ROW_STRIDE * 128 + tid] = q.seed_feat[tid];
-    // ---- agent -> seed edges: rows within the radius of the ego pose (first SEED_AGENT_MAX by index, the query row
-    //      itself being the last index), kept if they interact at column cur ----
-    if (warp != 0) return;
-    const int re = r0 + s.ego_row[b];
-    const float px = s.pos[((size_t)re * T + col) * 2], py = s.pos[((size_t)re * T + col) * 2 + 1];
-    const float hd = s.head[(size_t)re * T + col];
-    const float hx = cosf(hd), hy = sinf(hd);
-    int cnt = 0, seen = 0;
-    for (int j0 = 0; j0 < n; j0 += 32) {
-        const int j = j0 + lane, rj = r0 + j;
-        float dx = 0.f, dy = 0.f;
-        bool within = false;
-        if (j < n) {
-            dx = __fsub_rn(s.pos[((size_t)rj * T + col) * 2], px);
-            dy = __fsub_rn(s.pos[((size_t)rj * T + col) * 2 + 1], py);
-            within = dist2(dx, dy) < q.r_seed2;
-        }
-        const unsigned wm = __ballot_sync(0xffffffffu, within);
-        const bool in_first = within && (seen + __popc(wm & lanemask_lt())) < SEED_AGENT_MAX;
-        const bool ok = in_first && s.interact[(size_t)rj * T + col] != 0;
-        const unsigned mask = __ballot_sync(0xffffffffu, ok);
-        if (ok) {
-            const int slot = b * q.as_stride + cnt + __popc(mask & lanemask_lt());
-            q.as_src[slot] = rj;
-            q.as_raw[(size_t)slot * 3 + 0] = norm2(dx, dy);
-            q.as_raw[(size_t)slot * 3 + 1] = angle_between(hx, hy, dx, dy);
-            q.as_raw[(size_t)slot * 3 + 2] = wrap_angle(__fsub_rn(s.head[(size_t)rj * T + col], hd));
-        }
-        cnt += __popc(mask);
-        seen += __popc(wm);
-    }
-    if (lane == 0) q.as_cnt[b] = cnt;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -283,61 +337,104 @@ struct SeedDecideArgs {
 };
 __device__ __forceinline__ void seed_decide_scene(const SeedDecideArgs &a) {
     __shared__ __align__(16) float sx[128];
-    __shared__ __align__(16) float sh[128];
+    __shared__ __align__(16) float sh3[3][128];
     __shared__ float s_small[8];                        // state[2] type[3] shape[3]
     __shared__ float s_red[NT];
-    __shared__ int s_redi[NT];
+    __shared__ float s_wv[NWARP][INSERT_LIMIT];
+    __shared__ int s_wi[NWARP][INSERT_LIMIT];
     __shared__ float s_topv[INSERT_LIMIT];
     __shared__ int s_topi[INSERT_LIMIT];
     const DecState &s = a.s;
     const InsState &q = a.q;
     const int b = blockIdx.x, col = *s.col, t = *s.iter, T = s.T, G = s.G, S = s.S;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (!q.active[b]) return;
     if (tid < 128) sx[tid] = q.x_seed[(size_t)b * SEED_ROW_STRIDE * 128 + tid];
     __syncthreads();
-    mlp_head_row(sx, a.h_state, sh, s_small);
-    mlp_head_row(sx, a.h_type, sh, s_small + 2);
-    mlp_head_row(sx, a.h_shape, sh, s_small + 5);
-    // ---- position: softmax over the grid, top-k, draw (:1896-1902) ----
+    // ---- the three small heads (state, type, shape; layers.py:206-215): hidden layers, LayerNorms by three warps, then
+    //      the 2 + 3 + 3 outputs as one 128-dot per warp ----
+    const MlpHeadW *hw[3] = {&a.h_state, &a.h_type, &a.h_shape};
+    for (int i = 0; i < 3; ++i) gemv128(sx, hw[i]->w0, 128, hw[i]->b0, 128, sh3[i], s_red);
+    if (warp < 3) st4(sh3[warp] + 4 * lane, relu4(ln128(ld4(sh3[warp] + 4 * lane), hw[warp]->ln_g, hw[warp]->ln_b, lane)));
+    __syncthreads();
+    {
+        const int hi = warp < 2 ? 0 : (warp < 5 ? 1 : 2), n = warp < 2 ? warp : (warp < 5 ? warp - 2 : warp - 5);
+        const MlpHeadW &w = *hw[hi];
+        const float4 wv = ldg4(w.w3 + ((size_t)lane * w.n_pad + n) * 4), xv = ld4(sh3[hi] + 4 * lane);
+        const float d = warp_sum(fmaf(xv.w, wv.w, fmaf(xv.z, wv.z, fmaf(xv.y, wv.y, xv.x * wv.x))));
+        if (lane == 0) s_small[warp] = d + __ldg(w.b3 + n);
+    }
+    // ---- position: softmax over the grid, top-k, draw (:1896-1902).  Warp w owns a contiguous slice of the cells ----
     const float *lg = q.pos_logits + (size_t)b * SEED_ROW_STRIDE * G;
+    const int per = (G + NWARP - 1) / NWARP, g0 = warp * per, g1 = min(G, g0 + per);
+    constexpr int VPL = 8;                              // cells per lane (G <= 8 * 32 * NWARP)
+    float v[VPL];
     float mxv = -INFINITY;
-    for (int g = tid; g < G; g += NT) mxv = fmaxf(mxv, lg[g]);
-    s_red[tid] = mxv;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+        const int g = g0 + lane + 32 * j;
+        v[j] = g < g1 ? lg[g] : -INFINITY;
+        mxv = fmaxf(mxv, v[j]);
+    }
+    mxv = warp_max(mxv);
+    if (lane == 0) s_red[warp] = mxv;
     __syncthreads();
-    for (int o = NT / 2; o > 0; o >>= 1) { if (tid < o) s_red[tid] = fmaxf(s_red[tid], s_red[tid + o]); __syncthreads(); }
-    const float gmax = s_red[0];
-    __syncthreads();
+    float gmax = s_red[0];
+#pragma unroll
+    for (int w = 1; w < NWARP; ++w) gmax = fmaxf(gmax, s_red[w]);
     float sum = 0.f;
-    for (int g = tid; g < G; g += NT) sum += expf(lg[g] - gmax);
-    s_red[tid] = sum;
-    __syncthreads();
-    for (int o = NT / 2; o > 0; o >>= 1) { if (tid < o) s_red[tid] += s_red[tid + o]; __syncthreads(); }
-    const float den = s_red[0];
-    __syncthreads();
-    for (int k = 0; k < q.beam; ++k) {                  // k-th largest logit, ties to the lower index
-        float bv = -INFINITY; int bi = 0x7fffffff;
-        for (int g = tid; g < G; g += NT) {
-            bool taken = false;
-            for (int j = 0; j < k; ++j) taken |= s_topi[j] == g;
-            const float v = lg[g];
-            if (!taken && (v > bv || (v == bv && g < bi))) { bv = v; bi = g; }
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) sum += (g0 + lane + 32 * j < g1) ? expf(v[j] - gmax) : 0.f;
+    sum = warp_sum(sum);
+    if (lane == 0) s_red[NWARP + warp] = sum;
+    // the beam largest logits of the slice, ties to the lower index
+    for (int k = 0; k < q.beam; ++k) {
+        float bv = v[0]; int bi = g0 + lane;
+#pragma unroll
+        for (int j = 1; j < VPL; ++j)
+            if (v[j] > bv) { bv = v[j]; bi = g0 + lane + 32 * j; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
         }
-        s_red[tid] = bv; s_redi[tid] = bi;
-        __syncthreads();
-        for (int o = NT / 2; o > 0; o >>= 1) {
-            if (tid < o) {
-                const float ov = s_red[tid + o]; const int oi = s_redi[tid + o];
-                if (ov > s_red[tid] || (ov == s_red[tid] && oi < s_redi[tid])) { s_red[tid] = ov; s_redi[tid] = oi; }
+#pragma unroll
+        for (int j = 0; j < VPL; ++j)
+            if (bi == g0 + lane + 32 * j) v[j] = -INFINITY;
+        if (lane == 0) { s_wv[warp][k] = bv; s_wi[warp][k] = bi; }
+    }
+    __syncthreads();
+    float den = 0.f;
+#pragma unroll
+    for (int w = 0; w < NWARP; ++w) den += s_red[NWARP + w];
+    if (warp == 0) {                                    // merge the NWARP x beam candidates
+        float cv[3]; int ci[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int c = lane + 32 * j, cw = c / INSERT_LIMIT, ck = c - cw * INSERT_LIMIT;
+            const bool ok = c < NWARP * INSERT_LIMIT && ck < q.beam;
+            cv[j] = ok ? s_wv[cw][ck] : -INFINITY;
+            ci[j] = ok ? s_wi[cw][ck] : 0x7fffffff;
+        }
+        for (int k = 0; k < q.beam; ++k) {
+            float bv = cv[0]; int bi = ci[0];
+#pragma unroll
+            for (int j = 1; j < 3; ++j)
+                if (cv[j] > bv || (cv[j] == bv && ci[j] < bi)) { bv = cv[j]; bi = ci[j]; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
             }
-            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                if (ci[j] == bi) { cv[j] = -INFINITY; ci[j] = 0x7fffffff; }
+            if (lane == 0) { s_topv[k] = bv; s_topi[k] = bi; }
         }
-        if (tid == 0) { s_topv[k] = s_red[0]; s_topi[k] = s_redi[0]; }
-        __syncthreads();
     }
-    if (tid != 0) {
-        // the remaining threads only help with the (grid-sized) output rows below
-    }
+    __syncthreads();
     __shared__ int s_cell, s_append, s_row;
     if (tid == 0) {
         int cell = s_topi[0];
@@ -456,8 +553,11 @@ __global__ void __launch_bounds__(NT) k_seed_decide(const SeedDecideArgs a) {
         int any = 0, any_new = 0;
         for (int b = 0; b < (int)gridDim.x; ++b) {
             any |= ((volatile int *)q.active)[b] != 0;
-            any_new |= ((volatile int *)q.new_row)[b] >= 0;
+            const int nr = ((volatile int *)q.new_row)[b];
+            if (nr >= 0) q.new_list[any_new++] = b * a.s.cap + nr;
         }
+        *q.n_new_list = any_new;
+        any_new = any_new > 0;
         q.flags[0] = any; q.flags[1] = any_new;
         *q.done_ctr = 0;
         if (q.use_cond) {
@@ -476,7 +576,7 @@ __global__ void __launch_bounds__(64) k_new_edges(const DecState s, const InsSta
     const int b = blockIdx.x, col = *s.col, T = s.T;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i_new = q.new_row[b];
-    if (threadIdx.x == 0) q.ha_lo[b] = 1 << 30;           // the heading-stack K|V rows of the old rows exist from now on
+    if (b == 0 && threadIdx.x == 0) *q.as_new_n = 0;
     if (i_new < 0) {
         if (threadIdx.x == 0) { q.hp_cnt_s[b] = 0; q.ha_cnt_s[b] = 0; }
         return;
@@ -558,19 +658,28 @@ __global__ void __launch_bounds__(NT) k_head_finalize(const HeadFinalArgs a) {
     const int b = blockIdx.x, col = *s.col, T = s.T;
     const int tid = threadIdx.x;
     const int i_new = q.new_row[b];
+    if (tid == 0) q.ha_lo[b] = 1 << 30;                   // the heading-stack K|V rows of the old rows exist from now on
     if (i_new < 0) return;
     const int r = b * s.cap + i_new, re = b * s.cap + s.ego_row[b];
     if (tid < 128) sx[tid] = a.x[(size_t)r * 128 + tid];
     __syncthreads();
-    mlp_head_row(sx, a.h_heading, sh, s_out);           // 120 heading bins
+    __shared__ float s_red[256];
+    mlp_head_row(sx, a.h_heading, sh, s_out, s_red);    // 120 heading bins
     __shared__ int s_bin;
-    if (tid == 0) {
-        int bi = 0; float bv = s_out[0];
-        for (int k = 1; k < a.h_heading.n_out; ++k) if (s_out[k] > bv) { bv = s_out[k]; bi = k; }
-        s_bin = bi;
+    if (tid < 32) {                                     // argmax, first occurrence
+        float bv = -INFINITY; int bi = 0x7fffffff;
+        for (int k = tid; k < a.h_heading.n_out; k += 32)
+            if (s_out[k] > bv) { bv = s_out[k]; bi = k; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (tid == 0) s_bin = bi;
     }
     __syncthreads();
-    mlp_head_row(sx, a.h_offset, sh, s_out);            // 2 offsets
+    mlp_head_row(sx, a.h_offset, sh, s_out, s_red);     // 2 offsets
     if (tid == 0) {
         const float eh = s.head[(size_t)re * T + col];
         // decode_heading (attr_tokenizer.py:106-110) + wrap (:2063)
@@ -582,14 +691,30 @@ __global__ void __launch_bounds__(NT) k_head_finalize(const HeadFinalArgs a) {
         s.pos[o * 2 + 1] = __fadd_rn(s.pos[o * 2 + 1], __fmul_rn(tanhf(s_out[1]), 2.f));
         // sic (:2083): the heading vectors of EVERY agent inserted in this iteration become the newest one's
         for (int k = 0; k < q.n_new[b]; ++k) s.hv_src[b * s.cap + i_new - k] = r;
+        // the new row's edge towards the query row of the following passes (it is the last index of the scene)
+        const float ex = s.pos[((size_t)re * T + col) * 2], ey = s.pos[((size_t)re * T + col) * 2 + 1];
+        const float dx = __fsub_rn(s.pos[o * 2], ex), dy = __fsub_rn(s.pos[o * 2 + 1], ey);
+        if (dist2(dx, dy) < q.r_seed2) {
+            const int rank = q.as_seen[b];
+            q.as_seen[b] = rank + 1;
+            if (rank < SEED_AGENT_MAX && s.interact[o] != 0) {
+                const int slot = b * q.as_stride + q.as_cnt[b];
+                seed_edge_write(s, q, slot, r, col, dx, dy, eh, cosf(eh), sinf(eh));
+                q.as_cnt[b] += 1;
+                q.as_new_list[atomicAdd(q.as_new_n, 1)] = slot;
+            }
+        }
     }
 }
 
 // cat[r] += type_a_emb[type[r]] for the rows [row_lo[b], n_rows[b]) (their shape embedding was just written)
+// (one block per scene)
 __global__ void k_add_type_emb_rows(const DecState s, const int *row_lo, float *cat, const float *type_emb) {
-    const int r = blockIdx.x, b = r / s.cap, i = r - b * s.cap;
-    if (i < row_lo[b] || i >= s.n_rows[b]) return;
-    cat[(size_t)r * 128 + threadIdx.x] += type_emb[s.type[r] * 128 + threadIdx.x];
+    const int b = blockIdx.x;
+    for (int i = row_lo[b]; i < s.n_rows[b]; ++i) {
+        const int r = b * s.cap + i;
+        cat[(size_t)r * 128 + threadIdx.x] += type_emb[s.type[r] * 128 + threadIdx.x];
+    }
 }
 
 // copy rows [row_lo[b], n_rows[b]) of every scene from one [R][128] buffer to another
@@ -597,6 +722,15 @@ __global__ void k_copy_new_rows(const DecState s, const int *row_lo, const float
     const int r = blockIdx.x, b = r / s.cap, i = r - b * s.cap;
     if ((row_lo && i < row_lo[b]) || i >= s.n_rows[b]) return;
     dst[(size_t)r * 128 + threadIdx.x] = src[(size_t)r * 128 + threadIdx.x];
+}
+// the same for the rows appended by the last pass, into two destinations: one block per scene
+__global__ void k_copy_new_rows2(const DecState s, const int *row_lo, const float *src, float *dst0, float *dst1) {
+    const int b = blockIdx.x;
+    for (int i = row_lo[b]; i < s.n_rows[b]; ++i) {
+        const size_t o = (size_t)(b * s.cap + i) * 128 + threadIdx.x;
+        const float v = src[o];
+        dst0[o] = v; dst1[o] = v;
+    }
 }
 
 }  // namespace infgen

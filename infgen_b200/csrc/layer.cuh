@@ -221,15 +221,15 @@ struct AttnPre {               // per warp: its share of the row's edges, source
     int src0, src1;
 };
 template <int M>
-__device__ __forceinline__ AttnPre attn_prefetch(const SubArgs &A, const RowSpace &rows, int row0) {
+__device__ __forceinline__ AttnPre attn_prefetch(const SubArgs &A, const int *s_rid) {
     const int nparts = A.wide ? NWARP : NWARP / M;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m = A.wide ? 0 : warp / nparts, part = A.wide ? warp : warp % nparts;
-    const int r = row0 + m;
+    const int r = s_rid[m];                              // global row, -1 = inactive
     AttnPre p;
     int n = 0;
     p.e0 = 0;
-    if (A.has_attn && rows.active(r)) {
+    if (A.has_attn && r >= 0) {
         const int ri = r >> A.row_shift;
         n = A.cnt[ri];
         p.e0 = A.start ? A.start[ri] : ri * A.stride;
@@ -398,13 +398,20 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
     using L = LayerSmem<M>;
     cg::cluster_group cluster = cg::this_cluster();
     const int c = (int)cluster.block_rank();                       // head / column slice of this CTA
-    const int row0 = (int)(blockIdx.x / CL) * M;
+    const int tile = (int)(blockIdx.x / CL);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    unsigned act_mask = 0;                                         // bit m: row row0 + m is active
+    __shared__ int s_rid[8];                                       // global row of every tile position, -1 = inactive
+    if (tid < M) {
+        const int r = a.rows.tile_row(tile, tid, M);
+        s_rid[tid] = a.rows.active_row(r) ? r : -1;
+    }
+    __syncthreads();
+    unsigned act_mask = 0;                                         // bit m: tile position m holds an active row
 #pragma unroll
-    for (int m = 0; m < M; ++m) act_mask |= a.rows.active(row0 + m) ? (1u << m) : 0u;
+    for (int m = 0; m < M; ++m) act_mask |= s_rid[m] >= 0 ? (1u << m) : 0u;
     if (!act_mask) return;                                         // uniform over the whole cluster
     auto active = [&](int m) { return (act_mask >> m) & 1u; };
+    auto rid = [&](int m) { return s_rid[m]; };
     const int col_now = a.col_ptr ? *a.col_ptr : 0;
     int ts_n = 0;
     auto stamp = [&]() {
@@ -463,7 +470,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
 
     // ---- residual rows; q / s / qr of the first layer when they come from an earlier launch ----------------------
     for (int m = warp; m < M; m += NWARP) {
-        const int r = row0 + m;
+        const int r = rid(m);
         const bool act = active(m);
         st4(sx + m * LD1 + 4 * lane, act ? ld4(a.x + (size_t)r * 128 + 4 * lane) : z4);
         if (!a.pre0.w) {
@@ -481,9 +488,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
             else if (a.sub[i].elist == 1) f1 = i;
             else f2 = i;
         }
-        apre0 = attn_prefetch<M>(a.sub[f0 < 0 ? 0 : f0], a.rows, row0);
-        apre1 = attn_prefetch<M>(a.sub[f1 < 0 ? 0 : f1], a.rows, row0);
-        apre2 = attn_prefetch<M>(a.sub[f2 < 0 ? 0 : f2], a.rows, row0);
+        apre0 = attn_prefetch<M>(a.sub[f0 < 0 ? 0 : f0], s_rid);
+        apre1 = attn_prefetch<M>(a.sub[f1 < 0 ? 0 : f1], s_rid);
+        apre2 = attn_prefetch<M>(a.sub[f2 < 0 ? 0 : f2], s_rid);
     }
     // grid barriers count the CTAs that own at least one active row (the others returned above)
     unsigned bar_target = 0, bar_step = 0;
@@ -519,7 +526,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
         __syncthreads();
         slice_gemm<M, 32, 4>(su, LD1, wpre + cs_pre::WQS, 32, sred, [&](int m, int n, float v) {
             v += wpre[cs_pre::BQS + n];
-            const int r = row0 + m;
+            const int r = rid(m);
             const bool st = P.to_global && active(m);
             if (n < 16) {
                 sq[m * 16 + n] = v;
@@ -533,7 +540,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
         if (P.pre_kv) {
             const int col = col_now + P.col_add;
             slice_gemm<M, 32, 4>(su, LD1, wpre + cs_pre::WKV, 32, sred, [&](int m, int n, float v) {
-                const int r = row0 + m;
+                const int r = rid(m);
                 if (active(m)) {
                     const size_t slot = P.kv_ring ? ((size_t)r * a.ring + (col & (a.ring - 1))) : (size_t)r;
                     const int o = n < 16 ? 16 * c + n : 128 + 16 * c + (n - 16);
@@ -561,7 +568,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
                 }
                 acc *= g;
                 sqr[m * 128 + ch] = acc;
-                const int r = row0 + m;
+                const int r = rid(m);
                 if (P.to_global && active(m)) a.qr[(size_t)r * 1024 + c * 128 + ch] = acc;
             }
         }
@@ -663,7 +670,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
         // x2 = x1 + LN_ffpost(y)
         const bool last = si + 1 == a.n_sub;
         for (int m = warp; m < M; m += NWARP) {
-            const int r = row0 + m;
+            const int r = rid(m);
             float4 f = ld4(sy + m * LD1 + 4 * lane);
             f = ln128s(f, wpost + cs_post::LN_FFPOST_G, wpost + cs_post::LN_FFPOST_B, lane);
             const float4 x2 = add4(ld4(sx + m * LD1 + 4 * lane), f);

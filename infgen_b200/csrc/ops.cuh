@@ -59,6 +59,18 @@ struct RowSpace {
     int cap;                   // 0: all rows < n_total are active
     const int *n_rows;         // [n_scenes] device
     const int *row_lo;         // optional [n_scenes]: rows below it are skipped ("new rows only" launches)
+    // optional compact row list (the rows appended by the last insertion pass, one per scene at most): tile t of a kernel
+    // that processes M rows per tile then holds list[t*M .. t*M+M), entries >= *n_list are inactive - a handful of tiles
+    // for a whole batch instead of one (mostly empty) tile per M rows of the row space
+    const int *list, *n_list;
+    int list_cap;              // upper bound of *n_list (grid sizing)
+    // global row of position m of tile `tile` (-1: none)
+    __device__ __forceinline__ int tile_row(int tile, int m, int M) const {
+        if (!list) return tile * M + m;
+        const int i = tile * M + m;
+        return i < *n_list ? list[i] : -1;
+    }
+    __device__ __forceinline__ bool active_row(int r) const { return r >= 0 && (list ? true : active(r)); }
     __device__ __forceinline__ bool active(int r) const {
         if (r >= n_total) return false;
         if (cap == 0) return true;
@@ -279,9 +291,14 @@ __global__ void __launch_bounds__(NT_S) k_mlp_embed(const MlpEmbArgs a) {
     float *sH = sX + EM * ldx;               // [EM][HLD]
     float *sG = sH + EM * HLD;               // [EM][HLD]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int row0 = blockIdx.x * EM;
+    __shared__ int s_row[EM];                // global row of every tile position, -1 = inactive
+    if (tid < EM) {
+        const int r = a.rows.tile_row(blockIdx.x, tid, EM);
+        s_row[tid] = a.rows.active_row(r) ? r : -1;
+    }
+    __syncthreads();
     bool any = false;
-    for (int m = 0; m < EM; ++m) any |= a.rows.active(row0 + m);
+    for (int m = 0; m < EM; ++m) any |= s_row[m] >= 0;
     if (!any) return;
     ws_init(wsm);
     if (warp == NWARP) {
@@ -294,13 +311,13 @@ __global__ void __launch_bounds__(NT_S) k_mlp_embed(const MlpEmbArgs a) {
     WsCons ws(wsm);
     for (int i = tid; i < EM * ldx; i += NT) {
         const int m = i / ldx, k = i % ldx;
-        const int r = row0 + m;
-        sX[i] = (k < a.kin && a.rows.active(r)) ? a.x[(size_t)r * a.x_ld + k] : 0.f;
+        const int r = s_row[m];
+        sX[i] = (k < a.kin && r >= 0) ? a.x[(size_t)r * a.x_ld + k] : 0.f;
     }
     csync();
     mlp3_body<EM>(ws, a.w, sX, ldx, a.k4, sH, sG, [&](int m, int n, float v) {
-        const int r = row0 + m;
-        if (a.rows.active(r)) a.out[(size_t)r * a.out_ld + n] = v;
+        const int r = s_row[m];
+        if (r >= 0) a.out[(size_t)r * a.out_ld + n] = v;
     });
 }
 static inline size_t mlp_embed_smem(int k4) { return (size_t)(WS_SMEM_FLOATS + EM * mlp_ldx(k4) + 2 * EM * HLD) * sizeof(float); }
