@@ -567,7 +567,7 @@ static int launch_attn(infgen_engine *e, const RowSpace &rows, const SubArgs &su
     a.rows = rows; a.sub = sub; a.q = b.q; a.qr = b.qr;
     a.agg = b.agg; a.ragg = b.ragg; a.sal = b.sal;
     ProfScope ps(e, KC_ATTN);
-    k_attn<<<(rows.n_total + AW - 1) / AW, AW * 32, 0, e->stream>>>(a);
+    k_attn<<<(rows.n_total + AW - 1) / AW, AW * 32, ATTN_SMEM, e->stream>>>(a);
     CKL(); count_launch(e);
     return 0;
 }
@@ -1258,6 +1258,7 @@ int32_t infgen_create(const infgen_config *cfg, const float *weights, int64_t n_
     CK(cudaFuncSetAttribute(k_layer<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LayerSmem<8>::BYTES));
     CK(cudaFuncSetAttribute(k_fourier, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FOURIER_SMEM));
     CK(cudaFuncSetAttribute(k_fourier_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ftc::SMEM));
+    CK(cudaFuncSetAttribute(k_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATTN_SMEM));
     CK(cudaFuncSetAttribute(k_node<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NodeSmem::BYTES));
     CK(cudaFuncSetAttribute(k_node<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NodeSmem::BYTES));
     {

@@ -59,15 +59,57 @@ constexpr int AW = 4;          // warps (= rows) per CTA
 // head: 5 KB per edge).  The eight relative scores (one per head) are reduced with the butterfly reduce-scatter of
 // attn_phase, which leaves head h's score in lane group h, next to its K/V slice; each lane group runs its own online
 // softmax.  Loads of the next two edges are in flight while two are reduced.
-struct EdgeLd {
-    float4 rh, k, v;
-};
+//
+// What bounds it (measured, round 2): NOT the memory system - a plain LDG.128 gather of the same rows with two edges in
+// flight per warp runs at 10-11 TB/s out of L2 and 7.2 TB/s out of HBM (tools/probe/gather_bw.cu,
+// profiles/r2_gather_bw_probe.log; cp.async.bulk staging of the 1 KB rows reaches only 3-4 TB/s, and splitting a row's
+// edges over four warps made the kernel slower) - but instruction issue: ~185 instructions per edge and warp, 80 of them
+// the rescale-and-accumulate of the eight per-head relative sums.  Hence the LAZY rescale below: the softmax reference
+// value of a head only moves when a score exceeds it by more than ATTN_LAZY (weights stay below e^ATTN_LAZY, far
+// from fp32 overflow for <= 2048 edges), so the common edge needs no rescale multiply and half the broadcasts.
+// Staging: every warp owns a ring of ATTN_DEPTH edge slots in shared memory ([rhat 512 B | K 512 B | V 512 B] each), filled
+// with 16-byte cp.async copies (LDGSTS: no registers held while the rows are in flight), ATTN_DEPTH edges ahead of the edge
+// being reduced.  The launch is a single wave of ~14 warps per SM, every warp walking its row's edges as one chain, so
+// the depth of this prefetch - not bandwidth - sets the kernel time (with two edges in flight in registers the warp
+// stalled on L2 latency for every pair: ncu long-scoreboard 2.4 of 6.7 stalled warps per issue).
+constexpr int ATTN_DEPTH = 8;
+constexpr int ATTN_SLOT = 384;                         // floats per edge slot
+constexpr size_t ATTN_SMEM = (size_t)AW * ATTN_DEPTH * ATTN_SLOT * sizeof(float);
+__device__ __forceinline__ void cp_async16(float *dst_smem, const float *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __global__ void __launch_bounds__(AW * 32) k_attn(const AttnArgs a) {
+    extern __shared__ __align__(16) float smem_attn[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = blockIdx.x * AW + warp;
     if (!a.rows.active(r)) return;
     const SubArgs &A = a.sub;
+    float *ring = smem_attn + (size_t)warp * ATTN_DEPTH * ATTN_SLOT + 4 * lane;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int n = A.has_attn ? A.cnt[r] : 0;
+    const int e0 = A.start ? A.start[r] : r * A.stride;
+    const float *rhb = A.rhat + (size_t)e0 * 128 + 4 * lane;
+    const float *kvb = A.kv + 4 * lane;
+    // source rows of the edges, 64 at a time in two registers (edge e of the row: lane e & 31 of word (e >> 5) & 1)
+    int src_w0 = lane < n ? A.src[e0 + lane] : 0;
+    int src_w1 = 32 + lane < n ? A.src[e0 + 32 + lane] : 0;
+    auto issue = [&](int e) {                                // edge e -> slot e % ATTN_DEPTH (all lanes; e < n)
+        const int s0 = __shfl_sync(0xffffffffu, src_w0, e & 31), s1 = __shfl_sync(0xffffffffu, src_w1, e & 31);
+        const int sj = (e & 32) ? s1 : s0;
+        float *d = ring + (e % ATTN_DEPTH) * ATTN_SLOT;
+        if (A.has_pos) cp_async16(d, rhb + (size_t)e * 128);
+        const float *p = kvb + (size_t)sj * 256;
+        cp_async16(d + 128, p);
+        cp_async16(d + 256, p + 128);
+    };
+    for (int e = 0; e < ATTN_DEPTH; ++e) {                   // prologue: one commit group per edge slot
+        if (e < n) issue(e);
+        cp_async_commit();
+    }
     const float4 q4 = ld4(a.q + (size_t)r * 128 + 4 * lane);
     float4 qr4[8], ra[8];
 #pragma unroll
@@ -75,81 +117,90 @@ __global__ void __launch_bounds__(AW * 32) k_attn(const AttnArgs a) {
         qr4[h] = A.has_pos ? ld4(a.qr + ((size_t)r * 8 + h) * 128 + 4 * lane) : z4;
         ra[h] = z4;
     }
-    const int n = A.has_attn ? A.cnt[r] : 0;
-    const int e0 = A.start ? A.start[r] : r * A.stride;
-    const float *rhb = A.rhat + (size_t)e0 * 128 + 4 * lane;
-    const float *kvb = A.kv + 4 * lane;
-    float mx = -INFINITY, den = 0.f;
-    float4 av = z4;
+    float mx = -INFINITY, den = 0.f;                          // mx: softmax reference of this lane's head (one of its scores,
+    float4 av = z4;                                           //     at most ATTN_LAZY below the running maximum)
     const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
-
-    for (int blk = 0; blk < n; blk += 32) {
-        const int m = min(32, n - blk);
-        const int srcreg = (lane < m) ? A.src[e0 + blk + lane] : 0;
-        auto load = [&](EdgeLd &L, int i) {                  // edge blk + i (i < 32)
-            const int sj = __shfl_sync(0xffffffffu, srcreg, i & 31);
-            if (i < m) {
-                L.rh = A.has_pos ? ld4(rhb + (size_t)(blk + i) * 128) : z4;
-                const float4 *p = reinterpret_cast<const float4 *>(kvb + (size_t)sj * 256);
-                L.k = __ldcg(p);
-                L.v = __ldcg(p + 32);
-            }
-        };
-        auto compute = [&](const EdgeLd &L) {
-            float pk = dot4(q4, L.k);
-            pk += __shfl_xor_sync(0xffffffffu, pk, 1);
-            pk += __shfl_xor_sync(0xffffffffu, pk, 2);
-            float v[8];
+    constexpr float ATTN_LAZY = 8.0f;
+    // score of one edge for the head of this lane's group (all four lanes of the group hold it)
+    auto score = [&](const float4 rh, const float4 k) {
+        float pk = dot4(q4, k);
+        pk += __shfl_xor_sync(0xffffffffu, pk, 1);
+        pk += __shfl_xor_sync(0xffffffffu, pk, 2);
+        float v[8];
 #pragma unroll
-            for (int h = 0; h < 8; ++h) v[h] = dot4(qr4[h], L.rh);
+        for (int h = 0; h < 8; ++h) v[h] = dot4(qr4[h], rh);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float recv = __shfl_xor_sync(0xffffffffu, b4 ? v[i] : v[i + 4], 16);
-                v[i] = (b4 ? v[i + 4] : v[i]) + recv;
-            }
+        for (int i = 0; i < 4; ++i) {
+            const float recv = __shfl_xor_sync(0xffffffffu, b4 ? v[i] : v[i + 4], 16);
+            v[i] = (b4 ? v[i + 4] : v[i]) + recv;
+        }
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const float recv = __shfl_xor_sync(0xffffffffu, b3 ? v[i] : v[i + 2], 8);
-                v[i] = (b3 ? v[i + 2] : v[i]) + recv;
-            }
-            {
-                const float recv = __shfl_xor_sync(0xffffffffu, b2 ? v[0] : v[1], 4);
-                v[0] = (b2 ? v[1] : v[0]) + recv;
-            }
-            float pr = v[0];
-            pr += __shfl_xor_sync(0xffffffffu, pr, 1);
-            pr += __shfl_xor_sync(0xffffffffu, pr, 2);
-            const float p = (pr + pk) * 0.25f;               // head_dim ** -0.5
-            const float mn = fmaxf(mx, p);
-            const float sc = expf(mx - mn);                  // 0 for the first edge
-            const float w = expf(p - mn);
-            den = fmaf(den, sc, w);
-            av.x = fmaf(av.x, sc, w * L.v.x); av.y = fmaf(av.y, sc, w * L.v.y);
-            av.z = fmaf(av.z, sc, w * L.v.z); av.w = fmaf(av.w, sc, w * L.v.w);
+        for (int i = 0; i < 2; ++i) {
+            const float recv = __shfl_xor_sync(0xffffffffu, b3 ? v[i] : v[i + 2], 8);
+            v[i] = (b3 ? v[i + 2] : v[i]) + recv;
+        }
+        {
+            const float recv = __shfl_xor_sync(0xffffffffu, b2 ? v[0] : v[1], 4);
+            v[0] = (b2 ? v[1] : v[0]) + recv;
+        }
+        float pr = v[0];
+        pr += __shfl_xor_sync(0xffffffffu, pr, 1);
+        pr += __shfl_xor_sync(0xffffffffu, pr, 2);
+        return (pr + pk) * 0.25f;                            // head_dim ** -0.5
+    };
+    for (int e = 0; e < n; e += 2) {
+        // edges e, e + 1 have landed when at most ATTN_DEPTH - 2 younger groups are pending
+        cp_async_wait<ATTN_DEPTH - 2>();
+        __syncwarp();
+        const bool two = e + 1 < n;
+        const float *d0 = ring + (e % ATTN_DEPTH) * ATTN_SLOT, *d1 = ring + ((e + 1) % ATTN_DEPTH) * ATTN_SLOT;
+        const float4 rh0 = A.has_pos ? ld4(d0) : z4, k0 = ld4(d0 + 128), v0 = ld4(d0 + 256);
+        float4 rh1 = z4, k1 = z4, v1 = z4;
+        if (two) { rh1 = A.has_pos ? ld4(d1) : z4; k1 = ld4(d1 + 128); v1 = ld4(d1 + 256); }
+        __syncwarp();                                        // every lane has read its slots: they may be refilled
+        // the next two edges of the ring (two commit groups, empty ones past the end keep the group count in step)
+        if ((e + ATTN_DEPTH & 63) == 0 && e + ATTN_DEPTH < n) {     // crossing into the next 64 edges: refill the source words
+            src_w0 = e + ATTN_DEPTH + lane < n ? A.src[e0 + e + ATTN_DEPTH + lane] : 0;
+            src_w1 = e + ATTN_DEPTH + 32 + lane < n ? A.src[e0 + e + ATTN_DEPTH + 32 + lane] : 0;
+        }
+        if (e + ATTN_DEPTH < n) issue(e + ATTN_DEPTH);
+        cp_async_commit();
+        if (e + ATTN_DEPTH + 1 < n) issue(e + ATTN_DEPTH + 1);
+        cp_async_commit();
+        // two edges per step: their score chains are independent
+        const float p0 = score(rh0, k0);
+        const float p1 = two ? score(rh1, k1) : -INFINITY;
+        const float pm = fmaxf(p0, p1);
+        if (__any_sync(0xffffffffu, pm > mx + ATTN_LAZY)) {
+            // some head's score left the window above its reference (always on a row's first edges): move the reference
+            // of the heads concerned and rescale their sums
+            const float mn = pm > mx + ATTN_LAZY ? pm : mx;
+            const float sc = expf(mx - mn);                  // 0 on the first edge, 1 for heads that keep their reference
+            den *= sc;
+            av.x *= sc; av.y *= sc; av.z *= sc; av.w *= sc;
             mx = mn;
             if (A.has_pos) {
 #pragma unroll
                 for (int h = 0; h < 8; ++h) {
-                    const float sh = __shfl_sync(0xffffffffu, sc, 4 * h), wh = __shfl_sync(0xffffffffu, w, 4 * h);
-                    ra[h].x = fmaf(ra[h].x, sh, wh * L.rh.x); ra[h].y = fmaf(ra[h].y, sh, wh * L.rh.y);
-                    ra[h].z = fmaf(ra[h].z, sh, wh * L.rh.z); ra[h].w = fmaf(ra[h].w, sh, wh * L.rh.w);
+                    const float sh = __shfl_sync(0xffffffffu, sc, 4 * h);
+                    ra[h].x *= sh; ra[h].y *= sh; ra[h].z *= sh; ra[h].w *= sh;
                 }
             }
-        };
-        EdgeLd a0, a1, c0, c1;
-        load(a0, 0);
-        load(a1, 1);
-        for (int i = 0; i < m; i += 4) {
-            load(c0, i + 2);
-            load(c1, i + 3);
-            compute(a0);
-            if (i + 1 < m) compute(a1);
-            load(a0, i + 4);
-            load(a1, i + 5);
-            if (i + 2 < m) compute(c0);
-            if (i + 3 < m) compute(c1);
+        }
+        const float w0 = expf(p0 - mx), w1 = expf(p1 - mx);   // w1 = 0 for an absent edge
+        den += w0 + w1;
+        av.x = fmaf(w0, v0.x, fmaf(w1, v1.x, av.x)); av.y = fmaf(w0, v0.y, fmaf(w1, v1.y, av.y));
+        av.z = fmaf(w0, v0.z, fmaf(w1, v1.z, av.z)); av.w = fmaf(w0, v0.w, fmaf(w1, v1.w, av.w));
+        if (A.has_pos) {
+#pragma unroll
+            for (int h = 0; h < 8; ++h) {
+                const float g0 = __shfl_sync(0xffffffffu, w0, 4 * h), g1 = __shfl_sync(0xffffffffu, w1, 4 * h);
+                ra[h].x = fmaf(g0, rh0.x, fmaf(g1, rh1.x, ra[h].x)); ra[h].y = fmaf(g0, rh0.y, fmaf(g1, rh1.y, ra[h].y));
+                ra[h].z = fmaf(g0, rh0.z, fmaf(g1, rh1.z, ra[h].z)); ra[h].w = fmaf(g0, rh0.w, fmaf(g1, rh1.w, ra[h].w));
+            }
         }
     }
+    cp_async_wait<0>();
     const float inv = 1.0f / (den + 1e-16f);                 // torch_geometric.utils.softmax denominator
     st4(a.agg + (size_t)r * 128 + 4 * lane, make_float4(av.x * inv, av.y * inv, av.z * inv, av.w * inv));
     if ((lane & 3) == 0) a.sal[(size_t)r * 8 + (lane >> 2)] = den * inv;

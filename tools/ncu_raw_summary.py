@@ -19,3 +19,18 @@ for r in data:
     for key, label in WANT:
         if key in ix:
             print(f'   {label:44s} {r[ix[key]]} {units[ix[key]]}')
+    # issue-stall breakdown (warps per issue-active cycle), largest first
+    st = [(h, r[ix[h]]) for h in hdr if 'issue_stalled' in h and h.endswith('per_issue_active.ratio')]
+    def _f(x):
+        try:
+            return float(x.replace(',', ''))
+        except Exception:
+            return 0.0
+    for h, v in sorted(st, key=lambda kv: -_f(kv[1]))[:7]:
+        print(f"   stall {h.split('issue_stalled_')[1].split('_per_issue')[0]:38s} {v}")
+    for key in ('smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed.avg.per_cycle_elapsed',
+                'smsp__inst_executed.avg.per_cycle_active', 'l1tex__t_bytes.sum', 'lts__t_sectors_srcunit_tex_op_read.sum',
+                'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__throughput.avg.pct_of_peak_sustained_active',
+                'lts__throughput.avg.pct_of_peak_sustained_elapsed', 'dram__throughput.avg.pct_of_peak_sustained_elapsed'):
+        if key in ix:
+            print(f'   {key:60s} {r[ix[key]]} {units[ix[key]]}')
