@@ -535,7 +535,57 @@ def run_ours(args, rank, world, local_rank):
                     'rows_final_max': max(rows_final), 'launches_per_step': mb['launches'] / n_steps,
                     'workload_stats': st, 'roofline_kernels': kl}
 
+        def map_encoder():
+            """Row f1: `InfGenMapDecoder.forward` (runs once per scene right before the decode, infgen_decoder.py:124) on the
+            same engine; x_pt stays in HBM for the decode that follows."""
+            from infgen_b200.weights import make_map_state_dict
+            from infgen_b200.synth import make_map_tokens
+            from infgen_b200.map_encoder import load_map_vocab
+            msd, traj = make_map_state_dict(0), load_map_vocab()
+            datas = []
+            for i, s_ in enumerate(scenes):
+                pt = make_map_tokens(s_, i)
+                d = dict(s_)
+                d['pt_token'] = dict(s_['pt_token'])
+                d['pt_token'].update({k: pt[k] for k in ('type', 'pl_type', 'token_idx', 'pt_pred_mask', 'pt_valid_mask', 'pt_target_mask')})
+                d['pt_token']['light_type'] = pt['polygon_light_type'][pt['polygon']]
+                datas.append(d)
+            fdec = B200AgentDecoder(sd, cfg, device=local_rank, seed=2024, use_cuda_graph=True, map_state_dict=msd, map_traj_src=traj)
+            for _ in range(3):
+                fdec.map_encode(datas, want_x=False)
+            torch.cuda.synchronize(dev)
+            tm = []
+            for _ in range(10):
+                t0 = time.perf_counter()
+                fdec.map_encode(datas, want_x=False)
+                tm.append(time.perf_counter() - t0)
+            for _ in range(3):
+                fdec.inference_batch(datas, None, scene_ids=my_ids)
+            te = []
+            for _ in range(max(5, args.steps // 2)):
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                fdec.inference_batch(datas, None, scene_ids=my_ids)
+                te.append(time.perf_counter() - t0)
+            fdec.close()
+            out = {'workload': 'map encoder of the configs[1] scene (2048 map tokens, radius graph r = 10 m <= 100 neighbours, 3 '
+                               'pt2pt AttentionLayers) and the decode fed from it on ONE engine, host tensors in, x_pt kept in HBM',
+                   'map_encode_ms': statistics.mean(tm) * 1e3,
+                   'e2e_map_plus_decode_ms': statistics.mean(te) * 1e3,
+                   'e2e_map_plus_decode_value': agent_steps / statistics.mean(te), 'unit': UNIT}
+            try:
+                from oracle.map_decoder_oracle import map_encode as cpu_map
+                q = dict(datas[0]['pt_token'])
+                t0 = time.perf_counter()
+                with torch.no_grad():
+                    cpu_map(msd, q, traj)
+                out['cpu_port_map_encode_ms'] = (time.perf_counter() - t0) * 1e3
+            except Exception as ex:
+                out['cpu_port_error'] = repr(ex)[:200]
+            return out
+
         side('motion_only', motion_only)
+        side('map_encoder', map_encoder)
         side('configs2', lambda: batch(2, 5))
         side('configs4_one_gpu', lambda: batch(4, 2))
 

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define INFGEN_ABI_VERSION 4
+#define INFGEN_ABI_VERSION 5
 
 typedef enum {
     INFGEN_OK = 0,
@@ -95,7 +95,8 @@ typedef struct {
     const int32_t *pt_ptr;        /* [n_scenes+1] */
     const float *pt_pos;          /* [P][2] */
     const float *pt_ori;          /* [P]    */
-    const float *x_pt;            /* [P][128] map encoder output, agent_decoder.py:2143 */
+    const float *x_pt;            /* [P][128] map encoder output, agent_decoder.py:2143; NULL = the output of this engine's
+                                     infgen_map_encode on the same tokens, which then never leaves HBM */
 } infgen_scene_batch;
 
 /* Result buffers of one batch (any pointer may be NULL = not wanted). Layout [R = n_scenes*row_capacity][...]. */
@@ -162,6 +163,27 @@ int32_t infgen_read(infgen_engine *e, const infgen_outputs *out, int32_t loc);
 int32_t infgen_iterations_done(infgen_engine *e);
 /* number of kernels this library launched (or replayed through graphs) since the engine was created */
 int64_t infgen_kernel_launches(infgen_engine *e);
+
+/* ---- the map encoder: InfGenMapDecoder.forward (map_decoder.py:70-130), SURVEY.md 8f row f1 ---------------------- */
+/* Map tokens of a batch of scenes, concatenated; scene b owns [pt_ptr[b], pt_ptr[b+1]).  `loc` applies to the per-token
+ * arrays; pt_ptr is always host.  light_type is the owning polygon's light type gathered per token (map_decoder.py:85-86). */
+typedef struct {
+    int32_t n_scenes;
+    const int32_t *pt_ptr;        /* [n_scenes+1] */
+    const float *pt_pos;          /* [P][2] data['pt_token']['position'][:, :2] */
+    const float *pt_ori;          /* [P]    data['pt_token']['orientation'] */
+    const int32_t *type;          /* [P]    data['pt_token']['type']    (17 classes) */
+    const int32_t *pl_type;       /* [P]    data['pt_token']['pl_type'] (4) */
+    const int32_t *light_type;    /* [P]    data['map_polygon']['light_type'][token2pl[1]] (4) */
+    const int32_t *token_idx;     /* [P]    data['pt_token']['token_idx'] (map vocabulary, 1024) */
+    float pl2pl_radius;           /* 10     radius_graph radius (map_decoder.py:91), max_num_neighbors = 100 */
+} infgen_map_batch;
+/* token_emb over the map vocabulary (map_decoder.py:78-80): traj_src [n_tokens][22] = map_token['traj_src'].view(n, -1), host */
+int32_t infgen_map_setup(infgen_engine *e, const float *traj_src, int32_t n_tokens);
+/* x_pt [P][128] (and, when wanted, the token_predict_head logits [P][1024] of every token; the reference evaluates the head
+ * on x_pt[pt_pred_mask], map_decoder.py:119).  Either output may be NULL; the result also stays in the engine for a
+ * following infgen_load_scenes with x_pt == NULL.  Synchronises the stream when loc == INFGEN_HOST. */
+int32_t infgen_map_encode(infgen_engine *e, const infgen_map_batch *batch, int32_t loc, float *x_pt_out, float *logits_out);
 
 /* ---- per-kernel-class device timing for the roofline report (bench.py): CUDA events around every launch; turns
  * graph replay off while enabled ------------------------------------------------------------------------------ */

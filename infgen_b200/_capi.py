@@ -9,7 +9,7 @@ import os
 from typing import Optional
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib', 'libinfgen_b200.so')
-ABI_VERSION = 4
+ABI_VERSION = 5
 HOST, DEVICE = 0, 1
 
 c_f32p = C.POINTER(C.c_float)
@@ -37,6 +37,13 @@ class SceneBatch(C.Structure):
         ('pos_hist', c_f32p), ('head_hist', c_f32p), ('state_hist', c_i32p), ('token_hist', c_i32p),
         ('grid_hist', c_i32p), ('tsrc_hist', c_u8p), ('interact_hist', c_u8p), ('type', c_i32p), ('shape', c_f32p),
         ('pt_ptr', c_i32p), ('pt_pos', c_f32p), ('pt_ori', c_f32p), ('x_pt', c_f32p),
+    ]
+
+
+class MapBatch(C.Structure):
+    _fields_ = [
+        ('n_scenes', C.c_int32), ('pt_ptr', c_i32p), ('pt_pos', c_f32p), ('pt_ori', c_f32p), ('type', c_i32p),
+        ('pl_type', c_i32p), ('light_type', c_i32p), ('token_idx', c_i32p), ('pl2pl_radius', C.c_float),
     ]
 
 
@@ -70,6 +77,8 @@ SYMBOLS = {
     'infgen_rollout': (C.c_int32, [C.c_void_p]),
     'infgen_read': (C.c_int32, [C.c_void_p, C.POINTER(Outputs), C.c_int32]),
     'infgen_iterations_done': (C.c_int32, [C.c_void_p]),
+    'infgen_map_setup': (C.c_int32, [C.c_void_p, c_f32p, C.c_int32]),
+    'infgen_map_encode': (C.c_int32, [C.c_void_p, C.POINTER(MapBatch), C.c_int32, c_f32p, c_f32p]),
     'infgen_kernel_launches': (C.c_int64, [C.c_void_p]),
     'infgen_set_profile': (C.c_int32, [C.c_void_p, C.c_int32]),
     'infgen_profile_class_count': (C.c_int32, []),

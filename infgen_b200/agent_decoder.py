@@ -21,16 +21,23 @@ from .weights import pack_state_dict
 
 
 class B200AgentDecoder:
-    def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: Optional[DecoderConfig] = None, device: int = 0,
+    def __init__(self, state_dict: Optional[Dict[str, torch.Tensor]], cfg: Optional[DecoderConfig] = None, device: int = 0,
                  use_cuda_graph: bool = True, trace: bool = False, seed: int = 2024,
-                 vocab: Optional[Dict[str, torch.Tensor]] = None):
+                 vocab: Optional[Dict[str, torch.Tensor]] = None,
+                 map_state_dict: Optional[Dict[str, torch.Tensor]] = None,
+                 map_traj_src: Optional[torch.Tensor] = None):
+        """state_dict: `InfGenAgentDecoder.state_dict()` (None: an engine that only serves the map encoder).
+        map_state_dict: `InfGenMapDecoder.state_dict()` - the engine then also runs the map encoder (`map_encode`) and
+        `inference` accepts `map_enc=None`: x_pt is produced and consumed in HBM."""
         self.cfg = cfg or DecoderConfig()
         self.lib = _capi.load()
         self.device = device
         self.trace = trace
-        sd = {k[len('encoder.agent_encoder.'):] if k.startswith('encoder.agent_encoder.') else k: v
-              for k, v in state_dict.items()}
-        blob = pack_state_dict(sd, self.lib)
+        sd = None if state_dict is None else {
+            k[len('encoder.agent_encoder.'):] if k.startswith('encoder.agent_encoder.') else k: v
+            for k, v in state_dict.items()}
+        self.has_map = map_state_dict is not None
+        blob = pack_state_dict(sd, self.lib, map_state_dict)
         grid = PositionGrid(self.cfg.grid_range, self.cfg.grid_interval, self.cfg.pl2seed_radius,
                             self.cfg.angle_interval)
         self.grid = grid
@@ -58,6 +65,12 @@ class B200AgentDecoder:
         _capi.check(self.lib.infgen_create(C.byref(c), _capi.f32p(blob), blob.size, _capi.f32p(cells),
                                            _capi.f32p(vocab_arr), C.byref(h)))
         self._h = h
+        if self.has_map:
+            from .map_encoder import load_map_vocab, MAP_TOKEN_DIM
+            traj = map_traj_src if map_traj_src is not None else load_map_vocab()
+            traj = np.ascontiguousarray(torch.as_tensor(traj).float().reshape(traj.shape[0], -1).cpu().numpy())
+            assert traj.shape[1] == MAP_TOKEN_DIM, traj.shape
+            _capi.check(self.lib.infgen_map_setup(self._h, _capi.f32p(traj), traj.shape[0]))
         self._batch: Optional[HostBatch] = None
         self._scenes: Optional[Sequence[SceneHost]] = None
         self._host_cache: Optional[HostBatch] = None
@@ -99,10 +112,19 @@ class B200AgentDecoder:
                 token_hist=_capi.i32p(b.token_hist), grid_hist=_capi.i32p(b.grid_hist), tsrc_hist=_capi.u8p(b.tsrc_hist),
                 interact_hist=_capi.u8p(b.interact_hist), type=_capi.i32p(b.type), shape=_capi.f32p(b.shape),
                 pt_ptr=_capi.i32p(b.pt_ptr), pt_pos=_capi.f32p(b.pt_pos), pt_ori=_capi.f32p(b.pt_ori),
-                x_pt=_capi.f32p(b.x_pt))
+                x_pt=_capi.f32p(b.x_pt) if b.has_x_pt else None)
         loc = _capi.DEVICE if getattr(b, 'on_device', False) else _capi.HOST
         _capi.check(self.lib.infgen_load_scenes(self._h, C.byref(sb), loc))
         self._batch, self._scenes = batch, scenes
+
+    def map_encode(self, datas: Sequence[Dict], pl2pl_radius: float = 10.0, want_x: bool = True):
+        """`InfGenMapDecoder.forward` of several scenes on this engine (built with `map_state_dict`): x_pt per scene (when
+        wanted); the concatenated result also stays in HBM for a following `load` whose batch carries no x_pt."""
+        from .map_encoder import encode_on, map_token_fields
+        if not self.has_map:
+            raise RuntimeError('engine was built without map_state_dict')
+        x, _, ptr = encode_on(self._h, self.lib, [map_token_fields(d) for d in datas], pl2pl_radius, want_x, False)
+        return [torch.from_numpy(x[ptr[i]:ptr[i + 1]]) for i in range(len(datas))] if want_x else None
 
     def set_forcing(self, tokens: Optional[torch.Tensor], states: Optional[torch.Tensor]):
         """[R, S] int32 teacher-forcing overrides in the batch row space (None = off)."""
@@ -182,13 +204,18 @@ class B200AgentDecoder:
         }
 
     # ---- the reference call boundary ----------------------------------------------------------------------------
-    def inference_batch(self, datas: Sequence[Dict], map_encs: Sequence[Dict],
+    def inference_batch(self, datas: Sequence[Dict], map_encs: Optional[Sequence[Dict]],
                         scene_ids: Optional[Sequence[int]] = None, motion_only: bool = False) -> List[Dict]:
         """Closed-loop rollout of several independent scenes in one launch sequence (a capability the reference
-        lacks: its inference is batch-size-1, agent_decoder.py:1631; the oracle is one reference call per scene)."""
+        lacks: its inference is batch-size-1, agent_decoder.py:1631; the oracle is one reference call per scene).
+        map_encs=None (engines built with `map_state_dict`): the map encoder runs first on the same engine
+        (`InfGenDecoder.inference`, infgen_decoder.py:123-130) and x_pt never leaves HBM."""
         if motion_only and not self.cfg.disable_insertion:
             raise ValueError('motion_only needs an engine built with disable_insertion=True')
         self._check_vocab(datas[0])
+        if map_encs is None:
+            self.map_encode(datas, want_x=False)
+            map_encs = [None] * len(datas)
         scenes = [prepare_scene(d, m, self.cfg) for d, m in zip(datas, map_encs)]
         batch = self._host_cache
         if batch is not None and batch.fits(scenes):
@@ -212,9 +239,9 @@ class B200AgentDecoder:
                 batch = self._host_cache = HostBatch(scenes, self.cfg, scene_ids, row_capacity=new_cap)
         return assemble_outputs(batch, scenes, self.cfg)
 
-    def inference(self, data: Dict, map_enc: Dict, motion_only: bool = False) -> Dict:
+    def inference(self, data: Dict, map_enc: Optional[Dict], motion_only: bool = False) -> Dict:
         """`InfGenAgentDecoder.inference(data, map_enc)` (agent_decoder.py:1605-2389)."""
-        return self.inference_batch([data], [map_enc], motion_only=motion_only)[0]
+        return self.inference_batch([data], None if map_enc is None else [map_enc], motion_only=motion_only)[0]
 
     def _check_vocab(self, data):
         ag = data['agent']

@@ -19,6 +19,7 @@
 #include "node.cuh"
 #include "decode.cuh"
 #include "insert.cuh"
+#include "map.cuh"
 
 using namespace infgen;
 
@@ -104,6 +105,7 @@ static void w_head(const std::string &p, int kin, int nout) {
     w_add(p + ".w3", gemm_numel(128, pad128(nout))); w_add(p + ".b3", pad128(nout));
 }
 static const int GRID_SIZE = 1961, ANGLE_SIZE = 120, TOKEN_SIZE = 2048;
+static const int MAP_TOKEN_SIZE = 1024, MAP_TOKEN_DIM = 22;       // map_decoder.py:59-63
 // rows per scene: the scene's own agents plus everything the insertion stage may append (the reference never compacts:
 // up to 10 rows per iteration, agent_decoder.py:1738, i.e. 3,000 over a 150 s rollout)
 static const int MAX_ROW_CAPACITY = 8192;
@@ -128,6 +130,12 @@ static void build_layout() {
     w_head("seed_offset_xy_predict_head", 128, 2); w_head("seed_agent_occ_embed", GRID_SIZE, 128);
     w_head("seed_heading_rel_token_predict_head", 128, ANGLE_SIZE);
     w_head("grid_agent_occ_head", 128, GRID_SIZE); w_head("grid_pt_occ_head", 128, GRID_SIZE);
+    // map encoder `InfGenMapDecoder` (map_decoder.py:46-64); names carry the prefix "map."
+    w_add("map.type_pt_emb", 17 * 128); w_add("map.polygon_type_emb", 4 * 128); w_add("map.light_pl_emb", 4 * 128);
+    w_fourier("map.r_pt2pt_emb", 3);
+    for (int i = 0; i < 3; ++i) w_attn("map.pt2pt_layers." + std::to_string(i), true);
+    w_head("map.token_predict_head", 128, MAP_TOKEN_SIZE);
+    w_mlp_emb("map.token_emb", MAP_TOKEN_DIM);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -162,6 +170,13 @@ struct infgen_engine {
     float *tok_tab = nullptr, *grid_tab = nullptr;      // [3][V+2][128], [G+1][128]
     AttnW t[6], m[6], a[6];
     AttnW occ2sa[3], pt2sa[3], a2sa[3];                 // insertion stage (agent_decoder.py:235-247)
+    // map encoder (map_decoder.py:70-130)
+    AttnW mp[3];
+    FourierW f_pp;                                      // r_pt2pt_emb
+    MlpEmbW e_map_tok;
+    MlpHeadW h_map_tok;
+    float *map_tok_tab = nullptr;                       // [n_tokens][128] token_emb(traj_src)
+    int map_n_tokens = 0, map_P = 0;                    // vocabulary size; tokens of the last infgen_map_encode
     FourierW f_ps, f_as;                                // r_pt2sa_emb, r_a2sa_emb
     MlpHeadW h_seed_state, h_seed_type, h_seed_shape, h_seed_pos, h_seed_heading, h_seed_offset, h_occ_embed,
         h_ag_occ, h_pt_occ;
@@ -535,10 +550,10 @@ static int enqueue_embed_rows(infgen_engine *e, const int *row_lo) {
 // the launch boundary.  with_edges=false: history columns that receive no edges (prefill).
 // node-packed copies of the 18 motion layers (node.cuh): every Linear cut into contiguous 128-column blocks
 static int build_node_weights(infgen_engine *e) {
-    CK(cudaMalloc(&e->np_blob, (size_t)18 * np::FLOATS * sizeof(float)));
-    AttnW *stacks[3] = {e->t, e->m, e->a};
-    for (int s = 0; s < 3; ++s)
-        for (int i = 0; i < 6; ++i) {
+    CK(cudaMalloc(&e->np_blob, (size_t)21 * np::FLOATS * sizeof(float)));
+    AttnW *stacks[4] = {e->t, e->m, e->a, e->mp};
+    for (int s = 0; s < 4; ++s)
+        for (int i = 0; i < (s < 3 ? 6 : 3); ++i) {
             AttnW &w = stacks[s][i];
             float *d = e->np_blob + (size_t)(s * 6 + i) * np::FLOATS;
             auto pack = [&](const float *src, int off, int K4, int N) {
@@ -549,7 +564,7 @@ static int build_node_weights(infgen_engine *e) {
             pack(w.w_qs, np::QS, 32, 256); pack(w.w_kv, np::KV, 32, 256);
             CKL();
             w.npk = d;
-            static const char *names[3] = {"t_attn_layers.", "pt2a_attn_layers.", "a2a_attn_layers."};
+            static const char *names[4] = {"t_attn_layers.", "pt2a_attn_layers.", "a2a_attn_layers.", "map.pt2pt_layers."};
             e->npk[std::string(names[s]) + std::to_string(i)] = d;
         }
     return 0;
@@ -1253,6 +1268,10 @@ int32_t infgen_create(const infgen_config *cfg, const float *weights, int64_t n_
     e->h_occ_embed = make_head(e, "seed_agent_occ_embed", cfg->grid_size, 128);
     e->h_ag_occ = make_head(e, "grid_agent_occ_head", 128, cfg->grid_size);
     e->h_pt_occ = make_head(e, "grid_pt_occ_head", 128, cfg->grid_size);
+    for (int i = 0; i < 3; ++i) e->mp[i] = make_attn(e, "map.pt2pt_layers." + std::to_string(i), true);
+    e->f_pp = make_fourier(e, "map.r_pt2pt_emb", 3);
+    e->e_map_tok = make_mlp_emb(e, "map.token_emb");
+    e->h_map_tok = make_head(e, "map.token_predict_head", 128, MAP_TOKEN_SIZE);
     // kernels that need more than 48 KB of dynamic shared memory
     CK(cudaFuncSetAttribute(k_layer<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LayerSmem<4>::BYTES));
     CK(cudaFuncSetAttribute(k_layer<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LayerSmem<8>::BYTES));
@@ -1297,7 +1316,7 @@ int32_t infgen_destroy(infgen_engine *e) {
     cudaFree(e->blob); cudaFree(e->cs_blob); cudaFree(e->grid_cells); cudaFree(e->vocab); cudaFree(e->tok_tab); cudaFree(e->grid_tab);
     cudaFree(e->d_err); cudaFree(e->seed_feat);
     for (float *p : e->wimgs) cudaFree(p);
-    cudaFree(e->np_blob); cudaFree(e->t_dim_table);
+    cudaFree(e->np_blob); cudaFree(e->t_dim_table); cudaFree(e->map_tok_tab);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->side_stream) cudaStreamDestroy(e->side_stream);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
@@ -1409,7 +1428,14 @@ int32_t infgen_load_scenes(infgen_engine *e, const infgen_scene_batch *b, int32_
     if (P > 0) {
         CK(cudaMemcpyAsync(d_pt_pos, b->pt_pos, (size_t)P * 2 * sizeof(float), k, st));
         CK(cudaMemcpyAsync(d_pt_ori, b->pt_ori, (size_t)P * sizeof(float), k, st));
-        CK(cudaMemcpyAsync(d_x_pt, b->x_pt, (size_t)P * 128 * sizeof(float), k, st));
+        if (b->x_pt) {
+            CK(cudaMemcpyAsync(d_x_pt, b->x_pt, (size_t)P * 128 * sizeof(float), k, st));
+        } else {
+            // x_pt == NULL: the output of the engine's own map encoder (infgen_map_encode on the same tokens) stays in HBM
+            if (e->map_P != P || !e->bufs.count("map_x"))
+                return fail(INFGEN_ERR_STATE, "x_pt is NULL but infgen_map_encode has not run on these %d map tokens", P);
+            CK(cudaMemcpyAsync(d_x_pt, fbuf(e, "map_x"), (size_t)P * 128 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        }
     }
     s.n_rows = d_n_rows; s.ego_row = d_ego; s.scene_id = d_sid; s.type = d_type; s.pt_ptr = d_pt_ptr;
     s.pt_pos = d_pt_pos; s.pt_ori = d_pt_ori;
@@ -1719,6 +1745,116 @@ int32_t infgen_read(infgen_engine *e, const infgen_outputs *o, int32_t loc) {
     if (loc == INFGEN_HOST) {
         CK(cudaStreamSynchronize(st));
         RET(check_device_errors(e));
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// map encoder: InfGenMapDecoder.forward (map_decoder.py:70-130)
+// ---------------------------------------------------------------------------------------------------------------
+int32_t infgen_map_setup(infgen_engine *e, const float *traj_src, int32_t n_tokens) {
+    if (!e || !traj_src || n_tokens < 1) return fail(INFGEN_ERR_INVALID_ARG, "null argument");
+    cudaStream_t st = e->stream;
+    CK(cudaStreamSynchronize(st));
+    if (e->map_tok_tab) { CK(cudaFree(e->map_tok_tab)); e->map_tok_tab = nullptr; }
+    float *d_src = nullptr;
+    CK(cudaMalloc(&d_src, (size_t)n_tokens * MAP_TOKEN_DIM * sizeof(float)));
+    CK(cudaMalloc(&e->map_tok_tab, (size_t)n_tokens * 128 * sizeof(float)));
+    CK(cudaMemcpyAsync(d_src, traj_src, (size_t)n_tokens * MAP_TOKEN_DIM * sizeof(float), cudaMemcpyHostToDevice, st));
+    MlpEmbArgs ma;                            // token_emb over the whole vocabulary (map_decoder.py:79-80)
+    memset(&ma, 0, sizeof(ma));
+    ma.rows = flat_rows(n_tokens); ma.w = e->e_map_tok; ma.kin = MAP_TOKEN_DIM; ma.k4 = (MAP_TOKEN_DIM + 3) / 4;
+    ma.x = d_src; ma.x_ld = MAP_TOKEN_DIM; ma.out = e->map_tok_tab; ma.out_ld = 128;
+    RET(launch_mlp_embed(e, ma));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaFree(d_src));
+    e->map_n_tokens = n_tokens;
+    return 0;
+}
+
+int32_t infgen_map_encode(infgen_engine *e, const infgen_map_batch *b, int32_t loc, float *x_pt_out, float *logits_out) {
+    if (!e || !b) return fail(INFGEN_ERR_INVALID_ARG, "null argument");
+    if (!e->map_tok_tab) return fail(INFGEN_ERR_STATE, "infgen_map_setup has not run");
+    const int ns = b->n_scenes;
+    if (ns < 1 || b->pt_ptr[0] != 0) return fail(INFGEN_ERR_INVALID_ARG, "pt_ptr must start at 0");
+    const int P = b->pt_ptr[ns];
+    if (P < 1) return fail(INFGEN_ERR_INVALID_ARG, "no map tokens");
+    cudaStream_t st = e->stream;
+    const cudaMemcpyKind k = in_kind(loc);
+    MapState m;
+    memset(&m, 0, sizeof(m));
+    m.n_scenes = ns; m.P = P; m.r2 = b->pl2pl_radius * b->pl2pl_radius;
+    int *d_ptr, *d_type, *d_pl, *d_light, *d_tok, *d_scene;
+    float *d_pos, *d_ori, *x, *tmp;
+    RET(ensure_t(e, "map_pt_ptr", ns + 1, &d_ptr)); RET(ensure_t(e, "map_type", P, &d_type)); RET(ensure_t(e, "map_pl_type", P, &d_pl));
+    RET(ensure_t(e, "map_light", P, &d_light)); RET(ensure_t(e, "map_token_idx", P, &d_tok)); RET(ensure_t(e, "map_scene_of", P, &d_scene));
+    RET(ensure_t(e, "map_pos", (size_t)P * 2, &d_pos)); RET(ensure_t(e, "map_ori", P, &d_ori));
+    RET(ensure_t(e, "map_x", (size_t)P * 128, &x));
+    RET(ensure_t(e, "map_q", (size_t)P * 128, &tmp)); RET(ensure_t(e, "map_s", (size_t)P * 128, &tmp));
+    RET(ensure_t(e, "map_qr", (size_t)P * 1024, &tmp)); RET(ensure_t(e, "map_agg", (size_t)P * 128, &tmp));
+    RET(ensure_t(e, "map_ragg", (size_t)P * 1024, &tmp)); RET(ensure_t(e, "map_sal", (size_t)P * 8, &tmp));
+    RET(ensure_t(e, "map_kv", (size_t)P * 256, &tmp));
+    RET(ensure_t(e, "map_cnt", P, &m.cnt)); RET(ensure_t(e, "map_start", P, &m.start));
+    RET(ensure_t(e, "map_src", (size_t)P * MAP_STRIDE, &m.src)); RET(ensure_t(e, "map_raw", (size_t)P * MAP_STRIDE * 3, &m.raw));
+    RET(ensure_t(e, "map_rhat", (size_t)P * MAP_STRIDE * 128, &tmp));
+    { int *itmp; RET(ensure_t(e, "map_slots", (size_t)P * MAP_STRIDE + 4 + P, &itmp)); }
+    for (int i = 0; i < ns; ++i)
+        if (b->pt_ptr[i + 1] < b->pt_ptr[i]) return fail(INFGEN_ERR_INVALID_ARG, "pt_ptr must be non-decreasing");
+    CK(cudaMemcpyAsync(d_ptr, b->pt_ptr, (ns + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_pos, b->pt_pos, (size_t)P * 2 * sizeof(float), k, st));
+    CK(cudaMemcpyAsync(d_ori, b->pt_ori, (size_t)P * sizeof(float), k, st));
+    CK(cudaMemcpyAsync(d_type, b->type, (size_t)P * sizeof(int), k, st));
+    CK(cudaMemcpyAsync(d_pl, b->pl_type, (size_t)P * sizeof(int), k, st));
+    CK(cudaMemcpyAsync(d_light, b->light_type, (size_t)P * sizeof(int), k, st));
+    CK(cudaMemcpyAsync(d_tok, b->token_idx, (size_t)P * sizeof(int), k, st));
+    m.pt_ptr = d_ptr; m.pos = d_pos; m.ori = d_ori; m.type = d_type; m.pl_type = d_pl; m.light_type = d_light;
+    m.token_idx = d_tok; m.scene_of = d_scene;
+    k_map_scene_of<<<ns, 256, 0, st>>>(d_ptr, ns, d_scene);
+    CKL(); count_launch(e);
+    k_map_embed<<<(P + NWARP - 1) / NWARP, NT, 0, st>>>(m, e->map_tok_tab, W(e, "map.type_pt_emb"), W(e, "map.polygon_type_emb"),
+                                                       W(e, "map.light_pl_emb"), x);
+    CKL(); count_launch(e);
+    k_map_edges<<<(P + NWARP - 1) / NWARP, NT, 0, st>>>(m);
+    CKL(); count_launch(e);
+    // relative embedding of the edges (map_decoder.py:98-114), tensor-core path over a compact list of the valid slots
+    FourierArgs fj;
+    memset(&fj, 0, sizeof(fj));
+    fj.normalize = 1; fj.dim = 3; fj.n_slots = P * MAP_STRIDE; fj.cnt = m.cnt; fj.stride = MAP_STRIDE;
+    fj.raw = m.raw; fj.w = e->f_pp; fj.out = fbuf(e, "map_rhat");
+    if (e->fourier_tc) {
+        int *list = (int *)e->bufs["map_slots"].p, *n_list = list + (size_t)P * MAP_STRIDE;
+        k_slot_compact<<<1, 1024, 0, st>>>(m.cnt, P, MAP_STRIDE, list, n_list, n_list + 4);
+        CKL(); count_launch(e);
+        fj.slot_list = list; fj.n_list = n_list;
+    }
+    RET(launch_fourier(e, &fj, 1, KC_MISC));
+    // three pt2pt AttentionLayers (non-bipartite, :115-117) on the row-tile path
+    const RowSpace rows = flat_rows(P);
+    NodeBufs nb{x, fbuf(e, "map_q"), fbuf(e, "map_s"), fbuf(e, "map_qr"), fbuf(e, "map_agg"), fbuf(e, "map_ragg"), fbuf(e, "map_sal")};
+    float *kv = fbuf(e, "map_kv");
+    RET(launch_node(e, rows, nullptr, &e->mp[0], true, kv, false, nullptr, &nb));
+    for (int i = 0; i < 3; ++i) {
+        SubArgs g;
+        memset(&g, 0, sizeof(g));
+        g.has_attn = 1; g.has_pos = 1; g.kv = kv; g.cnt = m.cnt; g.start = m.start; g.src = m.src; g.rhat = fbuf(e, "map_rhat");
+        RET(launch_attn(e, rows, g, &nb));
+        RET(launch_node(e, rows, &e->mp[i], i < 2 ? &e->mp[i + 1] : nullptr, true, kv, false, nullptr, &nb));
+    }
+    e->map_P = P;
+    if (x_pt_out) CK(cudaMemcpyAsync(x_pt_out, x, (size_t)P * 128 * sizeof(float), out_kind(loc), st));
+    if (logits_out) {                                  // token_predict_head of every token (the caller selects pt_pred_mask)
+        float *lg;
+        RET(ensure_t(e, "map_logits", (size_t)P * MAP_TOKEN_SIZE, &lg));
+        MlpLayerArgs la;
+        memset(&la, 0, sizeof(la));
+        la.n = P; la.x = x; la.w = e->h_map_tok; la.out = lg;
+        k_mlp_layer<<<dim3((P + HM - 1) / HM, la.w.n_pad / 128, 1), NT_S, MLP_LAYER_SMEM, st>>>(la);
+        CKL(); count_launch(e);
+        CK(cudaMemcpyAsync(logits_out, lg, (size_t)P * MAP_TOKEN_SIZE * sizeof(float), out_kind(loc), st));
+    }
+    if (loc == INFGEN_HOST) {
+        CK(cudaStreamSynchronize(st));
+        RET(check_ftc_watchdog());
     }
     return 0;
 }

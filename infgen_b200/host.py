@@ -34,7 +34,7 @@ class SceneHost:
     shape: np.ndarray           # [A, 3] f32
     pt_pos: np.ndarray          # [P, 2]
     pt_ori: np.ndarray          # [P]
-    x_pt: np.ndarray            # [P, 128]
+    x_pt: Optional[np.ndarray]  # [P, 128]; None: produced by the engine's own map encoder, stays in HBM
     # kept for the output dict
     agent_id: torch.Tensor
     valid_mask: torch.Tensor
@@ -122,7 +122,7 @@ def prepare_scene(data: Dict, map_enc: Dict, cfg: DecoderConfig) -> SceneHost:
         pos_hist=f32(pos[:, :HC]), head_hist=f32(head[:, :HC]), state_hist=i32(hstate), token_hist=i32(token[:, :HC]),
         grid_hist=i32(grid[:, :HC]), tsrc_hist=u8(tsrc), interact_hist=u8(interact_mask), type=i32(type_a),
         shape=f32(shape[:, nh - 1]), pt_pos=pt_pos if pt_pos.dtype == np.float32 else f32(pt_pos), pt_ori=f32(_np(data['pt_token']['orientation'])),
-        x_pt=f32(_np(map_enc['x_pt'])),
+        x_pt=f32(_np(map_enc['x_pt'])) if map_enc is not None else None,
         agent_id=tt(sel(_np(ag['id'])).copy()), valid_mask=tt(valid), gt_traj=tt(sel(position)[:, nh:, :2]),
         pred_shape=tt(f32(shape[:, HC - 1]).copy()), pos0=tt(f32(sel(position)[:, 0, :2]).copy()),
         head0=tt(f32(sel(_np(ag['heading']))[:, 0]).copy()), hist_state_full=tt(np.ascontiguousarray(state[:, :HC], dtype=np.int64)))
@@ -179,7 +179,8 @@ class HostBatch:
         self.pt_ptr = buf((ns + 1,), torch.int32)
         self.pt_pos = buf((self.p_alloc, 2), torch.float32)
         self.pt_ori = buf((self.p_alloc,), torch.float32)
-        self.x_pt = buf((self.p_alloc, 128), torch.float32)
+        self.has_x_pt = all(s.x_pt is not None for s in scenes)
+        self.x_pt = buf((self.p_alloc if self.has_x_pt else 1, 128), torch.float32)
         # result buffers
         NR = max(5 * S, 1)
         self.out_pos = buf((R, T, 2), torch.float32)
@@ -206,6 +207,7 @@ class HostBatch:
         scenes are no larger than the ones it was grown for.)"""
         most = max(s.n_rows for s in scenes)
         return (len(scenes) == self.n_scenes and all(s.n_cols == self.T and s.n_iters == self.S for s in scenes)
+                and all(s.x_pt is not None for s in scenes) == self.has_x_pt
                 and most + (16 if self.reserve else 0) <= self.cap
                 and (not self.auto_cap or self.cap <= (most + self.reserve + 3) // 4 * 4)
                 and sum(s.pt_pos.shape[0] for s in scenes) <= self.p_alloc)
@@ -228,13 +230,16 @@ class HostBatch:
             pp[:, 0] = s.pt_pos[:, 0]
             pp[:, 1] = s.pt_pos[:, 1]
             self.pt_ori[p0:p0 + np_] = torch.from_numpy(s.pt_ori)
-            self.x_pt[p0:p0 + np_] = torch.from_numpy(s.x_pt)
+            if self.has_x_pt:
+                self.x_pt[p0:p0 + np_] = torch.from_numpy(s.x_pt)
             p0 += np_
 
     def h2d_bytes(self) -> int:
         names = ('n_rows', 'ego_row', 'scene_id', 'pos_hist', 'head_hist', 'state_hist', 'token_hist', 'grid_hist',
                  'tsrc_hist', 'interact_hist', 'type', 'shape', 'pt_ptr', 'pt_pos', 'pt_ori', 'x_pt')
         tot = sum(getattr(self, n).numel() * getattr(self, n).element_size() for n in names)
+        if not self.has_x_pt:
+            return tot - self.x_pt.numel() * 4 - (self.p_alloc - self.P) * (2 + 1) * 4
         return tot - (self.p_alloc - self.P) * (2 + 1 + 128) * 4          # only P map tokens are copied
 
     def d2h_bytes(self) -> int:
@@ -257,7 +262,7 @@ class DeviceBatch:
 
     def __init__(self, hb: HostBatch, device):
         for k in ('n_scenes', 'cap', 'T', 'S', 'R', 'P', 'p_alloc', 'n_rows', 'ego_row', 'scene_id', 'pt_ptr',
-                  'insertion', 'reserve'):
+                  'insertion', 'reserve', 'has_x_pt'):
             setattr(self, k, getattr(hb, k))
         if hb.insertion:
             for k in INS_OUT_NAMES:

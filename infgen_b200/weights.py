@@ -300,17 +300,37 @@ def packed_tensors(sd: Dict[str, torch.Tensor]) -> Dict[str, np.ndarray]:
     return out
 
 
-def pack_state_dict(sd: Dict[str, torch.Tensor], lib) -> np.ndarray:
+def packed_map_tensors(map_sd: Dict[str, torch.Tensor]) -> Dict[str, np.ndarray]:
+    """Packed tensors of the map encoder (`InfGenMapDecoder.state_dict()` names, map_decoder.py:46-64); library names
+    carry the prefix `map.`."""
+    sd = {f'map.{k}': v for k, v in map_sd.items()}
+    out: Dict[str, np.ndarray] = {}
+    for k in ('type_pt_emb', 'polygon_type_emb', 'light_pl_emb'):
+        out[f'map.{k}'] = _np(sd[f'map.{k}.weight']).reshape(-1)
+    _pack_fourier(out, sd, 'map.r_pt2pt_emb', 3)
+    for i in range(3):
+        _pack_attention(out, sd, f'map.pt2pt_layers.{i}', True)
+    _pack_mlp_layer(out, sd, 'map.token_predict_head')
+    _pack_mlp_embedding(out, sd, 'map.token_emb')
+    return out
+
+
+def pack_state_dict(sd: Dict[str, torch.Tensor], lib, map_sd: Dict[str, torch.Tensor] = None) -> np.ndarray:
     """One float32 blob in the layout `lib` (libinfgen_b200.so) reports; raises if a tensor is missing or mis-sized.
 
     `sd` uses the reference's `InfGenAgentDecoder.state_dict()` names (a full-model checkpoint's
-    `encoder.agent_encoder.` prefix is stripped by the caller).
+    `encoder.agent_encoder.` prefix is stripped by the caller), `map_sd` the names of `InfGenMapDecoder.state_dict()`
+    (`encoder.map_encoder.`).  Either may be None: an engine that only serves the other module keeps zeros there.
     """
-    tensors = packed_tensors(sd)
+    tensors = packed_tensors(sd) if sd is not None else {}
+    if map_sd is not None:
+        tensors.update(packed_map_tensors(map_sd))
     blob = np.zeros(int(lib.infgen_weight_blob_floats()), dtype=np.float32)
     n = lib.infgen_weight_count()
     for i in range(n):
         name = lib.infgen_weight_name(i).decode()
+        if (name.startswith('map.') and map_sd is None) or (not name.startswith('map.') and sd is None):
+            continue                               # the module this engine does not serve
         if name not in tensors:
             raise KeyError(f'library expects packed tensor {name!r} that the packer did not produce')
         arr = np.ascontiguousarray(tensors[name], dtype=np.float32).reshape(-1)

@@ -18,7 +18,7 @@ def kl(lst, ind=''):
 
 
 kl(d.get('roofline_kernels'))
-for n in ('motion_only', 'configs2', 'configs4_one_gpu'):
+for n in ('motion_only', 'map_encoder', 'configs2', 'configs4_one_gpu'):
     e = d.get(n)
     if not e:
         continue
