@@ -161,7 +161,10 @@ struct infgen_engine {
     std::unordered_map<std::string, FourierW> fourier_cache;
     std::vector<float *> wimgs;                         // FourierEmbedding tensor-core weight images (fourier_tc.cuh)
     std::unordered_map<std::string, const float *> npk;   // layer prefix -> node-packed copy
-    float *np_blob = nullptr;                           // node-packed motion layers (node.cuh), [18][np::FLOATS]
+    float *np_blob = nullptr;                           // node-packed motion + map layers (node.cuh), [21][np::FLOATS]
+    float *vrf_blob = nullptr;                          // their folded to_v_r tables, [21][vrf::FLOATS]
+    std::unordered_map<std::string, const float *> vrfs;
+    int attn_ctas = 296;                                // persistent k_attn CTAs: 2 per SM
     bool node_mma = false;                              // k_node GEMMs on mma.sync 3xTF32 (INFGEN_NODE_GEMM=mma)
     int layer_path = 0;                                 // 0 auto, 1 cluster kernels only, 2 row-tile (k_attn + k_node) only
     bool fourier_tc = true;                             // INFGEN_FOURIER=ffma selects the FFMA row-tile kernel instead
@@ -238,6 +241,8 @@ static AttnW make_attn(infgen_engine *e, const std::string &p, bool has_pos) {
     if (it != e->cs.end()) { w.cs_post = it->second.first; w.cs_pre = it->second.second; }
     auto nt = e->npk.find(p);
     if (nt != e->npk.end()) w.npk = nt->second;
+    auto vt = e->vrfs.find(p);
+    if (vt != e->vrfs.end()) w.vrf = vt->second;
     return w;
 }
 
@@ -550,55 +555,78 @@ static int enqueue_embed_rows(infgen_engine *e, const int *row_lo) {
 // the launch boundary.  with_edges=false: history columns that receive no edges (prefill).
 // node-packed copies of the 18 motion layers (node.cuh): every Linear cut into contiguous 128-column blocks
 static int build_node_weights(infgen_engine *e) {
-    CK(cudaMalloc(&e->np_blob, (size_t)21 * np::FLOATS * sizeof(float)));
-    AttnW *stacks[4] = {e->t, e->m, e->a, e->mp};
-    for (int s = 0; s < 4; ++s)
+    CK(cudaMalloc(&e->np_blob, (size_t)30 * np::FLOATS * sizeof(float)));
+    CK(cudaMalloc(&e->vrf_blob, (size_t)21 * vrf::FLOATS * sizeof(float)));
+    {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        e->attn_ctas = 2 * sms;
+    }
+    // motion stacks and the map encoder (k_attn + k_node), then the seed stacks of the insertion stage (k_node only: the
+    // agents' edge-less pass of large batches)
+    AttnW *stacks[7] = {e->t, e->m, e->a, e->mp, e->occ2sa, e->pt2sa, e->a2sa};
+    for (int s = 0; s < 7; ++s)
         for (int i = 0; i < (s < 3 ? 6 : 3); ++i) {
             AttnW &w = stacks[s][i];
-            float *d = e->np_blob + (size_t)(s * 6 + i) * np::FLOATS;
+            float *d = e->np_blob + (size_t)(s < 4 ? s * 6 + i : 21 + (s - 4) * 3 + i) * np::FLOATS;
             auto pack = [&](const float *src, int off, int K4, int N) {
                 k_node_pack<<<(K4 * N + 255) / 256, 256, 0, e->stream>>>(src, d + off, K4, N);
             };
-            pack(w.w_vr, np::VR, 32, 128); pack(w.w_g, np::G, 64, 128); pack(w.w_out, np::OUT, 32, 128);
+            if (w.has_pos) pack(w.w_vr, np::VR, 32, 128);
+            pack(w.w_g, np::G, 64, 128); pack(w.w_out, np::OUT, 32, 128);
             pack(w.w_ff1, np::FF1, 32, 512); pack(w.w_ff2, np::FF2, 128, 128);
             pack(w.w_qs, np::QS, 32, 256); pack(w.w_kv, np::KV, 32, 256);
             CKL();
             w.npk = d;
-            static const char *names[4] = {"t_attn_layers.", "pt2a_attn_layers.", "a2a_attn_layers.", "map.pt2pt_layers."};
+            static const char *names[7] = {"t_attn_layers.", "pt2a_attn_layers.", "a2a_attn_layers.", "map.pt2pt_layers.",
+                                           "occ2sa_attn_layers.", "pt2sa_attn_layers.", "a2sa_attn_layers."};
             e->npk[std::string(names[s]) + std::to_string(i)] = d;
+            if (s < 4) {
+                float *vf = e->vrf_blob + (size_t)(s * 6 + i) * vrf::FLOATS;
+                k_vr_fold_pack<<<1, 128, 0, e->stream>>>(w.w_vr, w.ln_r_g, w.ln_r_b, w.b_vr, vf);
+                CKL();
+                w.vrf = vf;
+                e->vrfs[std::string(names[s]) + std::to_string(i)] = vf;
+            }
         }
     return 0;
 }
 struct NodeBufs {              // hand-over buffers of the row-tile path
-    float *x, *q, *s, *qr, *agg, *ragg, *sal;
+    float *x, *q, *s, *qr, *agg;
 };
 static NodeBufs scene_node_bufs(infgen_engine *e) {
-    return NodeBufs{fbuf(e, "x"), fbuf(e, "q"), fbuf(e, "s"), fbuf(e, "qr"), fbuf(e, "agg"), fbuf(e, "ragg"), fbuf(e, "sal")};
+    return NodeBufs{fbuf(e, "x"), fbuf(e, "q"), fbuf(e, "s"), fbuf(e, "qr"), fbuf(e, "agg")};
 }
-static int launch_attn(infgen_engine *e, const RowSpace &rows, const SubArgs &sub, const NodeBufs *nb = nullptr) {
+// edge attention of layer `lw` (its folded to_v_r table) over `rows`
+static int launch_attn(infgen_engine *e, const RowSpace &rows, const SubArgs &sub, const AttnW &lw, const NodeBufs *nb = nullptr) {
     const NodeBufs b = nb ? *nb : scene_node_bufs(e);
     AttnArgs a;
     memset(&a, 0, sizeof(a));
     a.rows = rows; a.sub = sub; a.q = b.q; a.qr = b.qr;
-    a.agg = b.agg; a.ragg = b.ragg; a.sal = b.sal;
+    a.agg = b.agg; a.vrf = sub.has_pos ? lw.vrf : nullptr;
+    if (sub.has_pos && !lw.vrf) return fail(INFGEN_ERR_STATE, "layer has no folded to_v_r table for the row-tile path");
     ProfScope ps(e, KC_ATTN);
-    k_attn<<<(rows.n_total + AW - 1) / AW, AW * 32, ATTN_SMEM, e->stream>>>(a);
+    // (the kernel deals the ACTIVE rows over its warps; rows.n_total only bounds the useful grid)
+    const int upper = rows.cap ? std::min(rows.n_total, e->n_rows_sum + 10 * e->n_scenes * std::max(e->S, 1)) : rows.n_total;
+    const int ctas = std::max(1, std::min(e->attn_ctas, (upper + ATTN_WARPS - 1) / ATTN_WARPS));
+    k_attn<<<ctas, ATTN_WARPS * 32, ATTN_SMEM, e->stream>>>(a);
     CKL(); count_launch(e);
     return 0;
 }
 // finish layer `lw` (NULL: nothing to finish) and project the inputs of layer `pw` (NULL: none)
 static int launch_node(infgen_engine *e, const RowSpace &rows, const AttnW *lw, const AttnW *pw, bool pre_kv, float *kv_out,
-                       bool kv_ring, float *trace_out, const NodeBufs *nb = nullptr) {
+                       bool kv_ring, float *trace_out, const NodeBufs *nb = nullptr, bool edgeless = false, int cls = KC_NODE) {
     const NodeBufs b = nb ? *nb : scene_node_bufs(e);
     NodeArgs a;
     memset(&a, 0, sizeof(a));
-    a.rows = rows; a.x = b.x; a.agg = b.agg; a.ragg = b.ragg; a.sal = b.sal;
+    a.rows = rows; a.x = b.x; a.agg = b.agg;
     a.q = b.q; a.s = b.s; a.qr = b.qr;
     if (lw) { a.w_post = lw->npk; a.lw = *lw; }
     if (pw) { a.w_pre = pw->npk; a.pw = *pw; }
     a.pre_kv = pre_kv ? 1 : 0; a.kv_out = kv_out; a.kv_ring = kv_ring ? 1 : 0; a.col_add = 0; a.ring = RING;
-    a.col_ptr = e->st.col; a.trace_out = trace_out;
-    ProfScope ps(e, KC_NODE);
+    a.col_ptr = e->st.col; a.trace_out = trace_out; a.edgeless = edgeless ? 1 : 0;
+    ProfScope ps(e, cls);
     if (e->node_mma) k_node<true><<<(rows.n_total + NM - 1) / NM, NT_S, NodeSmem::BYTES, e->stream>>>(a);
     else k_node<false><<<(rows.n_total + NM - 1) / NM, NT_S, NodeSmem::BYTES, e->stream>>>(a);
     CKL(); count_launch(e);
@@ -631,11 +659,11 @@ static int enqueue_layers(infgen_engine *e, bool with_edges, int trace_iter) {
             g.rhat = fbuf(e, "rhat_a");
             float *trace = (trace_iter >= 0 && e->cfg.trace) ? fbuf(e, "trace_layer_out") + ((size_t)trace_iter * 6 + i) * R * 128
                                                              : nullptr;
-            RET(launch_attn(e, rows, t));
+            RET(launch_attn(e, rows, t, e->t[i]));
             RET(launch_node(e, rows, &e->t[i], &e->m[i], false, nullptr, false, nullptr));
-            RET(launch_attn(e, rows, m));
+            RET(launch_attn(e, rows, m, e->m[i]));
             RET(launch_node(e, rows, &e->m[i], &e->a[i], true, kva, false, nullptr));
-            RET(launch_attn(e, rows, g));
+            RET(launch_attn(e, rows, g, e->a[i]));
             RET(launch_node(e, rows, &e->a[i], i < 5 ? &e->t[i + 1] : nullptr, true, kv_t + (size_t)(i + 1) * kv_t_layer, true, trace));
         }
         return 0;
@@ -690,6 +718,36 @@ static int enqueue_layers(infgen_engine *e, bool with_edges, int trace_iter) {
 // ---------------------------------------------------------------------------------------------------------------
 // every active row >= row_lo through a stack of layers WITHOUT edges, keeping the K|V rows of the non-bipartite ones
 static int enqueue_edgeless(infgen_engine *e, const int *row_lo, float *x, bool seed_stack, bool new_only = false) {
+    if (!new_only && (e->R + 7) / 8 > MAX_CLUSTERS && e->layer_path != 1) {
+        // more than one wave of clusters: the row-tile kernel, one launch per layer (finish layer i, project layer i + 1)
+        RowSpace rows = scene_rows(e);
+        rows.row_lo = row_lo;
+        // (the two stacks run concurrently on two streams: each has its own skip-projection hand-over buffer)
+        NodeBufs nb{x, fbuf(e, "q"), fbuf(e, seed_stack ? "s" : "s_ha"), fbuf(e, "qr"), fbuf(e, "zero")};
+        const size_t kvl = (size_t)e->R * 256;
+        std::vector<const AttnW *> chain;
+        std::vector<float *> kv_of;                      // K|V destination of chain[i]'s projections (NULL: none)
+        if (seed_stack) {
+            for (int i = 0; i < 3; ++i) {
+                chain.push_back(&e->occ2sa[i]); kv_of.push_back(nullptr);
+                chain.push_back(&e->pt2sa[i]); kv_of.push_back(nullptr);
+                if (i == 2) { chain.push_back(&e->a2sa[i]); kv_of.push_back(fbuf(e, "kv_sa") + i * kvl); break; }
+                chain.push_back(&e->a2sa[i]); kv_of.push_back(fbuf(e, "kv_sa") + i * kvl);
+            }
+        } else {
+            for (int i = 0; i < 3; ++i) {
+                chain.push_back(&e->m[i]); kv_of.push_back(nullptr);
+                chain.push_back(&e->a[i]); kv_of.push_back(fbuf(e, "kv_ha") + i * kvl);
+            }
+        }
+        // the last layer of either chain only contributes its K|V projection (its output is never used)
+        const int n = (int)chain.size();
+        RET(launch_node(e, rows, nullptr, chain[0], kv_of[0] != nullptr, kv_of[0], false, nullptr, &nb, true, KC_INS_LAYER_AGENTS));
+        for (int i = 0; i + 1 < n; ++i)
+            RET(launch_node(e, rows, chain[i], chain[i + 1], kv_of[i + 1] != nullptr, kv_of[i + 1], false, nullptr, &nb, true,
+                            KC_INS_LAYER_AGENTS));
+        return 0;
+    }
     LayerArgs la;
     memset(&la, 0, sizeof(la));
     la.rows = new_only ? new_rows(e) : scene_rows(e);
@@ -757,14 +815,16 @@ static int enqueue_insertion_begin(infgen_engine *e) {
         k_ins_begin<<<ns, NT, 0, st>>>(s, q);
     }
     CKL(); count_launch(e);
-    // agents through the seed stack without edges -> K|V of the a2sa layers
+    // Every row through the two edge-less stacks of the stage -> the K|V rows later passes attend to: the seed stack
+    // (3 x {occ2sa, pt2sa, a2sa}: K|V of the a2sa layers) on the engine stream, and on the side stream the relative
+    // embeddings of the map -> seed and agent -> seed edges (the seed pose is the ego pose for every pass of the iteration;
+    // rows appended by a pass add their own edge) and the heading stack (motion layers 0..2 without edges: K|V of a2a for
+    // the heading stage of appended rows)
     {
         ProfScope ps(e, KC_INSERT);
-        k_copy_new_rows<<<R, 128, 0, st>>>(s, nullptr, fbuf(e, "x"), fbuf(e, "x_sa"));
+        k_copy_new_rows2<<<ns, 128, 0, st>>>(s, nullptr, fbuf(e, "x"), fbuf(e, "x_sa"), fbuf(e, "x_ha"));
     }
     CKL(); count_launch(e);
-    // relative embeddings of the map -> seed and agent -> seed edges (the seed pose is the ego pose for every pass of the
-    // iteration; rows appended by a pass add their own edge), concurrently with the agents' edge-less stack
     RET(side_fork(e, [&]() -> int {
         FourierArgs fj[2];
         memset(fj, 0, sizeof(fj));
@@ -772,7 +832,8 @@ static int enqueue_insertion_begin(infgen_engine *e) {
         fj[0].raw = q.ps_raw; fj[0].w = e->f_ps; fj[0].out = fbuf(e, "rhat_ps");
         fj[1].normalize = 1; fj[1].dim = 3; fj[1].n_slots = ns * q.as_stride; fj[1].cnt = q.as_cnt; fj[1].stride = q.as_stride;
         fj[1].raw = q.as_raw; fj[1].w = e->f_as; fj[1].out = fbuf(e, "rhat_as");
-        return launch_fourier(e, fj, 2, KC_INS_FOURIER);
+        RET(launch_fourier(e, fj, 2, KC_INS_FOURIER));
+        return enqueue_edgeless(e, nullptr, fbuf(e, "x_ha"), false);
     }));
     RET(enqueue_edgeless(e, nullptr, fbuf(e, "x_sa"), true));
     return side_join(e);
@@ -854,15 +915,6 @@ static int enqueue_heading_stage(infgen_engine *e) {
     const int ns = e->n_scenes, R = e->R;
     cudaStream_t st = e->stream;
     float *x = fbuf(e, "x"), *x_sa = fbuf(e, "x_sa"), *x_ha = fbuf(e, "x_ha");
-    // K|V of every row for the heading stack (motion layers 0..2 without edges): all rows on the first heading stage of
-    // the iteration (ha_lo = 0), none afterwards (k_new_edges raises ha_lo; appended rows are added at the end)
-    {
-        ProfScope ps(e, KC_INSERT);
-        k_copy_new_rows<<<R, 128, 0, st>>>(s, q.ha_lo, x, x_ha);
-    }
-    CKL(); count_launch(e);
-    // (concurrently with the embedding / edges of the new row; k_head_finalize raises ha_lo after the join)
-    RET(side_fork(e, [&]() -> int { return enqueue_edgeless(e, q.ha_lo, x_ha, false); }));
     // categorical embedding row of the new agent: type_a_emb[type] + shape_emb(shape)
     MlpEmbArgs ma;
     memset(&ma, 0, sizeof(ma));
@@ -887,7 +939,6 @@ static int enqueue_heading_stage(infgen_engine *e) {
     hj[1].normalize = 1; hj[1].dim = 3; hj[1].n_slots = ns * NEW_AGENT_MAX; hj[1].cnt = q.ha_cnt_s; hj[1].stride = NEW_AGENT_MAX;
     hj[1].raw = q.ha_raw; hj[1].w = e->f_a; hj[1].out = fbuf(e, "rhat_ha");
     RET(launch_fourier(e, hj, 2, KC_INS_FOURIER));
-    RET(side_join(e));
     {   // the new rows through 3 x {pt2a, a2a} with their 10 m neighbourhoods
         LayerArgs la;
         memset(&la, 0, sizeof(la));
@@ -1316,7 +1367,7 @@ int32_t infgen_destroy(infgen_engine *e) {
     cudaFree(e->blob); cudaFree(e->cs_blob); cudaFree(e->grid_cells); cudaFree(e->vocab); cudaFree(e->tok_tab); cudaFree(e->grid_tab);
     cudaFree(e->d_err); cudaFree(e->seed_feat);
     for (float *p : e->wimgs) cudaFree(p);
-    cudaFree(e->np_blob); cudaFree(e->t_dim_table); cudaFree(e->map_tok_tab);
+    cudaFree(e->np_blob); cudaFree(e->vrf_blob); cudaFree(e->t_dim_table); cudaFree(e->map_tok_tab);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->side_stream) cudaStreamDestroy(e->side_stream);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
@@ -1467,7 +1518,6 @@ int32_t infgen_load_scenes(infgen_engine *e, const infgen_scene_batch *b, int32_
     float *tmp;
     RET(ensure_t(e, "x", (size_t)R * 128, &tmp)); RET(ensure_t(e, "q", (size_t)R * 128, &tmp)); RET(ensure_t(e, "s", (size_t)R * 128, &tmp));
     RET(ensure_t(e, "qr", (size_t)R * 1024, &tmp)); RET(ensure_t(e, "agg", (size_t)R * 128, &tmp));
-    RET(ensure_t(e, "ragg", (size_t)R * 1024, &tmp)); RET(ensure_t(e, "sal", (size_t)R * 8, &tmp));
     RET(ensure_t(e, "zero", (size_t)R * 1024, &tmp)); RET(ensure_t(e, "xa", (size_t)R * 128, &tmp));
     RET(ensure_t(e, "kv_t", (size_t)6 * R * RING * 256, &tmp)); RET(ensure_t(e, "kv_a", (size_t)2 * R * 256, &tmp));
     { unsigned *gb; RET(ensure_t(e, "grid_bar", 4, &gb)); }
@@ -1526,6 +1576,7 @@ int32_t infgen_load_scenes(infgen_engine *e, const infgen_scene_batch *b, int32_
         RET(ensure_t(e, "o_ag_occ", nso * G, &q.o_ag_occ)); RET(ensure_t(e, "o_pt_occ", nso * G, &q.o_pt_occ));
         RET(ensure_t(e, "o_occ_gt", nso * G, &q.o_occ_gt));
         RET(ensure_t(e, "x_sa", (size_t)R * 128, &tmp)); RET(ensure_t(e, "x_ha", (size_t)R * 128, &tmp));
+        RET(ensure_t(e, "s_ha", (size_t)R * 128, &tmp));
         RET(ensure_t(e, "kv_sa", (size_t)3 * R * 256, &tmp)); RET(ensure_t(e, "kv_ha", (size_t)3 * R * 256, &tmp));
         RET(ensure_t(e, "kv_ms", (size_t)3 * std::max(P, 1) * 256, &tmp));
         RET(ensure_t(e, "rhat_ps", (size_t)ns * SEED_MAP_MAX * 128, &tmp)); RET(ensure_t(e, "rhat_as", (size_t)ns * q.as_stride * 128, &tmp));
@@ -1792,7 +1843,6 @@ int32_t infgen_map_encode(infgen_engine *e, const infgen_map_batch *b, int32_t l
     RET(ensure_t(e, "map_x", (size_t)P * 128, &x));
     RET(ensure_t(e, "map_q", (size_t)P * 128, &tmp)); RET(ensure_t(e, "map_s", (size_t)P * 128, &tmp));
     RET(ensure_t(e, "map_qr", (size_t)P * 1024, &tmp)); RET(ensure_t(e, "map_agg", (size_t)P * 128, &tmp));
-    RET(ensure_t(e, "map_ragg", (size_t)P * 1024, &tmp)); RET(ensure_t(e, "map_sal", (size_t)P * 8, &tmp));
     RET(ensure_t(e, "map_kv", (size_t)P * 256, &tmp));
     RET(ensure_t(e, "map_cnt", P, &m.cnt)); RET(ensure_t(e, "map_start", P, &m.start));
     RET(ensure_t(e, "map_src", (size_t)P * MAP_STRIDE, &m.src)); RET(ensure_t(e, "map_raw", (size_t)P * MAP_STRIDE * 3, &m.raw));
@@ -1830,14 +1880,14 @@ int32_t infgen_map_encode(infgen_engine *e, const infgen_map_batch *b, int32_t l
     RET(launch_fourier(e, &fj, 1, KC_MISC));
     // three pt2pt AttentionLayers (non-bipartite, :115-117) on the row-tile path
     const RowSpace rows = flat_rows(P);
-    NodeBufs nb{x, fbuf(e, "map_q"), fbuf(e, "map_s"), fbuf(e, "map_qr"), fbuf(e, "map_agg"), fbuf(e, "map_ragg"), fbuf(e, "map_sal")};
+    NodeBufs nb{x, fbuf(e, "map_q"), fbuf(e, "map_s"), fbuf(e, "map_qr"), fbuf(e, "map_agg")};
     float *kv = fbuf(e, "map_kv");
     RET(launch_node(e, rows, nullptr, &e->mp[0], true, kv, false, nullptr, &nb));
     for (int i = 0; i < 3; ++i) {
         SubArgs g;
         memset(&g, 0, sizeof(g));
         g.has_attn = 1; g.has_pos = 1; g.kv = kv; g.cnt = m.cnt; g.start = m.start; g.src = m.src; g.rhat = fbuf(e, "map_rhat");
-        RET(launch_attn(e, rows, g, &nb));
+        RET(launch_attn(e, rows, g, e->mp[i], &nb));
         RET(launch_node(e, rows, &e->mp[i], i < 2 ? &e->mp[i + 1] : nullptr, true, kv, false, nullptr, &nb));
     }
     e->map_P = P;
@@ -1982,9 +2032,8 @@ int32_t infgen_op_attention_layer(infgen_engine *e, const char *layer, const flo
     if (!d_x || !d_out || !d_kv || !d_src) return fail(INFGEN_ERR_CUDA, "temporary allocation failed");
     if (e->layer_path == 2 && w.npk) {
         // row-tile path (node.cuh): projections -> k_attn -> k_node, on a copy of x
-        NodeBufs nb{d_out, d_q, d_s, d_qr, tmp.alloc<float>((size_t)n_dst * 128), tmp.alloc<float>((size_t)n_dst * 1024),
-                    tmp.alloc<float>((size_t)n_dst * 8)};
-        if (!nb.agg || !nb.ragg || !nb.sal) return fail(INFGEN_ERR_CUDA, "temporary allocation failed");
+        NodeBufs nb{d_out, d_q, d_s, d_qr, tmp.alloc<float>((size_t)n_dst * 128)};
+        if (!nb.agg) return fail(INFGEN_ERR_CUDA, "temporary allocation failed");
         CK(cudaMemcpyAsync(d_out, d_x, (size_t)n_dst * 128 * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
         const RowSpace rows = flat_rows(n_dst);
         RET(launch_node(e, rows, nullptr, &w, !bip, d_kv, false, nullptr, &nb));
@@ -1999,7 +2048,7 @@ int32_t infgen_op_attention_layer(infgen_engine *e, const char *layer, const flo
         SubArgs g;
         memset(&g, 0, sizeof(g));
         g.has_attn = 1; g.has_pos = has_pos ? 1 : 0; g.kv = d_kv; g.cnt = d_cnt; g.start = d_start; g.src = d_src; g.rhat = d_rhat;
-        RET(launch_attn(e, rows, g, &nb));
+        RET(launch_attn(e, rows, g, w, &nb));
         RET(launch_node(e, rows, &w, nullptr, false, nullptr, false, nullptr, &nb));
         CK(cudaStreamSynchronize(e->stream));
         CK(cudaMemcpy(out, d_out, (size_t)n_dst * 128 * sizeof(float), cudaMemcpyDeviceToHost));

@@ -658,7 +658,6 @@ __global__ void __launch_bounds__(NT) k_head_finalize(const HeadFinalArgs a) {
     const int b = blockIdx.x, col = *s.col, T = s.T;
     const int tid = threadIdx.x;
     const int i_new = q.new_row[b];
-    if (tid == 0) q.ha_lo[b] = 1 << 30;                   // the heading-stack K|V rows of the old rows exist from now on
     if (i_new < 0) return;
     const int r = b * s.cap + i_new, re = b * s.cap + s.ego_row[b];
     if (tid < 128) sx[tid] = a.x[(size_t)r * 128 + tid];
@@ -726,7 +725,7 @@ __global__ void k_copy_new_rows(const DecState s, const int *row_lo, const float
 // the same for the rows appended by the last pass, into two destinations: one block per scene
 __global__ void k_copy_new_rows2(const DecState s, const int *row_lo, const float *src, float *dst0, float *dst1) {
     const int b = blockIdx.x;
-    for (int i = row_lo[b]; i < s.n_rows[b]; ++i) {
+    for (int i = row_lo ? row_lo[b] : 0; i < s.n_rows[b]; ++i) {
         const size_t o = (size_t)(b * s.cap + i) * 128 + threadIdx.x;
         const float v = src[o];
         dst0[o] = v; dst1[o] = v;

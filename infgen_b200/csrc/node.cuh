@@ -50,8 +50,32 @@ struct AttnArgs {
     RowSpace rows;
     SubArgs sub;               // kv, cnt, start, stride, src, rhat, has_attn, has_pos
     const float *q, *qr;       // [R][128], [R][8][128]
-    float *agg, *ragg, *sal;   // [R][128], [R][8][128], [R][8]
+    float *agg;                // [R][128] OUT: the attention output of the row INCLUDING the folded relative value term,
+                               //   agg2 = sum_e a_e v_j + Wvr (g_r * sum_e a_e rhat_e + b_r * sal) + bvr * sal   (ops.cuh algebra)
+    const float *vrf;          // the layer's folded to_v_r table (vrf::FLOATS floats, k_vr_fold_pack); NULL when !has_pos
 };
+// folded to_v_r of one layer, in the access order of the k_attn epilogue:
+//   W[((h * 4 + i) * 4 + j4) * 32 + lane][c] = g_r[4 lane + i] * Wvr[4 lane + i][16 h + 4 j4 + c]     (16,384 floats)
+//   C[n] = sum_k b_r[k] Wvr[k][n] + bvr[n]                                                               (128 floats)
+namespace vrf {
+constexpr int W = 0, C = 16384, FLOATS = 16384 + 128;
+}
+// w_vr: packed [32 k4][128 n][4]
+__global__ void __launch_bounds__(128) k_vr_fold_pack(const float *__restrict__ w_vr, const float *__restrict__ g_r,
+                                                     const float *__restrict__ b_r, const float *__restrict__ b_vr,
+                                                     float *__restrict__ out) {
+    const int n = threadIdx.x;                                // output column
+    auto wvr = [&](int k, int col) { return w_vr[((size_t)(k >> 2) * 128 + col) * 4 + (k & 3)]; };
+    float c = b_vr[n];
+    for (int k = 0; k < 128; ++k) c = fmaf(b_r[k], wvr(k, n), c);
+    out[vrf::C + n] = c;
+    for (int idx = threadIdx.x; idx < 16384; idx += blockDim.x) {
+        const int cc = idx & 3, lane = (idx >> 2) & 31, j4 = (idx >> 7) & 3, i = (idx >> 9) & 3, h = idx >> 11;
+        const int k = 4 * lane + i, col = 16 * h + 4 * j4 + cc;
+        out[vrf::W + idx] = g_r[k] * wvr(k, col);
+    }
+}
+
 constexpr int AW = 4;          // warps (= rows) per CTA
 
 // One warp per destination row, ALL 8 heads: lane l holds float4 #l of every 128-vector, i.e. dims 4(l&3).. of head l>>2.
@@ -72,9 +96,11 @@ constexpr int AW = 4;          // warps (= rows) per CTA
 // being reduced.  The launch is a single wave of ~14 warps per SM, every warp walking its row's edges as one chain, so
 // the depth of this prefetch - not bandwidth - sets the kernel time (with two edges in flight in registers the warp
 // stalled on L2 latency for every pair: ncu long-scoreboard 2.4 of 6.7 stalled warps per issue).
-constexpr int ATTN_DEPTH = 8;
+constexpr int ATTN_DEPTH = 4;                          // (8 fits only one CTA per SM next to the 64 KB to_v_r table)
 constexpr int ATTN_SLOT = 384;                         // floats per edge slot
-constexpr size_t ATTN_SMEM = (size_t)AW * ATTN_DEPTH * ATTN_SLOT * sizeof(float);
+constexpr int ATTN_WARPS = 8;                          // warps per (persistent) CTA
+constexpr int ATTN_SMEM_FLOATS = vrf::FLOATS + ATTN_WARPS * ATTN_DEPTH * ATTN_SLOT;
+constexpr size_t ATTN_SMEM = (size_t)ATTN_SMEM_FLOATS * sizeof(float);        // 113 KB: two CTAs per SM
 __device__ __forceinline__ void cp_async16(float *dst_smem, const float *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
 }
@@ -82,132 +108,209 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(AW * 32) k_attn(const AttnArgs a) {
+// Persistent CTAs (2 per SM): the folded to_v_r table of the layer is brought into shared memory once per CTA, then every
+// warp walks rows warp_global, warp_global + n_warps, ...
+__global__ void __launch_bounds__(ATTN_WARPS * 32, 2) k_attn(const AttnArgs a) {
     extern __shared__ __align__(16) float smem_attn[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int r = blockIdx.x * AW + warp;
-    if (!a.rows.active(r)) return;
     const SubArgs &A = a.sub;
-    float *ring = smem_attn + (size_t)warp * ATTN_DEPTH * ATTN_SLOT + 4 * lane;
+    float *sW = smem_attn, *sC = smem_attn + vrf::C;
+    float *ring = smem_attn + vrf::FLOATS + (size_t)warp * ATTN_DEPTH * ATTN_SLOT + 4 * lane;
+    if (a.vrf) {
+        for (int i = threadIdx.x; i < vrf::FLOATS / 4; i += ATTN_WARPS * 32) st4(sW + 4 * i, ldg4(a.vrf + 4 * i));
+    }
+    __syncthreads();
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int n = A.has_attn ? A.cnt[r] : 0;
-    const int e0 = A.start ? A.start[r] : r * A.stride;
-    const float *rhb = A.rhat + (size_t)e0 * 128 + 4 * lane;
-    const float *kvb = A.kv + 4 * lane;
-    // source rows of the edges, 64 at a time in two registers (edge e of the row: lane e & 31 of word (e >> 5) & 1)
-    int src_w0 = lane < n ? A.src[e0 + lane] : 0;
-    int src_w1 = 32 + lane < n ? A.src[e0 + 32 + lane] : 0;
-    auto issue = [&](int e) {                                // edge e -> slot e % ATTN_DEPTH (all lanes; e < n)
-        const int s0 = __shfl_sync(0xffffffffu, src_w0, e & 31), s1 = __shfl_sync(0xffffffffu, src_w1, e & 31);
-        const int sj = (e & 32) ? s1 : s0;
-        float *d = ring + (e % ATTN_DEPTH) * ATTN_SLOT;
-        if (A.has_pos) cp_async16(d, rhb + (size_t)e * 128);
-        const float *p = kvb + (size_t)sj * 256;
-        cp_async16(d + 128, p);
-        cp_async16(d + 256, p + 128);
-    };
-    for (int e = 0; e < ATTN_DEPTH; ++e) {                   // prologue: one commit group per edge slot
-        if (e < n) issue(e);
-        cp_async_commit();
-    }
-    const float4 q4 = ld4(a.q + (size_t)r * 128 + 4 * lane);
-    float4 qr4[8], ra[8];
-#pragma unroll
-    for (int h = 0; h < 8; ++h) {
-        qr4[h] = A.has_pos ? ld4(a.qr + ((size_t)r * 8 + h) * 128 + 4 * lane) : z4;
-        ra[h] = z4;
-    }
-    float mx = -INFINITY, den = 0.f;                          // mx: softmax reference of this lane's head (one of its scores,
-    float4 av = z4;                                           //     at most ATTN_LAZY below the running maximum)
-    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
     constexpr float ATTN_LAZY = 8.0f;
-    // score of one edge for the head of this lane's group (all four lanes of the group hold it)
-    auto score = [&](const float4 rh, const float4 k) {
-        float pk = dot4(q4, k);
-        pk += __shfl_xor_sync(0xffffffffu, pk, 1);
-        pk += __shfl_xor_sync(0xffffffffu, pk, 2);
-        float v[8];
+    // the g-th ACTIVE row of the row space (rows of scene b: [b * cap, b * cap + n_rows[b])), -1 past the end: the warps
+    // deal the active rows round-robin, so a sparsely filled capacity row space does not unbalance them
+    auto active_row = [&](int g) -> int {
+        if (a.rows.cap == 0) return g < a.rows.n_total ? g : -1;
+        const int ns = a.rows.n_total / a.rows.cap;
+        int acc = 0;
+        for (int b0 = 0; b0 < ns; b0 += 32) {
+            const int nb = b0 + lane < ns ? a.rows.n_rows[b0 + lane] : 0;
+            int inc = nb;
 #pragma unroll
-        for (int h = 0; h < 8; ++h) v[h] = dot4(qr4[h], rh);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float recv = __shfl_xor_sync(0xffffffffu, b4 ? v[i] : v[i + 4], 16);
-            v[i] = (b4 ? v[i + 4] : v[i]) + recv;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += y;
+            }
+            const unsigned hit = __ballot_sync(0xffffffffu, g < acc + inc);
+            if (hit) {
+                const int l = __ffs(hit) - 1;
+                const int excl = __shfl_sync(0xffffffffu, inc - nb, l);
+                return (b0 + l) * a.rows.cap + (g - acc - excl);
+            }
+            acc += __shfl_sync(0xffffffffu, inc, 31);
         }
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const float recv = __shfl_xor_sync(0xffffffffu, b3 ? v[i] : v[i + 2], 8);
-            v[i] = (b3 ? v[i + 2] : v[i]) + recv;
-        }
-        {
-            const float recv = __shfl_xor_sync(0xffffffffu, b2 ? v[0] : v[1], 4);
-            v[0] = (b2 ? v[1] : v[0]) + recv;
-        }
-        float pr = v[0];
-        pr += __shfl_xor_sync(0xffffffffu, pr, 1);
-        pr += __shfl_xor_sync(0xffffffffu, pr, 2);
-        return (pr + pk) * 0.25f;                            // head_dim ** -0.5
+        return -1;
     };
-    for (int e = 0; e < n; e += 2) {
-        // edges e, e + 1 have landed when at most ATTN_DEPTH - 2 younger groups are pending
-        cp_async_wait<ATTN_DEPTH - 2>();
-        __syncwarp();
-        const bool two = e + 1 < n;
-        const float *d0 = ring + (e % ATTN_DEPTH) * ATTN_SLOT, *d1 = ring + ((e + 1) % ATTN_DEPTH) * ATTN_SLOT;
-        const float4 rh0 = A.has_pos ? ld4(d0) : z4, k0 = ld4(d0 + 128), v0 = ld4(d0 + 256);
-        float4 rh1 = z4, k1 = z4, v1 = z4;
-        if (two) { rh1 = A.has_pos ? ld4(d1) : z4; k1 = ld4(d1 + 128); v1 = ld4(d1 + 256); }
-        __syncwarp();                                        // every lane has read its slots: they may be refilled
-        // the next two edges of the ring (two commit groups, empty ones past the end keep the group count in step)
-        if ((e + ATTN_DEPTH & 63) == 0 && e + ATTN_DEPTH < n) {     // crossing into the next 64 edges: refill the source words
-            src_w0 = e + ATTN_DEPTH + lane < n ? A.src[e0 + e + ATTN_DEPTH + lane] : 0;
-            src_w1 = e + ATTN_DEPTH + 32 + lane < n ? A.src[e0 + e + ATTN_DEPTH + 32 + lane] : 0;
+    for (int g = blockIdx.x * ATTN_WARPS + warp;; g += gridDim.x * ATTN_WARPS) {
+        const int r = active_row(g);
+        if (r < 0) break;
+        const int n = A.has_attn ? A.cnt[r] : 0;
+        const int e0 = A.start ? A.start[r] : r * A.stride;
+        const float *rhb = A.rhat + (size_t)e0 * 128 + 4 * lane;
+        const float *kvb = A.kv + 4 * lane;
+        // source rows of the edges, 64 at a time in two registers (edge e of the row: lane e & 31 of word (e >> 5) & 1)
+        int src_w0 = lane < n ? A.src[e0 + lane] : 0;
+        int src_w1 = 32 + lane < n ? A.src[e0 + 32 + lane] : 0;
+        auto issue = [&](int e) {                            // edge e -> slot e % ATTN_DEPTH (all lanes; e < n)
+            const int s0 = __shfl_sync(0xffffffffu, src_w0, e & 31), s1 = __shfl_sync(0xffffffffu, src_w1, e & 31);
+            const int sj = (e & 32) ? s1 : s0;
+            float *d = ring + (e % ATTN_DEPTH) * ATTN_SLOT;
+            if (A.has_pos) cp_async16(d, rhb + (size_t)e * 128);
+            const float *p = kvb + (size_t)sj * 256;
+            cp_async16(d + 128, p);
+            cp_async16(d + 256, p + 128);
+        };
+        for (int e = 0; e < ATTN_DEPTH; ++e) {               // prologue: one commit group per edge slot
+            if (e < n) issue(e);
+            cp_async_commit();
         }
-        if (e + ATTN_DEPTH < n) issue(e + ATTN_DEPTH);
-        cp_async_commit();
-        if (e + ATTN_DEPTH + 1 < n) issue(e + ATTN_DEPTH + 1);
-        cp_async_commit();
-        // two edges per step: their score chains are independent
-        const float p0 = score(rh0, k0);
-        const float p1 = two ? score(rh1, k1) : -INFINITY;
-        const float pm = fmaxf(p0, p1);
-        if (__any_sync(0xffffffffu, pm > mx + ATTN_LAZY)) {
-            // some head's score left the window above its reference (always on a row's first edges): move the reference
-            // of the heads concerned and rescale their sums
-            const float mn = pm > mx + ATTN_LAZY ? pm : mx;
-            const float sc = expf(mx - mn);                  // 0 on the first edge, 1 for heads that keep their reference
-            den *= sc;
-            av.x *= sc; av.y *= sc; av.z *= sc; av.w *= sc;
-            mx = mn;
+        const float4 q4 = ld4(a.q + (size_t)r * 128 + 4 * lane);
+        float4 qr4[8], ra[8];
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+            qr4[h] = A.has_pos ? ld4(a.qr + ((size_t)r * 8 + h) * 128 + 4 * lane) : z4;
+            ra[h] = z4;
+        }
+        float mx = -INFINITY, den = 0.f;                      // mx: softmax reference of this lane's head (one of its scores,
+        float4 av = z4;                                       //     at most ATTN_LAZY below the running maximum)
+        // score of one edge for the head of this lane's group (all four lanes of the group hold it)
+        auto score = [&](const float4 rh, const float4 k) {
+            float pk = dot4(q4, k);
+            pk += __shfl_xor_sync(0xffffffffu, pk, 1);
+            pk += __shfl_xor_sync(0xffffffffu, pk, 2);
+            float v[8];
+#pragma unroll
+            for (int h = 0; h < 8; ++h) v[h] = dot4(qr4[h], rh);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float recv = __shfl_xor_sync(0xffffffffu, b4 ? v[i] : v[i + 4], 16);
+                v[i] = (b4 ? v[i + 4] : v[i]) + recv;
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const float recv = __shfl_xor_sync(0xffffffffu, b3 ? v[i] : v[i + 2], 8);
+                v[i] = (b3 ? v[i + 2] : v[i]) + recv;
+            }
+            {
+                const float recv = __shfl_xor_sync(0xffffffffu, b2 ? v[0] : v[1], 4);
+                v[0] = (b2 ? v[1] : v[0]) + recv;
+            }
+            float pr = v[0];
+            pr += __shfl_xor_sync(0xffffffffu, pr, 1);
+            pr += __shfl_xor_sync(0xffffffffu, pr, 2);
+            return (pr + pk) * 0.25f;                        // head_dim ** -0.5
+        };
+        for (int e = 0; e < n; e += 2) {
+            // edges e, e + 1 have landed when at most ATTN_DEPTH - 2 younger groups are pending
+            cp_async_wait<ATTN_DEPTH - 2>();
+            const bool two = e + 1 < n;
+            const float *d0 = ring + (e % ATTN_DEPTH) * ATTN_SLOT, *d1 = ring + ((e + 1) % ATTN_DEPTH) * ATTN_SLOT;
+            // (every lane reads back exactly the 16-byte pieces it copied itself: no cross-lane hazard on the ring)
+            const float4 rh0 = A.has_pos ? ld4(d0) : z4, k0 = ld4(d0 + 128), v0 = ld4(d0 + 256);
+            float4 rh1 = z4, k1 = z4, v1 = z4;
+            if (two) { rh1 = A.has_pos ? ld4(d1) : z4; k1 = ld4(d1 + 128); v1 = ld4(d1 + 256); }
+            // the next two edges of the ring (two commit groups; empty ones past the end keep the group count in step)
+            if (((e + ATTN_DEPTH) & 63) == 0 && e + ATTN_DEPTH < n) {     // crossing into the next 64 edges: refill the source words
+                src_w0 = e + ATTN_DEPTH + lane < n ? A.src[e0 + e + ATTN_DEPTH + lane] : 0;
+                src_w1 = e + ATTN_DEPTH + 32 + lane < n ? A.src[e0 + e + ATTN_DEPTH + 32 + lane] : 0;
+            }
+            if (e + ATTN_DEPTH < n) issue(e + ATTN_DEPTH);
+            cp_async_commit();
+            if (e + ATTN_DEPTH + 1 < n) issue(e + ATTN_DEPTH + 1);
+            cp_async_commit();
+            // two edges per step: their score chains are independent
+            const float p0 = score(rh0, k0);
+            const float p1 = two ? score(rh1, k1) : -INFINITY;
+            const float pm = fmaxf(p0, p1);
+            if (__any_sync(0xffffffffu, pm > mx + ATTN_LAZY)) {
+                // some head's score left the window above its reference (always on a row's first edges): move the
+                // reference of the heads concerned and rescale their sums
+                const float mn = pm > mx + ATTN_LAZY ? pm : mx;
+                const float sc = expf(mx - mn);              // 0 on the first edge, 1 for heads that keep their reference
+                den *= sc;
+                av.x *= sc; av.y *= sc; av.z *= sc; av.w *= sc;
+                mx = mn;
+                if (A.has_pos) {
+#pragma unroll
+                    for (int h = 0; h < 8; ++h) {
+                        const float sh = __shfl_sync(0xffffffffu, sc, 4 * h);
+                        ra[h].x *= sh; ra[h].y *= sh; ra[h].z *= sh; ra[h].w *= sh;
+                    }
+                }
+            }
+            const float w0 = expf(p0 - mx), w1 = expf(p1 - mx);   // w1 = 0 for an absent edge
+            den += w0 + w1;
+            av.x = fmaf(w0, v0.x, fmaf(w1, v1.x, av.x)); av.y = fmaf(w0, v0.y, fmaf(w1, v1.y, av.y));
+            av.z = fmaf(w0, v0.z, fmaf(w1, v1.z, av.z)); av.w = fmaf(w0, v0.w, fmaf(w1, v1.w, av.w));
             if (A.has_pos) {
 #pragma unroll
                 for (int h = 0; h < 8; ++h) {
-                    const float sh = __shfl_sync(0xffffffffu, sc, 4 * h);
-                    ra[h].x *= sh; ra[h].y *= sh; ra[h].z *= sh; ra[h].w *= sh;
+                    const float g0 = __shfl_sync(0xffffffffu, w0, 4 * h), g1 = __shfl_sync(0xffffffffu, w1, 4 * h);
+                    ra[h].x = fmaf(g0, rh0.x, fmaf(g1, rh1.x, ra[h].x)); ra[h].y = fmaf(g0, rh0.y, fmaf(g1, rh1.y, ra[h].y));
+                    ra[h].z = fmaf(g0, rh0.z, fmaf(g1, rh1.z, ra[h].z)); ra[h].w = fmaf(g0, rh0.w, fmaf(g1, rh1.w, ra[h].w));
                 }
             }
         }
-        const float w0 = expf(p0 - mx), w1 = expf(p1 - mx);   // w1 = 0 for an absent edge
-        den += w0 + w1;
-        av.x = fmaf(w0, v0.x, fmaf(w1, v1.x, av.x)); av.y = fmaf(w0, v0.y, fmaf(w1, v1.y, av.y));
-        av.z = fmaf(w0, v0.z, fmaf(w1, v1.z, av.z)); av.w = fmaf(w0, v0.w, fmaf(w1, v1.w, av.w));
-        if (A.has_pos) {
-#pragma unroll
+        cp_async_wait<0>();
+        const float inv = 1.0f / (den + 1e-16f);             // torch_geometric.utils.softmax denominator
+        float4 out = make_float4(av.x * inv, av.y * inv, av.z * inv, av.w * inv);
+        if (A.has_pos && a.vrf) {
+            // ---- folded relative value term: agg2[16h + j] += sum_k ragg_h[k] W'[k][16h + j] + C[16h + j] * sal_h ----------
+            // lane l holds ragg_h[4l .. 4l+3]: 16 partial products per head, reduce-scattered over the warp (column
+            // j = lane >> 1 ends up in lanes 2j, 2j + 1), staged through the warp's first ring slot (idle now)
+            float *sv = ring - 4 * lane;                     // [128] scratch
+            __syncwarp();
+#pragma unroll 1
             for (int h = 0; h < 8; ++h) {
-                const float g0 = __shfl_sync(0xffffffffu, w0, 4 * h), g1 = __shfl_sync(0xffffffffu, w1, 4 * h);
-                ra[h].x = fmaf(g0, rh0.x, fmaf(g1, rh1.x, ra[h].x)); ra[h].y = fmaf(g0, rh0.y, fmaf(g1, rh1.y, ra[h].y));
-                ra[h].z = fmaf(g0, rh0.z, fmaf(g1, rh1.z, ra[h].z)); ra[h].w = fmaf(g0, rh0.w, fmaf(g1, rh1.w, ra[h].w));
-            }
-        }
-    }
-    cp_async_wait<0>();
-    const float inv = 1.0f / (den + 1e-16f);                 // torch_geometric.utils.softmax denominator
-    st4(a.agg + (size_t)r * 128 + 4 * lane, make_float4(av.x * inv, av.y * inv, av.z * inv, av.w * inv));
-    if ((lane & 3) == 0) a.sal[(size_t)r * 8 + (lane >> 2)] = den * inv;
+                const float ih = __shfl_sync(0xffffffffu, inv, 4 * h);
+                const float rr[4] = {ra[h].x * ih, ra[h].y * ih, ra[h].z * ih, ra[h].w * ih};
+                float p[16];
 #pragma unroll
-    for (int h = 0; h < 8; ++h) {
-        const float ih = __shfl_sync(0xffffffffu, inv, 4 * h);
-        st4(a.ragg + ((size_t)r * 8 + h) * 128 + 4 * lane, make_float4(ra[h].x * ih, ra[h].y * ih, ra[h].z * ih, ra[h].w * ih));
+                for (int j = 0; j < 16; ++j) p[j] = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        const float4 w = ld4(sW + ((size_t)((h * 4 + i) * 4 + j4) * 32 + lane) * 4);
+                        p[4 * j4 + 0] = fmaf(rr[i], w.x, p[4 * j4 + 0]); p[4 * j4 + 1] = fmaf(rr[i], w.y, p[4 * j4 + 1]);
+                        p[4 * j4 + 2] = fmaf(rr[i], w.z, p[4 * j4 + 2]); p[4 * j4 + 3] = fmaf(rr[i], w.w, p[4 * j4 + 3]);
+                    }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float recv = __shfl_xor_sync(0xffffffffu, b4 ? p[i] : p[i + 8], 16);
+                    p[i] = (b4 ? p[i + 8] : p[i]) + recv;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float recv = __shfl_xor_sync(0xffffffffu, b3 ? p[i] : p[i + 4], 8);
+                    p[i] = (b3 ? p[i + 4] : p[i]) + recv;
+                }
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const float recv = __shfl_xor_sync(0xffffffffu, b2 ? p[i] : p[i + 2], 4);
+                    p[i] = (b2 ? p[i + 2] : p[i]) + recv;
+                }
+                {
+                    const float recv = __shfl_xor_sync(0xffffffffu, b1 ? p[0] : p[1], 2);
+                    p[0] = (b1 ? p[1] : p[0]) + recv;
+                }
+                p[0] += __shfl_xor_sync(0xffffffffu, p[0], 1);
+                // column index of the value this lane ends up with: bit 3 = b4, bit 2 = b3, bit 1 = b2, bit 0 = b1
+                if ((lane & 1) == 0) sv[16 * h + (lane >> 1)] = p[0];
+            }
+            __syncwarp();
+            const float4 vr = ld4(sv + 4 * lane), c4 = ld4(sC + 4 * lane);
+            const float sal = den * inv;                     // of this lane's head (lane >> 2)
+            out.x += vr.x + c4.x * sal; out.y += vr.y + c4.y * sal; out.z += vr.z + c4.z * sal; out.w += vr.w + c4.w * sal;
+            __syncwarp();                                    // the scratch is a ring slot again from the next row on
+        }
+        st4(a.agg + (size_t)r * 128 + 4 * lane, out);
     }
 }
 
@@ -215,13 +318,15 @@ __global__ void __launch_bounds__(AW * 32) k_attn(const AttnArgs a) {
 struct NodeArgs {
     RowSpace rows;
     float *x;                  // [R][128] residual stream, updated in place
-    const float *agg, *ragg, *sal;
+    const float *agg;          // [R][128] attention output of k_attn (relative value term folded in)
     float *q, *s, *qr;         // hand-over: s of the post layer is read, q / s / qr of the pre layer are written
     const float *w_post;       // node-packed weights of the layer being finished (NULL: only the pre half runs)
     AttnW lw;                  // its bias / LayerNorm vectors
     const float *w_pre;        // node-packed weights of the following layer (NULL: none)
     AttnW pw;
     int pre_kv;                // also project k|v of these rows (non-bipartite layers)
+    int edgeless;              // rows without incoming edges (insertion stage: K|V of source-only rows): agg = 0, and the
+                               // pre half only produces s (and k|v): no q, no relative queries
     float *kv_out;
     int kv_ring, col_add, ring;
     const int *col_ptr;
@@ -277,7 +382,7 @@ __global__ void __launch_bounds__(NT_S) k_node(const NodeArgs a) {
         if (lane < NODE_STAGES) {
             WSeg segs[2];
             int n = 0;
-            if (post) segs[n++] = WSeg{a.w_post + (has_pos ? np::VR : np::G), has_pos ? 384 : 352, 512};
+            if (post) segs[n++] = WSeg{a.w_post + np::G, 352, 512};      // (to_v_r is folded into k_attn)
             if (pre) segs[n++] = WSeg{a.w_pre + np::QS, a.pre_kv ? 128 : 64, 512};
             ws_produce(wsm, segs, n);
         }
@@ -302,32 +407,14 @@ __global__ void __launch_bounds__(NT_S) k_node(const NodeArgs a) {
         st4(sx + m * LD1 + 4 * lane, x);
         if (post) {
             st4(ss + m * LD1 + 4 * lane, act ? ld4(a.s + (size_t)r * 128 + 4 * lane) : z4);
-            st4(scat + m * LD2 + 4 * lane, act ? ld4(a.agg + (size_t)r * 128 + 4 * lane) : z4);
+            st4(scat + m * LD2 + 4 * lane, (act && !a.edgeless) ? ld4(a.agg + (size_t)r * 128 + 4 * lane) : z4);
             st4(scat + m * LD2 + 128 + 4 * lane, ln128(x, a.lw.ln_dst_g, a.lw.ln_dst_b, lane));
-            if (lane < 8) ssal[m * 8 + lane] = act ? a.sal[(size_t)r * 8 + lane] : 0.f;
-            if (has_pos) {
-                const float4 g = ldg4(a.lw.ln_r_g + 4 * lane), b = ldg4(a.lw.ln_r_b + 4 * lane);
-#pragma unroll
-                for (int h = 0; h < 8; ++h) {
-                    // ragg' = g_r * ragg + b_r * sal (the LayerNorm affine of attn_prenorm_r folded after the sum)
-                    const float4 v = act ? ld4(a.ragg + ((size_t)r * 8 + h) * 128 + 4 * lane) : z4;
-                    const float sa = act ? a.sal[(size_t)r * 8 + h] : 0.f;
-                    st4(sr + (h * NM + m) * LD1 + 4 * lane, make_float4(fmaf(g.x, v.x, b.x * sa), fmaf(g.y, v.y, b.y * sa),
-                                                                         fmaf(g.z, v.z, b.z * sa), fmaf(g.w, v.w, b.w * sa)));
-                }
-            }
         }
     }
     csync();
     NODE_STAMP(1);
     if (post) {
-        // ---- agg2 = agg + Wvr ragg' + bvr * sal: warp w owns columns 16w.. = head w, so its A operand is ragg'[w] ---------
-        if (has_pos) {
-            stream_gemm<NM>(ws, sr + warp * NM * LD1, LD1, 32, [&](int m, int n, float v) {
-                scat[m * LD2 + n] += v + __ldg(a.lw.b_vr + n) * ssal[m * 8 + (n >> 4)];
-            });
-            csync();
-        }
+        // (agg arrives from k_attn with the relative value term already folded in: agg2 of ops.cuh)
         NODE_STAMP(2);
         // ---- gate: g = sigmoid(Wg [agg2 | xd] + bg);  u = agg2 + g * (s - agg2) ---------------------------------------------
         gemm(scat, LD2, 64, [&](int m, int n, float v) {
@@ -384,7 +471,7 @@ __global__ void __launch_bounds__(NT_S) k_node(const NodeArgs a) {
     gemm(su, LD1, 32, [&](int m, int n, float v) {
         v += __ldg(a.pw.b_qs + n);
         sq[m * LD1 + n] = v;
-        if (active(m)) a.q[(size_t)(row0 + m) * 128 + n] = v;
+        if (active(m) && !a.edgeless) a.q[(size_t)(row0 + m) * 128 + n] = v;
     });
     gemm(su, LD1, 32, [&](int m, int n, float v) {
         if (active(m)) a.s[(size_t)(row0 + m) * 128 + n] = v + __ldg(a.pw.b_qs + 128 + n);
@@ -393,7 +480,8 @@ __global__ void __launch_bounds__(NT_S) k_node(const NodeArgs a) {
     // slice of Wkr for the relative-query fold below (thread = head `warp`, channels 4 lane ..): requested now, so that
     // the loads are in flight during the k/v projections
     float4 wk[16];
-    if (a.pw.has_pos) {
+    const bool fold = a.pw.has_pos && !a.edgeless;
+    if (fold) {
 #pragma unroll
         for (int d = 0; d < 16; ++d) wk[d] = ldg4(a.pw.w_kr + (size_t)(16 * warp + d) * 128 + 4 * lane);
     }
@@ -414,7 +502,7 @@ __global__ void __launch_bounds__(NT_S) k_node(const NodeArgs a) {
     // thread = (head h = warp, channels 4 lane .. 4 lane + 3): the 16 x 4 slice of Wkr stays in registers and a row costs
     // 4 broadcast LDS.128 of q for 64 FMA (one thread per channel needed 4 LDS.128 per 16 FMA and was LSU-bound:
     // 13-15 k cycles for 262 k MAC, now ~3 k)
-    if (a.pw.has_pos) {
+    if (fold) {
         const int h = warp;
         const float4 g4 = ldg4(a.pw.ln_r_g + 4 * lane);
         for (int m = 0; m < NM; ++m) {

@@ -34,6 +34,7 @@ struct AttnW {                 // one AttentionLayer, pointers into the packed w
     int has_pos;               // has_pos_emb
     const float *cs_post, *cs_pre;   // cluster-sliced chunks of this layer (layer.cuh), [8][FLOATS] each
     const float *npk;                // node-packed copy (node.cuh), NULL when the layer has none
+    const float *vrf;                // folded to_v_r table for the k_attn epilogue (node.cuh vrf::), NULL when the layer has none
 };
 
 struct FourierW {              // one FourierEmbedding
