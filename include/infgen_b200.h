@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define INFGEN_ABI_VERSION 5
+#define INFGEN_ABI_VERSION 6
 
 typedef enum {
     INFGEN_OK = 0,
@@ -114,11 +114,18 @@ typedef struct {
     int32_t *n_rows_final;        /* [n_scenes] rows of each scene after the rollout (appended agents included) */
     int32_t *pred_type;           /* [R] predicted type of appended rows (:1955) */
     float *pred_shape;            /* [R][3] predicted shape of appended rows (:1956) */
-    float *state_prob_seed;       /* [n_scenes][11][S]        next_state_prob_seed (:2105) */
-    float *pos_prob_seed;         /* [n_scenes][11][S][grid]  next_pos_rel_prob_seed (:2104) */
-    float *agent_occ_seed;        /* [n_scenes][11][S][grid]  grid_agent_occ_seed (:2102) */
-    float *pt_occ_seed;           /* [n_scenes][11][S][grid]  grid_pt_occ_seed (:2103) */
-    float *occ_gt_seed;           /* [n_scenes][11][S][grid]  grid_agent_occ_gt_seed (:2101) */
+    /* Wire format of the insertion records.  The reference returns five dense tensors
+     * next_state_prob_seed [11][S], next_pos_rel_prob_seed / grid_agent_occ_seed / grid_pt_occ_seed /
+     * grid_agent_occ_gt_seed [11][S][grid] (agent_decoder.py:2099-2113, 2376-2386) that are zero except at [slot][t] of
+     * every insertion (slot = 1..10 within decode iteration t): 5.5 MB per 16-iteration scene, 104 MB per 150 s scene.
+     * Here one record per APPENDED ROW travels instead, indexed by the row (rows [n_rows[b], n_rows_final[b]) of scene b;
+     * nothing else is written or copied), and the host mirror scatters them into the dense tensors. */
+    int32_t *rec_meta;            /* [R][2]    (decode iteration t, slot) of the insertion that appended the row */
+    float *rec_state_prob;        /* [R]       next_state_prob_seed[slot][t] (:2105) */
+    float *rec_pos_prob;          /* [R][grid] next_pos_rel_prob_seed[slot][t] (:2104) */
+    float *rec_agent_occ;         /* [R][grid] grid_agent_occ_seed[slot][t] (:2102) */
+    float *rec_pt_occ;            /* [R][grid] grid_pt_occ_seed[slot][t] (:2103) */
+    float *rec_occ_gt;            /* [R][grid] grid_agent_occ_gt_seed[slot][t] (:2101) */
 } infgen_outputs;
 
 /* ---- library ------------------------------------------------------------------------------------------- */
@@ -158,7 +165,8 @@ int32_t infgen_prefill(infgen_engine *e);
 int32_t infgen_step(infgen_engine *e, int32_t n_iters);
 /* prefill + all remaining iterations */
 int32_t infgen_rollout(infgen_engine *e);
-/* outputs (:2303-2389). Synchronises the stream when loc == INFGEN_HOST. */
+/* outputs (:2303-2389). Synchronises the stream when loc == INFGEN_HOST, and whenever insertion records are requested
+ * (their extent is read back first). */
 int32_t infgen_read(infgen_engine *e, const infgen_outputs *out, int32_t loc);
 int32_t infgen_iterations_done(infgen_engine *e);
 /* number of kernels this library launched (or replayed through graphs) since the engine was created */

@@ -9,7 +9,7 @@ import os
 from typing import Optional
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib', 'libinfgen_b200.so')
-ABI_VERSION = 5
+ABI_VERSION = 6
 HOST, DEVICE = 0, 1
 
 c_f32p = C.POINTER(C.c_float)
@@ -51,8 +51,9 @@ class Outputs(C.Structure):
     _fields_ = [
         ('pos', c_f32p), ('head', c_f32p), ('pred_traj', c_f32p), ('pred_head', c_f32p), ('pred_state', c_f32p),
         ('next_token', c_i32p), ('next_state', c_i32p), ('hist_traj', c_f32p), ('hist_head', c_f32p),
-        ('n_rows_final', c_i32p), ('pred_type', c_i32p), ('pred_shape', c_f32p), ('state_prob_seed', c_f32p),
-        ('pos_prob_seed', c_f32p), ('agent_occ_seed', c_f32p), ('pt_occ_seed', c_f32p), ('occ_gt_seed', c_f32p),
+        ('n_rows_final', c_i32p), ('pred_type', c_i32p), ('pred_shape', c_f32p), ('rec_meta', c_i32p),
+        ('rec_state_prob', c_f32p), ('rec_pos_prob', c_f32p), ('rec_agent_occ', c_f32p), ('rec_pt_occ', c_f32p),
+        ('rec_occ_gt', c_f32p),
     ]
 
 

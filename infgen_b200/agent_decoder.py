@@ -16,7 +16,7 @@ import torch
 from . import _capi
 from .config import DecoderConfig, HIDDEN, NUM_LAYERS, TOKEN_SIZE
 from .grid import PositionGrid
-from .host import HostBatch, SceneHost, assemble_outputs, prepare_scene
+from .host import DenseRecordPool, HostBatch, SceneHost, assemble_outputs, prepare_scene
 from .weights import pack_state_dict
 
 
@@ -74,6 +74,9 @@ class B200AgentDecoder:
         self._batch: Optional[HostBatch] = None
         self._scenes: Optional[Sequence[SceneHost]] = None
         self._host_cache: Optional[HostBatch] = None
+        # dense insertion tensors of the output dicts are recycled every `depth` calls (host.DenseRecordPool); None = fresh
+        # tensors per call
+        self.dense_pool: Optional[DenseRecordPool] = DenseRecordPool(depth=2)
 
     # ---- construction helpers ---------------------------------------------------------------------------------
     @classmethod
@@ -157,9 +160,9 @@ class B200AgentDecoder:
                 n_rows_final=_capi.i32p(b.out_n_rows))
             if b.insertion:
                 o.pred_type, o.pred_shape = _capi.i32p(b.out_pred_type), _capi.f32p(b.out_pred_shape)
-                o.state_prob_seed, o.pos_prob_seed = _capi.f32p(b.out_state_prob_seed), _capi.f32p(b.out_pos_prob_seed)
-                o.agent_occ_seed, o.pt_occ_seed = _capi.f32p(b.out_agent_occ_seed), _capi.f32p(b.out_pt_occ_seed)
-                o.occ_gt_seed = _capi.f32p(b.out_occ_gt_seed)
+                o.rec_meta, o.rec_state_prob = _capi.i32p(b.out_rec_meta), _capi.f32p(b.out_rec_state_prob)
+                o.rec_pos_prob, o.rec_agent_occ = _capi.f32p(b.out_rec_pos_prob), _capi.f32p(b.out_rec_agent_occ)
+                o.rec_pt_occ, o.rec_occ_gt = _capi.f32p(b.out_rec_pt_occ), _capi.f32p(b.out_rec_occ_gt)
         loc = _capi.DEVICE if getattr(b, 'on_device', False) else _capi.HOST
         _capi.check(self.lib.infgen_read(self._h, C.byref(o), loc))
 
@@ -237,7 +240,9 @@ class B200AgentDecoder:
                     raise
                 new_cap = min(max(2 * batch.cap, batch.cap + 64), (batch.max_rows + 3) // 4 * 4)
                 batch = self._host_cache = HostBatch(scenes, self.cfg, scene_ids, row_capacity=new_cap)
-        return assemble_outputs(batch, scenes, self.cfg)
+        if self.dense_pool is not None:
+            self.dense_pool.next_generation()
+        return assemble_outputs(batch, scenes, self.cfg, self.dense_pool)
 
     def inference(self, data: Dict, map_enc: Optional[Dict], motion_only: bool = False) -> Dict:
         """`InfGenAgentDecoder.inference(data, map_enc)` (agent_decoder.py:1605-2389)."""

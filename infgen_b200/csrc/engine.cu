@@ -195,6 +195,7 @@ struct infgen_engine {
     // scene batch
     bool loaded = false;
     int n_scenes = 0, cap = 0, T = 0, S = 0, R = 0, P = 0, n_rows_sum = 0, max_rows = 0;
+    std::vector<int> n_rows0;                           // rows of every scene at load time (appended rows follow them)
     int iters_done = 0, prefilled = 0;
     std::unordered_map<std::string, DevBuf> bufs;       // named device buffers (debug-readable)
     DecState st;
@@ -1434,6 +1435,7 @@ int32_t infgen_load_scenes(infgen_engine *e, const infgen_scene_batch *b, int32_
     if (b->pt_ptr[0] != 0 || P < 0) return fail(INFGEN_ERR_INVALID_ARG, "pt_ptr must start at 0");
     if (e->n_scenes != ns || e->cap != cap || e->T != T || e->S != S || e->P != P) drop_graph(e);
     e->n_scenes = ns; e->cap = cap; e->R = R; e->T = T; e->S = S; e->P = P; e->n_rows_sum = sum; e->max_rows = mx;
+    e->n_rows0.assign(b->n_rows, b->n_rows + ns);
     e->row_tile = (R + 3) / 4 <= MAX_CLUSTERS ? 4 : 8;
     e->iters_done = 0; e->prefilled = 0; e->forcing = false;
     const int W = e->cfg.window, MM = e->cfg.max_pl2a_neighbors, V = e->cfg.token_size;
@@ -1571,10 +1573,9 @@ int32_t infgen_load_scenes(infgen_engine *e, const infgen_scene_batch *b, int32_
         RET(ensure_t(e, "pt_occ_logits", (size_t)ns * SEED_ROW_STRIDE * G, &q.pt_occ_logits));
         RET(ensure_t(e, "ins_col", R, &q.ins_col)); RET(ensure_t(e, "pred_type", R, &q.pred_type));
         RET(ensure_t(e, "pred_shape", (size_t)R * 3, &q.pred_shape));
-        const size_t nso = (size_t)ns * SEED_SLOTS * std::max(S, 1);
-        RET(ensure_t(e, "o_state_prob", nso, &q.o_state_prob)); RET(ensure_t(e, "o_pos_prob", nso * G, &q.o_pos_prob));
-        RET(ensure_t(e, "o_ag_occ", nso * G, &q.o_ag_occ)); RET(ensure_t(e, "o_pt_occ", nso * G, &q.o_pt_occ));
-        RET(ensure_t(e, "o_occ_gt", nso * G, &q.o_occ_gt));
+        RET(ensure_t(e, "rec_meta", (size_t)R * 2, &q.rec_meta)); RET(ensure_t(e, "rec_state_prob", (size_t)R, &q.rec_state_prob));
+        RET(ensure_t(e, "rec_pos_prob", (size_t)R * G, &q.rec_pos_prob)); RET(ensure_t(e, "rec_ag_occ", (size_t)R * G, &q.rec_ag_occ));
+        RET(ensure_t(e, "rec_pt_occ", (size_t)R * G, &q.rec_pt_occ)); RET(ensure_t(e, "rec_occ_gt", (size_t)R * G, &q.rec_occ_gt));
         RET(ensure_t(e, "x_sa", (size_t)R * 128, &tmp)); RET(ensure_t(e, "x_ha", (size_t)R * 128, &tmp));
         RET(ensure_t(e, "s_ha", (size_t)R * 128, &tmp));
         RET(ensure_t(e, "kv_sa", (size_t)3 * R * 256, &tmp)); RET(ensure_t(e, "kv_ha", (size_t)3 * R * 256, &tmp));
@@ -1589,11 +1590,6 @@ int32_t infgen_load_scenes(infgen_engine *e, const infgen_scene_batch *b, int32_
         CK(cudaMemsetAsync(q.ins_col, 0xff, (size_t)R * sizeof(int), e->stream));
         CK(cudaMemsetAsync(q.pred_type, 0, (size_t)R * sizeof(int), e->stream));
         CK(cudaMemsetAsync(q.pred_shape, 0, (size_t)R * 3 * sizeof(float), e->stream));
-        CK(cudaMemsetAsync(q.o_state_prob, 0, nso * sizeof(float), e->stream));
-        CK(cudaMemsetAsync(q.o_pos_prob, 0, nso * G * sizeof(float), e->stream));
-        CK(cudaMemsetAsync(q.o_ag_occ, 0, nso * G * sizeof(float), e->stream));
-        CK(cudaMemsetAsync(q.o_pt_occ, 0, nso * G * sizeof(float), e->stream));
-        CK(cudaMemsetAsync(q.o_occ_gt, 0, nso * G * sizeof(float), e->stream));
         e->ins_ready = true;
     }
     if (memcmp(&old, &s, sizeof(s)) != 0) drop_graph(e);
@@ -1782,14 +1778,25 @@ int32_t infgen_read(infgen_engine *e, const infgen_outputs *o, int32_t loc) {
     if (o->n_rows_final) CK(cudaMemcpyAsync(o->n_rows_final, s.n_rows, ns * sizeof(int), k, st));
     if (e->ins_ready) {
         const InsState &q = e->ins;
-        const size_t nso = ns * SEED_SLOTS * (size_t)std::max(e->S, 1), G = e->cfg.grid_size;
+        const size_t G = e->cfg.grid_size;
         if (o->pred_type) CK(cudaMemcpyAsync(o->pred_type, q.pred_type, R * sizeof(int), k, st));
         if (o->pred_shape) CK(cudaMemcpyAsync(o->pred_shape, q.pred_shape, R * 3 * sizeof(float), k, st));
-        if (o->state_prob_seed) CK(cudaMemcpyAsync(o->state_prob_seed, q.o_state_prob, nso * sizeof(float), k, st));
-        if (o->pos_prob_seed) CK(cudaMemcpyAsync(o->pos_prob_seed, q.o_pos_prob, nso * G * sizeof(float), k, st));
-        if (o->agent_occ_seed) CK(cudaMemcpyAsync(o->agent_occ_seed, q.o_ag_occ, nso * G * sizeof(float), k, st));
-        if (o->pt_occ_seed) CK(cudaMemcpyAsync(o->pt_occ_seed, q.o_pt_occ, nso * G * sizeof(float), k, st));
-        if (o->occ_gt_seed) CK(cudaMemcpyAsync(o->occ_gt_seed, q.o_occ_gt, nso * G * sizeof(float), k, st));
+        // insertion records: only the rows each scene appended travel (include/infgen_b200.h, "wire format")
+        if (o->rec_meta || o->rec_state_prob || o->rec_pos_prob || o->rec_agent_occ || o->rec_pt_occ || o->rec_occ_gt) {
+            std::vector<int> nf(ns);
+            CK(cudaMemcpyAsync(nf.data(), s.n_rows, ns * sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            for (size_t b = 0; b < ns; ++b) {
+                const size_t r0 = b * e->cap + e->n_rows0[b], n = (size_t)std::max(0, nf[b] - e->n_rows0[b]);
+                if (!n) continue;
+                if (o->rec_meta) CK(cudaMemcpyAsync(o->rec_meta + r0 * 2, q.rec_meta + r0 * 2, n * 2 * sizeof(int), k, st));
+                if (o->rec_state_prob) CK(cudaMemcpyAsync(o->rec_state_prob + r0, q.rec_state_prob + r0, n * sizeof(float), k, st));
+                if (o->rec_pos_prob) CK(cudaMemcpyAsync(o->rec_pos_prob + r0 * G, q.rec_pos_prob + r0 * G, n * G * sizeof(float), k, st));
+                if (o->rec_agent_occ) CK(cudaMemcpyAsync(o->rec_agent_occ + r0 * G, q.rec_ag_occ + r0 * G, n * G * sizeof(float), k, st));
+                if (o->rec_pt_occ) CK(cudaMemcpyAsync(o->rec_pt_occ + r0 * G, q.rec_pt_occ + r0 * G, n * G * sizeof(float), k, st));
+                if (o->rec_occ_gt) CK(cudaMemcpyAsync(o->rec_occ_gt + r0 * G, q.rec_occ_gt + r0 * G, n * G * sizeof(float), k, st));
+            }
+        }
     }
     // results in host memory are complete when this returns, and so are the error checks; device-resident results are
     // asynchronous: errors of that rollout surface at infgen_synchronize

@@ -73,8 +73,11 @@ struct InsState {
     float *shape_rows;                 // [R+1][3] shape fed to shape_emb (row R = 0.1)
     int *pred_type;                    // [R]
     float *pred_shape;                 // [R][3]
-    // outputs [ns][SEED_SLOTS][S] (+[G])
-    float *o_state_prob, *o_pos_prob, *o_ag_occ, *o_pt_occ, *o_occ_gt;
+    // records of the insertions, one per appended row and indexed by its global row (the dense [11][S](+[G]) tensors the
+    // reference returns are all zero except for these; the host rebuilds them, see include/infgen_b200.h "wire format")
+    int *rec_meta;                     // [R][2]: decode iteration, slot (1..10) within the iteration
+    float *rec_state_prob;             // [R]
+    float *rec_pos_prob, *rec_ag_occ, *rec_pt_occ, *rec_occ_gt;   // [R][G]
     int *err;
 };
 
@@ -524,15 +527,16 @@ __device__ __forceinline__ void seed_decide_scene(const SeedDecideArgs &a) {
         // P(enter) of this query (:2105)
         const float m2 = fmaxf(s_small[0], s_small[1]);
         const float e0 = expf(s_small[0] - m2), e1 = expf(s_small[1] - m2);
-        q.o_state_prob[((size_t)b * SEED_SLOTS + n_new) * S + t] = e1 / (e0 + e1);
+        q.rec_state_prob[r] = e1 / (e0 + e1);
+        q.rec_meta[(size_t)r * 2] = t; q.rec_meta[(size_t)r * 2 + 1] = n_new;
     }
     // grid-sized records of this insertion (:2099-2104)
-    const size_t ob = (((size_t)b * SEED_SLOTS + n_new) * S + t) * G;
+    const size_t ob = (size_t)r * G;
     for (int g = tid; g < G; g += NT) {
-        q.o_pos_prob[ob + g] = expf(lg[g] - gmax) / den;
-        q.o_ag_occ[ob + g] = q.ag_occ_logits[(size_t)b * SEED_ROW_STRIDE * G + g];
-        q.o_pt_occ[ob + g] = q.pt_occ_logits[(size_t)b * SEED_ROW_STRIDE * G + g];
-        q.o_occ_gt[ob + g] = q.occ[(size_t)b * G + g];
+        q.rec_pos_prob[ob + g] = expf(lg[g] - gmax) / den;
+        q.rec_ag_occ[ob + g] = q.ag_occ_logits[(size_t)b * SEED_ROW_STRIDE * G + g];
+        q.rec_pt_occ[ob + g] = q.pt_occ_logits[(size_t)b * SEED_ROW_STRIDE * G + g];
+        q.rec_occ_gt[ob + g] = q.occ[(size_t)b * G + g];
     }
 }
 

@@ -197,9 +197,11 @@ class HostBatch:
             from .weights import GRID_SIZE
             self.out_pred_type = buf((R,), torch.int32)
             self.out_pred_shape = buf((R, 3), torch.float32)
-            self.out_state_prob_seed = buf((ns, 11, max(S, 1)), torch.float32)
-            for name in ('out_pos_prob_seed', 'out_agent_occ_seed', 'out_pt_occ_seed', 'out_occ_gt_seed'):
-                setattr(self, name, buf((ns, 11, max(S, 1), GRID_SIZE), torch.float32))
+            # insertion records, one per appended row (wire format of include/infgen_b200.h)
+            self.out_rec_meta = buf((R, 2), torch.int32)
+            self.out_rec_state_prob = buf((R,), torch.float32)
+            for name in ('out_rec_pos_prob', 'out_rec_agent_occ', 'out_rec_pt_occ', 'out_rec_occ_gt'):
+                setattr(self, name, buf((R, GRID_SIZE), torch.float32))
         self.fill(scenes, scene_ids)
 
     def fits(self, scenes: Sequence[SceneHost]) -> bool:
@@ -243,17 +245,25 @@ class HostBatch:
         return tot - (self.p_alloc - self.P) * (2 + 1 + 128) * 4          # only P map tokens are copied
 
     def d2h_bytes(self) -> int:
+        """Bytes `infgen_read` brings back for this batch (after a read: the insertion records of the appended rows
+        included)."""
         names = ('out_pos', 'out_head', 'out_pred_traj', 'out_pred_head', 'out_pred_state', 'out_next_token',
-                 'out_next_state', 'out_hist_traj', 'out_hist_head')
-        return sum(getattr(self, n).numel() * getattr(self, n).element_size() for n in names)
+                 'out_next_state', 'out_hist_traj', 'out_hist_head', 'out_n_rows')
+        tot = sum(getattr(self, n).numel() * getattr(self, n).element_size() for n in names)
+        if self.insertion:
+            from .weights import GRID_SIZE
+            tot += self.out_pred_type.numel() * 4 + self.out_pred_shape.numel() * 4
+            appended = int((self.out_n_rows - self.n_rows).clamp(min=0).sum())
+            tot += appended * (4 * GRID_SIZE + 3) * 4
+        return tot
 
 
 IN_NAMES = ('pos_hist', 'head_hist', 'state_hist', 'token_hist', 'grid_hist', 'tsrc_hist', 'interact_hist', 'type',
             'shape', 'pt_pos', 'pt_ori', 'x_pt')
 OUT_NAMES = ('out_pos', 'out_head', 'out_pred_traj', 'out_pred_head', 'out_pred_state', 'out_next_token',
              'out_next_state', 'out_hist_traj', 'out_hist_head', 'out_n_rows')
-INS_OUT_NAMES = ('out_pred_type', 'out_pred_shape', 'out_state_prob_seed', 'out_pos_prob_seed', 'out_agent_occ_seed',
-                 'out_pt_occ_seed', 'out_occ_gt_seed')
+INS_OUT_NAMES = ('out_pred_type', 'out_pred_shape', 'out_rec_meta', 'out_rec_state_prob', 'out_rec_pos_prob',
+                 'out_rec_agent_occ', 'out_rec_pt_occ', 'out_rec_occ_gt')
 
 
 class DeviceBatch:
@@ -272,6 +282,37 @@ class DeviceBatch:
         for k in OUT_NAMES:
             setattr(self, k, torch.zeros_like(getattr(hb, k), device=device))
         self.on_device = True
+
+
+class DenseRecordPool:
+    """Recycled dense [11, S, grid] tensors for the insertion outputs of the reference dict.
+
+    A rollout's dense insertion tensors (5.5 MB per 16-iteration scene, 104 MB per 150 s scene) are zero except for one
+    [grid] record per inserted agent.  Fresh zeroed memory costs a page fault per touched page (or a full memset), which
+    made the output dict the slowest part of a batched call; so the tensors come from a ring of `depth` generations that
+    are recycled: when a generation is reused, exactly the records written last time are zeroed again.  Consequence for
+    callers: the five insertion tensors returned by call k alias memory that call k + depth reuses - copy them to keep them
+    longer (the reference's consumer, `InfGen.validation_step` infgen.py:742-777, reads them at once)."""
+
+    def __init__(self, depth: int = 2):
+        self.depth = depth
+        self.gen = 0
+        self.slots: Dict[tuple, list] = {}          # (generation, scene position, S) -> [arrays, (slots, ts)]
+
+    def next_generation(self):
+        self.gen = (self.gen + 1) % self.depth
+
+    def get(self, pos: int, n_iters: int, grid: int):
+        key = (self.gen, pos, n_iters)
+        ent = self.slots.get(key)
+        if ent is None:
+            ent = self.slots[key] = [[np.zeros((11, n_iters, grid), dtype=np.float32) for _ in range(4)], None]
+        elif ent[1] is not None:
+            sl, ts = ent[1]
+            for a in ent[0]:
+                a[sl, ts] = 0.0
+            ent[1] = None
+        return ent
 
 
 _ZERO_SEED_CACHE: Dict[int, Dict[str, torch.Tensor]] = {}
@@ -295,7 +336,8 @@ def _zero_seed_records(n_iters: int) -> Dict[str, torch.Tensor]:
     return dict(rec)
 
 
-def assemble_outputs(batch: HostBatch, scenes: Sequence[SceneHost], cfg: DecoderConfig) -> List[Dict]:
+def assemble_outputs(batch: HostBatch, scenes: Sequence[SceneHost], cfg: DecoderConfig,
+                     pool: Optional[DenseRecordPool] = None) -> List[Dict]:
     """agent_decoder.py:2303-2389: the per-scene output dict (keys/dtypes/shapes of the reference).  Rows appended by the
     insertion stage follow the scene's own rows; history-derived fields cover the scene's own rows only, as in the
     reference (`num_init_agent`, :2310)."""
@@ -349,12 +391,28 @@ def assemble_outputs(batch: HostBatch, scenes: Sequence[SceneHost], cfg: Decoder
             'log_message': (f'Number of total inserted agents: {n - n0}' if n > n0 else 'No agents inserted!'),
         }
         if batch.insertion:
+            # dense tensors of the reference from the per-row insertion records: pages stay untouched (lazily zeroed) except
+            # where a record lands
+            from .weights import GRID_SIZE
+            ka, kb = r0 + n0, r0 + n
+            meta = batch.out_rec_meta[ka:kb].numpy()
+            ts, slots = meta[:, 0].copy(), meta[:, 1].copy()
+            if pool is not None:
+                ent = pool.get(b, s.n_iters, GRID_SIZE)
+                arrays = ent[0]
+                ent[1] = (slots, ts) if kb > ka else None
+            else:
+                arrays = [np.zeros((11, s.n_iters, GRID_SIZE), dtype=np.float32) for _ in range(4)]
+            st_prob = np.zeros((11, s.n_iters), dtype=np.float32)
+            if kb > ka:
+                st_prob[slots, ts] = batch.out_rec_state_prob[ka:kb].numpy()
+                for a, src in zip(arrays, (batch.out_rec_pos_prob, batch.out_rec_agent_occ, batch.out_rec_pt_occ,
+                                           batch.out_rec_occ_gt)):
+                    a[slots, ts] = src[ka:kb].numpy()
             out.update({
-                'next_state_prob_seed': batch.out_state_prob_seed[b, :, :s.n_iters].clone(),
-                'next_pos_rel_prob_seed': batch.out_pos_prob_seed[b, :, :s.n_iters].clone(),
-                'grid_agent_occ_seed': batch.out_agent_occ_seed[b, :, :s.n_iters].clone(),
-                'grid_pt_occ_seed': batch.out_pt_occ_seed[b, :, :s.n_iters].clone(),
-                'grid_agent_occ_gt_seed': batch.out_occ_gt_seed[b, :, :s.n_iters].clone(),
+                'next_state_prob_seed': tt(st_prob),
+                'next_pos_rel_prob_seed': tt(arrays[0]), 'grid_agent_occ_seed': tt(arrays[1]),
+                'grid_pt_occ_seed': tt(arrays[2]), 'grid_agent_occ_gt_seed': tt(arrays[3]),
             })
         else:
             # the reference appends zero [11,1(,G)] records every iteration whether or not the stage runs
