@@ -151,7 +151,7 @@ def test_batched_scenes_equal_single_scene_runs():
                          cfg=cfg) for i, (a, p, rg) in enumerate(sizes)]
     dec = _make_decoder(sd, cfg)
     outs = dec.inference_batch(scenes, [s['map_enc'] for s in scenes])
-    assert sum(s_.n_rows for s_ in dec._scenes) > 512 or True   # > 512 active rows selects the 16-row tile
+    assert dec._batch.R > 512, 'the batch must exceed 512 rows: that selects the 16-row tile of k_heads'
     for i in (0, 1, 2, 7, 19):
         single = dec.inference(scenes[i], scenes[i]['map_enc'])
         assert np.array_equal(single['next_token_idx'].numpy(), outs[i]['next_token_idx'].numpy()), f'scene {i}'
@@ -432,3 +432,50 @@ def test_a2a_neighbour_limit_matches_oracle(monkeypatch):
     assert np.array_equal(cnt[:A], want_cnt)
     for i in range(A):
         assert np.array_equal(a_src[i, :cnt[i]], np.sort(src[dst == i])), f'row {i}'
+
+
+REFERENCE_KEYS = ('ego_index', 'agent_id', 'valid_mask', 'pos_a', 'head_a', 'gt_traj', 'pred_traj', 'pred_head', 'pred_type',
+                  'pred_state', 'pred_z', 'pred_shape', 'eval_shape', 'pred_valid', 'next_state_prob_seed',
+                  'next_pos_rel_prob_seed', 'next_token_idx', 'next_state_idx', 'grid_agent_occ_seed', 'grid_pt_occ_seed',
+                  'grid_agent_occ_gt_seed', 'agent_labels', 'log_message')          # agent_decoder.py:2358-2389
+
+
+@pytest.mark.parametrize('name', ['cfg0_a8', 'insert_a12'])
+def test_install_replaces_the_bound_method(name):
+    """`install(agent_encoder)` is the drop-in itself: it swaps `agent_encoder.inference` of a module that carries the
+    reference `state_dict()` (here a stub module; the reference class needs torch_geometric).  The call must return the
+    reference's dict: every key of agent_decoder.py:2358-2389, dtypes and shapes of the reference run (golden vectors /
+    oracle), on the device of `map_enc['x_pt']` - with the insertion stage on AND off (the reference returns the five
+    seed tensors in both modes, infgen.py:742-777 reads them unconditionally)."""
+    from infgen_b200.agent_decoder import install
+    from oracle.agent_decoder_oracle import rollout
+    scene, sd, cfg, spec = build_case(name)
+    z = np.load(os.path.join(GOLD, f'case_{name}.npz'))
+
+    class StubAgentEncoder(torch.nn.Module):            # what `model.encoder.agent_encoder` looks like to install()
+        def __init__(self, sd_):
+            super().__init__()
+            self._sd = sd_
+
+        def state_dict(self, *a, **k):
+            return dict(self._sd)
+
+        def inference(self, data, map_enc):
+            raise AssertionError('the reference method must have been replaced')
+    mod = StubAgentEncoder(sd)
+    dec = install(mod, cfg)
+    out = mod.inference(scene, scene['map_enc'])
+    assert mod._b200 is dec
+    assert set(out) == set(REFERENCE_KEYS), sorted(set(out) ^ set(REFERENCE_KEYS))
+    want = rollout(scene, sd, cfg, debug_force_enter=cfg.debug_force_enter)['out']
+    for k, w in want.items():
+        g = out[k]
+        if isinstance(w, torch.Tensor):
+            assert isinstance(g, torch.Tensor) and g.dtype == w.dtype and tuple(g.shape) == tuple(w.shape), \
+                (k, g.dtype, w.dtype, tuple(g.shape), tuple(w.shape))
+    for k in ('next_token_idx', 'next_state_idx', 'pred_valid', 'pred_type', 'agent_id'):
+        assert np.array_equal(out[k].numpy(), z[k]), k
+    S = out['next_token_idx'].shape[1] - cfg.hist_cols
+    assert tuple(out['next_state_prob_seed'].shape) == (11, S) and tuple(out['next_pos_rel_prob_seed'].shape) == (11, S, 1961)
+    assert isinstance(out['ego_index'], int) and isinstance(out['agent_labels'], list) and isinstance(out['log_message'], str)
+    dec.close()
