@@ -17,6 +17,7 @@
 #include "layer.cuh"
 #include "fourier_tc.cuh"
 #include "node.cuh"
+#include "node_tc.cuh"
 #include "decode.cuh"
 #include "insert.cuh"
 #include "map.cuh"
@@ -164,8 +165,11 @@ struct infgen_engine {
     float *np_blob = nullptr;                           // node-packed motion + map layers (node.cuh), [21][np::FLOATS]
     float *vrf_blob = nullptr;                          // their folded to_v_r tables, [21][vrf::FLOATS]
     std::unordered_map<std::string, const float *> vrfs;
+    std::unordered_map<std::string, const float *> tcimgs;   // layer prefix -> tensor-core weight image (node_tc.cuh)
     int attn_ctas = 296;                                // persistent k_attn CTAs: 2 per SM
     bool node_mma = false;                              // k_node GEMMs on mma.sync 3xTF32 (INFGEN_NODE_GEMM=mma)
+    bool node_tc = true;                                // row-tile path on k_node_tc (tcgen05); INFGEN_NODE_GEMM=ffma|mma: k_node
+    float *tc_blob = nullptr;                           // tensor-core weight images of the node-packed layers, [30][ntc::IMG_FLOATS]
     int layer_path = 0;                                 // 0 auto, 1 cluster kernels only, 2 row-tile (k_attn + k_node) only
     bool fourier_tc = true;                             // INFGEN_FOURIER=ffma selects the FFMA row-tile kernel instead
     std::unordered_map<std::string, std::pair<const float *, const float *>> cs;   // layer -> (post, pre) chunks
@@ -244,6 +248,8 @@ static AttnW make_attn(infgen_engine *e, const std::string &p, bool has_pos) {
     if (nt != e->npk.end()) w.npk = nt->second;
     auto vt = e->vrfs.find(p);
     if (vt != e->vrfs.end()) w.vrf = vt->second;
+    auto tt = e->tcimgs.find(p);
+    if (tt != e->tcimgs.end()) w.tcimg = tt->second;
     return w;
 }
 
@@ -458,6 +464,13 @@ static int check_ftc_watchdog() {
         return fail(INFGEN_ERR_CUDA, "k_fourier_tc: %d mbarrier waits timed out (first code*1000+thread per class: weights %d, "
                     "mma/A %d, mma/B %d, A stage %d, accumulator %d)", h[0], h[1], h[2], h[3], h[4], h[5]);
     }
+    CK(cudaMemcpyFromSymbol(h, g_ntc_hang, sizeof(h)));
+    if (h[0]) {
+        int z[8] = {0};
+        cudaMemcpyToSymbol(g_ntc_hang, z, sizeof(z));
+        return fail(INFGEN_ERR_CUDA, "k_node_tc: %d mbarrier waits timed out (first code*1000+thread per class: weights %d, "
+                    "mma/A %d, mma/B %d, A stage %d, accumulator %d, accumulator free %d)", h[0], h[1], h[2], h[3], h[4], h[5], h[6]);
+    }
     return 0;
 }
 // up to three FourierEmbeddings in one launch.  Embeddings without a categorical seed run on the tensor cores
@@ -558,6 +571,9 @@ static int enqueue_embed_rows(infgen_engine *e, const int *row_lo) {
 static int build_node_weights(infgen_engine *e) {
     CK(cudaMalloc(&e->np_blob, (size_t)30 * np::FLOATS * sizeof(float)));
     CK(cudaMalloc(&e->vrf_blob, (size_t)21 * vrf::FLOATS * sizeof(float)));
+    CK(cudaMalloc(&e->tc_blob, (size_t)30 * ntc::IMG_FLOATS * sizeof(float)));
+    float *kr_tmp = nullptr;                             // to_k_r.weight re-packed [32 k4][128][4]
+    CK(cudaMalloc(&kr_tmp, 16384 * sizeof(float)));
     {
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
@@ -580,9 +596,30 @@ static int build_node_weights(infgen_engine *e) {
             pack(w.w_qs, np::QS, 32, 256); pack(w.w_kv, np::KV, 32, 256);
             CKL();
             w.npk = d;
+            {
+                // tensor-core image (node_tc.cuh): the sixteen 128 x 128 blocks of the layer as hi / lo TF32 chunks
+                float *img = e->tc_blob + (size_t)(s < 4 ? s * 6 + i : 21 + (s - 4) * 3 + i) * ntc::IMG_FLOATS;
+                auto split = [&](const float *blk, int b) {
+                    k_wimg_split<<<64, 256, 0, e->stream>>>(blk, img + (size_t)b * 4 * ntc::CHUNK, 0);
+                };
+                split(d + np::G, ntc::B_G0); split(d + np::G + 16384, ntc::B_G1); split(d + np::OUT, ntc::B_OUT);
+                for (int j = 0; j < 4; ++j) {
+                    split(d + np::FF1 + j * 16384, ntc::B_UP0 + 2 * j);
+                    split(d + np::FF2 + j * 16384, ntc::B_DN0 + 2 * j);
+                }
+                split(d + np::QS, ntc::B_Q); split(d + np::QS + 16384, ntc::B_S);
+                split(d + np::KV, ntc::B_K); split(d + np::KV + 16384, ntc::B_V);
+                if (w.has_pos) {
+                    k_pack_kn<<<64, 256, 0, e->stream>>>(w.w_kr, kr_tmp);
+                    split(kr_tmp, ntc::B_KR);
+                }
+                CKL();
+                w.tcimg = img;
+            }
             static const char *names[7] = {"t_attn_layers.", "pt2a_attn_layers.", "a2a_attn_layers.", "map.pt2pt_layers.",
                                            "occ2sa_attn_layers.", "pt2sa_attn_layers.", "a2sa_attn_layers."};
             e->npk[std::string(names[s]) + std::to_string(i)] = d;
+            e->tcimgs[std::string(names[s]) + std::to_string(i)] = w.tcimg;
             if (s < 4) {
                 float *vf = e->vrf_blob + (size_t)(s * 6 + i) * vrf::FLOATS;
                 k_vr_fold_pack<<<1, 128, 0, e->stream>>>(w.w_vr, w.ln_r_g, w.ln_r_b, w.b_vr, vf);
@@ -591,6 +628,8 @@ static int build_node_weights(infgen_engine *e) {
                 e->vrfs[std::string(names[s]) + std::to_string(i)] = vf;
             }
         }
+    CK(cudaStreamSynchronize(e->stream));
+    cudaFree(kr_tmp);
     return 0;
 }
 struct NodeBufs {              // hand-over buffers of the row-tile path
@@ -628,7 +667,13 @@ static int launch_node(infgen_engine *e, const RowSpace &rows, const AttnW *lw, 
     a.pre_kv = pre_kv ? 1 : 0; a.kv_out = kv_out; a.kv_ring = kv_ring ? 1 : 0; a.col_add = 0; a.ring = RING;
     a.col_ptr = e->st.col; a.trace_out = trace_out; a.edgeless = edgeless ? 1 : 0;
     ProfScope ps(e, cls);
-    if (e->node_mma) k_node<true><<<(rows.n_total + NM - 1) / NM, NT_S, NodeSmem::BYTES, e->stream>>>(a);
+    if (e->node_tc && (!lw || lw->tcimg) && (!pw || pw->tcimg)) {
+        // tensor-core kernel: one CTA per 128 ACTIVE rows (the kernel compacts a capacity row space on the fly)
+        if (lw) a.tc_post = lw->tcimg;
+        if (pw) a.tc_pre = pw->tcimg;
+        const int upper = rows.cap ? std::min(rows.n_total, e->n_rows_sum + 10 * e->n_scenes * std::max(e->S, 1)) : rows.n_total;
+        k_node_tc<<<std::max(1, (upper + ntc::TM - 1) / ntc::TM), ntc::THREADS, ntc::SMEM, e->stream>>>(a);
+    } else if (e->node_mma) k_node<true><<<(rows.n_total + NM - 1) / NM, NT_S, NodeSmem::BYTES, e->stream>>>(a);
     else k_node<false><<<(rows.n_total + NM - 1) / NM, NT_S, NodeSmem::BYTES, e->stream>>>(a);
     CKL(); count_launch(e);
     return 0;
@@ -1332,9 +1377,11 @@ int32_t infgen_create(const infgen_config *cfg, const float *weights, int64_t n_
     CK(cudaFuncSetAttribute(k_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATTN_SMEM));
     CK(cudaFuncSetAttribute(k_node<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NodeSmem::BYTES));
     CK(cudaFuncSetAttribute(k_node<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NodeSmem::BYTES));
+    CK(cudaFuncSetAttribute(k_node_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntc::SMEM));
     {
         const char *ng = getenv("INFGEN_NODE_GEMM");            // "mma": 3xTF32 mma.sync tiles in k_node instead of FFMA
         e->node_mma = ng && !strcmp(ng, "mma");
+        e->node_tc = !(ng && (!strcmp(ng, "mma") || !strcmp(ng, "ffma")));   // default: k_node_tc (tcgen05, 128-row tiles)
         if (getenv("INFGEN_VERBOSE")) fprintf(stderr, "infgen_b200: node_mma=%d layer_path=%d fourier_tc=%d\n", (int)e->node_mma, e->layer_path, (int)e->fourier_tc);
     }
     RET(build_node_weights(e));
@@ -1368,7 +1415,7 @@ int32_t infgen_destroy(infgen_engine *e) {
     cudaFree(e->blob); cudaFree(e->cs_blob); cudaFree(e->grid_cells); cudaFree(e->vocab); cudaFree(e->tok_tab); cudaFree(e->grid_tab);
     cudaFree(e->d_err); cudaFree(e->seed_feat);
     for (float *p : e->wimgs) cudaFree(p);
-    cudaFree(e->np_blob); cudaFree(e->vrf_blob); cudaFree(e->t_dim_table); cudaFree(e->map_tok_tab);
+    cudaFree(e->np_blob); cudaFree(e->vrf_blob); cudaFree(e->tc_blob); cudaFree(e->t_dim_table); cudaFree(e->map_tok_tab);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->side_stream) cudaStreamDestroy(e->side_stream);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
@@ -1957,6 +2004,13 @@ int64_t infgen_debug_read(infgen_engine *e, const char *name, void *dst, int64_t
 int32_t infgen_debug_node_trace(long long *dst /* [32] */) {
     cudaDeviceSynchronize();
     cudaMemcpyFromSymbol(dst, g_node_trace, sizeof(long long) * 32);
+    return 0;
+}
+#endif
+#ifdef INFGEN_NTC_TRACE
+int32_t infgen_debug_ntc_trace(long long *dst /* [2][64] */) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(dst, g_ntc_trace, sizeof(long long) * 2 * 64);
     return 0;
 }
 #endif

@@ -331,6 +331,7 @@ struct NodeArgs {
     int kv_ring, col_add, ring;
     const int *col_ptr;
     float *trace_out;          // optional copy of the layer output [R][128]
+    const float *tc_post, *tc_pre;   // tensor-core weight images of the two layers (node_tc.cuh), k_node_tc only
 };
 #ifdef INFGEN_NODE_TRACE
 __device__ long long g_node_trace[32];   // debug: clock64 stamps of consumer thread 0 of CTA 0 at the phase boundaries

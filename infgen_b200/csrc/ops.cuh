@@ -35,6 +35,7 @@ struct AttnW {                 // one AttentionLayer, pointers into the packed w
     const float *cs_post, *cs_pre;   // cluster-sliced chunks of this layer (layer.cuh), [8][FLOATS] each
     const float *npk;                // node-packed copy (node.cuh), NULL when the layer has none
     const float *vrf;                // folded to_v_r table for the k_attn epilogue (node.cuh vrf::), NULL when the layer has none
+    const float *tcimg;              // tensor-core weight image for k_node_tc (node_tc.cuh ntc::), NULL when the layer has none
 };
 
 struct FourierW {              // one FourierEmbedding
