@@ -584,7 +584,43 @@ def run_ours(args, rank, world, local_rank):
                 out['cpu_port_error'] = repr(ex)[:200]
             return out
 
+        def scene_prep():
+            """Row f2: `TokenProcessor._tokenize_agent` + `InfGen._fetch_enterings` of the configs[1] scene's raw 10 Hz tracks on
+            the engine (infgen_prepare_scene), host tensors in and out, next to the CPU port on the host cores."""
+            from infgen_b200.scene_prep import B200ScenePrep
+            pdec = B200AgentDecoder(sd, cfg, device=local_rank, seed=2024, use_cuda_graph=False)
+            prep = B200ScenePrep(pdec)
+            ag = scenes[0]['agent']
+            raw = {k: ag[k] for k in ('valid_mask', 'heading', 'position', 'velocity', 'type', 'shape')}
+            raw['av_idx'] = ag['av_index']
+            mk = lambda: {'agent': {k: v.clone() for k, v in raw.items()}, 'pt_token': {'position': scenes[0]['pt_token']['position']}}
+            for _ in range(3):
+                prep.tokenize(mk())
+            ts = []
+            for _ in range(20):
+                d = mk()
+                t0 = time.perf_counter()
+                prep.tokenize(d)
+                ts.append(time.perf_counter() - t0)
+            pdec.close()
+            out = {'workload': 'agent tokenizer + enterings of the configs[1] scene (64 agents x 91 raw steps, 2048 map tokens): '
+                               'closed-loop match over 2048 vocabulary boxes per token step, ego-centric grid cells of agents and '
+                               'map tokens per column', 'gpu_ms': statistics.mean(ts) * 1e3, 'gpu_ms_min': min(ts) * 1e3}
+            try:
+                from oracle.scene_prep_oracle import tokenize_agent, fetch_enterings
+                from infgen_b200.synth import load_vocab
+                from infgen_b200.grid import PositionGrid
+                g = PositionGrid(cfg.grid_range, cfg.grid_interval, cfg.pl2seed_radius, cfg.angle_interval)
+                t0 = time.perf_counter()
+                tk = tokenize_agent(raw, load_vocab())
+                fetch_enterings(tk, scenes[0]['pt_token']['position'], int(raw['av_idx'][0]), g.cells, cfg.pl2seed_radius, cfg.angle_interval)
+                out['cpu_port_ms'] = (time.perf_counter() - t0) * 1e3
+            except Exception as ex:
+                out['cpu_port_error'] = repr(ex)[:200]
+            return out
+
         side('motion_only', motion_only)
+        side('scene_prep', scene_prep)
         side('map_encoder', map_encoder)
         side('configs2', lambda: batch(2, 5))
         side('configs4_one_gpu', lambda: batch(4, 2))

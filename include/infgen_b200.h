@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define INFGEN_ABI_VERSION 6
+#define INFGEN_ABI_VERSION 7
 
 typedef enum {
     INFGEN_OK = 0,
@@ -192,6 +192,44 @@ int32_t infgen_map_setup(infgen_engine *e, const float *traj_src, int32_t n_toke
  * on x_pt[pt_pred_mask], map_decoder.py:119).  Either output may be NULL; the result also stays in the engine for a
  * following infgen_load_scenes with x_pt == NULL.  Synchronises the stream when loc == INFGEN_HOST. */
 int32_t infgen_map_encode(infgen_engine *e, const infgen_map_batch *batch, int32_t loc, float *x_pt_out, float *logits_out);
+
+/* ---- per-scene preparation of the agent stream, SURVEY.md 8f row f2 ------------------------------------------------ */
+/* Raw 10 Hz tracks of ONE scene (the inputs of TokenProcessor._tokenize_agent, infgen/datasets/preprocess.py:364-373) and
+ * its map token positions.  All pointers host. */
+typedef struct {
+    int32_t n_agents, n_steps;    /* A, N raw steps (91); token steps T = n_steps / shift */
+    int32_t av_index;             /* data['agent']['av_idx'] */
+    int32_t n_pt;                 /* P map tokens */
+    const uint8_t *valid_mask;    /* [A][N] */
+    const float *heading;         /* [A][N] */
+    const float *position;        /* [A][N][3] */
+    const float *velocity;        /* [A][N][2] */
+    const uint8_t *type;          /* [A] 0 veh 1 ped 2 cyc */
+    const float *pt_position;     /* [P][3] data['pt_token']['position'] */
+} infgen_prep_in;
+/* Results (host, caller-allocated; any pointer of the second group may be NULL).  int64 where the reference has LongTensors. */
+typedef struct {
+    /* TokenProcessor._tokenize_agent (preprocess.py:533-546) */
+    int64_t *token_idx;           /* [A][T] motion token, -1 invalid, -2 BOS */
+    int64_t *state_idx;           /* [A][T] 0 invalid 1 valid 2 enter 3 exit */
+    float *token_contour;         /* [A][T][4][2] matched box */
+    float *token_pos;             /* [A][T][2] */
+    float *token_heading;         /* [A][T] */
+    uint8_t *raw_agent_valid_mask;/* [A][T] */
+    uint8_t *agent_valid_mask;    /* [A][T] (all ones with predict_state) */
+    /* InfGen._fetch_enterings (infgen/model/infgen.py:1008-1090) */
+    int64_t *grid_token_idx;      /* [A][T] ego-centric cell, -1 invalid / out of range */
+    float *grid_offset_xy;        /* [A][T][2] */
+    int64_t *heading_token_idx;   /* [A][T] */
+    float *pos_xy;                /* [A][T][2] */
+    float *heading_theta;         /* [A][T] */
+    int64_t *sort_indices;        /* [A][T] entering agents of a column by bearing, ego row elsewhere */
+    uint8_t *inrange_mask;        /* [A][T] */
+    uint8_t *bos_mask;            /* [A][T] */
+    int64_t *pt_grid_token_idx;   /* [T][P] */
+} infgen_prep_out;
+/* tokenize + fetch_enterings of one scene on the device (vocabulary and grid cells are the engine's). */
+int32_t infgen_prepare_scene(infgen_engine *e, const infgen_prep_in *in, const infgen_prep_out *out);
 
 /* ---- per-kernel-class device timing for the roofline report (bench.py): CUDA events around every launch; turns
  * graph replay off while enabled ------------------------------------------------------------------------------ */

@@ -9,7 +9,7 @@ import os
 from typing import Optional
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib', 'libinfgen_b200.so')
-ABI_VERSION = 6
+ABI_VERSION = 7
 HOST, DEVICE = 0, 1
 
 c_f32p = C.POINTER(C.c_float)
@@ -47,6 +47,27 @@ class MapBatch(C.Structure):
     ]
 
 
+c_i64p = C.POINTER(C.c_int64)
+
+
+class PrepIn(C.Structure):
+    _fields_ = [
+        ('n_agents', C.c_int32), ('n_steps', C.c_int32), ('av_index', C.c_int32), ('n_pt', C.c_int32),
+        ('valid_mask', c_u8p), ('heading', c_f32p), ('position', c_f32p), ('velocity', c_f32p), ('type', c_u8p),
+        ('pt_position', c_f32p),
+    ]
+
+
+class PrepOut(C.Structure):
+    _fields_ = [
+        ('token_idx', c_i64p), ('state_idx', c_i64p), ('token_contour', c_f32p), ('token_pos', c_f32p),
+        ('token_heading', c_f32p), ('raw_agent_valid_mask', c_u8p), ('agent_valid_mask', c_u8p),
+        ('grid_token_idx', c_i64p), ('grid_offset_xy', c_f32p), ('heading_token_idx', c_i64p), ('pos_xy', c_f32p),
+        ('heading_theta', c_f32p), ('sort_indices', c_i64p), ('inrange_mask', c_u8p), ('bos_mask', c_u8p),
+        ('pt_grid_token_idx', c_i64p),
+    ]
+
+
 class Outputs(C.Structure):
     _fields_ = [
         ('pos', c_f32p), ('head', c_f32p), ('pred_traj', c_f32p), ('pred_head', c_f32p), ('pred_state', c_f32p),
@@ -80,6 +101,7 @@ SYMBOLS = {
     'infgen_iterations_done': (C.c_int32, [C.c_void_p]),
     'infgen_map_setup': (C.c_int32, [C.c_void_p, c_f32p, C.c_int32]),
     'infgen_map_encode': (C.c_int32, [C.c_void_p, C.POINTER(MapBatch), C.c_int32, c_f32p, c_f32p]),
+    'infgen_prepare_scene': (C.c_int32, [C.c_void_p, C.POINTER(PrepIn), C.POINTER(PrepOut)]),
     'infgen_kernel_launches': (C.c_int64, [C.c_void_p]),
     'infgen_set_profile': (C.c_int32, [C.c_void_p, C.c_int32]),
     'infgen_profile_class_count': (C.c_int32, []),
@@ -150,6 +172,12 @@ def i32p(t):
     if t is None:
         return None
     return C.cast(_ptr(t), c_i32p)
+
+
+def i64p(t):
+    if t is None:
+        return None
+    return C.cast(_ptr(t), c_i64p)
 
 
 def u8p(t):

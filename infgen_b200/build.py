@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'lib', 'libinfgen_b200.so')
 SOURCES = ['engine.cu']
-DEPS = ['engine.cu', 'common.cuh', 'stream.cuh', 'ops.cuh', 'layer.cuh', 'decode.cuh', 'insert.cuh', 'fourier_tc.cuh', 'node.cuh', 'node_tc.cuh', 'map.cuh', os.path.join('..', '..', 'include', 'infgen_b200.h')]
+DEPS = ['engine.cu', 'common.cuh', 'stream.cuh', 'ops.cuh', 'layer.cuh', 'decode.cuh', 'insert.cuh', 'fourier_tc.cuh', 'node.cuh', 'node_tc.cuh', 'map.cuh', 'prep.cuh', os.path.join('..', '..', 'include', 'infgen_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-shared',
               '-Xcompiler', '-fPIC', '-Xptxas', '-v']
 

@@ -21,6 +21,7 @@
 #include "decode.cuh"
 #include "insert.cuh"
 #include "map.cuh"
+#include "prep.cuh"
 
 using namespace infgen;
 
@@ -169,6 +170,7 @@ struct infgen_engine {
     int attn_ctas = 296;                                // persistent k_attn CTAs: 2 per SM
     bool node_mma = false;                              // k_node GEMMs on mma.sync 3xTF32 (INFGEN_NODE_GEMM=mma)
     bool node_tc = true;                                // row-tile path on k_node_tc (tcgen05); INFGEN_NODE_GEMM=ffma|mma: k_node
+    void *prep_buf = nullptr; size_t prep_bytes = 0;    // arena of infgen_prepare_scene (row f2)
     float *tc_blob = nullptr;                           // tensor-core weight images of the node-packed layers, [30][ntc::IMG_FLOATS]
     int layer_path = 0;                                 // 0 auto, 1 cluster kernels only, 2 row-tile (k_attn + k_node) only
     bool fourier_tc = true;                             // INFGEN_FOURIER=ffma selects the FFMA row-tile kernel instead
@@ -1415,7 +1417,7 @@ int32_t infgen_destroy(infgen_engine *e) {
     cudaFree(e->blob); cudaFree(e->cs_blob); cudaFree(e->grid_cells); cudaFree(e->vocab); cudaFree(e->tok_tab); cudaFree(e->grid_tab);
     cudaFree(e->d_err); cudaFree(e->seed_feat);
     for (float *p : e->wimgs) cudaFree(p);
-    cudaFree(e->np_blob); cudaFree(e->vrf_blob); cudaFree(e->tc_blob); cudaFree(e->t_dim_table); cudaFree(e->map_tok_tab);
+    cudaFree(e->np_blob); cudaFree(e->vrf_blob); cudaFree(e->tc_blob); cudaFree(e->prep_buf); cudaFree(e->t_dim_table); cudaFree(e->map_tok_tab);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->side_stream) cudaStreamDestroy(e->side_stream);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
@@ -2054,6 +2056,86 @@ struct TmpDev {
     }
 };
 extern "C" {
+
+// ---------------------------------------------------------------------------------------------------------------
+// row f2: TokenProcessor._tokenize_agent + InfGen._fetch_enterings of one scene (prep.cuh)
+// ---------------------------------------------------------------------------------------------------------------
+int32_t infgen_prepare_scene(infgen_engine *e, const infgen_prep_in *in, const infgen_prep_out *out) {
+    if (!e || !in || !out) return fail(INFGEN_ERR_INVALID_ARG, "null argument");
+    const int A = in->n_agents, N = in->n_steps, P = in->n_pt, T = N / e->cfg.shift;
+    if (A <= 0 || N < 2 * e->cfg.shift || N > PREP_MAX_STEPS || T > 128 || P < 0 || in->av_index < 0 || in->av_index >= A)
+        return fail(INFGEN_ERR_INVALID_ARG, "prepare_scene: A=%d N=%d P=%d av=%d out of range", A, N, P, in->av_index);
+    if (!in->valid_mask || !in->heading || !in->position || !in->velocity || !in->type || (P > 0 && !in->pt_position) ||
+        !out->token_idx || !out->state_idx || !out->token_pos || !out->token_heading)
+        return fail(INFGEN_ERR_INVALID_ARG, "prepare_scene: missing input / output array");
+    // one arena for inputs, results and scratch, kept by the engine and grown on demand (no allocation per scene)
+    const size_t AT = (size_t)A * T;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_valid = take((size_t)A * N), o_head = take((size_t)A * N * 4), o_pos = take((size_t)A * N * 12),
+                 o_vel = take((size_t)A * N * 8), o_type = take(A), o_pt = take((size_t)std::max(P, 1) * 12);
+    const size_t o_tok = take(AT * 8), o_state = take(AT * 8), o_con = take(AT * 32), o_tpos = take(AT * 8), o_thead = take(AT * 4),
+                 o_rv = take(AT), o_av = take(AT), o_grid = take(AT * 8), o_goff = take(AT * 8), o_pxy = take(AT * 8),
+                 o_htok = take(AT * 8), o_hth = take(AT * 4), o_sort = take(AT * 8), o_inr = take(AT), o_bos = take(AT),
+                 o_ptg = take((size_t)T * std::max(P, 1) * 8), o_bear = take(AT * 4);
+    if (off > e->prep_bytes) {
+        CK(cudaStreamSynchronize(e->stream));
+        cudaFree(e->prep_buf);
+        e->prep_buf = nullptr; e->prep_bytes = 0;
+        CK(cudaMalloc(&e->prep_buf, off));
+        e->prep_bytes = off;
+    }
+    char *base = (char *)e->prep_buf;
+    auto up = [&](size_t o, const void *src, size_t bytes) {
+        return cudaMemcpyAsync(base + o, src, bytes, cudaMemcpyHostToDevice, e->stream);
+    };
+    CK(up(o_valid, in->valid_mask, (size_t)A * N)); CK(up(o_head, in->heading, (size_t)A * N * 4));
+    CK(up(o_pos, in->position, (size_t)A * N * 12)); CK(up(o_vel, in->velocity, (size_t)A * N * 8));
+    CK(up(o_type, in->type, A));
+    if (P > 0) CK(up(o_pt, in->pt_position, (size_t)P * 12));
+    TokenizeArgs ta;
+    memset(&ta, 0, sizeof(ta));
+    ta.A = A; ta.N = N; ta.T = T; ta.V = e->cfg.token_size; ta.predict_state = 1;
+    ta.valid = (const unsigned char *)(base + o_valid); ta.heading = (const float *)(base + o_head);
+    ta.pos = (const float *)(base + o_pos); ta.vel = (const float *)(base + o_vel);
+    ta.type = (const unsigned char *)(base + o_type); ta.vocab = e->vocab;
+    ta.token_idx = (long long *)(base + o_tok); ta.state_idx = (long long *)(base + o_state);
+    ta.contour = (float *)(base + o_con); ta.token_pos = (float *)(base + o_tpos); ta.token_heading = (float *)(base + o_thead);
+    ta.raw_valid = (unsigned char *)(base + o_rv); ta.agent_valid = (unsigned char *)(base + o_av);
+    EnterArgs ea;
+    memset(&ea, 0, sizeof(ea));
+    ea.A = A; ea.T = T; ea.P = P; ea.G = e->cfg.grid_size; ea.av = in->av_index;
+    ea.radius = e->cfg.pl2seed_radius; ea.angle_interval = e->cfg.angle_interval;
+    ea.token_pos = ta.token_pos; ea.token_heading = ta.token_heading; ea.state_idx = ta.state_idx;
+    ea.pt_pos = (const float *)(base + o_pt); ea.cells = e->grid_cells;
+    ea.grid_idx = (long long *)(base + o_grid); ea.grid_off = (float *)(base + o_goff); ea.pos_xy = (float *)(base + o_pxy);
+    ea.head_tok = (long long *)(base + o_htok); ea.head_theta = (float *)(base + o_hth); ea.sort_idx = (long long *)(base + o_sort);
+    ea.inrange = (unsigned char *)(base + o_inr); ea.bos = (unsigned char *)(base + o_bos);
+    ea.pt_grid = (long long *)(base + o_ptg); ea.bearing = (float *)(base + o_bear);
+    if (ea.angle_interval <= 0.f) ea.angle_interval = 3.0f;
+    if (ea.radius <= 0.f) ea.radius = 75.0f;
+    k_tokenize_agents<<<A, PREP_NT, 0, e->stream>>>(ta);
+    CKL(); count_launch(e);
+    k_fetch_enterings<<<dim3((A + P + 7) / 8, T), 256, 0, e->stream>>>(ea);
+    CKL(); count_launch(e);
+    k_sort_enterings<<<T, 128, 0, e->stream>>>(ea);
+    CKL(); count_launch(e);
+    auto down = [&](void *dst, const void *src, size_t bytes) {
+        if (dst) cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, e->stream);
+    };
+    down(out->token_idx, ta.token_idx, AT * 8); down(out->state_idx, ta.state_idx, AT * 8);
+    down(out->token_contour, ta.contour, AT * 32); down(out->token_pos, ta.token_pos, AT * 8);
+    down(out->token_heading, ta.token_heading, AT * 4); down(out->raw_agent_valid_mask, ta.raw_valid, AT);
+    down(out->agent_valid_mask, ta.agent_valid, AT);
+    down(out->grid_token_idx, ea.grid_idx, AT * 8); down(out->grid_offset_xy, ea.grid_off, AT * 8);
+    down(out->heading_token_idx, ea.head_tok, AT * 8); down(out->pos_xy, ea.pos_xy, AT * 8);
+    down(out->heading_theta, ea.head_theta, AT * 4); down(out->sort_indices, ea.sort_idx, AT * 8);
+    down(out->inrange_mask, ea.inrange, AT); down(out->bos_mask, ea.bos, AT);
+    if (P > 0) down(out->pt_grid_token_idx, ea.pt_grid, (size_t)T * P * 8);
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaGetLastError());
+    return 0;
+}
 
 int32_t infgen_op_attention_layer(infgen_engine *e, const char *layer, const float *x_src, int32_t n_src,
                                   const float *x_dst, int32_t n_dst, const float *r, const int32_t *edge_ptr,

@@ -172,6 +172,7 @@ def make_scene(seed: int, num_agents: int = 64, num_map_tokens: int = 2048, num_
         'shape': torch.from_numpy(shape)[:, None, :].repeat(1, num_steps, 1).contiguous(),
         'position': torch.from_numpy(np.concatenate([position, np.zeros((A, num_steps, 1))], -1).astype(np.float32)),
         'heading': torch.from_numpy(heading.astype(np.float32)),
+        'velocity': torch.from_numpy(vel.astype(np.float32)),
         'valid_mask': torch.from_numpy(valid_raw),
         'token_idx': torch.from_numpy(token_idx),
         'state_idx': torch.from_numpy(state),

@@ -32,3 +32,47 @@ def build_case(name: str):
     scene = make_scene(spec['scene_seed'], num_agents=spec['agents'], num_map_tokens=spec['map_tokens'],
                        num_steps=spec['steps'], ragged=spec['ragged'], ego_index=spec['ego'], cfg=cfg)
     return scene, sd, cfg, spec
+
+
+# --- row f2: per-scene preparation (TokenProcessor._tokenize_agent + InfGen._fetch_enterings) ------------------------------
+PREP_CASES = {
+    'a16': dict(scene_seed=31, agents=16, map_tokens=512, ragged=0.5, ego=2),
+    'a64': dict(scene_seed=13, agents=64, map_tokens=2048, ragged=0.3, ego=5),
+}
+
+
+def build_prep_case(name: str):
+    """Raw 10 Hz tracks of a synthetic scene (the inputs of TokenProcessor._tokenize_agent, preprocess.py:364-373) with
+    the irregularities real tracks have: first valid steps that are not multiples of 5 (extrapolation, :324-343), a
+    heading flip (clean_heading, :315-322), a track too short for any token, gaps."""
+    import numpy as np
+    spec = PREP_CASES[name]
+    cfg = DecoderConfig()
+    scene = make_scene(spec['scene_seed'], num_agents=spec['agents'], num_map_tokens=spec['map_tokens'], num_steps=91,
+                       ragged=spec['ragged'], ego_index=spec['ego'], cfg=cfg)
+    ag = scene['agent']
+    rng = np.random.default_rng(1000 + spec['scene_seed'])
+    valid = ag['valid_mask'].clone()
+    heading = ag['heading'].clone()
+    A = valid.shape[0]
+    for a in range(A):
+        if a == spec['ego']:
+            continue
+        u = rng.uniform()
+        if u < 0.25:                                   # late start at an arbitrary raw step
+            valid[a, :int(rng.integers(1, 60))] = False
+        elif u < 0.35:                                 # early end
+            valid[a, int(rng.integers(20, 88)):] = False
+        elif u < 0.40:                                 # a gap in the middle
+            g0 = int(rng.integers(15, 60))
+            valid[a, g0:g0 + int(rng.integers(3, 14))] = False
+        elif u < 0.45:                                 # three valid steps only
+            valid[a] = False
+            valid[a, 41:44] = True
+        if rng.uniform() < 0.15:                       # heading flip by ~pi for a few steps
+            h0 = int(rng.integers(5, 80))
+            heading[a, h0:h0 + 4] += 3.0
+    raw = {'valid_mask': valid, 'heading': heading, 'position': ag['position'].clone(), 'velocity': ag['velocity'].clone(),
+           'type': ag['type'].clone(), 'category': torch.zeros(A, dtype=torch.uint8), 'shape': ag['shape'].clone(),
+           'av_idx': torch.tensor([spec['ego']], dtype=torch.long)}
+    return raw, scene['pt_token']['position'].clone(), cfg, spec
