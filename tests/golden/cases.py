@@ -76,3 +76,19 @@ def build_prep_case(name: str):
            'type': ag['type'].clone(), 'category': torch.zeros(A, dtype=torch.uint8), 'shape': ag['shape'].clone(),
            'av_idx': torch.tensor([spec['ego']], dtype=torch.long)}
     return raw, scene['pt_token']['position'].clone(), cfg, spec
+
+
+# --- rows a15 / f4: teacher-forced InfGenAgentDecoder.forward, motion branch -------------------------------------------------
+FWD_CASES = {
+    'a24': dict(scene_seed=12, agents=24, map_tokens=768, ragged=0.6, ego=3, weight_seed=1),
+    'a64': dict(scene_seed=13, agents=64, map_tokens=2048, ragged=0.2, ego=5, weight_seed=0),
+}
+
+
+def build_fwd_case(name: str):
+    spec = FWD_CASES[name]
+    cfg = DecoderConfig(motion_beam_size=1, insert_beam_size=1, disable_insertion=False)
+    sd = make_state_dict(spec['weight_seed'])
+    scene = make_scene(spec['scene_seed'], num_agents=spec['agents'], num_map_tokens=spec['map_tokens'], num_steps=91,
+                       ragged=spec['ragged'], ego_index=spec['ego'], cfg=cfg)
+    return scene, sd, cfg, spec
