@@ -70,6 +70,10 @@ typedef struct {
     float a2sa_radius;            /* 10  heading stage, agents (agent_decoder.py:2028) */
     float pl2sa_radius;           /* 10  heading stage, map tokens (agent_decoder.py:2034) */
     float angle_interval;         /* 3   degrees per heading token (attr_tokenizer.py:20) */
+    /* teacher-forced pass (InfGenAgentDecoder.forward, agent_decoder.py:1104-1240): every column of the batch is given
+     * (hist_cols == n_cols, n_iters == 0) and every column is a destination; run with infgen_forward instead of
+     * prefill / step.  num_seed_feature must be 0 (the seed rows of _pad_feat are not part of the row space). */
+    int32_t teacher_forced;
 } infgen_config;
 
 /* One batch of scenes, already filtered/padded as agent_decoder.py:1609-1657 does (host side: infgen_b200/host.py). */
@@ -169,6 +173,12 @@ int32_t infgen_rollout(infgen_engine *e);
  * (their extent is read back first). */
 int32_t infgen_read(infgen_engine *e, const infgen_outputs *out, int32_t loc);
 int32_t infgen_iterations_done(infgen_engine *e);
+/* Motion branch of the teacher-forced pass (agent_decoder.py:1104-1240) over the loaded batch of
+ * an engine created with teacher_forced = 1: column by column, embedding -> edges whose destination is that column ->
+ * 6 x {temporal, map, agent} attention (K/V of the earlier columns from the cache) -> heads.  Outputs are COLUMN-major,
+ * [n_cols][R][...] with R = n_scenes * row_capacity (any may be NULL): x_a [T][R][128] last-layer features,
+ * token_logits [T][R][token_size] (next_token_prob), state_logits [T][R][3] (next_state_prob).  Synchronises. */
+int32_t infgen_forward(infgen_engine *e, float *x_a, float *token_logits, float *state_logits, int32_t loc);
 /* number of kernels this library launched (or replayed through graphs) since the engine was created */
 int64_t infgen_kernel_launches(infgen_engine *e);
 

@@ -27,6 +27,7 @@ class Config(C.Structure):
         ('seed', C.c_uint32), ('use_cuda_graph', C.c_int32), ('trace', C.c_int32),
         ('insert_beam_size', C.c_int32), ('debug_force_enter', C.c_int32), ('pl2seed_radius', C.c_float),
         ('a2sa_radius', C.c_float), ('pl2sa_radius', C.c_float), ('angle_interval', C.c_float),
+        ('teacher_forced', C.c_int32),
     ]
 
 
@@ -99,6 +100,7 @@ SYMBOLS = {
     'infgen_rollout': (C.c_int32, [C.c_void_p]),
     'infgen_read': (C.c_int32, [C.c_void_p, C.POINTER(Outputs), C.c_int32]),
     'infgen_iterations_done': (C.c_int32, [C.c_void_p]),
+    'infgen_forward': (C.c_int32, [C.c_void_p, c_f32p, c_f32p, c_f32p, C.c_int32]),
     'infgen_map_setup': (C.c_int32, [C.c_void_p, c_f32p, C.c_int32]),
     'infgen_map_encode': (C.c_int32, [C.c_void_p, C.POINTER(MapBatch), C.c_int32, c_f32p, c_f32p]),
     'infgen_prepare_scene': (C.c_int32, [C.c_void_p, C.POINTER(PrepIn), C.POINTER(PrepOut)]),

@@ -25,7 +25,7 @@ class B200AgentDecoder:
                  use_cuda_graph: bool = True, trace: bool = False, seed: int = 2024,
                  vocab: Optional[Dict[str, torch.Tensor]] = None,
                  map_state_dict: Optional[Dict[str, torch.Tensor]] = None,
-                 map_traj_src: Optional[torch.Tensor] = None):
+                 map_traj_src: Optional[torch.Tensor] = None, teacher_forced_cols: int = 0):
         """state_dict: `InfGenAgentDecoder.state_dict()` (None: an engine that only serves the map encoder).
         map_state_dict: `InfGenMapDecoder.state_dict()` - the engine then also runs the map encoder (`map_encode`) and
         `inference` accepts `map_enc=None`: x_pt is produced and consumed in HBM."""
@@ -50,12 +50,16 @@ class B200AgentDecoder:
         assert vocab_arr.shape == (3, TOKEN_SIZE, 6, 4, 2)
         cells = np.ascontiguousarray(grid.cells.numpy().astype(np.float32))
         c = _capi.Config(
-            abi_version=_capi.ABI_VERSION, device=device, num_layers=NUM_LAYERS, hist_cols=self.cfg.hist_cols,
+            abi_version=_capi.ABI_VERSION, device=device, num_layers=NUM_LAYERS,
+            hist_cols=teacher_forced_cols if teacher_forced_cols else self.cfg.hist_cols,
+            teacher_forced=int(bool(teacher_forced_cols)),
             window=self.cfg.window, shift=self.cfg.shift, num_historical_steps=self.cfg.num_historical_steps,
-            token_size=TOKEN_SIZE, grid_size=grid.grid_size, num_seed_feature=self.cfg.num_seed_feature,
+            token_size=TOKEN_SIZE, grid_size=grid.grid_size,
+            num_seed_feature=0 if teacher_forced_cols else self.cfg.num_seed_feature,
             max_pl2a_neighbors=self.cfg.max_pl2a_neighbors, max_a2a_neighbors=self.cfg.max_a2a_neighbors,
             pl2a_radius=self.cfg.pl2a_radius, a2a_radius=self.cfg.a2a_radius,
-            use_state_token=int(self.cfg.use_state_token), disable_insertion=int(self.cfg.disable_insertion),
+            use_state_token=int(self.cfg.use_state_token),
+            disable_insertion=1 if teacher_forced_cols else int(self.cfg.disable_insertion),
             motion_beam_size=self.cfg.motion_beam_size, seed=seed, use_cuda_graph=int(use_cuda_graph),
             trace=int(trace), insert_beam_size=self.cfg.insert_beam_size,
             debug_force_enter=int(self.cfg.debug_force_enter), pl2seed_radius=self.cfg.pl2seed_radius,
@@ -71,6 +75,7 @@ class B200AgentDecoder:
             traj = np.ascontiguousarray(torch.as_tensor(traj).float().reshape(traj.shape[0], -1).cpu().numpy())
             assert traj.shape[1] == MAP_TOKEN_DIM, traj.shape
             _capi.check(self.lib.infgen_map_setup(self._h, _capi.f32p(traj), traj.shape[0]))
+        self._state_dict_ref, self._vocab_ref, self._fwd = state_dict, vocab, {}
         self._batch: Optional[HostBatch] = None
         self._scenes: Optional[Sequence[SceneHost]] = None
         self._host_cache: Optional[HostBatch] = None
@@ -88,7 +93,17 @@ class B200AgentDecoder:
         """Build from a live reference `InfGenAgentDecoder` module (weights stay owned by the module)."""
         return cls(agent_encoder.state_dict(), cfg, **kw)
 
+    def forward(self, data: Dict, map_enc: Dict) -> Dict:
+        """Motion branch of the reference's teacher-forced `InfGenAgentDecoder.forward(data, map_enc)`
+        (agent_decoder.py:1104-1240 and the motion keys of its return value, :1388-1417, :1497-1507): see
+        infgen_b200/forward.py.  A second engine (every column a destination) is created on first use per column count."""
+        from .forward import teacher_forced_forward
+        return teacher_forced_forward(self, data, map_enc)
+
     def close(self):
+        for f in getattr(self, '_fwd', {}).values():
+            f.close()
+        self._fwd = {}
         if getattr(self, '_h', None):
             self.lib.infgen_destroy(self._h)
             self._h = None

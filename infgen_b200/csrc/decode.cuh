@@ -18,6 +18,8 @@ struct DecState {
     int a_stride;                  // agent<->agent slots per row: min(cap, max_a + 1)
     float r_m2, r_a2;              // squared radii
     int use_state_token, disable_insertion, beam;
+    int teacher_forced;            // InfGenAgentDecoder.forward: a temporal destination must itself be in the history mask
+                                   // (mask_t = hist x hist, agent_decoder.py:577-579; inference: hist x inference_mask)
     unsigned seed;
     const int *n_rows, *ego_row, *scene_id;
     int *col, *iter;               // device scalars: current column / iteration
@@ -74,7 +76,7 @@ __global__ void __launch_bounds__(NT) k_edge_build(const DecState s, int col_add
     if (kind == 0) {
         // ---- temporal: (r, c) -> (r, col), 0 < col - c <= W ------------------------------------------------------
         int cnt = 0;
-        if (i < n - s.q_rows) {
+        if (i < n - s.q_rows && (!s.teacher_forced || s.tsrc[(size_t)r * T + col] != 0)) {
             const int c = col - s.W + lane;
             const bool ok = lane < s.W && c >= 0 && s.tsrc[(size_t)r * T + c] != 0;
             const unsigned mask = __ballot_sync(0xffffffffu, ok);

@@ -1497,6 +1497,7 @@ int32_t infgen_load_scenes(infgen_engine *e, const infgen_scene_batch *b, int32_
     s.r_m2 = e->cfg.pl2a_radius * e->cfg.pl2a_radius; s.r_a2 = e->cfg.a2a_radius * e->cfg.a2a_radius;
     s.use_state_token = e->cfg.use_state_token; s.disable_insertion = e->cfg.disable_insertion;
     s.beam = e->cfg.motion_beam_size; s.seed = e->cfg.seed;
+    s.teacher_forced = e->cfg.teacher_forced;
     s.grid_cells = e->grid_cells; s.vocab = e->vocab;
     // ---- inputs ----
     int *d_n_rows, *d_ego, *d_sid, *d_type, *d_pt_ptr, *d_state_h, *d_token_h, *d_grid_h;
@@ -1754,6 +1755,53 @@ static int capture_iteration(infgen_engine *e, int which) {
     e->graph[which] = g;
     CK(cudaGraphGetNodes(g, nullptr, &e->graph_nodes[which]));
     CK(cudaGraphInstantiate(&e->graph_exec[which], g, 0));
+    return 0;
+}
+
+// Motion branch of the teacher-forced pass (agent_decoder.py:1104-1240): every column is embedded from the given token stream
+// and run through the stack as the destination column, in order, so that the temporal K/V of the earlier columns are in the
+// ring exactly as a closed-loop rollout would have left them (row a15 / f4).
+int32_t infgen_forward(infgen_engine *e, float *x_a, float *token_logits, float *state_logits, int32_t loc) {
+    if (!e || !e->loaded) return fail(INFGEN_ERR_STATE, "no scenes loaded");
+    if (!e->cfg.teacher_forced || e->st.HC != e->T || e->cfg.num_seed_feature != 0)
+        return fail(INFGEN_ERR_STATE, "infgen_forward needs an engine created with teacher_forced = 1, hist_cols == n_cols (%d vs %d) "
+                    "and num_seed_feature = 0", e->st.HC, e->T);
+    if (e->prefilled) return fail(INFGEN_ERR_STATE, "the batch has already been run");
+    DecState &s = e->st;
+    const int R = e->R, T = e->T, V = e->cfg.token_size;
+    float *d_x = nullptr, *d_tok = nullptr, *d_st = nullptr;
+    RET(ensure_t(e, "fwd_x", (size_t)T * R * 128, &d_x));
+    RET(ensure_t(e, "fwd_logits", (size_t)T * R * V, &d_tok));
+    RET(ensure_t(e, "fwd_state", (size_t)T * R * 3, &d_st));
+    CK(cudaMemsetAsync(s.col, 0, 2 * sizeof(int), e->stream));
+    for (int c = 0; c < T; ++c) {
+        RET(enqueue_embed_column(e, 0));
+        RET(enqueue_edges(e, 0));
+        RET(enqueue_layers(e, true, -1));
+        HeadArgs ha;
+        memset(&ha, 0, sizeof(ha));
+        ha.rows = scene_rows(e); ha.x = fbuf(e, "x"); ha.tok = e->h_tok; ha.st = e->h_state;
+        ha.part_v = fbuf(e, "part_v"); ha.part_i = (int *)e->bufs["part_i"].p;
+        ha.part_m = fbuf(e, "part_m"); ha.part_s = fbuf(e, "part_s"); ha.state_logits = fbuf(e, "state_logits");
+        ha.trace_head_in = d_x + (size_t)c * R * 128;
+        ha.trace_logits = d_tok + (size_t)c * R * V;
+        ha.trace_state = d_st + (size_t)c * R * 3;
+        {
+            ProfScope ps(e, KC_HEADS);
+            if (R > 512) k_heads<16><<<dim3((R + 15) / 16, NSLICE + 1), NT_S, heads_smem<16>(), e->stream>>>(ha);
+            else k_heads<HM><<<dim3((R + HM - 1) / HM, NSLICE + 1), NT_S, HEADS_SMEM, e->stream>>>(ha);
+        }
+        CKL(); count_launch(e);
+        k_set_scalar<<<1, 1, 0, e->stream>>>(s.col, c + 1);
+        CKL(); count_launch(e);
+    }
+    e->prefilled = 1;
+    const cudaMemcpyKind k = loc == INFGEN_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    if (x_a) CK(cudaMemcpyAsync(x_a, d_x, (size_t)T * R * 128 * sizeof(float), k, e->stream));
+    if (token_logits) CK(cudaMemcpyAsync(token_logits, d_tok, (size_t)T * R * V * sizeof(float), k, e->stream));
+    if (state_logits) CK(cudaMemcpyAsync(state_logits, d_st, (size_t)T * R * 3 * sizeof(float), k, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    RET(check_device_errors(e));
     return 0;
 }
 

@@ -3,12 +3,11 @@
 
     python tests/golden/make_golden_forward.py         # writes tests/golden/case_fwd_*.npz
 
-The reference method is called as is; forward hooks on `token_predict_head` / `state_predict_head` capture the motion
-branch's outputs (`next_token_prob`, `next_state_prob`, the last-layer feature `x_a`), and the call is ended right
-after them (`_build_occ_gt`, the first statement of the seed branch, is replaced by a function that raises) because
-the seed / refine branches are outside this row.  The extra fields `forward` reads at its top (grid offsets, heading
-tokens, entering order; `InfGen._fetch_enterings`) come from oracle/scene_prep_oracle.py, which is pinned against the
-reference's own `_fetch_enterings`."""
+The reference method is called as is and runs to its end (seed and refine branches included); the keys of the motion
+branch are taken from its return value (`x_a`, `next_token_prob`, `next_token_idx`, `next_token_idx_gt`,
+`next_token_eval_mask`, `next_state_prob`, `next_state_idx`, `next_state_idx_gt`, `next_state_eval_mask`).  The extra
+fields `forward` reads at its top (grid offsets, heading tokens, entering order; `InfGen._fetch_enterings`) come from
+oracle/scene_prep_oracle.py, which is pinned against the reference's own `_fetch_enterings`."""
 import os
 import sys
 import numpy as np
@@ -23,11 +22,11 @@ from oracle.scene_prep_oracle import fetch_enterings                           #
 from infgen_b200.grid import PositionGrid                                      # noqa: E402
 
 
-class _Stop(Exception):
-    pass
+MOTION_KEYS = ('next_token_idx', 'next_token_idx_gt', 'next_token_eval_mask', 'next_state_prob', 'next_state_idx',
+               'next_state_idx_gt', 'next_state_eval_mask')
 
 
-def reference_forward_motion(scene, sd, cfg):
+def reference_forward(scene, sd, cfg):
     dec = build_reference_decoder(sd, cfg)
     data = to_hetero(scene)
     ag = data['agent']
@@ -38,33 +37,29 @@ def reference_forward_motion(scene, sd, cfg):
     for k in ('grid_offset_xy', 'heading_token_idx', 'pos_xy', 'heading_theta', 'sort_indices', 'pt_grid_token_idx'):
         ag[k] = ent[k]
     A, P = ag['token_idx'].shape[0], data['pt_token']['position'].shape[0]
+    av = int(ag['av_index'][0])
     ag['batch'], ag['ptr'] = torch.zeros(A, dtype=torch.long), torch.tensor([0, A])
-    data['pt_token']['batch'] = torch.zeros(P, dtype=torch.long)
+    data['pt_token']['batch'], data['pt_token']['ptr'] = torch.zeros(P, dtype=torch.long), torch.tensor([0, P])
+    data['ego_pos'], data['ego_heading'] = ag['token_pos'][[av]], ag['token_heading'][[av]]
     data.num_graphs = 1
-    cap = {}
-    dec.token_predict_head.register_forward_hook(
-        lambda m, i, o: (cap.__setitem__('x_a', i[0].detach().clone()), cap.__setitem__('next_token_prob', o.detach().clone())) and None)
-    dec.state_predict_head.register_forward_hook(lambda m, i, o: cap.__setitem__('next_state_prob', o.detach().clone()))
-
-    def stop(*a, **k):
-        raise _Stop()
-    dec._build_occ_gt = stop
-    try:
-        with torch.no_grad():
-            dec.forward(data, {'x_pt': scene['map_enc']['x_pt'].clone()})
-    except _Stop:
-        pass
-    return {k: v[:A] for k, v in cap.items()}                     # rows [A, A + 10) are the seed rows (_pad_feat)
+    torch.manual_seed(0)                                          # (the seed branch draws random evaluation masks)
+    with torch.no_grad():
+        out = dec.forward(data, {'x_pt': scene['map_enc']['x_pt'].clone()})
+    res = {k: out[k] for k in MOTION_KEYS}
+    res['x_a'] = out['x_a'][:A]                                   # rows [A, A + 10) are the seed rows (_pad_feat)
+    res['next_token_prob'] = out['next_token_prob']
+    return res
 
 
 def main():
     for name in (sys.argv[1:] or list(FWD_CASES)):
         scene, sd, cfg, spec = build_fwd_case(name)
-        out = reference_forward_motion(scene, sd, cfg)
+        out = reference_forward(scene, sd, cfg)
         top_v, top_i = out['next_token_prob'].topk(8, dim=-1)
         save = {'x_a': out['x_a'].numpy(), 'next_state_prob': out['next_state_prob'].numpy(), 'top8_logit': top_v.numpy(),
                 'top8_index': top_i.numpy(), 'logit_sum': out['next_token_prob'].sum(-1).numpy(),
                 'logit_col5': out['next_token_prob'][:, 5].numpy()}
+        save.update({k: out[k].numpy() for k in MOTION_KEYS if k != 'next_state_prob'})
         path = os.path.join(os.path.dirname(os.path.abspath(__file__)), f'case_fwd_{name}.npz')
         np.savez_compressed(path, **save)
         print(f'{name}: x_a {tuple(out["x_a"].shape)}, {os.path.getsize(path) / 1e6:.2f} MB')
