@@ -55,6 +55,12 @@ constexpr int SM_FLOATS = SM_TMEM + 4;
 constexpr size_t SMEM = (size_t)SM_FLOATS * sizeof(float);
 static_assert(SMEM <= 227 * 1024, "shared memory budget");
 constexpr int MAX_JOBS = 20;
+#ifndef INFGEN_NTC_BACKOFF
+#define INFGEN_NTC_BACKOFF 0
+#endif
+// row warps poll their mbarriers without __nanosleep: one lane per warp polls, and a sleeping poller was measured to add
+// ~1-2 k cycles to every hand-over of the dependent chain (the sleep is far coarser than the 32 ns asked for)
+constexpr bool NTC_ROW_BACKOFF = INFGEN_NTC_BACKOFF != 0;
 // job code: blk[0:5) img[5] acc[6] accum[7] fresh[8] release[9] done[10] fold[11]
 __host__ __device__ constexpr uint32_t job(int blk, int img, int acc, int accum, int fresh, int done, int fold = 0) {
     return (uint32_t)blk | ((uint32_t)img << 5) | ((uint32_t)acc << 6) | ((uint32_t)accum << 7) | ((uint32_t)fresh << 8) |
@@ -308,7 +314,7 @@ __global__ void __launch_bounds__(ntc::THREADS, 1) k_node_tc(const NodeArgs a) {
         auto store_rows = [&](float *p, size_t mul, size_t add, const float *val) { reg2tile(val); tile2g(p, mul, add); };
         auto rt_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(RT) : "memory"); };
         auto warp_wait = [&](uint64_t *b, uint32_t parity, int code) {
-            if (lane == 0) ntc_wait<true>(b, parity, code);
+            if (lane == 0) ntc_wait<ntc::NTC_ROW_BACKOFF>(b, parity, code);
             __syncwarp();
             tc_fence_after();
         };

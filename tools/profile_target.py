@@ -1,6 +1,6 @@
 """Short workload for ncu: two closed-loop rollouts of the headline scene (64 agents, 2048 map tokens, 16 iterations).
     ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file out.csv \
-        python tools/profile_target.py [scenes] [graph]
+        python tools/profile_target.py [scenes] [graph] [insertion]
 The second rollout is the steady-state one (weights L2-resident)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -14,7 +14,8 @@ from infgen_b200.agent_decoder import B200AgentDecoder
 
 n_scenes = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 graph = bool(int(sys.argv[2])) if len(sys.argv) > 2 else False
-cfg = DecoderConfig(motion_beam_size=5, disable_insertion=True)
+insertion = bool(int(sys.argv[3])) if len(sys.argv) > 3 else False
+cfg = DecoderConfig(motion_beam_size=5, insert_beam_size=10, disable_insertion=not insertion)
 dec = B200AgentDecoder(make_state_dict(0), cfg, use_cuda_graph=graph)
 scenes = [make_scene(13 + i, num_agents=64, num_map_tokens=2048, num_steps=91, ragged=0.0, ego_index=5, cfg=cfg)
           for i in range(n_scenes)]
