@@ -904,24 +904,25 @@ static int enqueue_insertion_pass(infgen_engine *e) {
     {   // the query rows: 3 x {occ2sa, pt2sa, a2sa} with their edges
         LayerArgs la;
         memset(&la, 0, sizeof(la));
-        la.rows.n_total = ns * SEED_ROW_STRIDE; la.rows.cap = SEED_ROW_STRIDE; la.rows.n_rows = q.active;
+        la.rows.n_total = ns * q.seed_stride; la.rows.cap = q.seed_stride; la.rows.n_rows = q.active;
         la.rows.row_lo = nullptr;
         la.x = q.x_seed; la.ring = RING;
         la.pre0 = make_pre(e->occ2sa[0], false, nullptr, false, 0, false);
         const size_t kvl = (size_t)R * 256, kvm = (size_t)e->P * 256;
+        const int qshift = q.seed_stride == SEED_ROW_STRIDE ? 2 : 0, qwide = q.seed_stride == SEED_ROW_STRIDE ? 1 : 0;
         int n = 0;
         for (int i = 0; i < 3; ++i) {
             SubArgs &o = la.sub[n++];
-            o.w = e->occ2sa[i].cs_post; o.has_attn = 1; o.has_pos = 0; o.elist = 0; o.row_shift = 2; o.wide = 1;
+            o.w = e->occ2sa[i].cs_post; o.has_attn = 1; o.has_pos = 0; o.elist = 0; o.row_shift = qshift; o.wide = qwide;
             o.kv = q.kv_occ + (size_t)i * ns * 256; o.cnt = q.one_cnt; o.start = nullptr; o.stride = 1; o.src = q.occ_src;
             o.pre = make_pre(e->pt2sa[i], false, nullptr, false, 0, false);
             SubArgs &p = la.sub[n++];
-            p.w = e->pt2sa[i].cs_post; p.has_attn = 1; p.has_pos = 1; p.elist = 1; p.row_shift = 2; p.wide = 1;
+            p.w = e->pt2sa[i].cs_post; p.has_attn = 1; p.has_pos = 1; p.elist = 1; p.row_shift = qshift; p.wide = qwide;
             p.kv = fbuf(e, "kv_ms") + i * kvm; p.cnt = q.ps_cnt; p.start = nullptr; p.stride = SEED_MAP_MAX;
             p.src = q.ps_src; p.rhat = fbuf(e, "rhat_ps");
             p.pre = make_pre(e->a2sa[i], false, nullptr, false, 0, false);
             SubArgs &g = la.sub[n++];
-            g.w = e->a2sa[i].cs_post; g.has_attn = 1; g.has_pos = 1; g.elist = 2; g.row_shift = 2; g.wide = 1;
+            g.w = e->a2sa[i].cs_post; g.has_attn = 1; g.has_pos = 1; g.elist = 2; g.row_shift = qshift; g.wide = qwide;
             g.kv = fbuf(e, "kv_sa") + i * kvl; g.cnt = q.as_cnt; g.start = nullptr; g.stride = q.as_stride;
             g.src = q.as_src; g.rhat = fbuf(e, "rhat_as");
             if (i < 2) g.pre = make_pre(e->occ2sa[i + 1], false, nullptr, false, 0, false);
@@ -936,7 +937,7 @@ static int enqueue_insertion_pass(infgen_engine *e) {
     {   // the three grid-sized heads of the query rows in one launch
         MlpLayerArgs la;
         memset(&la, 0, sizeof(la));
-        la.n = ns * SEED_ROW_STRIDE; la.x = q.x_seed;
+        la.n = ns * q.seed_stride; la.x = q.x_seed;
         la.w = e->h_seed_pos; la.out = q.pos_logits;
         la.w2 = e->h_ag_occ; la.out2 = q.ag_occ_logits;
         la.w3 = e->h_pt_occ; la.out3 = q.pt_occ_logits;
@@ -1634,6 +1635,8 @@ int32_t infgen_load_scenes(infgen_engine *e, const infgen_scene_batch *b, int32_
         RET(ensure_t(e, "rhat_hp", (size_t)ns * NEW_MAP_MAX * 128, &tmp)); RET(ensure_t(e, "rhat_ha", (size_t)ns * NEW_AGENT_MAX * 128, &tmp));
         q.shape_rows = fbuf(e, "shape_rows");
         q.seed_feat = e->seed_feat; q.err = e->d_err;
+        // query rows: one per tile (all warps share its edges) while every scene's cluster fits one wave, packed otherwise
+        q.seed_stride = (ns <= MAX_CLUSTERS || getenv("INFGEN_SEED_WIDE")) ? SEED_ROW_STRIDE : 1;
         s.ins_col = q.ins_col;
         RET(ensure_t(e, "hv_src", R, &s.hv_src));
         CK(cudaMemsetAsync(s.hv_src, 0xff, (size_t)R * sizeof(int), e->stream));

@@ -24,9 +24,13 @@ constexpr int NEW_AGENT_MAX = 24;      // (:2029)
 constexpr int INSERT_LIMIT = 10;       // (:1738)
 constexpr int SEED_SLOTS = INSERT_LIMIT + 1;
 constexpr int SEED_ROW_STRIDE = 4;     // the query row of scene b is row 4b of its own row space: alone in its tile, so that
-                                       // all warps of the CTA share its (up to 2048) edges
+                                       // all warps of the CTA share its (up to 2048) edges (InsState::seed_stride = 4).
+                                       // Batches of more than one wave of clusters pack the query rows instead
+                                       // (seed_stride = 1: four scenes per tile, two warps per row): 32 scenes are 8 clusters
+                                       // in one wave, not 32 clusters in three
 
 struct InsState {
+    int seed_stride;                   // rows between the query rows of consecutive scenes: SEED_ROW_STRIDE or 1
     int beam;                          // insert_beam_size
     int force_enter;                   // the reference's DEBUG=1 switch (:1888-1889)
     unsigned seed;
@@ -326,7 +330,7 @@ __global__ void __launch_bounds__(NT) k_seed_prepare(const SeedPrepArgs a) {
     for (int i = 0; i < 3; ++i)
         gemv256(sn3[i], a.occ2sa[i].w_kv, a.occ2sa[i].b_kv, q.kv_occ + ((size_t)i * gridDim.x + b) * 256);
     // ---- query row feature ----
-    if (tid < 128) q.x_seed[(size_t)b * SEED_ROW_STRIDE * 128 + tid] = q.seed_feat[tid];
+    if (tid < 128) q.x_seed[(size_t)b * q.seed_stride * 128 + tid] = q.seed_feat[tid];
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -352,7 +356,7 @@ __device__ __forceinline__ void seed_decide_scene(const SeedDecideArgs &a) {
     const int b = blockIdx.x, col = *s.col, t = *s.iter, T = s.T, G = s.G, S = s.S;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (!q.active[b]) return;
-    if (tid < 128) sx[tid] = q.x_seed[(size_t)b * SEED_ROW_STRIDE * 128 + tid];
+    if (tid < 128) sx[tid] = q.x_seed[(size_t)b * q.seed_stride * 128 + tid];
     __syncthreads();
     // ---- the three small heads (state, type, shape; layers.py:206-215): hidden layers, LayerNorms by three warps, then
     //      the 2 + 3 + 3 outputs as one 128-dot per warp ----
@@ -368,7 +372,7 @@ __device__ __forceinline__ void seed_decide_scene(const SeedDecideArgs &a) {
         if (lane == 0) s_small[warp] = d + __ldg(w.b3 + n);
     }
     // ---- position: softmax over the grid, top-k, draw (:1896-1902).  Warp w owns a contiguous slice of the cells ----
-    const float *lg = q.pos_logits + (size_t)b * SEED_ROW_STRIDE * G;
+    const float *lg = q.pos_logits + (size_t)b * q.seed_stride * G;
     const int per = (G + NWARP - 1) / NWARP, g0 = warp * per, g1 = min(G, g0 + per);
     constexpr int VPL = 8;                              // cells per lane (G <= 8 * 32 * NWARP)
     float v[VPL];
@@ -534,8 +538,8 @@ __device__ __forceinline__ void seed_decide_scene(const SeedDecideArgs &a) {
     const size_t ob = (size_t)r * G;
     for (int g = tid; g < G; g += NT) {
         q.rec_pos_prob[ob + g] = expf(lg[g] - gmax) / den;
-        q.rec_ag_occ[ob + g] = q.ag_occ_logits[(size_t)b * SEED_ROW_STRIDE * G + g];
-        q.rec_pt_occ[ob + g] = q.pt_occ_logits[(size_t)b * SEED_ROW_STRIDE * G + g];
+        q.rec_ag_occ[ob + g] = q.ag_occ_logits[(size_t)b * q.seed_stride * G + g];
+        q.rec_pt_occ[ob + g] = q.pt_occ_logits[(size_t)b * q.seed_stride * G + g];
         q.rec_occ_gt[ob + g] = q.occ[(size_t)b * G + g];
     }
 }

@@ -251,6 +251,34 @@ def test_insertion_batch_equals_single():
             _close(x[k].numpy(), y[k].numpy(), f'scene {b} {k}')
 
 
+def test_insertion_packed_query_rows_equal_wide_mode(monkeypatch):
+    """More scenes than one wave of clusters (18 > 15): the seed-query rows are packed four scenes per tile (two warps per
+    row) instead of one scene per tile with all warps on its edges.  Same rollouts as the wide mode forced on the same
+    batch (INFGEN_SEED_WIDE=1), insertion stage live, top-3 position sampling."""
+    from infgen_b200.weights import make_state_dict
+    from infgen_b200.synth import make_scene
+    cfg = DecoderConfig(motion_beam_size=1, insert_beam_size=3, disable_insertion=False, debug_force_enter=True)
+    sd = make_state_dict(2)
+    scenes = [make_scene(60 + i, num_agents=8 + (i % 5), num_map_tokens=256 + 64 * (i % 3), num_steps=91, ragged=0.2,
+                         ego_index=i % 3, cfg=cfg) for i in range(18)]
+    maps = [s['map_enc'] for s in scenes]
+    dec = _make_decoder(sd, cfg, use_cuda_graph=True)
+    packed = dec.inference_batch(scenes, maps, scene_ids=list(range(18)))
+    dec.close()
+    monkeypatch.setenv('INFGEN_SEED_WIDE', '1')
+    dec = _make_decoder(sd, cfg, use_cuda_graph=True)
+    wide = dec.inference_batch(scenes, maps, scene_ids=list(range(18)))
+    dec.close()
+    inserted = 0
+    for b, (x, y) in enumerate(zip(packed, wide)):
+        inserted += x['pos_a'].shape[0] - scenes[b]['agent']['token_pos'].shape[0]
+        for k in ('next_token_idx', 'next_state_idx', 'agent_id', 'pred_type'):
+            assert torch.equal(x[k], y[k]), (b, k)
+        for k in ('pos_a', 'head_a', 'pred_traj', 'pred_head', 'next_pos_rel_prob_seed'):
+            _close(x[k].numpy(), y[k].numpy(), f'scene {b} {k}')
+    assert inserted > 18
+
+
 def test_long_horizon_matches_oracle():
     """A horizon longer than the scene (num_recurrent_steps_val = 150 -> 30 iterations, 32 columns): the temporal K/V ring
     (16 slots for a 12-column window) wraps twice; greedy tokens and trajectories against the oracle."""
