@@ -978,7 +978,7 @@ static int enqueue_heading_stage(infgen_engine *e) {
     RET(enqueue_embed_rows(e, q.row_lo));       // feature of the new row with the dummy heading
     {
         ProfScope ps(e, KC_INSERT);
-        k_new_edges<<<ns, 64, 0, st>>>(s, q);
+        k_new_edges<<<ns, NEW_EDGE_NT, 0, st>>>(s, q);
     }
     CKL(); count_launch(e);
     FourierArgs hj[2];

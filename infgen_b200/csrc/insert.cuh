@@ -580,7 +580,9 @@ __global__ void __launch_bounds__(NT) k_seed_decide(const SeedDecideArgs a) {
 // heading stage, edges of the appended rows (:2024-2035): agents within a2sa_radius (first NEW_AGENT_MAX by index)
 // that interact at column cur, map tokens within pl2sa_radius (first NEW_MAP_MAX).  One CTA (two warps) per scene.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) k_new_edges(const DecState s, const InsState q) {
+constexpr int NEW_EDGE_NT = 256;       // warp 0: agents; warps 1..7: contiguous slices of the scene's map tokens
+__global__ void __launch_bounds__(NEW_EDGE_NT) k_new_edges(const DecState s, const InsState q) {
+    __shared__ int s_cnt[NEW_EDGE_NT / 32];
     const int b = blockIdx.x, col = *s.col, T = s.T;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i_new = q.new_row[b];
@@ -593,7 +595,26 @@ __global__ void __launch_bounds__(64) k_new_edges(const DecState s, const InsSta
     const float px = s.pos[((size_t)r * T + col) * 2], py = s.pos[((size_t)r * T + col) * 2 + 1];
     const float hd = s.head[(size_t)r * T + col];
     const float hx = cosf(hd), hy = sinf(hd);
-    if (warp == 0) {
+    // map tokens: the first NEW_MAP_MAX within the radius by ascending index.  A single warp walking the (up to 2048) tokens
+    // 32 at a time is a chain of 64 dependent global round trips (41 us measured); seven warps count the hits of their
+    // slices first, then write them behind the slices before them.
+    constexpr int NMW = NEW_EDGE_NT / 32 - 1;
+    const int pt0 = s.pt_ptr[b], pt1 = s.pt_ptr[b + 1];
+    const int per = (((pt1 - pt0 + NMW - 1) / NMW) + 31) & ~31;
+    const int p_lo = pt0 + (warp - 1) * per, p_hi = min(pt1, p_lo + per);
+    if (warp > 0) {
+        int cnt = 0;
+        for (int p0 = p_lo; p0 < p_hi; p0 += 32) {
+            const int p = p0 + lane;
+            bool ok = false;
+            if (p < p_hi) {
+                const float dx = __fsub_rn(__ldg(s.pt_pos + (size_t)p * 2), px), dy = __fsub_rn(__ldg(s.pt_pos + (size_t)p * 2 + 1), py);
+                ok = dist2(dx, dy) < q.r_new_m2;
+            }
+            cnt += __popc(__ballot_sync(0xffffffffu, ok));
+        }
+        if (lane == 0) s_cnt[warp] = cnt;
+    } else {
         int cnt = 0, seen = 0;
         const int base = b * NEW_AGENT_MAX;
         for (int j0 = 0; j0 < n; j0 += 32) {
@@ -620,31 +641,39 @@ __global__ void __launch_bounds__(64) k_new_edges(const DecState s, const InsSta
             seen += __popc(wm);
         }
         if (lane == 0) { q.ha_cnt[r] = cnt; q.ha_start[r] = base; q.ha_cnt_s[b] = cnt; }
-    } else {
-        const int pt0 = s.pt_ptr[b], pt1 = s.pt_ptr[b + 1];
-        const int base = b * NEW_MAP_MAX;
-        int cnt = 0;
-        for (int p0 = pt0; p0 < pt1 && cnt < NEW_MAP_MAX; p0 += 32) {
-            const int p = p0 + lane;
-            float dx = 0.f, dy = 0.f;
-            bool ok = false;
-            if (p < pt1) {
-                dx = __fsub_rn(s.pt_pos[(size_t)p * 2], px);
-                dy = __fsub_rn(s.pt_pos[(size_t)p * 2 + 1], py);
-                ok = dist2(dx, dy) < q.r_new_m2;
-            }
-            const unsigned mask = __ballot_sync(0xffffffffu, ok);
-            const int rank = cnt + __popc(mask & lanemask_lt());
-            if (ok && rank < NEW_MAP_MAX) {
-                const int slot = base + rank;
-                q.hp_src[slot] = p;
-                q.hp_raw[(size_t)slot * 3 + 0] = norm2(dx, dy);
-                q.hp_raw[(size_t)slot * 3 + 1] = angle_between(hx, hy, dx, dy);
-                q.hp_raw[(size_t)slot * 3 + 2] = wrap_angle(__fsub_rn(s.pt_ori[p], hd));
-            }
-            cnt = min(NEW_MAP_MAX, cnt + __popc(mask));
+    }
+    __syncthreads();
+    if (warp == 0) {
+        if (lane == 0) {
+            int tot = 0;
+            for (int w = 1; w <= NMW; ++w) tot += s_cnt[w];
+            tot = min(tot, NEW_MAP_MAX);
+            q.hp_cnt[r] = tot; q.hp_start[r] = b * NEW_MAP_MAX; q.hp_cnt_s[b] = tot;
         }
-        if (lane == 0) { q.hp_cnt[r] = cnt; q.hp_start[r] = base; q.hp_cnt_s[b] = cnt; }
+        return;
+    }
+    int cnt = 0;                                      // hits of the slices before this warp's
+    for (int w = 1; w < warp; ++w) cnt += s_cnt[w];
+    const int base = b * NEW_MAP_MAX;
+    for (int p0 = p_lo; p0 < p_hi && cnt < NEW_MAP_MAX; p0 += 32) {
+        const int p = p0 + lane;
+        float dx = 0.f, dy = 0.f;
+        bool ok = false;
+        if (p < p_hi) {
+            dx = __fsub_rn(__ldg(s.pt_pos + (size_t)p * 2), px);
+            dy = __fsub_rn(__ldg(s.pt_pos + (size_t)p * 2 + 1), py);
+            ok = dist2(dx, dy) < q.r_new_m2;
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, ok);
+        const int rank = cnt + __popc(mask & lanemask_lt());
+        if (ok && rank < NEW_MAP_MAX) {
+            const int slot = base + rank;
+            q.hp_src[slot] = p;
+            q.hp_raw[(size_t)slot * 3 + 0] = norm2(dx, dy);
+            q.hp_raw[(size_t)slot * 3 + 1] = angle_between(hx, hy, dx, dy);
+            q.hp_raw[(size_t)slot * 3 + 2] = wrap_angle(__fsub_rn(__ldg(s.pt_ori + p), hd));
+        }
+        cnt += __popc(mask);
     }
 }
 
