@@ -964,6 +964,22 @@ static int enqueue_heading_stage(infgen_engine *e) {
     const int ns = e->n_scenes, R = e->R;
     cudaStream_t st = e->stream;
     float *x = fbuf(e, "x"), *x_sa = fbuf(e, "x_sa"), *x_ha = fbuf(e, "x_ha");
+    // the new row's edges and their relative embeddings only need its pose: on the side stream, concurrently with its
+    // categorical / column embedding (two chains of ~50 us each per inserted agent)
+    RET(side_fork(e, [&]() -> int {
+        {
+            ProfScope ps(e, KC_INSERT);
+            k_new_edges<<<ns, NEW_EDGE_NT, 0, e->stream>>>(s, q);
+        }
+        CKL(); count_launch(e);
+        FourierArgs hj[2];
+        memset(hj, 0, sizeof(hj));
+        hj[0].normalize = 1; hj[0].dim = 3; hj[0].n_slots = ns * NEW_MAP_MAX; hj[0].cnt = q.hp_cnt_s; hj[0].stride = NEW_MAP_MAX;
+        hj[0].raw = q.hp_raw; hj[0].w = e->f_m; hj[0].out = fbuf(e, "rhat_hp");
+        hj[1].normalize = 1; hj[1].dim = 3; hj[1].n_slots = ns * NEW_AGENT_MAX; hj[1].cnt = q.ha_cnt_s; hj[1].stride = NEW_AGENT_MAX;
+        hj[1].raw = q.ha_raw; hj[1].w = e->f_a; hj[1].out = fbuf(e, "rhat_ha");
+        return launch_fourier(e, hj, 2, KC_INS_FOURIER);
+    }));
     // categorical embedding row of the new agent: type_a_emb[type] + shape_emb(shape)
     MlpEmbArgs ma;
     memset(&ma, 0, sizeof(ma));
@@ -976,18 +992,7 @@ static int enqueue_heading_stage(infgen_engine *e) {
     }
     CKL(); count_launch(e);
     RET(enqueue_embed_rows(e, q.row_lo));       // feature of the new row with the dummy heading
-    {
-        ProfScope ps(e, KC_INSERT);
-        k_new_edges<<<ns, NEW_EDGE_NT, 0, st>>>(s, q);
-    }
-    CKL(); count_launch(e);
-    FourierArgs hj[2];
-    memset(hj, 0, sizeof(hj));
-    hj[0].normalize = 1; hj[0].dim = 3; hj[0].n_slots = ns * NEW_MAP_MAX; hj[0].cnt = q.hp_cnt_s; hj[0].stride = NEW_MAP_MAX;
-    hj[0].raw = q.hp_raw; hj[0].w = e->f_m; hj[0].out = fbuf(e, "rhat_hp");
-    hj[1].normalize = 1; hj[1].dim = 3; hj[1].n_slots = ns * NEW_AGENT_MAX; hj[1].cnt = q.ha_cnt_s; hj[1].stride = NEW_AGENT_MAX;
-    hj[1].raw = q.ha_raw; hj[1].w = e->f_a; hj[1].out = fbuf(e, "rhat_ha");
-    RET(launch_fourier(e, hj, 2, KC_INS_FOURIER));
+    RET(side_join(e));
     {   // the new rows through 3 x {pt2a, a2a} with their 10 m neighbourhoods
         LayerArgs la;
         memset(&la, 0, sizeof(la));

@@ -117,6 +117,50 @@ __device__ __forceinline__ void ntc_wait(uint64_t *b, uint32_t parity, int code)
     }
 }
 
+// The 12 MMAs of one 32-k chunk (four k-steps x {A_lo B_hi, A_hi B_lo, A_hi B_hi}) as ONE instruction sequence behind a single
+// elect.sync: at = TMEM address of the A stage ([hi 32 | lo 32] columns), b0 = descriptor of the chunk's B_hi image (B_lo is
+// 16 KB = 1024 descriptor units behind, a k-step is 4 KB = 256 units).  keep_first = 0 overwrites the accumulator.
+// (One elect.sync + setp per MMA made the issuing warp, not the tensor core, the pace setter: ~98 cycles per MMA.)
+__device__ __forceinline__ void umma_chunk_tf32x3(uint32_t acc, uint32_t at, uint64_t b0, uint32_t keep_first) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, pe, pt;\n\t"
+        ".reg .b32 ah, al;\n\t"
+        ".reg .b64 bh, bl;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.eq.b32 pt, %3, %3;\n\t"
+        "add.u32 al, %1, 32;\n\t"
+        "add.u64 bl, %2, 1024;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [al], %2, %3, p;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bl, %3, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, pt;\n\t"
+        "add.u32 ah, %1, 8;\n\t"
+        "add.u32 al, %1, 40;\n\t"
+        "add.u64 bh, %2, 256;\n\t"
+        "add.u64 bl, %2, 1280;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [al], bh, %3, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah], bl, %3, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah], bh, %3, pt;\n\t"
+        "add.u32 ah, %1, 16;\n\t"
+        "add.u32 al, %1, 48;\n\t"
+        "add.u64 bh, %2, 512;\n\t"
+        "add.u64 bl, %2, 1536;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [al], bh, %3, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah], bl, %3, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah], bh, %3, pt;\n\t"
+        "add.u32 ah, %1, 24;\n\t"
+        "add.u32 al, %1, 56;\n\t"
+        "add.u64 bh, %2, 768;\n\t"
+        "add.u64 bl, %2, 1792;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [al], bh, %3, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah], bl, %3, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah], bh, %3, pt;\n\t"
+        "}\n" ::"r"(acc),
+        "r"(at), "l"(b0), "r"(ftc::IDESC), "r"(keep_first)
+        : "memory");
+}
+
 // [128 k][128 n] row-major (element (k, n) at k * 128 + n) -> packed [32 k4][128 n][4]
 __global__ void k_pack_kn(const float *__restrict__ src, float *__restrict__ dst) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -225,16 +269,7 @@ __global__ void __launch_bounds__(ntc::THREADS, 1) k_node_tc(const NodeArgs a) {
                 const uint32_t at = tmem + TC_A + 64u * (uint32_t)c;
                 const uint64_t b0 = umma_desc(smem_u32(sB + sb * CHUNK));
                 if (!is_fold) {
-                    const uint32_t acc = tmem + (ab ? ACC1 : ACC0);
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const uint32_t ah = at + 8u * ks, al = at + 32u + 8u * ks;
-                        const uint64_t bh = b0 + (uint64_t)(ks * (4096 >> 4)), bl = bh + (16384 >> 4);
-                        const uint32_t keep = (accum ? 1u : 0u) | (c > 0) | (ks > 0);
-                        umma_tf32_ts(acc, al, bh, keep);
-                        umma_tf32_ts(acc, ah, bl, 1u);
-                        umma_tf32_ts(acc, ah, bh, 1u);
-                    }
+                    umma_chunk_tf32x3(tmem + (ab ? ACC1 : ACC0), at, b0, (accum ? 1u : 0u) | (c > 0));
                 } else {
                     // relative-query fold: heads 2c, 2c + 1 are the two 16-k halves of this chunk, each with its own accumulator
                     for (int hh = 0; hh < 2; ++hh) {
