@@ -617,6 +617,11 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
         }
         __syncthreads();
         // ---- agg2 = agg + Wvr ragg' + bvr * sal  -> all CTAs ---------------------------------------------------
+        if (!A.has_attn) {
+            // edge-less pass (insertion stage: K|V of source-only rows): agg2 = 0 for every head - nothing to exchange
+            for (int o = tid; o < M * 32; o += NT) st4(scat + (o >> 5) * LD2 + 4 * (o & 31), z4);
+            __syncthreads();
+        } else {
         xexpect(0, M * 128 * 4);
         if (A.has_pos) {
             slice_gemm<M, 16, (M == 4 ? 2 : 4)>(sragg, LD1, wpost + cs_post::WVR, 32, sred, [&](int m, int n, float v) {
@@ -627,6 +632,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
             for (int o = tid; o < M * 16; o += NT) xsend(scat + (o >> 4) * LD2 + 16 * c + (o & 15), 0, sagg[o]);
         }
         xwait(0);
+        }
         stamp();
         // ---- gate: g = sigmoid(Wg [agg | xd] + bg);  u = agg + g * (s - agg) ----------------------------------
         xexpect(1, M * 128 * 4);
