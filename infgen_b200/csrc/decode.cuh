@@ -389,6 +389,7 @@ struct ColEmbArgs {
     const float *state_tab;    // [4][128]
     const float *grid_tab;     // [grid_size+1][128]
     float *out;                // [R][128]
+    float *out2, *out3;        // optional copies of the embedded rows (insertion stage: inputs of the two edge-less stacks)
 };
 constexpr int XLD = 516;       // leading dimension of the 512-wide fusion input
 constexpr int COLEMB_SMEM_FLOATS = WS_SMEM_FLOATS + EM * XLD + EM * FLD + 2 * EM * HLD + EM * 4;
@@ -456,7 +457,11 @@ __global__ void __launch_bounds__(NT_S) k_embed_column(const ColEmbArgs a) {
     csync();
     mlp3_body<EM>(ws, a.fusion, sX, XLD, 128, sH, sA, [&](int m, int n, float v) {
         const int r = s_row[m];
-        if (r >= 0) a.out[(size_t)r * 128 + n] = v;
+        if (r >= 0) {
+            a.out[(size_t)r * 128 + n] = v;
+            if (a.out2) a.out2[(size_t)r * 128 + n] = v;
+            if (a.out3) a.out3[(size_t)r * 128 + n] = v;
+        }
     });
 }
 

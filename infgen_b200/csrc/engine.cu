@@ -550,13 +550,14 @@ static int enqueue_embed_column(infgen_engine *e, int col_add) {
     return 0;
 }
 
-static int enqueue_embed_rows(infgen_engine *e, const int *row_lo) {
+static int enqueue_embed_rows(infgen_engine *e, const int *row_lo, float *out2 = nullptr, float *out3 = nullptr) {
     DecState &s = e->st;
     ColEmbArgs ca;
     memset(&ca, 0, sizeof(ca));
     ca.rows = new_rows(e); ca.fx = e->f_x; ca.fusion = e->e_fusion;
     ca.s = s; ca.col_add = 0; ca.cat_tab = fbuf(e, "cat_tab");
     ca.tok_tab = e->tok_tab; ca.state_tab = e->state_emb; ca.grid_tab = e->grid_tab; ca.out = fbuf(e, "x");
+    ca.out2 = out2; ca.out3 = out3;
     {
         ProfScope ps(e, KC_INSERT);
         k_embed_column<<<row_tiles(ca.rows, EM), NT_S, COLEMB_SMEM, e->stream>>>(ca);
@@ -829,7 +830,6 @@ static int enqueue_edgeless(infgen_engine *e, const int *row_lo, float *x, bool 
     la.n_sub = n;
     return launch_layer(e, la, KC_INS_LAYER_AGENTS);
 }
-static int enqueue_embed_rows(infgen_engine *e, const int *row_lo);
 
 // Run `fn` on the side stream, concurrently with what the caller enqueues on the engine stream until side_join().  Works
 // the same inside a stream capture (parallel branches of the graph) and outside; profiled runs stay serial (the per-class
@@ -1023,13 +1023,9 @@ static int enqueue_heading_stage(infgen_engine *e) {
         k_head_finalize<<<ns, NT, 0, st>>>(ha);
     }
     CKL(); count_launch(e);
-    RET(enqueue_embed_rows(e, q.row_lo));       // final feature of the new row (:2086-2097)
-    // the new rows become sources of later passes: their edge-less K|V rows of both stacks
-    {
-        ProfScope ps(e, KC_INSERT);
-        k_copy_new_rows2<<<ns, 128, 0, st>>>(s, q.row_lo, x, x_sa, x_ha);
-    }
-    CKL(); count_launch(e);
+    // final feature of the new row (:2086-2097), also written to the inputs of the two edge-less stacks: the new rows become
+    // sources of later passes
+    RET(enqueue_embed_rows(e, q.row_lo, x_sa, x_ha));
     // off the critical path of the next pass (which needs the seed-stack K|V rows first): the heading-stack K|V rows of
     // the new rows and the relative embedding of their edge towards the query row
     RET(side_fork(e, [&]() -> int {
