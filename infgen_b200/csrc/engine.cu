@@ -157,6 +157,8 @@ struct infgen_engine {
     cudaStream_t stream = nullptr, own_stream = nullptr;
     cudaStream_t side_stream = nullptr;                 // edges of the next column, concurrent with its embedding
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t side_stream2 = nullptr;                // second concurrent branch (occupancy node of the next insertion pass)
+    cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr;
     bool early_edges = false;                           // motion-only engines build the next column's edges early
     float *blob = nullptr;
     float *cs_blob = nullptr;                           // cluster-sliced AttentionLayer chunks (layer.cuh)
@@ -852,6 +854,43 @@ static int side_join(infgen_engine *e) {
     CK(cudaStreamWaitEvent(e->stream, e->ev_join, 0));
     return 0;
 }
+// the same on the second side stream (a branch that stays open across several fork / join pairs of the first)
+template <typename Fn>
+static int side2_fork(infgen_engine *e, Fn fn) {
+    if (e->profile) return fn();
+    cudaStream_t main = e->stream;
+    CK(cudaEventRecord(e->ev_fork2, main));
+    CK(cudaStreamWaitEvent(e->side_stream2, e->ev_fork2, 0));
+    e->stream = e->side_stream2;
+    const int rc = fn();
+    e->stream = main;
+    RET(rc);
+    CK(cudaEventRecord(e->ev_join2, e->side_stream2));
+    return 0;
+}
+static int side2_join(infgen_engine *e) {
+    if (e->profile) return 0;
+    CK(cudaStreamWaitEvent(e->stream, e->ev_join2, 0));
+    return 0;
+}
+
+// Inputs of the next seed query that do not come out of attention layers: the occupancy node (grid occupancy ->
+// seed_agent_occ_embed -> K|V of the three occ2sa layers, :1850-1859) and the query row's input feature.  They only depend on
+// the grid cells of the rows at column cur, which are final the moment a row is appended (k_seed_decide), so the kernel runs
+// beside the edge-less stacks at the start of the stage and beside the heading stage of an appended row - never in the chain
+// query -> heads -> decision of a pass.
+static int enqueue_seed_prepare(infgen_engine *e) {
+    SeedPrepArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.s = e->st; pa.q = e->ins; pa.occ_embed = e->h_occ_embed;
+    for (int i = 0; i < 3; ++i) pa.occ2sa[i] = e->occ2sa[i];
+    {
+        ProfScope ps(e, KC_INSERT);
+        k_seed_prepare<<<e->n_scenes, NT, 0, e->stream>>>(pa);
+    }
+    CKL(); count_launch(e);
+    return 0;
+}
 
 static int enqueue_insertion_begin(infgen_engine *e) {
     DecState &s = e->st;
@@ -873,6 +912,7 @@ static int enqueue_insertion_begin(infgen_engine *e) {
         k_copy_new_rows2<<<ns, 128, 0, st>>>(s, nullptr, fbuf(e, "x"), fbuf(e, "x_sa"), fbuf(e, "x_ha"));
     }
     CKL(); count_launch(e);
+    RET(side2_fork(e, [&]() -> int { return enqueue_seed_prepare(e); }));
     RET(side_fork(e, [&]() -> int {
         FourierArgs fj[2];
         memset(fj, 0, sizeof(fj));
@@ -884,7 +924,8 @@ static int enqueue_insertion_begin(infgen_engine *e) {
         return enqueue_edgeless(e, nullptr, fbuf(e, "x_ha"), false);
     }));
     RET(enqueue_edgeless(e, nullptr, fbuf(e, "x_sa"), true));
-    return side_join(e);
+    RET(side_join(e));
+    return side2_join(e);
 }
 
 static int enqueue_insertion_pass(infgen_engine *e) {
@@ -892,15 +933,6 @@ static int enqueue_insertion_pass(infgen_engine *e) {
     InsState &q = e->ins;
     const int ns = e->n_scenes, R = e->R;
     cudaStream_t st = e->stream;
-    SeedPrepArgs pa;
-    memset(&pa, 0, sizeof(pa));
-    pa.s = s; pa.q = q; pa.occ_embed = e->h_occ_embed;
-    for (int i = 0; i < 3; ++i) pa.occ2sa[i] = e->occ2sa[i];
-    {
-        ProfScope ps(e, KC_INSERT);
-        k_seed_prepare<<<ns, NT, 0, st>>>(pa);
-    }
-    CKL(); count_launch(e);
     {   // the query rows: 3 x {occ2sa, pt2sa, a2sa} with their edges
         LayerArgs la;
         memset(&la, 0, sizeof(la));
@@ -964,6 +996,8 @@ static int enqueue_heading_stage(infgen_engine *e) {
     const int ns = e->n_scenes, R = e->R;
     cudaStream_t st = e->stream;
     float *x = fbuf(e, "x"), *x_sa = fbuf(e, "x_sa"), *x_ha = fbuf(e, "x_ha");
+    // the occupancy node of the next pass: the appended row's cell is known
+    RET(side2_fork(e, [&]() -> int { return enqueue_seed_prepare(e); }));
     // the new row's edges and their relative embeddings only need its pose: on the side stream, concurrently with its
     // categorical / column embedding (two chains of ~50 us each per inserted agent)
     RET(side_fork(e, [&]() -> int {
@@ -1037,7 +1071,8 @@ static int enqueue_heading_stage(infgen_engine *e) {
         return enqueue_edgeless(e, q.row_lo, x_ha, false, true);
     }));
     RET(enqueue_edgeless(e, q.row_lo, x_sa, true, true));
-    return side_join(e);
+    RET(side_join(e));
+    return side2_join(e);
 }
 
 // host-driven loop (plain launches)
@@ -1324,6 +1359,9 @@ int32_t infgen_create(const infgen_config *cfg, const float *weights, int64_t n_
     CK(cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&e->side_stream2, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&e->ev_fork2, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->ev_join2, cudaEventDisableTiming));
     e->early_edges = cfg->disable_insertion != 0 && !getenv("INFGEN_NO_EARLY_EDGES");   // (debug tools compare per-iteration edges)
     CK(cudaMalloc(&e->blob, (size_t)g_total * sizeof(float)));
     CK(cudaMemcpyAsync(e->blob, weights, (size_t)g_total * sizeof(float), cudaMemcpyHostToDevice, e->stream));
@@ -1424,6 +1462,9 @@ int32_t infgen_destroy(infgen_engine *e) {
     if (e->side_stream) cudaStreamDestroy(e->side_stream);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
+    if (e->side_stream2) cudaStreamDestroy(e->side_stream2);
+    if (e->ev_fork2) cudaEventDestroy(e->ev_fork2);
+    if (e->ev_join2) cudaEventDestroy(e->ev_join2);
     delete e;
     return 0;
 }

@@ -270,7 +270,6 @@ __global__ void __launch_bounds__(NT) k_seed_prepare(const SeedPrepArgs a) {
     const int b = blockIdx.x, col = *s.col, T = s.T, G = s.G;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n = s.n_rows[b], r0 = b * s.cap;
-    if (tid == 0) { q.new_row[b] = -1; q.row_lo[b] = n; }
     if (!q.active[b]) return;
     // ---- occupancy (:1851-1853) ----
     float *occ = q.occ + (size_t)b * G;
@@ -355,6 +354,7 @@ __device__ __forceinline__ void seed_decide_scene(const SeedDecideArgs &a) {
     const InsState &q = a.q;
     const int b = blockIdx.x, col = *s.col, t = *s.iter, T = s.T, G = s.G, S = s.S;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) { q.new_row[b] = -1; q.row_lo[b] = s.n_rows[b]; }     // nothing appended by this pass so far
     if (!q.active[b]) return;
     if (tid < 128) sx[tid] = q.x_seed[(size_t)b * q.seed_stride * 128 + tid];
     __syncthreads();
@@ -444,35 +444,43 @@ __device__ __forceinline__ void seed_decide_scene(const SeedDecideArgs &a) {
     __syncthreads();
     __shared__ int s_cell, s_append, s_row;
     if (tid == 0) {
-        int cell = s_topi[0];
-        if (q.beam > 1) {
-            float p[INSERT_LIMIT], total = 0.f;
+        float p[INSERT_LIMIT], total = 0.f;
+        if (q.beam > 1)
             for (int k = 0; k < q.beam; ++k) { p[k] = expf(s_topv[k] - gmax) / den; total += p[k]; }
-            const float thr = uniform01(q.seed ^ 0x5EEDu, (unsigned)s.scene_id[b], (unsigned)q.pass[b], (unsigned)t) * total;
-            float c = 0.f; int pick = q.beam - 1;
-            for (int k = 0; k < q.beam; ++k) { c += p[k]; if (thr < c) { pick = k; break; } }
-            cell = s_topi[pick];
-        }
-        s_cell = cell;
-        int append = 0;
-        const int pass = q.pass[b] + 1;
-        q.pass[b] = pass;
         const float *occ = q.occ + (size_t)b * G;
         // state (:1884-1889): argmax of the 2-way softmax, index 1 = 'enter'
         int enter = s_small[1] > s_small[0] ? 1 : 0;
         if (q.force_enter) enter = 1;
-        if (occ[cell] != 0.f) {                         // overlap filter (:1906-1909): retry
-            // with a deterministic choice (beam 1) every retry repeats this pass: the reference spins until the limit
-            if (q.beam == 1 || pass >= INSERT_LIMIT) q.active[b] = 0;
-        } else if (!enter || q.n_new[b] + 1 > INSERT_LIMIT) {
-            q.active[b] = 0;
-        } else if (s.n_rows[b] >= s.cap) {
-            *q.err = 2;                                  // row capacity exhausted
-            q.active[b] = 0;
-        } else {
-            append = 1;
-            if (pass >= INSERT_LIMIT) q.active[b] = 0;
+        int cell = s_topi[0], append = 0, pass = q.pass[b];
+        for (;;) {
+            if (q.beam > 1) {
+                const float thr = uniform01(q.seed ^ 0x5EEDu, (unsigned)s.scene_id[b], (unsigned)pass, (unsigned)t) * total;
+                float c = 0.f; int pick = q.beam - 1;
+                for (int k = 0; k < q.beam; ++k) { c += p[k]; if (thr < c) { pick = k; break; } }
+                cell = s_topi[pick];
+            }
+            ++pass;
+            if (occ[cell] != 0.f) {                     // overlap filter (:1906-1909): retry
+                // with a deterministic choice (beam 1) every retry repeats this pass: the reference spins until the limit
+                if (q.beam == 1 || pass >= INSERT_LIMIT) { q.active[b] = 0; break; }
+                // The reference restores its features and runs the whole query again (`feat_a = raw_feat_a.clone();
+                // continue`): nothing the query reads has changed, so every logit comes out the same and only the draw
+                // (keyed by the pass index) differs - the retry is taken here, without another pass of the stage
+                continue;
+            }
+            if (!enter || q.n_new[b] + 1 > INSERT_LIMIT) {
+                q.active[b] = 0;
+            } else if (s.n_rows[b] >= s.cap) {
+                *q.err = 2;                              // row capacity exhausted
+                q.active[b] = 0;
+            } else {
+                append = 1;
+                if (pass >= INSERT_LIMIT) q.active[b] = 0;
+            }
+            break;
         }
+        q.pass[b] = pass;
+        s_cell = cell;
         s_append = append;
         s_row = s.n_rows[b];
     }
