@@ -157,6 +157,7 @@ struct infgen_engine {
     cudaStream_t stream = nullptr, own_stream = nullptr;
     cudaStream_t side_stream = nullptr;                 // edges of the next column, concurrent with its embedding
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool ins_ride = false;                              // seed queries carry the last appended row (one scene per tile)
     cudaStream_t side_stream2 = nullptr;                // second concurrent branch (occupancy node of the next insertion pass)
     cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr;
     bool early_edges = false;                           // motion-only engines build the next column's edges early
@@ -534,6 +535,12 @@ static RowSpace new_rows(infgen_engine *e) {
     r.list = e->ins.new_list; r.n_list = e->ins.n_new_list; r.list_cap = e->n_scenes;
     return r;
 }
+// the rows the pass before the last one appended (their heading-stack K|V rows are due when the next row arrives)
+static RowSpace prev_rows(infgen_engine *e) {
+    RowSpace r = scene_rows(e);
+    r.list = e->ins.prev_list; r.n_list = e->ins.n_prev_list; r.list_cap = e->n_scenes;
+    return r;
+}
 
 // column embedding (agent_decoder.py:2265-2287) of column col+col_add -> x (temporal layer 0 projects it in k_layer)
 static int enqueue_embed_column(infgen_engine *e, int col_add) {
@@ -768,7 +775,9 @@ static int enqueue_layers(infgen_engine *e, bool with_edges, int trace_iter) {
 // IF node inside its body whose condition values k_ins_begin / k_seed_decide set on the device (no host round trip).
 // ---------------------------------------------------------------------------------------------------------------
 // every active row >= row_lo through a stack of layers WITHOUT edges, keeping the K|V rows of the non-bipartite ones
-static int enqueue_edgeless(infgen_engine *e, const int *row_lo, float *x, bool seed_stack, bool new_only = false) {
+// subset: 0 = every active row >= row_lo, 1 = the rows appended by the last pass, 2 = those of the pass before
+static int enqueue_edgeless(infgen_engine *e, const int *row_lo, float *x, bool seed_stack, int subset = 0) {
+    const bool new_only = subset != 0;
     if (!new_only && (e->R + 7) / 8 > MAX_CLUSTERS && e->layer_path != 1) {
         // more than one wave of clusters: the row-tile kernel, one launch per layer (finish layer i, project layer i + 1)
         RowSpace rows = scene_rows(e);
@@ -801,7 +810,7 @@ static int enqueue_edgeless(infgen_engine *e, const int *row_lo, float *x, bool 
     }
     LayerArgs la;
     memset(&la, 0, sizeof(la));
-    la.rows = new_only ? new_rows(e) : scene_rows(e);
+    la.rows = subset == 1 ? new_rows(e) : (subset == 2 ? prev_rows(e) : scene_rows(e));
     if (!new_only) la.rows.row_lo = row_lo;
     la.x = x; la.ring = RING; la.col_ptr = e->st.col;
     const size_t kvl = (size_t)e->R * 256;
@@ -942,6 +951,9 @@ static int enqueue_insertion_pass(infgen_engine *e) {
         la.pre0 = make_pre(e->occ2sa[0], false, nullptr, false, 0, false);
         const size_t kvl = (size_t)R * 256, kvm = (size_t)e->P * 256;
         const int qshift = q.seed_stride == SEED_ROW_STRIDE ? 2 : 0, qwide = q.seed_stride == SEED_ROW_STRIDE ? 1 : 0;
+        // one scene per tile: the row appended by the previous pass rides along (its a2sa K|V rows come out of this launch)
+        const bool ride = e->ins_ride;
+        if (ride) { la.x2 = fbuf(e, "x_sa"); la.ride_row = q.new_row; la.ride_cap = s.cap; }
         int n = 0;
         for (int i = 0; i < 3; ++i) {
             SubArgs &o = la.sub[n++];
@@ -952,7 +964,7 @@ static int enqueue_insertion_pass(infgen_engine *e) {
             p.w = e->pt2sa[i].cs_post; p.has_attn = 1; p.has_pos = 1; p.elist = 1; p.row_shift = qshift; p.wide = qwide;
             p.kv = fbuf(e, "kv_ms") + i * kvm; p.cnt = q.ps_cnt; p.start = nullptr; p.stride = SEED_MAP_MAX;
             p.src = q.ps_src; p.rhat = fbuf(e, "rhat_ps");
-            p.pre = make_pre(e->a2sa[i], false, nullptr, false, 0, false);
+            p.pre = make_pre(e->a2sa[i], ride, ride ? fbuf(e, "kv_sa") + i * kvl : nullptr, false, 0, false);
             SubArgs &g = la.sub[n++];
             g.w = e->a2sa[i].cs_post; g.has_attn = 1; g.has_pos = 1; g.elist = 2; g.row_shift = qshift; g.wide = qwide;
             g.kv = fbuf(e, "kv_sa") + i * kvl; g.cnt = q.as_cnt; g.start = nullptr; g.stride = q.as_stride;
@@ -997,7 +1009,12 @@ static int enqueue_heading_stage(infgen_engine *e) {
     cudaStream_t st = e->stream;
     float *x = fbuf(e, "x"), *x_sa = fbuf(e, "x_sa"), *x_ha = fbuf(e, "x_ha");
     // the occupancy node of the next pass: the appended row's cell is known
-    RET(side2_fork(e, [&]() -> int { return enqueue_seed_prepare(e); }));
+    // and, behind it, the heading-stack K|V rows of the row the pass before appended (this row's a2a layers may attend to it)
+    // (one scene per tile only; packed batches project the new rows at the end of this stage, beside their seed-stack chain)
+    RET(side2_fork(e, [&]() -> int {
+        RET(enqueue_seed_prepare(e));
+        return e->ins_ride ? enqueue_edgeless(e, nullptr, x_ha, false, 2) : 0;
+    }));
     // the new row's edges and their relative embeddings only need its pose: on the side stream, concurrently with its
     // categorical / column embedding (two chains of ~50 us each per inserted agent)
     RET(side_fork(e, [&]() -> int {
@@ -1027,6 +1044,7 @@ static int enqueue_heading_stage(infgen_engine *e) {
     CKL(); count_launch(e);
     RET(enqueue_embed_rows(e, q.row_lo));       // feature of the new row with the dummy heading
     RET(side_join(e));
+    RET(side2_join(e));
     {   // the new rows through 3 x {pt2a, a2a} with their 10 m neighbourhoods
         LayerArgs la;
         memset(&la, 0, sizeof(la));
@@ -1057,22 +1075,31 @@ static int enqueue_heading_stage(infgen_engine *e) {
         k_head_finalize<<<ns, NT, 0, st>>>(ha);
     }
     CKL(); count_launch(e);
-    // final feature of the new row (:2086-2097), also written to the inputs of the two edge-less stacks: the new rows become
-    // sources of later passes
-    RET(enqueue_embed_rows(e, q.row_lo, x_sa, x_ha));
-    // off the critical path of the next pass (which needs the seed-stack K|V rows first): the heading-stack K|V rows of
-    // the new rows and the relative embedding of their edge towards the query row
-    RET(side_fork(e, [&]() -> int {
+    // Final feature of the new row (:2086-2097), also written to the inputs of the two edge-less stacks (the new rows become
+    // sources of later passes), and the relative embedding of its edge towards the query row.
+    auto seed_edge_embedding = [&]() -> int {
         FourierArgs fj;
         memset(&fj, 0, sizeof(fj));
         fj.normalize = 1; fj.dim = 3; fj.n_slots = ns; fj.slot_list = q.as_new_list; fj.n_list = q.as_new_n;
         fj.raw = q.as_raw; fj.w = e->f_as; fj.out = fbuf(e, "rhat_as");
-        RET(launch_fourier(e, &fj, 1, KC_INS_FOURIER));
-        return enqueue_edgeless(e, q.row_lo, x_ha, false, true);
+        return launch_fourier(e, &fj, 1, KC_INS_FOURIER);
+    };
+    if (e->ins_ride) {
+        // One scene per tile: the edge embedding only needs the pose and runs beside the final embedding.  The row's
+        // seed-stack K|V rows come out of the next seed query (ride-along row), its heading-stack K|V rows are left to the
+        // next heading stage of the iteration (prev_rows above; the next iteration projects every row again).
+        RET(side_fork(e, seed_edge_embedding));
+        RET(enqueue_embed_rows(e, q.row_lo, x_sa, x_ha));
+        return side_join(e);
+    }
+    // packed query rows: both edge-less chains of the new rows here, on two streams
+    RET(enqueue_embed_rows(e, q.row_lo, x_sa, x_ha));
+    RET(side_fork(e, [&]() -> int {
+        RET(seed_edge_embedding());
+        return enqueue_edgeless(e, q.row_lo, x_ha, false, 1);
     }));
-    RET(enqueue_edgeless(e, q.row_lo, x_sa, true, true));
-    RET(side_join(e));
-    return side2_join(e);
+    RET(enqueue_edgeless(e, q.row_lo, x_sa, true, 1));
+    return side_join(e);
 }
 
 // host-driven loop (plain launches)
@@ -1648,6 +1675,7 @@ int32_t infgen_load_scenes(infgen_engine *e, const infgen_scene_batch *b, int32_
         RET(ensure_t(e, "as_seen", ns, &q.as_seen)); RET(ensure_t(e, "as_new_list", ns + 4, &q.as_new_list));
         q.as_new_n = q.as_new_list + ns;
         RET(ensure_t(e, "ins_new_list", ns + 4, &q.new_list)); q.n_new_list = q.new_list + ns;
+        RET(ensure_t(e, "ins_prev_list", ns + 4, &q.prev_list)); q.n_prev_list = q.prev_list + ns;
         q.as_stride = std::min(cap, SEED_AGENT_MAX);
         RET(ensure_t(e, "ps_cnt", ns, &q.ps_cnt)); RET(ensure_t(e, "ps_src", (size_t)ns * SEED_MAP_MAX, &q.ps_src));
         RET(ensure_t(e, "ps_raw", (size_t)ns * SEED_MAP_MAX * 3, &q.ps_raw));
@@ -1679,6 +1707,7 @@ int32_t infgen_load_scenes(infgen_engine *e, const infgen_scene_batch *b, int32_
         q.seed_feat = e->seed_feat; q.err = e->d_err;
         // query rows: one per tile (all warps share its edges) while every scene's cluster fits one wave, packed otherwise
         q.seed_stride = (ns <= MAX_CLUSTERS || getenv("INFGEN_SEED_WIDE")) ? SEED_ROW_STRIDE : 1;
+        e->ins_ride = q.seed_stride == SEED_ROW_STRIDE && !getenv("INFGEN_NO_RIDE");
         s.ins_col = q.ins_col;
         RET(ensure_t(e, "hv_src", R, &s.hv_src));
         CK(cudaMemsetAsync(s.hv_src, 0xff, (size_t)R * sizeof(int), e->stream));

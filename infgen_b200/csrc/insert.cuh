@@ -51,6 +51,7 @@ struct InsState {
     int *as_seen;                      // [ns] rows within the seed radius so far (the neighbour limit counts them all)
     int *as_new_list, *as_new_n;       // slots appended by the last heading stage (their relative embedding is due)
     int *new_list, *n_new_list;        // global rows appended by the last pass, compact (row-list launches of the heading stage)
+    int *prev_list, *n_prev_list;      // the same for the pass before (rows whose heading-stack K|V rows are still due)
     // loop control without the host: condition handles of the CUDA-graph WHILE (another pass) / IF (a row was appended)
     // nodes, set from k_ins_begin / k_seed_decide when the iteration is replayed as a graph (use_cond)
     int use_cond;
@@ -178,6 +179,7 @@ __global__ void __launch_bounds__(NT) k_ins_begin(const DecState s, const InsSta
         q.one_cnt[b] = 1; q.occ_src[b] = b; q.ha_lo[b] = 0;
         if (b == 0) {
             q.flags[0] = 1; q.flags[1] = 0; *q.done_ctr = 0;
+            *q.n_new_list = 0; *q.n_prev_list = 0;
             if (q.use_cond) cudaGraphSetConditional(q.h_pass, 1u);
         }
     }
@@ -567,6 +569,9 @@ __global__ void __launch_bounds__(NT) k_seed_decide(const SeedDecideArgs a) {
     if (s_last && threadIdx.x == 0) {
         __threadfence();
         int any = 0, any_new = 0;
+        const int n_prev = *q.n_new_list;
+        for (int i = 0; i < n_prev; ++i) q.prev_list[i] = q.new_list[i];
+        *q.n_prev_list = n_prev;
         for (int b = 0; b < (int)gridDim.x; ++b) {
             any |= ((volatile int *)q.active)[b] != 0;
             const int nr = ((volatile int *)q.new_row)[b];

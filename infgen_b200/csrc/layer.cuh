@@ -100,6 +100,14 @@ struct LayerArgs {
     int n_sub;
     SubArgs sub[MAX_SUB];
     unsigned *grid_bar;        // zeroed counter for the grid barriers (grid_sync)
+    // "ride-along" row of a seed-query launch (one scene per tile, M = rows.cap): tile position 1 of scene b carries row
+    // ride_cap * b + ride_row[b] of x2 (ride_row[b] >= 0 and the scene's query row active) through the same layers WITHOUT
+    // edges; the K|V projections of a `pre` with pre_kv are then stored for that row alone (slot = its row in x2).  The
+    // row appended by the previous insertion pass becomes a source of this pass's agent -> seed attention that way,
+    // without a chain of edge-less layers of its own in front of the query.
+    const float *x2;
+    const int *ride_row;
+    int ride_cap;
     long long *tstamp;         // optional [256] clock64 stamps of CTA 0 (debug: phase breakdown)
 };
 
@@ -401,9 +409,16 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
     const int tile = (int)(blockIdx.x / CL);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     __shared__ int s_rid[8];                                       // global row of every tile position, -1 = inactive
+    __shared__ int s_alt[8];                                       // ride-along: row of x2 carried by the position, else -1
     if (tid < M) {
         const int r = a.rows.tile_row(tile, tid, M);
-        s_rid[tid] = a.rows.active_row(r) ? r : -1;
+        int alt = -1;
+        if (a.ride_row && tid == 1 && a.rows.active_row(r - 1)) {
+            const int nr = a.ride_row[tile];
+            if (nr >= 0) alt = tile * a.ride_cap + nr;
+        }
+        s_alt[tid] = alt;
+        s_rid[tid] = (alt >= 0 || a.rows.active_row(r)) ? r : -1;
     }
     __syncthreads();
     unsigned act_mask = 0;                                         // bit m: tile position m holds an active row
@@ -472,7 +487,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
     for (int m = warp; m < M; m += NWARP) {
         const int r = rid(m);
         const bool act = active(m);
-        st4(sx + m * LD1 + 4 * lane, act ? ld4(a.x + (size_t)r * 128 + 4 * lane) : z4);
+        const float *xrow = s_alt[m] >= 0 ? a.x2 + (size_t)s_alt[m] * 128 : a.x + (size_t)r * 128;
+        st4(sx + m * LD1 + 4 * lane, act ? ld4(xrow + 4 * lane) : z4);
         if (!a.pre0.w) {
             st4(sqr + m * 128 + 4 * lane, act ? ld4(a.qr + (size_t)r * 1024 + c * 128 + 4 * lane) : z4);
             if (lane < 4) st4(sq + m * 16 + 4 * lane, act ? ld4(a.q + (size_t)r * 128 + 16 * c + 4 * lane) : z4);
@@ -540,8 +556,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
         if (P.pre_kv) {
             const int col = col_now + P.col_add;
             slice_gemm<M, 32, 4>(su, LD1, wpre + cs_pre::WKV, 32, sred, [&](int m, int n, float v) {
-                const int r = rid(m);
-                if (active(m)) {
+                const int r = a.ride_row ? s_alt[m] : rid(m);     // ride-along launches: K|V of the carried row only
+                if (active(m) && r >= 0) {
                     const size_t slot = P.kv_ring ? ((size_t)r * a.ring + (col & (a.ring - 1))) : (size_t)r;
                     const int o = n < 16 ? 16 * c + n : 128 + 16 * c + (n - 16);
                     P.kv_out[slot * 256 + o] = v + wpre[cs_pre::BKV + n];
@@ -681,7 +697,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
             f = ln128s(f, wpost + cs_post::LN_FFPOST_G, wpost + cs_post::LN_FFPOST_B, lane);
             const float4 x2 = add4(ld4(sx + m * LD1 + 4 * lane), f);
             st4(sx + m * LD1 + 4 * lane, x2);
-            if ((m & (CL - 1)) == c && active(m)) {                // row m is stored by CTA m % 8
+            if ((m & (CL - 1)) == c && active(m) && s_alt[m] < 0) { // row m is stored by CTA m % 8
                 if (last) st4(a.x + (size_t)r * 128 + 4 * lane, x2);
                 if (A.trace_out) st4(A.trace_out + (size_t)r * 128 + 4 * lane, x2);
             }
