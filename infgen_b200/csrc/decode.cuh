@@ -452,7 +452,9 @@ __global__ void __launch_bounds__(NT_S) k_embed_column(const ColEmbArgs a) {
         st4(sX + m * XLD + 256 + 4 * lane, s);
         st4(sX + m * XLD + 384 + 4 * lane, g);
     }
-    fourier_body<EM>(ws, a.fx, 2, sraw, sF, sH, sA);
+    bool single = s_row[0] >= 0;             // one appended row: GEMV path of the tile products
+    for (int m = 1; m < EM; ++m) single = single && s_row[m] < 0;
+    fourier_body<EM>(ws, a.fx, 2, sraw, sF, sH, sA, single);
     for (int m = warp; m < EM; m += NWARP) st4(sX + m * XLD + 128 + 4 * lane, ld4(sH + m * HLD + 4 * lane));
     csync();
     mlp3_body<EM>(ws, a.fusion, sX, XLD, 128, sH, sA, [&](int m, int n, float v) {
@@ -462,7 +464,7 @@ __global__ void __launch_bounds__(NT_S) k_embed_column(const ColEmbArgs a) {
             if (a.out2) a.out2[(size_t)r * 128 + n] = v;
             if (a.out3) a.out3[(size_t)r * 128 + n] = v;
         }
-    });
+    }, single);
 }
 
 __global__ void k_next_iter(int *col, int *iter) { *col += 1; *iter += 1; }

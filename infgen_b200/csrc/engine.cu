@@ -440,8 +440,12 @@ static const int MAX_CLUSTERS = 15;
 static int row_tiles(const RowSpace &r, int M) { return r.list ? (r.list_cap + M - 1) / M : (r.n_total + M - 1) / M; }
 static int launch_layer(infgen_engine *e, const LayerArgs &a_in, int cls) {
     LayerArgs a = a_in;
-    if (e->bufs.count("tstamp") && e->bufs["tstamp"].p)
-        a.tstamp = (long long *)e->bufs["tstamp"].p + (cls == KC_LAYER_A ? 256 : 0);
+    if (e->bufs.count("tstamp") && e->bufs["tstamp"].p) {
+        // debug stamps: INFGEN_TSTAMP_CLS=<class index> records that class alone (default: the motion stack launches)
+        static const int want = getenv("INFGEN_TSTAMP_CLS") ? atoi(getenv("INFGEN_TSTAMP_CLS")) : -1;
+        if (want < 0 ? (cls == KC_LAYER_STACK || cls == KC_LAYER_TM || cls == KC_LAYER_A) : cls == want)
+            a.tstamp = (long long *)e->bufs["tstamp"].p + (cls == KC_LAYER_A ? 256 : 0);
+    }
     ProfScope ps(e, cls);
     const int M = e->row_tile;
     const int clusters = row_tiles(a.rows, M);
@@ -486,7 +490,7 @@ static int launch_fourier(infgen_engine *e, const FourierArgs *jobs, int n_jobs,
     bool tc = e->fourier_tc;
     for (int j = 0; j < n_jobs; ++j) {
         if (jobs[j].dim < 1 || jobs[j].dim > 4) return fail(INFGEN_ERR_INVALID_ARG, "FourierEmbedding input_dim %d unsupported", jobs[j].dim);
-        if (jobs[j].cat_tab || !jobs[j].w.wimg) tc = false;
+        if (jobs[j].cat_tab || !jobs[j].w.wimg || jobs[j].ffma) tc = false;
     }
     const int tm = tc ? ftc::TM : FM;
     int tiles = 0;
@@ -839,7 +843,11 @@ static int enqueue_edgeless(infgen_engine *e, const int *row_lo, float *x, bool 
         }
     }
     la.n_sub = n;
-    return launch_layer(e, la, KC_INS_LAYER_AGENTS);
+    const int saved = e->row_tile;
+    if (new_only && e->n_scenes <= 4 * MAX_CLUSTERS) e->row_tile = 4;     // see the heading stage
+    const int rc = launch_layer(e, la, KC_INS_LAYER_AGENTS);
+    e->row_tile = saved;
+    return rc;
 }
 
 // Run `fn` on the side stream, concurrently with what the caller enqueues on the engine stream until side_join().  Works
@@ -985,14 +993,20 @@ static int enqueue_insertion_pass(infgen_engine *e) {
         la.w = e->h_seed_pos; la.out = q.pos_logits;
         la.w2 = e->h_ag_occ; la.out2 = q.ag_occ_logits;
         la.w3 = e->h_pt_occ; la.out3 = q.pt_occ_logits;
+        // and the three small ones (state, type, shape): [rows][2], [rows][3], [rows][3]
+        la.w4 = e->h_seed_state; la.out4 = q.small_logits;
+        la.w5 = e->h_seed_type; la.out5 = q.small_logits + (size_t)la.n * 2;
+        la.w6 = e->h_seed_shape; la.out6 = q.small_logits + (size_t)la.n * 5;
+        la.single_stride = q.seed_stride == SEED_ROW_STRIDE ? SEED_ROW_STRIDE : 0;
         const int npad = std::max(la.w.n_pad, std::max(la.w2.n_pad, la.w3.n_pad));
         ProfScope ps(e, KC_INS_HEADS);
-        k_mlp_layer<<<dim3((la.n + HM - 1) / HM, npad / 128, 3), NT_S, MLP_LAYER_SMEM, st>>>(la);
+        k_mlp_layer<<<dim3((la.n + HM - 1) / HM, npad / 128, 6), NT_S, MLP_LAYER_SMEM, st>>>(la);
         CKL(); count_launch(e);
     }
     SeedDecideArgs da;
     memset(&da, 0, sizeof(da));
-    da.s = s; da.q = q; da.h_state = e->h_seed_state; da.h_type = e->h_seed_type; da.h_shape = e->h_seed_shape;
+    da.s = s; da.q = q;
+    if (e->bufs.count("tstamp") && e->bufs["tstamp"].p) da.tstamp = (long long *)e->bufs["tstamp"].p + 384;
     {
         ProfScope ps(e, KC_INSERT);
         k_seed_decide<<<ns, NT, 0, st>>>(da);
@@ -1012,6 +1026,11 @@ static int enqueue_heading_stage(infgen_engine *e) {
     // and, behind it, the heading-stack K|V rows of the row the pass before appended (this row's a2a layers may attend to it)
     // (one scene per tile only; packed batches project the new rows at the end of this stage, beside their seed-stack chain)
     RET(side2_fork(e, [&]() -> int {
+        {   // (first: the grid-sized records of the insertion read the occupancy the query saw)
+            ProfScope ps(e, KC_INSERT);
+            k_seed_records<<<ns, NT, 0, e->stream>>>(s, q);
+        }
+        CKL(); count_launch(e);
         RET(enqueue_seed_prepare(e));
         return e->ins_ride ? enqueue_edgeless(e, nullptr, x_ha, false, 2) : 0;
     }));
@@ -1065,7 +1084,12 @@ static int enqueue_heading_stage(infgen_engine *e) {
             if (i < 2) g.pre = make_pre(e->m[i + 1], false, nullptr, false, 0, false);
         }
         la.n_sub = n;
-        RET(launch_layer(e, la, KC_INS_LAYER_NEW));
+        // a handful of rows: tiles of 4 (every projection phase of k_layer<4> is shorter than its k_layer<8> counterpart)
+        const int saved = e->row_tile;
+        if (e->n_scenes <= 4 * MAX_CLUSTERS) e->row_tile = 4;
+        const int rc = launch_layer(e, la, KC_INS_LAYER_NEW);
+        e->row_tile = saved;
+        RET(rc);
     }
     HeadFinalArgs ha;
     memset(&ha, 0, sizeof(ha));
@@ -1082,6 +1106,7 @@ static int enqueue_heading_stage(infgen_engine *e) {
         memset(&fj, 0, sizeof(fj));
         fj.normalize = 1; fj.dim = 3; fj.n_slots = ns; fj.slot_list = q.as_new_list; fj.n_list = q.as_new_n;
         fj.raw = q.as_raw; fj.w = e->f_as; fj.out = fbuf(e, "rhat_as");
+        fj.ffma = ns <= FM;                  // one tile of a few slots: the FFMA kernel (GEMV path for a single slot)
         return launch_fourier(e, &fj, 1, KC_INS_FOURIER);
     };
     if (e->ins_ride) {
@@ -1697,6 +1722,8 @@ int32_t infgen_load_scenes(infgen_engine *e, const infgen_scene_batch *b, int32_
         RET(ensure_t(e, "rec_meta", (size_t)R * 2, &q.rec_meta)); RET(ensure_t(e, "rec_state_prob", (size_t)R, &q.rec_state_prob));
         RET(ensure_t(e, "rec_pos_prob", (size_t)R * G, &q.rec_pos_prob)); RET(ensure_t(e, "rec_ag_occ", (size_t)R * G, &q.rec_ag_occ));
         RET(ensure_t(e, "rec_pt_occ", (size_t)R * G, &q.rec_pt_occ)); RET(ensure_t(e, "rec_occ_gt", (size_t)R * G, &q.rec_occ_gt));
+        RET(ensure_t(e, "rec_softmax", (size_t)ns * 2, &q.rec_softmax));
+        RET(ensure_t(e, "small_logits", (size_t)ns * SEED_ROW_STRIDE * 8, &q.small_logits));
         RET(ensure_t(e, "x_sa", (size_t)R * 128, &tmp)); RET(ensure_t(e, "x_ha", (size_t)R * 128, &tmp));
         RET(ensure_t(e, "s_ha", (size_t)R * 128, &tmp));
         RET(ensure_t(e, "kv_sa", (size_t)3 * R * 256, &tmp)); RET(ensure_t(e, "kv_ha", (size_t)3 * R * 256, &tmp));

@@ -73,6 +73,7 @@ struct InsState {
     const float *seed_feat;            // [128] `_build_agent_feature(..., state_index=invalid)` - a constant
     // head outputs of the query row
     float *pos_logits, *ag_occ_logits, *pt_occ_logits;   // [ns*SEED_ROW_STRIDE][G], row 4b
+    float *small_logits;               // state [rows][2] | type [rows][3] | shape [rows][3], rows = ns * seed_stride
     // per row
     int *ins_col;                      // [R] column at which the row was inserted, -1 for the scene's own agents
     float *shape_rows;                 // [R+1][3] shape fed to shape_emb (row R = 0.1)
@@ -83,6 +84,7 @@ struct InsState {
     int *rec_meta;                     // [R][2]: decode iteration, slot (1..10) within the iteration
     float *rec_state_prob;             // [R]
     float *rec_pos_prob, *rec_ag_occ, *rec_pt_occ, *rec_occ_gt;   // [R][G]
+    float *rec_softmax;                // [ns][2] max / sum-exp of the position logits of the last query (k_seed_records)
     int *err;
 };
 
@@ -341,50 +343,55 @@ __global__ void __launch_bounds__(NT) k_seed_prepare(const SeedPrepArgs a) {
 struct SeedDecideArgs {
     DecState s;
     InsState q;
-    MlpHeadW h_state, h_type, h_shape;
+    long long *tstamp;         // optional [64] clock64 stamps of CTA 0 (debug: phase breakdown, INFGEN_TSTAMP=1)
 };
+// order-preserving map float -> unsigned (max of the keys = max of the floats)
+__device__ __forceinline__ unsigned float_key(float v) {
+    const unsigned u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
 __device__ __forceinline__ void seed_decide_scene(const SeedDecideArgs &a) {
-    __shared__ __align__(16) float sx[128];
-    __shared__ __align__(16) float sh3[3][128];
     __shared__ float s_small[8];                        // state[2] type[3] shape[3]
-    __shared__ float s_red[NT];
-    __shared__ float s_wv[NWARP][INSERT_LIMIT];
-    __shared__ int s_wi[NWARP][INSERT_LIMIT];
-    __shared__ float s_topv[INSERT_LIMIT];
+    __shared__ float s_red[2 * NWARP];
+    __shared__ float s_wv[NWARP * INSERT_LIMIT];
+    __shared__ int s_wi[NWARP * INSERT_LIMIT];
+    __shared__ float s_topv[INSERT_LIMIT], s_p[INSERT_LIMIT], s_occ[INSERT_LIMIT];
     __shared__ int s_topi[INSERT_LIMIT];
     const DecState &s = a.s;
     const InsState &q = a.q;
     const int b = blockIdx.x, col = *s.col, t = *s.iter, T = s.T, G = s.G, S = s.S;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) { q.new_row[b] = -1; q.row_lo[b] = s.n_rows[b]; }     // nothing appended by this pass so far
+    int ts_n = 0;
+    auto stamp = [&]() { if (a.tstamp && b == 0 && tid == 0 && ts_n < 32) a.tstamp[ts_n++] = clock64(); };
+    stamp();
+    // scalars of the decision, fetched while the heads run (the decision itself is one thread's chain)
+    const int rows0 = s.n_rows[b], pass0 = q.pass[b], nnew0 = q.n_new[b];
+    if (tid == 0) { q.new_row[b] = -1; q.row_lo[b] = rows0; }            // nothing appended by this pass so far
     if (!q.active[b]) return;
-    if (tid < 128) sx[tid] = q.x_seed[(size_t)b * q.seed_stride * 128 + tid];
-    __syncthreads();
-    // ---- the three small heads (state, type, shape; layers.py:206-215): hidden layers, LayerNorms by three warps, then
-    //      the 2 + 3 + 3 outputs as one 128-dot per warp ----
-    const MlpHeadW *hw[3] = {&a.h_state, &a.h_type, &a.h_shape};
-    for (int i = 0; i < 3; ++i) gemv128(sx, hw[i]->w0, 128, hw[i]->b0, 128, sh3[i], s_red);
-    if (warp < 3) st4(sh3[warp] + 4 * lane, relu4(ln128(ld4(sh3[warp] + 4 * lane), hw[warp]->ln_g, hw[warp]->ln_b, lane)));
-    __syncthreads();
-    {
-        const int hi = warp < 2 ? 0 : (warp < 5 ? 1 : 2), n = warp < 2 ? warp : (warp < 5 ? warp - 2 : warp - 5);
-        const MlpHeadW &w = *hw[hi];
-        const float4 wv = ldg4(w.w3 + ((size_t)lane * w.n_pad + n) * 4), xv = ld4(sh3[hi] + 4 * lane);
-        const float d = warp_sum(fmaf(xv.w, wv.w, fmaf(xv.z, wv.z, fmaf(xv.y, wv.y, xv.x * wv.x))));
-        if (lane == 0) s_small[warp] = d + __ldg(w.b3 + n);
+    if (tid < NWARP * INSERT_LIMIT) { s_wv[tid] = -INFINITY; s_wi[tid] = 0x7fffffff; }
+    // the three small heads of the query row (state, type, shape; computed by k_mlp_layer beside the grid-sized ones)
+    if (tid < 8) {
+        const int rows = (int)gridDim.x * q.seed_stride, r = b * q.seed_stride;
+        const float *p = tid < 2 ? q.small_logits + (size_t)r * 2 + tid
+                                 : (tid < 5 ? q.small_logits + (size_t)rows * 2 + (size_t)r * 3 + (tid - 2)
+                                            : q.small_logits + (size_t)rows * 5 + (size_t)r * 3 + (tid - 5));
+        s_small[tid] = *p;
     }
-    // ---- position: softmax over the grid, top-k, draw (:1896-1902).  Warp w owns a contiguous slice of the cells ----
+    // the grid logits of the position head: warp w owns a contiguous slice of the cells
     const float *lg = q.pos_logits + (size_t)b * q.seed_stride * G;
     const int per = (G + NWARP - 1) / NWARP, g0 = warp * per, g1 = min(G, g0 + per);
     constexpr int VPL = 8;                              // cells per lane (G <= 8 * 32 * NWARP)
     float v[VPL];
-    float mxv = -INFINITY;
 #pragma unroll
     for (int j = 0; j < VPL; ++j) {
         const int g = g0 + lane + 32 * j;
         v[j] = g < g1 ? lg[g] : -INFINITY;
-        mxv = fmaxf(mxv, v[j]);
     }
+    stamp();
+    // ---- position: softmax over the grid, top-k, draw (:1896-1902) ----
+    float mxv = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) mxv = fmaxf(mxv, v[j]);
     mxv = warp_max(mxv);
     if (lane == 0) s_red[warp] = mxv;
     __syncthreads();
@@ -396,73 +403,70 @@ __device__ __forceinline__ void seed_decide_scene(const SeedDecideArgs &a) {
     for (int j = 0; j < VPL; ++j) sum += (g0 + lane + 32 * j < g1) ? expf(v[j] - gmax) : 0.f;
     sum = warp_sum(sum);
     if (lane == 0) s_red[NWARP + warp] = sum;
-    // the beam largest logits of the slice, ties to the lower index
+    stamp();
+    // the beam largest logits of the slice, ties to the lower index: the largest key by one warp reduction, then the lowest
+    // cell that holds it by another
     for (int k = 0; k < q.beam; ++k) {
         float bv = v[0]; int bi = g0 + lane;
 #pragma unroll
         for (int j = 1; j < VPL; ++j)
             if (v[j] > bv) { bv = v[j]; bi = g0 + lane + 32 * j; }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-        }
+        const unsigned key = float_key(bv), kmax = __reduce_max_sync(0xffffffffu, key);
+        const int win = __reduce_min_sync(0xffffffffu, key == kmax ? bi : 0x7fffffff);
+        const int wl = (win - g0) & 31;                 // the lane that owns cell `win`
+        const float wv = __shfl_sync(0xffffffffu, bv, wl);
 #pragma unroll
         for (int j = 0; j < VPL; ++j)
-            if (bi == g0 + lane + 32 * j) v[j] = -INFINITY;
-        if (lane == 0) { s_wv[warp][k] = bv; s_wi[warp][k] = bi; }
+            if (win == g0 + lane + 32 * j) v[j] = -INFINITY;
+        if (lane == 0) { s_wv[warp * INSERT_LIMIT + k] = wv; s_wi[warp * INSERT_LIMIT + k] = win; }
     }
     __syncthreads();
+    stamp();
     float den = 0.f;
 #pragma unroll
     for (int w = 0; w < NWARP; ++w) den += s_red[NWARP + w];
-    if (warp == 0) {                                    // merge the NWARP x beam candidates
-        float cv[3]; int ci[3];
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const int c = lane + 32 * j, cw = c / INSERT_LIMIT, ck = c - cw * INSERT_LIMIT;
-            const bool ok = c < NWARP * INSERT_LIMIT && ck < q.beam;
-            cv[j] = ok ? s_wv[cw][ck] : -INFINITY;
-            ci[j] = ok ? s_wi[cw][ck] : 0x7fffffff;
+    // merge the NWARP x beam candidates: a candidate's rank is the number of candidates that beat it (larger logit, or the
+    // same logit at a lower cell) - the order the reference's topk returns them in
+    // (slots beyond the beam hold -inf / INT_MAX and never beat a candidate)
+    if (tid < NWARP * INSERT_LIMIT && (tid % INSERT_LIMIT) < q.beam) {
+        const float cv = s_wv[tid];
+        const int ci = s_wi[tid];
+        int rank = 0;
+#pragma unroll 16
+        for (int o = 0; o < NWARP * INSERT_LIMIT; ++o) {
+            const float ov = s_wv[o];
+            const int oi = s_wi[o];
+            rank += (ov > cv || (ov == cv && oi < ci)) ? 1 : 0;
         }
-        for (int k = 0; k < q.beam; ++k) {
-            float bv = cv[0]; int bi = ci[0];
-#pragma unroll
-            for (int j = 1; j < 3; ++j)
-                if (cv[j] > bv || (cv[j] == bv && ci[j] < bi)) { bv = cv[j]; bi = ci[j]; }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-            }
-#pragma unroll
-            for (int j = 0; j < 3; ++j)
-                if (ci[j] == bi) { cv[j] = -INFINITY; ci[j] = 0x7fffffff; }
-            if (lane == 0) { s_topv[k] = bv; s_topi[k] = bi; }
-        }
+        if (rank < q.beam) { s_topv[rank] = cv; s_topi[rank] = ci; }
     }
     __syncthreads();
+    // probabilities and occupancy of the candidates, one lane each
+    const float *occ = q.occ + (size_t)b * G;
+    if (tid < q.beam) {
+        s_p[tid] = expf(s_topv[tid] - gmax) / den;
+        s_occ[tid] = occ[s_topi[tid]];
+    }
+    __syncthreads();
+    stamp();
     __shared__ int s_cell, s_append, s_row;
     if (tid == 0) {
-        float p[INSERT_LIMIT], total = 0.f;
+        float total = 0.f;
         if (q.beam > 1)
-            for (int k = 0; k < q.beam; ++k) { p[k] = expf(s_topv[k] - gmax) / den; total += p[k]; }
-        const float *occ = q.occ + (size_t)b * G;
+            for (int k = 0; k < q.beam; ++k) total += s_p[k];
         // state (:1884-1889): argmax of the 2-way softmax, index 1 = 'enter'
         int enter = s_small[1] > s_small[0] ? 1 : 0;
         if (q.force_enter) enter = 1;
-        int cell = s_topi[0], append = 0, pass = q.pass[b];
+        int pick = 0, append = 0, pass = pass0;
         for (;;) {
             if (q.beam > 1) {
                 const float thr = uniform01(q.seed ^ 0x5EEDu, (unsigned)s.scene_id[b], (unsigned)pass, (unsigned)t) * total;
-                float c = 0.f; int pick = q.beam - 1;
-                for (int k = 0; k < q.beam; ++k) { c += p[k]; if (thr < c) { pick = k; break; } }
-                cell = s_topi[pick];
+                float c = 0.f;
+                pick = q.beam - 1;
+                for (int k = 0; k < q.beam; ++k) { c += s_p[k]; if (thr < c) { pick = k; break; } }
             }
             ++pass;
-            if (occ[cell] != 0.f) {                     // overlap filter (:1906-1909): retry
+            if (s_occ[pick] != 0.f) {                   // overlap filter (:1906-1909): retry
                 // with a deterministic choice (beam 1) every retry repeats this pass: the reference spins until the limit
                 if (q.beam == 1 || pass >= INSERT_LIMIT) { q.active[b] = 0; break; }
                 // The reference restores its features and runs the whole query again (`feat_a = raw_feat_a.clone();
@@ -470,9 +474,9 @@ __device__ __forceinline__ void seed_decide_scene(const SeedDecideArgs &a) {
                 // (keyed by the pass index) differs - the retry is taken here, without another pass of the stage
                 continue;
             }
-            if (!enter || q.n_new[b] + 1 > INSERT_LIMIT) {
+            if (!enter || nnew0 + 1 > INSERT_LIMIT) {
                 q.active[b] = 0;
-            } else if (s.n_rows[b] >= s.cap) {
+            } else if (rows0 >= s.cap) {
                 *q.err = 2;                              // row capacity exhausted
                 q.active[b] = 0;
             } else {
@@ -482,11 +486,12 @@ __device__ __forceinline__ void seed_decide_scene(const SeedDecideArgs &a) {
             break;
         }
         q.pass[b] = pass;
-        s_cell = cell;
+        s_cell = s_topi[pick];
         s_append = append;
-        s_row = s.n_rows[b];
+        s_row = rows0;
     }
     __syncthreads();
+    stamp();
     if (!s_append) return;
     // ---- 1.5 append the new row (:1913-1995) ----
     const int i_new = s_row, r = b * s.cap + i_new, cell = s_cell;
@@ -495,18 +500,21 @@ __device__ __forceinline__ void seed_decide_scene(const SeedDecideArgs &a) {
     const float eh = s.head[(size_t)re * T + col];
     for (int c = tid; c < T; c += NT) {
         const size_t o = (size_t)r * T + c;
-        s.pos[o * 2] = 0.f; s.pos[o * 2 + 1] = 0.f; s.head[o] = 0.f;
-        s.state[o] = ST_INVALID; s.token[o] = -1; s.grid[o] = -1;
+        if (c != col) {                                  // (column col is written below)
+            s.pos[o * 2] = 0.f; s.pos[o * 2 + 1] = 0.f; s.head[o] = 0.f;
+            s.state[o] = ST_INVALID; s.token[o] = -1; s.grid[o] = -1;
+            s.next_state[o] = 0;
+        }
         s.interact[o] = c >= col ? 1 : 0;
         s.tsrc[o] = c >= col ? 1 : 0;                    // temporal_mask all true, sources from the BOS column on (:547-552)
-        s.next_token[o] = -1; s.next_state[o] = 0;
+        s.next_token[o] = -1;
     }
+    const int n_new = nnew0 + 1;
     for (int k = tid; k < 5 * S; k += NT) {
         const size_t o = (size_t)r * (5 * S) + k;
-        s.pred_traj[o * 2] = 0.f; s.pred_traj[o * 2 + 1] = 0.f; s.pred_head[o] = 0.f; s.pred_state[o] = 0.f;
+        const bool ph = t > 0 && k >= (t - 1) * 5 && k < t * 5;   // placeholders of the previous 0.5 s: written below
+        if (!ph) { s.pred_traj[o * 2] = 0.f; s.pred_traj[o * 2 + 1] = 0.f; s.pred_head[o] = 0.f; s.pred_state[o] = 0.f; }
     }
-    __syncthreads();
-    const int n_new = q.n_new[b] + 1;
     if (tid == 0) {
         // decode_pos (attr_tokenizer.py:91-99): grid cell in the ego frame -> world
         const float th = __fsub_rn(eh, 1.5707963267948966f);
@@ -543,13 +551,27 @@ __device__ __forceinline__ void seed_decide_scene(const SeedDecideArgs &a) {
         const float e0 = expf(s_small[0] - m2), e1 = expf(s_small[1] - m2);
         q.rec_state_prob[r] = e1 / (e0 + e1);
         q.rec_meta[(size_t)r * 2] = t; q.rec_meta[(size_t)r * 2 + 1] = n_new;
+        // the grid-sized records of this insertion are written by k_seed_records, off the pass's critical path
+        q.rec_softmax[2 * b] = gmax; q.rec_softmax[2 * b + 1] = den;
     }
-    // grid-sized records of this insertion (:2099-2104)
-    const size_t ob = (size_t)r * G;
-    for (int g = tid; g < G; g += NT) {
+    stamp();
+}
+
+// grid-sized records of the insertions of the last pass (:2099-2104): softmax of the position logits, the two occupancy
+// heads and the occupancy the query saw.  Runs at the start of the heading stage on a side stream, before the occupancy
+// node of the next pass is rebuilt.  One CTA per scene.
+__global__ void __launch_bounds__(NT) k_seed_records(const DecState s, const InsState q) {
+    const int b = blockIdx.x, G = s.G;
+    const int i_new = q.new_row[b];
+    if (i_new < 0) return;
+    const int r = b * s.cap + i_new;
+    const float gmax = q.rec_softmax[2 * b], den = q.rec_softmax[2 * b + 1];
+    const float *lg = q.pos_logits + (size_t)b * q.seed_stride * G;
+    const size_t ob = (size_t)r * G, qb = (size_t)b * q.seed_stride * G;
+    for (int g = threadIdx.x; g < G; g += NT) {
         q.rec_pos_prob[ob + g] = expf(lg[g] - gmax) / den;
-        q.rec_ag_occ[ob + g] = q.ag_occ_logits[(size_t)b * q.seed_stride * G + g];
-        q.rec_pt_occ[ob + g] = q.pt_occ_logits[(size_t)b * q.seed_stride * G + g];
+        q.rec_ag_occ[ob + g] = q.ag_occ_logits[qb + g];
+        q.rec_pt_occ[ob + g] = q.pt_occ_logits[qb + g];
         q.rec_occ_gt[ob + g] = q.occ[(size_t)b * G + g];
     }
 }
@@ -560,13 +582,17 @@ __global__ void __launch_bounds__(NT) k_seed_decide(const SeedDecideArgs a) {
     seed_decide_scene(a);
     const InsState &q = a.q;
     __shared__ int s_last;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        s_last = atomicAdd(q.done_ctr, 1) == (int)gridDim.x - 1;
+    if (gridDim.x > 1) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            s_last = atomicAdd(q.done_ctr, 1) == (int)gridDim.x - 1;
+        }
+        __syncthreads();
+    } else if (threadIdx.x == 0) {
+        s_last = 1;                                     // one scene: its own thread 0 wrote everything the summary reads
     }
-    __syncthreads();
-    if (s_last && threadIdx.x == 0) {
+    if (threadIdx.x == 0 && s_last) {
         __threadfence();
         int any = 0, any_new = 0;
         const int n_prev = *q.n_new_list;
@@ -586,6 +612,7 @@ __global__ void __launch_bounds__(NT) k_seed_decide(const SeedDecideArgs a) {
             cudaGraphSetConditional(q.h_new, (unsigned)any_new);
             q.stat[0] += 1; q.stat[1] += any_new;
         }
+        if (a.tstamp) a.tstamp[40] = clock64();
     }
 }
 
@@ -593,7 +620,7 @@ __global__ void __launch_bounds__(NT) k_seed_decide(const SeedDecideArgs a) {
 // heading stage, edges of the appended rows (:2024-2035): agents within a2sa_radius (first NEW_AGENT_MAX by index)
 // that interact at column cur, map tokens within pl2sa_radius (first NEW_MAP_MAX).  One CTA (two warps) per scene.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int NEW_EDGE_NT = 256;       // warp 0: agents; warps 1..7: contiguous slices of the scene's map tokens
+constexpr int NEW_EDGE_NT = 1024;      // warp 0: agents; warps 1..31: contiguous slices of the scene's map tokens
 __global__ void __launch_bounds__(NEW_EDGE_NT) k_new_edges(const DecState s, const InsState q) {
     __shared__ int s_cnt[NEW_EDGE_NT / 32];
     const int b = blockIdx.x, col = *s.col, T = s.T;

@@ -153,6 +153,12 @@ __device__ __forceinline__ void st_async_f32(uint32_t raddr, float v, uint32_t r
                  : "memory");
 }
 
+__device__ __forceinline__ void st_async_v4(uint32_t raddr, const float4 v, uint32_t rmbar) {
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr),
+                 "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(rmbar)
+                 : "memory");
+}
+
 // LayerNorm of a 128-vector (4 channels per lane) with the affine vectors in shared (or any generic) memory
 __device__ __forceinline__ float4 ln128s(const float4 v, const float *g, const float *b, int lane) {
     float mean, rstd;
@@ -216,6 +222,21 @@ __device__ __forceinline__ void slice_gemm(const float *xs, int ldx, const float
         for (int k = 0; k < KS; ++k) v += p[k * NCG * RG];
         epi(m, n, v);
     }
+}
+// The same product for outputs that leave the CTA: fin(m, n, value) finishes one output, the four outputs of columns
+// 4j .. 4j+3 of a row are then gathered in the lane of column 4j (three shuffles) and handed to send4(m, 4j, float4) - one
+// 16-byte remote store per peer instead of four 4-byte ones (the receiving mbarrier counts one transaction per store).
+template <int M, int NL, int TN, typename Fin, typename Send4>
+__device__ __forceinline__ void slice_gemm_x(const float *xs, int ldx, const float *w, int K4, float *red, Fin fin, Send4 send4) {
+    static_assert((M * NL) % 32 == 0 && NL % 4 == 0, "whole warps in the output loop, whole quads per row");
+    const int lane = threadIdx.x & 31;
+    slice_gemm<M, NL, TN>(xs, ldx, w, K4, red, [&](int m, int n, float v) {
+        v = fin(m, n, v);
+        const int b = lane & ~3;
+        const float4 q = make_float4(__shfl_sync(0xffffffffu, v, b), __shfl_sync(0xffffffffu, v, b + 1),
+                                     __shfl_sync(0xffffffffu, v, b + 2), __shfl_sync(0xffffffffu, v, b + 3));
+        if ((lane & 3) == 0) send4(m, n, q);
+    });
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -445,11 +466,11 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
     uint32_t rbase[CL];                                             // this CTA's shared window as seen ... of every peer
 #pragma unroll
     for (int p = 0; p < CL; ++p) rbase[p] = mapa_u32(sbase, (uint32_t)p);
-    // send one float to the same shared-memory location of all CL CTAs, completing `bytes` on their exchange barrier xb
-    auto xsend = [&](const float *dst, int xb, float v) {
+    // send four floats to the same shared-memory location of all CL CTAs, completing 16 bytes on their exchange barrier xb
+    auto xsend4 = [&](const float *dst, int xb, const float4 v) {   // dst: 16-byte aligned
         const uint32_t off = smem_u32(dst) - sbase, boff = smem_u32(&xbar[xb]) - sbase;
 #pragma unroll
-        for (int p = 0; p < CL; ++p) st_async_f32(rbase[p] + off, v, rbase[p] + boff);
+        for (int p = 0; p < CL; ++p) st_async_v4(rbase[p] + off, v, rbase[p] + boff);
     };
     auto xexpect = [&](int xb, uint32_t bytes) {                   // once per exchange, any time before the wait
         if (tid == 0) mbar_expect_tx(&xbar[xb], bytes);
@@ -640,31 +661,31 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
         } else {
         xexpect(0, M * 128 * 4);
         if (A.has_pos) {
-            slice_gemm<M, 16, (M == 4 ? 2 : 4)>(sragg, LD1, wpost + cs_post::WVR, 32, sred, [&](int m, int n, float v) {
-                v += sagg[m * 16 + n] + wpost[cs_post::BVR + n] * ssal[m];
-                xsend(scat + m * LD2 + 16 * c + n, 0, v);
-            });
+            slice_gemm_x<M, 16, (M == 4 ? 2 : 4)>(sragg, LD1, wpost + cs_post::WVR, 32, sred,
+                [&](int m, int n, float v) { return v + sagg[m * 16 + n] + wpost[cs_post::BVR + n] * ssal[m]; },
+                [&](int m, int n, const float4 v) { xsend4(scat + m * LD2 + 16 * c + n, 0, v); });
         } else {
-            for (int o = tid; o < M * 16; o += NT) xsend(scat + (o >> 4) * LD2 + 16 * c + (o & 15), 0, sagg[o]);
+            for (int o = tid; o < M * 4; o += NT) xsend4(scat + (o >> 2) * LD2 + 16 * c + 4 * (o & 3), 0, ld4(sagg + 4 * o));
         }
         xwait(0);
         }
         stamp();
         // ---- gate: g = sigmoid(Wg [agg | xd] + bg);  u = agg + g * (s - agg) ----------------------------------
         xexpect(1, M * 128 * 4);
-        slice_gemm<M, 16, (M == 4 ? 2 : 4)>(scat, LD2, wpost + cs_post::WG, 64, sred, [&](int m, int n, float v) {
-            const float g = sigmoidf(v + wpost[cs_post::BG + n]);
-            const float ag = scat[m * LD2 + 16 * c + n];
-            const float u = ag + g * (ss[m * 16 + n] - ag);
-            xsend(su + m * LD1 + 16 * c + n, 1, u);
-        });
+        slice_gemm_x<M, 16, (M == 4 ? 2 : 4)>(scat, LD2, wpost + cs_post::WG, 64, sred,
+            [&](int m, int n, float v) {
+                const float g = sigmoidf(v + wpost[cs_post::BG + n]);
+                const float ag = scat[m * LD2 + 16 * c + n];
+                return ag + g * (ss[m * 16 + n] - ag);
+            },
+            [&](int m, int n, const float4 u) { xsend4(su + m * LD1 + 16 * c + n, 1, u); });
         xwait(1);
         stamp();
         // ---- to_out ------------------------------------------------------------------------------------------
         xexpect(2, M * 128 * 4);
-        slice_gemm<M, 16, (M == 4 ? 2 : 4)>(su, LD1, wpost + cs_post::WO, 32, sred, [&](int m, int n, float v) {
-            xsend(so + m * LD1 + 16 * c + n, 2, v + wpost[cs_post::BO + n]);
-        });
+        slice_gemm_x<M, 16, (M == 4 ? 2 : 4)>(su, LD1, wpost + cs_post::WO, 32, sred,
+            [&](int m, int n, float v) { return v + wpost[cs_post::BO + n]; },
+            [&](int m, int n, const float4 v) { xsend4(so + m * LD1 + 16 * c + n, 2, v); });
         xwait(2);
         stamp();
         // x1 = x + LN_post(o);  so = LN_ffpre(x1)
@@ -678,15 +699,15 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
         __syncthreads();
         // ---- FFN ---------------------------------------------------------------------------------------------
         xexpect(3, M * 512 * 4);
-        slice_gemm<M, 64, 4>(so, LD1, wpost + cs_post::W1, 32, sred, [&](int m, int n, float v) {
-            xsend(sh + m * LD5 + 64 * c + n, 3, fmaxf(v + wpost[cs_post::B1 + n], 0.f));
-        });
+        slice_gemm_x<M, 64, 4>(so, LD1, wpost + cs_post::W1, 32, sred,
+            [&](int m, int n, float v) { return fmaxf(v + wpost[cs_post::B1 + n], 0.f); },
+            [&](int m, int n, const float4 v) { xsend4(sh + m * LD5 + 64 * c + n, 3, v); });
         xwait(3);
         stamp();
         xexpect(4, M * 128 * 4);
-        slice_gemm<M, 16, (M == 4 ? 2 : 4)>(sh, LD5, wpost + cs_post::W2, 128, sred, [&](int m, int n, float v) {
-            xsend(sy + m * LD1 + 16 * c + n, 4, v + wpost[cs_post::B2 + n]);
-        });
+        slice_gemm_x<M, 16, (M == 4 ? 2 : 4)>(sh, LD5, wpost + cs_post::W2, 128, sred,
+            [&](int m, int n, float v) { return v + wpost[cs_post::B2 + n]; },
+            [&](int m, int n, const float4 v) { xsend4(sy + m * LD1 + 16 * c + n, 4, v); });
         xwait(4);
         stamp();
         // x2 = x1 + LN_ffpost(y)

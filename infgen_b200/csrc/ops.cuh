@@ -132,7 +132,8 @@ struct FourierArgs {
     float *out;                // [slots][128]
     int normalize;             // 1: store (y - mean) / std of the output (input of every layer's attn_prenorm_r)
     const int *slot_list;      // optional compact list of the valid slots (k_slot_compact); tiles walk it instead of
-    const int *n_list;         //   the strided slot space: *n_list entries (k_fourier_tc only)
+    const int *n_list;         //   the strided slot space: *n_list entries
+    int ffma;                  // 1: the FFMA kernel even where the tensor-core one applies (a handful of slots: its GEMV path)
     int raw_stride;            // floats per slot in `raw` (0: dim)
     const float *dim_table;    // optional [table_n][128]: the per-dim MLP output of input dim `dim` (the one after the
     int table_n;               //   last tensor-core dim) for the inputs -1, -2, .. -table_n (k_fourier_tc only)
@@ -158,7 +159,7 @@ __device__ __forceinline__ int fourier_segs(const FourierW &w, int dim, WSeg *se
 // zeros); the result (before any standardisation) is left in sH.  Ends with a csync().
 template <int M>
 __device__ __forceinline__ void fourier_body(WsCons &ws, const FourierW &w, int dim, const float *sraw, float *sF,
-                                             float *sH, float *sA) {
+                                             float *sH, float *sA, bool single = false) {
     const int tid = threadIdx.x;
     for (int d = 0; d < dim; ++d) {
         csync();
@@ -177,16 +178,16 @@ __device__ __forceinline__ void fourier_body(WsCons &ws, const FourierW &w, int 
             sF[tid * FLD + 129] = 0.f; sF[tid * FLD + 130] = 0.f; sF[tid * FLD + 131] = 0.f;
         }
         csync();
-        tile_gemm<M>(ws, sF, FLD, 33, [&](int m, int n, float v) { sH[m * HLD + n] = v + __ldg(w.b0[d] + n); });
+        tile_gemm<M>(ws, sF, FLD, 33, [&](int m, int n, float v) { sH[m * HLD + n] = v + __ldg(w.b0[d] + n); }, single);
         csync();
         rows_layernorm_c<M, true>(sH, HLD, w.ln_g[d], w.ln_b[d]);
         csync();
-        tile_gemm<M>(ws, sH, HLD, 32, [&](int m, int n, float v) { sA[m * HLD + n] += v + __ldg(w.b3[d] + n); });
+        tile_gemm<M>(ws, sH, HLD, 32, [&](int m, int n, float v) { sA[m * HLD + n] += v + __ldg(w.b3[d] + n); }, single);
     }
     csync();
     rows_layernorm_c<M, true>(sA, HLD, w.out_ln_g, w.out_ln_b);
     csync();
-    tile_gemm<M>(ws, sA, HLD, 32, [&](int m, int n, float v) { sH[m * HLD + n] = v + __ldg(w.b_out + n); });
+    tile_gemm<M>(ws, sA, HLD, 32, [&](int m, int n, float v) { sH[m * HLD + n] = v + __ldg(w.b_out + n); }, single);
     csync();
 }
 
@@ -206,14 +207,23 @@ __global__ void __launch_bounds__(NT_S) k_fourier(const FourierBatch fb) {
     const FourierArgs &a = fb.job[j];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int s0 = ((int)blockIdx.x - fb.tile0[j]) * FM;
+    __shared__ int s_slot[FM];              // slot of every tile position (a compact slot list redirects it)
     int v = 0;
     if (tid < FM) {
-        const int s = s0 + tid;
-        if (s < a.n_slots) v = a.cnt ? ((s % a.stride) < a.cnt[s / a.stride]) : 1;
+        int s = s0 + tid;
+        if (a.slot_list) {
+            v = s < *a.n_list;
+            s = v ? a.slot_list[s] : 0;
+        } else if (s < a.n_slots) {
+            v = a.cnt ? ((s % a.stride) < a.cnt[s / a.stride]) : 1;
+        }
         s_valid[tid] = v;
+        s_slot[tid] = s;
         for (int d = 0; d < 4; ++d) sraw[tid * 4 + d] = (v && d < a.dim) ? a.raw[(size_t)s * a.dim + d] : 0.f;
     }
     if (!__syncthreads_or(v)) return;
+    bool single = s_valid[0] != 0;          // only the first position live: GEMV path of the tile products
+    for (int m = 1; m < FM; ++m) single = single && !s_valid[m];
     ws_init(wsm);
     if (warp == NWARP) {
         if (lane < WS_STAGES) {
@@ -228,12 +238,12 @@ __global__ void __launch_bounds__(NT_S) k_fourier(const FourierBatch fb) {
     for (int m = warp; m < FM; m += NWARP) {
         float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
         if (a.cat_tab && s_valid[m]) {
-            const int row = a.cat_idx ? a.cat_idx[s0 + m] : (s0 + m);
+            const int row = a.cat_idx ? a.cat_idx[s_slot[m]] : s_slot[m];
             c = ld4(a.cat_tab + (size_t)row * 128 + 4 * lane);
         }
         st4(sA + m * HLD + 4 * lane, c);
     }
-    fourier_body<FM>(ws, a.w, a.dim, sraw, sF, sH, sA);
+    fourier_body<FM>(ws, a.w, a.dim, sraw, sF, sH, sA, single);
     for (int m = warp; m < FM; m += NWARP) {
         if (!s_valid[m]) continue;
         float4 y = ld4(sH + m * HLD + 4 * lane);
@@ -242,7 +252,7 @@ __global__ void __launch_bounds__(NT_S) k_fourier(const FourierBatch fb) {
             ln_stats(y, mean, rstd);
             y = make_float4((y.x - mean) * rstd, (y.y - mean) * rstd, (y.z - mean) * rstd, (y.w - mean) * rstd);
         }
-        st4(a.out + (size_t)(s0 + m) * 128 + 4 * lane, y);
+        st4(a.out + (size_t)s_slot[m] * 128 + 4 * lane, y);
     }
 }
 
@@ -260,16 +270,16 @@ __device__ __forceinline__ int mlp3_segs(const MlpEmbW &w, int k4, WSeg *segs) {
 // consumers: sX [M][ldx] -> epi(m, n, value); sH, sG: [M][HLD] scratch.  The caller csync()s after filling sX.
 template <int M, typename Epi>
 __device__ __forceinline__ void mlp3_body(WsCons &ws, const MlpEmbW &w, const float *sX, int ldx, int k4, float *sH,
-                                          float *sG, Epi epi) {
-    tile_gemm<M>(ws, sX, ldx, k4, [&](int m, int n, float v) { sH[m * HLD + n] = v + __ldg(w.b0 + n); });
+                                          float *sG, Epi epi, bool single = false) {
+    tile_gemm<M>(ws, sX, ldx, k4, [&](int m, int n, float v) { sH[m * HLD + n] = v + __ldg(w.b0 + n); }, single);
     csync();
     rows_layernorm_c<M, true>(sH, HLD, w.ln1_g, w.ln1_b);
     csync();
-    tile_gemm<M>(ws, sH, HLD, 32, [&](int m, int n, float v) { sG[m * HLD + n] = v + __ldg(w.b3 + n); });
+    tile_gemm<M>(ws, sH, HLD, 32, [&](int m, int n, float v) { sG[m * HLD + n] = v + __ldg(w.b3 + n); }, single);
     csync();
     rows_layernorm_c<M, true>(sG, HLD, w.ln4_g, w.ln4_b);
     csync();
-    tile_gemm<M>(ws, sG, HLD, 32, [&](int m, int n, float v) { epi(m, n, v + __ldg(w.b6 + n)); });
+    tile_gemm<M>(ws, sG, HLD, 32, [&](int m, int n, float v) { epi(m, n, v + __ldg(w.b6 + n)); }, single);
 }
 // leading dimension of a [rows][4*k4] input tile: padded so that it is 4 (mod 32) floats when wide
 __host__ __device__ __forceinline__ int mlp_ldx(int k4) { return k4 * 4 + ((k4 * 4) % 32 == 0 ? 4 : 0); }
@@ -317,10 +327,12 @@ __global__ void __launch_bounds__(NT_S) k_mlp_embed(const MlpEmbArgs a) {
         sX[i] = (k < a.kin && r >= 0) ? a.x[(size_t)r * a.x_ld + k] : 0.f;
     }
     csync();
+    bool single = s_row[0] >= 0;
+    for (int m = 1; m < EM; ++m) single = single && s_row[m] < 0;
     mlp3_body<EM>(ws, a.w, sX, ldx, a.k4, sH, sG, [&](int m, int n, float v) {
         const int r = s_row[m];
         if (r >= 0) a.out[(size_t)r * a.out_ld + n] = v;
-    });
+    }, single);
 }
 static inline size_t mlp_embed_smem(int k4) { return (size_t)(WS_SMEM_FLOATS + EM * mlp_ldx(k4) + 2 * EM * HLD) * sizeof(float); }
 
@@ -478,9 +490,11 @@ struct MlpLayerArgs {
     const float *x;
     MlpHeadW w;
     float *out;                // [n][n_out]
-    // up to three heads over the same input rows in one launch (blockIdx.z): the grid-sized heads of the seed query
-    MlpHeadW w2, w3;
-    float *out2, *out3;
+    // up to six heads over the same input rows in one launch (blockIdx.z): the heads of the seed query
+    MlpHeadW w2, w3, w4, w5, w6;
+    float *out2, *out3, *out4, *out5, *out6;
+    int single_stride;         // > 0: only rows 0, single_stride, 2 * single_stride, .. are live; a tile that holds one live
+                               //      row (its first) takes the GEMV path of the tile products
 };
 constexpr size_t MLP_LAYER_SMEM = (size_t)(WS_SMEM_FLOATS + 2 * HM * HLD) * sizeof(float);
 __global__ void __launch_bounds__(NT_S) k_mlp_layer(const MlpLayerArgs a) {
@@ -489,8 +503,18 @@ __global__ void __launch_bounds__(NT_S) k_mlp_layer(const MlpLayerArgs a) {
     float *sx = smem + WS_SMEM_FLOATS, *sh = sx + HM * HLD;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = blockIdx.x * HM, n0 = blockIdx.y * 128;
-    const MlpHeadW &hw = blockIdx.z == 0 ? a.w : (blockIdx.z == 1 ? a.w2 : a.w3);
-    float *out = blockIdx.z == 0 ? a.out : (blockIdx.z == 1 ? a.out2 : a.out3);
+    // (selected by value: indexing the parameter block dynamically would move it to a local-memory frame)
+    MlpHeadW hw;
+    float *out;
+    switch (blockIdx.z) {
+        case 0: hw = a.w; out = a.out; break;
+        case 1: hw = a.w2; out = a.out2; break;
+        case 2: hw = a.w3; out = a.out3; break;
+        case 3: hw = a.w4; out = a.out4; break;
+        case 4: hw = a.w5; out = a.out5; break;
+        default: hw = a.w6; out = a.out6; break;
+    }
+    const bool single = a.single_stride >= HM || (a.single_stride > 0 && row0 + a.single_stride >= a.n);
     if (n0 >= hw.n_pad) return;
     ws_init(wsm);
     if (warp == NWARP) {
@@ -508,14 +532,14 @@ __global__ void __launch_bounds__(NT_S) k_mlp_layer(const MlpLayerArgs a) {
         st4(sx + m * HLD + 4 * lane, r < a.n ? ld4(a.x + (size_t)r * 128 + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f));
     }
     csync();
-    tile_gemm<HM>(ws, sx, HLD, hw.k4_in, [&](int m, int n, float v) { sh[m * HLD + n] = v + __ldg(hw.b0 + n); });
+    tile_gemm<HM>(ws, sx, HLD, hw.k4_in, [&](int m, int n, float v) { sh[m * HLD + n] = v + __ldg(hw.b0 + n); }, single);
     csync();
     rows_layernorm_c<HM, true>(sh, HLD, hw.ln_g, hw.ln_b);
     csync();
     tile_gemm<HM>(ws, sh, HLD, 32, [&](int m, int n, float v) {
         const int r = row0 + m;
         if (r < a.n && n0 + n < hw.n_out) out[(size_t)r * hw.n_out + n0 + n] = v + __ldg(hw.b3 + n0 + n);
-    });
+    }, single);
 }
 
 }  // namespace infgen

@@ -140,11 +140,43 @@ using WsCons = WsConsT<WS_STAGES>;
 // lanes, RL = 32/CL row lanes.  X: shared, row-major, leading dimension ldx; ldx % 32 == 4 keeps the row-lane loads
 // bank-conflict free.  epi(m, n, value) once per output.  No barrier inside: the caller csync()s before.
 // ---------------------------------------------------------------------------------------------------------------------
+// single (uniform over the CTA): only row 0 of the tile is live (the row an insertion pass appended).  The product is then
+// a GEMV: lanes 0..15 of warp w own one column each and walk the k4 rows of every stage in the same order as the tile code
+// (bitwise the same row 0), 16 instead of 40 shared-memory loads per warp and stage; epi runs for row 0 only.
 template <int M, typename Cons, typename Epi>
-__device__ __forceinline__ void stream_gemm(Cons &ws, const float *xs, int ldx, int K4, Epi epi) {
+__device__ __forceinline__ void stream_gemm(Cons &ws, const float *xs, int ldx, int K4, Epi epi, bool single = false) {
     static_assert(M == 8 || M == 16 || M == 32, "tile rows");
     constexpr int NTT = M / 8, CLN = 16 / NTT, RLN = 32 / CLN;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (single) {
+        const bool on = lane < 16;
+        const int c = 16 * warp + (lane & 15);
+        float a1 = 0.f;
+        for (int kb = 0; kb < K4; kb += WS_ROWS) {
+            const int rows = min(WS_ROWS, K4 - kb);
+            const float *w = ws.acquire();
+            if (on) {
+                if (rows == WS_ROWS) {
+                    float4 wv[WS_ROWS], xv[WS_ROWS];
+#pragma unroll
+                    for (int kk = 0; kk < WS_ROWS; ++kk) { wv[kk] = ld4(w + (kk * 128 + c) * 4); xv[kk] = ld4(xs + 4 * (kb + kk)); }
+#pragma unroll
+                    for (int kk = 0; kk < WS_ROWS; ++kk) {
+                        a1 = fmaf(xv[kk].x, wv[kk].x, a1); a1 = fmaf(xv[kk].y, wv[kk].y, a1);
+                        a1 = fmaf(xv[kk].z, wv[kk].z, a1); a1 = fmaf(xv[kk].w, wv[kk].w, a1);
+                    }
+                } else {
+                    for (int kk = 0; kk < rows; ++kk) {
+                        const float4 wv = ld4(w + (kk * 128 + c) * 4), xv = ld4(xs + 4 * (kb + kk));
+                        a1 = fmaf(xv.x, wv.x, a1); a1 = fmaf(xv.y, wv.y, a1); a1 = fmaf(xv.z, wv.z, a1); a1 = fmaf(xv.w, wv.w, a1);
+                    }
+                }
+            }
+            ws.release();
+        }
+        if (on) epi(0, c, a1);
+        return;
+    }
     const int cl = lane % CLN, rl = lane / CLN;
     float acc[4][NTT];
 #pragma unroll
@@ -365,14 +397,16 @@ __device__ __forceinline__ void stream_gemm_mma(Cons &ws, const float *xs, int l
 // FFMA (128 MAC/clk/SM) - only tcgen05 would be, and that needs 64/128-row tiles a single scene does not have.
 // Build with -DINFGEN_MMA to use the tensor-core variant for the 16/32-row tiles (parity-tested, same tolerances).
 template <int M, typename Cons, typename Epi>
-__device__ __forceinline__ void tile_gemm(Cons &ws, const float *xs, int ldx, int K4, Epi epi) {
+__device__ __forceinline__ void tile_gemm(Cons &ws, const float *xs, int ldx, int K4, Epi epi, bool single = false) {
 #ifdef INFGEN_MMA
     if constexpr (M == 16 || M == 32) {
-        stream_gemm_mma<M>(ws, xs, ldx, K4, epi);
-        return;
+        if (!single) {
+            stream_gemm_mma<M>(ws, xs, ldx, K4, epi);
+            return;
+        }
     }
 #endif
-    stream_gemm<M>(ws, xs, ldx, K4, epi);
+    stream_gemm<M>(ws, xs, ldx, K4, epi, single);
 }
 
 // In-place LayerNorm (+ optional ReLU) of M rows, one warp per row; callers csync() before and after
