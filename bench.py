@@ -602,10 +602,33 @@ def run_ours(args, rank, world, local_rank):
                 t0 = time.perf_counter()
                 prep.tokenize(d)
                 ts.append(time.perf_counter() - t0)
+            # map side (InfGen.match_token_map): 2,048 polylines of 5 m against the 1,024-entry map vocabulary
+            from infgen_b200.map_encoder import load_map_vocab
+            src = load_map_vocab()
+            sp = src[:, torch.linspace(0, src.shape[1] - 1, steps=3).long()].contiguous()
+            rng = np.random.default_rng(11)
+            P = 2048
+            ids, theta = rng.integers(0, sp.shape[0], size=P), rng.uniform(-np.pi, np.pi, size=P).astype(np.float32)
+            c_, s_ = np.cos(theta)[:, None], np.sin(theta)[:, None]
+            loc = sp.numpy()[ids] + rng.normal(0.0, 0.05, size=(P, 3, 2)).astype(np.float32)
+            world_pts = np.stack([loc[..., 0] * c_ - loc[..., 1] * s_, loc[..., 0] * s_ + loc[..., 1] * c_], -1)
+            world_pts = (world_pts - world_pts[:, :1] + rng.uniform(-150.0, 150.0, size=(P, 1, 2))).astype(np.float32)
+            md = {'map_save': {'traj_pos': torch.from_numpy(world_pts), 'traj_theta': torch.from_numpy(theta),
+                               'pl_idx_list': torch.from_numpy(np.sort(rng.integers(0, 64, size=P)).astype(np.float32))},
+                  'pt_token': {'side': torch.zeros(P, dtype=torch.uint8), 'num_nodes': P}}
+            for _ in range(3):
+                prep.match_token_map(md)
+            tm = []
+            for _ in range(10):
+                t0 = time.perf_counter()
+                prep.match_token_map(md)
+                tm.append(time.perf_counter() - t0)
             pdec.close()
             out = {'workload': 'agent tokenizer + enterings of the configs[1] scene (64 agents x 91 raw steps, 2048 map tokens): '
                                'closed-loop match over 2048 vocabulary boxes per token step, ego-centric grid cells of agents and '
-                               'map tokens per column', 'gpu_ms': statistics.mean(ts) * 1e3, 'gpu_ms_min': min(ts) * 1e3}
+                               'map tokens per column', 'gpu_ms': statistics.mean(ts) * 1e3, 'gpu_ms_min': min(ts) * 1e3,
+                   'map_match_workload': 'InfGen.match_token_map: 2,048 map polylines against the 1,024-entry map vocabulary, '
+                   'host tensors in and out', 'map_match_gpu_ms': statistics.mean(tm) * 1e3}
             try:
                 from oracle.scene_prep_oracle import tokenize_agent, fetch_enterings
                 from infgen_b200.synth import load_vocab
@@ -615,6 +638,10 @@ def run_ours(args, rank, world, local_rank):
                 tk = tokenize_agent(raw, load_vocab())
                 fetch_enterings(tk, scenes[0]['pt_token']['position'], int(raw['av_idx'][0]), g.cells, cfg.pl2seed_radius, cfg.angle_interval)
                 out['cpu_port_ms'] = (time.perf_counter() - t0) * 1e3
+                from oracle.scene_prep_oracle import match_token_map
+                t0 = time.perf_counter()
+                match_token_map(world_pts, theta, md['map_save']['pl_idx_list'], md['pt_token']['side'], sp)
+                out['map_match_cpu_port_ms'] = (time.perf_counter() - t0) * 1e3
             except Exception as ex:
                 out['cpu_port_error'] = repr(ex)[:200]
             return out

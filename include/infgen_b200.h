@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define INFGEN_ABI_VERSION 7
+#define INFGEN_ABI_VERSION 8
 
 typedef enum {
     INFGEN_OK = 0,
@@ -240,6 +240,27 @@ typedef struct {
 } infgen_prep_out;
 /* tokenize + fetch_enterings of one scene on the device (vocabulary and grid cells are the engine's). */
 int32_t infgen_prepare_scene(infgen_engine *e, const infgen_prep_in *in, const infgen_prep_out *out);
+
+/* ---- row f2, map side: `InfGen.match_token_map` (infgen/model/infgen.py:918-984) on the device.  Inputs are the
+ * `map_save` fields `TokenProcessor._tokenize_map` writes (preprocess.py:749-758), host arrays. --------------------- */
+typedef struct {
+    int32_t n_tokens;             /* P polylines of 5 m (three points each) */
+    int32_t n_vocab;              /* entries of the map vocabulary (1024) */
+    int32_t n_polygons;           /* distinct polygons of the scene */
+    const float *traj_pos;        /* [P][3][2] data['map_save']['traj_pos'].float() */
+    const float *traj_theta;      /* [P]       data['map_save']['traj_theta'].float() */
+    const int32_t *pl_rank;       /* [P] row of data['map_save']['pl_idx_list'][i] among its sorted distinct values */
+    const uint8_t *side;          /* [P] data['pt_token']['side'] */
+    const float *sample_pt;       /* [n_vocab][3][2] map_token['sample_pt'] (infgen.py:208-209) */
+} infgen_map_match_in;
+typedef struct {
+    int64_t *token_idx;           /* [P] data['pt_token']['token_idx'] */
+    float *position;              /* [P][3] first point of the polyline, z = 0 */
+    float *orientation;           /* [P] */
+    int32_t *side_counts;         /* [n_polygons][3] polylines per polygon and side (rows of traj_mask, infgen.py:955-971) */
+    float *best_distance;         /* [P] optional: summed squared distance of the match */
+} infgen_map_match_out;
+int32_t infgen_match_map_tokens(infgen_engine *e, const infgen_map_match_in *in, const infgen_map_match_out *out);
 
 /* ---- per-kernel-class device timing for the roofline report (bench.py): CUDA events around every launch; turns
  * graph replay off while enabled ------------------------------------------------------------------------------ */

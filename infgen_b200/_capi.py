@@ -9,7 +9,7 @@ import os
 from typing import Optional
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib', 'libinfgen_b200.so')
-ABI_VERSION = 7
+ABI_VERSION = 8
 HOST, DEVICE = 0, 1
 
 c_f32p = C.POINTER(C.c_float)
@@ -69,6 +69,20 @@ class PrepOut(C.Structure):
     ]
 
 
+class MapMatchIn(C.Structure):
+    _fields_ = [
+        ('n_tokens', C.c_int32), ('n_vocab', C.c_int32), ('n_polygons', C.c_int32),
+        ('traj_pos', c_f32p), ('traj_theta', c_f32p), ('pl_rank', c_i32p), ('side', c_u8p), ('sample_pt', c_f32p),
+    ]
+
+
+class MapMatchOut(C.Structure):
+    _fields_ = [
+        ('token_idx', c_i64p), ('position', c_f32p), ('orientation', c_f32p), ('side_counts', c_i32p),
+        ('best_distance', c_f32p),
+    ]
+
+
 class Outputs(C.Structure):
     _fields_ = [
         ('pos', c_f32p), ('head', c_f32p), ('pred_traj', c_f32p), ('pred_head', c_f32p), ('pred_state', c_f32p),
@@ -104,6 +118,7 @@ SYMBOLS = {
     'infgen_map_setup': (C.c_int32, [C.c_void_p, c_f32p, C.c_int32]),
     'infgen_map_encode': (C.c_int32, [C.c_void_p, C.POINTER(MapBatch), C.c_int32, c_f32p, c_f32p]),
     'infgen_prepare_scene': (C.c_int32, [C.c_void_p, C.POINTER(PrepIn), C.POINTER(PrepOut)]),
+    'infgen_match_map_tokens': (C.c_int32, [C.c_void_p, C.POINTER(MapMatchIn), C.POINTER(MapMatchOut)]),
     'infgen_kernel_launches': (C.c_int64, [C.c_void_p]),
     'infgen_set_profile': (C.c_int32, [C.c_void_p, C.c_int32]),
     'infgen_profile_class_count': (C.c_int32, []),

@@ -2286,6 +2286,56 @@ int32_t infgen_prepare_scene(infgen_engine *e, const infgen_prep_in *in, const i
     return 0;
 }
 
+int32_t infgen_match_map_tokens(infgen_engine *e, const infgen_map_match_in *in, const infgen_map_match_out *out) {
+    if (!e || !in || !out) return fail(INFGEN_ERR_INVALID_ARG, "null argument");
+    const int P = in->n_tokens, V = in->n_vocab, NP = in->n_polygons;
+    if (P <= 0 || V <= 0 || V > 8192 || NP <= 0)
+        return fail(INFGEN_ERR_INVALID_ARG, "match_map_tokens: P=%d V=%d polygons=%d out of range", P, V, NP);
+    if (!in->traj_pos || !in->traj_theta || !in->pl_rank || !in->side || !in->sample_pt || !out->token_idx ||
+        !out->position || !out->orientation || !out->side_counts)
+        return fail(INFGEN_ERR_INVALID_ARG, "match_map_tokens: missing input / output array");
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_pos = take((size_t)P * 24), o_th = take((size_t)P * 4), o_rank = take((size_t)P * 4), o_side = take(P),
+                 o_voc = take((size_t)V * 24), o_tok = take((size_t)P * 8), o_out = take((size_t)P * 12), o_ori = take((size_t)P * 4),
+                 o_best = take((size_t)P * 4), o_cnt = take((size_t)NP * 12);
+    if (off > e->prep_bytes) {
+        CK(cudaStreamSynchronize(e->stream));
+        cudaFree(e->prep_buf);
+        e->prep_buf = nullptr; e->prep_bytes = 0;
+        CK(cudaMalloc(&e->prep_buf, off));
+        e->prep_bytes = off;
+    }
+    char *base = (char *)e->prep_buf;
+    auto up = [&](size_t o, const void *src, size_t bytes) {
+        return cudaMemcpyAsync(base + o, src, bytes, cudaMemcpyHostToDevice, e->stream);
+    };
+    CK(up(o_pos, in->traj_pos, (size_t)P * 24)); CK(up(o_th, in->traj_theta, (size_t)P * 4));
+    CK(up(o_rank, in->pl_rank, (size_t)P * 4)); CK(up(o_side, in->side, P)); CK(up(o_voc, in->sample_pt, (size_t)V * 24));
+    CK(cudaMemsetAsync(base + o_cnt, 0, (size_t)NP * 12, e->stream));
+    MapMatchArgs ma;
+    memset(&ma, 0, sizeof(ma));
+    ma.P = P; ma.V = V;
+    ma.traj_pos = (const float *)(base + o_pos); ma.traj_theta = (const float *)(base + o_th);
+    ma.pl_rank = (const int *)(base + o_rank); ma.side = (const unsigned char *)(base + o_side);
+    ma.sample_pt = (const float *)(base + o_voc);
+    ma.token_idx = (long long *)(base + o_tok); ma.position = (float *)(base + o_out); ma.orientation = (float *)(base + o_ori);
+    ma.best = (float *)(base + o_best); ma.counts = (int *)(base + o_cnt);
+    const size_t smem = (size_t)V * 24;
+    if (smem > 48 * 1024)
+        CK(cudaFuncSetAttribute(k_match_map_tokens, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_match_map_tokens<<<(P + MATCH_NT / 32 - 1) / (MATCH_NT / 32), MATCH_NT, smem, e->stream>>>(ma);
+    CKL(); count_launch(e);
+    CK(cudaMemcpyAsync(out->token_idx, ma.token_idx, (size_t)P * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(out->position, ma.position, (size_t)P * 12, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(out->orientation, ma.orientation, (size_t)P * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(out->side_counts, ma.counts, (size_t)NP * 12, cudaMemcpyDeviceToHost, e->stream));
+    if (out->best_distance) CK(cudaMemcpyAsync(out->best_distance, ma.best, (size_t)P * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+
 int32_t infgen_op_attention_layer(infgen_engine *e, const char *layer, const float *x_src, int32_t n_src,
                                   const float *x_dst, int32_t n_dst, const float *r, const int32_t *edge_ptr,
                                   const int32_t *edge_src, float *out) {

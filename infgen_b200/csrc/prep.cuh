@@ -288,4 +288,70 @@ __global__ void k_sort_enterings(const EnterArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Map side of the preparation: `InfGen.match_token_map` (infgen/model/infgen.py:918-984).  One warp per 5 m map polyline
+// (three points): the points are moved into the frame of the first one (:927-935), the lanes stride over the map
+// vocabulary (three sample points per entry, shared memory) and keep the entry with the smallest summed squared distance
+// (:936-937; ties to the lower index as torch.argmin); lane 0 also counts the polyline for its (polygon, side) row of
+// the scene's [polygon, side, slot] mask (:955-971).
+// ---------------------------------------------------------------------------------------------------------------
+struct MapMatchArgs {
+    int P, V;
+    const float *traj_pos;         // [P][3][2]
+    const float *traj_theta;       // [P]
+    const int *pl_rank;            // [P] row of the owning polygon among the scene's sorted distinct polygons
+    const unsigned char *side;     // [P] 0 left, 1 right, 2 centre
+    const float *sample_pt;        // [V][3][2]
+    long long *token_idx;          // [P]
+    float *position;               // [P][3]
+    float *orientation;            // [P]
+    float *best;                   // [P] distance of the match (tests: margin of near ties)
+    int *counts;                   // [polygons][3], zeroed
+};
+constexpr int MATCH_NT = 256;
+__global__ void __launch_bounds__(MATCH_NT) k_match_map_tokens(const MapMatchArgs a) {
+    extern __shared__ __align__(16) float s_tok[];                 // [V][6]
+    for (int i = threadIdx.x; i < a.V * 6; i += MATCH_NT) s_tok[i] = a.sample_pt[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * (MATCH_NT / 32) + warp;
+    if (t >= a.P) return;
+    const float *tp = a.traj_pos + (size_t)t * 6;
+    const float th = a.traj_theta[t];
+    const float c = cosf(th), s = sinf(th);
+    float lx[3], ly[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {                                   // [dx, dy] x [[c, -s], [s, c]]
+        const float dx = __fsub_rn(tp[2 * j], tp[0]), dy = __fsub_rn(tp[2 * j + 1], tp[1]);
+        lx[j] = __fmaf_rn(dy, s, __fmul_rn(dx, c));                 // torch's K = 2 bmm on the CPU: fma(a1, b1, a0 * b0)
+        ly[j] = __fmaf_rn(dy, c, __fmul_rn(dx, -s));
+    }
+    float bd = INFINITY;
+    int bi = 0x7fffffff;
+    for (int v = lane; v < a.V; v += 32) {
+        const float *q = s_tok + v * 6;
+        float d = 0.f;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float ex = __fsub_rn(q[2 * j], lx[j]), ey = __fsub_rn(q[2 * j + 1], ly[j]);
+            d = __fadd_rn(d, __fmul_rn(ex, ex));
+            d = __fadd_rn(d, __fmul_rn(ey, ey));
+        }
+        if (d < bd) { bd = d; bi = v; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+    }
+    if (lane == 0) {
+        a.token_idx[t] = bi;
+        a.position[(size_t)t * 3] = tp[0]; a.position[(size_t)t * 3 + 1] = tp[1]; a.position[(size_t)t * 3 + 2] = 0.f;
+        a.orientation[t] = th;
+        if (a.best) a.best[t] = bd;
+        atomicAdd(a.counts + a.pl_rank[t] * 3 + min((int)a.side[t], 2), 1);
+    }
+}
+
 }  // namespace infgen

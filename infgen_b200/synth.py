@@ -228,3 +228,49 @@ def make_map_tokens(scene, seed: int = 0, n_polygons: int = 64):
         'pt_pred_mask': torch.from_numpy(pred), 'pt_valid_mask': torch.ones(P, dtype=torch.bool),
         'pt_target_mask': torch.from_numpy(pred.copy()),
     }
+
+
+def make_raw_map(seed: int, n_polygons: int = 24, extent: float = 120.0):
+    """Synthetic RAW map of a scene, schema of the reference's pre-processed scenario files (`map_point` / `map_polygon` /
+    point -> polygon edges): lanes as polygons whose points are sampled every ~1 m along straight,
+    curved and kinked centre lines, some with a second point type (road edge) running beside the centre line.  Input of
+    `TokenProcessor._tokenize_map` (reference preprocess.py:693-761), whose `map_save` fields `match_token_map` consumes.
+    numpy PCG64: bit-identical in every container."""
+    rng = np.random.default_rng(20_000 + seed)
+    pos, ori, typ, pl = [], [], [], []
+    pl_type = []
+    for i in range(n_polygons):
+        n = int(rng.integers(12, 90))
+        s = np.arange(n) * rng.uniform(0.8, 1.3)
+        x0, y0 = rng.uniform(-extent, extent, size=2)
+        th0 = rng.uniform(-np.pi, np.pi)
+        kind = i % 4
+        if kind == 0:                                    # straight
+            th = np.full(n, th0)
+        elif kind == 1:                                  # arc
+            th = th0 + s / rng.uniform(25.0, 80.0) * rng.choice([-1.0, 1.0])
+        elif kind == 2:                                  # S curve
+            th = th0 + 0.4 * np.sin(s / rng.uniform(8.0, 20.0))
+        else:                                            # kink (a polyline split, preprocess.py:66-77)
+            th = np.where(np.arange(n) < n // 2, th0, th0 + rng.uniform(0.5, 1.2))
+        dx, dy = np.cos(th), np.sin(th)
+        step = np.diff(s, prepend=0.0)
+        px, py = x0 + np.cumsum(dx * step), y0 + np.cumsum(dy * step)
+        groups = [(16, 0.0)] if i % 3 else [(16, 0.0), (12, 1.8)]
+        for t, lateral in groups:
+            pos.append(np.stack([px - lateral * dy, py + lateral * dx, np.zeros(n)], -1))
+            ori.append(th)
+            typ.append(np.full(n, t))
+            pl.append(np.full(n, i))
+        pl_type.append(int(rng.integers(0, 4)))
+    pos = np.concatenate(pos).astype(np.float32)
+    M = pos.shape[0]
+    return {
+        'map_point': {'num_nodes': M, 'position': torch.from_numpy(pos),
+                      'orientation': torch.from_numpy(np.concatenate(ori).astype(np.float32)),
+                      'type': torch.from_numpy(np.concatenate(typ).astype(np.uint8))},
+        'map_polygon': {'num_nodes': n_polygons, 'type': torch.from_numpy(np.array(pl_type, dtype=np.uint8)),
+                        'light_type': torch.full((n_polygons,), 3, dtype=torch.uint8)},
+        ('map_point', 'to', 'map_polygon'): {
+            'edge_index': torch.stack([torch.arange(M), torch.from_numpy(np.concatenate(pl).astype(np.int64))])},
+    }

@@ -187,3 +187,54 @@ def fetch_enterings(tok: Dict[str, torch.Tensor], pt_pos: torch.Tensor, av_index
     return {'grid_token_idx': grid, 'grid_offset_xy': off, 'heading_token_idx': encode_heading(rel, angle_interval),
             'pos_xy': pos_xy, 'heading_theta': wrap_angle(rel), 'sort_indices': sort_indices,
             'inrange_mask': torch.stack(in_l, 1), 'bos_mask': torch.stack(bos_l, 1), 'pt_grid_token_idx': pt_grid}
+
+
+# ---- map side of the preparation ----------------------------------------------------------------------------------------
+def match_token_map(traj_pos, traj_theta, pl_idx_list, side, sample_pt) -> Dict[str, torch.Tensor]:
+    """`InfGen.match_token_map` /root/reference/infgen/model/infgen.py:918-984 (noise=False): every 5 m map polyline
+    (three points, `_tokenize_map` preprocess.py:118-130) is moved into the frame of its first point (:927-935), matched to
+    the vocabulary entry with the smallest summed squared distance over the three sample points (:936-937), and the
+    [polygon, side, slot] mask of the scene is built from the token counts per polygon and side (:955-971).
+    traj_pos [P,3,2] (any float dtype), traj_theta [P], pl_idx_list [P], side [P] uint8, sample_pt [V,3,2]."""
+    traj_pos = torch.as_tensor(traj_pos).to(torch.float)
+    traj_theta = torch.as_tensor(traj_theta).to(torch.float)
+    pl_idx_list = torch.as_tensor(pl_idx_list)
+    side = torch.as_tensor(side)
+    sample_pt = torch.as_tensor(sample_pt).to(torch.float)
+    P = traj_pos.shape[0]
+    cos, sin = traj_theta.cos(), traj_theta.sin()
+    rot = traj_theta.new_zeros(P, 2, 2)
+    rot[:, 0, 0], rot[:, 0, 1], rot[:, 1, 0], rot[:, 1, 1] = cos, -sin, sin, cos
+    local = torch.bmm(traj_pos - traj_pos[:, 0:1], rot)
+    distance = torch.sum((sample_pt[None] - local.unsqueeze(1)) ** 2, dim=(-2, -1))
+    token_idx = torch.argmin(distance, dim=1)
+    polygons = pl_idx_list.unique()
+    token2pl = torch.stack([torch.arange(P), pl_idx_list.long()])
+    counts = torch.stack([torch.stack([((pl_idx_list == pl) & (side == k)).sum() for k in range(3)]) for pl in polygons]).float()
+    longest = int(counts.max().item())
+    traj_mask = torch.arange(longest)[None, None, :] < counts[:, :, None]
+    position = torch.cat([traj_pos[:, 0, :], torch.zeros(P, 1)], dim=-1)
+    return {'token_idx': token_idx, 'position': position, 'orientation': traj_theta.clone(), 'height': position[:, -1],
+            'traj_mask': traj_mask, 'token2pl': token2pl, 'distance': distance}
+
+
+def sample_pt_pred(traj_mask: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """`InfGen.sample_pt_pred` /root/reference/infgen/model/infgen.py:986-1006: a third of the slots 1.. of every
+    (polygon, side) row is drawn without replacement from ONE global permutation (torch.randperm - the same torch RNG
+    stream as the reference when seeded alike), masked out of the valid set, and the slot before each masked slot
+    predicts it."""
+    n_pl, n_side, L = traj_mask.shape
+    raw = torch.arange(1, L).repeat(n_pl, n_side, 1)
+    k = (L - 1) // 3
+    masked = raw.view(-1)[torch.randperm(raw.numel())[:n_pl * n_side * k].reshape(n_pl, n_side, k)]
+    masked = torch.sort(masked, -1)[0]
+    valid = traj_mask.clone()
+    valid.scatter_(2, masked, False)
+    pred = traj_mask.clone()
+    pred.scatter_(2, masked, False)
+    keep = torch.ones_like(pred)
+    keep.scatter_(2, masked - 1, False)
+    pred.masked_fill_(keep, False)
+    pred = pred * torch.roll(traj_mask, shifts=-1, dims=2)
+    target = torch.roll(pred, shifts=1, dims=2)
+    return {'pt_valid_mask': valid[traj_mask], 'pt_pred_mask': pred[traj_mask], 'pt_target_mask': target[traj_mask]}

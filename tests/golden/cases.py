@@ -78,6 +78,13 @@ def build_prep_case(name: str):
     return raw, scene['pt_token']['position'].clone(), cfg, spec
 
 
+# --- row f2, map side: InfGen.match_token_map / sample_pt_pred over a tokenized synthetic raw map --------------------------------
+MAPMATCH_CASES = {
+    'p24': dict(seed=1, polygons=24, mask_seed=7),
+    'p96': dict(seed=2, polygons=96, mask_seed=8),
+}
+
+
 # --- rows a15 / f4: teacher-forced InfGenAgentDecoder.forward, motion branch -------------------------------------------------
 FWD_CASES = {
     'a24': dict(scene_seed=12, agents=24, map_tokens=768, ragged=0.6, ego=3, weight_seed=1),

@@ -133,3 +133,71 @@ def test_prepare_scene_rejects_bad_arguments(prep):
     raw['av_idx'] = torch.tensor([99])
     with pytest.raises(_capi.InfgenError):
         run_gpu(prep, raw, pt_pos)
+
+
+# ---- map side: infgen_match_map_tokens / B200ScenePrep.match_token_map ------------------------------------------------------
+from tests.golden.cases import MAPMATCH_CASES                      # noqa: E402
+
+
+def _map_case(name):
+    gold = np.load(os.path.join(GOLD, f'case_mapmatch_{name}.npz'))
+    data = {'map_save': {'traj_pos': torch.from_numpy(gold['in_traj_pos']), 'traj_theta': torch.from_numpy(gold['in_traj_theta']),
+                         'pl_idx_list': torch.from_numpy(gold['in_pl_idx_list'])},
+            'pt_token': {'side': torch.from_numpy(gold['in_side']), 'num_nodes': int(gold['in_traj_pos'].shape[0])}}
+    return gold, data
+
+
+@pytest.mark.parametrize('name', list(MAPMATCH_CASES))
+def test_map_match_matches_reference_golden(prep, name):
+    """Vocabulary match of every 5 m map polyline, [polygon, side, slot] mask, positions / orientations and the
+    pt_token -> polygon edges against the unmodified reference method; the prediction masks under the reference's seed."""
+    from oracle.scene_prep_oracle import match_token_map
+    from tests.test_oracle_prep_vs_golden import _sample_pt
+    gold, data = _map_case(name)
+    data = prep.match_token_map(data, want_distance=True)
+    pt = data['pt_token']
+    got, want = pt['token_idx'].numpy(), gold['token_idx']
+    # bit-exact, except where the argmin is decided by less than 1e-5 m^2 (device cosf / sinf differ from libm in the last ulp)
+    bad = np.nonzero(got != want)[0]
+    if len(bad):
+        dist = match_token_map(gold['in_traj_pos'], gold['in_traj_theta'], gold['in_pl_idx_list'], gold['in_side'],
+                               _sample_pt())['distance'].numpy()
+        for t in bad:
+            assert abs(dist[t, got[t]] - dist[t, want[t]]) < 1e-5, (t, got[t], want[t])
+    assert len(bad) <= max(1, len(want) // 200)
+    assert np.array_equal(pt['traj_mask'].numpy(), gold['traj_mask'])
+    assert np.array_equal(data[('pt_token', 'to', 'map_polygon')]['edge_index'].numpy(), gold['token2pl'])
+    for k in ('position', 'orientation', 'height'):
+        assert np.array_equal(pt[k].numpy(), gold[k]), k
+    assert pt['token_idx'].dtype == torch.long and pt['traj_mask'].dtype == torch.bool
+    torch.manual_seed(MAPMATCH_CASES[name]['mask_seed'])
+    data = prep.sample_pt_pred(data)
+    for k in ('pt_valid_mask', 'pt_pred_mask', 'pt_target_mask'):
+        assert np.array_equal(pt[k].numpy(), gold[k]), k
+
+
+def test_map_match_full_size_properties(prep):
+    """8,192 polylines against the 1,024-entry vocabulary: every vocabulary entry placed anywhere in the plane at any
+    heading is matched to itself (distance ~ 0), and a scene's counts add up to its polylines."""
+    from tests.test_oracle_prep_vs_golden import _sample_pt
+    sp = _sample_pt()
+    rng = np.random.default_rng(5)
+    P = 8192
+    ids = rng.integers(0, sp.shape[0], size=P)
+    theta = rng.uniform(-np.pi, np.pi, size=P).astype(np.float32)
+    origin = rng.uniform(-150.0, 150.0, size=(P, 1, 2)).astype(np.float32)
+    c, s = np.cos(theta)[:, None], np.sin(theta)[:, None]
+    loc = sp.numpy()[ids]                                          # [P,3,2] in the token frame; world = loc @ R(theta)^T + o
+    world = np.stack([loc[..., 0] * c - loc[..., 1] * s, loc[..., 0] * s + loc[..., 1] * c], -1) + origin
+    world = world - world[:, :1] + origin                          # first point at the origin of the frame
+    pl = np.sort(rng.integers(0, 300, size=P))
+    side = rng.integers(0, 3, size=P).astype(np.uint8)
+    data = {'map_save': {'traj_pos': torch.from_numpy(world), 'traj_theta': torch.from_numpy(theta),
+                         'pl_idx_list': torch.from_numpy(pl.astype(np.float32))},
+            'pt_token': {'side': torch.from_numpy(side), 'num_nodes': P}}
+    data = prep.match_token_map(data, want_distance=True)
+    pt = data['pt_token']
+    d_self = ((sp.numpy()[pt['token_idx'].numpy()] - sp.numpy()[ids]) ** 2).sum((-2, -1))
+    assert float(pt['match_distance'].max()) < 1e-3            # found an entry as close as the planted one ...
+    assert float(d_self.max()) < 1e-2                          # ... which is the planted one or a duplicate of it
+    assert int(pt['traj_mask'].sum()) == P

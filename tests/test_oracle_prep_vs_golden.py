@@ -32,3 +32,29 @@ def test_prep_oracle_matches_reference(name):
         assert np.array_equal(got[k].numpy(), gold[k]), k
     for k in FLT_KEYS:                                   # same torch ops on the same CPU: 1e-6 abs covers BLAS differences
         np.testing.assert_allclose(got[k].numpy(), gold[k], rtol=0, atol=1e-5, err_msg=k)
+
+
+# ---- map side: match_token_map / sample_pt_pred -----------------------------------------------------------------------------
+from tests.golden.cases import MAPMATCH_CASES                      # noqa: E402
+
+
+def _sample_pt():
+    from infgen_b200.map_encoder import load_map_vocab
+    traj_src = load_map_vocab()
+    return traj_src[:, torch.linspace(0, traj_src.shape[1] - 1, steps=3).long()]       # init_map_token, infgen.py:203-211
+
+
+@pytest.mark.parametrize('name', list(MAPMATCH_CASES))
+def test_map_match_oracle_matches_reference(name):
+    from oracle.scene_prep_oracle import match_token_map, sample_pt_pred
+    gold = np.load(os.path.join(GOLD, f'case_mapmatch_{name}.npz'))
+    got = match_token_map(gold['in_traj_pos'], gold['in_traj_theta'], gold['in_pl_idx_list'], gold['in_side'], _sample_pt())
+    for k in ('token_idx', 'traj_mask', 'token2pl'):
+        assert np.array_equal(got[k].numpy(), gold[k]), k
+    for k in ('position', 'orientation', 'height'):
+        assert np.array_equal(got[k].numpy(), gold[k]), k
+    torch.manual_seed(MAPMATCH_CASES[name]['mask_seed'])
+    masks = sample_pt_pred(got['traj_mask'])
+    for k in ('pt_valid_mask', 'pt_pred_mask', 'pt_target_mask'):
+        assert np.array_equal(masks[k].numpy(), gold[k]), k
+    assert masks['pt_pred_mask'].sum() > 0 and (masks['pt_pred_mask'].sum() == masks['pt_target_mask'].sum())
