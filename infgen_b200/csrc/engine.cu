@@ -160,6 +160,8 @@ struct infgen_engine {
     bool ins_ride = false;                              // seed queries carry the last appended row (one scene per tile)
     cudaStream_t side_stream2 = nullptr;                // second concurrent branch (occupancy node of the next insertion pass)
     cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr;
+    cudaStream_t side_stream3 = nullptr;                // third (heading-stack K|V rows of the row appended one pass earlier)
+    cudaEvent_t ev_fork3 = nullptr, ev_join3 = nullptr;
     bool early_edges = false;                           // motion-only engines build the next column's edges early
     float *blob = nullptr;
     float *cs_blob = nullptr;                           // cluster-sliced AttentionLayer chunks (layer.cuh)
@@ -890,6 +892,24 @@ static int side2_join(infgen_engine *e) {
     CK(cudaStreamWaitEvent(e->stream, e->ev_join2, 0));
     return 0;
 }
+template <typename Fn>
+static int side3_fork(infgen_engine *e, Fn fn) {
+    if (e->profile) return fn();
+    cudaStream_t main = e->stream;
+    CK(cudaEventRecord(e->ev_fork3, main));
+    CK(cudaStreamWaitEvent(e->side_stream3, e->ev_fork3, 0));
+    e->stream = e->side_stream3;
+    const int rc = fn();
+    e->stream = main;
+    RET(rc);
+    CK(cudaEventRecord(e->ev_join3, e->side_stream3));
+    return 0;
+}
+static int side3_join(infgen_engine *e) {
+    if (e->profile) return 0;
+    CK(cudaStreamWaitEvent(e->stream, e->ev_join3, 0));
+    return 0;
+}
 
 // Inputs of the next seed query that do not come out of attention layers: the occupancy node (grid occupancy ->
 // seed_agent_occ_embed -> K|V of the three occ2sa layers, :1850-1859) and the query row's input feature.  They only depend on
@@ -1031,9 +1051,9 @@ static int enqueue_heading_stage(infgen_engine *e) {
             k_seed_records<<<ns, NT, 0, e->stream>>>(s, q);
         }
         CKL(); count_launch(e);
-        RET(enqueue_seed_prepare(e));
-        return e->ins_ride ? enqueue_edgeless(e, nullptr, x_ha, false, 2) : 0;
+        return enqueue_seed_prepare(e);
     }));
+    if (e->ins_ride) RET(side3_fork(e, [&]() -> int { return enqueue_edgeless(e, nullptr, x_ha, false, 2); }));
     // the new row's edges and their relative embeddings only need its pose: on the side stream, concurrently with its
     // categorical / column embedding (two chains of ~50 us each per inserted agent)
     RET(side_fork(e, [&]() -> int {
@@ -1063,7 +1083,7 @@ static int enqueue_heading_stage(infgen_engine *e) {
     CKL(); count_launch(e);
     RET(enqueue_embed_rows(e, q.row_lo));       // feature of the new row with the dummy heading
     RET(side_join(e));
-    RET(side2_join(e));
+    if (e->ins_ride) RET(side3_join(e));
     {   // the new rows through 3 x {pt2a, a2a} with their 10 m neighbourhoods
         LayerArgs la;
         memset(&la, 0, sizeof(la));
@@ -1115,7 +1135,8 @@ static int enqueue_heading_stage(infgen_engine *e) {
         // next heading stage of the iteration (prev_rows above; the next iteration projects every row again).
         RET(side_fork(e, seed_edge_embedding));
         RET(enqueue_embed_rows(e, q.row_lo, x_sa, x_ha));
-        return side_join(e);
+        RET(side_join(e));
+        return side2_join(e);                    // (records + occupancy node of the next pass)
     }
     // packed query rows: both edge-less chains of the new rows here, on two streams
     RET(enqueue_embed_rows(e, q.row_lo, x_sa, x_ha));
@@ -1124,7 +1145,8 @@ static int enqueue_heading_stage(infgen_engine *e) {
         return enqueue_edgeless(e, q.row_lo, x_ha, false, 1);
     }));
     RET(enqueue_edgeless(e, q.row_lo, x_sa, true, 1));
-    return side_join(e);
+    RET(side_join(e));
+    return side2_join(e);
 }
 
 // host-driven loop (plain launches)
@@ -1414,6 +1436,9 @@ int32_t infgen_create(const infgen_config *cfg, const float *weights, int64_t n_
     CK(cudaStreamCreateWithFlags(&e->side_stream2, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&e->ev_fork2, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&e->ev_join2, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&e->side_stream3, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&e->ev_fork3, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->ev_join3, cudaEventDisableTiming));
     e->early_edges = cfg->disable_insertion != 0 && !getenv("INFGEN_NO_EARLY_EDGES");   // (debug tools compare per-iteration edges)
     CK(cudaMalloc(&e->blob, (size_t)g_total * sizeof(float)));
     CK(cudaMemcpyAsync(e->blob, weights, (size_t)g_total * sizeof(float), cudaMemcpyHostToDevice, e->stream));
@@ -1517,6 +1542,9 @@ int32_t infgen_destroy(infgen_engine *e) {
     if (e->side_stream2) cudaStreamDestroy(e->side_stream2);
     if (e->ev_fork2) cudaEventDestroy(e->ev_fork2);
     if (e->ev_join2) cudaEventDestroy(e->ev_join2);
+    if (e->side_stream3) cudaStreamDestroy(e->side_stream3);
+    if (e->ev_fork3) cudaEventDestroy(e->ev_fork3);
+    if (e->ev_join3) cudaEventDestroy(e->ev_join3);
     delete e;
     return 0;
 }
