@@ -819,6 +819,7 @@ static int enqueue_edgeless(infgen_engine *e, const int *row_lo, float *x, bool 
     la.rows = subset == 1 ? new_rows(e) : (subset == 2 ? prev_rows(e) : scene_rows(e));
     if (!new_only) la.rows.row_lo = row_lo;
     la.x = x; la.ring = RING; la.col_ptr = e->st.col;
+    la.no_store = 1;                                    // the chain's output rows are never used: x may be a shared input
     const size_t kvl = (size_t)e->R * 256;
     int n = 0;
     if (seed_stack) {                                   // 3 x {occ2sa, pt2sa, a2sa}: K|V of the a2sa layers
@@ -944,11 +945,15 @@ static int enqueue_insertion_begin(infgen_engine *e) {
     // embeddings of the map -> seed and agent -> seed edges (the seed pose is the ego pose for every pass of the iteration;
     // rows appended by a pass add their own edge) and the heading stack (motion layers 0..2 without edges: K|V of a2a for
     // the heading stage of appended rows)
-    {
+    // The cluster kernel keeps the residual rows in shared memory and (no_store) never writes them back, so both chains
+    // read x itself; the row-tile kernels of large batches update their residual stream in global memory and get copies.
+    const bool chain_copies = (R + 7) / 8 > MAX_CLUSTERS && e->layer_path != 1;
+    float *x_in_sa = chain_copies ? fbuf(e, "x_sa") : fbuf(e, "x"), *x_in_ha = chain_copies ? fbuf(e, "x_ha") : fbuf(e, "x");
+    if (chain_copies) {
         ProfScope ps(e, KC_INSERT);
         k_copy_new_rows2<<<ns, 128, 0, st>>>(s, nullptr, fbuf(e, "x"), fbuf(e, "x_sa"), fbuf(e, "x_ha"));
+        CKL(); count_launch(e);
     }
-    CKL(); count_launch(e);
     RET(side2_fork(e, [&]() -> int { return enqueue_seed_prepare(e); }));
     RET(side_fork(e, [&]() -> int {
         FourierArgs fj[2];
@@ -958,9 +963,9 @@ static int enqueue_insertion_begin(infgen_engine *e) {
         fj[1].normalize = 1; fj[1].dim = 3; fj[1].n_slots = ns * q.as_stride; fj[1].cnt = q.as_cnt; fj[1].stride = q.as_stride;
         fj[1].raw = q.as_raw; fj[1].w = e->f_as; fj[1].out = fbuf(e, "rhat_as");
         RET(launch_fourier(e, fj, 2, KC_INS_FOURIER));
-        return enqueue_edgeless(e, nullptr, fbuf(e, "x_ha"), false);
+        return enqueue_edgeless(e, nullptr, x_in_ha, false);
     }));
-    RET(enqueue_edgeless(e, nullptr, fbuf(e, "x_sa"), true));
+    RET(enqueue_edgeless(e, nullptr, x_in_sa, true));
     RET(side_join(e));
     return side2_join(e);
 }

@@ -108,6 +108,7 @@ struct LayerArgs {
     const float *x2;
     const int *ride_row;
     int ride_cap;
+    int no_store;              // 1: x is read only (launches that exist for the K|V rows of their `pre` projections)
     long long *tstamp;         // optional [256] clock64 stamps of CTA 0 (debug: phase breakdown)
 };
 
@@ -719,7 +720,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_layer(cons
             const float4 x2 = add4(ld4(sx + m * LD1 + 4 * lane), f);
             st4(sx + m * LD1 + 4 * lane, x2);
             if ((m & (CL - 1)) == c && active(m) && s_alt[m] < 0) { // row m is stored by CTA m % 8
-                if (last) st4(a.x + (size_t)r * 128 + 4 * lane, x2);
+                if (last && !a.no_store) st4(a.x + (size_t)r * 128 + 4 * lane, x2);
                 if (A.trace_out) st4(A.trace_out + (size_t)r * 128 + 4 * lane, x2);
             }
         }
