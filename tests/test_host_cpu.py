@@ -62,3 +62,43 @@ def test_output_dict_matches_oracle_ragged_scene():
     """Late-entering / early-exiting tracks: rows invalid at the current step are filtered (agent_decoder.py:1609-1628),
     the ego index shifts, the history masks differ from all-true."""
     _check(*_rollout(0.5))
+
+
+def test_batch_assembly_equals_per_scene_assembly_with_insertion_records():
+    """The batch-wide output assembly (tables over the whole row space, one index_put_ per dense insertion tensor, recycled
+    storage) returns exactly what the per-scene assembly returns - for two consecutive calls that reuse the pooled
+    storage with different records (the first call's records must be gone from the second call's tensors)."""
+    from infgen_b200.host import DenseBatchPool, _assemble_outputs_per_scene
+    cfg = DecoderConfig(motion_beam_size=1, insert_beam_size=3)
+    datas = [make_scene(40 + i, num_agents=6 + i, num_map_tokens=256, num_steps=91, ragged=0.3 * (i % 2), ego_index=i % 3, cfg=cfg)
+             for i in range(4)]
+    shs = [prepare_scene(d, d['map_enc'], cfg) for d in datas]
+    hb = HostBatch(shs, cfg, list(range(4)), pin=False)
+    rng = np.random.default_rng(3)
+    for name in ('out_pos', 'out_head', 'out_pred_traj', 'out_pred_head', 'out_hist_traj', 'out_hist_head', 'out_rec_pos_prob',
+                 'out_rec_agent_occ', 'out_rec_pt_occ', 'out_rec_occ_gt', 'out_rec_state_prob', 'out_pred_shape'):
+        t = getattr(hb, name)
+        t.copy_(torch.from_numpy(rng.standard_normal(tuple(t.shape)).astype(np.float32)))
+    hb.out_pred_state.copy_(torch.from_numpy(rng.integers(0, 4, size=tuple(hb.out_pred_state.shape)).astype(np.float32)))
+    hb.out_next_token.copy_(torch.from_numpy(rng.integers(-2, 2048, size=tuple(hb.out_next_token.shape)).astype(np.int32)))
+    hb.out_next_state.copy_(torch.from_numpy(rng.integers(0, 4, size=tuple(hb.out_next_state.shape)).astype(np.int32)))
+    hb.out_pred_type.copy_(torch.from_numpy(rng.integers(0, 3, size=tuple(hb.out_pred_type.shape)).astype(np.int32)))
+    pool = DenseBatchPool(depth=1)                       # depth 1: every call recycles the storage of the call before
+    for call in range(3):
+        for b, sh in enumerate(shs):
+            k = int(rng.integers(0, 12)) if not (call == 1 and b == 2) else 0      # one scene without insertions
+            hb.out_n_rows[b] = sh.n_rows + k
+            pairs = rng.permutation(10 * (hb.S - 1))[:k]
+            meta = np.stack([pairs // 10 + 1, pairs % 10 + 1], -1).astype(np.int32)           # [iteration, slot]
+            hb.out_rec_meta[b * hb.cap + sh.n_rows: b * hb.cap + sh.n_rows + k] = torch.from_numpy(meta)
+        pool.next_generation()
+        got = assemble_outputs(hb, shs, cfg, pool)
+        want = _assemble_outputs_per_scene(hb, shs, cfg, None)
+        for b, (x, y) in enumerate(zip(got, want)):
+            assert set(x) == set(y)
+            for k_, v in y.items():
+                if isinstance(v, torch.Tensor):
+                    assert x[k_].dtype == v.dtype and tuple(x[k_].shape) == tuple(v.shape), (call, b, k_)
+                    assert torch.equal(x[k_], v), (call, b, k_)
+                else:
+                    assert x[k_] == v, (call, b, k_)
