@@ -16,7 +16,7 @@ import torch
 from . import _capi
 from .config import DecoderConfig, HIDDEN, NUM_LAYERS, TOKEN_SIZE
 from .grid import PositionGrid
-from .host import DenseBatchPool, DenseRecordPool, HostBatch, SceneHost, assemble_outputs, prepare_scene
+from .host import DensePools, HostBatch, SceneHost, assemble_outputs, prepare_scene
 from .weights import pack_state_dict
 
 
@@ -81,7 +81,7 @@ class B200AgentDecoder:
         self._host_cache: Optional[HostBatch] = None
         # dense insertion tensors of the output dicts are recycled every `depth` calls (host.DenseRecordPool); None = fresh
         # tensors per call
-        self.dense_pool: Optional[DenseBatchPool] = DenseBatchPool(depth=2)
+        self.dense_pool: Optional[DensePools] = DensePools(depth=2)
 
     # ---- construction helpers ---------------------------------------------------------------------------------
     @classmethod

@@ -962,11 +962,12 @@ static int enqueue_insertion_begin(infgen_engine *e) {
         fj[0].raw = q.ps_raw; fj[0].w = e->f_ps; fj[0].out = fbuf(e, "rhat_ps");
         fj[1].normalize = 1; fj[1].dim = 3; fj[1].n_slots = ns * q.as_stride; fj[1].cnt = q.as_cnt; fj[1].stride = q.as_stride;
         fj[1].raw = q.as_raw; fj[1].w = e->f_as; fj[1].out = fbuf(e, "rhat_as");
-        RET(launch_fourier(e, fj, 2, KC_INS_FOURIER));
-        return enqueue_edgeless(e, nullptr, x_in_ha, false);
+        return launch_fourier(e, fj, 2, KC_INS_FOURIER);
     }));
+    RET(side3_fork(e, [&]() -> int { return enqueue_edgeless(e, nullptr, x_in_ha, false); }));
     RET(enqueue_edgeless(e, nullptr, x_in_sa, true));
     RET(side_join(e));
+    RET(side3_join(e));
     return side2_join(e);
 }
 

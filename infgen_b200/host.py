@@ -449,12 +449,28 @@ class DenseBatchPool:
         return ent
 
 
+class DensePools:
+    """Both pools of a decoder: per-scene storage for small calls, batch-wide storage from BATCH_MIN scenes on."""
+    BATCH_MIN = 4
+
+    def __init__(self, depth: int = 2):
+        self.scene, self.batch = DenseRecordPool(depth), DenseBatchPool(depth)
+
+    def next_generation(self):
+        self.scene.next_generation()
+        self.batch.next_generation()
+
+
 def assemble_outputs(batch: HostBatch, scenes: Sequence[SceneHost], cfg: DecoderConfig, pool=None) -> List[Dict]:
     """agent_decoder.py:2303-2389: the per-scene output dicts (keys / dtypes / shapes of the reference) of a whole batch.
     Everything that has the same form for every row of the row space is computed ONCE for the batch - the trajectory /
     heading / state tables, the validity mask, the int64 token tables, the dense insertion tensors - and the per-scene dict
     entries are views of those batch arrays (a per-scene loop of ~40 small numpy / torch calls was a quarter of the
     end-to-end time of a 32-scene call).  Scenes whose horizons differ fall back to the per-scene assembly."""
+    if isinstance(pool, DensePools):
+        # a handful of scenes: the per-scene numpy assembly is quicker than the batch-wide torch calls (whose fixed cost
+        # - thread-pool wake-ups of index_put_ / index_select - is ~2 ms per call)
+        pool = pool.batch if len(scenes) >= DensePools.BATCH_MIN else pool.scene
     if not isinstance(pool, (DenseBatchPool, type(None))) or any(s.n_rec != scenes[0].n_rec or s.n_iters != scenes[0].n_iters
                                                                for s in scenes):
         return _assemble_outputs_per_scene(batch, scenes, cfg, pool if isinstance(pool, DenseRecordPool) else None)
