@@ -399,6 +399,9 @@ def run_ours(args, rank, world, local_rank):
     import numpy as np
     import torch
     import torch.distributed as dist
+    # torchrun pins OMP_NUM_THREADS to 1 per rank; the host side of the public call (output assembly: index_put_ over the
+    # insertion records of a batch) uses the rank's share of the host cores
+    torch.set_num_threads(max(1, min(16, (os.cpu_count() or 1) // max(world, 1))))
     from infgen_b200.weights import make_state_dict
     from infgen_b200.agent_decoder import B200AgentDecoder
     from infgen_b200.host import prepare_scene, HostBatch, DeviceBatch
