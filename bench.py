@@ -373,25 +373,46 @@ def ncu_traffic(kernel):
     return None
 
 
-def timed_device_rollouts(dec, db, hosts, steps, warmup, stream, flush, barrier):
-    """load + rollout + read with device-resident inputs / results, CUDA events on the engine stream."""
+def timed_device_rollouts(runs, steps, warmup, stream, flush, barrier):
+    """load + rollout + read with device-resident inputs / results.  runs: [(decoder, DeviceBatch, hosts, stream)] - one
+    entry per engine of the decoder's group (several engines roll their shares of a batch out concurrently, each on its own
+    stream).  Timed with CUDA events on `stream`: the engine streams wait for the start event and `stream` waits for an
+    event behind every engine's last copy before the end event is recorded."""
     import torch
+
+    def one_step():
+        # every engine's rollout is enqueued before the first read (infgen_read waits for the row counts of its engine: the
+        # insertion records that travel depend on them)
+        for d, db, hosts, _ in runs:
+            d.load(db, hosts); d.rollout()
+        for d, _, _, _ in runs:
+            d.read()
+
     with torch.cuda.stream(stream):
         for _ in range(max(3, warmup)):
-            dec.load(db, hosts); dec.rollout(); dec.read()
+            one_step()
         barrier()
-        l0 = dec.kernel_launches()
+        l0 = sum(d.kernel_launches() for d, _, _, _ in runs)
         evs = []
         for _ in range(steps):
             flush.fill_(1)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            dec.load(db, hosts); dec.rollout(); dec.read()
+            for _, _, _, st in runs:
+                if st is not stream:
+                    st.wait_event(e0)
+            one_step()
+            for _, _, _, st in runs:
+                if st is not stream:
+                    done = torch.cuda.Event()
+                    done.record(st)
+                    stream.wait_event(done)
             e1.record(stream)
             evs.append((e0, e1))
         barrier()
-        dec.synchronize()                                 # surfaces device-side errors of the device-resident rollouts
-        launches = dec.kernel_launches() - l0
+        for d, _, _, _ in runs:
+            d.synchronize()                               # surfaces device-side errors of the device-resident rollouts
+        launches = sum(d.kernel_launches() for d, _, _, _ in runs) - l0
     return [a.elapsed_time(b) for a, b in evs], launches
 
 
@@ -434,18 +455,33 @@ def run_ours(args, rank, world, local_rank):
         # the public call first: it also settles the row capacity (the insertion stage may need capacity reruns)
         for _ in range(2):
             outs = dec.inference_batch(scn, mps, scene_ids=ids)
-        hosts = list(dec._scenes)
-        cap = dec._batch.cap
-        hb = HostBatch(hosts, dec_cfg, scene_ids=ids, row_capacity=cap)
-        dec.set_stream(stream.cuda_stream)
-        with torch.cuda.stream(stream):
-            db = DeviceBatch(hb, dev)
+        # the engines of the call (a batch of more than `scenes_per_engine` scenes is dealt to several, each with its own
+        # stream and iteration graph) and the scenes each one served
+        groups = dec._groups or [(dec, list(range(len(scn))))]
+        runs, hosts, hbs = [], [], []
+        for gi, (d, pos) in enumerate(groups):
+            hosts_g = list(d._scenes)
+            hb = HostBatch(hosts_g, dec_cfg, scene_ids=[ids[i] for i in pos], row_capacity=d._batch.cap)
+            st = stream if gi == 0 else torch.cuda.Stream(device=dev)
+            d.set_stream(st.cuda_stream)
+            with torch.cuda.stream(st):
+                db = DeviceBatch(hb, dev)
+            runs.append((d, db, hosts_g, st))
+            hosts += hosts_g
+            hbs.append(hb)
+        torch.cuda.synchronize(dev)
         sampler = ClockSampler(local_rank) if sampler_rank0 and rank == 0 else None
-        step_ms, launches = timed_device_rollouts(dec, db, hosts, steps, warmup, stream, flush, barrier)
+        step_ms, launches = timed_device_rollouts(runs, steps, warmup, stream, flush, barrier)
         clocks = sampler.stop() if sampler else None
-        dec.set_stream(None)
-        res = {'dec': dec, 'hb': hb, 'hosts': hosts, 'outs': outs, 'step_ms': step_ms, 'launches': launches,
-               'clocks': clocks, 'cap': cap}
+        for d, _, _, _ in runs:
+            d.set_stream(None)
+        # (the kernel profile of the roofline leg replays the WHOLE batch on engine 0: per-launch figures at the batch size
+        #  the configuration names, whatever the number of engines the timed rollouts were dealt to)
+        cap = max(d._batch.cap for d, _ in groups)
+        hb_all = hbs[0] if len(groups) == 1 else HostBatch(hosts, dec_cfg, scene_ids=ids, row_capacity=cap)
+        res = {'dec': dec, 'hb': hb_all, 'hosts': hosts, 'outs': outs, 'step_ms': step_ms,
+               'launches': launches, 'clocks': clocks, 'cap': cap, 'engines': len(groups),
+               'scenes_per_engine': [len(pos) for _, pos in groups]}
         if e2e:
             for _ in range(max(1, warmup - 2)):
                 dec.inference_batch(scn, mps, scene_ids=ids)
@@ -459,7 +495,8 @@ def run_ours(args, rank, world, local_rank):
                 ts.append(time.perf_counter() - t0)
             barrier()
             res['e2e_s'] = ts
-            res['h2d'], res['d2h'] = dec._batch.h2d_bytes(), dec._batch.d2h_bytes()
+            gs = dec._groups or [(dec, None)]
+            res['h2d'], res['d2h'] = sum(d._batch.h2d_bytes() for d, _ in gs), sum(d._batch.d2h_bytes() for d, _ in gs)
         return res
 
     m = measure(cfg, scenes, maps, my_ids, args.steps, args.warmup, sampler_rank0=True)
@@ -534,7 +571,9 @@ def run_ours(args, rank, world, local_rank):
             return {'workload': f"{wc['name']} on one GPU: {wc['text']}; inputs in HBM for `value`, public call for `e2e_value`",
                     'value': a / (statistics.mean(mb['step_ms']) * 1e-3), 'ms_per_step': statistics.mean(mb['step_ms']),
                     'e2e_value': a / statistics.mean(mb['e2e_s']), 'e2e_ms_per_step': statistics.mean(mb['e2e_s']) * 1e3,
-                    'unit': UNIT, 'row_capacity': mb['cap'], 'rows_final_mean': statistics.mean(rows_final),
+                    'unit': UNIT, 'engines': mb['engines'], 'scenes_per_engine': mb['scenes_per_engine'],
+                    'roofline_kernels_note': 'profiled replay of the whole batch on ONE engine' if mb['engines'] > 1 else None,
+                    'row_capacity': mb['cap'], 'rows_final_mean': statistics.mean(rows_final),
                     'rows_final_max': max(rows_final), 'launches_per_step': mb['launches'] / n_steps,
                     'workload_stats': st, 'roofline_kernels': kl}
 
@@ -675,8 +714,10 @@ def run_ours(args, rank, world, local_rank):
             'warmup': max(3, args.warmup), 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': config_block(w, world),
-            'impl_detail': {'parallelism': f'scenes sharded round-robin over {world} rank(s), one rollout stream per GPU, no '
-                            'data-path collective', 'l2': 'flushed between steps (256 MiB write)',
+            'impl_detail': {'parallelism': f'scenes sharded round-robin over {world} rank(s), no data-path collective; per GPU '
+                            f"{m['engines']} engine(s) x {m['scenes_per_engine']} scenes, one rollout stream and iteration graph "
+                            'per engine, rollouts concurrent (roofline_kernels: profiled replay of the whole per-GPU batch on '
+                            'one engine)', 'l2': 'flushed between steps (256 MiB write)',
                             'timed_region': 'infgen_load_scenes (device copies, map K/V caches) + prefill + S iterations '
                             '(one CUDA graph per iteration: insertion stage with WHILE / IF conditional nodes + motion '
                             'stage) + result copies', 'row_capacity': m['cap'],

@@ -25,10 +25,21 @@ class B200AgentDecoder:
                  use_cuda_graph: bool = True, trace: bool = False, seed: int = 2024,
                  vocab: Optional[Dict[str, torch.Tensor]] = None,
                  map_state_dict: Optional[Dict[str, torch.Tensor]] = None,
-                 map_traj_src: Optional[torch.Tensor] = None, teacher_forced_cols: int = 0):
+                 map_traj_src: Optional[torch.Tensor] = None, teacher_forced_cols: int = 0,
+                 scenes_per_engine: int = 8, max_engines: int = 6):
         """state_dict: `InfGenAgentDecoder.state_dict()` (None: an engine that only serves the map encoder).
         map_state_dict: `InfGenMapDecoder.state_dict()` - the engine then also runs the map encoder (`map_encode`) and
-        `inference` accepts `map_enc=None`: x_pt is produced and consumed in HBM."""
+        `inference` accepts `map_enc=None`: x_pt is produced and consumed in HBM.
+        scenes_per_engine / max_engines: `inference_batch` deals a batch of more than `scenes_per_engine` scenes to several
+        engines (own stream, own iteration graph each; created on first use) whose rollouts run concurrently - scenes are
+        independent, and a rollout with the insertion stage on is a chain of small launches that leaves most of the GPU
+        idle (measured on B200, 64-agent scenes: 8 scenes on one engine 78 ms, 2 x 8 on two engines 87 ms, 4 x 8 on four
+        101 ms against 119 ms for 32 scenes on one; more than ~6 concurrent engines is slower again).  0 = never split."""
+        self._init_args = dict(state_dict=state_dict, cfg=cfg, device=device, use_cuda_graph=use_cuda_graph, seed=seed,
+                               vocab=vocab, map_state_dict=map_state_dict, map_traj_src=map_traj_src)
+        self.scenes_per_engine, self.max_engines = scenes_per_engine, max_engines
+        self._replicas: List['B200AgentDecoder'] = []
+        self._groups = None                      # [(decoder, scene positions)] of the last split call
         self.cfg = cfg or DecoderConfig()
         self.lib = _capi.load()
         self.device = device
@@ -104,6 +115,9 @@ class B200AgentDecoder:
         for f in getattr(self, '_fwd', {}).values():
             f.close()
         self._fwd = {}
+        for r in getattr(self, '_replicas', []):
+            r.close()
+        self._replicas = []
         if getattr(self, '_h', None):
             self.lib.infgen_destroy(self._h)
             self._h = None
@@ -231,6 +245,10 @@ class B200AgentDecoder:
         if motion_only and not self.cfg.disable_insertion:
             raise ValueError('motion_only needs an engine built with disable_insertion=True')
         self._check_vocab(datas[0])
+        groups = self._split(len(datas))
+        self._groups = None
+        if groups is not None:
+            return self._inference_groups(groups, datas, map_encs, scene_ids)
         if map_encs is None:
             self.map_encode(datas, want_x=False)
             map_encs = [None] * len(datas)
@@ -258,6 +276,67 @@ class B200AgentDecoder:
         if self.dense_pool is not None:
             self.dense_pool.next_generation()
         return assemble_outputs(batch, scenes, self.cfg, self.dense_pool)
+
+    # ---- several engines for one batch ----------------------------------------------------------------------------
+    def _split(self, n: int):
+        """Scene positions per engine, or None for a single engine: balanced contiguous groups of at most
+        `scenes_per_engine` scenes (more per group once `max_engines` engines are in use)."""
+        if self.scenes_per_engine <= 0 or n <= self.scenes_per_engine or self.max_engines <= 1 or self.trace:
+            return None
+        if self.cfg.disable_insertion:                   # the motion stage alone is throughput-bound at batch: one row space
+            return None
+        k = min(self.max_engines, -(-n // self.scenes_per_engine))
+        bounds = [n * i // k for i in range(k + 1)]
+        return [list(range(bounds[i], bounds[i + 1])) for i in range(k)]
+
+    def engine(self, i: int) -> 'B200AgentDecoder':
+        """Engine i of the group (0 = this decoder); the others are replicas built from the same arguments on first use."""
+        while len(self._replicas) < i:
+            self._replicas.append(B200AgentDecoder(scenes_per_engine=0, **self._init_args))
+        return self if i == 0 else self._replicas[i - 1]
+
+    def _inference_groups(self, groups, datas, map_encs, scene_ids):
+        """Deal the scenes to the engines, enqueue every rollout (load + prefill + S graph replays are asynchronous to the
+        host), then read and assemble group by group: the output dicts of the first groups are built while the later
+        groups are still running."""
+        ids = list(scene_ids) if scene_ids is not None else list(range(len(datas)))
+        runs = []
+        for gi, pos in enumerate(groups):
+            d = self.engine(gi)
+            sub = [datas[i] for i in pos]
+            if map_encs is None:
+                d.map_encode(sub, want_x=False)
+                sub_maps = [None] * len(sub)
+            else:
+                sub_maps = [map_encs[i] for i in pos]
+            scenes = [prepare_scene(x, m, d.cfg) for x, m in zip(sub, sub_maps)]
+            gids = [ids[i] for i in pos]
+            batch = d._host_cache
+            if batch is not None and batch.fits(scenes):
+                batch.fill(scenes, gids)
+            else:
+                batch = d._host_cache = HostBatch(scenes, d.cfg, gids)
+            d.load(batch, scenes)
+            d.rollout()
+            runs.append((d, batch, scenes, gids))
+        outs = []
+        for d, batch, scenes, gids in runs:
+            while True:
+                try:
+                    d.read()
+                    break
+                except _capi.CapacityError:          # see inference_batch: rerun this group in a larger row space
+                    if not batch.insertion or batch.cap >= batch.max_rows:
+                        raise
+                    new_cap = min(max(2 * batch.cap, batch.cap + 64), (batch.max_rows + 3) // 4 * 4)
+                    batch = d._host_cache = HostBatch(scenes, d.cfg, gids, row_capacity=new_cap)
+                    d.load(batch, scenes)
+                    d.rollout()
+            if d.dense_pool is not None:
+                d.dense_pool.next_generation()
+            outs.extend(assemble_outputs(batch, scenes, d.cfg, d.dense_pool))
+        self._groups = [(d, pos) for (d, _, _, _), pos in zip(runs, groups)]
+        return outs
 
     def inference(self, data: Dict, map_enc: Optional[Dict], motion_only: bool = False) -> Dict:
         """`InfGenAgentDecoder.inference(data, map_enc)` (agent_decoder.py:1605-2389)."""

@@ -149,7 +149,7 @@ def test_batched_scenes_equal_single_scene_runs():
     sizes = [(5, 256, 0.0), (33, 384, 0.4), (64, 512, 0.2), (12, 300, 0.0), (48, 768, 0.5)] * 4
     scenes = [make_scene(100 + i, num_agents=a, num_map_tokens=p, num_steps=91, ragged=rg, ego_index=min(2, a - 1),
                          cfg=cfg) for i, (a, p, rg) in enumerate(sizes)]
-    dec = _make_decoder(sd, cfg)
+    dec = _make_decoder(sd, cfg, scenes_per_engine=0)
     outs = dec.inference_batch(scenes, [s['map_enc'] for s in scenes])
     assert dec._batch.R > 512, 'the batch must exceed 512 rows: that selects the 16-row tile of k_heads'
     for i in (0, 1, 2, 7, 19):
@@ -262,11 +262,11 @@ def test_insertion_packed_query_rows_equal_wide_mode(monkeypatch):
     scenes = [make_scene(60 + i, num_agents=8 + (i % 5), num_map_tokens=256 + 64 * (i % 3), num_steps=91, ragged=0.2,
                          ego_index=i % 3, cfg=cfg) for i in range(18)]
     maps = [s['map_enc'] for s in scenes]
-    dec = _make_decoder(sd, cfg, use_cuda_graph=True)
+    dec = _make_decoder(sd, cfg, use_cuda_graph=True, scenes_per_engine=0)           # one engine: 18 scenes in one row space
     packed = dec.inference_batch(scenes, maps, scene_ids=list(range(18)))
     dec.close()
     monkeypatch.setenv('INFGEN_SEED_WIDE', '1')
-    dec = _make_decoder(sd, cfg, use_cuda_graph=True)
+    dec = _make_decoder(sd, cfg, use_cuda_graph=True, scenes_per_engine=0)
     wide = dec.inference_batch(scenes, maps, scene_ids=list(range(18)))
     dec.close()
     inserted = 0
@@ -277,6 +277,38 @@ def test_insertion_packed_query_rows_equal_wide_mode(monkeypatch):
         for k in ('pos_a', 'head_a', 'pred_traj', 'pred_head', 'next_pos_rel_prob_seed'):
             _close(x[k].numpy(), y[k].numpy(), f'scene {b} {k}')
     assert inserted > 18
+
+
+def test_engine_groups_equal_single_engine():
+    """A batch dealt to several engines (own stream and iteration graph each, rollouts concurrent) == the same batch on one
+    engine: 19 scenes as 3 engines x 6-7 scenes against one row space of 19, insertion stage live, top-3 position and
+    top-5 motion sampling (the sampler is keyed by the scene id, not by the position in a batch); a second call reuses the
+    engines and their staging buffers."""
+    from infgen_b200.weights import make_state_dict
+    from infgen_b200.synth import make_scene
+    cfg = DecoderConfig(motion_beam_size=5, insert_beam_size=3, disable_insertion=False, debug_force_enter=True)
+    sd = make_state_dict(2)
+    scenes = [make_scene(80 + i, num_agents=8 + (i % 5), num_map_tokens=256 + 64 * (i % 3), num_steps=91, ragged=0.2,
+                         ego_index=i % 3, cfg=cfg) for i in range(19)]
+    maps = [s['map_enc'] for s in scenes]
+    ids = [100 + i for i in range(19)]
+    dec = _make_decoder(sd, cfg, use_cuda_graph=True, scenes_per_engine=0)
+    single = dec.inference_batch(scenes, maps, scene_ids=ids)
+    assert dec._groups is None
+    dec.close()
+    dec = _make_decoder(sd, cfg, use_cuda_graph=True, scenes_per_engine=7)
+    for call in range(2):
+        split = dec.inference_batch(scenes, maps, scene_ids=ids)
+        assert [len(pos) for _, pos in dec._groups] == [6, 6, 7] and len({id(d) for d, _ in dec._groups}) == 3
+        inserted = 0
+        for b, (x, y) in enumerate(zip(split, single)):
+            inserted += x['pos_a'].shape[0] - scenes[b]['agent']['token_pos'].shape[0]
+            for k in ('next_token_idx', 'next_state_idx', 'agent_id', 'pred_type'):
+                assert torch.equal(x[k], y[k]), (call, b, k)
+            for k in ('pos_a', 'head_a', 'pred_traj', 'pred_head', 'next_pos_rel_prob_seed'):
+                _close(x[k].numpy(), y[k].numpy(), f'call {call} scene {b} {k}')
+        assert inserted > 19
+    dec.close()
 
 
 def test_long_horizon_matches_oracle():

@@ -16,7 +16,8 @@ n_scenes = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 graph = bool(int(sys.argv[2])) if len(sys.argv) > 2 else False
 insertion = bool(int(sys.argv[3])) if len(sys.argv) > 3 else False
 cfg = DecoderConfig(motion_beam_size=5, insert_beam_size=10, disable_insertion=not insertion)
-dec = B200AgentDecoder(make_state_dict(0), cfg, use_cuda_graph=graph)
+# one engine whatever the batch size: the captures document the kernels at the batch size asked for
+dec = B200AgentDecoder(make_state_dict(0), cfg, use_cuda_graph=graph, scenes_per_engine=0)
 scenes = [make_scene(13 + i, num_agents=64, num_map_tokens=2048, num_steps=91, ragged=0.0, ego_index=5, cfg=cfg)
           for i in range(n_scenes)]
 # the second rollout is bracketed by cudaProfilerStart/Stop: run ncu with `--profile-from-start off` to capture exactly it
