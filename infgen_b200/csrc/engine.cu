@@ -1767,7 +1767,9 @@ int32_t infgen_load_scenes(infgen_engine *e, const infgen_scene_batch *b, int32_
         q.shape_rows = fbuf(e, "shape_rows");
         q.seed_feat = e->seed_feat; q.err = e->d_err;
         // query rows: one per tile (all warps share its edges) while every scene's cluster fits one wave, packed otherwise
-        q.seed_stride = (ns <= MAX_CLUSTERS || getenv("INFGEN_SEED_WIDE")) ? SEED_ROW_STRIDE : 1;
+        // (INFGEN_SEED_WIDE_MAX: experiments with the switch-over point; default = one wave of clusters)
+        const int wide_max = getenv("INFGEN_SEED_WIDE_MAX") ? atoi(getenv("INFGEN_SEED_WIDE_MAX")) : MAX_CLUSTERS;
+        q.seed_stride = (ns <= wide_max || getenv("INFGEN_SEED_WIDE")) ? SEED_ROW_STRIDE : 1;
         e->ins_ride = q.seed_stride == SEED_ROW_STRIDE && !getenv("INFGEN_NO_RIDE");
         s.ins_col = q.ins_col;
         RET(ensure_t(e, "hv_src", R, &s.hv_src));

@@ -16,7 +16,7 @@ cfg = DecoderConfig(motion_beam_size=5, insert_beam_size=10)
 sd = make_state_dict(0)
 datas = [make_scene(13 + i, num_agents=64, num_map_tokens=2048, num_steps=91, ragged=0.0, ego_index=5, cfg=cfg) for i in range(n)]
 scenes = [prepare_scene(d, d['map_enc'], cfg) for d in datas]
-for K in (4, 6, 8):
+for K in (2, 4):
     decs = [B200AgentDecoder(sd, cfg, seed=2024) for _ in range(K)]
     groups = [list(range(k * n // K, (k + 1) * n // K)) for k in range(K)]
     hbs = [HostBatch([scenes[i] for i in g], cfg, g, row_capacity=224) for g in groups]
