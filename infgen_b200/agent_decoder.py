@@ -26,17 +26,18 @@ class B200AgentDecoder:
                  vocab: Optional[Dict[str, torch.Tensor]] = None,
                  map_state_dict: Optional[Dict[str, torch.Tensor]] = None,
                  map_traj_src: Optional[torch.Tensor] = None, teacher_forced_cols: int = 0,
-                 scenes_per_engine: int = 8, max_engines: int = 4):
+                 scenes_per_engine: int = 2, max_engines: int = 4):
         """state_dict: `InfGenAgentDecoder.state_dict()` (None: an engine that only serves the map encoder).
         map_state_dict: `InfGenMapDecoder.state_dict()` - the engine then also runs the map encoder (`map_encode`) and
         `inference` accepts `map_enc=None`: x_pt is produced and consumed in HBM.
-        scenes_per_engine / max_engines: `inference_batch` deals a batch of more than `scenes_per_engine` scenes to several
-        engines (own stream, own iteration graph each; created on first use) whose rollouts run concurrently - scenes are
-        independent, and a rollout with the insertion stage on is a chain of small launches that leaves most of the GPU
-        idle (measured on B200, 64-agent scenes: 8 scenes on one engine 78 ms, 2 x 8 on two engines 87 ms, 4 x 8 on four
-        101 ms against 119 ms for 32 scenes on one).  Every engine drives four streams; with the default of 8 hardware
-        queues (CUDA_DEVICE_MAX_CONNECTIONS) a fifth engine makes the streams alias badly (32 scenes: 166 ms on 5-6 engines;
-        with 32 connections 6-8 engines run like 4), hence max_engines = 4.  scenes_per_engine = 0: never split."""
+        scenes_per_engine / max_engines: with the insertion stage on, `inference_batch` deals a batch of at least
+        2 * `scenes_per_engine` scenes to up to `max_engines` engines (own stream, own iteration graph each; created on first
+        use) whose rollouts run concurrently - scenes are independent, and such a rollout is a chain of small launches that
+        leaves most of the GPU idle.  Measured on B200 (64-agent scenes, ms per batch, engines x scenes): 16 iterations -
+        1x8 78, 4x2 75; 1x16 100, 2x8 87, 4x4 84; 1x32 119, 4x8 101; 300 iterations - 1x8 2,879, 2x4 2,731, 4x2 2,602.
+        Every engine drives four streams; with the default of 8 hardware queues (CUDA_DEVICE_MAX_CONNECTIONS) a fifth
+        engine makes the streams alias badly (32 scenes: 166 ms on 5-6 engines; with 32 connections 6-8 engines run like 4),
+        hence max_engines = 4.  scenes_per_engine = 0: never split."""
         self._init_args = dict(state_dict=state_dict, cfg=cfg, device=device, use_cuda_graph=use_cuda_graph, seed=seed,
                                vocab=vocab, map_state_dict=map_state_dict, map_traj_src=map_traj_src)
         self.scenes_per_engine, self.max_engines = scenes_per_engine, max_engines
@@ -281,9 +282,9 @@ class B200AgentDecoder:
 
     # ---- several engines for one batch ----------------------------------------------------------------------------
     def _split(self, n: int):
-        """Scene positions per engine, or None for a single engine: balanced contiguous groups of at most
+        """Scene positions per engine, or None for a single engine: balanced contiguous groups of about
         `scenes_per_engine` scenes (more per group once `max_engines` engines are in use)."""
-        if self.scenes_per_engine <= 0 or n <= self.scenes_per_engine or self.max_engines <= 1 or self.trace:
+        if self.scenes_per_engine <= 0 or n < 2 * self.scenes_per_engine or self.max_engines <= 1 or self.trace:
             return None
         if self.cfg.disable_insertion:                   # the motion stage alone is throughput-bound at batch: one row space
             return None
