@@ -102,3 +102,27 @@ def test_batch_assembly_equals_per_scene_assembly_with_insertion_records():
                     assert torch.equal(x[k_], v), (call, b, k_)
                 else:
                     assert x[k_] == v, (call, b, k_)
+
+
+def test_engine_group_split_policy():
+    """`B200AgentDecoder._split`: contiguous, balanced groups that cover every scene once; one engine for small batches, for
+    motion-only engines and for traced runs; never more than `max_engines` groups."""
+    from infgen_b200.agent_decoder import B200AgentDecoder
+    d = B200AgentDecoder.__new__(B200AgentDecoder)
+    d.scenes_per_engine, d.max_engines, d.trace = 2, 4, False
+    d.cfg = DecoderConfig(disable_insertion=False)
+    assert d._split(1) is None and d._split(3) is None
+    assert d._split(4) == [[0, 1], [2, 3]]
+    assert [len(g) for g in d._split(8)] == [2, 2, 2, 2]
+    assert [len(g) for g in d._split(19)] == [4, 5, 5, 5]
+    for n in range(4, 70):
+        g = d._split(n)
+        assert 2 <= len(g) <= 4 and sum(g, []) == list(range(n)) and max(map(len, g)) - min(map(len, g)) <= 1
+    d.scenes_per_engine = 7
+    assert d._split(13) is None and [len(g) for g in d._split(19)] == [6, 6, 7]
+    d.scenes_per_engine = 0
+    assert d._split(64) is None
+    d.scenes_per_engine, d.trace = 2, True
+    assert d._split(64) is None
+    d.trace, d.cfg = False, DecoderConfig(disable_insertion=True)
+    assert d._split(64) is None
