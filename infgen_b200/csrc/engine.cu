@@ -941,10 +941,10 @@ static int enqueue_insertion_begin(infgen_engine *e) {
     }
     CKL(); count_launch(e);
     // Every row through the two edge-less stacks of the stage -> the K|V rows later passes attend to: the seed stack
-    // (3 x {occ2sa, pt2sa, a2sa}: K|V of the a2sa layers) on the engine stream, and on the side stream the relative
-    // embeddings of the map -> seed and agent -> seed edges (the seed pose is the ego pose for every pass of the iteration;
-    // rows appended by a pass add their own edge) and the heading stack (motion layers 0..2 without edges: K|V of a2a for
-    // the heading stage of appended rows)
+    // (3 x {occ2sa, pt2sa, a2sa}: K|V of the a2sa layers) on the engine stream; on side streams the relative embeddings of
+    // the map -> seed and agent -> seed edges (the seed pose is the ego pose for every pass of the iteration; rows appended
+    // by a pass add their own edge), the heading stack (motion layers 0..2 without edges: K|V of a2a for the heading stage
+    // of appended rows) and the occupancy node of the first pass
     // The cluster kernel keeps the residual rows in shared memory and (no_store) never writes them back, so both chains
     // read x itself; the row-tile kernels of large batches update their residual stream in global memory and get copies.
     const bool chain_copies = (R + 7) / 8 > MAX_CLUSTERS && e->layer_path != 1;
