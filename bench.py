@@ -452,6 +452,8 @@ def run_ours(args, rank, world, local_rank):
     def measure(dec_cfg, scn, mps, ids, steps, warmup, sampler_rank0=False, e2e=True):
         """value (device-resident) and e2e (public call) of one decoder configuration on one list of scenes."""
         kw = {'scenes_per_engine': int(os.environ['INFGEN_SCENES_PER_ENGINE'])} if 'INFGEN_SCENES_PER_ENGINE' in os.environ else {}
+        if 'INFGEN_MAX_ENGINES' in os.environ:
+            kw['max_engines'] = int(os.environ['INFGEN_MAX_ENGINES'])
         dec = B200AgentDecoder(sd, dec_cfg, device=local_rank, seed=2024, use_cuda_graph=True, **kw)
         # the public call first: it also settles the row capacity (the insertion stage may need capacity reruns)
         for _ in range(2):
